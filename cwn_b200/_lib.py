@@ -1,0 +1,73 @@
+"""ctypes binding of `libcwn_b200.so` (declared in include/cwn_b200.h). There is NO fallback: if the library
+cannot be loaded, every message-passing op raises."""
+import ctypes
+import os
+
+from cwn_b200 import build as _build
+
+_c_f32p = ctypes.c_void_p
+_c_i32p = ctypes.c_void_p
+_c_i64p = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_i32 = ctypes.c_int32
+_f32 = ctypes.c_float
+_vp = ctypes.c_void_p
+
+_SIGNATURES = {
+    'cwn_version': (ctypes.c_char_p, []),
+    'cwn_last_error_string': (ctypes.c_char_p, []),
+    'cwn_launch_count': (ctypes.c_ulonglong, []),
+    'cwn_csr_plan_workspace_bytes': (ctypes.c_size_t, [_i64, _i64]),
+    'cwn_csr_plan_build': (ctypes.c_int, [_c_i64p, _c_i64p, _c_i64p, _i64, _i64, _c_i32p, _c_i32p, _c_i32p,
+                                          _c_i32p, _c_i32p, _vp, ctypes.c_size_t, _vp]),
+    'cwn_csr_gather_reduce_f32': (ctypes.c_int, [_c_f32p, _i64, _c_i32p, _c_i32p, _i64, _i32, _c_f32p, _i64,
+                                                 _c_f32p, _c_f32p, _i64, _i32, _vp]),
+    'cwn_gather_rows_f32': (ctypes.c_int, [_c_f32p, _i64, _c_i64p, _i64, _i32, _f32, _c_f32p, _i64, _vp]),
+    'cwn_csr_cob_fwd_f32': (ctypes.c_int, [_c_f32p, _i64, _c_f32p, _i64, _c_i32p, _c_i32p, _c_i32p, _i64, _i32,
+                                           _i32, _c_f32p, _i64, _c_f32p, _c_f32p, _i64, _vp]),
+    'cwn_csr_cob_bwd_f32': (ctypes.c_int, [_c_f32p, _i64, _c_f32p, _i64, _c_f32p, _i64, _c_i32p, _c_i32p,
+                                           _c_i32p, _i64, _i32, _i32, _c_f32p, _i64, _vp]),
+    'cwn_check_index_range': (ctypes.c_int, [_c_i64p, _i64, _i64, _c_i32p, _vp]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    """Every entry point include/cwn_b200.h declares."""
+    return sorted(_SIGNATURES)
+
+
+def load():
+    """Load (building in-tree first if the `.so` is absent or stale and nvcc is present). Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    try:
+        path = _build.build_library()
+    except RuntimeError:
+        if not os.path.exists(path):
+            raise
+    if not os.path.exists(path):
+        raise RuntimeError(f'cwn_b200: CUDA extension {path} is missing; there is no CPU or PyTorch fallback')
+    lib = ctypes.CDLL(path)
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc, what=''):
+    if rc == 0:
+        return
+    msg = load().cwn_last_error_string().decode()
+    if rc < 0:
+        raise ValueError(f'cwn_b200 {what}: argument error {rc}: {msg}')
+    raise RuntimeError(f'cwn_b200 {what}: CUDA error {rc}: {msg}')
+
+
+def launch_count():
+    return int(load().cwn_launch_count())

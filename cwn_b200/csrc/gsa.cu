@@ -1,0 +1,438 @@
+// Fused gather -> message -> reduce kernels over CSR plans (one destination row per thread group, no atomics).
+//
+// Layout: a feature row of F fp32 is covered by LPR lanes (power of two <= 32) that each own VPL vectors of
+// W floats (W = 4: 128-bit loads when F, every ld and every base pointer allow it; W = 1 otherwise, e.g. the
+// F = 1 fixtures of the reference tests). A 256-thread CTA therefore owns 256/LPR destination rows; the grid is
+// a multiple of the 148 SMs and strides over the rows. Inside a row the messages are visited in plan order
+// (ascending original message id), four gathers in flight at a time, and accumulated sequentially, which makes
+// the result independent of the launch geometry and bit-identical to a sequential CPU scatter_add_.
+//
+// Replaces (reference): Tensor.index_select + torch_scatter.scatter, mp/cell_mp.py:195-198 + :423-479;
+// the per-message MLP of mp/layers.py:210-211,290-293 (in its split-weight form, see include/cwn_b200.h).
+#include "common.cuh"
+
+namespace cwn {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;  // gathers in flight per row
+
+template <typename V> struct VecOps;
+template <> struct VecOps<float4> {
+  static constexpr int W = 4;
+  static __device__ __forceinline__ float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  static __device__ __forceinline__ float4 load(const float* p) { return ldg_f4(p); }
+  static __device__ __forceinline__ void store(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+  template <class Fn> static __device__ __forceinline__ float4 map2(float4 a, float4 b, Fn f) {
+    return make_float4(f(a.x, b.x), f(a.y, b.y), f(a.z, b.z), f(a.w, b.w));
+  }
+  template <class Fn> static __device__ __forceinline__ float4 map3(float4 a, float4 b, float4 c, Fn f) {
+    return make_float4(f(a.x, b.x, c.x), f(a.y, b.y, c.y), f(a.z, b.z, c.z), f(a.w, b.w, c.w));
+  }
+};
+template <> struct VecOps<float> {
+  static constexpr int W = 1;
+  static __device__ __forceinline__ float zero() { return 0.f; }
+  static __device__ __forceinline__ float load(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ void store(float* p, float v) { *p = v; }
+  template <class Fn> static __device__ __forceinline__ float map2(float a, float b, Fn f) { return f(a, b); }
+  template <class Fn> static __device__ __forceinline__ float map3(float a, float b, float c, Fn f) {
+    return f(a, b, c);
+  }
+};
+
+struct AddRn { __device__ __forceinline__ float operator()(float a, float b) const { return __fadd_rn(a, b); } };
+struct MaxOp { __device__ __forceinline__ float operator()(float a, float b) const { return fmaxf(a, b); } };
+
+// out[r] = (1+eps) * x_res[r] + REDUCE_i x_src[idx ? idx[i] : i]
+template <typename V, int LPR, int VPL, int REDUCE>
+__global__ void __launch_bounds__(kThreads)
+csr_gather_reduce_kernel(const float* __restrict__ x_src, int64_t ld_src, const int32_t* __restrict__ rowptr,
+                         const int32_t* __restrict__ idx, int64_t n_rows, int FV /* F / W */,
+                         const float* __restrict__ x_res, int64_t ld_res, const float* __restrict__ eps,
+                         float* __restrict__ out, int64_t ld_out) {
+  using O = VecOps<V>;
+  constexpr int RPB = kThreads / LPR;
+  const int lane = threadIdx.x % LPR;
+  const int sub = threadIdx.x / LPR;
+  const float scale = x_res ? __fadd_rn(1.f, eps ? __ldg(eps) : 0.f) : 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * RPB + sub; r < n_rows; r += (int64_t)gridDim.x * RPB) {
+    const int beg = __ldg(rowptr + r), end = __ldg(rowptr + r + 1);
+    for (int c0 = 0; c0 < FV; c0 += LPR * VPL) {  // one trip unless F > 4*32*VPL
+      V acc[VPL];
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) acc[k] = O::zero();
+      for (int i = beg; i < end; i += kUnroll) {
+        int64_t s[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) s[u] = (i + u < end) ? (idx ? (int64_t)__ldg(idx + i + u) : (int64_t)(i + u)) : -1;
+        V v[kUnroll][VPL];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+          for (int k = 0; k < VPL; ++k) {
+            const int c = c0 + lane + k * LPR;
+            if (s[u] >= 0 && c < FV) v[u][k] = O::load(x_src + s[u] * ld_src + (int64_t)c * O::W);
+          }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+          for (int k = 0; k < VPL; ++k) {
+            const int c = c0 + lane + k * LPR;
+            if (s[u] >= 0 && c < FV) {
+              if (REDUCE == CWN_REDUCE_MAX) acc[k] = (i + u == beg) ? v[u][k] : O::map2(acc[k], v[u][k], MaxOp());
+              else acc[k] = O::map2(acc[k], v[u][k], AddRn());
+            }
+          }
+      }
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int c = c0 + lane + k * LPR;
+        if (c >= FV) continue;
+        V a = acc[k];
+        if (REDUCE == CWN_REDUCE_MEAN) {
+          const float cnt = (float)max(end - beg, 1);
+          a = O::map2(a, a, [cnt](float x, float) { return __fdiv_rn(x, cnt); });
+        }
+        if (x_res) {  // GIN residual added after the aggregation, as mp/layers.py:191-192 does
+          V xr = O::load(x_res + r * ld_res + (int64_t)c * O::W);
+          a = O::map2(a, xr, [scale](float s_, float x) { return __fadd_rn(s_, __fmul_rn(scale, x)); });
+        }
+        O::store(out + r * ld_out + (int64_t)c * O::W, a);
+      }
+    }
+  }
+}
+
+// out[r] = (1+eps) * x_res[r] + SUM_i act(P[src[i]] + Q[cob[i]])
+template <typename V, int LPR, int VPL, int ACT>
+__global__ void __launch_bounds__(kThreads)
+csr_cob_fwd_kernel(const float* __restrict__ P, int64_t ld_p, const float* __restrict__ Q, int64_t ld_q,
+                   const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src,
+                   const int32_t* __restrict__ cob, int64_t n_rows, int FV, const float* __restrict__ x_res,
+                   int64_t ld_res, const float* __restrict__ eps, float* __restrict__ out, int64_t ld_out) {
+  using O = VecOps<V>;
+  constexpr int RPB = kThreads / LPR;
+  constexpr int U = 2;  // two operands per message: 2*U gathers in flight
+  const int lane = threadIdx.x % LPR;
+  const int sub = threadIdx.x / LPR;
+  const float scale = x_res ? __fadd_rn(1.f, eps ? __ldg(eps) : 0.f) : 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * RPB + sub; r < n_rows; r += (int64_t)gridDim.x * RPB) {
+    const int beg = __ldg(rowptr + r), end = __ldg(rowptr + r + 1);
+    for (int c0 = 0; c0 < FV; c0 += LPR * VPL) {
+      V acc[VPL];
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) acc[k] = O::zero();
+      for (int i = beg; i < end; i += U) {
+        int64_t s[U], q[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const bool ok = i + u < end;
+          s[u] = ok ? (int64_t)__ldg(src + i + u) : -1;
+          q[u] = ok ? (int64_t)__ldg(cob + i + u) : -1;
+        }
+        V vp[U][VPL], vq[U][VPL];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int k = 0; k < VPL; ++k) {
+            const int c = c0 + lane + k * LPR;
+            if (s[u] >= 0 && c < FV) {
+              vp[u][k] = O::load(P + s[u] * ld_p + (int64_t)c * O::W);
+              vq[u][k] = O::load(Q + q[u] * ld_q + (int64_t)c * O::W);
+            }
+          }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int k = 0; k < VPL; ++k) {
+            const int c = c0 + lane + k * LPR;
+            if (s[u] >= 0 && c < FV)
+              acc[k] = O::map3(acc[k], vp[u][k], vq[u][k], [](float a, float p, float q_) {
+                return __fadd_rn(a, act_fwd<ACT>(__fadd_rn(p, q_)));
+              });
+          }
+      }
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int c = c0 + lane + k * LPR;
+        if (c >= FV) continue;
+        V a = acc[k];
+        if (x_res) {
+          V xr = O::load(x_res + r * ld_res + (int64_t)c * O::W);
+          a = O::map2(a, xr, [scale](float s_, float x) { return __fadd_rn(s_, __fmul_rn(scale, x)); });
+        }
+        O::store(out + r * ld_out + (int64_t)c * O::W, a);
+      }
+    }
+  }
+}
+
+// gA[r] = SUM_i G[dst[i]] * act'(A[r] + B[oth[i]])
+template <typename V, int LPR, int VPL, int ACT>
+__global__ void __launch_bounds__(kThreads)
+csr_cob_bwd_kernel(const float* __restrict__ G, int64_t ld_g, const float* __restrict__ A, int64_t ld_a,
+                   const float* __restrict__ B, int64_t ld_b, const int32_t* __restrict__ rowptr,
+                   const int32_t* __restrict__ dst, const int32_t* __restrict__ oth, int64_t n_rows, int FV,
+                   float* __restrict__ gA, int64_t ld_ga) {
+  using O = VecOps<V>;
+  constexpr int RPB = kThreads / LPR;
+  constexpr int U = 2;
+  const int lane = threadIdx.x % LPR;
+  const int sub = threadIdx.x / LPR;
+  for (int64_t r = (int64_t)blockIdx.x * RPB + sub; r < n_rows; r += (int64_t)gridDim.x * RPB) {
+    const int beg = __ldg(rowptr + r), end = __ldg(rowptr + r + 1);
+    for (int c0 = 0; c0 < FV; c0 += LPR * VPL) {
+      V acc[VPL], a[VPL];
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int c = c0 + lane + k * LPR;
+        acc[k] = O::zero();
+        a[k] = (c < FV && beg < end) ? O::load(A + r * ld_a + (int64_t)c * O::W) : O::zero();
+      }
+      for (int i = beg; i < end; i += U) {
+        int64_t t[U], o[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const bool ok = i + u < end;
+          t[u] = ok ? (int64_t)__ldg(dst + i + u) : -1;
+          o[u] = ok ? (int64_t)__ldg(oth + i + u) : -1;
+        }
+        V vg[U][VPL], vb[U][VPL];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int k = 0; k < VPL; ++k) {
+            const int c = c0 + lane + k * LPR;
+            if (t[u] >= 0 && c < FV) {
+              vg[u][k] = O::load(G + t[u] * ld_g + (int64_t)c * O::W);
+              vb[u][k] = O::load(B + o[u] * ld_b + (int64_t)c * O::W);
+            }
+          }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int k = 0; k < VPL; ++k) {
+            const int c = c0 + lane + k * LPR;
+            if (t[u] >= 0 && c < FV) {
+              V d = O::map2(a[k], vb[u][k], [](float x, float y) { return act_bwd<ACT>(__fadd_rn(x, y)); });
+              acc[k] = O::map3(acc[k], vg[u][k], d, [](float s_, float g, float d_) {
+                return __fadd_rn(s_, __fmul_rn(g, d_));
+              });
+            }
+          }
+      }
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int c = c0 + lane + k * LPR;
+        if (c < FV) O::store(gA + r * ld_ga + (int64_t)c * O::W, acc[k]);
+      }
+    }
+  }
+}
+
+// out[e] = scale * x[idx[e]]  (int64 API indices; one message row per thread group)
+template <typename V, int LPR>
+__global__ void __launch_bounds__(kThreads)
+gather_rows_kernel(const float* __restrict__ x, int64_t ld_x, const int64_t* __restrict__ idx, int64_t E, int FV,
+                   float scale, float* __restrict__ out, int64_t ld_out) {
+  using O = VecOps<V>;
+  constexpr int RPB = kThreads / LPR;
+  const int lane = threadIdx.x % LPR;
+  const int sub = threadIdx.x / LPR;
+  for (int64_t e = (int64_t)blockIdx.x * RPB + sub; e < E; e += (int64_t)gridDim.x * RPB) {
+    const int64_t s = __ldg(idx + e);
+    for (int c = lane; c < FV; c += LPR) {
+      V v = O::load(x + s * ld_x + (int64_t)c * O::W);
+      if (scale != 1.f) v = O::map2(v, v, [scale](float a, float) { return __fmul_rn(scale, a); });
+      O::store(out + e * ld_out + (int64_t)c * O::W, v);
+    }
+  }
+}
+
+__global__ void check_index_range_kernel(const int64_t* __restrict__ idx, int64_t E, int64_t n, int32_t* flags) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = idx[e];
+    if (v < 0 || v >= n) atomicOr(flags, 2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dispatch
+struct Geometry {
+  bool vec;  // 128-bit path
+  int fv;    // F / W
+  int lpr;   // lanes per row
+  int vpl;   // vectors per lane
+};
+
+static Geometry geometry(int F, bool can_vec) {
+  Geometry g;
+  g.vec = can_vec && (F % 4 == 0);
+  g.fv = g.vec ? F / 4 : F;
+  int lpr = 1;
+  while (lpr < g.fv && lpr < 32) lpr <<= 1;
+  g.lpr = lpr;
+  g.vpl = (g.fv > 32) ? 2 : 1;
+  return g;
+}
+
+static int grid_for(int64_t rows, int lpr) {
+  const int64_t rpb = kThreads / lpr;
+  int64_t need = (rows + rpb - 1) / rpb;
+  const int64_t cap = (int64_t)kNumSMs * 16;  // 8 resident CTAs/SM x 2 waves, multiple of the SM count
+  if (need > cap) need = cap;
+  if (need < 1) need = 1;
+  return (int)need;
+}
+
+#define CWN_DISPATCH_LPR(LPRV, ...)                    \
+  switch (LPRV) {                                      \
+    case 1: { constexpr int LPR = 1; __VA_ARGS__; } break;   \
+    case 2: { constexpr int LPR = 2; __VA_ARGS__; } break;   \
+    case 4: { constexpr int LPR = 4; __VA_ARGS__; } break;   \
+    case 8: { constexpr int LPR = 8; __VA_ARGS__; } break;   \
+    case 16: { constexpr int LPR = 16; __VA_ARGS__; } break; \
+    default: { constexpr int LPR = 32; __VA_ARGS__; } break; \
+  }
+
+#define CWN_DISPATCH_ACT(ACTV, ...)                                            \
+  switch (ACTV) {                                                              \
+    case CWN_ACT_ID: { constexpr int ACT = CWN_ACT_ID; __VA_ARGS__; } break;       \
+    case CWN_ACT_RELU: { constexpr int ACT = CWN_ACT_RELU; __VA_ARGS__; } break;   \
+    case CWN_ACT_ELU: { constexpr int ACT = CWN_ACT_ELU; __VA_ARGS__; } break;     \
+    case CWN_ACT_SIGMOID: { constexpr int ACT = CWN_ACT_SIGMOID; __VA_ARGS__; } break; \
+    default: { constexpr int ACT = CWN_ACT_TANH; __VA_ARGS__; } break;             \
+  }
+
+static int check_matrix(const float* p, int64_t ld, int F, const char* name) {
+  if (!p) return fail(CWN_E_NULL, name);
+  if (ld < F) return fail(CWN_E_SHAPE, "leading dimension smaller than F");
+  if (!aligned4(p)) return fail(CWN_E_ALIGN, name);
+  return CWN_OK;
+}
+
+static bool vec_ok(const float* p, int64_t ld) { return p == nullptr || (aligned16(p) && ld % 4 == 0); }
+
+}  // namespace cwn
+
+using namespace cwn;
+
+extern "C" int cwn_csr_gather_reduce_f32(const float* x_src, int64_t ld_src, const int32_t* rowptr,
+                                         const int32_t* idx, int64_t n_rows, int32_t F, const float* x_res,
+                                         int64_t ld_res, const float* eps, float* out, int64_t ld_out,
+                                         int32_t reduce, cwn_stream_t stream) {
+  if (n_rows < 0 || F <= 0 || n_rows > INT32_MAX) return fail(CWN_E_SHAPE, "cwn_csr_gather_reduce_f32: bad n_rows/F");
+  if (reduce < CWN_REDUCE_ADD || reduce > CWN_REDUCE_MAX) return fail(CWN_E_ENUM, "unknown reduce");
+  if (x_res && reduce != CWN_REDUCE_ADD) return fail(CWN_E_ENUM, "x_res requires CWN_REDUCE_ADD");
+  if (n_rows == 0) return CWN_OK;
+  if (!rowptr) return fail(CWN_E_NULL, "rowptr");
+  int rc;
+  if ((rc = check_matrix(out, ld_out, F, "out"))) return rc;
+  // x_src may be NULL only if there are no messages at all; the kernel never dereferences it then
+  if (x_src && (rc = check_matrix(x_src, ld_src, F, "x_src"))) return rc;
+  if (x_res && (rc = check_matrix(x_res, ld_res, F, "x_res"))) return rc;
+  const Geometry g = geometry(F, vec_ok(x_src, ld_src) && vec_ok(x_res, ld_res) && vec_ok(out, ld_out));
+  const int grid = grid_for(n_rows, g.lpr);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(VT, VPLV, RED)                                                                                   \
+  csr_gather_reduce_kernel<VT, LPR, VPLV, RED><<<grid, kThreads, 0, st>>>(x_src, ld_src, rowptr, idx, n_rows, g.fv, \
+                                                                           x_res, ld_res, eps, out, ld_out)
+#define BY_REDUCE(VT, VPLV)                                              \
+  if (reduce == CWN_REDUCE_ADD) LAUNCH(VT, VPLV, CWN_REDUCE_ADD);        \
+  else if (reduce == CWN_REDUCE_MEAN) LAUNCH(VT, VPLV, CWN_REDUCE_MEAN); \
+  else LAUNCH(VT, VPLV, CWN_REDUCE_MAX)
+  if (g.vec) {
+    if (g.vpl == 1) { CWN_DISPATCH_LPR(g.lpr, BY_REDUCE(float4, 1)) } else { constexpr int LPR = 32; BY_REDUCE(float4, 2); }
+  } else {
+    if (g.vpl == 1) { CWN_DISPATCH_LPR(g.lpr, BY_REDUCE(float, 1)) } else { constexpr int LPR = 32; BY_REDUCE(float, 2); }
+  }
+#undef BY_REDUCE
+#undef LAUNCH
+  return launched("cwn_csr_gather_reduce_f32");
+}
+
+extern "C" int cwn_gather_rows_f32(const float* x, int64_t ld_x, const int64_t* idx, int64_t E, int32_t F,
+                                   float scale, float* out, int64_t ld_out, cwn_stream_t stream) {
+  if (E < 0 || F <= 0) return fail(CWN_E_SHAPE, "cwn_gather_rows_f32: bad E/F");
+  if (E == 0) return CWN_OK;
+  if (!idx) return fail(CWN_E_NULL, "idx");
+  int rc;
+  if ((rc = check_matrix(x, ld_x, F, "x"))) return rc;
+  if ((rc = check_matrix(out, ld_out, F, "out"))) return rc;
+  const Geometry g = geometry(F, vec_ok(x, ld_x) && vec_ok(out, ld_out));
+  const int grid = grid_for(E, g.lpr);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g.vec) {
+    CWN_DISPATCH_LPR(g.lpr, gather_rows_kernel<float4, LPR><<<grid, kThreads, 0, st>>>(x, ld_x, idx, E, g.fv, scale, out, ld_out))
+  } else {
+    CWN_DISPATCH_LPR(g.lpr, gather_rows_kernel<float, LPR><<<grid, kThreads, 0, st>>>(x, ld_x, idx, E, g.fv, scale, out, ld_out))
+  }
+  return launched("cwn_gather_rows_f32");
+}
+
+extern "C" int cwn_csr_cob_fwd_f32(const float* P, int64_t ld_p, const float* Q, int64_t ld_q,
+                                   const int32_t* rowptr, const int32_t* src, const int32_t* cob, int64_t n_rows,
+                                   int32_t F, int32_t act, const float* x_res, int64_t ld_res, const float* eps,
+                                   float* out, int64_t ld_out, cwn_stream_t stream) {
+  if (n_rows < 0 || F <= 0 || n_rows > INT32_MAX) return fail(CWN_E_SHAPE, "cwn_csr_cob_fwd_f32: bad n_rows/F");
+  if (act < CWN_ACT_ID || act > CWN_ACT_TANH) return fail(CWN_E_ENUM, "unknown activation");
+  if (n_rows == 0) return CWN_OK;
+  if (!rowptr || !src || !cob) return fail(CWN_E_NULL, "plan");
+  int rc;
+  if ((rc = check_matrix(P, ld_p, F, "P"))) return rc;
+  if ((rc = check_matrix(Q, ld_q, F, "Q"))) return rc;
+  if ((rc = check_matrix(out, ld_out, F, "out"))) return rc;
+  if (x_res && (rc = check_matrix(x_res, ld_res, F, "x_res"))) return rc;
+  const Geometry g = geometry(F, vec_ok(P, ld_p) && vec_ok(Q, ld_q) && vec_ok(x_res, ld_res) && vec_ok(out, ld_out));
+  const int grid = grid_for(n_rows, g.lpr);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(VT, VPLV)                                                                                           \
+  CWN_DISPATCH_ACT(act, csr_cob_fwd_kernel<VT, LPR, VPLV, ACT><<<grid, kThreads, 0, st>>>(                           \
+                            P, ld_p, Q, ld_q, rowptr, src, cob, n_rows, g.fv, x_res, ld_res, eps, out, ld_out))
+  if (g.vec) {
+    if (g.vpl == 1) { CWN_DISPATCH_LPR(g.lpr, LAUNCH(float4, 1)) } else { constexpr int LPR = 32; LAUNCH(float4, 2) }
+  } else {
+    if (g.vpl == 1) { CWN_DISPATCH_LPR(g.lpr, LAUNCH(float, 1)) } else { constexpr int LPR = 32; LAUNCH(float, 2) }
+  }
+#undef LAUNCH
+  return launched("cwn_csr_cob_fwd_f32");
+}
+
+extern "C" int cwn_csr_cob_bwd_f32(const float* G, int64_t ld_g, const float* A, int64_t ld_a, const float* B,
+                                   int64_t ld_b, const int32_t* rowptr, const int32_t* dst, const int32_t* oth,
+                                   int64_t n_rows, int32_t F, int32_t act, float* gA, int64_t ld_ga,
+                                   cwn_stream_t stream) {
+  if (n_rows < 0 || F <= 0 || n_rows > INT32_MAX) return fail(CWN_E_SHAPE, "cwn_csr_cob_bwd_f32: bad n_rows/F");
+  if (act < CWN_ACT_ID || act > CWN_ACT_TANH) return fail(CWN_E_ENUM, "unknown activation");
+  if (n_rows == 0) return CWN_OK;
+  if (!rowptr || !dst || !oth) return fail(CWN_E_NULL, "plan");
+  int rc;
+  if ((rc = check_matrix(A, ld_a, F, "A"))) return rc;
+  if ((rc = check_matrix(gA, ld_ga, F, "gA"))) return rc;
+  // G / B may be NULL only when there are no messages
+  if (G && (rc = check_matrix(G, ld_g, F, "G"))) return rc;
+  if (B && (rc = check_matrix(B, ld_b, F, "B"))) return rc;
+  const Geometry g = geometry(F, vec_ok(G, ld_g) && vec_ok(A, ld_a) && vec_ok(B, ld_b) && vec_ok(gA, ld_ga));
+  const int grid = grid_for(n_rows, g.lpr);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(VT, VPLV)                                                                  \
+  CWN_DISPATCH_ACT(act, csr_cob_bwd_kernel<VT, LPR, VPLV, ACT><<<grid, kThreads, 0, st>>>(  \
+                            G, ld_g, A, ld_a, B, ld_b, rowptr, dst, oth, n_rows, g.fv, gA, ld_ga))
+  if (g.vec) {
+    if (g.vpl == 1) { CWN_DISPATCH_LPR(g.lpr, LAUNCH(float4, 1)) } else { constexpr int LPR = 32; LAUNCH(float4, 2) }
+  } else {
+    if (g.vpl == 1) { CWN_DISPATCH_LPR(g.lpr, LAUNCH(float, 1)) } else { constexpr int LPR = 32; LAUNCH(float, 2) }
+  }
+#undef LAUNCH
+  return launched("cwn_csr_cob_bwd_f32");
+}
+
+extern "C" int cwn_check_index_range(const int64_t* idx, int64_t E, int64_t n, int32_t* flags,
+                                     cwn_stream_t stream) {
+  if (E < 0) return fail(CWN_E_SHAPE, "cwn_check_index_range: bad E");
+  if (E == 0) return CWN_OK;
+  if (!idx || !flags) return fail(CWN_E_NULL, "idx/flags");
+  int64_t need = (E + 255) / 256;
+  if (need > kNumSMs * 8) need = kNumSMs * 8;
+  check_index_range_kernel<<<(int)need, 256, 0, (cudaStream_t)stream>>>(idx, E, n, flags);
+  return launched("cwn_check_index_range");
+}

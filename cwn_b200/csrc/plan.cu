@@ -1,0 +1,126 @@
+// CSR plan builder: stable grouping of the messages of one adjacency by one of their columns.
+//
+// The reference scatters with unsorted destinations and atomics (torch_scatter.scatter -> scatter_add_,
+// mp/cell_mp.py:439-440) every layer, forward and backward. Index tensors are constant across layers and between
+// forward and backward, so the B200 design sorts ONCE per batch and every later pass is an
+// atomic-free, deterministic segmented reduction.
+//
+// Pipeline (all stream-ordered, no host sync, caller-provided workspace):
+//   1. narrow_keys   : int64 key -> int32 key (out-of-range keys go to the dummy row n_rows and raise flag bit 0),
+//                      value = message id
+//   2. cub::DeviceRadixSort::SortPairs over ceil(log2(n_rows+1)) bits (LSD radix sort => stable)
+//   3. finish_plan   : rowptr[r] = lower_bound(sorted keys, r); payload columns permuted + narrowed to int32
+#include <cub/device/device_radix_sort.cuh>
+#include "common.cuh"
+
+namespace cwn {
+
+thread_local char g_err[256] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+__global__ void narrow_keys_kernel(const int64_t* __restrict__ key, int64_t E, int64_t n_rows,
+                                   int32_t* __restrict__ key32, int32_t* __restrict__ val, int32_t* flags) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t k = key[e];
+    if (k < 0 || k >= n_rows) {
+      k = n_rows;
+      if (flags) atomicOr(flags, 1);
+    }
+    key32[e] = (int32_t)k;
+    val[e] = (int32_t)e;
+  }
+}
+
+__global__ void finish_plan_kernel(const int32_t* __restrict__ key_sorted, const int32_t* __restrict__ perm,
+                                   int64_t E, int64_t n_rows, const int64_t* __restrict__ pay0,
+                                   const int64_t* __restrict__ pay1, int32_t* __restrict__ rowptr,
+                                   int32_t* __restrict__ pay0_sorted, int32_t* __restrict__ pay1_sorted) {
+  const int64_t total = (E > n_rows + 1) ? E : n_rows + 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i <= n_rows) {  // first position whose key is >= i
+      int64_t lo = 0, hi = E;
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (key_sorted[mid] < (int32_t)i) lo = mid + 1; else hi = mid;
+      }
+      rowptr[i] = (int32_t)lo;
+    }
+    if (i < E) {
+      const int32_t e = perm[i];
+      if (pay0) pay0_sorted[i] = (int32_t)pay0[e];
+      if (pay1) pay1_sorted[i] = (int32_t)pay1[e];
+    }
+  }
+}
+
+__global__ void fill_zero_kernel(int32_t* p, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0;
+}
+
+static int key_bits(int64_t n_rows) {  // keys take values 0..n_rows (n_rows = dummy row)
+  int bits = 1;
+  while ((int64_t(1) << bits) <= n_rows) ++bits;
+  return bits;
+}
+
+static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+
+static size_t cub_temp_bytes(int64_t E, int64_t n_rows) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const int32_t*)nullptr, (int32_t*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)E, 0, key_bits(n_rows));
+  return bytes;
+}
+
+static int blocks_for(int64_t n) {
+  int64_t b = (n + 255) / 256;
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace cwn
+
+using namespace cwn;
+
+extern "C" const char* cwn_version(void) { return "cwn_b200 0.1 (sm_100a)"; }
+extern "C" const char* cwn_last_error_string(void) { return g_err; }
+extern "C" unsigned long long cwn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" size_t cwn_csr_plan_workspace_bytes(int64_t E, int64_t n_rows) {
+  if (E <= 0 || n_rows < 0 || E > INT32_MAX) return 256;
+  return 3 * align_up((size_t)E * sizeof(int32_t)) + align_up(cub_temp_bytes(E, n_rows)) + 256;
+}
+
+extern "C" int cwn_csr_plan_build(const int64_t* key, const int64_t* pay0, const int64_t* pay1, int64_t E,
+                                  int64_t n_rows, int32_t* rowptr, int32_t* perm, int32_t* pay0_sorted,
+                                  int32_t* pay1_sorted, int32_t* flags, void* workspace, size_t workspace_bytes,
+                                  cwn_stream_t stream) {
+  if (E < 0 || n_rows < 0 || E > INT32_MAX || n_rows >= INT32_MAX) return fail(CWN_E_SHAPE, "cwn_csr_plan_build: bad E/n_rows");
+  if (!rowptr) return fail(CWN_E_NULL, "rowptr");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (E == 0) {
+    fill_zero_kernel<<<blocks_for(n_rows + 1), 256, 0, st>>>(rowptr, n_rows + 1);
+    return launched("cwn_csr_plan_build(empty)");
+  }
+  if (!key || !perm) return fail(CWN_E_NULL, "key/perm");
+  if ((pay0 && !pay0_sorted) || (pay1 && !pay1_sorted)) return fail(CWN_E_NULL, "payload output");
+  if (!workspace || workspace_bytes < cwn_csr_plan_workspace_bytes(E, n_rows)) return fail(CWN_E_WORKSPACE, "workspace too small");
+  char* ws = (char*)workspace;
+  const size_t col = align_up((size_t)E * sizeof(int32_t));
+  int32_t* key32 = (int32_t*)ws;
+  int32_t* val = (int32_t*)(ws + col);
+  int32_t* key_sorted = (int32_t*)(ws + 2 * col);
+  void* cub_temp = ws + 3 * col;
+  size_t cub_bytes = workspace_bytes - 3 * col;
+
+  narrow_keys_kernel<<<blocks_for(E), 256, 0, st>>>(key, E, n_rows, key32, val, flags);
+  int rc = launched("narrow_keys");
+  if (rc) return rc;
+  cudaError_t ce = cub::DeviceRadixSort::SortPairs(cub_temp, cub_bytes, key32, key_sorted, val, perm, (int)E, 0,
+                                                   key_bits(n_rows), st);
+  g_launches.fetch_add(1 + (key_bits(n_rows) + 7) / 8, std::memory_order_relaxed);  // histogram + onesweep passes
+  if ((rc = cuda_status(ce, "cub::DeviceRadixSort::SortPairs"))) return rc;
+  finish_plan_kernel<<<blocks_for(E > n_rows + 1 ? E : n_rows + 1), 256, 0, st>>>(
+      key_sorted, perm, E, n_rows, pay0, pay1, rowptr, pay0_sorted, pay1_sorted);
+  return launched("finish_plan");
+}

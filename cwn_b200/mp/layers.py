@@ -1,0 +1,411 @@
+"""Cochain convolution layers on top of `CochainMessagePassing` (reference `mp/layers.py`).
+
+Module structure, constructor signatures and parameter names follow the reference so that a reference
+state_dict loads unchanged (`mp_levels.{d}.update_up_nn.0.weight`, `...msg_up_nn.1.weight`, `eps1`, ...).
+The compute differs: `SparseCINCochainConv.forward` recognises the nets `SparseCINConv` builds by default and then
+issues at most TWO fused kernels per cochain (upper pass with or without coboundary MLP, boundary pass), each
+with the GIN residual `(1 + eps) * x` folded in; anything it does not recognise (user-supplied callables,
+subclasses overriding a hook) goes through the generic hook protocol of `CochainMessagePassing.propagate`.
+"""
+from abc import ABC, abstractmethod
+from typing import Callable, Optional
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+from torch.nn import Linear, Sequential, BatchNorm1d as BN
+
+from cwn_b200 import ops
+from cwn_b200.mp.cell_mp import CochainMessagePassing, CochainMessagePassingParams
+from cwn_b200.mp.nn import activation_name, reset
+from cwn_b200.mp.params import LazyRows, as_tensor
+
+
+# ----------------------------------------------------------------------------------------------- test vehicles
+class DummyCochainMessagePassing(CochainMessagePassing):
+    """Parameter-free layer used by the known-answer tests: message = neighbour + shared (co)boundary features
+    (reference `mp/layers.py:14-40`)."""
+
+    def __init__(self, up_msg_size, down_msg_size, boundary_msg_size=None, use_boundary_msg=False,
+                 use_down_msg=True):
+        super(DummyCochainMessagePassing, self).__init__(up_msg_size, down_msg_size,
+                                                         boundary_msg_size=boundary_msg_size,
+                                                         use_boundary_msg=use_boundary_msg,
+                                                         use_down_msg=use_down_msg)
+
+    def message_up(self, up_x_j: Tensor, up_attr: Tensor) -> Tensor:
+        return up_x_j + up_attr
+
+    def message_down(self, down_x_j: Tensor, down_attr: Tensor) -> Tensor:
+        return down_x_j + down_attr
+
+    def forward(self, cochain: CochainMessagePassingParams):
+        up_out, down_out, boundary_out = self.propagate(cochain.up_index, cochain.down_index,
+                                                        cochain.boundary_index, x=cochain.x,
+                                                        up_attr=cochain.kwargs['up_attr'],
+                                                        down_attr=cochain.kwargs['down_attr'],
+                                                        boundary_attr=cochain.kwargs['boundary_attr'])
+        return cochain.x + up_out + down_out + boundary_out
+
+
+class _PerDimension(torch.nn.Module):
+    """Runs `mp_levels[d]` on the parameters of dimension d (shared `forward` of the *Conv containers)."""
+
+    def forward(self, *cochain_params: CochainMessagePassingParams, start_to_process=0):
+        assert len(cochain_params) <= self.max_dim + 1
+        out = []
+        for dim in range(len(cochain_params)):
+            if dim < start_to_process:
+                out.append(cochain_params[dim].x)
+            else:
+                out.append(self.mp_levels[dim].forward(cochain_params[dim]))
+        return out
+
+
+class DummyCellularMessagePassing(_PerDimension):
+    def __init__(self, input_dim=1, max_dim: int = 2, use_boundary_msg=False, use_down_msg=True):
+        super(DummyCellularMessagePassing, self).__init__()
+        self.max_dim = max_dim
+        self.mp_levels = torch.nn.ModuleList(
+            DummyCochainMessagePassing(input_dim, input_dim, boundary_msg_size=input_dim,
+                                       use_boundary_msg=use_boundary_msg, use_down_msg=use_down_msg)
+            for _ in range(max_dim + 1))
+
+
+# ----------------------------------------------------------------------------------------------- dense CIN
+class CINCochainConv(CochainMessagePassing):
+    """Dense CIN cochain layer: upper and lower messages through an MLP over `cat[x_j, attr]`, one update MLP
+    (reference `mp/layers.py:62-103`). The message nets are arbitrary callables (and contain BatchNorm over the
+    message population in `CIN0`), so the passes run through the generic gather -> hook -> reduce kernels."""
+
+    def __init__(self, up_msg_size: int, down_msg_size: int, msg_up_nn: Callable, msg_down_nn: Callable,
+                 update_nn: Callable, eps: float = 0., train_eps: bool = False):
+        super(CINCochainConv, self).__init__(up_msg_size, down_msg_size, use_boundary_msg=False)
+        self.msg_up_nn = msg_up_nn
+        self.msg_down_nn = msg_down_nn
+        self.update_nn = update_nn
+        self.initial_eps = eps
+        if train_eps:
+            self.eps = torch.nn.Parameter(torch.Tensor([eps]))
+        else:
+            self.register_buffer('eps', torch.Tensor([eps]))
+        self.reset_parameters()
+
+    def forward(self, cochain: CochainMessagePassingParams):
+        out_up, out_down, _ = self.propagate(cochain.up_index, cochain.down_index, None, x=cochain.x,
+                                             up_attr=cochain.kwargs['up_attr'],
+                                             down_attr=cochain.kwargs['down_attr'])
+        out_up = out_up + (1 + self.eps) * cochain.x
+        out_down = out_down + (1 + self.eps) * cochain.x
+        return self.update_nn(out_up + out_down)
+
+    def reset_parameters(self):
+        reset(self.msg_up_nn)
+        reset(self.msg_down_nn)
+        reset(self.update_nn)
+        self.eps.data.fill_(self.initial_eps)
+
+    def message_up(self, up_x_j: Tensor, up_attr: Tensor) -> Tensor:
+        if up_attr is not None:
+            return self.msg_up_nn(torch.cat([up_x_j, up_attr], dim=-1))
+        return self.msg_up_nn(up_x_j)
+
+    def message_down(self, down_x_j: Tensor, down_attr: Tensor) -> Tensor:
+        return self.msg_down_nn(torch.cat([down_x_j, down_attr], dim=-1))
+
+
+class CINConv(_PerDimension):
+    """One `CINCochainConv` per dimension, all sharing the SAME nn objects (reference `mp/layers.py:106-124`)."""
+
+    def __init__(self, up_msg_size: int, down_msg_size: int, msg_up_nn: Callable, msg_down_nn: Callable,
+                 update_nn: Callable, eps: float = 0., train_eps: bool = False, max_dim: int = 2):
+        super(CINConv, self).__init__()
+        self.max_dim = max_dim
+        self.mp_levels = torch.nn.ModuleList(
+            CINCochainConv(up_msg_size, down_msg_size, msg_up_nn, msg_down_nn, update_nn, eps, train_eps)
+            for _ in range(max_dim + 1))
+
+    def forward(self, *cochain_params: CochainMessagePassingParams):
+        return super(CINConv, self).forward(*cochain_params)
+
+
+# ----------------------------------------------------------------------------------------------- sparse CIN
+class Catter(torch.nn.Module):
+    def forward(self, x):
+        return torch.cat([as_tensor(v) for v in x], dim=-1)
+
+
+def take_first(xs):
+    """Default upper message without coboundaries: the neighbour's features (reference `:295`)."""
+    return xs[0]
+
+
+def identity(x):
+    """Default boundary message (reference `:299`)."""
+    return x
+
+
+class SparseCINCochainConv(CochainMessagePassing):
+    """CIN cochain layer over boundaries and upper-adjacent cells (reference `mp/layers.py:154-214`):
+        u = SUM_up msg_up(x_j, y_cob) + (1+eps1) x ;  b = SUM_bnd msg_b(x_{d-1,j}) + (1+eps2) x
+        out = combine_nn(cat[update_up_nn(u), update_boundaries_nn(b)])
+    """
+
+    def __init__(self, dim: int, up_msg_size: int, down_msg_size: int, boundary_msg_size: Optional[int],
+                 msg_up_nn: Callable, msg_boundaries_nn: Callable, update_up_nn: Callable,
+                 update_boundaries_nn: Callable, combine_nn: Callable, eps: float = 0.,
+                 train_eps: bool = False):
+        super(SparseCINCochainConv, self).__init__(up_msg_size, down_msg_size,
+                                                   boundary_msg_size=boundary_msg_size, use_down_msg=False)
+        self.dim = dim
+        self.msg_up_nn = msg_up_nn
+        self.msg_boundaries_nn = msg_boundaries_nn
+        self.update_up_nn = update_up_nn
+        self.update_boundaries_nn = update_boundaries_nn
+        self.combine_nn = combine_nn
+        self.initial_eps = eps
+        if train_eps:
+            self.eps1 = torch.nn.Parameter(torch.Tensor([eps]))
+            self.eps2 = torch.nn.Parameter(torch.Tensor([eps]))
+        else:
+            self.register_buffer('eps1', torch.Tensor([eps]))
+            self.register_buffer('eps2', torch.Tensor([eps]))
+        self.reset_parameters()
+
+    # -------------------------------------------------------------- recognition of the closed-form messages
+    def _hooks_untouched(self):
+        klass = type(self)
+        return all(getattr(klass, name) is getattr(SparseCINCochainConv, name)
+                   for name in ('message_up', 'message_boundary', 'aggregate_up', 'aggregate_boundary',
+                                'update', 'propagate')) \
+            and self.aggr_up == 'add' and self.aggr_boundary == 'add' and self.flow == 'source_to_target'
+
+    def _up_message_form(self):
+        """('identity',) | ('cob', Linear, act_name) | None (unrecognised -> generic hook path)."""
+        nn_ = self.msg_up_nn
+        if nn_ is take_first:
+            return ('identity',)
+        if (isinstance(nn_, Sequential) and len(nn_) == 3 and isinstance(nn_[0], Catter)
+                and isinstance(nn_[1], Linear)):
+            act = activation_name(nn_[2])
+            if act is not None:
+                return ('cob', nn_[1], act)
+        return None
+
+    def _fused_forward(self, cochain: CochainMessagePassingParams):
+        """Both passes through the fused kernels, residuals included; NotImplemented if not recognised."""
+        x = cochain.x
+        form = self._up_message_form()
+        if form is None or self.msg_boundaries_nn is not identity or not self._hooks_untouched():
+            return NotImplemented
+        if not isinstance(x, Tensor) or x.dim() != 2:
+            return NotImplemented
+        n = x.size(0)
+        up_index, up_attr = cochain.up_index, cochain.kwargs['up_attr']
+        b_index, b_attr = cochain.boundary_index, cochain.kwargs['boundary_attr']
+        if up_index is not None and form[0] == 'cob':
+            lin = form[1]
+            if not (isinstance(up_attr, LazyRows) and x.size(1) + up_attr.source.size(1) == lin.in_features):
+                return NotImplemented  # dense / missing coboundary features: let the hook protocol decide
+
+        # upper adjacencies
+        if up_index is None:
+            if self.up_msg_size != x.size(1):
+                return NotImplemented
+            out_up = (1 + self.eps1) * x
+        elif form[0] == 'identity':
+            out_up = ops.gather_scatter(x, up_index, n, 'add', x_res=x, eps=self.eps1)
+        else:
+            _, lin, act = form
+            fx = x.size(1)
+            # W [x_j ; y_cob] + b  ==  (x W1^T)[src] + (y W2^T + b)[cob]: two per-CELL GEMMs instead of one per
+            # message, then a memory-bound fused pass
+            P = F.linear(x, lin.weight[:, :fx])
+            Q = F.linear(up_attr.source, lin.weight[:, fx:], lin.bias)
+            out_up = ops.cob_pass(P, Q, up_index, up_attr.index, n, act=act, x_res=x, eps=self.eps1)
+
+        # boundaries (the pass only runs when boundary features exist, reference mp/cell_mp.py:381)
+        if b_attr is not None:
+            if b_index is None:
+                return NotImplemented
+            out_b = ops.gather_scatter(as_tensor(b_attr), b_index, n, 'add', x_res=x, eps=self.eps2)
+        else:
+            if self.boundary_msg_size != x.size(1):
+                return NotImplemented
+            out_b = (1 + self.eps2) * x
+        return out_up, out_b
+
+    def forward(self, cochain: CochainMessagePassingParams):
+        fused = self._fused_forward(cochain)
+        if fused is NotImplemented:
+            out_up, _, out_boundaries = self.propagate(cochain.up_index, cochain.down_index,
+                                                       cochain.boundary_index, x=cochain.x,
+                                                       up_attr=cochain.kwargs['up_attr'],
+                                                       boundary_attr=cochain.kwargs['boundary_attr'])
+            out_up = out_up + (1 + self.eps1) * cochain.x
+            out_boundaries = out_boundaries + (1 + self.eps2) * cochain.x
+        else:
+            out_up, out_boundaries = fused
+        out_up = self.update_up_nn(out_up)
+        out_boundaries = self.update_boundaries_nn(out_boundaries)
+        return self.combine_nn(torch.cat([out_up, out_boundaries], dim=-1))
+
+    def reset_parameters(self):
+        reset(self.msg_up_nn)
+        reset(self.msg_boundaries_nn)
+        reset(self.update_up_nn)
+        reset(self.update_boundaries_nn)
+        reset(self.combine_nn)
+        self.eps1.data.fill_(self.initial_eps)
+        self.eps2.data.fill_(self.initial_eps)
+
+    def message_up(self, up_x_j: Tensor, up_attr: Tensor) -> Tensor:
+        return self.msg_up_nn((up_x_j, up_attr))
+
+    def message_boundary(self, boundary_x_j: Tensor) -> Tensor:
+        return self.msg_boundaries_nn(boundary_x_j)
+
+
+class SparseCINConv(_PerDimension):
+    """Cellular GIN with messages from upper neighbours and boundaries, one `SparseCINCochainConv` per dimension
+    with its own nets unless `passed_*` callables are supplied (reference `mp/layers.py:271-342`).
+
+    kwargs: `layer_dim`, `hidden`, `act_module`."""
+
+    def __init__(self, up_msg_size: int, down_msg_size: int, boundary_msg_size: Optional[int],
+                 passed_msg_up_nn: Optional[Callable], passed_msg_boundaries_nn: Optional[Callable],
+                 passed_update_up_nn: Optional[Callable], passed_update_boundaries_nn: Optional[Callable],
+                 eps: float = 0., train_eps: bool = False, max_dim: int = 2, graph_norm=BN,
+                 use_coboundaries=False, **kwargs):
+        super(SparseCINConv, self).__init__()
+        self.max_dim = max_dim
+        self.mp_levels = torch.nn.ModuleList()
+
+        def update_mlp():
+            return Sequential(Linear(kwargs['layer_dim'], kwargs['hidden']), graph_norm(kwargs['hidden']),
+                              kwargs['act_module'](),
+                              Linear(kwargs['hidden'], kwargs['hidden']), graph_norm(kwargs['hidden']),
+                              kwargs['act_module']())
+
+        for dim in range(max_dim + 1):
+            msg_up_nn = passed_msg_up_nn
+            if msg_up_nn is None:
+                if use_coboundaries:
+                    msg_up_nn = Sequential(Catter(), Linear(kwargs['layer_dim'] * 2, kwargs['layer_dim']),
+                                           kwargs['act_module']())
+                else:
+                    msg_up_nn = take_first
+            msg_boundaries_nn = identity if passed_msg_boundaries_nn is None else passed_msg_boundaries_nn
+            update_up_nn = update_mlp() if passed_update_up_nn is None else passed_update_up_nn
+            update_boundaries_nn = update_mlp() if passed_update_boundaries_nn is None \
+                else passed_update_boundaries_nn
+            combine_nn = Sequential(Linear(kwargs['hidden'] * 2, kwargs['hidden']), graph_norm(kwargs['hidden']),
+                                    kwargs['act_module']())
+            self.mp_levels.append(SparseCINCochainConv(
+                dim, up_msg_size, down_msg_size, boundary_msg_size=boundary_msg_size, msg_up_nn=msg_up_nn,
+                msg_boundaries_nn=msg_boundaries_nn, update_up_nn=update_up_nn,
+                update_boundaries_nn=update_boundaries_nn, combine_nn=combine_nn, eps=eps, train_eps=train_eps))
+
+
+# ----------------------------------------------------------------------------------------------- initialisation
+class InitReduceConv(torch.nn.Module):
+    """Initial features of d-cells as a reduction of their boundary features (reference `mp/layers.py:473-487`).
+
+    `out_size` (host int) avoids the reference's `boundary_index[1].max() + 1` device sync; when omitted the
+    reference behaviour (sync) is kept."""
+
+    def __init__(self, reduce='add'):
+        super(InitReduceConv, self).__init__()
+        if reduce not in ops.REDUCE_CODES:
+            raise NotImplementedError(f'cwn_b200: InitReduceConv reduce={reduce!r} is not supported')
+        self.reduce = reduce
+
+    def forward(self, boundary_x, boundary_index, out_size: Optional[int] = None):
+        if out_size is None:
+            out_size = int(boundary_index[1, :].max()) + 1
+        return ops.gather_scatter(boundary_x, boundary_index, out_size, reduce=self.reduce)
+
+
+class AbstractEmbedVEWithReduce(torch.nn.Module, ABC):
+    """Embeds vertex (and optionally edge) integer features and initialises the features of higher cells by
+    reducing over boundaries; rings are reduced from the REDUCED edge features and halved
+    (reference `mp/layers.py:490-547`)."""
+
+    def __init__(self, v_embed_layer: Callable, e_embed_layer: Optional[Callable], init_reduce: InitReduceConv):
+        super(AbstractEmbedVEWithReduce, self).__init__()
+        self.v_embed_layer = v_embed_layer
+        self.e_embed_layer = e_embed_layer
+        self.init_reduce = init_reduce
+
+    @abstractmethod
+    def _prepare_v_inputs(self, v_params):
+        pass
+
+    @abstractmethod
+    def _prepare_e_inputs(self, e_params):
+        pass
+
+    def forward(self, *cochain_params: CochainMessagePassingParams):
+        assert 1 <= len(cochain_params) <= 3
+        v_params = cochain_params[0]
+        e_params = cochain_params[1] if len(cochain_params) >= 2 else None
+        c_params = cochain_params[2] if len(cochain_params) == 3 else None
+
+        vx = self.v_embed_layer(self._prepare_v_inputs(v_params))
+        out = [vx]
+        if e_params is None:
+            assert c_params is None
+            return out
+
+        reduced_ex = self.init_reduce(vx, e_params.boundary_index, getattr(e_params, 'num_cells', None))
+        ex = reduced_ex
+        if e_params.x is not None:
+            ex = self.e_embed_layer(self._prepare_e_inputs(e_params))
+            assert ex.size(1) == vx.size(1)
+        out.append(ex)
+
+        if c_params is not None:
+            cx = self.init_reduce(reduced_ex, c_params.boundary_index, getattr(c_params, 'num_cells', None)) / 2.
+            out.append(cx)
+        return out
+
+    def reset_parameters(self):
+        reset(self.v_embed_layer)
+        reset(self.e_embed_layer)
+
+
+class EmbedVEWithReduce(AbstractEmbedVEWithReduce):
+    """`nn.Embedding` over scalar integer features stored as `[N, 1]` floats (ZINC; reference `:550-570`)."""
+
+    def __init__(self, v_embed_layer: torch.nn.Embedding, e_embed_layer: Optional[torch.nn.Embedding],
+                 init_reduce: InitReduceConv):
+        super(EmbedVEWithReduce, self).__init__(v_embed_layer, e_embed_layer, init_reduce)
+
+    def _prepare_v_inputs(self, v_params):
+        assert v_params.x is not None
+        assert v_params.x.dim() == 2
+        assert v_params.x.size(1) == 1
+        return v_params.x.squeeze(1).to(dtype=torch.long)
+
+    def _prepare_e_inputs(self, e_params):
+        assert self.e_embed_layer is not None
+        assert e_params.x.dim() == 2
+        assert e_params.x.size(1) == 1
+        return e_params.x.squeeze(1).to(dtype=torch.long)
+
+
+class OGBEmbedVEWithReduce(AbstractEmbedVEWithReduce):
+    """OGB Atom/Bond encoders over multi-column integer features (reference `:573-593`)."""
+
+    def __init__(self, v_embed_layer, e_embed_layer, init_reduce: InitReduceConv):
+        super(OGBEmbedVEWithReduce, self).__init__(v_embed_layer, e_embed_layer, init_reduce)
+
+    def _prepare_v_inputs(self, v_params):
+        assert v_params.x is not None
+        assert v_params.x.dim() == 2
+        return v_params.x.to(dtype=torch.long)
+
+    def _prepare_e_inputs(self, e_params):
+        assert self.e_embed_layer is not None
+        assert e_params.x.dim() == 2
+        return e_params.x.to(dtype=torch.long)

@@ -1,0 +1,186 @@
+"""`SparseCIN` and `CIN0` — the float-feature models of the hot path (reference `mp/models.py:12-257`).
+Constructor signatures, module names (state_dict keys) and forward semantics follow the reference; message
+passing, readout and their gradients run in the cwn_b200 CUDA kernels."""
+import torch
+import torch.nn.functional as F
+from torch.nn import Linear, Sequential, BatchNorm1d as BN
+
+from cwn_b200.data.complex import ComplexBatch
+from cwn_b200.mp.layers import CINConv, SparseCINConv
+from cwn_b200.mp.nn import (JumpingKnowledge, get_graph_norm, get_nonlinearity, get_pooling_fn,
+                            num_complexes_of, pool_complex)
+
+
+def _readout_head(model, xs, act, res, include_partial):
+    """Shared tail of the SparseCIN-family forwards (reference `mp/models.py:230-254`,
+    `mp/molec_models.py:137-161`): per-dimension lin1 + act, sum/mean over dimensions, dropout, lin2."""
+    new_xs = []
+    for i, x in enumerate(xs):
+        if model.apply_dropout_before == 'lin1':
+            x = F.dropout(x, p=model.dropout_rate, training=model.training)
+        new_xs.append(act(model.lin1s[model.readout_dims[i]](x)))
+    x = torch.stack(new_xs, dim=0)
+    if model.apply_dropout_before == 'final_readout':
+        x = F.dropout(x, p=model.dropout_rate, training=model.training)
+    if model.final_readout == 'mean':
+        x = x.mean(0)
+    elif model.final_readout == 'sum':
+        x = x.sum(0)
+    else:
+        raise NotImplementedError
+    if model.apply_dropout_before not in ['lin1', 'final_readout']:
+        x = F.dropout(x, p=model.dropout_rate, training=model.training)
+    x = model.lin2(x)
+    if include_partial:
+        res['out'] = x
+        return x, res
+    return x
+
+
+class _JumpMixin(object):
+    def jump_complex(self, jump_xs):
+        return [self.jump(jumpx) for jumpx in jump_xs]
+
+
+class CIN0(torch.nn.Module, _JumpMixin):
+    """Dense cellular GIN: upper + lower messages through shared MLPs (reference `mp/models.py:12-109`)."""
+
+    def __init__(self, num_input_features, num_classes, num_layers, hidden, dropout_rate: float = 0.5,
+                 max_dim: int = 2, jump_mode=None, nonlinearity='relu', readout='sum'):
+        super(CIN0, self).__init__()
+        self.max_dim = max_dim
+        self.dropout_rate = dropout_rate
+        self.jump_mode = jump_mode
+        self.convs = torch.nn.ModuleList()
+        self.nonlinearity = nonlinearity
+        self.readout = readout
+        self.pooling_fn = get_pooling_fn(readout)
+        conv_nonlinearity = get_nonlinearity(nonlinearity, return_module=True)
+        for i in range(num_layers):
+            layer_dim = num_input_features if i == 0 else hidden
+            conv_update = Sequential(Linear(layer_dim, hidden), conv_nonlinearity(), Linear(hidden, hidden),
+                                     conv_nonlinearity(), BN(hidden))
+            conv_up = Sequential(Linear(layer_dim * 2, layer_dim), conv_nonlinearity(), BN(layer_dim))
+            conv_down = Sequential(Linear(layer_dim * 2, layer_dim), conv_nonlinearity(), BN(layer_dim))
+            self.convs.append(CINConv(layer_dim, layer_dim, conv_up, conv_down, conv_update, train_eps=False,
+                                      max_dim=self.max_dim))
+        self.jump = JumpingKnowledge(jump_mode) if jump_mode is not None else None
+        self.lin1 = Linear(num_layers * hidden if jump_mode == 'cat' else hidden, hidden)
+        self.lin2 = Linear(hidden, num_classes)
+
+    def reset_parameters(self):
+        for conv in self.convs:
+            conv.reset_parameters()
+        if self.jump_mode is not None:
+            self.jump.reset_parameters()
+        self.lin1.reset_parameters()
+        self.lin2.reset_parameters()
+
+    def pool_complex(self, xs, data):
+        return pool_complex(xs, data, self.max_dim, self.readout)
+
+    def forward(self, data: ComplexBatch):
+        model_nonlinearity = get_nonlinearity(self.nonlinearity, return_module=False)
+        xs, jump_xs = None, None
+        for c, conv in enumerate(self.convs):
+            params = data.get_all_cochain_params(max_dim=self.max_dim)
+            xs = conv(*params)
+            data.set_xs(xs)
+            if self.jump_mode is not None:
+                if jump_xs is None:
+                    jump_xs = [[] for _ in xs]
+                for i, x in enumerate(xs):
+                    jump_xs[i] += [x]
+        if self.jump_mode is not None:
+            xs = self.jump_complex(jump_xs)
+        pooled_xs = self.pool_complex(xs, data)
+        x = pooled_xs.sum(dim=0)
+        x = model_nonlinearity(self.lin1(x))
+        x = F.dropout(x, p=self.dropout_rate, training=self.training)
+        x = self.lin2(x)
+        return x
+
+    def __repr__(self):
+        return self.__class__.__name__
+
+
+class SparseCIN(torch.nn.Module, _JumpMixin):
+    """Cellular GIN over boundaries and upper adjacencies (reference `mp/models.py:112-257`)."""
+
+    def __init__(self, num_input_features, num_classes, num_layers, hidden, dropout_rate: float = 0.5,
+                 max_dim: int = 2, jump_mode=None, nonlinearity='relu', readout='sum', train_eps=False,
+                 final_hidden_multiplier: int = 2, use_coboundaries=False, readout_dims=(0, 1, 2),
+                 final_readout='sum', apply_dropout_before='lin2', graph_norm='bn'):
+        super(SparseCIN, self).__init__()
+        self.max_dim = max_dim
+        if readout_dims is not None:
+            self.readout_dims = tuple([dim for dim in readout_dims if dim <= max_dim])
+        else:
+            self.readout_dims = list(range(max_dim + 1))
+        self.final_readout = final_readout
+        self.dropout_rate = dropout_rate
+        self.apply_dropout_before = apply_dropout_before
+        self.jump_mode = jump_mode
+        self.convs = torch.nn.ModuleList()
+        self.nonlinearity = nonlinearity
+        self.readout = readout
+        self.pooling_fn = get_pooling_fn(readout)
+        self.graph_norm = get_graph_norm(graph_norm)
+        act_module = get_nonlinearity(nonlinearity, return_module=True)
+        for i in range(num_layers):
+            layer_dim = num_input_features if i == 0 else hidden
+            self.convs.append(
+                SparseCINConv(up_msg_size=layer_dim, down_msg_size=layer_dim, boundary_msg_size=layer_dim,
+                              passed_msg_boundaries_nn=None, passed_msg_up_nn=None, passed_update_up_nn=None,
+                              passed_update_boundaries_nn=None, train_eps=train_eps, max_dim=self.max_dim,
+                              hidden=hidden, act_module=act_module, layer_dim=layer_dim,
+                              graph_norm=self.graph_norm, use_coboundaries=use_coboundaries))
+        self.jump = JumpingKnowledge(jump_mode) if jump_mode is not None else None
+        self.lin1s = torch.nn.ModuleList()
+        for _ in range(max_dim + 1):
+            if jump_mode == 'cat':
+                # bias-free: a dimension absent from a complex must contribute exactly zero
+                self.lin1s.append(Linear(num_layers * hidden, final_hidden_multiplier * hidden, bias=False))
+            else:
+                self.lin1s.append(Linear(hidden, final_hidden_multiplier * hidden))
+        self.lin2 = Linear(final_hidden_multiplier * hidden, num_classes)
+
+    def reset_parameters(self):
+        for conv in self.convs:
+            conv.reset_parameters()
+        if self.jump_mode is not None:
+            self.jump.reset_parameters()
+        self.lin1s.reset_parameters()
+        self.lin2.reset_parameters()
+
+    def pool_complex(self, xs, data):
+        pooled = pool_complex(xs, data, self.max_dim, self.readout)
+        return [pooled[i] for i in range(self.max_dim + 1)]
+
+    def forward(self, data: ComplexBatch, include_partial=False):
+        act = get_nonlinearity(self.nonlinearity, return_module=False)
+        xs, jump_xs = None, None
+        res = {}
+        for c, conv in enumerate(self.convs):
+            params = data.get_all_cochain_params(max_dim=self.max_dim, include_down_features=False)
+            xs = conv(*params, start_to_process=0)
+            data.set_xs(xs)
+            if include_partial:
+                for k in range(len(xs)):
+                    res[f"layer{c}_{k}"] = xs[k]
+            if self.jump_mode is not None:
+                if jump_xs is None:
+                    jump_xs = [[] for _ in xs]
+                for i, x in enumerate(xs):
+                    jump_xs[i] += [x]
+        if self.jump_mode is not None:
+            xs = self.jump_complex(jump_xs)
+        xs = self.pool_complex(xs, data)
+        xs = [xs[i] for i in self.readout_dims]
+        if include_partial:
+            for k in range(len(xs)):
+                res[f"pool_{k}"] = xs[k]
+        return _readout_head(self, xs, act, res, include_partial)
+
+    def __repr__(self):
+        return self.__class__.__name__

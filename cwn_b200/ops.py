@@ -1,0 +1,375 @@
+"""Autograd operators of the hot path, all thin wrappers over the C ABI in include/cwn_b200.h.
+
+PyTorch is used for device memory (caching allocator), the current stream and autograd bookkeeping only; the
+arithmetic of gather / message / aggregate runs in the hand-written sm_100a kernels. Every function here
+requires CUDA fp32 tensors and raises otherwise (no CPU path, no torch_scatter, no eager fallback).
+
+Replaces in the reference: `__lift__` (mp/cell_mp.py:195-198), `aggregate_*` (mp/cell_mp.py:423-479),
+`InitReduceConv` (mp/layers.py:484-487), `global_add_pool/global_mean_pool` (mp/nn.py:59), the `up_attr` gather of
+`data/complex.py:579-580`, and the autograd of all of them.
+"""
+import torch
+from torch import Tensor
+from torch.autograd import Function
+
+from cwn_b200 import _lib
+
+REDUCE_CODES = {'add': 0, 'sum': 0, 'mean': 1, 'max': 2}
+ACT_CODES = {'id': 0, 'relu': 1, 'elu': 2, 'sigmoid': 3, 'tanh': 4}
+
+
+# --------------------------------------------------------------------------------------------- helpers
+def _require_cuda_f32(t: Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f'cwn_b200: `{name}` is on {t.device}; the message-passing path is CUDA-only '
+                           f'(sm_100a kernels, no CPU fallback)')
+    if t.dtype != torch.float32:
+        raise TypeError(f'cwn_b200: `{name}` must be float32, got {t.dtype}')
+
+
+def _rows(t: Tensor) -> Tensor:
+    """2-D view with unit inner stride (the C ABI takes an explicit leading dimension)."""
+    if t.dim() == 1:
+        t = t.unsqueeze(-1)
+    if t.dim() != 2:
+        raise ValueError(f'cwn_b200: expected a [rows, features] matrix, got shape {tuple(t.shape)}')
+    if t.size(1) > 0 and t.stride(1) != 1 or (t.size(0) > 1 and t.stride(0) < t.size(1)):
+        t = t.contiguous()
+    return t
+
+
+def _ptr(t):
+    return None if t is None or t.numel() == 0 else t.data_ptr()
+
+
+def _ld(t):
+    return t.stride(0) if t.size(0) > 1 else max(t.size(1), 1)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# --------------------------------------------------------------------------------------------- CSR plans
+class Plan(object):
+    """Messages grouped (stably) by one index column: `rowptr[n_rows+1]`, `perm[E]`, up to two payload columns."""
+    __slots__ = ('rowptr', 'perm', 'pay0', 'pay1', 'n_rows', 'E')
+
+    def __init__(self, rowptr, perm, pay0, pay1, n_rows, E):
+        self.rowptr, self.perm, self.pay0, self.pay1, self.n_rows, self.E = rowptr, perm, pay0, pay1, n_rows, E
+
+
+def build_plan(key: Tensor, n_rows: int, pay0: Tensor = None, pay1: Tensor = None) -> Plan:
+    """cwn_csr_plan_build: stable CSR grouping of `key` (int64 [E], values in [0, n_rows))."""
+    if not key.is_cuda:
+        raise RuntimeError('cwn_b200: index tensors must live on the GPU (CUDA-only path)')
+    if key.dtype != torch.long:
+        raise TypeError('cwn_b200: index tensors must be torch.long')
+    lib = _lib.load()
+    E = key.numel()
+    dev = key.device
+    key = key.contiguous()
+    pay0 = pay0.contiguous() if pay0 is not None else None
+    pay1 = pay1.contiguous() if pay1 is not None else None
+    with torch.cuda.device(dev):
+        rowptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
+        perm = torch.empty(E, dtype=torch.int32, device=dev)
+        p0 = torch.empty(E, dtype=torch.int32, device=dev) if pay0 is not None else None
+        p1 = torch.empty(E, dtype=torch.int32, device=dev) if pay1 is not None else None
+        ws_bytes = lib.cwn_csr_plan_workspace_bytes(E, n_rows)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.cwn_csr_plan_build(_ptr(key), _ptr(pay0), _ptr(pay1), E, n_rows, rowptr.data_ptr(),
+                                          _ptr(perm), _ptr(p0), _ptr(p1), None, ws.data_ptr(), ws_bytes,
+                                          _stream()), 'csr_plan_build')
+    return Plan(rowptr, perm, p0, p1, n_rows, E)
+
+
+class Adjacency(object):
+    """One adjacency of a cochain (`index` int64 [2, E]: row 0 = source, row 1 = destination; optional per-message
+    coboundary/boundary id column `cob`) with its lazily built, cached CSR plans:
+        by_dst : grouped by destination, payload (source, cob)   -> forward passes
+        by_src : grouped by source,      payload (destination, cob) -> gradient w.r.t. the gathered operand
+        by_cob : grouped by cob,         payload (destination, source) -> gradient w.r.t. the coboundary operand
+    Index tensors are constant across layers and between forward and backward, so each plan is built once per
+    batch. The cache lives on the index tensor object itself and is keyed by its version counter."""
+
+    def __init__(self, index: Tensor, n_src: int, n_dst: int, cob: Tensor = None, n_cob: int = None):
+        if index.dim() != 2 or index.size(0) != 2:
+            raise ValueError('cwn_b200: adjacency index must have shape [2, num_messages]')
+        self.index, self.n_src, self.n_dst, self.cob, self.n_cob = index, int(n_src), int(n_dst), cob, n_cob
+        self.E = index.size(1)
+
+    @classmethod
+    def of(cls, index: Tensor, n_src: int, n_dst: int, cob: Tensor = None, n_cob: int = None):
+        cache = index.__dict__.setdefault('_cwn_adj', {})
+        k = (int(n_src), int(n_dst), None if cob is None else (cob.data_ptr(), cob._version), n_cob,
+             index._version, index.data_ptr())
+        adj = cache.get(k)
+        if adj is None:
+            cache.clear()  # stale plans of an index that was modified in place
+            adj = cache[k] = cls(index, n_src, n_dst, cob, n_cob)
+            adj._plans = {}
+        return adj
+
+    def _plan(self, kind):
+        plan = self._plans.get(kind)
+        if plan is None:
+            src, dst = self.index[0], self.index[1]
+            if kind == 'by_dst':
+                plan = build_plan(dst, self.n_dst, src, self.cob)
+            elif kind == 'by_src':
+                plan = build_plan(src, self.n_src, dst, self.cob)
+            else:
+                plan = build_plan(self.cob, self.n_cob, dst, src)
+            self._plans[kind] = plan
+        return plan
+
+    by_dst = property(lambda self: self._plan('by_dst'))
+    by_src = property(lambda self: self._plan('by_src'))
+    by_cob = property(lambda self: self._plan('by_cob'))
+
+
+def clear_plan_cache(*indices):
+    for idx in indices:
+        if idx is not None:
+            idx.__dict__.pop('_cwn_adj', None)
+
+
+# --------------------------------------------------------------------------------------------- raw launches
+def _launch_gather_reduce(x_src, plan_rowptr, idx, n_rows, F, x_res, eps, reduce_code):
+    lib = _lib.load()
+    dev = plan_rowptr.device
+    with torch.cuda.device(dev):
+        out = torch.empty(n_rows, F, dtype=torch.float32, device=dev)
+        _lib.check(lib.cwn_csr_gather_reduce_f32(
+            _ptr(x_src), _ld(x_src) if x_src is not None else F, plan_rowptr.data_ptr(), _ptr(idx), n_rows, F,
+            _ptr(x_res), _ld(x_res) if x_res is not None else F, _ptr(eps), _ptr(out), F, reduce_code,
+            _stream()), 'csr_gather_reduce')
+    return out
+
+
+def _launch_gather_rows(x, idx, scale):
+    lib = _lib.load()
+    E, F = idx.numel(), x.size(1)
+    with torch.cuda.device(x.device):
+        out = torch.empty(E, F, dtype=torch.float32, device=x.device)
+        _lib.check(lib.cwn_gather_rows_f32(_ptr(x), _ld(x), _ptr(idx), E, F, float(scale), _ptr(out), F,
+                                           _stream()), 'gather_rows')
+    return out
+
+
+def _eps_grad(ctx_needs, g, x_res, eps):
+    """(grad x_res, grad eps) of out = (1 + eps) * x_res + ..."""
+    g_res = g_eps = None
+    if x_res is not None and ctx_needs[0]:
+        g_res = g if eps is None else g * (1.0 + eps)
+    if eps is not None and ctx_needs[1]:
+        g_eps = (g * x_res).sum().reshape(eps.shape)
+    return g_res, g_eps
+
+
+def _check_eps(eps):
+    if eps is not None:
+        _require_cuda_f32(eps, 'eps')
+        if eps.numel() != 1:
+            raise ValueError('cwn_b200: eps must hold a single value')
+
+
+# --------------------------------------------------------------------------------------------- autograd ops
+class _GatherReduce(Function):
+    """out[r] = (1+eps)*x_res[r] + REDUCE_{e: dst_e = r} x_src[src_e]  — the fused identity-message pass."""
+
+    @staticmethod
+    def forward(ctx, x_src, x_res, eps, adj: Adjacency, reduce: str):
+        code = REDUCE_CODES[reduce]
+        plan = adj.by_dst
+        F = x_src.size(1)
+        out = _launch_gather_reduce(x_src, plan.rowptr, plan.pay0, adj.n_dst, F, x_res, eps, code)
+        ctx.adj, ctx.reduce = adj, reduce
+        ctx.save_for_backward(x_res if (eps is not None and eps.requires_grad) else None, eps)
+        ctx.has_res = x_res is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        adj = ctx.adj
+        x_res, eps = ctx.saved_tensors
+        g = _rows(g)
+        g_src = None
+        if ctx.needs_input_grad[0]:
+            if ctx.reduce == 'max':
+                raise NotImplementedError('cwn_b200: backward of max aggregation is not implemented')
+            gm = g
+            if ctx.reduce == 'mean':
+                deg = (adj.by_dst.rowptr[1:] - adj.by_dst.rowptr[:-1]).clamp_(min=1).to(g.dtype)
+                gm = g / deg.unsqueeze(-1)
+            plan = adj.by_src  # transposed pass: gX[s] = sum_{e: src_e = s} G[dst_e]
+            g_src = _launch_gather_reduce(gm, plan.rowptr, plan.pay0, adj.n_src, g.size(1), None, None, 0)
+        g_res, g_eps = _eps_grad(ctx.needs_input_grad[1:3], g, x_res if ctx.has_res else None, eps) \
+            if ctx.has_res else (None, None)
+        if ctx.has_res and ctx.needs_input_grad[1] and g_res is None:
+            g_res = g
+        return g_src, g_res, g_eps, None, None
+
+
+class _CobPass(Function):
+    """out[r] = (1+eps)*x_res[r] + SUM_{e: dst_e = r} act(P[src_e] + Q[cob_e]) — upper pass with coboundaries."""
+
+    @staticmethod
+    def forward(ctx, P, Q, x_res, eps, adj: Adjacency, act: str):
+        lib = _lib.load()
+        plan = adj.by_dst
+        F = P.size(1)
+        with torch.cuda.device(P.device):
+            out = torch.empty(adj.n_dst, F, dtype=torch.float32, device=P.device)
+            _lib.check(lib.cwn_csr_cob_fwd_f32(
+                _ptr(P), _ld(P), _ptr(Q), _ld(Q), plan.rowptr.data_ptr(), _ptr(plan.pay0), _ptr(plan.pay1),
+                adj.n_dst, F, ACT_CODES[act], _ptr(x_res), _ld(x_res) if x_res is not None else F, _ptr(eps),
+                _ptr(out), F, _stream()), 'csr_cob_fwd')
+        ctx.adj, ctx.act = adj, act
+        ctx.has_res = x_res is not None
+        ctx.save_for_backward(P, Q, x_res if (eps is not None and eps.requires_grad) else None, eps)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        adj, act = ctx.adj, ACT_CODES[ctx.act]
+        P, Q, x_res, eps = ctx.saved_tensors
+        g = _rows(g)
+        F = P.size(1)
+        gP = gQ = None
+        with torch.cuda.device(P.device):
+            if ctx.needs_input_grad[0]:
+                plan = adj.by_src
+                gP = torch.empty_like(P, memory_format=torch.contiguous_format)
+                _lib.check(lib.cwn_csr_cob_bwd_f32(
+                    _ptr(g), _ld(g), _ptr(P), _ld(P), _ptr(Q), _ld(Q), plan.rowptr.data_ptr(), _ptr(plan.pay0),
+                    _ptr(plan.pay1), adj.n_src, F, act, _ptr(gP), F, _stream()), 'csr_cob_bwd(P)')
+            if ctx.needs_input_grad[1]:
+                plan = adj.by_cob
+                gQ = torch.empty_like(Q, memory_format=torch.contiguous_format)
+                _lib.check(lib.cwn_csr_cob_bwd_f32(
+                    _ptr(g), _ld(g), _ptr(Q), _ld(Q), _ptr(P), _ld(P), plan.rowptr.data_ptr(), _ptr(plan.pay0),
+                    _ptr(plan.pay1), adj.n_cob, F, act, _ptr(gQ), F, _stream()), 'csr_cob_bwd(Q)')
+        g_res = g_eps = None
+        if ctx.has_res:
+            g_res, g_eps = _eps_grad(ctx.needs_input_grad[2:4], g, x_res, eps)
+            if ctx.needs_input_grad[2] and g_res is None:
+                g_res = g
+        return gP, gQ, g_res, g_eps, None, None
+
+
+class _GatherRows(Function):
+    """out[e] = scale * x[idx[e]]"""
+
+    @staticmethod
+    def forward(ctx, x, idx, scale):
+        ctx.idx, ctx.n, ctx.scale = idx, x.size(0), scale
+        return _launch_gather_rows(x, idx, scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _rows(g)
+        idx = ctx.idx
+        cache = idx.__dict__.setdefault('_cwn_rowplan', {})
+        k = (ctx.n, idx._version, idx.data_ptr())
+        plan = cache.get(k)
+        if plan is None:
+            cache.clear()
+            plan = cache[k] = build_plan(idx, ctx.n)
+        gx = _launch_gather_reduce(g, plan.rowptr, plan.perm, ctx.n, g.size(1), None, None, 0)
+        if ctx.scale != 1.0:
+            gx = gx * ctx.scale
+        return gx, None, None
+
+
+class _ScatterRows(Function):
+    """out[r] = REDUCE_{e: dst[e] = r} msg[e]  (aggregation of messages materialised by a user hook, or readout)."""
+
+    @staticmethod
+    def forward(ctx, msg, dst, n_dst, reduce):
+        cache = dst.__dict__.setdefault('_cwn_rowplan', {})
+        k = (n_dst, dst._version, dst.data_ptr())
+        plan = cache.get(k)
+        if plan is None:
+            cache.clear()
+            plan = cache[k] = build_plan(dst, n_dst)
+        ctx.dst, ctx.plan, ctx.reduce = dst, plan, reduce
+        return _launch_gather_reduce(msg, plan.rowptr, plan.perm, n_dst, msg.size(1), None, None,
+                                     REDUCE_CODES[reduce])
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.reduce == 'max':
+            raise NotImplementedError('cwn_b200: backward of max aggregation is not implemented')
+        g = _rows(g)
+        if ctx.reduce == 'mean':
+            deg = (ctx.plan.rowptr[1:] - ctx.plan.rowptr[:-1]).clamp_(min=1).to(g.dtype)
+            g = g / deg.unsqueeze(-1)
+        return _launch_gather_rows(g, ctx.dst, 1.0), None, None, None
+
+
+# --------------------------------------------------------------------------------------------- public API
+def gather_scatter(x_src: Tensor, index: Tensor, n_dst: int, reduce: str = 'add', x_res: Tensor = None,
+                   eps: Tensor = None) -> Tensor:
+    """Fused `scatter(x_src.index_select(0, index[0]), index[1], dim_size=n_dst, reduce)` [+ (1+eps) * x_res]."""
+    if reduce not in REDUCE_CODES:
+        raise ValueError(f'cwn_b200: unknown aggregation {reduce!r}')
+    x_src = _rows(x_src)
+    _require_cuda_f32(x_src, 'x_src')
+    if x_res is not None:
+        x_res = _rows(x_res)
+        _require_cuda_f32(x_res, 'x_res')
+        if x_res.size(0) != n_dst or x_res.size(1) != x_src.size(1):
+            raise ValueError('cwn_b200: residual operand must have shape [n_dst, F]')
+    _check_eps(eps)
+    adj = Adjacency.of(index, x_src.size(0), n_dst)
+    return _GatherReduce.apply(x_src, x_res, eps, adj, reduce)
+
+
+def cob_pass(P: Tensor, Q: Tensor, index: Tensor, cob: Tensor, n_dst: int, act: str = 'relu',
+             x_res: Tensor = None, eps: Tensor = None) -> Tensor:
+    """Upper-adjacency pass with coboundary features in split-weight form (see include/cwn_b200.h)."""
+    if act not in ACT_CODES:
+        raise ValueError(f'cwn_b200: unknown activation {act!r}')
+    P, Q = _rows(P), _rows(Q)
+    _require_cuda_f32(P, 'P')
+    _require_cuda_f32(Q, 'Q')
+    if P.size(1) != Q.size(1):
+        raise ValueError('cwn_b200: P and Q must have the same width')
+    if x_res is not None:
+        x_res = _rows(x_res)
+        _require_cuda_f32(x_res, 'x_res')
+    _check_eps(eps)
+    if cob.numel() != index.size(1):
+        raise ValueError('cwn_b200: one coboundary id per message is required')
+    adj = Adjacency.of(index, P.size(0), n_dst, cob, Q.size(0))
+    return _CobPass.apply(P, Q, x_res, eps, adj, act)
+
+
+def gather_rows(x: Tensor, idx: Tensor, scale: float = 1.0) -> Tensor:
+    """`scale * x.index_select(0, idx)` (reference `__lift__`, mp/cell_mp.py:195-198)."""
+    x = _rows(x)
+    _require_cuda_f32(x, 'x')
+    if idx.dtype != torch.long or not idx.is_cuda:
+        raise TypeError('cwn_b200: gather index must be a CUDA torch.long tensor')
+    return _GatherRows.apply(x, idx.contiguous(), float(scale))
+
+
+def scatter_rows(msg: Tensor, dst: Tensor, n_dst: int, reduce: str = 'add') -> Tensor:
+    """`torch_scatter.scatter(msg, dst, dim=0, dim_size=n_dst, reduce)` (mp/cell_mp.py:439-440)."""
+    if reduce not in REDUCE_CODES:
+        raise ValueError(f'cwn_b200: unknown aggregation {reduce!r}')
+    msg = _rows(msg)
+    _require_cuda_f32(msg, 'messages')
+    if dst.dtype != torch.long or not dst.is_cuda:
+        raise TypeError('cwn_b200: scatter index must be a CUDA torch.long tensor')
+    if dst.numel() != msg.size(0):
+        raise ValueError('cwn_b200: one destination per message is required')
+    return _ScatterRows.apply(msg, dst.contiguous(), int(n_dst), reduce)
+
+
+def segment_pool(x: Tensor, batch: Tensor, size: int, mean: bool = False) -> Tensor:
+    """Per-complex readout `global_add_pool / global_mean_pool(x, batch, size)` (mp/nn.py:59)."""
+    return scatter_rows(x, batch, size, 'mean' if mean else 'add')

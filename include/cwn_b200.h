@@ -1,0 +1,120 @@
+/* cwn_b200 — C ABI of the B200-native cochain message-passing hot path.
+ *
+ * The reference (twitter-research/cwn) is pure Python: its hot path bottoms out in three third-party calls,
+ *   Tensor.index_select(dim, idx)                         mp/cell_mp.py:195-198, data/complex.py:579-580,587-588
+ *   torch_scatter.scatter(src, index, dim=-2, dim_size=N, reduce)   mp/cell_mp.py:437-440,456-459,476-479; mp/layers.py:487
+ *   torch_geometric global_add_pool / global_mean_pool     mp/nn.py:50-60 (= scatter over the `batch` vector)
+ * plus the per-message Linear(2F->F)+activation of SparseCINConv(use_coboundaries=True), mp/layers.py:210-211,290-293.
+ * This library is what replaces that boundary. There is no native ABI in the reference to copy; the entry points
+ * below are what a binding for this path binds (see INTEGRATION.md for the ctypes stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch caching allocator); the library never
+ *     allocates, frees or keeps pointers, and is re-entrant / thread-safe (autograd calls it from worker threads);
+ *   - matrices are row-major fp32 with an explicit leading dimension `ld` (in elements);
+ *   - adjacency columns arrive as int64 (the reference API: `assert index.dtype == torch.long`,
+ *     mp/cell_mp.py:158) and are narrowed ONCE per batch to int32 CSR plans that every layer, forward and
+ *     backward, reuses;
+ *   - all work is stream-ordered on `stream` (a cudaStream_t); no call synchronises the device;
+ *   - return value: 0 = ok, >0 = cudaError_t, <0 = argument error (CWN_E_*); cwn_last_error_string() gives the
+ *     calling thread's last message. No exception crosses the boundary.
+ */
+#ifndef CWN_B200_H
+#define CWN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cwn_stream_t; /* cudaStream_t */
+
+enum {
+  CWN_OK = 0,
+  CWN_E_NULL = -1,      /* required pointer is NULL */
+  CWN_E_SHAPE = -2,     /* negative size, ld < F, F <= 0, sizes beyond int32 range */
+  CWN_E_ENUM = -3,      /* unknown reduce / activation code */
+  CWN_E_WORKSPACE = -4, /* workspace too small */
+  CWN_E_ALIGN = -5      /* pointer not 4-byte aligned */
+};
+
+/* aggregation of the messages that reach a destination (reference: aggr_up/aggr_down/aggr_boundary,
+ * mp/cell_mp.py:84-86,104-105). Rows without messages are 0 for every mode (mp/test_cell_mp.py:114-134). */
+enum { CWN_REDUCE_ADD = 0, CWN_REDUCE_MEAN = 1, CWN_REDUCE_MAX = 2 };
+
+/* activation of the coboundary message MLP (reference mp/nn.py:7-27) */
+enum { CWN_ACT_ID = 0, CWN_ACT_RELU = 1, CWN_ACT_ELU = 2, CWN_ACT_SIGMOID = 3, CWN_ACT_TANH = 4 };
+
+const char* cwn_version(void);
+const char* cwn_last_error_string(void);
+/* number of kernels this library has launched in this process (for bench.py's gpu_launches) */
+unsigned long long cwn_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * CSR plan: group the E messages of one adjacency by one of its columns.
+ *   key[e] in [0, n_rows)  : the grouping column (destination = index[1] for the forward pass; source = index[0]
+ *                            for the gradient w.r.t. the gathered operand; shared_coboundaries for the gradient
+ *                            w.r.t. the coboundary operand)
+ *   pay0, pay1 (nullable)  : other per-message columns to carry along (e.g. source and coboundary ids)
+ * Outputs (all int32, caller-allocated):
+ *   rowptr[n_rows+1]       : messages of row r are positions [rowptr[r], rowptr[r+1])
+ *   perm[E]                : original message id at each position; STABLE (ascending e inside a row), so a
+ *                            sequential in-row accumulation reproduces the order of CPU scatter_add_ exactly
+ *   pay0_sorted[E], pay1_sorted[E] : pay*[perm[i]] narrowed to int32 (only written if the input is non-NULL)
+ *   flags[1] (nullable)    : bit 0 set if some key was outside [0, n_rows) (such messages are dropped)
+ * Replaces: the unsorted atomics scatter of torch_scatter (reference mp/cell_mp.py:439-440).
+ */
+size_t cwn_csr_plan_workspace_bytes(int64_t E, int64_t n_rows);
+int cwn_csr_plan_build(const int64_t* key, const int64_t* pay0, const int64_t* pay1, int64_t E, int64_t n_rows,
+                       int32_t* rowptr, int32_t* perm, int32_t* pay0_sorted, int32_t* pay1_sorted,
+                       int32_t* flags, void* workspace, size_t workspace_bytes, cwn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused gather -> (identity message) -> reduce, one destination row per thread group, no atomics:
+ *   out[r,:] = (x_res ? (1 + *eps) * x_res[r,:] : 0) + REDUCE_{i in row r} x_src[ idx ? idx[i] : i , :]
+ * `idx` = the plan's source column (fused identity pass: boundary messages, upper messages without coboundaries,
+ * InitReduceConv, and — with the transposed plan — their gradients), or the plan's `perm` (aggregation of
+ * messages a user hook materialised), or NULL (sorted segments: the per-complex readout, rowptr = ptr).
+ * `eps` (device scalar, nullable => 0) is the GIN epsilon of mp/layers.py:191-192; x_res requires CWN_REDUCE_ADD.
+ * Replaces: index_select + scatter (mp/cell_mp.py:198 + :439-440 / :478-479), mp/layers.py:485-487, mp/nn.py:59.
+ */
+int cwn_csr_gather_reduce_f32(const float* x_src, int64_t ld_src, const int32_t* rowptr, const int32_t* idx,
+                              int64_t n_rows, int32_t F, const float* x_res, int64_t ld_res, const float* eps,
+                              float* out, int64_t ld_out, int32_t reduce, cwn_stream_t stream);
+
+/* Row gather out[e,:] = scale * x[idx[e],:] (int64 idx straight from the API). Used for operands of user-defined
+ * message hooks (reference __lift__, mp/cell_mp.py:195-198), lazily requested `up_attr`/`down_attr`
+ * (data/complex.py:579-580,587-588) and the gradient of the readout. */
+int cwn_gather_rows_f32(const float* x, int64_t ld_x, const int64_t* idx, int64_t E, int32_t F, float scale,
+                        float* out, int64_t ld_out, cwn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Upper-adjacency pass with coboundary features (SparseCINConv(use_coboundaries=True), mp/layers.py:210-211,
+ * 290-293): message_e = act(W [x[s_e] ; y[c_e]] + b). With W = [W1 | W2] the per-message Linear splits into two
+ * per-CELL products P = x W1^T, Q = y W2^T + b (dense, done by the caller), and the pass becomes memory-bound:
+ *   out[r,:] = (x_res ? (1 + *eps) * x_res[r,:] : 0) + SUM_{i in row r} act( P[src[i],:] + Q[cob[i],:] )
+ * (plan grouped by destination; src/cob = the plan's two payload columns).
+ */
+int cwn_csr_cob_fwd_f32(const float* P, int64_t ld_p, const float* Q, int64_t ld_q, const int32_t* rowptr,
+                        const int32_t* src, const int32_t* cob, int64_t n_rows, int32_t F, int32_t act,
+                        const float* x_res, int64_t ld_res, const float* eps, float* out, int64_t ld_out,
+                        cwn_stream_t stream);
+
+/* Gradient of the pass above w.r.t. ONE of its two gathered operands A (the other is B), on the plan grouped by
+ * A's index column, so A[r,:] is read once per row and nothing is atomically accumulated:
+ *   gA[r,:] = SUM_{i in row r} G[dst[i],:] * act'( A[r,:] + B[oth[i],:] )
+ * Call once with (A,B) = (P,Q) on the by-source plan and once with (A,B) = (Q,P) on the by-coboundary plan. */
+int cwn_csr_cob_bwd_f32(const float* G, int64_t ld_g, const float* A, int64_t ld_a, const float* B, int64_t ld_b,
+                        const int32_t* rowptr, const int32_t* dst, const int32_t* oth, int64_t n_rows, int32_t F,
+                        int32_t act, float* gA, int64_t ld_ga, cwn_stream_t stream);
+
+/* Debug aid: sets bit 1 of flags[0] if any idx[e] is outside [0, n). (The reference relies on torch's device
+ * assert for out-of-range indices.) */
+int cwn_check_index_range(const int64_t* idx, int64_t E, int64_t n, int32_t* flags, cwn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CWN_B200_H */
