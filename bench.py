@@ -1,0 +1,372 @@
+"""bench.py — cells/sec of one training step of the ZINC-shaped ring-lifted CWN (BASELINE.json configs[1]).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
+
+A "step" = one pass of the hot path over one batch of 128 synthetic ZINC-shaped complexes (V=23, E=25, rings
+{6,6,5} -> 6 528 cells): EmbedSparseCIN (4 layers, hidden 64, edge embeddings, coboundary messages, BatchNorm,
+sum readout) forward -> L1 loss -> backward -> gradient all-reduce (N>1) -> Adam step. The optimizer step is inside
+the timed region although the metric is named fwd+bwd, so nothing is skipped.
+
+  value : cells/s with the batch already resident in HBM (CSR plans are rebuilt every step: each step is a new
+          batch), max over ranks, L2 flushed between steps
+  e2e   : the same through the public API from HOST memory: ComplexBatch.to(device) (one pinned staging buffer
+          per dtype) -> plans -> step -> loss.item()
+  roofline : the dominant cwn kernel of the step, algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json
+  cpu_baseline : the oracle (torch-only port of the reference path; the reference itself cannot be imported
+          here: torch_scatter / torch_geometric are absent) on the host cores, bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL_CFG = dict(atom_types=28, bond_types=4, out_size=1, num_layers=4, hidden=64, dropout_rate=0.0, max_dim=2,
+                 embed_edge=True, use_coboundaries=True, graph_norm='bn', readout='sum')
+WORKLOAD = 'ZINC ring-lift (max_ring=6) EmbedSparseCIN 4-layer hidden=64 batch=128 (BASELINE.json configs[1])'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='cwn', choices=['cwn', 'reference'])
+    ap.add_argument('--batch', type=int, default=128)
+    ap.add_argument('--pool', type=int, default=8, help='distinct pre-collated batches cycled through')
+    ap.add_argument('--mode', default='auto', choices=['auto', 'eager', 'graph'])
+    ap.add_argument('--no-sweep', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def l1(out, y):
+    return torch.nn.functional.l1_loss(out, y.view(-1, 1))  # reference exp/train_utils.py:25-26
+
+
+def make_batches(n_batches, batch_size, seed0):
+    from cwn_b200.data import synthetic
+    from cwn_b200.data.complex import ComplexBatch
+    return [ComplexBatch.from_complex_list(synthetic.zinc_like_complexes(batch_size, seed=seed0 + i))
+            for i in range(n_batches)]
+
+
+def cells_of(batch):
+    return sum(batch.cochains[d].num_cells for d in range(batch.dimension + 1))
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_steps(steps, warmup, batch_size, budget_s=None):
+    """The oracle's forward + loss + backward + Adam on the host cores. Returns (cells/s, ms/step, steps done)."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import cwn_oracle as O
+    from cwn_b200.mp.molec_models import EmbedSparseCIN
+    torch.manual_seed(0)
+    sd = {k: v.detach().clone() for k, v in EmbedSparseCIN(**MODEL_CFG).state_dict().items()}
+    leaves = []
+    for k, v in sd.items():
+        if v.is_floating_point() and 'running' not in k and not k.endswith(('eps1', 'eps2')):
+            v.requires_grad_(True)
+            leaves.append(v)
+    leaves = list({id(v): v for v in leaves}.values())
+    opt = torch.optim.Adam(leaves, lr=1e-3)
+    batches = make_batches(4, batch_size, seed0=1000)
+    cells = cells_of(batches[0])
+    done, t_total = 0, 0.0
+    for i in range(warmup + steps):
+        snap = O.Snapshot(batches[i % len(batches)])
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        out = O.embed_sparse_cin(sd, MODEL_CFG, snap, training=True)
+        loss = l1(out, snap.y)
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            done += 1
+            t_total += dt
+            if budget_s is not None and t_total > budget_s:
+                break
+    ms = 1e3 * t_total / max(done, 1)
+    return cells / (ms / 1e3), ms, done, cells
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    value, ms, done, cells = cpu_steps(args.steps, args.warmup, args.batch)
+    cores = torch.get_num_threads()
+    line = {
+        'impl': 'reference', 'metric': 'cells/sec fwd+bwd ZINC ring-lifted CWN', 'value': value, 'unit': 'cells/s',
+        'n_gpus': args.gpus, 'steps': done, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'cells_per_step': cells, 'step': 'fwd+loss+bwd+adam'},
+        'cpu_baseline': {'value': value, 'unit': 'cells/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'{done} full steps of the same workload (batch {args.batch}) through the '
+                                   f'torch-only oracle; the reference cannot be imported (torch_scatter, '
+                                   f'torch_geometric, torch_sparse absent)'},
+        'e2e': {'value': value, 'unit': 'cells/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
+                                          '-i', str(self.gpu), '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 9 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) >= 9 and r[2].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        return json.load(open(path))['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md: 6.65 TB/s)'
+
+
+def kernel_sweep(dev):
+    """BASELINE config 5, one point: block-diagonal edge-upper adjacency at 1M edges/dim, F=64 — the regime where
+    the HBM roofline is the bound. Algorithmic bytes per SURVEY 8(d)."""
+    from cwn_b200 import ops
+    from cwn_b200.data import synthetic
+    peak, _ = peaks()
+    out = []
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    for kind, F in [('edge_up', 64), ('edge_boundary', 64), ('edge_up', 256)]:
+        index, cob, n_src, n_dst, n_cob = synthetic.tiled_adjacency(kind, 40_000)
+        index = index.to(dev)
+        x = torch.randn(n_src, F, device=dev)
+        ops.gather_scatter(x, index, n_dst)  # builds the plan
+        ms = []
+        for _ in range(5):
+            flush.zero_()
+            with ops.KernelProfile() as prof:
+                ops.gather_scatter(x, index, n_dst)
+            rec = prof.summary()['csr_gather_reduce']
+            ms.append(rec['ms'])
+        t = sorted(ms)[len(ms) // 2]
+        gbs = rec['bytes'] / (t * 1e-3) / 1e9
+        out.append({'kernel': 'csr_gather_reduce', 'adjacency': kind, 'F': F, 'cells': n_dst, 'messages': index.size(1),
+                    'ms': t, 'algorithmic_GBps': gbs, 'frac_of_peak': gbs / peak})
+        if cob is not None and F == 64:
+            cob = cob.to(dev)
+            P, Q = torch.randn(n_src, F, device=dev, requires_grad=True), torch.randn(n_cob, F, device=dev, requires_grad=True)
+            o = ops.cob_pass(P, Q, index, cob, n_dst)
+            o.sum().backward()
+            g = torch.randn_like(o)
+            for name in ('csr_cob_fwd', 'csr_cob_bwd'):
+                ms = []
+                for _ in range(5):
+                    P.grad = Q.grad = None
+                    flush.zero_()
+                    with ops.KernelProfile() as prof:
+                        o = ops.cob_pass(P, Q, index, cob, n_dst)
+                        o.backward(g)
+                    rec = prof.summary()[name]
+                    ms.append(rec['ms'] / rec['launches'])
+                t = sorted(ms)[len(ms) // 2]
+                gbs = rec['bytes'] / rec['launches'] / (t * 1e-3) / 1e9
+                out.append({'kernel': name, 'adjacency': kind, 'F': F, 'cells': n_dst, 'messages': index.size(1),
+                            'ms': t, 'algorithmic_GBps': gbs, 'frac_of_peak': gbs / peak})
+    return out
+
+
+def run_cwn(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from cwn_b200 import _lib, ops
+    from cwn_b200.dist import FlatGradBucket, broadcast_parameters
+    from cwn_b200.mp.molec_models import EmbedSparseCIN
+
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py: no CUDA device; the cwn_b200 path is CUDA-only (use --impl reference for the CPU arm)')
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    _lib.load()
+    torch.manual_seed(0)
+    model = EmbedSparseCIN(**MODEL_CFG).to(dev).train()
+    broadcast_parameters(model)
+    bucket = FlatGradBucket(model)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+
+    host_batches = make_batches(args.pool, args.batch, seed0=1000 + 100 * rank)
+    cells = cells_of(host_batches[0])
+    dev_batches = [b.to(dev) for b in make_batches(args.pool, args.batch, seed0=1000 + 100 * rank)]
+    index_tensors = [[t for d in range(3) for t in (b.cochains[d].upper_index, b.cochains[d].boundary_index,
+                                                    b.cochains[d].batch)] for b in dev_batches]
+    inputs = [[b.cochains[d].x for d in range(3)] for b in dev_batches]
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2
+
+    def step(batch):
+        bucket.zero()
+        out = model(batch)
+        loss = l1(out, batch.y)
+        loss.backward()
+        bucket.all_reduce()
+        opt.step()
+        return loss
+
+    def resident_step(i):
+        b = dev_batches[i % args.pool]
+        ops.clear_plan_cache(*index_tensors[i % args.pool])  # every step is a new batch: plans are rebuilt
+        for d, x in enumerate(inputs[i % args.pool]):         # the forward overwrites cochain.x (set_xs): restore
+            b.cochains[d]._x = x
+        return step(b)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for i in range(max(args.warmup, 3)):
+        resident_step(i)
+    barrier()
+
+    # ---- timed region: device-resident inputs
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = _lib.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        resident_step(i)
+        ev[i][1].record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    ms_total = sum(a.elapsed_time(b) for a, b in ev)
+    clock_info = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = cells * world / (ms_step / 1e3)
+
+    # ---- e2e: host batch -> device -> step -> loss back, every step
+    for i in range(3):
+        hb = make_host_copy(host_batches[i % args.pool])
+        float(step(hb.to(dev)).item())
+    barrier()
+    e2e_ms, h2d = 0.0, 0
+    for i in range(args.steps):
+        hb = make_host_copy(host_batches[i % args.pool])
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        db = hb.to(dev)
+        loss_value = float(step(db).item())
+        e2e_ms += 1e3 * (time.perf_counter() - t0)
+        h2d = db._h2d_bytes
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = cells * world / (float(t.item()) / args.steps / 1e3)
+
+    if rank != 0:
+        return
+    # ---- per-kernel roofline of the step (instrumented re-run of the same steps)
+    with ops.KernelProfile() as prof:
+        for i in range(args.steps):
+            flush.zero_()
+            resident_step(i)
+    summary = prof.summary()
+    peak, peak_src = peaks()
+    dom = max((k for k in summary if k != 'csr_plan_build'), key=lambda k: summary[k]['ms'])
+    rec = summary[dom]
+    achieved = rec['bytes'] / (rec['ms'] * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'launches_per_step': rec['launches'] / args.steps,
+                'avg_launch_us': 1e3 * rec['ms'] / rec['launches'],
+                'algorithmic_bytes_per_launch': rec['bytes'] / rec['launches'],
+                'kernel_ms_per_step': {k: v['ms'] / args.steps for k, v in summary.items()},
+                'note': 'at batch 128 every adjacency pass moves ~1-2 MB (L2-resident): the step is launch/latency '
+                        'bound, see kernel_sweep for the HBM-bound regime'}
+    line = {
+        'metric': 'cells/sec fwd+bwd ZINC ring-lifted CWN', 'value': value, 'unit': 'cells/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'cells_per_step_per_gpu': cells, 'global_batch': args.batch * world,
+                   'parallelism': f'dp{world}', 'step': 'plans+fwd+loss+bwd+allreduce+adam', 'mode': 'eager',
+                   'l2': 'flushed (256 MB write) between timed steps', 'last_loss': loss_value},
+        'clocks': clock_info, 'gpu_launches': int(launches),
+        'e2e': {'value': e2e_value, 'unit': 'cells/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 4},
+        'roofline': roofline,
+    }
+    if not args.no_sweep:
+        line['kernel_sweep'] = kernel_sweep(dev)
+    if not args.no_cpu_baseline:
+        v, ms, done, _ = cpu_steps(10, 2, args.batch, budget_s=20.0)
+        line['cpu_baseline'] = {'value': v, 'unit': 'cells/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                                'ms_per_step': ms,
+                                'sample': f'{done} full steps of the same workload through the torch-only oracle'}
+    print(json.dumps(line), flush=True)
+
+
+def make_host_copy(batch):
+    """Fresh host-side ComplexBatch sharing the (CPU) tensors of `batch` (`.to()` rebinds attributes in place)."""
+    import copy
+    new = copy.copy(batch)
+    new.cochains = {d: copy.copy(c) for d, c in batch.cochains.items()}
+    return new
+
+
+def main():
+    args = parse()
+    from cwn_b200.dist import init_from_env
+    if args.impl == 'reference':
+        rank = int(os.environ.get('RANK', '0'))
+        run_reference(args, rank)
+        return
+    rank, world, local_rank = init_from_env()
+    run_cwn(args, rank, world, local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

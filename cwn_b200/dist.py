@@ -1,0 +1,97 @@
+"""Data-parallel plumbing around the hot path (the reference has none: single process, single device,
+`exp/run_exp.py:22-23`).
+
+Complexes never exchange messages (block-diagonal adjacency, `data/complex.py:148-169`), so the only collective is
+the gradient all-reduce: one process per GPU, each with its own batch of complexes and its own CSR plans, the
+model replicated. All gradients live in ONE flat fp32 bucket (every `param.grad` is a view into it, so backward
+writes straight into the bucket) that is all-reduced with a single NCCL call over NVLink/NVSwitch — ~1.7 MB at
+hidden 64 / 4 layers, i.e. latency-bound; bucketing for bandwidth would be pointless.
+
+BatchNorm statistics stay per-rank (shard-local), exactly like running the reference on each shard; numerical
+equality with a single-process run on the union batch therefore holds for `graph_norm='id'`/'ln' or in eval mode,
+and that is what the multi-process tests check.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from torchrun's env (RANK, WORLD_SIZE, MASTER_ADDR, MASTER_PORT).
+    Returns (rank, world_size, local_rank). World size 1 without env => no process group."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if backend is None:
+            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        kwargs = {}
+        if backend == 'nccl':
+            torch.cuda.set_device(local_rank)
+            kwargs['device_id'] = torch.device('cuda', local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kwargs)
+    return rank, world, local_rank
+
+
+class FlatGradBucket(object):
+    """All gradients of a module in one contiguous buffer; `all_reduce()` averages it across ranks in one call."""
+
+    def __init__(self, module: torch.nn.Module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        if not self.params:
+            raise ValueError('module has no trainable parameters')
+        dev, dtype = self.params[0].device, self.params[0].dtype
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=dtype, device=dev)
+        off = 0
+        for p in self.params:
+            if p.device != dev or p.dtype != dtype:
+                raise ValueError('FlatGradBucket needs all parameters on one device with one dtype')
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce(self, async_op=False):
+        """Average over ranks (sum then / world_size). No-op without a process group."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return None
+        world = dist.get_world_size()
+        if dist.get_backend() == 'nccl':
+            return dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, async_op=async_op)
+        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
+        if async_op:
+            work.wait()
+        self.flat.div_(world)
+        return None
+
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0):
+    """Make every rank start from rank `src`'s weights and buffers."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src)
+
+
+def shard(items, rank: int, world: int):
+    """Contiguous shard of a list of complexes for `rank` (independent units, no halo)."""
+    per = (len(items) + world - 1) // world
+    return items[rank * per:(rank + 1) * per]
+
+
+def train_step(model, batch, loss_fn, bucket: FlatGradBucket, optimizer=None):
+    """One data-parallel step: zero bucket -> forward -> loss -> backward -> all-reduce -> optimizer.
+    DDP-aware twin of the inner loop of the reference's `train()` (`exp/train_utils.py:57-72`), minus its
+    per-step `loss.item()` host sync."""
+    bucket.zero()
+    out = model(batch)
+    loss = loss_fn(out, batch.y)
+    loss.backward()
+    bucket.all_reduce()
+    if optimizer is not None:
+        optimizer.step()
+    return loss

@@ -245,6 +245,12 @@ class CochainMessagePassing(torch.nn.Module):
             out = fused(index, size, kwargs)
             if out is not NotImplemented:
                 return out
+        for key, param in self.inspector.params[f'message_{adjacency}'].items():
+            # fail on a never-passed plain hook argument BEFORE any gather is launched (same TypeError as the
+            # reference's Inspector.distribute)
+            if key[-2:] not in ('_i', '_j') and key not in kwargs and key not in self.special_args \
+                    and param.default is _EMPTY:
+                raise TypeError(f'Required parameter {key} is empty.')
         coll_dict = self.__collect__(self.__user_args__, index, size, adjacency, kwargs)
         msg_kwargs = self.inspector.distribute(f'message_{adjacency}', coll_dict)
         out = self.get_msg_func(adjacency)(**msg_kwargs)

@@ -50,6 +50,49 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# --------------------------------------------------------------------------------------------- per-kernel timing
+class KernelProfile(object):
+    """CUDA-event timing of every C-ABI launch made while active (bench.py's roofline leg). Events are recorded on
+    the launching stream right around the launch; `summary()` synchronises once at the end."""
+
+    def __init__(self):
+        self.records = []  # (kernel name, algorithmic bytes, start event, stop event)
+
+    def __enter__(self):
+        global _profile
+        _profile = self
+        return self
+
+    def __exit__(self, *exc):
+        global _profile
+        _profile = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, nbytes, e0, e1 in self.records:
+            rec = out.setdefault(name, {'launches': 0, 'ms': 0.0, 'bytes': 0})
+            rec['launches'] += 1
+            rec['ms'] += e0.elapsed_time(e1)
+            rec['bytes'] += nbytes
+        return out
+
+
+_profile = None
+
+
+def _call(name, algo_bytes, fn, *args):
+    """Invoke one C-ABI entry point, timing it when a KernelProfile is active."""
+    if _profile is None:
+        _lib.check(fn(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.check(fn(*args), name)
+    e1.record()
+    _profile.records.append((name, algo_bytes, e0, e1))
+
+
 # --------------------------------------------------------------------------------------------- CSR plans
 class Plan(object):
     """Messages grouped (stably) by one index column: `rowptr[n_rows+1]`, `perm[E]`, up to two payload columns."""
@@ -78,9 +121,10 @@ def build_plan(key: Tensor, n_rows: int, pay0: Tensor = None, pay1: Tensor = Non
         p1 = torch.empty(E, dtype=torch.int32, device=dev) if pay1 is not None else None
         ws_bytes = lib.cwn_csr_plan_workspace_bytes(E, n_rows)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        _lib.check(lib.cwn_csr_plan_build(_ptr(key), _ptr(pay0), _ptr(pay1), E, n_rows, rowptr.data_ptr(),
-                                          _ptr(perm), _ptr(p0), _ptr(p1), None, ws.data_ptr(), ws_bytes,
-                                          _stream()), 'csr_plan_build')
+        npay = (pay0 is not None) + (pay1 is not None)
+        _call('csr_plan_build', 8 * E * (1 + npay) + 4 * E * (1 + npay) + 4 * (n_rows + 1),
+              lib.cwn_csr_plan_build, _ptr(key), _ptr(pay0), _ptr(pay1), E, n_rows, rowptr.data_ptr(), _ptr(perm),
+              _ptr(p0), _ptr(p1), None, ws.data_ptr(), ws_bytes, _stream())
     return Plan(rowptr, perm, p0, p1, n_rows, E)
 
 
@@ -102,11 +146,13 @@ class Adjacency(object):
     @classmethod
     def of(cls, index: Tensor, n_src: int, n_dst: int, cob: Tensor = None, n_cob: int = None):
         cache = index.__dict__.setdefault('_cwn_adj', {})
-        k = (int(n_src), int(n_dst), None if cob is None else (cob.data_ptr(), cob._version), n_cob,
-             index._version, index.data_ptr())
+        gen = (index._version, index.data_ptr())
+        if cache.get('gen') != gen:  # first use, or the index was modified in place: drop stale plans
+            cache.clear()
+            cache['gen'] = gen
+        k = (int(n_src), int(n_dst), None if cob is None else (cob.data_ptr(), cob._version), n_cob)
         adj = cache.get(k)
         if adj is None:
-            cache.clear()  # stale plans of an index that was modified in place
             adj = cache[k] = cls(index, n_src, n_dst, cob, n_cob)
             adj._plans = {}
         return adj
@@ -133,18 +179,23 @@ def clear_plan_cache(*indices):
     for idx in indices:
         if idx is not None:
             idx.__dict__.pop('_cwn_adj', None)
+            idx.__dict__.pop('_cwn_rowplan', None)
 
 
 # --------------------------------------------------------------------------------------------- raw launches
 def _launch_gather_reduce(x_src, plan_rowptr, idx, n_rows, F, x_res, eps, reduce_code):
+    """Algorithmic bytes: 16 B of int64 index per message + one read of every source row + one write
+    of every destination row (+ one read of the residual rows when fused)."""
     lib = _lib.load()
     dev = plan_rowptr.device
+    E = idx.numel() if idx is not None else (x_src.size(0) if x_src is not None else 0)
+    n_src = x_src.size(0) if x_src is not None else 0
+    algo = 16 * E + 4 * F * (n_src + n_rows + (n_rows if x_res is not None else 0))
     with torch.cuda.device(dev):
         out = torch.empty(n_rows, F, dtype=torch.float32, device=dev)
-        _lib.check(lib.cwn_csr_gather_reduce_f32(
-            _ptr(x_src), _ld(x_src) if x_src is not None else F, plan_rowptr.data_ptr(), _ptr(idx), n_rows, F,
-            _ptr(x_res), _ld(x_res) if x_res is not None else F, _ptr(eps), _ptr(out), F, reduce_code,
-            _stream()), 'csr_gather_reduce')
+        _call('csr_gather_reduce', algo, lib.cwn_csr_gather_reduce_f32,
+              _ptr(x_src), _ld(x_src) if x_src is not None else F, plan_rowptr.data_ptr(), _ptr(idx), n_rows, F,
+              _ptr(x_res), _ld(x_res) if x_res is not None else F, _ptr(eps), _ptr(out), F, reduce_code, _stream())
     return out
 
 
@@ -153,8 +204,8 @@ def _launch_gather_rows(x, idx, scale):
     E, F = idx.numel(), x.size(1)
     with torch.cuda.device(x.device):
         out = torch.empty(E, F, dtype=torch.float32, device=x.device)
-        _lib.check(lib.cwn_gather_rows_f32(_ptr(x), _ld(x), _ptr(idx), E, F, float(scale), _ptr(out), F,
-                                           _stream()), 'gather_rows')
+        _call('gather_rows', 8 * E + 4 * F * (x.size(0) + E), lib.cwn_gather_rows_f32,
+              _ptr(x), _ld(x), _ptr(idx), E, F, float(scale), _ptr(out), F, _stream())
     return out
 
 
@@ -222,10 +273,11 @@ class _CobPass(Function):
         F = P.size(1)
         with torch.cuda.device(P.device):
             out = torch.empty(adj.n_dst, F, dtype=torch.float32, device=P.device)
-            _lib.check(lib.cwn_csr_cob_fwd_f32(
-                _ptr(P), _ld(P), _ptr(Q), _ld(Q), plan.rowptr.data_ptr(), _ptr(plan.pay0), _ptr(plan.pay1),
-                adj.n_dst, F, ACT_CODES[act], _ptr(x_res), _ld(x_res) if x_res is not None else F, _ptr(eps),
-                _ptr(out), F, _stream()), 'csr_cob_fwd')
+            algo = 24 * adj.E + 4 * F * (P.size(0) + Q.size(0) + adj.n_dst * (2 if x_res is not None else 1))
+            _call('csr_cob_fwd', algo, lib.cwn_csr_cob_fwd_f32,
+                  _ptr(P), _ld(P), _ptr(Q), _ld(Q), plan.rowptr.data_ptr(), _ptr(plan.pay0), _ptr(plan.pay1),
+                  adj.n_dst, F, ACT_CODES[act], _ptr(x_res), _ld(x_res) if x_res is not None else F, _ptr(eps),
+                  _ptr(out), F, _stream())
         ctx.adj, ctx.act = adj, act
         ctx.has_res = x_res is not None
         ctx.save_for_backward(P, Q, x_res if (eps is not None and eps.requires_grad) else None, eps)
@@ -243,15 +295,17 @@ class _CobPass(Function):
             if ctx.needs_input_grad[0]:
                 plan = adj.by_src
                 gP = torch.empty_like(P, memory_format=torch.contiguous_format)
-                _lib.check(lib.cwn_csr_cob_bwd_f32(
-                    _ptr(g), _ld(g), _ptr(P), _ld(P), _ptr(Q), _ld(Q), plan.rowptr.data_ptr(), _ptr(plan.pay0),
-                    _ptr(plan.pay1), adj.n_src, F, act, _ptr(gP), F, _stream()), 'csr_cob_bwd(P)')
+                algo = 24 * adj.E + 4 * F * (g.size(0) + 2 * P.size(0) + Q.size(0))
+                _call('csr_cob_bwd', algo, lib.cwn_csr_cob_bwd_f32,
+                      _ptr(g), _ld(g), _ptr(P), _ld(P), _ptr(Q), _ld(Q), plan.rowptr.data_ptr(), _ptr(plan.pay0),
+                      _ptr(plan.pay1), adj.n_src, F, act, _ptr(gP), F, _stream())
             if ctx.needs_input_grad[1]:
                 plan = adj.by_cob
                 gQ = torch.empty_like(Q, memory_format=torch.contiguous_format)
-                _lib.check(lib.cwn_csr_cob_bwd_f32(
-                    _ptr(g), _ld(g), _ptr(Q), _ld(Q), _ptr(P), _ld(P), plan.rowptr.data_ptr(), _ptr(plan.pay0),
-                    _ptr(plan.pay1), adj.n_cob, F, act, _ptr(gQ), F, _stream()), 'csr_cob_bwd(Q)')
+                algo = 24 * adj.E + 4 * F * (g.size(0) + 2 * Q.size(0) + P.size(0))
+                _call('csr_cob_bwd', algo, lib.cwn_csr_cob_bwd_f32,
+                      _ptr(g), _ld(g), _ptr(Q), _ld(Q), _ptr(P), _ld(P), plan.rowptr.data_ptr(), _ptr(plan.pay0),
+                      _ptr(plan.pay1), adj.n_cob, F, act, _ptr(gQ), F, _stream())
         g_res = g_eps = None
         if ctx.has_res:
             g_res, g_eps = _eps_grad(ctx.needs_input_grad[2:4], g, x_res, eps)

@@ -1,0 +1,114 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports every symbol include/cwn_b200.h declares; the
+operator API refuses non-CUDA tensors (no CPU fallback); host-side hook bookkeeping mirrors the reference."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from cwn_b200 import _lib, ops
+from cwn_b200.mp.cell_mp import CochainMessagePassing
+from cwn_b200.mp.layers import CINConv, DummyCochainMessagePassing, SparseCINConv, SparseCINCochainConv
+from cwn_b200.mp.models import CIN0, SparseCIN
+from cwn_b200.mp.molec_models import EmbedSparseCIN, OGBEmbedSparseCIN
+from helpers import fixture, golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'cwn_b200.h')).read()
+    declared = set(re.findall(r'\b(cwn_[a-z0-9_]+)\s*\(', header))
+    assert declared, 'no declarations found'
+    lib = ctypes.CDLL(_lib.load()._name)
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/cwn_b200.h but not exported'
+    assert declared == set(_lib.exported_symbols())
+    assert b'sm_100a' in _lib.load().cwn_version()
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    lib = _lib.load()
+    assert lib.cwn_csr_gather_reduce_f32(None, 4, None, None, -1, 4, None, 4, None, None, 4, 0, None) == -2
+    assert lib.cwn_csr_gather_reduce_f32(None, 4, None, None, 3, 4, None, 4, None, None, 4, 9, None) == -3
+    assert lib.cwn_csr_gather_reduce_f32(None, 4, None, None, 3, 4, None, 4, None, None, 4, 0, None) == -1
+    assert b'rowptr' in lib.cwn_last_error_string()
+    assert lib.cwn_csr_cob_fwd_f32(None, 4, None, 4, None, None, None, 3, 4, 77, None, 4, None, None, 4, None) == -3
+    assert lib.cwn_csr_plan_workspace_bytes(1000, 10) >= 3 * 4000
+    with pytest.raises(ValueError):
+        _lib.check(-2, 'x')
+    with pytest.raises(RuntimeError):
+        _lib.check(700, 'x')
+
+
+def test_no_cpu_fallback():
+    house = fixture('house')
+    p = house.get_cochain_params(dim=1)
+    cmp = CochainMessagePassing(up_msg_size=1, down_msg_size=1)
+    with pytest.raises(RuntimeError, match='CUDA-only'):
+        cmp.propagate(p.up_index, p.down_index, p.boundary_index, x=p.x, up_attr=p.kwargs['up_attr'],
+                      down_attr=p.kwargs['down_attr'], boundary_attr=p.kwargs['boundary_attr'])
+    with pytest.raises(RuntimeError, match='CUDA-only'):
+        ops.gather_scatter(p.x, p.up_index, 6)
+    with pytest.raises(RuntimeError):
+        ops.scatter_rows(torch.ones(3, 2), torch.tensor([0, 1, 0]), 2)
+    with pytest.raises(RuntimeError):
+        ops.build_plan(torch.tensor([0, 1]), 2)
+    model = SparseCIN(1, 3, 2, 5)
+    from cwn_b200.data.complex import ComplexBatch
+    with pytest.raises(RuntimeError, match='CUDA-only'):
+        model.eval()(ComplexBatch.from_complex_list([fixture('house'), fixture('kite')]))
+
+
+def test_propagate_input_checks_match_reference():  # mp/cell_mp.py:153-193
+    cmp = CochainMessagePassing(1, 1)
+    x = torch.ones(3, 1)
+    with pytest.raises(AssertionError):
+        cmp.propagate(torch.zeros(2, 2, dtype=torch.int32), None, None, x=x, up_attr=None)
+    with pytest.raises(AssertionError):
+        cmp.propagate(torch.zeros(3, 2, dtype=torch.long), None, None, x=x, up_attr=None)
+    with pytest.raises(ValueError):
+        cmp.propagate('nope', None, None, x=x, up_attr=None)
+    with pytest.raises(ValueError, match='expected size'):
+        cmp.propagate(torch.zeros(2, 2, dtype=torch.long), None, None, up_size=(7, 7), x=x, up_attr=None)
+    with pytest.raises(TypeError, match='up_attr'):  # hook argument never passed (Inspector.distribute)
+        cmp.propagate(torch.zeros(2, 2, dtype=torch.long), None, None, x=x)
+    # no adjacency at all: update() fabricates zeros of the configured message sizes (mp/cell_mp.py:511-524)
+    cmp = CochainMessagePassing(up_msg_size=4, down_msg_size=2, boundary_msg_size=3)
+    up, down, bnd = cmp.propagate(None, None, None, x=x)
+    assert (up.shape, down.shape, bnd.shape) == ((3, 4), (3, 2), (3, 3)) and float(up.abs().sum()) == 0
+
+
+def test_hook_bookkeeping():
+    base = CochainMessagePassing(1, 1)
+    assert base._default_hooks == {'up': True, 'down': True, 'boundary': True}
+    assert base.__user_args__ == {'up_x_j', 'up_attr', 'down_x_j', 'down_attr', 'boundary_x_j'}
+    assert base.__update_user_args__ == {'x'}
+    assert not (base.fuse_up or base.fuse_down or base.fuse_boundary)
+    dummy = DummyCochainMessagePassing(1, 1)
+    assert dummy._default_hooks == {'up': False, 'down': False, 'boundary': True}
+    assert base.boundary_msg_size == 1 and CochainMessagePassing(2, 5).boundary_msg_size == 5
+    with pytest.raises(AssertionError):
+        CochainMessagePassing(1, 1, aggr_up='median')
+
+
+def test_module_structure_loads_reference_state_dicts():
+    """Parameter names/shapes equal the reference's (golden state_dicts were saved by reference models)."""
+    from cwn_b200.mp.nn import get_graph_norm
+    for name, klass in [('sparse_cin_eval', SparseCIN), ('sparse_cin_eval_dim1', SparseCIN),
+                        ('embed_sparse_cin_eval', EmbedSparseCIN), ('cin0_eval', CIN0),
+                        ('sparse_cin_train', SparseCIN), ('embed_sparse_cin_train', EmbedSparseCIN),
+                        ('embed_sparse_cin_train_nocob', EmbedSparseCIN),
+                        ('ogb_embed_sparse_cin_train', OGBEmbedSparseCIN), ('cin0_train', CIN0)]:
+        m = golden()['models'][name]
+        model = klass(**m['cfg'])
+        missing, unexpected = model.load_state_dict(m['state_dict'], strict=True)
+        assert not missing and not unexpected
+    conv = SparseCINConv(4, 4, 4, None, None, None, None, layer_dim=4, hidden=8, act_module=torch.nn.ReLU,
+                         use_coboundaries=True, train_eps=True)
+    assert isinstance(conv.mp_levels[0], SparseCINCochainConv) and len(conv.mp_levels) == 3
+    assert conv.mp_levels[1]._up_message_form()[0] == 'cob' and isinstance(conv.mp_levels[0].eps1, torch.nn.Parameter)
+    shared = CIN0(1, 3, 2, 5).convs[0]
+    assert isinstance(shared, CINConv)
+    assert shared.mp_levels[0].msg_up_nn is shared.mp_levels[2].msg_up_nn  # weights shared across dimensions

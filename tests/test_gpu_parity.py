@@ -1,0 +1,444 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle, the reference's known answers and the golden
+vectors recorded from the reference. Integer / index work must be bit-exact; fp32 features must agree within
+rtol 1e-5 (+ atol 1e-5 scaled to the data, stated per test) as BASELINE.json's north_star requires."""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+import cwn_oracle as O
+from cwn_b200 import ops
+from cwn_b200.data import synthetic
+from cwn_b200.data.complex import ComplexBatch
+from cwn_b200.mp.cell_mp import CochainMessagePassing
+from cwn_b200.mp.layers import DummyCellularMessagePassing, InitReduceConv
+from cwn_b200.mp.models import CIN0, SparseCIN
+from cwn_b200.mp.molec_models import EmbedSparseCIN, OGBEmbedSparseCIN
+from helpers import assert_close, batch_of, fixture, golden, oracle_state, share_cin0_levels
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def T(v):
+    return torch.tensor(v, dtype=torch.float).view(-1, 1)
+
+
+def _rand_adj(n_src, n_dst, E, seed, n_cob=0):
+    g = torch.Generator().manual_seed(seed)
+    idx = torch.stack([torch.randint(0, n_src, (E,), generator=g), torch.randint(0, n_dst, (E,), generator=g)])
+    cob = torch.randint(0, n_cob, (E,), generator=g) if n_cob else None
+    return idx, cob
+
+
+# ------------------------------------------------------------------------------------------------ plans
+@pytest.mark.parametrize('E,n_rows', [(0, 5), (1, 1), (17, 4), (1000, 37), (50_000, 70_000), (300_000, 9)])
+def test_csr_plan_is_a_stable_sort(E, n_rows):
+    g = torch.Generator().manual_seed(E + n_rows)
+    key = torch.randint(0, n_rows, (E,), generator=g)
+    pay = torch.randint(0, 1 << 20, (E,), generator=g)
+    plan = ops.build_plan(key.to(DEV), n_rows, pay.to(DEV))
+    order = torch.sort(key, stable=True)[1]
+    counts = torch.bincount(key, minlength=n_rows)
+    rowptr = torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)])
+    assert torch.equal(plan.rowptr.cpu().long(), rowptr)
+    assert torch.equal(plan.perm.cpu().long(), order)
+    assert torch.equal(plan.pay0.cpu().long(), pay[order])
+
+
+# ------------------------------------------------------------------------------------------------ fused identity pass
+@pytest.mark.parametrize('F', [1, 3, 4, 16, 20, 64, 100, 128, 256, 520])
+@pytest.mark.parametrize('reduce', ['add', 'mean', 'max'])
+def test_gather_scatter_forward_matches_oracle(F, reduce):
+    n_src, n_dst, E = 301, 257, 2000
+    idx, _ = _rand_adj(n_src, n_dst - 7, E, F)  # last 7 destinations receive nothing -> zero rows
+    x = torch.randn(n_src, F)
+    ref = O.scatter(x.index_select(0, idx[0]), idx[1], n_dst, reduce)
+    out = ops.gather_scatter(x.to(DEV), idx.to(DEV), n_dst, reduce)
+    assert_close(out, ref, rtol=1e-5, atol=1e-5, what=f'{reduce} F={F}')
+    assert float(out[-7:].abs().sum()) == 0.0
+
+
+def test_gather_scatter_is_bit_exact_with_sequential_cpu_scatter_add():
+    """Stable plan + in-row sequential accumulation == a sequential scatter_add_ in message order, bit for bit."""
+    n_src, n_dst, E, F = 500, 100, 5000, 64
+    idx, _ = _rand_adj(n_src, n_dst, E, 1)
+    x = torch.randn(n_src, F) * 100
+    ref = np.zeros((n_dst, F), dtype=np.float32)
+    np.add.at(ref, idx[1].numpy(), x.numpy()[idx[0].numpy()])  # unbuffered, in order
+    out = ops.gather_scatter(x.to(DEV), idx.to(DEV), n_dst)
+    assert torch.equal(out.cpu(), torch.from_numpy(ref))
+    # and it does not depend on where the rows sit in memory (strided source)
+    wide = torch.zeros(n_src, F + 8, device=DEV)
+    wide[:, 4:F + 4] = x.to(DEV)
+    assert torch.equal(ops.gather_scatter(wide[:, 4:F + 4], idx.to(DEV), n_dst).cpu(), torch.from_numpy(ref))
+
+
+@pytest.mark.parametrize('F', [1, 5, 64, 256])
+@pytest.mark.parametrize('reduce', ['add', 'mean'])
+def test_gather_scatter_backward_matches_autograd_of_oracle(F, reduce):
+    n_src, n_dst, E = 120, 90, 700
+    idx, _ = _rand_adj(n_src, n_dst, E, 7 + F)
+    x = torch.randn(n_src, F, requires_grad=True)
+    res = torch.randn(n_dst, F, requires_grad=True)
+    eps = torch.tensor([0.25], requires_grad=True)
+    w = torch.randn(n_dst, F)
+    ref = O.scatter(x.index_select(0, idx[0]), idx[1], n_dst, reduce)
+    if reduce == 'add':
+        ref = ref + (1 + eps) * res
+    (ref * w).sum().backward()
+    xg, rg, eg = (t.detach().to(DEV).requires_grad_(True) for t in (x, res, eps))
+    out = ops.gather_scatter(xg, idx.to(DEV), n_dst, reduce, x_res=rg if reduce == 'add' else None,
+                             eps=eg if reduce == 'add' else None)
+    assert_close(out, ref, what='fwd')
+    (out * w.to(DEV)).sum().backward()
+    assert_close(xg.grad, x.grad, rtol=1e-5, atol=1e-5, what='grad x')
+    if reduce == 'add':
+        assert_close(rg.grad, res.grad, what='grad residual')
+        assert_close(eg.grad, eps.grad, rtol=1e-4, atol=1e-4, what='grad eps')
+
+
+def test_empty_and_degenerate_adjacencies():
+    x = torch.randn(6, 8, device=DEV)
+    empty = torch.zeros(2, 0, dtype=torch.long, device=DEV)
+    assert torch.equal(ops.gather_scatter(x, empty, 6), torch.zeros(6, 8, device=DEV))
+    xr = x.clone().requires_grad_(True)
+    out = ops.gather_scatter(xr, empty, 4)
+    out.sum().backward()
+    assert float(xr.grad.abs().sum()) == 0.0
+    one = torch.tensor([[5], [0]], device=DEV)
+    assert torch.equal(ops.gather_scatter(x, one, 2)[0], x[5])
+    assert ops.scatter_rows(torch.zeros(0, 8, device=DEV), torch.zeros(0, dtype=torch.long, device=DEV), 3).shape == (3, 8)
+
+
+# ------------------------------------------------------------------------------------------------ coboundary pass
+@pytest.mark.parametrize('act', ['relu', 'elu', 'id', 'sigmoid', 'tanh'])
+@pytest.mark.parametrize('F', [4, 64, 72])
+def test_cob_pass_forward_backward(act, F):
+    n, n_cob, E = 150, 40, 900
+    idx, cob = _rand_adj(n, n, E, 3 + F, n_cob)
+    fn = O._ACT[act]
+    P = torch.randn(n, F, requires_grad=True)
+    Q = torch.randn(n_cob, F, requires_grad=True)
+    res = torch.randn(n, F, requires_grad=True)
+    eps = torch.tensor([0.5])
+    w = torch.randn(n, F)
+    ref = O.scatter(fn(P.index_select(0, idx[0]) + Q.index_select(0, cob)), idx[1], n) + (1 + eps) * res
+    (ref * w).sum().backward()
+    Pg, Qg, rg = (t.detach().to(DEV).requires_grad_(True) for t in (P, Q, res))
+    out = ops.cob_pass(Pg, Qg, idx.to(DEV), cob.to(DEV), n, act=act, x_res=rg, eps=eps.to(DEV))
+    assert_close(out, ref, rtol=1e-5, atol=1e-5, what='fwd')
+    (out * w.to(DEV)).sum().backward()
+    assert_close(Pg.grad, P.grad, rtol=1e-5, atol=2e-5, what='grad P')
+    assert_close(Qg.grad, Q.grad, rtol=1e-5, atol=2e-5, what='grad Q')
+    assert_close(rg.grad, res.grad, what='grad res')
+
+
+def test_split_weight_form_equals_per_message_linear():
+    """act(W [x_j ; y_c] + b) summed per destination == the split form the kernel evaluates (fp32, rtol 1e-5)."""
+    n, n_cob, E, F = 300, 80, 2500, 64
+    idx, cob = _rand_adj(n, n, E, 11, n_cob)
+    x, y = torch.randn(n, F), torch.randn(n_cob, F)
+    lin = torch.nn.Linear(2 * F, F)
+    with torch.no_grad():
+        ref = O.scatter(torch.relu(lin(torch.cat([x[idx[0]], y[cob]], -1))), idx[1], n)
+        W, b = lin.weight.to(DEV), lin.bias.to(DEV)
+        P = torch.nn.functional.linear(x.to(DEV), W[:, :F])
+        Q = torch.nn.functional.linear(y.to(DEV), W[:, F:], b)
+        out = ops.cob_pass(P, Q, idx.to(DEV), cob.to(DEV), n, act='relu')
+    assert_close(out, ref, rtol=1e-5, atol=2e-5, what='split weights')
+
+
+# ------------------------------------------------------------------------------------------------ rows / readout
+def test_gather_rows_scatter_rows_pool():
+    n, E, F, B = 200, 1500, 48, 17
+    g = torch.Generator().manual_seed(5)
+    idx = torch.randint(0, n, (E,), generator=g)
+    x = torch.randn(n, F, requires_grad=True)
+    w = torch.randn(E, F)
+    (x.index_select(0, idx) * w).sum().backward()
+    xg = x.detach().to(DEV).requires_grad_(True)
+    out = ops.gather_rows(xg, idx.to(DEV))
+    assert torch.equal(out.cpu(), x.detach()[idx])
+    (out * w.to(DEV)).sum().backward()
+    assert_close(xg.grad, x.grad, what='gather_rows backward')
+    batch = torch.sort(torch.randint(0, B - 2, (n,), generator=g))[0]  # sorted, complexes B-2.. are empty
+    for mean in (False, True):
+        ref = O.scatter(x.detach(), batch, B, 'mean' if mean else 'add')
+        assert_close(ops.segment_pool(x.detach().to(DEV), batch.to(DEV), B, mean=mean), ref, what='pool')
+    msg = torch.randn(E, F, requires_grad=True)
+    w2 = torch.randn(n, F)
+    (O.scatter(msg, idx, n, 'mean') * w2).sum().backward()
+    mg = msg.detach().to(DEV).requires_grad_(True)
+    (ops.scatter_rows(mg, idx.to(DEV), n, 'mean') * w2.to(DEV)).sum().backward()
+    assert_close(mg.grad, msg.grad, what='scatter_rows backward')
+
+
+def test_readout_assignment_is_bit_exact():
+    """Integer-valued features: every cell must land in exactly its complex (north_star: bit-exact readout)."""
+    comps = synthetic.zinc_like_complexes(64, seed=9, ragged=True)
+    batch = ComplexBatch.from_complex_list(comps)
+    for d in range(batch.dimension + 1):
+        c = batch.cochains[d]
+        x = torch.randint(-8, 9, (c.num_cells, 16)).float()
+        ref = torch.zeros(64, 16).index_add_(0, c.batch, x)
+        assert torch.equal(ops.segment_pool(x.to(DEV), c.batch.to(DEV), 64).cpu(), ref)
+
+
+# ------------------------------------------------------------------------------------------------ operator API: KATs
+def _propagate(comp, dim, **kw):
+    p = comp.get_cochain_params(dim=dim)
+    cmp = CochainMessagePassing(up_msg_size=1, down_msg_size=1, **kw).to(DEV)
+    return cmp.propagate(p.up_index, p.down_index, p.boundary_index, x=p.x, up_attr=p.kwargs['up_attr'],
+                         down_attr=p.kwargs['down_attr'], boundary_attr=p.kwargs['boundary_attr'])
+
+
+def test_reference_known_answers_on_gpu():  # mp/test_cell_mp.py:13-111, :179-270
+    house = fixture('house').to(DEV)
+    up, down, bnd = _propagate(house, 1)
+    assert torch.equal(down.cpu(), T([6, 10, 17, 9, 13, 10]))
+    assert torch.equal(up.cpu(), T([0, 0, 11, 0, 9, 8]))
+    assert torch.equal(bnd.cpu(), T([3, 5, 7, 5, 9, 8]))
+    up, down, bnd = _propagate(house, 0)
+    assert torch.equal(up.cpu(), T([6, 4, 11, 9, 7]))
+    assert torch.equal(down.cpu(), torch.zeros(5, 1)) and torch.equal(bnd.cpu(), torch.zeros(5, 1))
+    up, down, bnd = _propagate(house, 2)
+    assert torch.equal(up.cpu(), torch.zeros(1, 1)) and torch.equal(bnd.cpu(), T([14]))
+    bridged = fixture('bridged').to(DEV)
+    up, _, _ = _propagate(bridged, 1)
+    assert torch.equal(up.cpu(), T([24, 22, 20, 18, 22, 20]))
+    _, down, bnd = _propagate(bridged, 2)
+    assert torch.equal(down.cpu(), T([10, 8, 6])) and torch.equal(bnd.cpu(), T([16, 16, 10]))
+    # two 2-cells sharing an edge, no upper adjacency (mp/test_cell_mp.py:91-111)
+    cmp = CochainMessagePassing(1, 1).to(DEV)
+    x = torch.tensor([[32.], [17.]], device=DEV)
+    up, down, _ = cmp.propagate(None, torch.tensor([[0, 1], [1, 0]], device=DEV), None, x=x,
+                                down_attr=torch.tensor([[1.], [1.]], device=DEV))
+    assert torch.equal((up + down).cpu(), T([17, 32]))
+
+
+@pytest.mark.parametrize('name', list(golden()['fixtures']))
+def test_propagate_and_dummy_layers_equal_reference_on_every_fixture(name):
+    kat = golden()['kat'][name]
+    comp = fixture(name).to(DEV)
+    for d in range(comp.dimension + 1):
+        for got, ref in zip(_propagate(comp, d), kat['propagate'][d]):
+            assert torch.equal(got.cpu(), ref)
+    for b, dn in [(False, True), (True, False), (True, True)]:
+        ref = kat[f'dummy_b{int(b)}_d{int(dn)}']
+        if isinstance(ref, str):
+            continue
+        layer = DummyCellularMessagePassing(use_boundary_msg=b, use_down_msg=dn).to(DEV)
+        for got, r in zip(layer.forward(*comp.get_all_cochain_params()), ref):  # generic hook path
+            assert torch.equal(got.cpu(), r)
+
+
+@pytest.mark.parametrize('reduce', ['mean', 'max'])
+def test_mean_max_aggregations_equal_reference(reduce):
+    house = fixture('house').to(DEV)
+    for d in range(3):
+        got = _propagate(house, d, aggr_up=reduce, aggr_down=reduce, aggr_boundary=reduce)
+        for g, r in zip(got, golden()['kat']['house'][f'propagate_{reduce}'][d]):
+            assert torch.equal(g.cpu(), r)
+
+
+def test_isolated_cells_and_empty_index():  # mp/test_cell_mp.py:114-176
+    sd = fixture('square_dot').to(DEV)
+    up, down, _ = _propagate(sd, 0)
+    assert float(up[4].abs().sum()) == 0 and bool((up[:4] != 0).all()) and float(down.abs().sum()) == 0
+    for name in ('fullstop', 'colon'):
+        comp = fixture(name).to(DEV)
+        p = comp.get_cochain_params(dim=0)
+        cmp = CochainMessagePassing(1, 1).to(DEV)
+        up, _, _ = cmp.propagate(up_index=p.up_index, down_index=None, boundary_index=None, x=p.x, up_attr=None)
+        assert torch.equal(up, torch.zeros_like(p.x))
+        up, _, _ = cmp.propagate(up_index=torch.zeros(2, 0, dtype=torch.long, device=DEV), down_index=None,
+                                 boundary_index=None, x=p.x, up_attr=None)
+        assert torch.equal(up, torch.zeros_like(p.x))
+
+
+def test_init_reduce_known_answers():  # mp/test_layers.py:135-149
+    house = fixture('house').to(DEV)
+    v, e, t = (house.get_cochain_params(dim=d) for d in range(3))
+    conv = InitReduceConv(reduce='add')
+    assert torch.equal(conv.forward(v.x, e.boundary_index).cpu(), T([3, 5, 7, 5, 9, 8]))
+    assert torch.equal(conv.forward(e.x, t.boundary_index).cpu(), T([14]))
+
+
+def test_user_overridden_hooks_are_honoured():
+    class Scaled(CochainMessagePassing):
+        def message_up(self, up_x_j, up_attr, up_x_i):
+            return 2 * up_x_j + up_x_i - up_attr
+
+        def aggregate_boundary(self, inputs, agg_boundary_index, boundary_ptr=None, boundary_dim_size=None):
+            return 10 * super().aggregate_boundary(inputs, agg_boundary_index, boundary_ptr, boundary_dim_size)
+
+    house = fixture('house')
+    snap = O.Snapshot(house)
+    p = O.get_cochain_params(snap.cochains, 1)
+    ref_up = O.scatter(2 * p.x[p.up_index[0]] + p.x[p.up_index[1]] - p.up_attr, p.up_index[1], 6)
+    hg = fixture('house').to(DEV)
+    q = hg.get_cochain_params(dim=1)
+    up, _, bnd = Scaled(1, 1).to(DEV).propagate(q.up_index, q.down_index, q.boundary_index, x=q.x,
+                                                up_attr=q.kwargs['up_attr'], down_attr=q.kwargs['down_attr'],
+                                                boundary_attr=q.kwargs['boundary_attr'])
+    assert torch.equal(up.cpu(), ref_up) and torch.equal(bnd.cpu(), 10 * T([3, 5, 7, 5, 9, 8]))
+
+
+# ------------------------------------------------------------------------------------------------ models
+KLASS = {'sparse_cin': SparseCIN, 'embed_sparse_cin': EmbedSparseCIN, 'ogb_embed_sparse_cin': OGBEmbedSparseCIN,
+         'cin0': CIN0}
+ORACLE = {'sparse_cin': O.sparse_cin, 'embed_sparse_cin': O.embed_sparse_cin,
+          'ogb_embed_sparse_cin': O.ogb_embed_sparse_cin, 'cin0': O.cin0}
+
+
+def _family(name):
+    for k in ('ogb_embed_sparse_cin', 'embed_sparse_cin', 'sparse_cin', 'cin0'):
+        if name.startswith(k):
+            return k
+
+
+@pytest.mark.parametrize('name', ['sparse_cin_eval', 'sparse_cin_eval_dim1', 'embed_sparse_cin_eval', 'cin0_eval'])
+def test_eval_models_match_reference_outputs(name):
+    m = golden()['models'][name]
+    model = KLASS[_family(name)](**m['cfg'])
+    model.load_state_dict(m['state_dict'])
+    model.to(DEV).eval()
+    for chunk, ref in zip(m['chunks'], m['outputs']):
+        batch = batch_of(chunk, max_dim=m['max_dim'])
+        if m['strip']:
+            for d in (1, 2):
+                if d in batch.cochains:
+                    batch.cochains[d]._x = None
+        batch.to(DEV)
+        with torch.no_grad():
+            if name.startswith('cin0'):
+                assert_close(model(batch), ref, rtol=1e-5, atol=1e-5, what=name)
+            else:
+                out, res = model(batch, include_partial=True)
+                assert_close(out, ref[0], rtol=1e-5, atol=1e-5, what=name)
+                assert set(res) == set(ref[1])
+                for k in res:
+                    assert_close(res[k], ref[1][k], rtol=1e-5, atol=1e-5, what=f'{name}:{k}')
+
+
+def _loss(name, out, y):
+    if name.startswith('ogb'):
+        return torch.nn.functional.binary_cross_entropy_with_logits(out, (y.view(-1, 1) > 0).float())
+    return torch.nn.functional.l1_loss(out, y.view(-1, 1))
+
+
+@pytest.mark.parametrize('name', ['sparse_cin_train', 'embed_sparse_cin_train', 'embed_sparse_cin_train_nocob',
+                                  'ogb_embed_sparse_cin_train', 'cin0_train'])
+def test_train_step_matches_reference_and_oracle(name):
+    """Forward, loss, every parameter gradient and the BatchNorm running statistics of one training step."""
+    m = golden()['models'][name]
+    fam = _family(name)
+    model = KLASS[fam](**m['cfg'])
+    model.load_state_dict(m['state_dict'])
+    model.to(DEV).train()
+    batch = batch_of(m['inputs'], max_dim=m['cfg'].get('max_dim', 2)).to(DEV)
+    out = model(batch)
+    loss = _loss(name, out, batch.y)
+    loss.backward()
+    # (1) against the golden vectors recorded from the reference
+    assert_close(out, m['output'], rtol=1e-5, atol=1e-5, what=name)
+    assert_close(loss, m['loss'], rtol=1e-5, atol=1e-6, what=name + ':loss')
+    got = dict(model.named_parameters())
+    for k, ref in m['grads'].items():
+        assert_close(got[k].grad, ref, rtol=1e-4, atol=2e-6, what=f'{name}:grad:{k}')
+    for k, ref in m['state_dict_after'].items():
+        if 'running' in k:
+            assert_close(model.state_dict()[k], ref, rtol=1e-5, atol=1e-6, what=f'{name}:{k}')
+    # (2) against the oracle fed the same weights on the CPU
+    sd = oracle_state(m['state_dict'], requires_grad=True)
+    if fam == 'cin0':
+        share_cin0_levels(sd)
+    snap = O.Snapshot(batch_of(m['inputs'], max_dim=m['cfg'].get('max_dim', 2)))
+    ref_out = ORACLE[fam](sd, m['cfg'], snap, training=True)
+    assert_close(out, ref_out, rtol=1e-5, atol=1e-5, what=name + ':oracle')
+
+
+def test_batched_equals_unbatched():  # mp/test_models.py:139-185, mp/test_molec_models.py:11-68
+    names = golden()['testing_list']
+    torch.manual_seed(0)
+    for max_dim, bs in [(2, 5), (1, 23), (2, 2)]:
+        model = SparseCIN(num_input_features=1, num_classes=3, num_layers=3, hidden=5, jump_mode='cat',
+                          max_dim=max_dim).to(DEV).eval()
+        batched, single = {}, {}
+        with torch.no_grad():
+            for i in range(0, len(names), bs):
+                _, res = model(batch_of(names[i:i + bs], max_dim=max_dim).to(DEV), include_partial=True)
+                for k, v in res.items():
+                    batched.setdefault(k, []).append(v)
+            for n in names:
+                _, res = model(batch_of([n], max_dim=max_dim).to(DEV), include_partial=True)
+                for k, v in res.items():
+                    single.setdefault(k, []).append(v)
+        assert set(batched) == set(single)
+        for k in batched:
+            assert_close(torch.cat(batched[k]), torch.cat(single[k]), rtol=0, atol=1e-6, what=k)
+
+
+def test_zinc_shaped_training_step_against_oracle():
+    """BASELINE config 2 shape (hidden 64, 4 layers, use_coboundaries, edge embeddings) on a reduced batch."""
+    cfg = dict(atom_types=28, bond_types=4, out_size=1, num_layers=4, hidden=64, dropout_rate=0.0, max_dim=2,
+               embed_edge=True, use_coboundaries=True)
+    torch.manual_seed(0)
+    model = EmbedSparseCIN(**cfg)
+    sd = oracle_state(model.state_dict(), requires_grad=True)
+    comps = synthetic.zinc_like_complexes(16, seed=0)
+    snap = O.Snapshot(ComplexBatch.from_complex_list(comps))
+    ref = O.embed_sparse_cin(sd, cfg, snap, training=True)
+    ref_loss = torch.nn.functional.l1_loss(ref, snap.y.view(-1, 1))
+    ref_loss.backward()
+    model.to(DEV).train()
+    batch = ComplexBatch.from_complex_list(synthetic.zinc_like_complexes(16, seed=0)).to(DEV)
+    out = model(batch)
+    loss = torch.nn.functional.l1_loss(out, batch.y.view(-1, 1))
+    loss.backward()
+    assert_close(out, ref, rtol=1e-5, atol=1e-5, what='out')
+    assert_close(loss, ref_loss, rtol=1e-5, atol=1e-6, what='loss')
+    for k, p in model.named_parameters():
+        assert_close(p.grad, sd[k].grad, rtol=1e-4, atol=1e-5, what=f'grad {k}')
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+@pytest.mark.parametrize('kind', ['edge_boundary', 'ring_boundary', 'vertex_up', 'edge_up'])
+def test_full_size_properties(kind):
+    """~1M cells per dimension (BASELINE config 5): exactness on integer-valued features, message conservation
+    and linearity — properties that do not need the CPU oracle to finish."""
+    n_units = 40_000
+    index, cob, n_src, n_dst, n_cob = synthetic.tiled_adjacency(kind, n_units)
+    index = index.to(DEV)
+    F = 64
+    g = torch.Generator(device=DEV).manual_seed(0)
+    xi = torch.randint(-4, 5, (n_src, F), device=DEV, generator=g).float()
+    out = ops.gather_scatter(xi, index, n_dst)
+    ref = torch.zeros(n_dst, F, device=DEV).index_add_(0, index[1], xi.index_select(0, index[0]))
+    assert torch.equal(out, ref)  # small integers: every summation order is exact
+    outdeg = torch.bincount(index[0], minlength=n_src).double()
+    assert torch.equal(out.double().sum(0), (xi.double() * outdeg.unsqueeze(-1)).sum(0))  # conservation
+    a, b = torch.randn(n_src, F, device=DEV, generator=g), torch.randn(n_src, F, device=DEV, generator=g)
+    lhs = ops.gather_scatter(2 * a - 3 * b, index, n_dst)
+    rhs = 2 * ops.gather_scatter(a, index, n_dst) - 3 * ops.gather_scatter(b, index, n_dst)
+    assert_close(lhs, rhs, rtol=1e-5, atol=1e-4, what='linearity')
+    # transposed pass (the backward) conserves too
+    ar = a.requires_grad_(True)
+    ops.gather_scatter(ar, index, n_dst).sum().backward()
+    assert torch.equal(ar.grad[:, 0].double(), outdeg)
+
+
+def test_packed_host_to_device_copy_is_lossless():
+    comps = synthetic.zinc_like_complexes(32, seed=2)
+    a = ComplexBatch.from_complex_list(comps)
+    b = ComplexBatch.from_complex_list(synthetic.zinc_like_complexes(32, seed=2)).to(DEV)
+    assert b._h2d_bytes > 0
+    for d in range(3):
+        for k in ('x', 'upper_index', 'boundary_index', 'shared_coboundaries', 'batch'):
+            u, v = getattr(a.cochains[d], k), getattr(b.cochains[d], k)
+            assert (u is None) == (v is None)
+            if u is not None:
+                assert v.is_cuda and torch.equal(u, v.cpu()) and v.data_ptr() % 16 == 0
+    assert torch.equal(a.y, b.y.cpu())
