@@ -46,6 +46,7 @@ def parse():
     ap.add_argument('--pool', type=int, default=8, help='distinct pre-collated batches cycled through')
     ap.add_argument('--mode', default='auto', choices=['auto', 'eager', 'graph'])
     ap.add_argument('--no-sweep', action='store_true')
+    ap.add_argument('--sweep-only', action='store_true', help='only the per-adjacency kernel sweep (for ncu)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
 
@@ -223,13 +224,16 @@ def run_cwn(args, rank, world, local_rank):
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
     _lib.load()
+    if args.sweep_only:
+        print(json.dumps({'kernel_sweep': kernel_sweep(dev)}), flush=True)
+        return
     torch.manual_seed(0)
     model = EmbedSparseCIN(**MODEL_CFG).to(dev).train()
     broadcast_parameters(model)
     bucket = FlatGradBucket(model)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=True)
 
-    host_batches = make_batches(args.pool, args.batch, seed0=1000 + 100 * rank)
+    host_batches = [b.pack_(pin_memory=True) for b in make_batches(args.pool, args.batch, seed0=1000 + 100 * rank)]
     cells = cells_of(host_batches[0])
     dev_batches = [b.to(dev) for b in make_batches(args.pool, args.batch, seed0=1000 + 100 * rank)]
     index_tensors = [[t for d in range(3) for t in (b.cochains[d].upper_index, b.cochains[d].boundary_index,
@@ -246,12 +250,44 @@ def run_cwn(args, rank, world, local_rank):
         opt.step()
         return loss
 
-    def resident_step(i):
+    def eager_resident_step(i):
         b = dev_batches[i % args.pool]
         ops.clear_plan_cache(*index_tensors[i % args.pool])  # every step is a new batch: plans are rebuilt
         for d, x in enumerate(inputs[i % args.pool]):         # the forward overwrites cochain.x (set_xs): restore
             b.cochains[d]._x = x
         return step(b)
+
+    # ---- whole-step CUDA graph (plans + fwd + loss + bwd [+ adam]) over static packed buffers
+    mode, captured, launches_per_step = 'eager', None, None
+    if args.mode in ('auto', 'graph'):
+        from cwn_b200.graph import CapturedStep
+        try:
+            captured = CapturedStep(model, l1, bucket, opt, optimizer_in_graph=(world == 1))
+            static = make_batches(1, args.batch, seed0=999)[0].to(dev)
+            captured.capture(static)
+            l0 = _lib.launch_count()
+            captured._body()  # one eager pass of the captured body: counts the cwn kernels one replay launches
+            launches_per_step = _lib.launch_count() - l0
+            mode = 'cuda-graph'
+        except Exception as exc:  # noqa: BLE001 — reported in the JSON line, never silent
+            if args.mode == 'graph':
+                raise
+            print(f'bench.py: CUDA-graph capture failed ({type(exc).__name__}: {exc}); running eagerly',
+                  file=sys.stderr, flush=True)
+            captured, mode = None, f'eager (graph capture failed: {type(exc).__name__})'
+            torch.cuda.synchronize()
+
+    def resident_step(i):
+        if captured is not None:
+            return captured.run(dev_batches[i % args.pool])
+        return eager_resident_step(i)
+
+    def e2e_step(i):
+        if captured is not None:
+            captured.run(host_batches[i % args.pool])  # pinned host -> static device buffers, one copy per dtype
+            return float(captured.loss.item()), host_batches[i % args.pool].packed_nbytes
+        db = make_host_copy(host_batches[i % args.pool]).to(dev)
+        return float(step(db).item()), db._h2d_bytes
 
     def barrier():
         if world > 1:
@@ -276,7 +312,7 @@ def run_cwn(args, rank, world, local_rank):
         resident_step(i)
         ev[i][1].record()
     barrier()
-    launches = _lib.launch_count() - l0
+    launches = _lib.launch_count() - l0 if captured is None else launches_per_step * args.steps
     ms_total = sum(a.elapsed_time(b) for a, b in ev)
     clock_info = clocks.stop() if rank == 0 else None
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -285,21 +321,17 @@ def run_cwn(args, rank, world, local_rank):
     ms_step = float(t.item()) / args.steps
     value = cells * world / (ms_step / 1e3)
 
-    # ---- e2e: host batch -> device -> step -> loss back, every step
+    # ---- e2e: host batch (pinned) -> device -> step -> loss back on the host, every step
     for i in range(3):
-        hb = make_host_copy(host_batches[i % args.pool])
-        float(step(hb.to(dev)).item())
+        e2e_step(i)
     barrier()
     e2e_ms, h2d = 0.0, 0
     for i in range(args.steps):
-        hb = make_host_copy(host_batches[i % args.pool])
         flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        db = hb.to(dev)
-        loss_value = float(step(db).item())
+        loss_value, h2d = e2e_step(i)
         e2e_ms += 1e3 * (time.perf_counter() - t0)
-        h2d = db._h2d_bytes
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -311,7 +343,7 @@ def run_cwn(args, rank, world, local_rank):
     with ops.KernelProfile() as prof:
         for i in range(args.steps):
             flush.zero_()
-            resident_step(i)
+            eager_resident_step(i)
     summary = prof.summary()
     peak, peak_src = peaks()
     dom = max((k for k in summary if k != 'csr_plan_build'), key=lambda k: summary[k]['ms'])
@@ -323,6 +355,7 @@ def run_cwn(args, rank, world, local_rank):
                 'avg_launch_us': 1e3 * rec['ms'] / rec['launches'],
                 'algorithmic_bytes_per_launch': rec['bytes'] / rec['launches'],
                 'kernel_ms_per_step': {k: v['ms'] / args.steps for k, v in summary.items()},
+                'timed_in': 'instrumented eager re-run of the same steps (CUDA events around every C-ABI launch)',
                 'note': 'at batch 128 every adjacency pass moves ~1-2 MB (L2-resident): the step is launch/latency '
                         'bound, see kernel_sweep for the HBM-bound regime'}
     line = {
@@ -330,7 +363,7 @@ def run_cwn(args, rank, world, local_rank):
         'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'cells_per_step_per_gpu': cells, 'global_batch': args.batch * world,
-                   'parallelism': f'dp{world}', 'step': 'plans+fwd+loss+bwd+allreduce+adam', 'mode': 'eager',
+                   'parallelism': f'dp{world}', 'step': 'plans+fwd+loss+bwd+allreduce+adam', 'mode': mode,
                    'l2': 'flushed (256 MB write) between timed steps', 'last_loss': loss_value},
         'clocks': clock_info, 'gpu_launches': int(launches),
         'e2e': {'value': e2e_value, 'unit': 'cells/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 4},

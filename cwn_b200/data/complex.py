@@ -349,48 +349,95 @@ class Complex(object):
                 assert n_down is not None
                 cochain.num_cells_down = n_down
 
-    def to(self, device, **kwargs):
-        """Move every tensor of the complex. CPU -> CUDA goes through one pinned staging buffer per dtype and a
-        single async H2D copy each (the reference copies attribute by attribute, :539-546)."""
-        device = torch.device(device)
+    # ------------------------------------------------------------------ packed storage + device transfer
+    def _slots(self):
+        """(owner cochain or None for the complex label, attribute name, tensor) of every tensor of the complex."""
         slots = []
         for dim in range(self.dimension + 1):
             for key, t in self.cochains[dim]._tensor_items():
                 slots.append((self.cochains[dim], key, t))
         if self.y is not None and torch.is_tensor(self.y):
             slots.append((None, 'y', self.y))
-        packable = device.type == 'cuda' and not kwargs and all(t.device.type == 'cpu' for _, _, t in slots)
-        if not packable:
-            for owner, key, t in slots:
-                moved = t.to(device, **kwargs)
-                if owner is None:
-                    self.y = moved
-                else:
-                    owner._assign(key, moved)
-            return self
+        return slots
+
+    def _rebind(self, owner, key, value):
+        if owner is None:
+            self.y = value
+        else:
+            owner._assign(key, value)
+
+    def pack_(self, pin_memory: bool = False):
+        """Re-home every tensor into ONE flat buffer per dtype (16-byte aligned sub-ranges; attributes become
+        views), optionally pinned. A packed batch crosses PCIe/NVLink-C2C as one copy per dtype and can be loaded
+        into the static buffers of a captured CUDA graph (`load_packed_`). Returns self."""
+        slots = self._slots()
+        if slots and len({t.device for _, _, t in slots}) != 1:
+            raise ValueError('pack_: all tensors must live on one device')
         by_dtype: Dict[torch.dtype, list] = {}
         for slot in slots:
             by_dtype.setdefault(slot[2].dtype, []).append(slot)
-        self._h2d_bytes = 0
+        self._flat, self._layout = {}, []
         for dtype, group in by_dtype.items():
-            # 16-byte aligned sub-buffers so every feature/index matrix keeps vector-load alignment
             esz = torch.empty((), dtype=dtype).element_size()
             align = max(1, 16 // esz)
             offs, total = [], 0
             for _, _, t in group:
                 offs.append(total)
                 total += (t.numel() + align - 1) // align * align
-            stage = torch.empty(max(total, 1), dtype=dtype, pin_memory=True)
-            for (_, _, t), o in zip(group, offs):
-                stage[o:o + t.numel()].copy_(t.reshape(-1))
-            dev = stage.to(device, non_blocking=True)
-            self._h2d_bytes += total * esz
+            dev = group[0][2].device
+            flat = torch.zeros(max(total, 1), dtype=dtype, device=dev,
+                               pin_memory=bool(pin_memory and dev.type == 'cpu'))
             for (owner, key, t), o in zip(group, offs):
-                view = dev[o:o + t.numel()].view(t.shape)
-                if owner is None:
-                    self.y = view
-                else:
-                    owner._assign(key, view)
+                view = flat[o:o + t.numel()].view(t.shape)
+                view.copy_(t)
+                self._rebind(owner, key, view)
+                self._layout.append((None if owner is None else owner.dim, key, dtype, o, tuple(t.shape)))
+            self._flat[dtype] = flat
+        return self
+
+    @property
+    def packed_signature(self):
+        """Hashable description of the packed layout (shapes + offsets); equal signatures => buffers are
+        interchangeable element for element."""
+        if getattr(self, '_layout', None) is None:
+            return None
+        return tuple(self._layout)
+
+    @property
+    def packed_nbytes(self):
+        return sum(f.numel() * f.element_size() for f in getattr(self, '_flat', {}).values())
+
+    def load_packed_(self, other, non_blocking=True):
+        """Overwrite this (packed) complex's tensors with those of `other` (packed, identical signature) — one
+        copy per dtype, no allocation: the input side of a replayed CUDA graph."""
+        if self.packed_signature is None or self.packed_signature != other.packed_signature:
+            raise ValueError('load_packed_: layouts differ (different cell/message counts); re-capture or run eagerly')
+        for dtype, flat in self._flat.items():
+            flat.copy_(other._flat[dtype], non_blocking=non_blocking)
+        return self
+
+    def to(self, device, **kwargs):
+        """Move every tensor of the complex. CPU -> CUDA packs (pinned) if needed and then issues ONE async H2D
+        copy per dtype (the reference copies attribute by attribute, `data/complex.py:276-283,539-546`)."""
+        device = torch.device(device)
+        slots = self._slots()
+        packable = device.type == 'cuda' and not kwargs and all(t.device.type == 'cpu' for _, _, t in slots)
+        if not packable:
+            for owner, key, t in slots:
+                self._rebind(owner, key, t.to(device, **kwargs))
+            self._flat = self._layout = None
+            return self
+        if getattr(self, '_layout', None) is None or any(not f.is_pinned() for f in self._flat.values()):
+            self.pack_(pin_memory=True)
+        by_key = {(None if o is None else o.dim, k): o for o, k, _ in slots}
+        dev_flat = {dtype: flat.to(device, non_blocking=True) for dtype, flat in self._flat.items()}
+        self._h2d_bytes = self.packed_nbytes
+        for dim, key, dtype, off, shape in self._layout:
+            n = 1
+            for sdim in shape:
+                n *= sdim
+            self._rebind(by_key[(dim, key)], key, dev_flat[dtype][off:off + n].view(shape))
+        self._flat = dev_flat
         return self
 
     def get_cochain_params(self, dim: int, max_dim: int = 2, include_top_features=True,

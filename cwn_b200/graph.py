@@ -1,0 +1,93 @@
+"""Whole-step CUDA-graph capture of the hot path.
+
+At the reference's real-data shape (128 molecules, ~6.5k cells) one adjacency pass moves 1-2 MB: the training step
+is bound by launch latency and host-side dispatch, not by HBM ("two regimes"). The B200 answer is to
+take the host out of the loop: the CSR plan builds, every fused message-passing kernel, the dense update nets, the
+loss, the whole backward pass and the optimizer are captured ONCE into a CUDA graph over static, packed batch
+buffers; a training step is then `load_packed_` (one copy per dtype into the static buffers, from pinned host
+memory or from HBM) + one graph launch.
+
+A graph is specific to a packed layout (`Complex.packed_signature`: the cell and message counts of every
+dimension). Batches of identically shaped complexes (the synthetic benchmark) share one graph; ragged real batches
+get one graph per signature (`CapturedStep.for_batch` keeps them in a dict) and fall back to eager execution
+beyond `max_graphs` distinct layouts.
+"""
+import torch
+
+from cwn_b200 import ops
+
+
+def _index_tensors(batch):
+    out = []
+    for d in range(batch.dimension + 1):
+        c = batch.cochains[d]
+        out += [c.upper_index, c.lower_index, c.boundary_index, c.batch, c.shared_coboundaries, c.shared_boundaries]
+    return [t for t in out if t is not None]
+
+
+class CapturedStep(object):
+    """forward -> loss -> backward (-> optimizer) on batches of one packed layout, as a single CUDA graph.
+
+    Args:
+        model, loss_fn(out, y): the training closure pieces.
+        bucket: `cwn_b200.dist.FlatGradBucket` (gradients are written into its static flat buffer).
+        optimizer: captured into the graph when `optimizer_in_graph` (single GPU; needs `capturable=True`);
+            with data parallelism the all-reduce runs between the graph and a (separately captured) optimizer.
+    """
+
+    def __init__(self, model, loss_fn, bucket, optimizer=None, optimizer_in_graph=True, warmup=3):
+        self.model, self.loss_fn, self.bucket, self.optimizer = model, loss_fn, bucket, optimizer
+        self.optimizer_in_graph = optimizer_in_graph and optimizer is not None
+        self.warmup = warmup
+        self.graph = self.opt_graph = self.static = self.loss = None
+
+    def _body(self):
+        b = self.static
+        for d, x in enumerate(self._inputs):  # the forward overwrites cochain.x with hidden features (set_xs)
+            b.cochains[d]._x = x
+        ops.clear_plan_cache(*self._indices)  # plans are part of the step: every step is a new batch
+        self.bucket.zero()
+        out = self.model(b)
+        loss = self.loss_fn(out, b.y)
+        loss.backward()
+        if self.optimizer_in_graph:
+            self.optimizer.step()
+        return loss
+
+    def capture(self, example):
+        """`example`: a packed batch ON THE DEVICE; it becomes the graph's static input (do not reuse it)."""
+        if example.packed_signature is None:
+            raise ValueError('CapturedStep.capture needs a packed batch (ComplexBatch.pack_() / .to(device))')
+        self.static = example
+        self._inputs = [example.cochains[d].x for d in range(example.dimension + 1)]
+        self._indices = _index_tensors(example)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # lazy initialisations (cuBLAS workspaces, optimizer state) before capture
+            for _ in range(self.warmup):
+                self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body()
+        if self.optimizer is not None and not self.optimizer_in_graph:
+            self.opt_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.opt_graph):
+                self.optimizer.step()
+        return self
+
+    @property
+    def signature(self):
+        return None if self.static is None else self.static.packed_signature
+
+    def run(self, batch=None):
+        """Load `batch` (packed, same layout; host-pinned or device) into the static buffers and replay.
+        Returns the static loss tensor (valid until the next run)."""
+        if batch is not None:
+            self.static.load_packed_(batch)
+        self.graph.replay()
+        if self.opt_graph is not None:
+            self.bucket.all_reduce()
+            self.opt_graph.replay()
+        return self.loss

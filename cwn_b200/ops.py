@@ -209,13 +209,13 @@ def _launch_gather_rows(x, idx, scale):
     return out
 
 
-def _eps_grad(ctx_needs, g, x_res, eps):
-    """(grad x_res, grad eps) of out = (1 + eps) * x_res + ..."""
+def _residual_grads(needs_res, needs_eps, g, x_res_saved, eps):
+    """(grad x_res, grad eps) of out = (1 + eps) * x_res + ... ; `x_res_saved` is only kept when eps needs a grad."""
     g_res = g_eps = None
-    if x_res is not None and ctx_needs[0]:
+    if needs_res:
         g_res = g if eps is None else g * (1.0 + eps)
-    if eps is not None and ctx_needs[1]:
-        g_eps = (g * x_res).sum().reshape(eps.shape)
+    if needs_eps and eps is not None:
+        g_eps = (g * x_res_saved).sum().reshape(eps.shape)
     return g_res, g_eps
 
 
@@ -256,10 +256,9 @@ class _GatherReduce(Function):
                 gm = g / deg.unsqueeze(-1)
             plan = adj.by_src  # transposed pass: gX[s] = sum_{e: src_e = s} G[dst_e]
             g_src = _launch_gather_reduce(gm, plan.rowptr, plan.pay0, adj.n_src, g.size(1), None, None, 0)
-        g_res, g_eps = _eps_grad(ctx.needs_input_grad[1:3], g, x_res if ctx.has_res else None, eps) \
-            if ctx.has_res else (None, None)
-        if ctx.has_res and ctx.needs_input_grad[1] and g_res is None:
-            g_res = g
+        g_res = g_eps = None
+        if ctx.has_res:
+            g_res, g_eps = _residual_grads(ctx.needs_input_grad[1], ctx.needs_input_grad[2], g, x_res, eps)
         return g_src, g_res, g_eps, None, None
 
 
@@ -308,9 +307,7 @@ class _CobPass(Function):
                       _ptr(plan.pay1), adj.n_cob, F, act, _ptr(gQ), F, _stream())
         g_res = g_eps = None
         if ctx.has_res:
-            g_res, g_eps = _eps_grad(ctx.needs_input_grad[2:4], g, x_res, eps)
-            if ctx.needs_input_grad[2] and g_res is None:
-                g_res = g
+            g_res, g_eps = _residual_grads(ctx.needs_input_grad[2], ctx.needs_input_grad[3], g, x_res, eps)
         return gP, gQ, g_res, g_eps, None, None
 
 

@@ -442,3 +442,42 @@ def test_packed_host_to_device_copy_is_lossless():
             if u is not None:
                 assert v.is_cuda and torch.equal(u, v.cpu()) and v.data_ptr() % 16 == 0
     assert torch.equal(a.y, b.y.cpu())
+
+
+def test_residual_gradient_with_buffer_eps():
+    """eps as a non-trainable buffer != 0 (train_eps=False, eps given): grad of the residual operand is (1+eps) g."""
+    n, F = 50, 16
+    idx, _ = _rand_adj(n, n, 200, 21)
+    x = torch.randn(n, F, requires_grad=True)
+    eps = torch.tensor([0.5])
+    (O.scatter(x.index_select(0, idx[0]), idx[1], n) + (1 + eps) * x).pow(2).sum().backward()
+    xg = x.detach().to(DEV).requires_grad_(True)
+    ops.gather_scatter(xg, idx.to(DEV), n, 'add', x_res=xg, eps=eps.to(DEV)).pow(2).sum().backward()
+    assert_close(xg.grad, x.grad, rtol=1e-5, atol=1e-4, what='grad through fused residual')
+
+
+def test_captured_cuda_graph_step_equals_eager_step():
+    """cwn_b200.graph.CapturedStep: plans + forward + loss + backward replayed from a CUDA graph on new batches of
+    the same layout give the loss and gradients of the eager path."""
+    from cwn_b200.dist import FlatGradBucket
+    from cwn_b200.graph import CapturedStep
+    cfg = dict(atom_types=28, bond_types=4, out_size=1, num_layers=2, hidden=32, dropout_rate=0.0, max_dim=2,
+               embed_edge=True, use_coboundaries=True)
+    torch.manual_seed(0)
+    m_graph, m_eager = EmbedSparseCIN(**cfg).to(DEV).train(), EmbedSparseCIN(**cfg).to(DEV).train()
+    m_eager.load_state_dict(m_graph.state_dict())
+    loss_fn = lambda out, y: torch.nn.functional.l1_loss(out, y.view(-1, 1))  # noqa: E731
+    b_graph, b_eager = FlatGradBucket(m_graph), FlatGradBucket(m_eager)
+    mk = lambda seed: ComplexBatch.from_complex_list(synthetic.zinc_like_complexes(8, seed=seed))  # noqa: E731
+    cap = CapturedStep(m_graph, loss_fn, b_graph, optimizer=None).capture(mk(0).to(DEV))
+    for seed, pinned_host in [(1, True), (2, False), (1, True)]:
+        batch = mk(seed).pack_(pin_memory=True) if pinned_host else mk(seed).to(DEV)
+        loss = cap.run(batch)
+        b_eager.zero()
+        eb = mk(seed).to(DEV)
+        ref = loss_fn(m_eager(eb), eb.y)
+        ref.backward()
+        assert_close(loss, ref, rtol=1e-6, atol=1e-7, what='loss')
+        assert_close(b_graph.flat, b_eager.flat, rtol=1e-5, atol=1e-6, what='flat gradient bucket')
+    with pytest.raises(ValueError, match='layouts differ'):
+        cap.run(ComplexBatch.from_complex_list(synthetic.zinc_like_complexes(9, seed=3)).pack_())
