@@ -47,6 +47,7 @@ def parse():
     ap.add_argument('--mode', default='auto', choices=['auto', 'eager', 'graph'])
     ap.add_argument('--no-sweep', action='store_true')
     ap.add_argument('--sweep-only', action='store_true', help='only the per-adjacency kernel sweep (for ncu)')
+    ap.add_argument('--sweep-full', action='store_true', help='BASELINE config 5 grid, one JSON line per point')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
 
@@ -213,6 +214,76 @@ def kernel_sweep(dev):
     return out
 
 
+def kernel_sweep_full(dev):
+    """BASELINE config 5: N in {1e4,1e5,1e6} cells/dim x F in {16,64,256} x the four adjacency types, block-diagonal
+    ZINC-like layout (+ one uniform-random stress point per F); forward, transposed (backward) and coboundary passes.
+    One JSON object per point on stdout."""
+    from cwn_b200 import ops
+    from cwn_b200.data import synthetic
+    peak, _ = peaks()
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+
+    def timed(fn, name, reps=5):
+        ms = []
+        for _ in range(reps):
+            flush.zero_()
+            with ops.KernelProfile() as prof:
+                fn()
+            rec = prof.summary()[name]
+            ms.append(rec['ms'] / rec['launches'])
+        t = sorted(ms)[len(ms) // 2]
+        return t, rec['bytes'] / rec['launches']
+
+    units_per = {'edge_boundary': 25, 'ring_boundary': 3, 'vertex_up': 23, 'edge_up': 25}
+    points = [(k, n, 'block-diagonal') for k in units_per for n in (10_000, 100_000, 1_000_000)] + \
+             [('random', 1_000_000, 'uniform-random')]
+    for kind, n_cells, layout in points:
+        if kind == 'random':
+            index, cob, n_src, n_dst, n_cob = synthetic.random_adjacency(n_cells, n_cells, 3_200_000, n_cells // 8)
+        else:
+            index, cob, n_src, n_dst, n_cob = synthetic.tiled_adjacency(kind, max(1, n_cells // units_per[kind]))
+        index = index.to(dev)
+        cob = cob.to(dev) if cob is not None else None
+        for F in (16, 64, 256):
+            x = torch.randn(n_src, F, device=dev, requires_grad=True)
+            out = ops.gather_scatter(x, index, n_dst)
+            g = torch.randn_like(out)
+            out.backward(g)  # builds the transposed plan
+            rows = []
+            t, b = timed(lambda: ops.gather_scatter(x.detach(), index, n_dst), 'csr_gather_reduce')
+            rows.append(('identity_fwd', t, b))
+
+            def bwd():
+                x.grad = None
+                ops.gather_scatter(x, index, n_dst).backward(g)
+            with ops.KernelProfile() as prof:
+                flush.zero_()
+                bwd()
+            recs = [r for r in prof.records if r[0] == 'csr_gather_reduce']
+            torch.cuda.synchronize()
+            rows.append(('identity_bwd', recs[1][2].elapsed_time(recs[1][3]), recs[1][1]))
+            if cob is not None:
+                P = torch.randn(n_src, F, device=dev, requires_grad=True)
+                Q = torch.randn(n_cob, F, device=dev, requires_grad=True)
+                o = ops.cob_pass(P, Q, index, cob, n_dst)
+                o.backward(g)
+
+                def both():
+                    P.grad = Q.grad = None
+                    ops.cob_pass(P, Q, index, cob, n_dst).backward(g)
+                t, b = timed(both, 'csr_cob_fwd')
+                rows.append(('cob_fwd', t, b))
+                t, b = timed(both, 'csr_cob_bwd')
+                rows.append(('cob_bwd (avg of dP, dQ)', t, b))
+            for name, t, b in rows:
+                gbs = b / (t * 1e-3) / 1e9
+                print(json.dumps({'pass': name, 'adjacency': kind, 'layout': layout, 'cells': n_dst,
+                                  'messages': index.size(1), 'F': F, 'us': round(1e3 * t, 2),
+                                  'algorithmic_MB': round(b / 1e6, 3), 'GBps': round(gbs, 1),
+                                  'frac_of_measured_peak': round(gbs / peak, 4)}), flush=True)
+            del x, out, g
+
+
 def run_cwn(args, rank, world, local_rank):
     import torch.distributed as dist
     from cwn_b200 import _lib, ops
@@ -226,6 +297,9 @@ def run_cwn(args, rank, world, local_rank):
     _lib.load()
     if args.sweep_only:
         print(json.dumps({'kernel_sweep': kernel_sweep(dev)}), flush=True)
+        return
+    if args.sweep_full:
+        kernel_sweep_full(dev)
         return
     torch.manual_seed(0)
     model = EmbedSparseCIN(**MODEL_CFG).to(dev).train()

@@ -13,6 +13,13 @@ _i32 = ctypes.c_int32
 _f32 = ctypes.c_float
 _vp = ctypes.c_void_p
 
+class PlanDesc(ctypes.Structure):
+    """cwn_plan_desc of include/cwn_b200.h."""
+    _fields_ = [('key', ctypes.c_void_p), ('pay0', ctypes.c_void_p), ('pay1', ctypes.c_void_p),
+                ('E', ctypes.c_int64), ('n_rows', ctypes.c_int64), ('rowptr', ctypes.c_void_p),
+                ('perm', ctypes.c_void_p), ('pay0_sorted', ctypes.c_void_p), ('pay1_sorted', ctypes.c_void_p)]
+
+
 _SIGNATURES = {
     'cwn_version': (ctypes.c_char_p, []),
     'cwn_last_error_string': (ctypes.c_char_p, []),
@@ -20,6 +27,8 @@ _SIGNATURES = {
     'cwn_csr_plan_workspace_bytes': (ctypes.c_size_t, [_i64, _i64]),
     'cwn_csr_plan_build': (ctypes.c_int, [_c_i64p, _c_i64p, _c_i64p, _i64, _i64, _c_i32p, _c_i32p, _c_i32p,
                                           _c_i32p, _c_i32p, _vp, ctypes.c_size_t, _vp]),
+    'cwn_csr_plan_small_capacity': (ctypes.c_int64, []),
+    'cwn_csr_plan_build_small': (ctypes.c_int, [ctypes.POINTER(PlanDesc), _i32, _c_i32p, _vp]),
     'cwn_csr_gather_reduce_f32': (ctypes.c_int, [_c_f32p, _i64, _c_i32p, _c_i32p, _i64, _i32, _c_f32p, _i64,
                                                  _c_f32p, _c_f32p, _i64, _i32, _vp]),
     'cwn_gather_rows_f32': (ctypes.c_int, [_c_f32p, _i64, _c_i64p, _i64, _i32, _f32, _c_f32p, _i64, _vp]),

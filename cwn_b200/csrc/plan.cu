@@ -10,6 +10,7 @@
 //                      value = message id
 //   2. cub::DeviceRadixSort::SortPairs over ceil(log2(n_rows+1)) bits (LSD radix sort => stable)
 //   3. finish_plan   : rowptr[r] = lower_bound(sorted keys, r); payload columns permuted + narrowed to int32
+#include <cub/block/block_radix_sort.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include "common.cuh"
 
@@ -55,6 +56,67 @@ __global__ void finish_plan_kernel(const int32_t* __restrict__ key_sorted, const
 
 __global__ void fill_zero_kernel(int32_t* p, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0;
+}
+
+// ---- all the (small) plans of one batch in ONE launch: one CTA per plan, block-wide stable radix sort in shared
+// memory. At the reference's real-data shape (128 molecules: E <= 10 240 per adjacency) this replaces ~6 launches
+// per plan (13 plans per batch) by a single kernel.
+constexpr int kSmallThreads = 512;
+constexpr int kSmallItems = 24;
+constexpr int kSmallCapacity = kSmallThreads * kSmallItems;  // 12 288 messages per plan
+constexpr int kMaxPlansPerLaunch = 16;
+
+struct PlanBatch {
+  cwn_plan_desc d[kMaxPlansPerLaunch];
+  int bits[kMaxPlansPerLaunch];
+};
+
+__global__ void __launch_bounds__(kSmallThreads)
+small_plans_kernel(const __grid_constant__ PlanBatch batch, int32_t* flags) {
+  using Sort = cub::BlockRadixSort<int32_t, kSmallThreads, kSmallItems, int32_t>;
+  extern __shared__ __align__(16) unsigned char smem[];
+  typename Sort::TempStorage& temp = *reinterpret_cast<typename Sort::TempStorage*>(smem);
+  int32_t* sorted = reinterpret_cast<int32_t*>(smem + ((sizeof(typename Sort::TempStorage) + 15) & ~size_t(15)));
+  const cwn_plan_desc& p = batch.d[blockIdx.x];
+  const int E = (int)p.E;
+  const int n_rows = (int)p.n_rows;
+  const int t = threadIdx.x;
+  int32_t keys[kSmallItems], vals[kSmallItems];
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < kSmallItems; ++i) {
+    const int e = t * kSmallItems + i;  // blocked arrangement: ascending message id => stability is meaningful
+    int32_t k = n_rows;                 // padding and out-of-range keys sort behind every real row
+    if (e < E) {
+      const int64_t kk = p.key[e];
+      if (kk >= 0 && kk < n_rows) k = (int32_t)kk; else bad = true;
+    }
+    keys[i] = k;
+    vals[i] = e;
+  }
+  if (bad && flags) atomicOr(flags, 1);
+  Sort(temp).Sort(keys, vals, 0, batch.bits[blockIdx.x]);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kSmallItems; ++i) {
+    const int pos = t * kSmallItems + i;
+    sorted[pos] = keys[i];
+    if (pos < E) {
+      const int32_t e = vals[i];
+      p.perm[pos] = e;
+      if (p.pay0) p.pay0_sorted[pos] = (int32_t)p.pay0[e];
+      if (p.pay1) p.pay1_sorted[pos] = (int32_t)p.pay1[e];
+    }
+  }
+  __syncthreads();
+  for (int r = t; r <= n_rows; r += kSmallThreads) {  // rowptr[r] = first position whose key is >= r
+    int lo = 0, hi = E;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (sorted[mid] < r) lo = mid + 1; else hi = mid;
+    }
+    p.rowptr[r] = lo;
+  }
 }
 
 static int key_bits(int64_t n_rows) {  // keys take values 0..n_rows (n_rows = dummy row)
@@ -123,4 +185,38 @@ extern "C" int cwn_csr_plan_build(const int64_t* key, const int64_t* pay0, const
   finish_plan_kernel<<<blocks_for(E > n_rows + 1 ? E : n_rows + 1), 256, 0, st>>>(
       key_sorted, perm, E, n_rows, pay0, pay1, rowptr, pay0_sorted, pay1_sorted);
   return launched("finish_plan");
+}
+
+extern "C" int64_t cwn_csr_plan_small_capacity(void) { return kSmallCapacity; }
+
+extern "C" int cwn_csr_plan_build_small(const cwn_plan_desc* descs, int32_t n_plans, int32_t* flags,
+                                        cwn_stream_t stream) {
+  if (n_plans < 0) return fail(CWN_E_SHAPE, "cwn_csr_plan_build_small: negative plan count");
+  if (n_plans == 0) return CWN_OK;
+  if (!descs) return fail(CWN_E_NULL, "descs");
+  using Sort = cub::BlockRadixSort<int32_t, kSmallThreads, kSmallItems, int32_t>;
+  const size_t smem = ((sizeof(typename Sort::TempStorage) + 15) & ~size_t(15)) + (size_t)kSmallCapacity * sizeof(int32_t);
+  static std::atomic<bool> configured{false};
+  if (!configured.load(std::memory_order_acquire)) {
+    cudaError_t ce = cudaFuncSetAttribute(small_plans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return cuda_status(ce, "cudaFuncSetAttribute(small_plans_kernel)");
+    configured.store(true, std::memory_order_release);
+  }
+  for (int base = 0; base < n_plans; base += kMaxPlansPerLaunch) {
+    PlanBatch batch;
+    const int n = (n_plans - base < kMaxPlansPerLaunch) ? n_plans - base : kMaxPlansPerLaunch;
+    for (int i = 0; i < n; ++i) {
+      const cwn_plan_desc& d = descs[base + i];
+      if (d.E < 0 || d.n_rows < 0 || d.E > kSmallCapacity || d.n_rows >= INT32_MAX)
+        return fail(CWN_E_SHAPE, "cwn_csr_plan_build_small: plan exceeds cwn_csr_plan_small_capacity()");
+      if (!d.rowptr || (d.E > 0 && (!d.key || !d.perm))) return fail(CWN_E_NULL, "plan descriptor");
+      if ((d.pay0 && !d.pay0_sorted) || (d.pay1 && !d.pay1_sorted)) return fail(CWN_E_NULL, "payload output");
+      batch.d[i] = d;
+      batch.bits[i] = key_bits(d.n_rows);
+    }
+    small_plans_kernel<<<n, kSmallThreads, smem, (cudaStream_t)stream>>>(batch, flags);
+    int rc = launched("small_plans_kernel");
+    if (rc) return rc;
+  }
+  return CWN_OK;
 }

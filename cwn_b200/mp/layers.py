@@ -16,6 +16,7 @@ from torch import Tensor
 from torch.nn import Linear, Sequential, BatchNorm1d as BN
 
 from cwn_b200 import ops
+from cwn_b200.streams import run_concurrently
 from cwn_b200.mp.cell_mp import CochainMessagePassing, CochainMessagePassingParams
 from cwn_b200.mp.nn import activation_name, reset
 from cwn_b200.mp.params import LazyRows, as_tensor
@@ -51,15 +52,21 @@ class DummyCochainMessagePassing(CochainMessagePassing):
 class _PerDimension(torch.nn.Module):
     """Runs `mp_levels[d]` on the parameters of dimension d (shared `forward` of the *Conv containers)."""
 
+    concurrent_dims = True  # False when the dimensions share nn objects (their BatchNorm buffers would race)
+
     def forward(self, *cochain_params: CochainMessagePassingParams, start_to_process=0):
         assert len(cochain_params) <= self.max_dim + 1
-        out = []
-        for dim in range(len(cochain_params)):
+
+        def level(dim):
             if dim < start_to_process:
-                out.append(cochain_params[dim].x)
-            else:
-                out.append(self.mp_levels[dim].forward(cochain_params[dim]))
-        return out
+                return lambda: cochain_params[dim].x
+            return lambda: self.mp_levels[dim].forward(cochain_params[dim])
+
+        x0 = cochain_params[0].x if len(cochain_params) else None
+        device = x0.device if torch.is_tensor(x0) else None
+        # the dimensions of a layer are independent: one concurrent branch each
+        return run_concurrently([level(dim) for dim in range(len(cochain_params))],
+                                device if self.concurrent_dims else None)
 
 
 class DummyCellularMessagePassing(_PerDimension):
@@ -116,6 +123,8 @@ class CINCochainConv(CochainMessagePassing):
 
 class CINConv(_PerDimension):
     """One `CINCochainConv` per dimension, all sharing the SAME nn objects (reference `mp/layers.py:106-124`)."""
+
+    concurrent_dims = False  # the SAME BatchNorm objects serve every dimension, in order
 
     def __init__(self, up_msg_size: int, down_msg_size: int, msg_up_nn: Callable, msg_down_nn: Callable,
                  update_nn: Callable, eps: float = 0., train_eps: bool = False, max_dim: int = 2):
@@ -193,7 +202,8 @@ class SparseCINCochainConv(CochainMessagePassing):
         return None
 
     def _fused_forward(self, cochain: CochainMessagePassingParams):
-        """Both passes through the fused kernels, residuals included; NotImplemented if not recognised."""
+        """(upper branch, boundary branch) thunks running the fused kernels, residuals included; NotImplemented
+        if the layer's nets / hooks are not the recognised closed forms."""
         x = cochain.x
         form = self._up_message_form()
         if form is None or self.msg_boundaries_nn is not identity or not self._hooks_untouched():
@@ -208,46 +218,47 @@ class SparseCINCochainConv(CochainMessagePassing):
             if not (isinstance(up_attr, LazyRows) and x.size(1) + up_attr.source.size(1) == lin.in_features):
                 return NotImplemented  # dense / missing coboundary features: let the hook protocol decide
 
-        # upper adjacencies
-        if up_index is None:
-            if self.up_msg_size != x.size(1):
-                return NotImplemented
-            out_up = (1 + self.eps1) * x
-        elif form[0] == 'identity':
-            out_up = ops.gather_scatter(x, up_index, n, 'add', x_res=x, eps=self.eps1)
-        else:
+        if up_index is None and self.up_msg_size != x.size(1):
+            return NotImplemented
+        if b_attr is not None and b_index is None:
+            return NotImplemented
+        if b_attr is None and self.boundary_msg_size != x.size(1):
+            return NotImplemented
+
+        def up_branch():  # upper adjacencies
+            if up_index is None:
+                return (1 + self.eps1) * x
+            if form[0] == 'identity':
+                return ops.gather_scatter(x, up_index, n, 'add', x_res=x, eps=self.eps1)
             _, lin, act = form
             fx = x.size(1)
             # W [x_j ; y_cob] + b  ==  (x W1^T)[src] + (y W2^T + b)[cob]: two per-CELL GEMMs instead of one per
             # message, then a memory-bound fused pass
             P = F.linear(x, lin.weight[:, :fx])
             Q = F.linear(up_attr.source, lin.weight[:, fx:], lin.bias)
-            out_up = ops.cob_pass(P, Q, up_index, up_attr.index, n, act=act, x_res=x, eps=self.eps1)
+            return ops.cob_pass(P, Q, up_index, up_attr.index, n, act=act, x_res=x, eps=self.eps1)
 
-        # boundaries (the pass only runs when boundary features exist, reference mp/cell_mp.py:381)
-        if b_attr is not None:
-            if b_index is None:
-                return NotImplemented
-            out_b = ops.gather_scatter(as_tensor(b_attr), b_index, n, 'add', x_res=x, eps=self.eps2)
-        else:
-            if self.boundary_msg_size != x.size(1):
-                return NotImplemented
-            out_b = (1 + self.eps2) * x
-        return out_up, out_b
+        def boundary_branch():  # the pass only runs when boundary features exist (reference mp/cell_mp.py:381)
+            if b_attr is not None:
+                return ops.gather_scatter(as_tensor(b_attr), b_index, n, 'add', x_res=x, eps=self.eps2)
+            return (1 + self.eps2) * x
+
+        return up_branch, boundary_branch
 
     def forward(self, cochain: CochainMessagePassingParams):
         fused = self._fused_forward(cochain)
         if fused is NotImplemented:
-            out_up, _, out_boundaries = self.propagate(cochain.up_index, cochain.down_index,
-                                                       cochain.boundary_index, x=cochain.x,
-                                                       up_attr=cochain.kwargs['up_attr'],
-                                                       boundary_attr=cochain.kwargs['boundary_attr'])
-            out_up = out_up + (1 + self.eps1) * cochain.x
-            out_boundaries = out_boundaries + (1 + self.eps2) * cochain.x
+            agg_up, _, agg_b = self.propagate(cochain.up_index, cochain.down_index, cochain.boundary_index,
+                                              x=cochain.x, up_attr=cochain.kwargs['up_attr'],
+                                              boundary_attr=cochain.kwargs['boundary_attr'])
+            up_branch = lambda: agg_up + (1 + self.eps1) * cochain.x          # noqa: E731
+            boundary_branch = lambda: agg_b + (1 + self.eps2) * cochain.x     # noqa: E731
         else:
-            out_up, out_boundaries = fused
-        out_up = self.update_up_nn(out_up)
-        out_boundaries = self.update_boundaries_nn(out_boundaries)
+            up_branch, boundary_branch = fused
+        # the two branches (aggregation + update MLP) are independent until combine_nn
+        out_up, out_boundaries = run_concurrently([lambda: self.update_up_nn(up_branch()),
+                                                   lambda: self.update_boundaries_nn(boundary_branch())],
+                                                  cochain.x.device)
         return self.combine_nn(torch.cat([out_up, out_boundaries], dim=-1))
 
     def reset_parameters(self):

@@ -5,6 +5,7 @@ import torch
 import torch.nn.functional as F
 from torch.nn import Linear, Sequential, BatchNorm1d as BN
 
+from cwn_b200 import ops
 from cwn_b200.data.complex import ComplexBatch
 from cwn_b200.mp.layers import CINConv, SparseCINConv
 from cwn_b200.mp.nn import (JumpingKnowledge, get_graph_norm, get_nonlinearity, get_pooling_fn,
@@ -124,6 +125,7 @@ class SparseCIN(torch.nn.Module, _JumpMixin):
         self.convs = torch.nn.ModuleList()
         self.nonlinearity = nonlinearity
         self.readout = readout
+        self.use_coboundaries = use_coboundaries
         self.pooling_fn = get_pooling_fn(readout)
         self.graph_norm = get_graph_norm(graph_norm)
         act_module = get_nonlinearity(nonlinearity, return_module=True)
@@ -161,6 +163,8 @@ class SparseCIN(torch.nn.Module, _JumpMixin):
         act = get_nonlinearity(self.nonlinearity, return_module=False)
         xs, jump_xs = None, None
         res = {}
+        # every CSR plan of this batch (all dimensions, forward + backward, readout) in one kernel launch
+        ops.prepare_plans(data, self.max_dim, self.use_coboundaries, backward=torch.is_grad_enabled())
         for c, conv in enumerate(self.convs):
             params = data.get_all_cochain_params(max_dim=self.max_dim, include_down_features=False)
             xs = conv(*params, start_to_process=0)

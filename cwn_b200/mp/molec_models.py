@@ -3,6 +3,7 @@ import torch
 import torch.nn.functional as F
 from torch.nn import Embedding, Linear
 
+from cwn_b200 import ops
 from cwn_b200.data.complex import ComplexBatch
 from cwn_b200.mp.encoders import AtomEncoder, BondEncoder
 from cwn_b200.mp.layers import EmbedVEWithReduce, InitReduceConv, OGBEmbedVEWithReduce, SparseCINConv
@@ -22,6 +23,7 @@ class _EmbedSparseCINBase(torch.nn.Module, _JumpMixin):
         self.convs = torch.nn.ModuleList()
         self.nonlinearity = nonlinearity
         self.readout = readout
+        self.use_coboundaries = use_coboundaries
         self.graph_norm = get_graph_norm(graph_norm)
         act_module = get_nonlinearity(nonlinearity, return_module=True)
         for i in range(num_layers):
@@ -60,6 +62,8 @@ class _EmbedSparseCINBase(torch.nn.Module, _JumpMixin):
         act = get_nonlinearity(self.nonlinearity, return_module=False)
         xs, jump_xs = None, None
         res = {}
+        # every CSR plan of this batch (all dimensions, forward + backward, readout) in one kernel launch
+        ops.prepare_plans(data, self.max_dim, self.use_coboundaries, backward=torch.is_grad_enabled())
         # embed vertices (+edges) and populate the higher dimensions by boundary reduction
         params = data.get_all_cochain_params(max_dim=self.max_dim, include_down_features=False)
         xs = list(self.init_conv(*params))

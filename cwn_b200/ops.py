@@ -128,6 +128,48 @@ def build_plan(key: Tensor, n_rows: int, pay0: Tensor = None, pay1: Tensor = Non
     return Plan(rowptr, perm, p0, p1, n_rows, E)
 
 
+def build_plans(requests):
+    """Build many plans at once. `requests`: list of (key, n_rows, pay0, pay1). Every plan small enough for
+    cwn_csr_plan_build_small goes into ONE kernel launch (one CTA per plan); larger ones use the CUB path."""
+    if not requests:
+        return []
+    lib = _lib.load()
+    cap = lib.cwn_csr_plan_small_capacity()
+    plans = [None] * len(requests)
+    small, keep = [], []
+    for i, (key, n_rows, pay0, pay1) in enumerate(requests):
+        if key.numel() > cap:
+            plans[i] = build_plan(key, n_rows, pay0, pay1)
+            continue
+        if not key.is_cuda or key.dtype != torch.long:
+            raise RuntimeError('cwn_b200: index tensors must be CUDA torch.long tensors (CUDA-only path)')
+        dev, E = key.device, key.numel()
+        key = key.contiguous()
+        pay0 = pay0.contiguous() if pay0 is not None else None
+        pay1 = pay1.contiguous() if pay1 is not None else None
+        with torch.cuda.device(dev):
+            # one allocation per plan: [rowptr | perm | pay0 | pay1]
+            npay = (pay0 is not None) + (pay1 is not None)
+            buf = torch.empty(n_rows + 1 + E * (1 + npay), dtype=torch.int32, device=dev)
+        rowptr, perm = buf[:n_rows + 1], buf[n_rows + 1:n_rows + 1 + E]
+        off = n_rows + 1 + E
+        p0 = p1 = None
+        if pay0 is not None:
+            p0, off = buf[off:off + E], off + E
+        if pay1 is not None:
+            p1 = buf[off:off + E]
+        plans[i] = Plan(rowptr, perm, p0, p1, n_rows, E)
+        small.append(_lib.PlanDesc(_ptr(key), _ptr(pay0), _ptr(pay1), E, n_rows, rowptr.data_ptr(), _ptr(perm),
+                                   _ptr(p0), _ptr(p1)))
+        keep += [key, pay0, pay1]
+    if small:
+        arr = (_lib.PlanDesc * len(small))(*small)
+        algo = sum(12 * d.E * (1 + (d.pay0 is not None) + (d.pay1 is not None)) + 4 * (d.n_rows + 1) for d in small)
+        with torch.cuda.device(requests[0][0].device):
+            _call('csr_plan_build_small', algo, lib.cwn_csr_plan_build_small, arr, len(small), None, _stream())
+    return plans
+
+
 class Adjacency(object):
     """One adjacency of a cochain (`index` int64 [2, E]: row 0 = source, row 1 = destination; optional per-message
     coboundary/boundary id column `cob`) with its lazily built, cached CSR plans:
@@ -157,22 +199,79 @@ class Adjacency(object):
             adj._plans = {}
         return adj
 
+    def request(self, kind):
+        """(key, n_rows, pay0, pay1) of plan `kind`."""
+        src, dst = self.index[0], self.index[1]
+        if kind == 'by_dst':
+            return dst, self.n_dst, src, self.cob
+        if kind == 'by_src':
+            return src, self.n_src, dst, self.cob
+        return self.cob, self.n_cob, dst, src
+
     def _plan(self, kind):
         plan = self._plans.get(kind)
         if plan is None:
-            src, dst = self.index[0], self.index[1]
-            if kind == 'by_dst':
-                plan = build_plan(dst, self.n_dst, src, self.cob)
-            elif kind == 'by_src':
-                plan = build_plan(src, self.n_src, dst, self.cob)
-            else:
-                plan = build_plan(self.cob, self.n_cob, dst, src)
-            self._plans[kind] = plan
+            plan = self._plans[kind] = build_plans([self.request(kind)])[0]
         return plan
 
     by_dst = property(lambda self: self._plan('by_dst'))
     by_src = property(lambda self: self._plan('by_src'))
     by_cob = property(lambda self: self._plan('by_cob'))
+
+
+def _row_plan(idx: Tensor, n_rows: int, install: Plan = None) -> Plan:
+    """Plan grouping the entries of a 1-D index (readout `batch` vector, gather indices) by value; cached on it."""
+    cache = idx.__dict__.setdefault('_cwn_rowplan', {})
+    gen = (idx._version, idx.data_ptr())
+    if cache.get('gen') != gen:
+        cache.clear()
+        cache['gen'] = gen
+    if install is not None:
+        cache[n_rows] = install
+    plan = cache.get(n_rows)
+    if plan is None:
+        plan = cache[n_rows] = build_plans([(idx, n_rows, None, None)])[0]
+    return plan
+
+
+def prepare_plans(data, max_dim: int = 2, use_coboundaries: bool = False, backward: bool = True,
+                  readout: bool = True):
+    """Build, in ONE kernel launch, every CSR plan a SparseCIN-family forward (+ backward) pass over `data` will
+    ask for: per dimension the upper adjacency (by destination; by source and by coboundary for the gradients),
+    the boundary adjacency (by destination / by source) and the readout grouping of `batch`. Plans that are
+    already cached are skipped; anything not prepared here is still built lazily on first use."""
+    wanted = []  # (installer, request)
+    top = min(max_dim, data.dimension)
+    for d in range(top + 1):
+        c = data.cochains[d]
+        n = c.num_cells
+        if c.upper_index is not None and (d + 1) in data.cochains and c.upper_index.is_cuda:
+            cob, n_cob = None, None
+            if use_coboundaries and c.shared_coboundaries is not None:
+                cob, n_cob = c.shared_coboundaries, data.cochains[d + 1].num_cells
+            adj = Adjacency.of(c.upper_index, n, n, cob, n_cob)
+            kinds = ['by_dst'] + (['by_src'] + (['by_cob'] if cob is not None else []) if backward else [])
+            wanted += [(adj, k) for k in kinds if k not in adj._plans]
+        if d > 0 and c.boundary_index is not None and c.boundary_index.is_cuda:
+            adj = Adjacency.of(c.boundary_index, data.cochains[d - 1].num_cells, n)
+            wanted += [(adj, k) for k in (['by_dst', 'by_src'] if backward else ['by_dst']) if k not in adj._plans]
+    reqs = [adj.request(k) for adj, k in wanted]
+    pools = []
+    if readout:
+        size = getattr(data, 'num_complexes', None)
+        for d in range(top + 1):
+            b = data.cochains[d].batch
+            if size is not None and b is not None and b.is_cuda:
+                cache = b.__dict__.get('_cwn_rowplan', {})
+                if cache.get('gen') != (b._version, b.data_ptr()) or int(size) not in cache:
+                    pools.append(b)
+                    reqs.append((b, int(size), None, None))
+    plans = build_plans(reqs)
+    for (adj, k), plan in zip(wanted, plans):
+        adj._plans[k] = plan
+    for b, plan in zip(pools, plans[len(wanted):]):
+        _row_plan(b, plan.n_rows, install=plan)
+    return len(plans)
 
 
 def clear_plan_cache(*indices):
@@ -322,13 +421,7 @@ class _GatherRows(Function):
     @staticmethod
     def backward(ctx, g):
         g = _rows(g)
-        idx = ctx.idx
-        cache = idx.__dict__.setdefault('_cwn_rowplan', {})
-        k = (ctx.n, idx._version, idx.data_ptr())
-        plan = cache.get(k)
-        if plan is None:
-            cache.clear()
-            plan = cache[k] = build_plan(idx, ctx.n)
+        plan = _row_plan(ctx.idx, ctx.n)
         gx = _launch_gather_reduce(g, plan.rowptr, plan.perm, ctx.n, g.size(1), None, None, 0)
         if ctx.scale != 1.0:
             gx = gx * ctx.scale
@@ -340,12 +433,7 @@ class _ScatterRows(Function):
 
     @staticmethod
     def forward(ctx, msg, dst, n_dst, reduce):
-        cache = dst.__dict__.setdefault('_cwn_rowplan', {})
-        k = (n_dst, dst._version, dst.data_ptr())
-        plan = cache.get(k)
-        if plan is None:
-            cache.clear()
-            plan = cache[k] = build_plan(dst, n_dst)
+        plan = _row_plan(dst, n_dst)
         ctx.dst, ctx.plan, ctx.reduce = dst, plan, reduce
         return _launch_gather_reduce(msg, plan.rowptr, plan.perm, n_dst, msg.size(1), None, None,
                                      REDUCE_CODES[reduce])

@@ -1,0 +1,47 @@
+"""Fork/join execution of independent branches on concurrent CUDA streams.
+
+Within a layer the cochain dimensions are independent of each other, and inside a cochain the upper-adjacency
+branch and the boundary branch are independent until `combine_nn` (reference `mp/layers.py:184-199, 333-342` runs
+them one after the other). Each of their kernels covers only a few thousand rows — a fraction of the 148 SMs — so
+the branches are issued on side streams that fork from and re-join the current stream. Under CUDA-graph capture
+(`cwn_b200/graph.py`) the fork/join becomes graph edges: the replayed DAG runs the branches concurrently with no
+host involvement. Autograd replays each backward node on the stream of its forward op, so the backward pass gets
+the same concurrency.
+
+Memory safety relies on the fork/join discipline: every side stream waits for its parent before starting and the
+parent waits for all side streams before continuing, so a block freed after the join cannot be handed to a kernel
+that runs before its last reader.
+
+Set CWN_B200_STREAMS=0 to run everything on the current stream.
+"""
+import os
+
+import torch
+
+ENABLED = os.environ.get('CWN_B200_STREAMS', '1') != '0'
+_pools = {}
+
+
+def _side_streams(parent: torch.cuda.Stream, n: int):
+    key = (parent.device, parent.cuda_stream)
+    pool = _pools.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=parent.device))
+    return pool[:n]
+
+
+def run_concurrently(thunks, device=None):
+    """Run the zero-argument callables `thunks` as concurrent branches; returns their results in order."""
+    thunks = list(thunks)
+    if (not ENABLED or len(thunks) < 2 or device is None or torch.device(device).type != 'cuda'):
+        return [t() for t in thunks]
+    parent = torch.cuda.current_stream(device)
+    streams = _side_streams(parent, len(thunks))
+    outs = []
+    for s, t in zip(streams, thunks):
+        s.wait_stream(parent)
+        with torch.cuda.stream(s):
+            outs.append(t())
+    for s in streams:
+        parent.wait_stream(s)
+    return outs

@@ -71,6 +71,23 @@ int cwn_csr_plan_build(const int64_t* key, const int64_t* pay0, const int64_t* p
                        int32_t* rowptr, int32_t* perm, int32_t* pay0_sorted, int32_t* pay1_sorted,
                        int32_t* flags, void* workspace, size_t workspace_bytes, cwn_stream_t stream);
 
+/* All the plans of one batch in ONE kernel launch (one CTA per plan, block-wide stable radix sort in shared memory).
+ * Every plan must have E <= cwn_csr_plan_small_capacity() messages; `descs` is a HOST array read during the call
+ * (its device pointers follow the conventions of cwn_csr_plan_build). No workspace. */
+typedef struct {
+  const int64_t* key;
+  const int64_t* pay0; /* nullable */
+  const int64_t* pay1; /* nullable */
+  int64_t E;
+  int64_t n_rows;
+  int32_t* rowptr;
+  int32_t* perm;
+  int32_t* pay0_sorted;
+  int32_t* pay1_sorted;
+} cwn_plan_desc;
+int64_t cwn_csr_plan_small_capacity(void);
+int cwn_csr_plan_build_small(const cwn_plan_desc* descs, int32_t n_plans, int32_t* flags, cwn_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Fused gather -> (identity message) -> reduce, one destination row per thread group, no atomics:
  *   out[r,:] = (x_res ? (1 + *eps) * x_res[r,:] : 0) + REDUCE_{i in row r} x_src[ idx ? idx[i] : i , :]

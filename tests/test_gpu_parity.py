@@ -47,6 +47,23 @@ def test_csr_plan_is_a_stable_sort(E, n_rows):
     assert torch.equal(plan.pay0.cpu().long(), pay[order])
 
 
+def test_batched_plan_build_matches_single_builds():
+    """cwn_csr_plan_build_small (all plans of a batch in one launch) == the CUB path, incl. empty and oversized."""
+    g = torch.Generator().manual_seed(0)
+    specs = [(0, 7), (1, 1), (999, 40), (12288, 3200), (12289, 50), (5000, 1), (40_000, 9000), (300, 100_000)] * 3
+    reqs = []
+    for E, n_rows in specs:
+        key = torch.randint(0, n_rows, (E,), generator=g).to(DEV)
+        pay0 = torch.randint(0, 1 << 20, (E,), generator=g).to(DEV)
+        pay1 = torch.randint(0, 1 << 20, (E,), generator=g).to(DEV) if E % 2 else None
+        reqs.append((key, n_rows, pay0, pay1))
+    for plan, (key, n_rows, pay0, pay1) in zip(ops.build_plans(reqs), reqs):
+        ref = ops.build_plan(key, n_rows, pay0, pay1)
+        assert torch.equal(plan.rowptr, ref.rowptr) and torch.equal(plan.perm, ref.perm)
+        assert torch.equal(plan.pay0, ref.pay0)
+        assert (plan.pay1 is None) == (ref.pay1 is None) and (plan.pay1 is None or torch.equal(plan.pay1, ref.pay1))
+
+
 # ------------------------------------------------------------------------------------------------ fused identity pass
 @pytest.mark.parametrize('F', [1, 3, 4, 16, 20, 64, 100, 128, 256, 520])
 @pytest.mark.parametrize('reduce', ['add', 'mean', 'max'])
