@@ -418,6 +418,9 @@ def test_zinc_shaped_training_step_against_oracle():
     assert_close(out, ref, rtol=1e-5, atol=1e-5, what='out')
     assert_close(loss, ref_loss, rtol=1e-5, atol=1e-6, what='loss')
     for k, p in model.named_parameters():
+        if sd[k].grad is None:  # e.g. the coboundary message net of the top dimension: no upper adjacency there
+            assert p.grad is None or float(p.grad.abs().sum()) == 0.0, k
+            continue
         assert_close(p.grad, sd[k].grad, rtol=1e-4, atol=1e-5, what=f'grad {k}')
 
 
