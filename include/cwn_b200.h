@@ -127,6 +127,85 @@ int cwn_csr_cob_bwd_f32(const float* G, int64_t ld_g, const float* A, int64_t ld
                         const int32_t* rowptr, const int32_t* dst, const int32_t* oth, int64_t n_rows, int32_t F,
                         int32_t act, float* gA, int64_t ld_ga, cwn_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Dense update / combine nets of SparseCINConv (reference mp/layers.py:191-199, 303-325):
+ *   Linear -> BatchNorm -> act -> Linear -> BatchNorm -> act  (x2 branches),  Linear(2H->H) -> BatchNorm -> act.
+ * One "unit" is  z = f_in(X) W^T + b  followed by BatchNorm statistics over the rows, where the input transform
+ * f_in(x)[k] = act_in((x[k] - in_mean[k]) * in_scale[k] + in_beta[k]) is the PREVIOUS unit's BatchNorm + activation
+ * applied on the fly while the tile is loaded (so normalised activations are never written to HBM), and X may be the
+ * virtual concatenation [X0 | X1] (combine_nn's torch.cat). All entry points are GROUPED: `descs` is a host array of
+ * up to CWN_MAX_GROUP problems (the two branches of the three cochain dimensions) served by ONE launch.
+ * fp32 FFMA throughout: TF32 tensor cores cannot meet the 1e-5 rtol parity gate at K = 64..128.
+ */
+#define CWN_MAX_GROUP 8
+
+typedef struct {
+  const float* x0; int64_t ld_x0; int32_t k0;              /* first input block  [n_rows, k0] */
+  const float* x1; int64_t ld_x1; int32_t k1;              /* optional second block (k1 = 0: absent) */
+  const float* in_mean0; const float* in_scale0; const float* in_beta0; /* per-column input transform, NULL = none */
+  const float* in_mean1; const float* in_scale1; const float* in_beta1;
+  int32_t in_act;                                          /* CWN_ACT_* applied after the affine */
+  const float* w; int64_t ld_w;                            /* [h, k0 + k1] row-major (torch Linear.weight) */
+  const float* bias;                                       /* [h], nullable */
+  float* z; int64_t ld_z;                                  /* output [n_rows, h] */
+  float* stats;                                            /* nullable: per row tile (64 rows) [n_tiles, 2, h] = (mean, M2) */
+  int64_t n_rows; int32_t h;
+} cwn_linear_desc;
+int cwn_linear_fwd_grouped(const cwn_linear_desc* descs, int32_t n, cwn_stream_t stream);
+
+/* BatchNorm statistics from the per-tile partials of cwn_linear_fwd_grouped (training), or from the running
+ * statistics (training = 0). Writes mean[h], scale[h] = gamma * rstd, rstd[h]; in training mode also updates
+ * running_mean / running_var (unbiased) with `momentum` and increments num_batches_tracked (all nullable). */
+typedef struct {
+  const float* stats; int32_t n_tiles; int64_t n_rows; int32_t h;
+  const float* gamma; const float* beta; float eps; float momentum; int32_t training;
+  float* running_mean; float* running_var; int64_t* num_batches_tracked;
+  float* mean; float* scale; float* rstd;
+} cwn_bn_desc;
+int cwn_bn_finalize_grouped(const cwn_bn_desc* descs, int32_t n, cwn_stream_t stream);
+
+/* out = act((z - mean) * scale + beta): the layer output that neighbouring cells gather from. */
+typedef struct {
+  const float* z; int64_t ld_z; const float* mean; const float* scale; const float* beta; int32_t act;
+  float* out; int64_t ld_out; int64_t n_rows; int32_t h;
+} cwn_bn_act_desc;
+int cwn_bn_act_grouped(const cwn_bn_act_desc* descs, int32_t n, cwn_stream_t stream);
+
+/* Backward of one unit. With y = (z - mean) * scale + beta, out = act(y), zhat = (z - mean) * rstd:
+ *   step 1 (cwn_unit_bwd_reduce_grouped): per-tile partials of s1 = SUM_rows g_out * act'(y), s2 = SUM_rows g_out * act'(y) * zhat
+ *   step 2 (cwn_unit_bwd_finalize_grouped): c1 = s1/N, c2 = s2/N, g_gamma = s2, g_beta = s1
+ *   step 3 (cwn_unit_bwd_grouped): g_z = scale * (g_out*act'(y) - c1 - zhat*c2)   [has_bn = 0: g_z = g_out * act'(z)]
+ *            g_in = g_z W (gradient w.r.t. f_in(X), split into g_in0 | g_in1), per-CTA partials of
+ *            g_W = g_z^T f_in(X) and g_b = SUM_rows g_z
+ *   step 4 (cwn_wgrad_finalize_grouped): ordered sum of the partials -> g_W, g_b (accumulated INTO the outputs if accumulate != 0)
+ * Everything is deterministic (no atomics). */
+typedef struct {
+  /* forward operands (saved) */
+  const float* x0; int64_t ld_x0; int32_t k0; const float* x1; int64_t ld_x1; int32_t k1;
+  const float* in_mean0; const float* in_scale0; const float* in_beta0;
+  const float* in_mean1; const float* in_scale1; const float* in_beta1; int32_t in_act;
+  const float* w; int64_t ld_w;
+  const float* z; int64_t ld_z; int32_t has_bn; int32_t act;   /* act of THIS unit's output (CWN_ACT_ID if none) */
+  const float* mean; const float* scale; const float* rstd; const float* beta;
+  /* incoming gradient w.r.t. the unit's output */
+  const float* g_out; int64_t ld_g;
+  /* BN-backward reductions */
+  float* red_partials;   /* [n_tiles, 2, h] */
+  float* c1; float* c2;  /* [h] each */
+  float* g_gamma; float* g_beta; int32_t accumulate_affine;
+  /* outputs */
+  float* g_in0; int64_t ld_gi0; float* g_in1; int64_t ld_gi1;   /* nullable: gradient not needed */
+  float* w_partials;     /* [n_ctas, h, k0+k1] */
+  float* b_partials;     /* [n_ctas, h] */
+  int32_t n_ctas;        /* CTAs assigned to this problem in step 3 (each strides over the row tiles) */
+  float* g_w; int64_t ld_gw; float* g_b; int32_t accumulate_w;
+  int64_t n_rows; int32_t h;
+} cwn_unit_bwd_desc;
+int cwn_unit_bwd_reduce_grouped(const cwn_unit_bwd_desc* descs, int32_t n, cwn_stream_t stream);
+int cwn_unit_bwd_finalize_grouped(const cwn_unit_bwd_desc* descs, int32_t n, cwn_stream_t stream);
+int cwn_unit_bwd_grouped(const cwn_unit_bwd_desc* descs, int32_t n, cwn_stream_t stream);
+int cwn_wgrad_finalize_grouped(const cwn_unit_bwd_desc* descs, int32_t n, cwn_stream_t stream);
+
 /* Debug aid: sets bit 1 of flags[0] if any idx[e] is outside [0, n). (The reference relies on torch's device
  * assert for out-of-range indices.) */
 int cwn_check_index_range(const int64_t* idx, int64_t E, int64_t n, int32_t* flags, cwn_stream_t stream);
