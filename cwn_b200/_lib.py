@@ -20,6 +20,44 @@ class PlanDesc(ctypes.Structure):
                 ('perm', ctypes.c_void_p), ('pay0_sorted', ctypes.c_void_p), ('pay1_sorted', ctypes.c_void_p)]
 
 
+_P, _I64, _I32, _F = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float
+
+
+class LinearDesc(ctypes.Structure):
+    """cwn_linear_desc"""
+    _fields_ = [('x0', _P), ('ld_x0', _I64), ('k0', _I32), ('x1', _P), ('ld_x1', _I64), ('k1', _I32),
+                ('in_mean0', _P), ('in_scale0', _P), ('in_beta0', _P), ('in_mean1', _P), ('in_scale1', _P),
+                ('in_beta1', _P), ('in_act', _I32), ('w', _P), ('ld_w', _I64), ('bias', _P), ('z', _P),
+                ('ld_z', _I64), ('stats', _P), ('n_rows', _I64), ('h', _I32)]
+
+
+class BNDesc(ctypes.Structure):
+    """cwn_bn_desc"""
+    _fields_ = [('stats', _P), ('n_tiles', _I32), ('n_rows', _I64), ('h', _I32), ('gamma', _P), ('beta', _P),
+                ('eps', _F), ('momentum', _F), ('training', _I32), ('running_mean', _P), ('running_var', _P),
+                ('num_batches_tracked', _P), ('mean', _P), ('scale', _P), ('rstd', _P)]
+
+
+class BNActDesc(ctypes.Structure):
+    """cwn_bn_act_desc"""
+    _fields_ = [('z', _P), ('ld_z', _I64), ('mean', _P), ('scale', _P), ('beta', _P), ('act', _I32), ('out', _P),
+                ('ld_out', _I64), ('n_rows', _I64), ('h', _I32)]
+
+
+class UnitBwdDesc(ctypes.Structure):
+    """cwn_unit_bwd_desc"""
+    _fields_ = [('x0', _P), ('ld_x0', _I64), ('k0', _I32), ('x1', _P), ('ld_x1', _I64), ('k1', _I32),
+                ('in_mean0', _P), ('in_scale0', _P), ('in_beta0', _P), ('in_mean1', _P), ('in_scale1', _P),
+                ('in_beta1', _P), ('in_act', _I32), ('w', _P), ('ld_w', _I64), ('z', _P), ('ld_z', _I64),
+                ('has_bn', _I32), ('act', _I32), ('mean', _P), ('scale', _P), ('rstd', _P), ('beta', _P),
+                ('g_out', _P), ('ld_g', _I64), ('red_partials', _P), ('c1', _P), ('c2', _P), ('g_gamma', _P),
+                ('g_beta', _P), ('accumulate_affine', _I32), ('g_in0', _P), ('ld_gi0', _I64), ('g_in1', _P),
+                ('ld_gi1', _I64), ('w_partials', _P), ('b_partials', _P), ('n_ctas', _I32), ('g_w', _P),
+                ('ld_gw', _I64), ('g_b', _P), ('accumulate_w', _I32), ('n_rows', _I64), ('h', _I32)]
+
+
+MAX_GROUP = 8
+
 _SIGNATURES = {
     'cwn_version': (ctypes.c_char_p, []),
     'cwn_last_error_string': (ctypes.c_char_p, []),
@@ -36,6 +74,13 @@ _SIGNATURES = {
                                            _i32, _c_f32p, _i64, _c_f32p, _c_f32p, _i64, _vp]),
     'cwn_csr_cob_bwd_f32': (ctypes.c_int, [_c_f32p, _i64, _c_f32p, _i64, _c_f32p, _i64, _c_i32p, _c_i32p,
                                            _c_i32p, _i64, _i32, _i32, _c_f32p, _i64, _vp]),
+    'cwn_linear_fwd_grouped': (ctypes.c_int, [ctypes.POINTER(LinearDesc), _i32, _vp]),
+    'cwn_bn_finalize_grouped': (ctypes.c_int, [ctypes.POINTER(BNDesc), _i32, _vp]),
+    'cwn_bn_act_grouped': (ctypes.c_int, [ctypes.POINTER(BNActDesc), _i32, _vp]),
+    'cwn_unit_bwd_reduce_grouped': (ctypes.c_int, [ctypes.POINTER(UnitBwdDesc), _i32, _vp]),
+    'cwn_unit_bwd_finalize_grouped': (ctypes.c_int, [ctypes.POINTER(UnitBwdDesc), _i32, _vp]),
+    'cwn_unit_bwd_grouped': (ctypes.c_int, [ctypes.POINTER(UnitBwdDesc), _i32, _vp]),
+    'cwn_wgrad_finalize_grouped': (ctypes.c_int, [ctypes.POINTER(UnitBwdDesc), _i32, _vp]),
     'cwn_check_index_range': (ctypes.c_int, [_c_i64p, _i64, _i64, _c_i32p, _vp]),
 }
 

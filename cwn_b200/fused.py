@@ -1,0 +1,301 @@
+"""The dense update / combine nets of one `SparseCINConv` layer — all cochain dimensions, both branches — as ONE
+autograd node over the grouped kernels of `csrc/dense.cu`.
+
+Reference semantics (mp/layers.py:191-199 with the default nets of :303-325), per dimension d:
+    a_up  = act(BN(Linear(act(BN(Linear(u_d))))))          update_up_nn
+    a_bnd = act(BN(Linear(act(BN(Linear(b_d))))))          update_boundaries_nn
+    out_d = act(BN(Linear(cat[a_up, a_bnd])))              combine_nn
+where u_d / b_d are the aggregated upper / boundary messages with the GIN residual already added. PyTorch runs this
+as ~40 library kernels per dimension per layer (plus as many again in backward); here a layer is 7 launches forward
+(3 grouped GEMM+statistics, 3 grouped BatchNorm finalisations, 1 grouped BatchNorm+activation) and 11 backward,
+BatchNorm in training mode with exact batch statistics, running statistics updated as torch does.
+
+Supported closed form: `graph_norm` BatchNorm1d (affine, tracking running statistics) or Identity, activation in
+{relu, elu, id, sigmoid, tanh}. Anything else (LayerNorm, user-supplied nets, eval-mode backward, a cochain with a
+single cell — where torch's BatchNorm raises) makes `recognise()` / `applicable()` return None / False and the
+layer runs through its torch modules instead.
+"""
+import ctypes
+
+import torch
+from torch.autograd import Function
+from torch.nn import BatchNorm1d, Identity, Linear, Sequential
+
+from cwn_b200 import _lib, ops
+from cwn_b200.mp.nn import activation_name
+
+TM = 64  # row tile of csrc/dense.cu
+
+
+class _Unit(object):
+    """Linear (+ optional BatchNorm) (+ activation) as the kernels see it."""
+    __slots__ = ('lin', 'bn', 'act')
+
+    def __init__(self, lin, bn, act):
+        self.lin, self.bn, self.act = lin, bn, act
+
+
+def _parse(seq, n_units):
+    """Sequential(Linear, norm, act[, Linear, norm, act]) -> list of _Unit, or None if it is something else."""
+    if not isinstance(seq, Sequential) or len(seq) != 3 * n_units:
+        return None
+    units = []
+    for i in range(n_units):
+        lin, norm, act = seq[3 * i], seq[3 * i + 1], seq[3 * i + 2]
+        if not isinstance(lin, Linear) or lin.bias is None:
+            return None
+        if isinstance(norm, BatchNorm1d):
+            if not (norm.affine and norm.track_running_stats and norm.momentum is not None):
+                return None
+        elif not isinstance(norm, Identity):
+            return None
+        name = activation_name(act)
+        if name is None:
+            return None
+        units.append(_Unit(lin, norm if isinstance(norm, BatchNorm1d) else None, name))
+    return units
+
+
+def recognise(level):
+    """(up units, boundary units, combine unit) of a SparseCINCochainConv built with the default nets, else None."""
+    up = _parse(level.update_up_nn, 2)
+    bnd = _parse(level.update_boundaries_nn, 2)
+    comb = _parse(level.combine_nn, 1)
+    if up is None or bnd is None or comb is None:
+        return None
+    if len({u.act for u in up + bnd}) != 1:
+        return None
+    h = up[1].lin.out_features
+    if bnd[1].lin.out_features != h or comb[0].lin.in_features != 2 * h:
+        return None
+    if up[0].lin.out_features != up[1].lin.in_features or bnd[0].lin.out_features != bnd[1].lin.in_features:
+        return None
+    if max(u.lin.out_features for u in up + bnd + comb) > 128:
+        return None  # shared-memory budget of unit_bwd_kernel
+    return up, bnd, comb[0]
+
+
+def applicable(forms, us, bs, training):
+    if any(f is None for f in forms):
+        return False
+    for f, u, b in zip(forms, us, bs):
+        if not (u.is_cuda and u.dtype == torch.float32 and u.dim() == 2 and b.shape == u.shape):
+            return False
+        if u.size(1) != f[0][0].lin.in_features or b.size(1) != f[1][0].lin.in_features:
+            return False
+        has_bn = any(unit.bn is not None for unit in f[0] + f[1] + [f[2]])
+        if has_bn and training and u.size(0) < 2:
+            return False  # torch raises "Expected more than 1 value per channel"; keep that behaviour
+        if has_bn and not training and torch.is_grad_enabled():
+            return False  # eval-mode BatchNorm backward: rare, leave it to torch
+    return True
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _launch(fn_name, desc_type, descs):
+    lib = _lib.load()
+    fn = getattr(lib, fn_name)
+    stream = torch.cuda.current_stream().cuda_stream
+    for i in range(0, len(descs), _lib.MAX_GROUP):
+        chunk = descs[i:i + _lib.MAX_GROUP]
+        arr = (desc_type * len(chunk))(*chunk)
+        ops._call(fn_name[4:], 0, fn, arr, len(chunk), stream)
+
+
+class _UnitState(object):
+    """Everything one unit keeps between forward and backward."""
+    __slots__ = ('unit', 'x0', 'x1', 'in0', 'in1', 'in_act', 'z', 'mean', 'scale', 'rstd', 'n', 'h')
+
+
+def _in_vectors(prev):
+    """(mean, scale, beta) of the BatchNorm feeding a unit's input, or None if that unit had no BatchNorm."""
+    if prev is None or prev.unit.bn is None:
+        return None
+    return prev.mean, prev.scale, prev.unit.bn.bias
+
+
+class FusedSparseCINDense(Function):
+    """outs = f(us[0], bs[0], us[1], bs[1], ..., *parameters). `ctx_forms` carries the module structure."""
+
+    @staticmethod
+    def forward(ctx, forms, training, n_dims, *tensors):
+        us, bs = list(tensors[0:2 * n_dims:2]), list(tensors[1:2 * n_dims:2])
+        dev = us[0].device
+        with torch.cuda.device(dev):
+            states = []  # per dim: dict name -> _UnitState
+
+            def new_state(unit, x0, x1, prev0, prev1):
+                st = _UnitState()
+                st.unit, st.x0, st.x1 = unit, x0, x1
+                st.in0, st.in1 = _in_vectors(prev0), _in_vectors(prev1)
+                st.in_act = prev0.unit.act if prev0 is not None else 'id'
+                st.n, st.h = x0.size(0), unit.lin.out_features
+                st.z = torch.empty(st.n, st.h, dtype=torch.float32, device=dev)
+                st.mean = st.scale = st.rstd = None
+                return st
+
+            def run_units(sts):
+                lin, bn = [], []
+                keep = []
+                for st in sts:
+                    unit = st.unit
+                    n_tiles = (st.n + TM - 1) // TM
+                    stats = None
+                    if unit.bn is not None:
+                        st.mean, st.scale, st.rstd = (torch.empty(st.h, dtype=torch.float32, device=dev) for _ in range(3))
+                        if training:
+                            stats = torch.empty(max(n_tiles, 1) * 2 * st.h, dtype=torch.float32, device=dev)
+                            keep.append(stats)
+                    i0 = st.in0 or (None, None, None)
+                    i1 = st.in1 or (None, None, None)
+                    lin.append(_lib.LinearDesc(
+                        _p(st.x0), st.x0.stride(0), st.x0.size(1), _p(st.x1), st.x1.stride(0) if st.x1 is not None else 0,
+                        st.x1.size(1) if st.x1 is not None else 0, _p(i0[0]), _p(i0[1]), _p(i0[2]), _p(i1[0]), _p(i1[1]),
+                        _p(i1[2]), ops.ACT_CODES[st.in_act], _p(unit.lin.weight), unit.lin.weight.stride(0),
+                        _p(unit.lin.bias), _p(st.z), st.h, _p(stats), st.n, st.h))
+                    if unit.bn is not None:
+                        m = unit.bn
+                        bn.append(_lib.BNDesc(_p(stats), n_tiles, st.n, st.h, _p(m.weight), _p(m.bias), float(m.eps),
+                                              float(m.momentum), int(training), _p(m.running_mean), _p(m.running_var),
+                                              _p(m.num_batches_tracked), _p(st.mean), _p(st.scale), _p(st.rstd)))
+                _launch('cwn_linear_fwd_grouped', _lib.LinearDesc, lin)
+                if bn:
+                    _launch('cwn_bn_finalize_grouped', _lib.BNDesc, bn)
+
+            l1, l2, l3 = [], [], []
+            for d in range(n_dims):
+                up, bnd, comb = forms[d]
+                s = {}
+                s['u1'] = new_state(up[0], us[d].contiguous(), None, None, None)
+                s['b1'] = new_state(bnd[0], bs[d].contiguous(), None, None, None)
+                states.append(s)
+                l1 += [s['u1'], s['b1']]
+            run_units(l1)
+            for d in range(n_dims):
+                up, bnd, comb = forms[d]
+                s = states[d]
+                s['u2'] = new_state(up[1], s['u1'].z, None, s['u1'], None)
+                s['b2'] = new_state(bnd[1], s['b1'].z, None, s['b1'], None)
+                l2 += [s['u2'], s['b2']]
+            run_units(l2)
+            for d in range(n_dims):
+                s = states[d]
+                s['c'] = new_state(forms[d][2], s['u2'].z, s['b2'].z, s['u2'], s['b2'])
+                l3.append(s['c'])
+            run_units(l3)
+            outs, descs = [], []
+            for d in range(n_dims):
+                st = states[d]['c']
+                out = torch.empty(st.n, st.h, dtype=torch.float32, device=dev)
+                beta = st.unit.bn.bias if st.unit.bn is not None else None
+                descs.append(_lib.BNActDesc(_p(st.z), st.h, _p(st.mean), _p(st.scale), _p(beta),
+                                            ops.ACT_CODES[st.unit.act], _p(out), st.h, st.n, st.h))
+                outs.append(out)
+            _launch('cwn_bn_act_grouped', _lib.BNActDesc, descs)
+        ctx.states, ctx.n_dims, ctx.forms = states, n_dims, forms
+        ctx.n_inputs = len(tensors)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *g_outs):
+        states, n_dims = ctx.states, ctx.n_dims
+        dev = states[0]['c'].z.device
+        grads = {}  # id(parameter) -> gradient tensor
+        keep = []
+
+        def new(*shape):
+            t = torch.empty(*shape, dtype=torch.float32, device=dev)
+            keep.append(t)
+            return t
+
+        def unit_descs(items):
+            """items: list of (state, g_out, want_g_in0, want_g_in1) -> (descs, list of (g_in0, g_in1))"""
+            descs, gins = [], []
+            for st, g, want0, want1 in items:
+                unit = st.unit
+                k0 = st.x0.size(1)
+                k1 = st.x1.size(1) if st.x1 is not None else 0
+                n_tiles = (st.n + TM - 1) // TM
+                n_ctas = min(n_tiles, 148)
+                has_bn = unit.bn is not None
+                g = g.contiguous()
+                gi0 = new(st.n, k0) if want0 else None
+                gi1 = new(st.n, k1) if (want1 and k1) else None
+                gw, gb = new(st.h, k0 + k1), new(st.h)
+                grads[id(unit.lin.weight)], grads[id(unit.lin.bias)] = gw, gb
+                red = c1 = c2 = gg = gbeta = None
+                if has_bn:
+                    red, c1, c2, gg, gbeta = new(max(n_tiles, 1) * 2 * st.h), new(st.h), new(st.h), new(st.h), new(st.h)
+                    grads[id(unit.bn.weight)], grads[id(unit.bn.bias)] = gg, gbeta
+                i0 = st.in0 or (None, None, None)
+                i1 = st.in1 or (None, None, None)
+                descs.append(_lib.UnitBwdDesc(
+                    _p(st.x0), st.x0.stride(0), k0, _p(st.x1), st.x1.stride(0) if st.x1 is not None else 0, k1,
+                    _p(i0[0]), _p(i0[1]), _p(i0[2]), _p(i1[0]), _p(i1[1]), _p(i1[2]), ops.ACT_CODES[st.in_act],
+                    _p(unit.lin.weight), unit.lin.weight.stride(0), _p(st.z), st.h, int(has_bn),
+                    ops.ACT_CODES[unit.act], _p(st.mean), _p(st.scale), _p(st.rstd),
+                    _p(unit.bn.bias) if has_bn else None, _p(g), g.stride(0), _p(red), _p(c1), _p(c2), _p(gg),
+                    _p(gbeta), 0, _p(gi0), k0, _p(gi1), k1, _p(new(max(n_ctas, 1) * st.h * (k0 + k1))),
+                    _p(new(max(n_ctas, 1) * st.h)), n_ctas, _p(gw), k0 + k1, _p(gb), 0, st.n, st.h))
+                keep.append(g)
+                gins.append((gi0, gi1))
+            return descs, gins
+
+        def run(items):
+            descs, gins = unit_descs(items)
+            if any(d.has_bn for d in descs):
+                _launch('cwn_unit_bwd_reduce_grouped', _lib.UnitBwdDesc, descs)
+                _launch('cwn_unit_bwd_finalize_grouped', _lib.UnitBwdDesc, descs)
+            _launch('cwn_unit_bwd_grouped', _lib.UnitBwdDesc, descs)
+            return descs, gins
+
+        with torch.cuda.device(dev):
+            all_descs = []
+            g_outs = [g if g is not None else torch.zeros_like(states[d]['c'].z) for d, g in enumerate(g_outs)]
+            descs, gins = run([(states[d]['c'], g_outs[d], True, True) for d in range(n_dims)])
+            all_descs += descs
+            items = []
+            for d in range(n_dims):
+                items += [(states[d]['u2'], gins[d][0], True, False), (states[d]['b2'], gins[d][1], True, False)]
+            descs, gins2 = run(items)
+            all_descs += descs
+            need_u = [ctx.needs_input_grad[3 + 2 * d] for d in range(n_dims)]
+            need_b = [ctx.needs_input_grad[4 + 2 * d] for d in range(n_dims)]
+            items = []
+            for d in range(n_dims):
+                items += [(states[d]['u1'], gins2[2 * d][0], need_u[d], False),
+                          (states[d]['b1'], gins2[2 * d + 1][0], need_b[d], False)]
+            descs, gins1 = run(items)
+            all_descs += descs
+            _launch('cwn_wgrad_finalize_grouped', _lib.UnitBwdDesc, all_descs)
+
+        out = [None, None, None]
+        for d in range(n_dims):
+            out += [gins1[2 * d][0], gins1[2 * d + 1][0]]
+        out += [grads.get(id(p)) for p in _parameters(ctx.forms)]
+        ctx.states = None
+        return tuple(out)
+
+
+def _parameters(forms):
+    params = []
+    for up, bnd, comb in forms:
+        for unit in up + bnd + [comb]:
+            params += [unit.lin.weight, unit.lin.bias]
+            if unit.bn is not None:
+                params += [unit.bn.weight, unit.bn.bias]
+    return params
+
+
+def sparse_cin_dense(forms, us, bs, training):
+    """Run the update/combine nets of every dimension of a layer. `forms[d] = recognise(level_d)`."""
+    n_dims = len(us)
+    params = _parameters(forms)
+    flat = []
+    for u, b in zip(us, bs):
+        flat += [u, b]
+
+    return list(FusedSparseCINDense.apply(forms, training, n_dims, *flat, *params))

@@ -245,6 +245,13 @@ class SparseCINCochainConv(CochainMessagePassing):
 
         return up_branch, boundary_branch
 
+    def dense_tail(self, agg_up, agg_boundaries):
+        """update nets + combine on the aggregated (residual included) messages, through the torch modules."""
+        out_up, out_boundaries = run_concurrently([lambda: self.update_up_nn(agg_up),
+                                                   lambda: self.update_boundaries_nn(agg_boundaries)],
+                                                  agg_up.device)
+        return self.combine_nn(torch.cat([out_up, out_boundaries], dim=-1))
+
     def forward(self, cochain: CochainMessagePassingParams):
         fused = self._fused_forward(cochain)
         if fused is NotImplemented:
@@ -281,7 +288,31 @@ class SparseCINConv(_PerDimension):
     """Cellular GIN with messages from upper neighbours and boundaries, one `SparseCINCochainConv` per dimension
     with its own nets unless `passed_*` callables are supplied (reference `mp/layers.py:271-342`).
 
-    kwargs: `layer_dim`, `hidden`, `act_module`."""
+    kwargs: `layer_dim`, `hidden`, `act_module`.
+
+    When every level carries the default nets, a layer runs as: all aggregation passes of all dimensions as
+    concurrent branches, then the update/combine nets of all dimensions as ONE fused autograd node
+    (`cwn_b200.fused`); otherwise each level runs on its own (torch modules for the dense nets)."""
+
+    fuse_dense = True
+
+    def forward(self, *cochain_params: CochainMessagePassingParams, start_to_process=0):
+        assert len(cochain_params) <= self.max_dim + 1
+        n = len(cochain_params)
+        if self.fuse_dense and start_to_process == 0 and n > 0:
+            from cwn_b200 import fused
+            forms = getattr(self, '_dense_forms', None)
+            if forms is None:
+                forms = self._dense_forms = [fused.recognise(level) for level in self.mp_levels]
+            branches = [self.mp_levels[d]._fused_forward(cochain_params[d]) for d in range(n)]
+            if all(f is not None for f in forms[:n]) and all(b is not NotImplemented for b in branches):
+                device = cochain_params[0].x.device
+                aggs = run_concurrently([t for pair in branches for t in pair], device)
+                us, bs = aggs[0::2], aggs[1::2]
+                if fused.applicable(forms[:n], us, bs, self.mp_levels[0].training):
+                    return fused.sparse_cin_dense(forms[:n], us, bs, self.mp_levels[0].training)
+                return [self.mp_levels[d].dense_tail(us[d], bs[d]) for d in range(n)]
+        return super(SparseCINConv, self).forward(*cochain_params, start_to_process=start_to_process)
 
     def __init__(self, up_msg_size: int, down_msg_size: int, boundary_msg_size: Optional[int],
                  passed_msg_up_nn: Optional[Callable], passed_msg_boundaries_nn: Optional[Callable],

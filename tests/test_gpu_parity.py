@@ -501,3 +501,58 @@ def test_captured_cuda_graph_step_equals_eager_step():
         assert_close(b_graph.flat, b_eager.flat, rtol=1e-5, atol=1e-6, what='flat gradient bucket')
     with pytest.raises(ValueError, match='layouts differ'):
         cap.run(ComplexBatch.from_complex_list(synthetic.zinc_like_complexes(9, seed=3)).pack_())
+
+
+@pytest.mark.parametrize('layer_dim,hidden,act,norm,cob', [(64, 64, 'relu', 'bn', True), (8, 20, 'elu', 'bn', False),
+                                                           (16, 16, 'tanh', 'id', True), (32, 128, 'relu', 'bn', True),
+                                                           (5, 5, 'sigmoid', 'bn', False), (12, 70, 'id', 'bn', True)])
+def test_fused_dense_layer_equals_torch_modules(layer_dim, hidden, act, norm, cob):
+    """cwn_b200.fused (grouped Linear+BatchNorm+act kernels, all dimensions in one autograd node) against the same
+    SparseCINConv run through its torch modules: outputs, input gradients, every parameter gradient and the
+    BatchNorm running statistics of a training-mode step; plus eval mode."""
+    from cwn_b200.mp.layers import SparseCINConv
+    from cwn_b200.mp.nn import get_graph_norm, get_nonlinearity
+    torch.manual_seed(1)
+    mk = lambda: SparseCINConv(layer_dim, layer_dim, layer_dim, None, None, None, None, layer_dim=layer_dim,  # noqa: E731
+                               hidden=hidden, act_module=get_nonlinearity(act), graph_norm=get_graph_norm(norm),
+                               use_coboundaries=cob, train_eps=True).to(DEV)
+    fused_conv, torch_conv = mk(), mk()
+    torch_conv.load_state_dict(fused_conv.state_dict())
+    torch_conv.fuse_dense = False
+    comps = synthetic.float_feature_complexes(7, layer_dim, seed=11, ragged=True)
+    results = []
+    for conv in (fused_conv, torch_conv):
+        conv.train()
+        batch = ComplexBatch.from_complex_list(
+            synthetic.float_feature_complexes(7, layer_dim, seed=11, ragged=True)).to(DEV)
+        for d in range(3):
+            batch.cochains[d]._x = batch.cochains[d].x.clone().requires_grad_(True)
+        params = batch.get_all_cochain_params(max_dim=2, include_down_features=False)
+        outs = conv(*params)
+        g = torch.Generator(device=DEV).manual_seed(3)
+        loss = sum((o * torch.randn(o.shape, device=DEV, generator=g)).sum() for o in outs)
+        loss.backward()
+        results.append((outs, [batch.cochains[d].x.grad for d in range(3)], dict(conv.named_parameters()),
+                        dict(conv.named_buffers())))
+    (o1, gx1, p1, b1), (o2, gx2, p2, b2) = results
+    for d in range(3):
+        assert_close(o1[d], o2[d], rtol=1e-5, atol=2e-5, what=f'out {d}')
+        assert_close(gx1[d], gx2[d], rtol=1e-4, atol=5e-5, what=f'grad x {d}')
+    for k in p1:
+        if p2[k].grad is None:
+            assert p1[k].grad is None or float(p1[k].grad.abs().sum()) == 0, k
+        else:
+            scale = float(p2[k].grad.abs().max()) + 1e-6
+            assert_close(p1[k].grad, p2[k].grad, rtol=1e-4, atol=1e-4 * scale, what=f'grad {k}')
+    for k in b1:
+        assert_close(b1[k].float(), b2[k].float(), rtol=1e-5, atol=1e-6, what=f'buffer {k}')
+    with torch.no_grad():
+        for conv in (fused_conv, torch_conv):
+            conv.eval()
+        outs = []
+        for conv in (fused_conv, torch_conv):
+            batch = ComplexBatch.from_complex_list(
+                synthetic.float_feature_complexes(7, layer_dim, seed=11, ragged=True)).to(DEV)
+            outs.append(conv(*batch.get_all_cochain_params(max_dim=2, include_down_features=False)))
+        for d in range(3):
+            assert_close(outs[0][d], outs[1][d], rtol=1e-5, atol=2e-5, what=f'eval out {d}')
