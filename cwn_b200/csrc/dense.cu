@@ -88,19 +88,67 @@ __device__ __forceinline__ void tile_mma(const float* __restrict__ As, int lda, 
   }
 }
 
-// f_in(X)[row][k] for the (possibly concatenated, possibly BatchNorm+activation-transformed) unit input
+// f_in(X)[row][k] for the (possibly concatenated, possibly BatchNorm+activation-transformed) unit input.
+// `vin` = the per-column (mean, scale, beta) of the input transform staged in shared memory: vin[0..K4) mean,
+// vin[K4..2K4) scale, vin[2K4..3K4) beta (identity = 0, 1, 0).
 template <class D>
-__device__ __forceinline__ float unit_input(const D& d, int64_t row, int k) {
-  float v;
-  if (k < d.k0) {
-    v = __ldg(d.x0 + row * d.ld_x0 + k);
-    if (d.in_scale0) v = (v - __ldg(d.in_mean0 + k)) * __ldg(d.in_scale0 + k) + __ldg(d.in_beta0 + k);
-  } else {
-    const int k1 = k - d.k0;
-    v = __ldg(d.x1 + row * d.ld_x1 + k1);
-    if (d.in_scale1) v = (v - __ldg(d.in_mean1 + k1)) * __ldg(d.in_scale1 + k1) + __ldg(d.in_beta1 + k1);
+__device__ __forceinline__ void stage_input_vectors(const D& d, float* vin, int K, int K4) {
+  for (int k = threadIdx.x; k < K4; k += DT) {
+    float m = 0.f, sc = 1.f, b = 0.f;
+    if (k < d.k0) {
+      if (d.in_scale0) { m = __ldg(d.in_mean0 + k); sc = __ldg(d.in_scale0 + k); b = __ldg(d.in_beta0 + k); }
+    } else if (k < K) {
+      const int k1 = k - d.k0;
+      if (d.in_scale1) { m = __ldg(d.in_mean1 + k1); sc = __ldg(d.in_scale1 + k1); b = __ldg(d.in_beta1 + k1); }
+    }
+    vin[k] = m; vin[K4 + k] = sc; vin[2 * K4 + k] = b;
   }
-  return act_apply(d.in_act, v);
+}
+
+template <class D>
+__device__ __forceinline__ bool input_vec_ok(const D& d) {
+  auto ok = [](const float* p, int64_t ld) { return ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) && (ld % 4 == 0); };
+  return (d.k0 % 4 == 0) && (d.k1 % 4 == 0) && ok(d.x0, d.ld_x0) && (d.k1 == 0 || ok(d.x1, d.ld_x1));
+}
+
+// dst[r * ldd + (k - kc)] = f_in(X)[row0 + r][k] for r < TM, k in [kc, kc + width), zero outside the matrix.
+// 128-bit loads when the layout allows; (r, column) advance incrementally so there is one division per thread.
+template <class D>
+__device__ __forceinline__ void load_input_tile(const D& d, const float* vin, int K, int K4, int64_t row0, int rows,
+                                                int kc, int width, float* dst, int ldd, bool vec) {
+  const int act = d.in_act;
+  if (vec) {
+    const int nc4 = width / 4;  // width is a multiple of 4
+    int r = threadIdx.x / nc4, c4 = threadIdx.x % nc4;
+    const int dr = DT / nc4, dc = DT % nc4;
+#pragma unroll 4
+    while (r < TM) {
+      const int k = kc + c4 * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows && k < K) {
+        const float* src = (k < d.k0) ? d.x0 + (row0 + r) * d.ld_x0 + k : d.x1 + (row0 + r) * d.ld_x1 + (k - d.k0);
+        v = ldg_f4(src);
+        v.x = act_apply(act, (v.x - vin[k]) * vin[K4 + k] + vin[2 * K4 + k]);
+        v.y = act_apply(act, (v.y - vin[k + 1]) * vin[K4 + k + 1] + vin[2 * K4 + k + 1]);
+        v.z = act_apply(act, (v.z - vin[k + 2]) * vin[K4 + k + 2] + vin[2 * K4 + k + 2]);
+        v.w = act_apply(act, (v.w - vin[k + 3]) * vin[K4 + k + 3] + vin[2 * K4 + k + 3]);
+      }
+      *reinterpret_cast<float4*>(dst + r * ldd + c4 * 4) = v;
+      r += dr;
+      c4 += dc;
+      if (c4 >= nc4) { c4 -= nc4; ++r; }
+    }
+  } else {
+    for (int i = threadIdx.x; i < TM * width; i += DT) {
+      const int r = i / width, kk = i % width, k = kc + kk;
+      float v = 0.f;
+      if (r < rows && k < K) {
+        v = (k < d.k0) ? __ldg(d.x0 + (row0 + r) * d.ld_x0 + k) : __ldg(d.x1 + (row0 + r) * d.ld_x1 + (k - d.k0));
+        v = act_apply(act, (v - vin[k]) * vin[K4 + k] + vin[2 * K4 + k]);
+      }
+      dst[r * ldd + kk] = v;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ forward unit
@@ -112,24 +160,34 @@ __global__ void __launch_bounds__(DT) linear_fwd_kernel(const __grid_constant__ 
   const int col_tiles = (d.h + TN - 1) / TN;
   const int rt = t / col_tiles, ct = t % col_tiles;
   const int K = d.k0 + d.k1, K4 = round4(K), lda = K4 + 4;
-  float* As = smem;             // [TM][lda]
-  float* Bs = smem + TM * lda;  // [K4][LDT]   Bs[k][n] = W[col0 + n][k]
+  float* As = smem;               // [TM][lda]
+  float* Bs = As + TM * lda;      // [K4][LDT]   Bs[k][n] = W[col0 + n][k]
+  float* vin = Bs + K4 * LDT;     // [3][K4]
   const int64_t row0 = (int64_t)rt * TM;
+  const int rows = (int)((d.n_rows - row0 < TM) ? d.n_rows - row0 : TM);
   const int col0 = ct * TN;
   const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
 
-  for (int i = tid; i < TN * K4; i += DT) {
-    const int n = i / K4, k = i % K4;
-    float w = 0.f;
-    if (k < K && col0 + n < d.h) w = __ldg(d.w + (int64_t)(col0 + n) * d.ld_w + k);
-    Bs[k * LDT + n] = w;
+  stage_input_vectors(d, vin, K, K4);
+  {  // weight tile, transposed into Bs: lanes run along n so the shared-memory stores are conflict-free
+    const bool wvec = ((reinterpret_cast<uintptr_t>(d.w) & 15u) == 0) && (d.ld_w % 4 == 0) && (K % 4 == 0);
+    const int n = tid % TN;
+    const bool live = col0 + n < d.h;
+    const float* wrow = d.w + (int64_t)(col0 + n) * d.ld_w;
+    if (wvec) {
+      for (int c4 = tid / TN; c4 < K4 / 4; c4 += DT / TN) {
+        const float4 w = live ? ldg_f4(wrow + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        Bs[(c4 * 4 + 0) * LDT + n] = w.x;
+        Bs[(c4 * 4 + 1) * LDT + n] = w.y;
+        Bs[(c4 * 4 + 2) * LDT + n] = w.z;
+        Bs[(c4 * 4 + 3) * LDT + n] = w.w;
+      }
+    } else {
+      for (int k = tid / TN; k < K4; k += DT / TN) Bs[k * LDT + n] = (live && k < K) ? __ldg(wrow + k) : 0.f;
+    }
   }
-  for (int i = tid; i < TM * K4; i += DT) {
-    const int r = i / K4, k = i % K4;
-    float v = 0.f;
-    if (k < K && row0 + r < d.n_rows) v = unit_input(d, row0 + r, k);
-    As[r * lda + k] = v;
-  }
+  __syncthreads();  // vin ready
+  load_input_tile(d, vin, K, K4, row0, rows, 0, K4, As, lda, input_vec_ok(d));
   __syncthreads();
   float acc[4][4] = {};
   tile_mma(As, lda, Bs, LDT, K4, ty, tx, acc);
@@ -140,72 +198,101 @@ __global__ void __launch_bounds__(DT) linear_fwd_kernel(const __grid_constant__ 
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[i][j] += b;
   }
+  const bool zvec = ((reinterpret_cast<uintptr_t>(d.z) & 15u) == 0) && (d.ld_z % 4 == 0) && (col0 + tx * 4 + 3 < d.h);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int64_t row = row0 + ty * 4 + i;
-    if (row >= d.n_rows) continue;
+    const int r = ty * 4 + i;
+    if (r >= rows) continue;
+    float* zrow = d.z + (row0 + r) * d.ld_z + col0 + tx * 4;
+    if (zvec) {
+      *reinterpret_cast<float4*>(zrow) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = col0 + tx * 4 + j;
-      if (c < d.h) d.z[row * d.ld_z + c] = acc[i][j];
+      for (int j = 0; j < 4; ++j)
+        if (col0 + tx * 4 + j < d.h) zrow[j] = acc[i][j];
     }
   }
   if (!d.stats) return;
   __syncthreads();  // As/Bs are dead: reuse the front of shared memory for the output tile
-  float* Ys = smem;  // [TM][LDT]
+  float* Ys = smem;              // [TM][LDT]
+  float* red = smem + TM * LDT;  // [4][TN]
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     *reinterpret_cast<float4*>(Ys + (ty * 4 + i) * LDT + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
   __syncthreads();
-  if (tid < TN && col0 + tid < d.h) {
-    const int cnt = (int)((d.n_rows - row0 < TM) ? d.n_rows - row0 : TM);
-    float s = 0.f;
-    for (int r = 0; r < cnt; ++r) s += Ys[r * LDT + tid];
-    const float mean = s / (float)cnt;
-    float m2 = 0.f;
-    for (int r = 0; r < cnt; ++r) {
-      const float dv = Ys[r * LDT + tid] - mean;
-      m2 = fmaf(dv, dv, m2);
-    }
-    d.stats[((int64_t)rt * 2 + 0) * d.h + col0 + tid] = mean;
-    d.stats[((int64_t)rt * 2 + 1) * d.h + col0 + tid] = m2;
+  // per-column (mean, M2) of this tile: 4 row groups per column, combined in a fixed order
+  const int c = tid & (TN - 1), part = tid >> 6;
+  float s = 0.f;
+  for (int r = part; r < rows; r += 4) s += Ys[r * LDT + c];
+  red[part * TN + c] = s;
+  __syncthreads();
+  const float mean = (((red[c] + red[TN + c]) + red[2 * TN + c]) + red[3 * TN + c]) / (float)rows;
+  __syncthreads();
+  float m2 = 0.f;
+  for (int r = part; r < rows; r += 4) {
+    const float dv = Ys[r * LDT + c] - mean;
+    m2 = fmaf(dv, dv, m2);
+  }
+  red[part * TN + c] = m2;
+  __syncthreads();
+  if (part == 0 && col0 + c < d.h) {
+    d.stats[((int64_t)rt * 2 + 0) * d.h + col0 + c] = mean;
+    d.stats[((int64_t)rt * 2 + 1) * d.h + col0 + c] = ((red[c] + red[TN + c]) + red[2 * TN + c]) + red[3 * TN + c];
   }
 }
 
 // ------------------------------------------------------------------------------------------------ BN statistics
+constexpr int kStageFloats = 12288;  // 48 KB of per-tile partials staged in shared memory at a time
+
 __global__ void __launch_bounds__(DT) bn_finalize_kernel(const __grid_constant__ Group<cwn_bn_desc> g) {
+  __shared__ float stage[kStageFloats];
   const cwn_bn_desc& d = g.d[blockIdx.x];
-  for (int c = threadIdx.x; c < d.h; c += DT) {
-    float mean, rstd;
-    if (d.training) {
-      float n = 0.f, m2 = 0.f;
-      mean = 0.f;
-      for (int t = 0; t < d.n_tiles; ++t) {  // Chan's parallel-variance merge, tiles in order (deterministic)
-        const int64_t left = d.n_rows - (int64_t)t * TM;
-        const float cnt = (float)(left < TM ? left : TM);
-        const float mt = d.stats[((int64_t)t * 2 + 0) * d.h + c];
-        const float m2t = d.stats[((int64_t)t * 2 + 1) * d.h + c];
-        const float delta = mt - mean, tot = n + cnt;
-        mean += delta * (cnt / tot);
-        m2 += m2t + delta * delta * (n * cnt / tot);
-        n = tot;
+  if (d.training) {
+    // Chan's parallel-variance merge of the per-tile (mean, M2), tiles in order (deterministic). The partials are
+    // pulled into shared memory with coalesced loads first: the merge itself is a dependent chain per column.
+    const int per_tile = 2 * d.h;
+    const int chunk = kStageFloats / per_tile > 0 ? kStageFloats / per_tile : 1;
+    float n = 0.f, m2 = 0.f, mean = 0.f;  // column threadIdx.x (h <= DT is guaranteed by the host)
+    for (int t0 = 0; t0 < d.n_tiles; t0 += chunk) {
+      const int nt = (d.n_tiles - t0 < chunk) ? d.n_tiles - t0 : chunk;
+      __syncthreads();
+      for (int i = threadIdx.x; i < nt * per_tile; i += DT) stage[i] = d.stats[(int64_t)t0 * per_tile + i];
+      __syncthreads();
+      if (threadIdx.x < d.h) {
+        const int c = threadIdx.x;
+        for (int t = 0; t < nt; ++t) {
+          const int64_t left = d.n_rows - (int64_t)(t0 + t) * TM;
+          const float cnt = (float)(left < TM ? left : TM);
+          const float mt = stage[t * per_tile + c], m2t = stage[t * per_tile + d.h + c];
+          const float delta = mt - mean, tot = n + cnt;
+          mean += delta * (cnt / tot);
+          m2 += m2t + delta * delta * (n * cnt / tot);
+          n = tot;
+        }
       }
+    }
+    if (threadIdx.x < d.h) {
+      const int c = threadIdx.x;
       const float var = m2 / (float)d.n_rows;
-      rstd = 1.f / sqrtf(var + d.eps);
+      const float rstd = 1.f / sqrtf(var + d.eps);
       if (d.running_mean) d.running_mean[c] = (1.f - d.momentum) * d.running_mean[c] + d.momentum * mean;
       if (d.running_var) {
         const float unbiased = d.n_rows > 1 ? m2 / (float)(d.n_rows - 1) : var;
         d.running_var[c] = (1.f - d.momentum) * d.running_var[c] + d.momentum * unbiased;
       }
-    } else {
-      mean = d.running_mean[c];
-      rstd = 1.f / sqrtf(d.running_var[c] + d.eps);
+      d.mean[c] = mean;
+      d.rstd[c] = rstd;
+      d.scale[c] = d.gamma ? d.gamma[c] * rstd : rstd;
     }
+    if (threadIdx.x == 0 && d.num_batches_tracked) *d.num_batches_tracked += 1;
+  } else if (threadIdx.x < d.h) {
+    const int c = threadIdx.x;
+    const float mean = d.running_mean[c];
+    const float rstd = 1.f / sqrtf(d.running_var[c] + d.eps);
     d.mean[c] = mean;
     d.rstd[c] = rstd;
     d.scale[c] = d.gamma ? d.gamma[c] * rstd : rstd;
   }
-  if (threadIdx.x == 0 && d.training && d.num_batches_tracked) *d.num_batches_tracked += 1;
 }
 
 __global__ void __launch_bounds__(DT) bn_act_kernel(const __grid_constant__ Group<cwn_bn_act_desc> g) {
@@ -248,13 +335,19 @@ __global__ void __launch_bounds__(DT) unit_bwd_reduce_kernel(const __grid_consta
   for (int col0 = 0; col0 < d.h; col0 += TN) {
     const int c = col0 + lane_c;
     float s1 = 0.f, s2 = 0.f;
-    if (c < d.h)
+    if (c < d.h) {
+      const float mean = __ldg(d.mean + c), scale = __ldg(d.scale + c), rstd = __ldg(d.rstd + c);
+      const float beta = d.beta ? __ldg(d.beta + c) : 0.f;
+      const float* zp = d.z + row0 * d.ld_z + c;
+      const float* gp = d.g_out + row0 * d.ld_g + c;
+#pragma unroll 4
       for (int r = rg; r < rows; r += 4) {
-        float gy, zhat;
-        unit_gy(d, row0 + r, c, gy, zhat);
+        const float zc = __ldg(zp + r * d.ld_z) - mean;
+        const float gy = __ldg(gp + r * d.ld_g) * act_grad(d.act, zc * scale + beta);
         s1 += gy;
-        s2 = fmaf(gy, zhat, s2);
+        s2 = fmaf(gy, zc * rstd, s2);
       }
+    }
     part[0][rg][lane_c] = s1;
     part[1][rg][lane_c] = s2;
     __syncthreads();
@@ -267,15 +360,26 @@ __global__ void __launch_bounds__(DT) unit_bwd_reduce_kernel(const __grid_consta
 }
 
 __global__ void __launch_bounds__(DT) unit_bwd_finalize_kernel(const __grid_constant__ Group<cwn_unit_bwd_desc> g) {
+  __shared__ float stage[kStageFloats];
   const cwn_unit_bwd_desc& d = g.d[blockIdx.x];
   if (!d.has_bn) return;
   const int n_tiles = (int)((d.n_rows + TM - 1) / TM);
-  for (int c = threadIdx.x; c < d.h; c += DT) {
-    float s1 = 0.f, s2 = 0.f;
-    for (int t = 0; t < n_tiles; ++t) {
-      s1 += d.red_partials[((int64_t)t * 2 + 0) * d.h + c];
-      s2 += d.red_partials[((int64_t)t * 2 + 1) * d.h + c];
-    }
+  const int per_tile = 2 * d.h;
+  const int chunk = kStageFloats / per_tile > 0 ? kStageFloats / per_tile : 1;
+  float s1 = 0.f, s2 = 0.f;  // column threadIdx.x
+  for (int t0 = 0; t0 < n_tiles; t0 += chunk) {
+    const int nt = (n_tiles - t0 < chunk) ? n_tiles - t0 : chunk;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nt * per_tile; i += DT) stage[i] = d.red_partials[(int64_t)t0 * per_tile + i];
+    __syncthreads();
+    if (threadIdx.x < d.h)
+      for (int t = 0; t < nt; ++t) {
+        s1 += stage[t * per_tile + threadIdx.x];
+        s2 += stage[t * per_tile + d.h + threadIdx.x];
+      }
+  }
+  if (threadIdx.x < d.h) {
+    const int c = threadIdx.x;
     d.c1[c] = s1 / (float)d.n_rows;
     d.c2[c] = s2 / (float)d.n_rows;
     if (d.g_gamma) d.g_gamma[c] = d.accumulate_affine ? d.g_gamma[c] + s2 : s2;
@@ -290,54 +394,103 @@ __global__ void __launch_bounds__(DT) unit_bwd_kernel(const __grid_constant__ Gr
   const int p = find_problem(g, blockIdx.x);
   const cwn_unit_bwd_desc& d = g.d[p];
   const int j = blockIdx.x - g.start[p];
-  const int K = d.k0 + d.k1, H4 = round4(d.h), ldg = H4 + 4;
+  const int K = d.k0 + d.k1, K4 = round4(K), H4 = round4(d.h), ldg = H4 + 4;
   const int m_tiles = (d.h + TM - 1) / TM;
   float* Gz = smem;                        // [TM][ldg]            g_z[r][c]
   float* GzT = Gz + TM * ldg;              // [m_tiles*TM][LDT]    g_z^T[c][r]
   float* Ain = GzT + m_tiles * TM * LDT;   // [TM][LDT]            f_in(X)[r][k chunk]
   float* Ws = Ain + TM * LDT;              // [H4][LDT]            W[c][k chunk]
+  float* vin = Ws + H4 * LDT;              // [3][K4]              input transform
+  float* vout = vin + 3 * K4;              // [6][H4]              mean, scale, rstd, beta, c1, c2 of this unit
   const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
   const int n_tiles = (int)((d.n_rows + TM - 1) / TM);
   float* wpart = d.w_partials + (int64_t)j * d.h * K;
   float* bpart = d.b_partials + (int64_t)j * d.h;
+  const bool in_vec = input_vec_ok(d);
+  const bool w_vec = ((reinterpret_cast<uintptr_t>(d.w) & 15u) == 0) && (d.ld_w % 4 == 0) && (K % 4 == 0);
+  const bool g_vec = ((reinterpret_cast<uintptr_t>(d.z) & 15u) == 0) && (d.ld_z % 4 == 0) && (d.h % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(d.g_out) & 15u) == 0) && (d.ld_g % 4 == 0);
+
+  stage_input_vectors(d, vin, K, K4);
+  for (int c = tid; c < H4; c += DT) {
+    const bool live = c < d.h && d.has_bn;
+    vout[c] = live ? __ldg(d.mean + c) : 0.f;
+    vout[H4 + c] = live ? __ldg(d.scale + c) : 1.f;
+    vout[2 * H4 + c] = live ? __ldg(d.rstd + c) : 0.f;
+    vout[3 * H4 + c] = (live && d.beta) ? __ldg(d.beta + c) : 0.f;
+    vout[4 * H4 + c] = live ? d.c1[c] : 0.f;
+    vout[5 * H4 + c] = live ? d.c2[c] : 0.f;
+  }
+  for (int i = tid; i < m_tiles * TM * LDT; i += DT) GzT[i] = 0.f;  // rows c >= h stay zero for good
   bool first = true;
   for (int tile = j; tile < n_tiles; tile += d.n_ctas, first = false) {
     const int64_t row0 = (int64_t)tile * TM;
     const int rows = (int)((d.n_rows - row0 < TM) ? d.n_rows - row0 : TM);
     __syncthreads();
-    for (int i = tid; i < TM * H4; i += DT) {  // g_z of this tile
-      const int r = i / H4, c = i % H4;
-      float gz = 0.f;
-      if (r < rows && c < d.h) {
-        float gy, zhat;
-        unit_gy(d, row0 + r, c, gy, zhat);
-        gz = d.has_bn ? __ldg(d.scale + c) * (gy - d.c1[c] - zhat * d.c2[c]) : gy;
+    // g_z = scale * (g_out act'(y) - c1 - zhat c2) of this tile (plain g_out act'(z) without BatchNorm)
+    if (g_vec) {
+      const int nc4 = H4 / 4;
+      int r = tid / nc4, c4 = tid % nc4;
+      const int dr = DT / nc4, dc = DT % nc4;
+#pragma unroll 4
+      while (r < TM) {
+        const int c = c4 * 4;
+        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows) {
+          const float4 z = ldg_f4(d.z + (row0 + r) * d.ld_z + c);
+          const float4 gv = ldg_f4(d.g_out + (row0 + r) * d.ld_g + c);
+          const float zz[4] = {z.x, z.y, z.z, z.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w};
+          float o[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float zc = zz[q] - vout[c + q];
+            const float gy = gg[q] * act_grad(d.act, zc * vout[H4 + c + q] + vout[3 * H4 + c + q]);
+            o[q] = d.has_bn ? vout[H4 + c + q] * (gy - vout[4 * H4 + c + q] - zc * vout[2 * H4 + c + q] * vout[5 * H4 + c + q]) : gy;
+          }
+          out = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        *reinterpret_cast<float4*>(Gz + r * ldg + c) = out;
+        r += dr;
+        c4 += dc;
+        if (c4 >= nc4) { c4 -= nc4; ++r; }
       }
-      Gz[r * ldg + c] = gz;
+    } else {
+      for (int i = tid; i < TM * H4; i += DT) {
+        const int r = i / H4, c = i % H4;
+        float gz = 0.f;
+        if (r < rows && c < d.h) {
+          const float zc = __ldg(d.z + (row0 + r) * d.ld_z + c) - vout[c];
+          const float gy = __ldg(d.g_out + (row0 + r) * d.ld_g + c) * act_grad(d.act, zc * vout[H4 + c] + vout[3 * H4 + c]);
+          gz = d.has_bn ? vout[H4 + c] * (gy - vout[4 * H4 + c] - zc * vout[2 * H4 + c] * vout[5 * H4 + c]) : gy;
+        }
+        Gz[r * ldg + c] = gz;
+      }
     }
-    for (int i = tid; i < m_tiles * TM * TM; i += DT) GzT[(i / TM) * LDT + (i % TM)] = 0.f;
     __syncthreads();
-    for (int i = tid; i < TM * d.h; i += DT) {
-      const int r = i / d.h, c = i % d.h;
-      GzT[c * LDT + r] = Gz[r * ldg + c];
-    }
-    if (tid < d.h || (d.h > DT)) {
-      for (int c = tid; c < d.h; c += DT) {  // bias gradient partial: column sums of g_z
-        float s = 0.f;
-        for (int r = 0; r < rows; ++r) s += Gz[r * ldg + c];
-        bpart[c] = first ? s : bpart[c] + s;
+    {  // transpose into GzT (lanes along r: conflict-free stores) and the bias-gradient partial (column sums)
+      const int r = tid & (TM - 1);
+      for (int c = tid >> 6; c < d.h; c += DT / TM) GzT[c * LDT + r] = Gz[r * ldg + c];
+      for (int c = tid; c < d.h; c += DT) {
+        float s_ = 0.f;
+        for (int rr = 0; rr < rows; ++rr) s_ += Gz[rr * ldg + c];
+        bpart[c] = first ? s_ : bpart[c] + s_;
       }
     }
     for (int kc = 0; kc < K; kc += TN) {
       __syncthreads();
-      for (int i = tid; i < H4 * TN; i += DT) {  // W[c][kc + k]
-        const int c = i / TN, k = i % TN;
-        Ws[c * LDT + k] = (c < d.h && kc + k < K) ? __ldg(d.w + (int64_t)c * d.ld_w + kc + k) : 0.f;
+      if (w_vec) {  // W[c][kc + k], natural layout
+        for (int i = tid; i < H4 * (TN / 4); i += DT) {
+          const int c = i / (TN / 4), k = (i % (TN / 4)) * 4;
+          const float4 w = (c < d.h && kc + k < K) ? ldg_f4(d.w + (int64_t)c * d.ld_w + kc + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(Ws + c * LDT + k) = w;
+        }
+      } else {
+        for (int i = tid; i < H4 * TN; i += DT) {
+          const int c = i / TN, k = i % TN;
+          Ws[c * LDT + k] = (c < d.h && kc + k < K) ? __ldg(d.w + (int64_t)c * d.ld_w + kc + k) : 0.f;
+        }
       }
-      for (int i = tid; i < TM * TN; i += DT) {  // f_in(X)[r][kc + k]
-        const int r = i / TN, k = i % TN;
-        Ain[r * LDT + k] = (r < rows && kc + k < K) ? unit_input(d, row0 + r, kc + k) : 0.f;
-      }
+      load_input_tile(d, vin, K, K4, row0, rows, kc, TN, Ain, LDT, in_vec);
       __syncthreads();
       if (d.g_in0 || d.g_in1) {  // input gradient chunk: [64 rows] x [64 k] = Gz [64 x h] * Ws [h x 64]
         float acc[4][4] = {};
@@ -418,7 +571,7 @@ extern "C" int cwn_linear_fwd_grouped(const cwn_linear_desc* descs, int32_t n, c
   Group<cwn_linear_desc> g;
   g.n = n;
   int total = 0;
-  size_t smem = (size_t)TM * LDT * sizeof(float);
+  size_t smem = ((size_t)TM * LDT + 4 * TN) * sizeof(float);
   for (int i = 0; i < n; ++i) {
     const cwn_linear_desc& d = descs[i];
     if (d.n_rows < 0 || d.h <= 0 || d.k0 <= 0 || d.k1 < 0 || d.n_rows > (int64_t)INT32_MAX * TM)
@@ -428,7 +581,7 @@ extern "C" int cwn_linear_fwd_grouped(const cwn_linear_desc* descs, int32_t n, c
     g.start[i] = total;
     total += (int)((d.n_rows + TM - 1) / TM) * ((d.h + TN - 1) / TN);
     const int K4 = round4(d.k0 + d.k1);
-    const size_t need = ((size_t)TM * (K4 + 4) + (size_t)K4 * LDT) * sizeof(float);
+    const size_t need = ((size_t)TM * (K4 + 4) + (size_t)K4 * LDT + 3 * (size_t)K4) * sizeof(float);
     if (need > smem) smem = need;
   }
   g.start[n] = total;
@@ -445,7 +598,7 @@ extern "C" int cwn_bn_finalize_grouped(const cwn_bn_desc* descs, int32_t n, cwn_
   g.n = n;
   for (int i = 0; i < n; ++i) {
     const cwn_bn_desc& d = descs[i];
-    if (d.h <= 0 || d.n_rows < 0) return fail(CWN_E_SHAPE, "cwn_bn_finalize_grouped: bad shape");
+    if (d.h <= 0 || d.h > DT || d.n_rows < 0) return fail(CWN_E_SHAPE, "cwn_bn_finalize_grouped: bad shape (h <= 256)");
     if (!d.mean || !d.scale || !d.rstd) return fail(CWN_E_NULL, "cwn_bn_finalize_grouped: outputs");
     if (d.training ? !d.stats : (!d.running_mean || !d.running_var)) return fail(CWN_E_NULL, "cwn_bn_finalize_grouped: statistics");
     g.d[i] = d;
@@ -481,7 +634,7 @@ static int load_bwd_group(const cwn_unit_bwd_desc* descs, int n, Group<cwn_unit_
   g.n = n;
   for (int i = 0; i < n; ++i) {
     const cwn_unit_bwd_desc& d = descs[i];
-    if (d.n_rows < 0 || d.h <= 0 || d.k0 <= 0 || d.k1 < 0 || d.n_ctas < 0) return fail(CWN_E_SHAPE, what);
+    if (d.n_rows < 0 || d.h <= 0 || d.h > DT || d.k0 <= 0 || d.k1 < 0 || d.n_ctas < 0) return fail(CWN_E_SHAPE, what);
     if (d.n_rows > 0 && (!d.x0 || !d.w || !d.z || !d.g_out || (d.k1 > 0 && !d.x1))) return fail(CWN_E_NULL, what);
     if (d.has_bn && (!d.mean || !d.scale || !d.rstd || !d.red_partials || !d.c1 || !d.c2)) return fail(CWN_E_NULL, what);
     g.d[i] = d;
@@ -526,8 +679,9 @@ extern "C" int cwn_unit_bwd_grouped(const cwn_unit_bwd_desc* descs, int32_t n, c
     if (d.n_rows > 0 && (!d.w_partials || !d.b_partials)) return fail(CWN_E_NULL, "cwn_unit_bwd_grouped: partial buffers");
     g.start[i] = total;
     total += d.n_ctas;
-    const int H4 = round4(d.h), m_tiles = (d.h + TM - 1) / TM;
-    const size_t need = ((size_t)TM * (H4 + 4) + (size_t)m_tiles * TM * LDT + (size_t)TM * LDT + (size_t)H4 * LDT) * sizeof(float);
+    const int H4 = round4(d.h), m_tiles = (d.h + TM - 1) / TM, K4 = round4(d.k0 + d.k1);
+    const size_t need = ((size_t)TM * (H4 + 4) + (size_t)m_tiles * TM * LDT + (size_t)TM * LDT + (size_t)H4 * LDT +
+                         3 * (size_t)K4 + 6 * (size_t)H4) * sizeof(float);
     if (need > smem) smem = need;
   }
   g.start[n] = total;

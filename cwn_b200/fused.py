@@ -299,3 +299,70 @@ def sparse_cin_dense(forms, us, bs, training):
         flat += [u, b]
 
     return list(FusedSparseCINDense.apply(forms, training, n_dims, *flat, *params))
+
+
+# ------------------------------------------------------------------------------------------------ plain linears
+class GroupedLinear(Function):
+    """ys[i] = xs[i] @ ws[i].T (+ bs[i]) for up to 8 independent problems in one launch forward and two backward
+    (input gradients + per-CTA weight-gradient partials, then their ordered sum). Weights may be column slices of a
+    larger matrix (explicit leading dimension), which is how the coboundary message Linear(2F -> F) of
+    mp/layers.py:290-293 is applied as two per-cell products (x W1^T, y W2^T + b)."""
+
+    @staticmethod
+    def forward(ctx, n, has_bias, *tensors):
+        xs, ws = tensors[:n], tensors[n:2 * n]
+        bs = list(tensors[2 * n:])
+        biases, j = [], 0
+        for i in range(n):
+            biases.append(bs[j] if has_bias[i] else None)
+            j += 1 if has_bias[i] else 0
+        dev = xs[0].device
+        ys, descs = [], []
+        with torch.cuda.device(dev):
+            xs = [x if x.stride(1) == 1 else x.contiguous() for x in xs]
+            for x, w, b in zip(xs, ws, biases):
+                y = torch.empty(x.size(0), w.size(0), dtype=torch.float32, device=dev)
+                descs.append(_lib.LinearDesc(_p(x), x.stride(0), x.size(1), None, 0, 0, None, None, None, None, None,
+                                             None, 0, _p(w), w.stride(0), _p(b), _p(y), y.size(1), None, x.size(0),
+                                             w.size(0)))
+                ys.append(y)
+            _launch('cwn_linear_fwd_grouped', _lib.LinearDesc, descs)
+        ctx.n, ctx.has_bias = n, has_bias
+        ctx.save_for_backward(*xs, *ws)
+        return tuple(ys)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        n = ctx.n
+        xs, ws = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
+        dev = xs[0].device
+        gxs, gws, gbs, descs, keep = [], [], [], [], []
+        with torch.cuda.device(dev):
+            for i, (x, w, g) in enumerate(zip(xs, ws, gs)):
+                nr, k, h = x.size(0), x.size(1), w.size(0)
+                g = (g if g is not None else torch.zeros(nr, h, device=dev)).contiguous()
+                n_tiles = (nr + TM - 1) // TM
+                n_ctas = min(n_tiles, 148)
+                gx = torch.empty(nr, k, dtype=torch.float32, device=dev) if ctx.needs_input_grad[2 + i] else None
+                gw = torch.empty(h, k, dtype=torch.float32, device=dev)
+                gb = torch.empty(h, dtype=torch.float32, device=dev)
+                wp = torch.empty(max(n_ctas, 1) * h * k, dtype=torch.float32, device=dev)
+                bp = torch.empty(max(n_ctas, 1) * h, dtype=torch.float32, device=dev)
+                keep += [g, wp, bp]
+                # the "z" operand is only read through act'(z) with act = id, so any valid [n, h] matrix will do
+                descs.append(_lib.UnitBwdDesc(
+                    _p(x), x.stride(0), k, None, 0, 0, None, None, None, None, None, None, 0, _p(w), w.stride(0),
+                    _p(g), g.stride(0), 0, 0, None, None, None, None, _p(g), g.stride(0), None, None, None, None, None,
+                    0, _p(gx), k, None, 0, _p(wp), _p(bp), n_ctas, _p(gw), k, _p(gb), 0, nr, h))
+                gxs.append(gx)
+                gws.append(gw)
+                gbs.append(gb if ctx.has_bias[i] else None)
+            _launch('cwn_unit_bwd_grouped', _lib.UnitBwdDesc, descs)
+            _launch('cwn_wgrad_finalize_grouped', _lib.UnitBwdDesc, descs)
+        return (None, None, *gxs, *gws, *[b for b in gbs if b is not None])
+
+
+def grouped_linear(xs, ws, bs):
+    """[x @ w.T + b for x, w, b in zip(xs, ws, bs)] (b may be None) with one launch; fp32 CUDA matrices."""
+    has_bias = tuple(b is not None for b in bs)
+    return list(GroupedLinear.apply(len(xs), has_bias, *xs, *ws, *[b for b in bs if b is not None]))

@@ -225,18 +225,25 @@ class SparseCINCochainConv(CochainMessagePassing):
         if b_attr is None and self.boundary_msg_size != x.size(1):
             return NotImplemented
 
-        def up_branch():  # upper adjacencies
+        def up_branch(pq=None):  # upper adjacencies
             if up_index is None:
                 return (1 + self.eps1) * x
             if form[0] == 'identity':
                 return ops.gather_scatter(x, up_index, n, 'add', x_res=x, eps=self.eps1)
             _, lin, act = form
-            fx = x.size(1)
             # W [x_j ; y_cob] + b  ==  (x W1^T)[src] + (y W2^T + b)[cob]: two per-CELL GEMMs instead of one per
             # message, then a memory-bound fused pass
-            P = F.linear(x, lin.weight[:, :fx])
-            Q = F.linear(up_attr.source, lin.weight[:, fx:], lin.bias)
-            return ops.cob_pass(P, Q, up_index, up_attr.index, n, act=act, x_res=x, eps=self.eps1)
+            if pq is None:
+                fx = x.size(1)
+                pq = F.linear(x, lin.weight[:, :fx]), F.linear(up_attr.source, lin.weight[:, fx:], lin.bias)
+            return ops.cob_pass(pq[0], pq[1], up_index, up_attr.index, n, act=act, x_res=x, eps=self.eps1)
+
+        # operands of the two split-weight products, so that a container can batch them over dimensions
+        up_branch.split_linear = None
+        if up_index is not None and form[0] == 'cob':
+            fx = x.size(1)
+            up_branch.split_linear = ([x, up_attr.source], [form[1].weight[:, :fx], form[1].weight[:, fx:]],
+                                      [None, form[1].bias])
 
         def boundary_branch():  # the pass only runs when boundary features exist (reference mp/cell_mp.py:381)
             if b_attr is not None:
@@ -307,6 +314,16 @@ class SparseCINConv(_PerDimension):
             branches = [self.mp_levels[d]._fused_forward(cochain_params[d]) for d in range(n)]
             if all(f is not None for f in forms[:n]) and all(b is not NotImplemented for b in branches):
                 device = cochain_params[0].x.device
+                # the split-weight products of every dimension's coboundary message net in one grouped launch
+                reqs = [(d, branches[d][0].split_linear) for d in range(n) if branches[d][0].split_linear]
+                if reqs and all(t.is_cuda and t.dtype == torch.float32 for _, r in reqs for t in r[0]):
+                    xs = [t for _, r in reqs for t in r[0]]
+                    ws = [t for _, r in reqs for t in r[1]]
+                    bs_ = [t for _, r in reqs for t in r[2]]
+                    prods = fused.grouped_linear(xs, ws, bs_)
+                    for i, (d, _) in enumerate(reqs):
+                        up, pq = branches[d][0], (prods[2 * i], prods[2 * i + 1])
+                        branches[d] = ((lambda up=up, pq=pq: up(pq)), branches[d][1])
                 aggs = run_concurrently([t for pair in branches for t in pair], device)
                 us, bs = aggs[0::2], aggs[1::2]
                 if fused.applicable(forms[:n], us, bs, self.mp_levels[0].training):

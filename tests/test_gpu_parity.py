@@ -543,7 +543,9 @@ def test_fused_dense_layer_equals_torch_modules(layer_dim, hidden, act, norm, co
             assert p1[k].grad is None or float(p1[k].grad.abs().sum()) == 0, k
         else:
             scale = float(p2[k].grad.abs().max()) + 1e-6
-            assert_close(p1[k].grad, p2[k].grad, rtol=1e-4, atol=1e-4 * scale, what=f'grad {k}')
+            # d/d eps = <g, x>: a sum of ~1e5 signed terms, so its fp32 rounding is not relative to the result
+            atol = 2e-5 if k.endswith(('eps1', 'eps2')) else 1e-4 * scale
+            assert_close(p1[k].grad, p2[k].grad, rtol=1e-4, atol=atol, what=f'grad {k}')
     for k in b1:
         assert_close(b1[k].float(), b2[k].float(), rtol=1e-5, atol=1e-6, what=f'buffer {k}')
     with torch.no_grad():
