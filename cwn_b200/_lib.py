@@ -28,7 +28,10 @@ class LinearDesc(ctypes.Structure):
     _fields_ = [('x0', _P), ('ld_x0', _I64), ('k0', _I32), ('x1', _P), ('ld_x1', _I64), ('k1', _I32),
                 ('in_mean0', _P), ('in_scale0', _P), ('in_beta0', _P), ('in_mean1', _P), ('in_scale1', _P),
                 ('in_beta1', _P), ('in_act', _I32), ('w', _P), ('ld_w', _I64), ('bias', _P), ('z', _P),
-                ('ld_z', _I64), ('stats', _P), ('n_rows', _I64), ('h', _I32)]
+                ('ld_z', _I64), ('stats', _P), ('n_rows', _I64), ('h', _I32),
+                ('bn_gamma', _P), ('bn_eps', _F), ('bn_momentum', _F), ('bn_training', _I32),
+                ('bn_running_mean', _P), ('bn_running_var', _P), ('bn_num_batches_tracked', _P),
+                ('bn_mean', _P), ('bn_scale', _P), ('bn_rstd', _P), ('counter', _P)]
 
 
 class BNDesc(ctypes.Structure):
@@ -53,7 +56,8 @@ class UnitBwdDesc(ctypes.Structure):
                 ('g_out', _P), ('ld_g', _I64), ('red_partials', _P), ('c1', _P), ('c2', _P), ('g_gamma', _P),
                 ('g_beta', _P), ('accumulate_affine', _I32), ('g_in0', _P), ('ld_gi0', _I64), ('g_in1', _P),
                 ('ld_gi1', _I64), ('w_partials', _P), ('b_partials', _P), ('n_ctas', _I32), ('g_w', _P),
-                ('ld_gw', _I64), ('g_b', _P), ('accumulate_w', _I32), ('n_rows', _I64), ('h', _I32)]
+                ('ld_gw', _I64), ('g_b', _P), ('accumulate_w', _I32), ('n_rows', _I64), ('h', _I32),
+                ('counter', _P)]
 
 
 MAX_GROUP = 8

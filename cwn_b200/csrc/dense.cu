@@ -151,6 +151,74 @@ __device__ __forceinline__ void load_input_tile(const D& d, const float* vin, in
   }
 }
 
+// "last CTA done" hand-off: every CTA of a problem publishes its partials, bumps the problem's counter, and the one
+// that observes the final count runs the (cheap, ordered => deterministic) merge. Saves a dependent launch.
+__device__ __forceinline__ bool last_cta_of_problem(int32_t* counter, int total) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1) == total - 1);
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
+constexpr int kStageFloats = 8192;  // 32 KB of per-tile partials staged in shared memory at a time
+
+// BatchNorm statistics of one problem from the per-tile (mean, M2) partials (training) or the running statistics.
+// `stage`: kStageFloats floats of shared memory. Column = threadIdx.x (h <= DT).
+__device__ __forceinline__ void bn_finalize_body(const float* stats, int n_tiles, int64_t n_rows, int h, const float* gamma,
+                                                 float eps, float momentum, int training, float* running_mean,
+                                                 float* running_var, int64_t* nbt, float* mean_out, float* scale_out,
+                                                 float* rstd_out, float* stage, int stage_floats = kStageFloats) {
+  if (training) {
+    // Chan's parallel-variance merge, tiles in order (deterministic). The partials are pulled into shared memory with
+    // coalesced loads first: the merge itself is a dependent chain per column.
+    const int per_tile = 2 * h;
+    const int chunk = stage_floats / per_tile > 0 ? stage_floats / per_tile : 1;
+    float n = 0.f, m2 = 0.f, mean = 0.f;
+    for (int t0 = 0; t0 < n_tiles; t0 += chunk) {
+      const int nt = (n_tiles - t0 < chunk) ? n_tiles - t0 : chunk;
+      __syncthreads();
+      for (int i = threadIdx.x; i < nt * per_tile; i += DT) stage[i] = __ldcg(stats + (int64_t)t0 * per_tile + i);
+      __syncthreads();
+      if (threadIdx.x < h) {
+        const int c = threadIdx.x;
+        for (int t = 0; t < nt; ++t) {
+          const int64_t left = n_rows - (int64_t)(t0 + t) * TM;
+          const float cnt = (float)(left < TM ? left : TM);
+          const float mt = stage[t * per_tile + c], m2t = stage[t * per_tile + h + c];
+          const float delta = mt - mean, tot = n + cnt;
+          mean += delta * (cnt / tot);
+          m2 += m2t + delta * delta * (n * cnt / tot);
+          n = tot;
+        }
+      }
+    }
+    if (threadIdx.x < h) {
+      const int c = threadIdx.x;
+      const float var = m2 / (float)n_rows;
+      const float rstd = 1.f / sqrtf(var + eps);
+      if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      if (running_var) {
+        const float unbiased = n_rows > 1 ? m2 / (float)(n_rows - 1) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+      }
+      mean_out[c] = mean;
+      rstd_out[c] = rstd;
+      scale_out[c] = gamma ? gamma[c] * rstd : rstd;
+    }
+    if (threadIdx.x == 0 && nbt) *nbt += 1;
+  } else if (threadIdx.x < h) {
+    const int c = threadIdx.x;
+    const float mean = running_mean[c];
+    const float rstd = 1.f / sqrtf(running_var[c] + eps);
+    mean_out[c] = mean;
+    rstd_out[c] = rstd;
+    scale_out[c] = gamma ? gamma[c] * rstd : rstd;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ forward unit
 __global__ void __launch_bounds__(DT) linear_fwd_kernel(const __grid_constant__ Group<cwn_linear_desc> g) {
   extern __shared__ __align__(16) float smem[];
@@ -212,7 +280,12 @@ __global__ void __launch_bounds__(DT) linear_fwd_kernel(const __grid_constant__ 
         if (col0 + tx * 4 + j < d.h) zrow[j] = acc[i][j];
     }
   }
-  if (!d.stats) return;
+  if (!d.stats) {
+    if (d.bn_mean && !d.bn_training && blockIdx.x == g.start[p])  // eval: statistics are the running ones
+      bn_finalize_body(nullptr, 0, d.n_rows, d.h, d.bn_gamma, d.bn_eps, d.bn_momentum, 0, d.bn_running_mean,
+                       d.bn_running_var, nullptr, d.bn_mean, d.bn_scale, d.bn_rstd, nullptr);
+    return;
+  }
   __syncthreads();  // As/Bs are dead: reuse the front of shared memory for the output tile
   float* Ys = smem;              // [TM][LDT]
   float* red = smem + TM * LDT;  // [4][TN]
@@ -239,60 +312,24 @@ __global__ void __launch_bounds__(DT) linear_fwd_kernel(const __grid_constant__ 
     d.stats[((int64_t)rt * 2 + 0) * d.h + col0 + c] = mean;
     d.stats[((int64_t)rt * 2 + 1) * d.h + col0 + c] = ((red[c] + red[TN + c]) + red[2 * TN + c]) + red[3 * TN + c];
   }
+  if (d.bn_mean && d.counter) {
+    const int total = g.start[p + 1] - g.start[p];
+    if (last_cta_of_problem(d.counter, total)) {
+      const int n_tiles = (int)((d.n_rows + TM - 1) / TM);
+      bn_finalize_body(d.stats, n_tiles, d.n_rows, d.h, d.bn_gamma, d.bn_eps, d.bn_momentum, 1, d.bn_running_mean,
+                       d.bn_running_var, d.bn_num_batches_tracked, d.bn_mean, d.bn_scale, d.bn_rstd, smem,
+                       TM * lda + K4 * LDT);  // this problem's share of the dynamic shared memory
+      if (threadIdx.x == 0) *d.counter = 0;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ BN statistics
-constexpr int kStageFloats = 12288;  // 48 KB of per-tile partials staged in shared memory at a time
-
 __global__ void __launch_bounds__(DT) bn_finalize_kernel(const __grid_constant__ Group<cwn_bn_desc> g) {
   __shared__ float stage[kStageFloats];
   const cwn_bn_desc& d = g.d[blockIdx.x];
-  if (d.training) {
-    // Chan's parallel-variance merge of the per-tile (mean, M2), tiles in order (deterministic). The partials are
-    // pulled into shared memory with coalesced loads first: the merge itself is a dependent chain per column.
-    const int per_tile = 2 * d.h;
-    const int chunk = kStageFloats / per_tile > 0 ? kStageFloats / per_tile : 1;
-    float n = 0.f, m2 = 0.f, mean = 0.f;  // column threadIdx.x (h <= DT is guaranteed by the host)
-    for (int t0 = 0; t0 < d.n_tiles; t0 += chunk) {
-      const int nt = (d.n_tiles - t0 < chunk) ? d.n_tiles - t0 : chunk;
-      __syncthreads();
-      for (int i = threadIdx.x; i < nt * per_tile; i += DT) stage[i] = d.stats[(int64_t)t0 * per_tile + i];
-      __syncthreads();
-      if (threadIdx.x < d.h) {
-        const int c = threadIdx.x;
-        for (int t = 0; t < nt; ++t) {
-          const int64_t left = d.n_rows - (int64_t)(t0 + t) * TM;
-          const float cnt = (float)(left < TM ? left : TM);
-          const float mt = stage[t * per_tile + c], m2t = stage[t * per_tile + d.h + c];
-          const float delta = mt - mean, tot = n + cnt;
-          mean += delta * (cnt / tot);
-          m2 += m2t + delta * delta * (n * cnt / tot);
-          n = tot;
-        }
-      }
-    }
-    if (threadIdx.x < d.h) {
-      const int c = threadIdx.x;
-      const float var = m2 / (float)d.n_rows;
-      const float rstd = 1.f / sqrtf(var + d.eps);
-      if (d.running_mean) d.running_mean[c] = (1.f - d.momentum) * d.running_mean[c] + d.momentum * mean;
-      if (d.running_var) {
-        const float unbiased = d.n_rows > 1 ? m2 / (float)(d.n_rows - 1) : var;
-        d.running_var[c] = (1.f - d.momentum) * d.running_var[c] + d.momentum * unbiased;
-      }
-      d.mean[c] = mean;
-      d.rstd[c] = rstd;
-      d.scale[c] = d.gamma ? d.gamma[c] * rstd : rstd;
-    }
-    if (threadIdx.x == 0 && d.num_batches_tracked) *d.num_batches_tracked += 1;
-  } else if (threadIdx.x < d.h) {
-    const int c = threadIdx.x;
-    const float mean = d.running_mean[c];
-    const float rstd = 1.f / sqrtf(d.running_var[c] + d.eps);
-    d.mean[c] = mean;
-    d.rstd[c] = rstd;
-    d.scale[c] = d.gamma ? d.gamma[c] * rstd : rstd;
-  }
+  bn_finalize_body(d.stats, d.n_tiles, d.n_rows, d.h, d.gamma, d.eps, d.momentum, d.training, d.running_mean,
+                   d.running_var, d.num_batches_tracked, d.mean, d.scale, d.rstd, stage);
 }
 
 __global__ void __launch_bounds__(DT) bn_act_kernel(const __grid_constant__ Group<cwn_bn_act_desc> g) {
@@ -321,6 +358,31 @@ __device__ __forceinline__ void unit_gy(const cwn_unit_bwd_desc& d, int64_t row,
   } else {
     zhat = 0.f;
     gy = g * act_grad(d.act, z);
+  }
+}
+
+__device__ __forceinline__ void unit_bwd_finalize_body(const cwn_unit_bwd_desc& d, float* stage) {
+  const int n_tiles = (int)((d.n_rows + TM - 1) / TM);
+  const int per_tile = 2 * d.h;
+  const int chunk = kStageFloats / per_tile > 0 ? kStageFloats / per_tile : 1;
+  float s1 = 0.f, s2 = 0.f;  // column threadIdx.x
+  for (int t0 = 0; t0 < n_tiles; t0 += chunk) {
+    const int nt = (n_tiles - t0 < chunk) ? n_tiles - t0 : chunk;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nt * per_tile; i += DT) stage[i] = __ldcg(d.red_partials + (int64_t)t0 * per_tile + i);
+    __syncthreads();
+    if (threadIdx.x < d.h)
+      for (int t = 0; t < nt; ++t) {
+        s1 += stage[t * per_tile + threadIdx.x];
+        s2 += stage[t * per_tile + d.h + threadIdx.x];
+      }
+  }
+  if (threadIdx.x < d.h) {
+    const int c = threadIdx.x;
+    d.c1[c] = s1 / (float)d.n_rows;
+    d.c2[c] = s2 / (float)d.n_rows;
+    if (d.g_gamma) d.g_gamma[c] = d.accumulate_affine ? d.g_gamma[c] + s2 : s2;
+    if (d.g_beta) d.g_beta[c] = d.accumulate_affine ? d.g_beta[c] + s1 : s1;
   }
 }
 
@@ -357,34 +419,20 @@ __global__ void __launch_bounds__(DT) unit_bwd_reduce_kernel(const __grid_consta
     }
     __syncthreads();
   }
+  if (d.counter) {
+    __shared__ float stage[kStageFloats];
+    if (last_cta_of_problem(d.counter, g.start[p + 1] - g.start[p])) {
+      unit_bwd_finalize_body(d, stage);
+      if (threadIdx.x == 0) *d.counter = 0;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(DT) unit_bwd_finalize_kernel(const __grid_constant__ Group<cwn_unit_bwd_desc> g) {
   __shared__ float stage[kStageFloats];
   const cwn_unit_bwd_desc& d = g.d[blockIdx.x];
   if (!d.has_bn) return;
-  const int n_tiles = (int)((d.n_rows + TM - 1) / TM);
-  const int per_tile = 2 * d.h;
-  const int chunk = kStageFloats / per_tile > 0 ? kStageFloats / per_tile : 1;
-  float s1 = 0.f, s2 = 0.f;  // column threadIdx.x
-  for (int t0 = 0; t0 < n_tiles; t0 += chunk) {
-    const int nt = (n_tiles - t0 < chunk) ? n_tiles - t0 : chunk;
-    __syncthreads();
-    for (int i = threadIdx.x; i < nt * per_tile; i += DT) stage[i] = d.red_partials[(int64_t)t0 * per_tile + i];
-    __syncthreads();
-    if (threadIdx.x < d.h)
-      for (int t = 0; t < nt; ++t) {
-        s1 += stage[t * per_tile + threadIdx.x];
-        s2 += stage[t * per_tile + d.h + threadIdx.x];
-      }
-  }
-  if (threadIdx.x < d.h) {
-    const int c = threadIdx.x;
-    d.c1[c] = s1 / (float)d.n_rows;
-    d.c2[c] = s2 / (float)d.n_rows;
-    if (d.g_gamma) d.g_gamma[c] = d.accumulate_affine ? d.g_gamma[c] + s2 : s2;
-    if (d.g_beta) d.g_beta[c] = d.accumulate_affine ? d.g_beta[c] + s1 : s1;
-  }
+  unit_bwd_finalize_body(d, stage);
 }
 
 // g_z tile -> input gradient (g_z W) and per-CTA partial weight gradient (g_z^T f_in(X)); CTA j of a problem strides

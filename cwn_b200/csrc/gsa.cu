@@ -9,6 +9,7 @@
 //
 // Replaces (reference): Tensor.index_select + torch_scatter.scatter, mp/cell_mp.py:195-198 + :423-479;
 // the per-message MLP of mp/layers.py:210-211,290-293 (in its split-weight form, see include/cwn_b200.h).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace cwn {
@@ -100,6 +101,83 @@ csr_gather_reduce_kernel(const float* __restrict__ x_src, int64_t ld_src, const 
         O::store(out + r * ld_out + (int64_t)c * O::W, a);
       }
     }
+  }
+}
+
+// Same contract as csr_gather_reduce_kernel, restructured for the HBM-bound regime (ncu on the first version: 60 %
+// issue-slot utilisation, 27 % DRAM throughput — the per-row scalar loads of rowptr/idx and the row-at-a-time gather
+// window were the cost). A group of LPR lanes now owns LPR CONSECUTIVE rows: the row pointers and the message indices
+// of the whole chunk are fetched with coalesced loads (one element per lane) and broadcast by warp shuffles, and the
+// 128-bit gathers are issued four at a time ACROSS row boundaries. Messages are still accumulated strictly in plan
+// order, one row after the other, so results stay bit-identical to the sequential definition.
+template <typename V, int LPR, int REDUCE>
+__global__ void __launch_bounds__(kThreads)
+csr_gather_reduce_chunked_kernel(const float* __restrict__ x_src, int64_t ld_src, const int32_t* __restrict__ rowptr,
+                                 const int32_t* __restrict__ idx, int64_t n_rows, int FV,
+                                 const float* __restrict__ x_res, int64_t ld_res, const float* __restrict__ eps,
+                                 float* __restrict__ out, int64_t ld_out) {
+  using O = VecOps<V>;
+  constexpr int GPB = kThreads / LPR;  // groups per CTA
+  const int lane = threadIdx.x % LPR;
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x % 32) / LPR * LPR));
+  const float scale = x_res ? __fadd_rn(1.f, eps ? __ldg(eps) : 0.f) : 0.f;
+  const bool col_live = lane < FV;
+  const int64_t n_chunks = (n_rows + LPR - 1) / LPR;
+  for (int64_t chunk = (int64_t)blockIdx.x * GPB + threadIdx.x / LPR; chunk < n_chunks; chunk += (int64_t)gridDim.x * GPB) {
+    const int64_t r0 = chunk * LPR;
+    const int nrow = (int)((n_rows - r0 < LPR) ? n_rows - r0 : LPR);
+    const int my_beg = (lane < nrow) ? __ldg(rowptr + r0 + lane) : 0;
+    const int my_end = (lane < nrow) ? __ldg(rowptr + r0 + lane + 1) : 0;
+    const int m0 = __shfl_sync(gmask, my_beg, 0, LPR);
+    const int m1 = __shfl_sync(gmask, my_end, nrow - 1, LPR);
+    int cur = 0;
+    int cur_end = __shfl_sync(gmask, my_end, 0, LPR);
+    int cur_beg = m0;
+    V acc = O::zero();
+
+    auto flush = [&]() {  // finish row `cur`
+      V a = acc;
+      if (REDUCE == CWN_REDUCE_MEAN) {
+        const float cnt = (float)max(cur_end - cur_beg, 1);
+        a = O::map2(a, a, [cnt](float v, float) { return __fdiv_rn(v, cnt); });
+      }
+      if (col_live) {
+        const int64_t r = r0 + cur;
+        if (x_res) {
+          V xr = O::load(x_res + r * ld_res + (int64_t)lane * O::W);
+          a = O::map2(a, xr, [scale](float s_, float x) { return __fadd_rn(s_, __fmul_rn(scale, x)); });
+        }
+        O::store(out + r * ld_out + (int64_t)lane * O::W, a);
+      }
+      acc = O::zero();
+      ++cur;
+      cur_beg = cur_end;
+      cur_end = __shfl_sync(gmask, my_end, cur < LPR ? cur : LPR - 1, LPR);
+    };
+
+    for (int base = m0; base < m1; base += LPR) {
+      const int cnt = (m1 - base < LPR) ? m1 - base : LPR;
+      const int my_idx = (lane < cnt) ? (idx ? __ldg(idx + base + lane) : base + lane) : 0;
+      for (int j0 = 0; j0 < cnt; j0 += kUnroll) {
+        V v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int s = __shfl_sync(gmask, my_idx, (j0 + u < LPR) ? j0 + u : LPR - 1, LPR);
+          if (j0 + u < cnt && col_live) v[u] = O::load(x_src + (int64_t)s * ld_src + (int64_t)lane * O::W);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int m = base + j0 + u;
+          if (j0 + u >= cnt) break;
+          while (m >= cur_end) flush();  // also writes the (zero / residual-only) rows that have no message
+          if (col_live) {
+            if (REDUCE == CWN_REDUCE_MAX) acc = (m == cur_beg) ? v[u] : O::map2(acc, v[u], MaxOp());
+            else acc = O::map2(acc, v[u], AddRn());
+          }
+        }
+      }
+    }
+    while (cur < nrow) flush();
   }
 }
 
@@ -312,6 +390,11 @@ static int check_matrix(const float* p, int64_t ld, int F, const char* name) {
 
 static bool vec_ok(const float* p, int64_t ld) { return p == nullptr || (aligned16(p) && ld % 4 == 0); }
 
+static bool getenv_flag(const char* name) {  // A/B switches for profiling; read once
+  const char* v = getenv(name);
+  return v && v[0] == '1';
+}
+
 }  // namespace cwn
 
 using namespace cwn;
@@ -340,11 +423,39 @@ extern "C" int cwn_csr_gather_reduce_f32(const float* x_src, int64_t ld_src, con
   if (reduce == CWN_REDUCE_ADD) LAUNCH(VT, VPLV, CWN_REDUCE_ADD);        \
   else if (reduce == CWN_REDUCE_MEAN) LAUNCH(VT, VPLV, CWN_REDUCE_MEAN); \
   else LAUNCH(VT, VPLV, CWN_REDUCE_MAX)
+#define LAUNCH_CHUNKED(VT, RED)                                                                                        \
+  csr_gather_reduce_chunked_kernel<VT, LPR, RED><<<grid_c, kThreads, 0, st>>>(x_src, ld_src, rowptr, idx, n_rows, g.fv, \
+                                                                              x_res, ld_res, eps, out, ld_out)
+#define BY_REDUCE_CHUNKED(VT)                                              \
+  if (reduce == CWN_REDUCE_ADD) LAUNCH_CHUNKED(VT, CWN_REDUCE_ADD);        \
+  else if (reduce == CWN_REDUCE_MEAN) LAUNCH_CHUNKED(VT, CWN_REDUCE_MEAN); \
+  else LAUNCH_CHUNKED(VT, CWN_REDUCE_MAX)
+  // One group of LPR lanes per LPR consecutive rows. Only worth it when there are enough rows to fill the machine
+  // with chunks (the HBM-bound regime); small batches keep one row per group for latency.
+  const int64_t chunks = (n_rows + g.lpr - 1) / g.lpr;
+  const int grid_c = grid_for(chunks, g.lpr);
+  const bool chunked = g.vpl == 1 && g.lpr >= 4 && n_rows >= 32768 && !getenv_flag("CWN_B200_GATHER_V1");
   if (g.vec) {
-    if (g.vpl == 1) { CWN_DISPATCH_LPR(g.lpr, BY_REDUCE(float4, 1)) } else { constexpr int LPR = 32; BY_REDUCE(float4, 2); }
+    if (chunked) {
+      switch (g.lpr) {
+        case 4: { constexpr int LPR = 4; BY_REDUCE_CHUNKED(float4); } break;
+        case 8: { constexpr int LPR = 8; BY_REDUCE_CHUNKED(float4); } break;
+        case 16: { constexpr int LPR = 16; BY_REDUCE_CHUNKED(float4); } break;
+        default: { constexpr int LPR = 32; BY_REDUCE_CHUNKED(float4); } break;
+      }
+    } else if (g.vpl == 1) { CWN_DISPATCH_LPR(g.lpr, BY_REDUCE(float4, 1)) } else { constexpr int LPR = 32; BY_REDUCE(float4, 2); }
   } else {
-    if (g.vpl == 1) { CWN_DISPATCH_LPR(g.lpr, BY_REDUCE(float, 1)) } else { constexpr int LPR = 32; BY_REDUCE(float, 2); }
+    if (chunked) {
+      switch (g.lpr) {
+        case 4: { constexpr int LPR = 4; BY_REDUCE_CHUNKED(float); } break;
+        case 8: { constexpr int LPR = 8; BY_REDUCE_CHUNKED(float); } break;
+        case 16: { constexpr int LPR = 16; BY_REDUCE_CHUNKED(float); } break;
+        default: { constexpr int LPR = 32; BY_REDUCE_CHUNKED(float); } break;
+      }
+    } else if (g.vpl == 1) { CWN_DISPATCH_LPR(g.lpr, BY_REDUCE(float, 1)) } else { constexpr int LPR = 32; BY_REDUCE(float, 2); }
   }
+#undef BY_REDUCE_CHUNKED
+#undef LAUNCH_CHUNKED
 #undef BY_REDUCE
 #undef LAUNCH
   return launched("cwn_csr_gather_reduce_f32");

@@ -78,6 +78,9 @@ def recognise(level):
 def applicable(forms, us, bs, training):
     if any(f is None for f in forms):
         return False
+    params = _parameters(forms)
+    if len({id(p) for p in params}) != len(params):
+        return False  # nets shared between dimensions (passed_update_*_nn): gradients would collide in one launch
     for f, u, b in zip(forms, us, bs):
         if not (u.is_cuda and u.dtype == torch.float32 and u.dim() == 2 and b.shape == u.shape):
             return False
@@ -95,6 +98,55 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+_counter_rings = {}
+
+
+def _counters(device, n):
+    """`n` zero int32 counters for the last-CTA hand-offs of one grouped launch. They come from a per-device ring
+    and are reset to zero by the kernel that uses them, so no memset is ever launched."""
+    ring = _counter_rings.get(device)
+    if ring is None:
+        ring = _counter_rings[device] = [torch.zeros(8192, dtype=torch.int32, device=device), 0]
+    buf, pos = ring
+    if pos + n > buf.numel():
+        pos = 0
+    ring[1] = pos + n
+    return buf[pos:pos + n]
+
+
+def _direct_grad(p):
+    """Gradient buffer to accumulate INTO (the parameter's pre-allocated `.grad`, e.g. a view of
+    cwn_b200.dist.FlatGradBucket) or None. Writing there from the kernel replaces one AccumulateGrad elementwise
+    launch per parameter per step (~150 of them); autograd then receives no gradient for that input."""
+    g = p.grad
+    if DIRECT_PARAM_GRADS and g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.is_cuda \
+            and g.shape == p.shape:
+        return g
+    return None
+
+
+DIRECT_PARAM_GRADS = True
+
+
+def _algorithmic_bytes(fn_name, d):
+    """Compulsory fp32 traffic of one problem of a grouped launch (inputs read once, outputs written once)."""
+    n, h = d.n_rows, d.h
+    if fn_name == 'cwn_linear_fwd_grouped':
+        k = d.k0 + d.k1
+        return 4 * (n * k + n * h + h * k + h)
+    if fn_name == 'cwn_bn_act_grouped':
+        return 4 * (2 * n * h + 3 * h)
+    if fn_name == 'cwn_unit_bwd_reduce_grouped':
+        return 4 * (2 * n * h) if d.has_bn else 0
+    if fn_name == 'cwn_unit_bwd_grouped':
+        k = d.k0 + d.k1
+        return 4 * (2 * n * h + n * k + (n * k if (d.g_in0 or d.g_in1) else 0) + h * k + d.n_ctas * (h * k + h))
+    if fn_name == 'cwn_wgrad_finalize_grouped':
+        k = d.k0 + d.k1
+        return 4 * (d.n_ctas + 1) * (h * k + h)
+    return 0  # the two finalize kernels move a few KB
+
+
 def _launch(fn_name, desc_type, descs):
     lib = _lib.load()
     fn = getattr(lib, fn_name)
@@ -102,7 +154,8 @@ def _launch(fn_name, desc_type, descs):
     for i in range(0, len(descs), _lib.MAX_GROUP):
         chunk = descs[i:i + _lib.MAX_GROUP]
         arr = (desc_type * len(chunk))(*chunk)
-        ops._call(fn_name[4:], 0, fn, arr, len(chunk), stream)
+        nbytes = sum(_algorithmic_bytes(fn_name, d) for d in chunk) if ops._profile is not None else 0
+        ops._call(fn_name[4:], nbytes, fn, arr, len(chunk), stream)
 
 
 class _UnitState(object):
@@ -138,32 +191,30 @@ class FusedSparseCINDense(Function):
                 return st
 
             def run_units(sts):
-                lin, bn = [], []
-                keep = []
-                for st in sts:
+                lin = []
+                counters = _counters(dev, len(sts))
+                for i, st in enumerate(sts):
                     unit = st.unit
                     n_tiles = (st.n + TM - 1) // TM
                     stats = None
+                    bn_fields = (None, 0.0, 0.0, 0, None, None, None, None, None, None, None)
                     if unit.bn is not None:
-                        st.mean, st.scale, st.rstd = (torch.empty(st.h, dtype=torch.float32, device=dev) for _ in range(3))
+                        m = unit.bn
+                        vecs = torch.empty(3, st.h, dtype=torch.float32, device=dev)
+                        st.mean, st.scale, st.rstd = vecs[0], vecs[1], vecs[2]
                         if training:
                             stats = torch.empty(max(n_tiles, 1) * 2 * st.h, dtype=torch.float32, device=dev)
-                            keep.append(stats)
+                        bn_fields = (_p(m.weight), float(m.eps), float(m.momentum), int(training), _p(m.running_mean),
+                                     _p(m.running_var), _p(m.num_batches_tracked), _p(st.mean), _p(st.scale),
+                                     _p(st.rstd), counters[i:i + 1].data_ptr())
                     i0 = st.in0 or (None, None, None)
                     i1 = st.in1 or (None, None, None)
                     lin.append(_lib.LinearDesc(
                         _p(st.x0), st.x0.stride(0), st.x0.size(1), _p(st.x1), st.x1.stride(0) if st.x1 is not None else 0,
                         st.x1.size(1) if st.x1 is not None else 0, _p(i0[0]), _p(i0[1]), _p(i0[2]), _p(i1[0]), _p(i1[1]),
                         _p(i1[2]), ops.ACT_CODES[st.in_act], _p(unit.lin.weight), unit.lin.weight.stride(0),
-                        _p(unit.lin.bias), _p(st.z), st.h, _p(stats), st.n, st.h))
-                    if unit.bn is not None:
-                        m = unit.bn
-                        bn.append(_lib.BNDesc(_p(stats), n_tiles, st.n, st.h, _p(m.weight), _p(m.bias), float(m.eps),
-                                              float(m.momentum), int(training), _p(m.running_mean), _p(m.running_var),
-                                              _p(m.num_batches_tracked), _p(st.mean), _p(st.scale), _p(st.rstd)))
+                        _p(unit.lin.bias), _p(st.z), st.h, _p(stats), st.n, st.h, *bn_fields))
                 _launch('cwn_linear_fwd_grouped', _lib.LinearDesc, lin)
-                if bn:
-                    _launch('cwn_bn_finalize_grouped', _lib.BNDesc, bn)
 
             l1, l2, l3 = [], [], []
             for d in range(n_dims):
@@ -214,7 +265,8 @@ class FusedSparseCINDense(Function):
         def unit_descs(items):
             """items: list of (state, g_out, want_g_in0, want_g_in1) -> (descs, list of (g_in0, g_in1))"""
             descs, gins = [], []
-            for st, g, want0, want1 in items:
+            counters = _counters(dev, len(items))
+            for i, (st, g, want0, want1) in enumerate(items):
                 unit = st.unit
                 k0 = st.x0.size(1)
                 k1 = st.x1.size(1) if st.x1 is not None else 0
@@ -224,12 +276,21 @@ class FusedSparseCINDense(Function):
                 g = g.contiguous()
                 gi0 = new(st.n, k0) if want0 else None
                 gi1 = new(st.n, k1) if (want1 and k1) else None
-                gw, gb = new(st.h, k0 + k1), new(st.h)
-                grads[id(unit.lin.weight)], grads[id(unit.lin.bias)] = gw, gb
+                # parameter gradients: straight into `.grad` when it is pre-allocated (accumulate), else fresh tensors
+                gw, gb = _direct_grad(unit.lin.weight), _direct_grad(unit.lin.bias)
+                acc_w = int(gw is not None and gb is not None)
+                if not acc_w:
+                    gw, gb = new(st.h, k0 + k1), new(st.h)
+                    grads[id(unit.lin.weight)], grads[id(unit.lin.bias)] = gw, gb
                 red = c1 = c2 = gg = gbeta = None
+                acc_a = 0
                 if has_bn:
-                    red, c1, c2, gg, gbeta = new(max(n_tiles, 1) * 2 * st.h), new(st.h), new(st.h), new(st.h), new(st.h)
-                    grads[id(unit.bn.weight)], grads[id(unit.bn.bias)] = gg, gbeta
+                    red, c1, c2 = new(max(n_tiles, 1) * 2 * st.h), new(st.h), new(st.h)
+                    gg, gbeta = _direct_grad(unit.bn.weight), _direct_grad(unit.bn.bias)
+                    acc_a = int(gg is not None and gbeta is not None)
+                    if not acc_a:
+                        gg, gbeta = new(st.h), new(st.h)
+                        grads[id(unit.bn.weight)], grads[id(unit.bn.bias)] = gg, gbeta
                 i0 = st.in0 or (None, None, None)
                 i1 = st.in1 or (None, None, None)
                 descs.append(_lib.UnitBwdDesc(
@@ -238,17 +299,17 @@ class FusedSparseCINDense(Function):
                     _p(unit.lin.weight), unit.lin.weight.stride(0), _p(st.z), st.h, int(has_bn),
                     ops.ACT_CODES[unit.act], _p(st.mean), _p(st.scale), _p(st.rstd),
                     _p(unit.bn.bias) if has_bn else None, _p(g), g.stride(0), _p(red), _p(c1), _p(c2), _p(gg),
-                    _p(gbeta), 0, _p(gi0), k0, _p(gi1), k1, _p(new(max(n_ctas, 1) * st.h * (k0 + k1))),
-                    _p(new(max(n_ctas, 1) * st.h)), n_ctas, _p(gw), k0 + k1, _p(gb), 0, st.n, st.h))
+                    _p(gbeta), acc_a, _p(gi0), k0, _p(gi1), k1, _p(new(max(n_ctas, 1) * st.h * (k0 + k1))),
+                    _p(new(max(n_ctas, 1) * st.h)), n_ctas, _p(gw), gw.stride(0), _p(gb), acc_w, st.n, st.h,
+                    counters[i:i + 1].data_ptr() if has_bn else None))
                 keep.append(g)
                 gins.append((gi0, gi1))
             return descs, gins
 
         def run(items):
             descs, gins = unit_descs(items)
-            if any(d.has_bn for d in descs):
+            if any(d.has_bn for d in descs):  # column reductions; the last CTA of each problem finalises them
                 _launch('cwn_unit_bwd_reduce_grouped', _lib.UnitBwdDesc, descs)
-                _launch('cwn_unit_bwd_finalize_grouped', _lib.UnitBwdDesc, descs)
             _launch('cwn_unit_bwd_grouped', _lib.UnitBwdDesc, descs)
             return descs, gins
 
@@ -324,7 +385,7 @@ class GroupedLinear(Function):
                 y = torch.empty(x.size(0), w.size(0), dtype=torch.float32, device=dev)
                 descs.append(_lib.LinearDesc(_p(x), x.stride(0), x.size(1), None, 0, 0, None, None, None, None, None,
                                              None, 0, _p(w), w.stride(0), _p(b), _p(y), y.size(1), None, x.size(0),
-                                             w.size(0)))
+                                             w.size(0), None, 0.0, 0.0, 0, None, None, None, None, None, None, None))
                 ys.append(y)
             _launch('cwn_linear_fwd_grouped', _lib.LinearDesc, descs)
         ctx.n, ctx.has_bias = n, has_bias
@@ -353,7 +414,7 @@ class GroupedLinear(Function):
                 descs.append(_lib.UnitBwdDesc(
                     _p(x), x.stride(0), k, None, 0, 0, None, None, None, None, None, None, 0, _p(w), w.stride(0),
                     _p(g), g.stride(0), 0, 0, None, None, None, None, _p(g), g.stride(0), None, None, None, None, None,
-                    0, _p(gx), k, None, 0, _p(wp), _p(bp), n_ctas, _p(gw), k, _p(gb), 0, nr, h))
+                    0, _p(gx), k, None, 0, _p(wp), _p(bp), n_ctas, _p(gw), k, _p(gb), 0, nr, h, None))
                 gxs.append(gx)
                 gws.append(gw)
                 gbs.append(gb if ctx.has_bias[i] else None)

@@ -410,7 +410,7 @@ class AbstractEmbedVEWithReduce(torch.nn.Module, ABC):
         e_params = cochain_params[1] if len(cochain_params) >= 2 else None
         c_params = cochain_params[2] if len(cochain_params) == 3 else None
 
-        vx = self.v_embed_layer(self._prepare_v_inputs(v_params))
+        vx = self._embed(self.v_embed_layer, self._prepare_v_inputs(v_params))
         out = [vx]
         if e_params is None:
             assert c_params is None
@@ -419,7 +419,7 @@ class AbstractEmbedVEWithReduce(torch.nn.Module, ABC):
         reduced_ex = self.init_reduce(vx, e_params.boundary_index, getattr(e_params, 'num_cells', None))
         ex = reduced_ex
         if e_params.x is not None:
-            ex = self.e_embed_layer(self._prepare_e_inputs(e_params))
+            ex = self._embed(self.e_embed_layer, self._prepare_e_inputs(e_params))
             assert ex.size(1) == vx.size(1)
         out.append(ex)
 
@@ -427,6 +427,16 @@ class AbstractEmbedVEWithReduce(torch.nn.Module, ABC):
             cx = self.init_reduce(reduced_ex, c_params.boundary_index, getattr(c_params, 'num_cells', None)) / 2.
             out.append(cx)
         return out
+
+    @staticmethod
+    def _embed(layer, inputs):
+        """A plain `nn.Embedding` lookup is a row gather: run it (and its gradient, a segmented reduction over a
+        CSR plan of the type ids instead of torch's sort-based embedding backward) on the cwn kernels."""
+        if (type(layer) is torch.nn.Embedding and layer.padding_idx is None and layer.max_norm is None
+                and not layer.sparse and not layer.scale_grad_by_freq and inputs.dim() == 1 and inputs.is_cuda
+                and layer.weight.dtype == torch.float32):
+            return ops.gather_rows(layer.weight, inputs)
+        return layer(inputs)
 
     def reset_parameters(self):
         reset(self.v_embed_layer)

@@ -312,7 +312,7 @@ def _residual_grads(needs_res, needs_eps, g, x_res_saved, eps):
     """(grad x_res, grad eps) of out = (1 + eps) * x_res + ... ; `x_res_saved` is only kept when eps needs a grad."""
     g_res = g_eps = None
     if needs_res:
-        g_res = g if eps is None else g * (1.0 + eps)
+        g_res = g if eps is None else torch.addcmul(g, g, eps)  # (1 + eps) * g in one launch
     if needs_eps and eps is not None:
         g_eps = (g * x_res_saved).sum().reshape(eps.shape)
     return g_res, g_eps

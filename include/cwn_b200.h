@@ -150,6 +150,13 @@ typedef struct {
   float* z; int64_t ld_z;                                  /* output [n_rows, h] */
   float* stats;                                            /* nullable: per row tile (64 rows) [n_tiles, 2, h] = (mean, M2) */
   int64_t n_rows; int32_t h;
+  /* optional fused BatchNorm finalisation (same outputs as cwn_bn_finalize_grouped): the LAST CTA of the problem to
+   * finish merges the per-tile partials, so no second launch is needed. `counter` must point to a zero int32; it is
+   * reset to zero before the kernel ends. bn_mean == NULL disables it. */
+  const float* bn_gamma; float bn_eps; float bn_momentum; int32_t bn_training;
+  float* bn_running_mean; float* bn_running_var; int64_t* bn_num_batches_tracked;
+  float* bn_mean; float* bn_scale; float* bn_rstd;
+  int32_t* counter;
 } cwn_linear_desc;
 int cwn_linear_fwd_grouped(const cwn_linear_desc* descs, int32_t n, cwn_stream_t stream);
 
@@ -200,6 +207,7 @@ typedef struct {
   int32_t n_ctas;        /* CTAs assigned to this problem in step 3 (each strides over the row tiles) */
   float* g_w; int64_t ld_gw; float* g_b; int32_t accumulate_w;
   int64_t n_rows; int32_t h;
+  int32_t* counter;      /* nullable: zero int32; if set, the last CTA of cwn_unit_bwd_reduce_grouped performs step 2 */
 } cwn_unit_bwd_desc;
 int cwn_unit_bwd_reduce_grouped(const cwn_unit_bwd_desc* descs, int32_t n, cwn_stream_t stream);
 int cwn_unit_bwd_finalize_grouped(const cwn_unit_bwd_desc* descs, int32_t n, cwn_stream_t stream);

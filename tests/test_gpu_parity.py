@@ -548,6 +548,20 @@ def test_fused_dense_layer_equals_torch_modules(layer_dim, hidden, act, norm, co
             assert_close(p1[k].grad, p2[k].grad, rtol=1e-4, atol=atol, what=f'grad {k}')
     for k in b1:
         assert_close(b1[k].float(), b2[k].float(), rtol=1e-5, atol=1e-6, what=f'buffer {k}')
+    # second step on the fused layer: `.grad` now exists, so the kernels accumulate straight into it (the
+    # FlatGradBucket mode) instead of handing gradients to autograd; same inputs => same gradients
+    for prm in fused_conv.parameters():
+        if prm.grad is not None:
+            prm.grad.zero_()
+    batch = ComplexBatch.from_complex_list(synthetic.float_feature_complexes(7, layer_dim, seed=11, ragged=True)).to(DEV)
+    outs = fused_conv(*batch.get_all_cochain_params(max_dim=2, include_down_features=False))
+    g = torch.Generator(device=DEV).manual_seed(3)
+    sum((o * torch.randn(o.shape, device=DEV, generator=g)).sum() for o in outs).backward()
+    for k in p1:
+        if p2[k].grad is not None:
+            scale = float(p2[k].grad.abs().max()) + 1e-6
+            atol = 2e-5 if k.endswith(('eps1', 'eps2')) else 1e-4 * scale
+            assert_close(p1[k].grad, p2[k].grad, rtol=1e-4, atol=atol, what=f'direct grad {k}')
     with torch.no_grad():
         for conv in (fused_conv, torch_conv):
             conv.eval()
@@ -558,3 +572,25 @@ def test_fused_dense_layer_equals_torch_modules(layer_dim, hidden, act, norm, co
             outs.append(conv(*batch.get_all_cochain_params(max_dim=2, include_down_features=False)))
         for d in range(3):
             assert_close(outs[0][d], outs[1][d], rtol=1e-5, atol=2e-5, what=f'eval out {d}')
+
+
+@pytest.mark.parametrize('F', [16, 20, 64, 128])
+@pytest.mark.parametrize('reduce', ['add', 'mean', 'max'])
+def test_chunked_gather_kernel_large_row_counts(F, reduce):
+    """>= 32768 destination rows select the chunked kernel (coalesced index loads + shuffles). Integer-valued
+    features make every summation order exact, so equality with torch's own scatter must be bit-exact; rows without
+    messages (every 7th destination is skipped, plus a tail) must come out as zeros / residual only."""
+    n_src, n_dst, E = 50_000, 70_001, 260_000
+    g = torch.Generator().manual_seed(F)
+    dst = torch.randint(0, n_dst - 300, (E,), generator=g)
+    dst = dst - (dst % 7 == 0).long()  # leave holes
+    dst.clamp_(min=1)
+    idx = torch.stack([torch.randint(0, n_src, (E,), generator=g), dst]).to(DEV)
+    x = torch.randint(-6, 7, (n_src, F), generator=g).float().to(DEV)
+    ref = O.scatter(x.index_select(0, idx[0]), idx[1], n_dst, reduce)
+    out = ops.gather_scatter(x, idx, n_dst, reduce)
+    assert torch.equal(out, ref)
+    if reduce == 'add':
+        res = torch.randint(-3, 4, (n_dst, F), generator=g).float().to(DEV)
+        eps = torch.tensor([1.0], device=DEV)
+        assert torch.equal(ops.gather_scatter(x, idx, n_dst, 'add', x_res=res, eps=eps), ref + 2 * res)
