@@ -288,6 +288,7 @@ def run_cwn(args, rank, world, local_rank):
     import torch.distributed as dist
     from cwn_b200 import _lib, ops
     from cwn_b200.dist import FlatGradBucket, broadcast_parameters
+    from cwn_b200.optim import FlatAdam
     from cwn_b200.mp.molec_models import EmbedSparseCIN
 
     if not torch.cuda.is_available():
@@ -305,7 +306,7 @@ def run_cwn(args, rank, world, local_rank):
     model = EmbedSparseCIN(**MODEL_CFG).to(dev).train()
     broadcast_parameters(model)
     bucket = FlatGradBucket(model)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=True)
+    opt = FlatAdam(model, bucket, lr=1e-3)  # one launch; also clears the gradient bucket for the next step
 
     host_batches = [b.pack_(pin_memory=True) for b in make_batches(args.pool, args.batch, seed0=1000 + 100 * rank)]
     cells = cells_of(host_batches[0])
@@ -316,7 +317,6 @@ def run_cwn(args, rank, world, local_rank):
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2
 
     def step(batch):
-        bucket.zero()
         out = model(batch)
         loss = l1(out, batch.y)
         loss.backward()

@@ -191,7 +191,7 @@ class FusedSparseCINDense(Function):
                 return st
 
             def run_units(sts):
-                lin = []
+                lin, alive = [], []  # `alive`: descriptors hold raw pointers only — keep the scratch tensors referenced
                 counters = _counters(dev, len(sts))
                 for i, st in enumerate(sts):
                     unit = st.unit
@@ -204,6 +204,7 @@ class FusedSparseCINDense(Function):
                         st.mean, st.scale, st.rstd = vecs[0], vecs[1], vecs[2]
                         if training:
                             stats = torch.empty(max(n_tiles, 1) * 2 * st.h, dtype=torch.float32, device=dev)
+                            alive.append(stats)
                         bn_fields = (_p(m.weight), float(m.eps), float(m.momentum), int(training), _p(m.running_mean),
                                      _p(m.running_var), _p(m.num_batches_tracked), _p(st.mean), _p(st.scale),
                                      _p(st.rstd), counters[i:i + 1].data_ptr())
@@ -364,66 +365,104 @@ def sparse_cin_dense(forms, us, bs, training):
 
 # ------------------------------------------------------------------------------------------------ plain linears
 class GroupedLinear(Function):
-    """ys[i] = xs[i] @ ws[i].T (+ bs[i]) for up to 8 independent problems in one launch forward and two backward
-    (input gradients + per-CTA weight-gradient partials, then their ordered sum). Weights may be column slices of a
-    larger matrix (explicit leading dimension), which is how the coboundary message Linear(2F -> F) of
-    mp/layers.py:290-293 is applied as two per-cell products (x W1^T, y W2^T + b)."""
+    """ys[i] = xs[i] @ W_i[:, off_i : off_i + k_i].T (+ b_i) for up to 8 independent problems in one launch forward
+    and two backward (input gradients + per-CTA weight-gradient partials, then their ordered sum). A problem may use a
+    COLUMN RANGE of a larger weight matrix — that is how the coboundary message Linear(2F -> F) of
+    mp/layers.py:290-293 is applied as two per-cell products (x W[:, :F]^T and y W[:, F:]^T + b) without slicing
+    tensors, and how both halves of its gradient land in one [F, 2F] buffer.
+
+    spec: tuple of (weight slot, column offset, bias slot or -1) per problem; tensors = xs, unique weights, biases."""
 
     @staticmethod
-    def forward(ctx, n, has_bias, *tensors):
-        xs, ws = tensors[:n], tensors[n:2 * n]
-        bs = list(tensors[2 * n:])
-        biases, j = [], 0
-        for i in range(n):
-            biases.append(bs[j] if has_bias[i] else None)
-            j += 1 if has_bias[i] else 0
+    def forward(ctx, spec, n_weights, *tensors):
+        n = len(spec)
+        xs = [x if x.stride(1) == 1 else x.contiguous() for x in tensors[:n]]
+        weights = tensors[n:n + n_weights]
+        biases = tensors[n + n_weights:]
         dev = xs[0].device
         ys, descs = [], []
         with torch.cuda.device(dev):
-            xs = [x if x.stride(1) == 1 else x.contiguous() for x in xs]
-            for x, w, b in zip(xs, ws, biases):
+            for x, (wi, off, bi) in zip(xs, spec):
+                w = weights[wi]
+                b = biases[bi] if bi >= 0 else None
                 y = torch.empty(x.size(0), w.size(0), dtype=torch.float32, device=dev)
                 descs.append(_lib.LinearDesc(_p(x), x.stride(0), x.size(1), None, 0, 0, None, None, None, None, None,
-                                             None, 0, _p(w), w.stride(0), _p(b), _p(y), y.size(1), None, x.size(0),
-                                             w.size(0), None, 0.0, 0.0, 0, None, None, None, None, None, None, None))
+                                             None, 0, w.data_ptr() + 4 * off, w.stride(0), _p(b), _p(y), y.size(1), None,
+                                             x.size(0), w.size(0), None, 0.0, 0.0, 0, None, None, None, None, None, None,
+                                             None))
                 ys.append(y)
             _launch('cwn_linear_fwd_grouped', _lib.LinearDesc, descs)
-        ctx.n, ctx.has_bias = n, has_bias
-        ctx.save_for_backward(*xs, *ws)
+        ctx.spec, ctx.n_weights, ctx.n_biases = spec, n_weights, len(biases)
+        ctx.params = list(weights) + list(biases)  # for direct gradient accumulation (identity of the Parameters)
+        ctx.save_for_backward(*xs, *weights)
         return tuple(ys)
 
     @staticmethod
     def backward(ctx, *gs):
-        n = ctx.n
-        xs, ws = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
+        spec, n = ctx.spec, len(ctx.spec)
+        xs, weights = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
+        w_params, b_params = ctx.params[:ctx.n_weights], ctx.params[ctx.n_weights:]
         dev = xs[0].device
-        gxs, gws, gbs, descs, keep = [], [], [], [], []
         with torch.cuda.device(dev):
-            for i, (x, w, g) in enumerate(zip(xs, ws, gs)):
+            # gradient buffers: the parameter's own `.grad` (accumulate) when pre-allocated, else fresh tensors
+            gw_bufs, gw_out, acc = [], [], []
+            for slot, (w, prm) in enumerate(zip(weights, w_params)):
+                direct = _direct_grad(prm)
+                covered = sum(xs[i].size(1) for i, (wi, _, _) in enumerate(spec) if wi == slot)
+                if direct is not None:
+                    gw_bufs.append(direct), gw_out.append(None), acc.append(1)
+                else:
+                    buf = torch.empty_like(w, memory_format=torch.contiguous_format) if covered == w.size(1) \
+                        else torch.zeros_like(w, memory_format=torch.contiguous_format)
+                    gw_bufs.append(buf), gw_out.append(buf), acc.append(0)
+            gb_bufs, gb_out, acc_b = [], [], []
+            for prm in b_params:
+                direct = _direct_grad(prm)
+                if direct is not None:
+                    gb_bufs.append(direct), gb_out.append(None), acc_b.append(1)
+                else:
+                    buf = torch.empty_like(prm)
+                    gb_bufs.append(buf), gb_out.append(buf), acc_b.append(0)
+            gxs, descs, keep = [], [], []
+            for i, (x, g, (wi, off, bi)) in enumerate(zip(xs, gs, spec)):
+                w = weights[wi]
                 nr, k, h = x.size(0), x.size(1), w.size(0)
                 g = (g if g is not None else torch.zeros(nr, h, device=dev)).contiguous()
                 n_tiles = (nr + TM - 1) // TM
                 n_ctas = min(n_tiles, 148)
                 gx = torch.empty(nr, k, dtype=torch.float32, device=dev) if ctx.needs_input_grad[2 + i] else None
-                gw = torch.empty(h, k, dtype=torch.float32, device=dev)
-                gb = torch.empty(h, dtype=torch.float32, device=dev)
                 wp = torch.empty(max(n_ctas, 1) * h * k, dtype=torch.float32, device=dev)
                 bp = torch.empty(max(n_ctas, 1) * h, dtype=torch.float32, device=dev)
+                gb = gb_bufs[bi] if bi >= 0 else None
+                # a weight and its bias accumulate together (one flag per problem): both or neither are direct
+                accumulate = acc[wi] if bi < 0 else int(acc[wi] and acc_b[bi])
+                if bi >= 0 and acc[wi] != acc_b[bi]:
+                    raise RuntimeError('cwn_b200: weight and bias of a Linear must both have (or both lack) a .grad')
                 keep += [g, wp, bp]
                 # the "z" operand is only read through act'(z) with act = id, so any valid [n, h] matrix will do
                 descs.append(_lib.UnitBwdDesc(
-                    _p(x), x.stride(0), k, None, 0, 0, None, None, None, None, None, None, 0, _p(w), w.stride(0),
-                    _p(g), g.stride(0), 0, 0, None, None, None, None, _p(g), g.stride(0), None, None, None, None, None,
-                    0, _p(gx), k, None, 0, _p(wp), _p(bp), n_ctas, _p(gw), k, _p(gb), 0, nr, h, None))
+                    _p(x), x.stride(0), k, None, 0, 0, None, None, None, None, None, None, 0,
+                    w.data_ptr() + 4 * off, w.stride(0), _p(g), g.stride(0), 0, 0, None, None, None, None, _p(g),
+                    g.stride(0), None, None, None, None, None, 0, _p(gx), k, None, 0, _p(wp), _p(bp), n_ctas,
+                    gw_bufs[wi].data_ptr() + 4 * off, gw_bufs[wi].stride(0), _p(gb), accumulate, nr, h, None))
                 gxs.append(gx)
-                gws.append(gw)
-                gbs.append(gb if ctx.has_bias[i] else None)
             _launch('cwn_unit_bwd_grouped', _lib.UnitBwdDesc, descs)
             _launch('cwn_wgrad_finalize_grouped', _lib.UnitBwdDesc, descs)
-        return (None, None, *gxs, *gws, *[b for b in gbs if b is not None])
+        return (None, None, *gxs, *gw_out, *gb_out)
 
 
-def grouped_linear(xs, ws, bs):
-    """[x @ w.T + b for x, w, b in zip(xs, ws, bs)] (b may be None) with one launch; fp32 CUDA matrices."""
-    has_bias = tuple(b is not None for b in bs)
-    return list(GroupedLinear.apply(len(xs), has_bias, *xs, *ws, *[b for b in bs if b is not None]))
+def grouped_linear(problems):
+    """problems: list of (x, weight, column offset, bias or None); y = x @ weight[:, off:off + x.size(1)].T + bias.
+    One launch for all of them; fp32 CUDA matrices."""
+    weights, biases, spec = [], [], []
+    for x, w, off, b in problems:
+        wi = next((i for i, t in enumerate(weights) if t is w), None)
+        if wi is None:
+            weights.append(w)
+            wi = len(weights) - 1
+        bi = -1
+        if b is not None:
+            biases.append(b)
+            bi = len(biases) - 1
+        spec.append((wi, int(off), bi))
+    return list(GroupedLinear.apply(tuple(spec), len(weights), *[p[0] for p in problems], *weights, *biases))

@@ -8,9 +8,9 @@ buffers; a training step is then `load_packed_` (one copy per dtype into the sta
 memory or from HBM) + one graph launch.
 
 A graph is specific to a packed layout (`Complex.packed_signature`: the cell and message counts of every
-dimension). Batches of identically shaped complexes (the synthetic benchmark) share one graph; ragged real batches
-get one graph per signature (`CapturedStep.for_batch` keeps them in a dict) and fall back to eager execution
-beyond `max_graphs` distinct layouts.
+dimension). Batches of identically shaped complexes (the synthetic benchmark) share one graph; `run()` refuses a
+batch with another layout (`load_packed_` raises), in which case the caller runs the eager path or captures
+another `CapturedStep` for that layout. Padding ragged batches to a few bucketed layouts is future work.
 """
 import torch
 
@@ -46,7 +46,8 @@ class CapturedStep(object):
         for d, x in enumerate(self._inputs):  # the forward overwrites cochain.x with hidden features (set_xs)
             b.cochains[d]._x = x
         ops.clear_plan_cache(*self._indices)  # plans are part of the step: every step is a new batch
-        self.bucket.zero()
+        if not getattr(self.optimizer, 'zero_grad', False):
+            self.bucket.zero()  # (FlatAdam clears the gradients it consumed itself)
         out = self.model(b)
         loss = self.loss_fn(out, b.y)
         loss.backward()
@@ -75,6 +76,7 @@ class CapturedStep(object):
             self.opt_graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.opt_graph):
                 self.optimizer.step()
+        self.bucket.zero()  # gradients accumulated by the warm-up / capture passes must not leak into step 1
         return self
 
     @property

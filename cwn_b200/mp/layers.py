@@ -242,8 +242,7 @@ class SparseCINCochainConv(CochainMessagePassing):
         up_branch.split_linear = None
         if up_index is not None and form[0] == 'cob':
             fx = x.size(1)
-            up_branch.split_linear = ([x, up_attr.source], [form[1].weight[:, :fx], form[1].weight[:, fx:]],
-                                      [None, form[1].bias])
+            up_branch.split_linear = [(x, form[1].weight, 0, None), (up_attr.source, form[1].weight, fx, form[1].bias)]
 
         def boundary_branch():  # the pass only runs when boundary features exist (reference mp/cell_mp.py:381)
             if b_attr is not None:
@@ -316,11 +315,8 @@ class SparseCINConv(_PerDimension):
                 device = cochain_params[0].x.device
                 # the split-weight products of every dimension's coboundary message net in one grouped launch
                 reqs = [(d, branches[d][0].split_linear) for d in range(n) if branches[d][0].split_linear]
-                if reqs and all(t.is_cuda and t.dtype == torch.float32 for _, r in reqs for t in r[0]):
-                    xs = [t for _, r in reqs for t in r[0]]
-                    ws = [t for _, r in reqs for t in r[1]]
-                    bs_ = [t for _, r in reqs for t in r[2]]
-                    prods = fused.grouped_linear(xs, ws, bs_)
+                if reqs and all(prob[0].is_cuda and prob[0].dtype == torch.float32 for _, r in reqs for prob in r):
+                    prods = fused.grouped_linear([prob for _, r in reqs for prob in r])
                     for i, (d, _) in enumerate(reqs):
                         up, pq = branches[d][0], (prods[2 * i], prods[2 * i + 1])
                         branches[d] = ((lambda up=up, pq=pq: up(pq)), branches[d][1])

@@ -214,6 +214,13 @@ int cwn_unit_bwd_finalize_grouped(const cwn_unit_bwd_desc* descs, int32_t n, cwn
 int cwn_unit_bwd_grouped(const cwn_unit_bwd_desc* descs, int32_t n, cwn_stream_t stream);
 int cwn_wgrad_finalize_grouped(const cwn_unit_bwd_desc* descs, int32_t n, cwn_stream_t stream);
 
+/* Adam (torch.optim.Adam semantics: L2 weight decay, no amsgrad; reference exp/run_exp.py:343) over flat parameter /
+ * gradient / moment buffers in ONE launch. `step` (device int32, number of updates so far) is advanced by the kernel;
+ * `counter` must point to a zero int32 and is reset by the kernel. zero_grad != 0 clears `grad` after use. */
+int cwn_adam_step_f32(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, int32_t* step, int32_t* counter, int32_t zero_grad,
+                      cwn_stream_t stream);
+
 /* Debug aid: sets bit 1 of flags[0] if any idx[e] is outside [0, n). (The reference relies on torch's device
  * assert for out-of-range indices.) */
 int cwn_check_index_range(const int64_t* idx, int64_t E, int64_t n, int32_t* flags, cwn_stream_t stream);

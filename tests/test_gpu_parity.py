@@ -594,3 +594,26 @@ def test_chunked_gather_kernel_large_row_counts(F, reduce):
         res = torch.randint(-3, 4, (n_dst, F), generator=g).float().to(DEV)
         eps = torch.tensor([1.0], device=DEV)
         assert torch.equal(ops.gather_scatter(x, idx, n_dst, 'add', x_res=res, eps=eps), ref + 2 * res)
+
+
+def test_flat_adam_matches_torch_adam():
+    from cwn_b200.dist import FlatGradBucket
+    from cwn_b200.optim import FlatAdam
+    torch.manual_seed(0)
+    mk = lambda: torch.nn.Sequential(torch.nn.Linear(7, 33), torch.nn.ReLU(), torch.nn.Linear(33, 5)).to(DEV)  # noqa: E731
+    a, b = mk(), mk()
+    b.load_state_dict(a.state_dict())
+    ref = torch.optim.Adam(b.parameters(), lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-2)
+    bucket = FlatGradBucket(a)
+    opt = FlatAdam(a, bucket, lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-2)
+    for it in range(5):
+        x = torch.randn(16, 7, device=DEV)
+        a(x).pow(2).sum().backward()
+        ref.zero_grad()
+        b(x).pow(2).sum().backward()
+        opt.step()
+        ref.step()
+        assert float(bucket.flat.abs().sum()) == 0.0  # the kernel cleared the gradients it consumed
+        for p, q in zip(a.parameters(), b.parameters()):
+            assert_close(p, q, rtol=1e-5, atol=1e-6, what=f'step {it}')
+    assert opt.num_steps == 5
