@@ -62,8 +62,9 @@ __global__ void fill_zero_kernel(int32_t* p, int64_t n) {
 // memory. At the reference's real-data shape (128 molecules: E <= 10 240 per adjacency) this replaces ~6 launches
 // per plan (13 plans per batch) by a single kernel.
 constexpr int kSmallThreads = 512;
-constexpr int kSmallItems = 24;
-constexpr int kSmallCapacity = kSmallThreads * kSmallItems;  // 12 288 messages per plan
+constexpr int kSmallItemsMax = 24;
+constexpr int kSmallItemsMin = 8;  // second instantiation for batches whose plans all have E <= 4096
+constexpr int kSmallCapacity = kSmallThreads * kSmallItemsMax;  // 12 288 messages per plan
 constexpr int kMaxPlansPerLaunch = 16;
 
 struct PlanBatch {
@@ -71,6 +72,7 @@ struct PlanBatch {
   int bits[kMaxPlansPerLaunch];
 };
 
+template <int kSmallItems>
 __global__ void __launch_bounds__(kSmallThreads)
 small_plans_kernel(const __grid_constant__ PlanBatch batch, int32_t* flags) {
   using Sort = cub::BlockRadixSort<int32_t, kSmallThreads, kSmallItems, int32_t>;
@@ -194,11 +196,14 @@ extern "C" int cwn_csr_plan_build_small(const cwn_plan_desc* descs, int32_t n_pl
   if (n_plans < 0) return fail(CWN_E_SHAPE, "cwn_csr_plan_build_small: negative plan count");
   if (n_plans == 0) return CWN_OK;
   if (!descs) return fail(CWN_E_NULL, "descs");
-  using Sort = cub::BlockRadixSort<int32_t, kSmallThreads, kSmallItems, int32_t>;
-  const size_t smem = ((sizeof(typename Sort::TempStorage) + 15) & ~size_t(15)) + (size_t)kSmallCapacity * sizeof(int32_t);
+  using SortMax = cub::BlockRadixSort<int32_t, kSmallThreads, kSmallItemsMax, int32_t>;
+  using SortMin = cub::BlockRadixSort<int32_t, kSmallThreads, kSmallItemsMin, int32_t>;
+  const size_t smem_max = ((sizeof(typename SortMax::TempStorage) + 15) & ~size_t(15)) + (size_t)kSmallThreads * kSmallItemsMax * sizeof(int32_t);
+  const size_t smem_min = ((sizeof(typename SortMin::TempStorage) + 15) & ~size_t(15)) + (size_t)kSmallThreads * kSmallItemsMin * sizeof(int32_t);
   static std::atomic<bool> configured{false};
   if (!configured.load(std::memory_order_acquire)) {
-    cudaError_t ce = cudaFuncSetAttribute(small_plans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t ce = cudaFuncSetAttribute(small_plans_kernel<kSmallItemsMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(small_plans_kernel<kSmallItemsMin>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_min);
     if (ce != cudaSuccess) return cuda_status(ce, "cudaFuncSetAttribute(small_plans_kernel)");
     configured.store(true, std::memory_order_release);
   }
@@ -214,7 +219,12 @@ extern "C" int cwn_csr_plan_build_small(const cwn_plan_desc* descs, int32_t n_pl
       batch.d[i] = d;
       batch.bits[i] = key_bits(d.n_rows);
     }
-    small_plans_kernel<<<n, kSmallThreads, smem, (cudaStream_t)stream>>>(batch, flags);
+    int64_t max_e = 0;
+    for (int i = 0; i < n; ++i) max_e = batch.d[i].E > max_e ? batch.d[i].E : max_e;
+    if (max_e <= kSmallThreads * kSmallItemsMin)
+      small_plans_kernel<kSmallItemsMin><<<n, kSmallThreads, smem_min, (cudaStream_t)stream>>>(batch, flags);
+    else
+      small_plans_kernel<kSmallItemsMax><<<n, kSmallThreads, smem_max, (cudaStream_t)stream>>>(batch, flags);
     int rc = launched("small_plans_kernel");
     if (rc) return rc;
   }

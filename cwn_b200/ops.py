@@ -279,6 +279,7 @@ def clear_plan_cache(*indices):
         if idx is not None:
             idx.__dict__.pop('_cwn_adj', None)
             idx.__dict__.pop('_cwn_rowplan', None)
+            idx.__dict__.pop('_cwn_splitkey', None)
 
 
 # --------------------------------------------------------------------------------------------- raw launches
@@ -421,8 +422,27 @@ class _GatherRows(Function):
     @staticmethod
     def backward(ctx, g):
         g = _rows(g)
-        plan = _row_plan(ctx.idx, ctx.n)
-        gx = _launch_gather_reduce(g, plan.rowptr, plan.perm, ctx.n, g.size(1), None, None, 0)
+        idx, n, E = ctx.idx, ctx.n, ctx.idx.numel()
+        split = 1
+        if E > 32 * max(n, 1):  # few, very long rows (an embedding table): one thread group per row would serialise
+            split = 2
+            while split < 256 and split * 8 * n < E:
+                split *= 2
+        if split == 1:
+            plan = _row_plan(idx, n)
+            gx = _launch_gather_reduce(g, plan.rowptr, plan.perm, n, g.size(1), None, None, 0)
+        else:
+            # two-level segmented sum: `split` interleaved sub-rows per row (deterministic), then their ordered sum
+            cache = idx.__dict__.setdefault('_cwn_splitkey', {})
+            gen = (idx._version, idx.data_ptr(), split)
+            if cache.get('gen') != gen:
+                cache.clear()
+                cache['gen'] = gen
+                lanes = torch.arange(E, device=idx.device).bitwise_and_(split - 1)
+                cache['key'] = torch.add(lanes, idx, alpha=split)
+            plan = _row_plan(cache['key'], n * split)
+            part = _launch_gather_reduce(g, plan.rowptr, plan.perm, n * split, g.size(1), None, None, 0)
+            gx = part.view(n, split, g.size(1)).sum(dim=1)
         if ctx.scale != 1.0:
             gx = gx * ctx.scale
         return gx, None, None

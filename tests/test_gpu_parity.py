@@ -544,7 +544,7 @@ def test_fused_dense_layer_equals_torch_modules(layer_dim, hidden, act, norm, co
         else:
             scale = float(p2[k].grad.abs().max()) + 1e-6
             # d/d eps = <g, x>: a sum of ~1e5 signed terms, so its fp32 rounding is not relative to the result
-            atol = 2e-5 if k.endswith(('eps1', 'eps2')) else 1e-4 * scale
+            atol = max(2e-5, 1e-4 * scale)  # (biases feeding a BatchNorm have an analytically zero gradient: pure rounding noise)
             assert_close(p1[k].grad, p2[k].grad, rtol=1e-4, atol=atol, what=f'grad {k}')
     for k in b1:
         assert_close(b1[k].float(), b2[k].float(), rtol=1e-5, atol=1e-6, what=f'buffer {k}')
@@ -560,7 +560,7 @@ def test_fused_dense_layer_equals_torch_modules(layer_dim, hidden, act, norm, co
     for k in p1:
         if p2[k].grad is not None:
             scale = float(p2[k].grad.abs().max()) + 1e-6
-            atol = 2e-5 if k.endswith(('eps1', 'eps2')) else 1e-4 * scale
+            atol = max(2e-5, 1e-4 * scale)  # (biases feeding a BatchNorm have an analytically zero gradient: pure rounding noise)
             assert_close(p1[k].grad, p2[k].grad, rtol=1e-4, atol=atol, what=f'direct grad {k}')
     with torch.no_grad():
         for conv in (fused_conv, torch_conv):
@@ -617,3 +617,18 @@ def test_flat_adam_matches_torch_adam():
         for p, q in zip(a.parameters(), b.parameters()):
             assert_close(p, q, rtol=1e-5, atol=1e-6, what=f'step {it}')
     assert opt.num_steps == 5
+
+
+def test_embedding_style_gather_backward_uses_split_rows():
+    """Few table rows, many lookups (an embedding): the gradient is a two-level segmented sum; integer-valued
+    gradients make it exactly equal to torch's index_add_."""
+    n, E, F = 7, 5000, 64
+    g = torch.Generator().manual_seed(2)
+    idx = torch.randint(0, n - 1, (E,), generator=g).to(DEV)  # row n-1 is never looked up -> zero gradient
+    w = torch.randn(n, F, device=DEV, requires_grad=True)
+    out = ops.gather_rows(w, idx)
+    assert torch.equal(out, w.detach()[idx])
+    go = torch.randint(-3, 4, (E, F), generator=g).float().to(DEV)
+    out.backward(go)
+    ref = torch.zeros(n, F, device=DEV).index_add_(0, idx, go)
+    assert torch.equal(w.grad, ref) and float(w.grad[-1].abs().sum()) == 0.0
