@@ -134,7 +134,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
-                                          '-i', str(self.gpu), '-lms', '100'], stdout=subprocess.PIPE, text=True)
+                                          '-i', str(self.gpu), '-lms', '20'], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
@@ -368,15 +368,15 @@ def run_cwn(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up
+    # ---- warm-up (the clock sampler runs from here to the end of the timed region: the region itself lasts tens of ms)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
     for i in range(max(args.warmup, 3)):
         resident_step(i)
     barrier()
 
     # ---- timed region: device-resident inputs
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     l0 = _lib.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()

@@ -632,3 +632,27 @@ def test_embedding_style_gather_backward_uses_split_rows():
     out.backward(go)
     ref = torch.zeros(n, F, device=DEV).index_add_(0, idx, go)
     assert torch.equal(w.grad, ref) and float(w.grad[-1].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize('act,F', [('relu', 64), ('elu', 32), ('tanh', 128)])
+def test_chunked_cob_kernels_large_row_counts(act, F):
+    """>= 32768 rows select the chunked coboundary kernels (forward, and both gradient passes); checked against
+    torch autograd on the same device (fp32, rtol 1e-5)."""
+    n, n_cob, E = 40_000, 9_000, 150_000
+    g = torch.Generator().manual_seed(F)
+    idx = torch.stack([torch.randint(0, n, (E,), generator=g), torch.randint(0, n - 50, (E,), generator=g)]).to(DEV)
+    cob = torch.randint(0, n_cob - 10, (E,), generator=g).to(DEV)
+    P0, Q0 = torch.randn(n, F, generator=g).to(DEV), torch.randn(40_000, F, generator=g).to(DEV)  # Q rows >= 32768 too
+    res0, w = torch.randn(n, F, generator=g).to(DEV), torch.randn(n, F, generator=g).to(DEV)
+    eps = torch.tensor([0.25], device=DEV)
+    fn = O._ACT[act]
+    P, Q, res = (t.clone().requires_grad_(True) for t in (P0, Q0, res0))
+    ref = O.scatter(fn(P.index_select(0, idx[0]) + Q.index_select(0, cob)), idx[1], n) + (1 + eps) * res
+    (ref * w).sum().backward()
+    Pg, Qg, rg = (t.clone().requires_grad_(True) for t in (P0, Q0, res0))
+    out = ops.cob_pass(Pg, Qg, idx, cob, n, act=act, x_res=rg, eps=eps)
+    assert_close(out, ref, rtol=1e-5, atol=2e-5, what='fwd')
+    (out * w).sum().backward()
+    assert_close(Pg.grad, P.grad, rtol=1e-5, atol=5e-5, what='grad P')
+    assert_close(Qg.grad, Q.grad, rtol=1e-5, atol=1e-4, what='grad Q')
+    assert float(out[-50:].sub((1 + eps) * res0[-50:]).abs().max()) == 0.0  # rows without messages: residual only
