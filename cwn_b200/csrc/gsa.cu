@@ -245,145 +245,6 @@ csr_cob_fwd_kernel(const float* __restrict__ P, int64_t ld_p, const float* __res
   }
 }
 
-// Chunked variants of the two-operand passes for the HBM-bound regime (same scheme as
-// csr_gather_reduce_chunked_kernel: LPR consecutive rows per lane group, coalesced plan loads + shuffles, gathers
-// issued across row boundaries, strictly ordered accumulation).
-template <typename V, int LPR, int ACT>
-__global__ void __launch_bounds__(kThreads)
-csr_cob_fwd_chunked_kernel(const float* __restrict__ P, int64_t ld_p, const float* __restrict__ Q, int64_t ld_q,
-                           const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src,
-                           const int32_t* __restrict__ cob, int64_t n_rows, int FV, const float* __restrict__ x_res,
-                           int64_t ld_res, const float* __restrict__ eps, float* __restrict__ out, int64_t ld_out) {
-  using O = VecOps<V>;
-  constexpr int GPB = kThreads / LPR;
-  constexpr int U = 4;
-  const int lane = threadIdx.x % LPR;
-  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x % 32) / LPR * LPR));
-  const float scale = x_res ? __fadd_rn(1.f, eps ? __ldg(eps) : 0.f) : 0.f;
-  const bool col_live = lane < FV;
-  const int64_t n_chunks = (n_rows + LPR - 1) / LPR;
-  for (int64_t chunk = (int64_t)blockIdx.x * GPB + threadIdx.x / LPR; chunk < n_chunks; chunk += (int64_t)gridDim.x * GPB) {
-    const int64_t r0 = chunk * LPR;
-    const int nrow = (int)((n_rows - r0 < LPR) ? n_rows - r0 : LPR);
-    const int my_beg = (lane < nrow) ? __ldg(rowptr + r0 + lane) : 0;
-    const int my_end = (lane < nrow) ? __ldg(rowptr + r0 + lane + 1) : 0;
-    const int m0 = __shfl_sync(gmask, my_beg, 0, LPR);
-    const int m1 = __shfl_sync(gmask, my_end, nrow - 1, LPR);
-    int cur = 0;
-    int cur_end = __shfl_sync(gmask, my_end, 0, LPR);
-    V acc = O::zero();
-    auto flush = [&]() {
-      if (col_live) {
-        const int64_t r = r0 + cur;
-        V a = acc;
-        if (x_res) {
-          V xr = O::load(x_res + r * ld_res + (int64_t)lane * O::W);
-          a = O::map2(a, xr, [scale](float s_, float x) { return __fadd_rn(s_, __fmul_rn(scale, x)); });
-        }
-        O::store(out + r * ld_out + (int64_t)lane * O::W, a);
-      }
-      acc = O::zero();
-      ++cur;
-      cur_end = __shfl_sync(gmask, my_end, cur < LPR ? cur : LPR - 1, LPR);
-    };
-    for (int base = m0; base < m1; base += LPR) {
-      const int cnt = (m1 - base < LPR) ? m1 - base : LPR;
-      const int my_s = (lane < cnt) ? __ldg(src + base + lane) : 0;
-      const int my_c = (lane < cnt) ? __ldg(cob + base + lane) : 0;
-      for (int j0 = 0; j0 < cnt; j0 += U) {
-        V vp[U], vq[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int jj = (j0 + u < LPR) ? j0 + u : LPR - 1;
-          const int s_ = __shfl_sync(gmask, my_s, jj, LPR);
-          const int c_ = __shfl_sync(gmask, my_c, jj, LPR);
-          if (j0 + u < cnt && col_live) {
-            vp[u] = O::load(P + (int64_t)s_ * ld_p + (int64_t)lane * O::W);
-            vq[u] = O::load(Q + (int64_t)c_ * ld_q + (int64_t)lane * O::W);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (j0 + u >= cnt) break;
-          while (base + j0 + u >= cur_end) flush();
-          if (col_live)
-            acc = O::map3(acc, vp[u], vq[u], [](float a, float p, float q_) {
-              return __fadd_rn(a, act_fwd<ACT>(__fadd_rn(p, q_)));
-            });
-        }
-      }
-    }
-    while (cur < nrow) flush();
-  }
-}
-
-template <typename V, int LPR, int ACT>
-__global__ void __launch_bounds__(kThreads)
-csr_cob_bwd_chunked_kernel(const float* __restrict__ G, int64_t ld_g, const float* __restrict__ A, int64_t ld_a,
-                           const float* __restrict__ B, int64_t ld_b, const int32_t* __restrict__ rowptr,
-                           const int32_t* __restrict__ dst, const int32_t* __restrict__ oth, int64_t n_rows, int FV,
-                           float* __restrict__ gA, int64_t ld_ga) {
-  using O = VecOps<V>;
-  constexpr int GPB = kThreads / LPR;
-  constexpr int U = 4;
-  const int lane = threadIdx.x % LPR;
-  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x % 32) / LPR * LPR));
-  const bool col_live = lane < FV;
-  const int64_t n_chunks = (n_rows + LPR - 1) / LPR;
-  for (int64_t chunk = (int64_t)blockIdx.x * GPB + threadIdx.x / LPR; chunk < n_chunks; chunk += (int64_t)gridDim.x * GPB) {
-    const int64_t r0 = chunk * LPR;
-    const int nrow = (int)((n_rows - r0 < LPR) ? n_rows - r0 : LPR);
-    const int my_beg = (lane < nrow) ? __ldg(rowptr + r0 + lane) : 0;
-    const int my_end = (lane < nrow) ? __ldg(rowptr + r0 + lane + 1) : 0;
-    const int m0 = __shfl_sync(gmask, my_beg, 0, LPR);
-    const int m1 = __shfl_sync(gmask, my_end, nrow - 1, LPR);
-    int cur = 0, cur_end = __shfl_sync(gmask, my_end, 0, LPR);      // accumulation cursor
-    int icur = 0, icur_end = cur_end;                               // issue cursor (row of the message being fetched)
-    V acc = O::zero();
-    auto flush = [&]() {
-      if (col_live) O::store(gA + (r0 + cur) * ld_ga + (int64_t)lane * O::W, acc);
-      acc = O::zero();
-      ++cur;
-      cur_end = __shfl_sync(gmask, my_end, cur < LPR ? cur : LPR - 1, LPR);
-    };
-    for (int base = m0; base < m1; base += LPR) {
-      const int cnt = (m1 - base < LPR) ? m1 - base : LPR;
-      const int my_t = (lane < cnt) ? __ldg(dst + base + lane) : 0;
-      const int my_o = (lane < cnt) ? __ldg(oth + base + lane) : 0;
-      for (int j0 = 0; j0 < cnt; j0 += U) {
-        V vg[U], vb[U], va[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int jj = (j0 + u < LPR) ? j0 + u : LPR - 1;
-          const int t_ = __shfl_sync(gmask, my_t, jj, LPR);
-          const int o_ = __shfl_sync(gmask, my_o, jj, LPR);
-          if (j0 + u < cnt) {
-            while (base + j0 + u >= icur_end) {  // the row this message belongs to (its A row is the third operand)
-              ++icur;
-              icur_end = __shfl_sync(gmask, my_end, icur < LPR ? icur : LPR - 1, LPR);
-            }
-            if (col_live) {
-              vg[u] = O::load(G + (int64_t)t_ * ld_g + (int64_t)lane * O::W);
-              vb[u] = O::load(B + (int64_t)o_ * ld_b + (int64_t)lane * O::W);
-              va[u] = O::load(A + (r0 + icur) * ld_a + (int64_t)lane * O::W);  // same row for a run of messages: L1 hit
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (j0 + u >= cnt) break;
-          while (base + j0 + u >= cur_end) flush();
-          if (col_live) {
-            V d = O::map2(va[u], vb[u], [](float x, float y) { return act_bwd<ACT>(__fadd_rn(x, y)); });
-            acc = O::map3(acc, vg[u], d, [](float s_, float g, float d_) { return __fadd_rn(s_, __fmul_rn(g, d_)); });
-          }
-        }
-      }
-    }
-    while (cur < nrow) flush();
-  }
-}
-
 // gA[r] = SUM_i G[dst[i]] * act'(A[r] + B[oth[i]])
 template <typename V, int LPR, int VPL, int ACT>
 __global__ void __launch_bounds__(kThreads)
@@ -638,15 +499,9 @@ extern "C" int cwn_csr_cob_fwd_f32(const float* P, int64_t ld_p, const float* Q,
 #define LAUNCH(VT, VPLV)                                                                                           \
   CWN_DISPATCH_ACT(act, csr_cob_fwd_kernel<VT, LPR, VPLV, ACT><<<grid, kThreads, 0, st>>>(                           \
                             P, ld_p, Q, ld_q, rowptr, src, cob, n_rows, g.fv, x_res, ld_res, eps, out, ld_out))
-  const bool chunked = g.vec && g.vpl == 1 && g.lpr >= 8 && n_rows >= 32768 && !getenv_flag("CWN_B200_GATHER_V1");
-  if (chunked) {
-    const int grid_c = grid_for((n_rows + g.lpr - 1) / g.lpr, g.lpr);
-#define LAUNCH_C(LPRV)                                                                                             \
-    CWN_DISPATCH_ACT(act, csr_cob_fwd_chunked_kernel<float4, LPRV, ACT><<<grid_c, kThreads, 0, st>>>(                  \
-                              P, ld_p, Q, ld_q, rowptr, src, cob, n_rows, g.fv, x_res, ld_res, eps, out, ld_out))
-    if (g.lpr == 8) { LAUNCH_C(8) } else if (g.lpr == 16) { LAUNCH_C(16) } else { LAUNCH_C(32) }
-#undef LAUNCH_C
-  } else if (g.vec) {
+  // (a chunked variant like csr_gather_reduce_chunked_kernel was measured SLOWER for the two-operand passes —
+  //  0.38 vs 0.40 of the HBM peak forward, 0.41 vs 0.53 backward at 1M rows, 80 registers — and was removed)
+  if (g.vec) {
     if (g.vpl == 1) { CWN_DISPATCH_LPR(g.lpr, LAUNCH(float4, 1)) } else { constexpr int LPR = 32; LAUNCH(float4, 2) }
   } else {
     if (g.vpl == 1) { CWN_DISPATCH_LPR(g.lpr, LAUNCH(float, 1)) } else { constexpr int LPR = 32; LAUNCH(float, 2) }
@@ -675,15 +530,7 @@ extern "C" int cwn_csr_cob_bwd_f32(const float* G, int64_t ld_g, const float* A,
 #define LAUNCH(VT, VPLV)                                                                  \
   CWN_DISPATCH_ACT(act, csr_cob_bwd_kernel<VT, LPR, VPLV, ACT><<<grid, kThreads, 0, st>>>(  \
                             G, ld_g, A, ld_a, B, ld_b, rowptr, dst, oth, n_rows, g.fv, gA, ld_ga))
-  const bool chunked = g.vec && g.vpl == 1 && g.lpr >= 8 && n_rows >= 32768 && !getenv_flag("CWN_B200_GATHER_V1");
-  if (chunked) {
-    const int grid_c = grid_for((n_rows + g.lpr - 1) / g.lpr, g.lpr);
-#define LAUNCH_C(LPRV)                                                                         \
-    CWN_DISPATCH_ACT(act, csr_cob_bwd_chunked_kernel<float4, LPRV, ACT><<<grid_c, kThreads, 0, st>>>( \
-                              G, ld_g, A, ld_a, B, ld_b, rowptr, dst, oth, n_rows, g.fv, gA, ld_ga))
-    if (g.lpr == 8) { LAUNCH_C(8) } else if (g.lpr == 16) { LAUNCH_C(16) } else { LAUNCH_C(32) }
-#undef LAUNCH_C
-  } else if (g.vec) {
+  if (g.vec) {
     if (g.vpl == 1) { CWN_DISPATCH_LPR(g.lpr, LAUNCH(float4, 1)) } else { constexpr int LPR = 32; LAUNCH(float4, 2) }
   } else {
     if (g.vpl == 1) { CWN_DISPATCH_LPR(g.lpr, LAUNCH(float, 1)) } else { constexpr int LPR = 32; LAUNCH(float, 2) }

@@ -562,6 +562,7 @@ def test_fused_dense_layer_equals_torch_modules(layer_dim, hidden, act, norm, co
             scale = float(p2[k].grad.abs().max()) + 1e-6
             atol = max(2e-5, 1e-4 * scale)  # (biases feeding a BatchNorm have an analytically zero gradient: pure rounding noise)
             assert_close(p1[k].grad, p2[k].grad, rtol=1e-4, atol=atol, what=f'direct grad {k}')
+    torch_conv.load_state_dict(fused_conv.state_dict())  # (the fused layer has seen one more training step)
     with torch.no_grad():
         for conv in (fused_conv, torch_conv):
             conv.eval()
@@ -635,9 +636,9 @@ def test_embedding_style_gather_backward_uses_split_rows():
 
 
 @pytest.mark.parametrize('act,F', [('relu', 64), ('elu', 32), ('tanh', 128)])
-def test_chunked_cob_kernels_large_row_counts(act, F):
-    """>= 32768 rows select the chunked coboundary kernels (forward, and both gradient passes); checked against
-    torch autograd on the same device (fp32, rtol 1e-5)."""
+def test_cob_kernels_large_row_counts(act, F):
+    """Coboundary pass at 40k rows (forward and both gradient passes, grid-stride regime) against torch autograd on
+    the same device (fp32, rtol 1e-5)."""
     n, n_cob, E = 40_000, 9_000, 150_000
     g = torch.Generator().manual_seed(F)
     idx = torch.stack([torch.randint(0, n, (E,), generator=g), torch.randint(0, n - 50, (E,), generator=g)]).to(DEV)
