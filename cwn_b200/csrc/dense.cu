@@ -20,7 +20,7 @@
 
 namespace cwn {
 
-constexpr int TM = 64;    // rows per tile
+constexpr int TM = 64;    // rows per tile (large problems); small ones use 32-row tiles for twice the CTAs
 constexpr int TN = 64;    // columns per tile
 constexpr int DT = 256;   // threads per CTA (16 x 16, 4x4 outputs each)
 constexpr int LDT = TN + 4;
@@ -62,20 +62,29 @@ __device__ __forceinline__ float act_grad(int act, float v) {  // derivative as 
 
 __host__ __device__ __forceinline__ int round4(int v) { return (v + 3) & ~3; }
 
-// acc[4][4] += A[64 x inner] * B[inner x 64] with A row-major in shared memory (rows = output rows, float4 along the
-// inner dimension) and B inner-major (float4 along the output columns). Thread (ty, tx) owns rows 4ty.., cols 4tx..
+// acc[R][4] += A[(16 R) x inner] * B[inner x 64] with A row-major in shared memory (rows = output rows, float4 along
+// the inner dimension) and B inner-major (float4 along the output columns). Thread (ty, tx) owns rows R*ty.., cols 4tx..
+// The operands of step k+4 are fetched into a second register set before the FMAs of step k are issued: with only a
+// couple of warps per scheduler (these launches are small) the shared-memory latency would otherwise sit exposed.
+template <int R>
 __device__ __forceinline__ void tile_mma(const float* __restrict__ As, int lda, const float* __restrict__ Bs, int ldb,
-                                         int inner4, int ty, int tx, float (&acc)[4][4]) {
-  const float* a0 = As + (ty * 4) * lda;
+                                         int inner4, int ty, int tx, float (&acc)[R][4]) {
+  const float* a0 = As + (ty * R) * lda;
   const float* b0 = Bs + tx * 4;
+  float4 a[R], b[4], an[R], bn[4];
+#pragma unroll
+  for (int i = 0; i < R; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * lda);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) b[q] = *reinterpret_cast<const float4*>(b0 + q * ldb);
   for (int k = 0; k < inner4; k += 4) {
-    float4 a[4], b[4];
+    if (k + 4 < inner4) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * lda + k);
+      for (int i = 0; i < R; ++i) an[i] = *reinterpret_cast<const float4*>(a0 + i * lda + k + 4);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) b[q] = *reinterpret_cast<const float4*>(b0 + (k + q) * ldb);
+      for (int q = 0; q < 4; ++q) bn[q] = *reinterpret_cast<const float4*>(b0 + (k + 4 + q) * ldb);
+    }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < R; ++i) {
       const float av[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -85,6 +94,10 @@ __device__ __forceinline__ void tile_mma(const float* __restrict__ As, int lda, 
         acc[i][3] = fmaf(av[q], b[q].w, acc[i][3]);
       }
     }
+#pragma unroll
+    for (int i = 0; i < R; ++i) a[i] = an[i];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) b[q] = bn[q];
   }
 }
 
@@ -115,14 +128,14 @@ __device__ __forceinline__ bool input_vec_ok(const D& d) {
 // 128-bit loads when the layout allows; (r, column) advance incrementally so there is one division per thread.
 template <class D>
 __device__ __forceinline__ void load_input_tile(const D& d, const float* vin, int K, int K4, int64_t row0, int rows,
-                                                int kc, int width, float* dst, int ldd, bool vec) {
+                                                int kc, int width, float* dst, int ldd, bool vec, int tile_rows) {
   const int act = d.in_act;
   if (vec) {
     const int nc4 = width / 4;  // width is a multiple of 4
     int r = threadIdx.x / nc4, c4 = threadIdx.x % nc4;
     const int dr = DT / nc4, dc = DT % nc4;
 #pragma unroll 4
-    while (r < TM) {
+    while (r < tile_rows) {
       const int k = kc + c4 * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < rows && k < K) {
@@ -139,7 +152,7 @@ __device__ __forceinline__ void load_input_tile(const D& d, const float* vin, in
       if (c4 >= nc4) { c4 -= nc4; ++r; }
     }
   } else {
-    for (int i = threadIdx.x; i < TM * width; i += DT) {
+    for (int i = threadIdx.x; i < tile_rows * width; i += DT) {
       const int r = i / width, kk = i % width, k = kc + kk;
       float v = 0.f;
       if (r < rows && k < K) {
@@ -170,7 +183,8 @@ constexpr int kStageFloats = 8192;  // 32 KB of per-tile partials staged in shar
 __device__ __forceinline__ void bn_finalize_body(const float* stats, int n_tiles, int64_t n_rows, int h, const float* gamma,
                                                  float eps, float momentum, int training, float* running_mean,
                                                  float* running_var, int64_t* nbt, float* mean_out, float* scale_out,
-                                                 float* rstd_out, float* stage, int stage_floats = kStageFloats) {
+                                                 float* rstd_out, float* stage, int stage_floats = kStageFloats,
+                                                 int tile_rows = TM) {
   if (training) {
     // Chan's parallel-variance merge, tiles in order (deterministic). The partials are pulled into shared memory with
     // coalesced loads first: the merge itself is a dependent chain per column.
@@ -185,8 +199,8 @@ __device__ __forceinline__ void bn_finalize_body(const float* stats, int n_tiles
       if (threadIdx.x < h) {
         const int c = threadIdx.x;
         for (int t = 0; t < nt; ++t) {
-          const int64_t left = n_rows - (int64_t)(t0 + t) * TM;
-          const float cnt = (float)(left < TM ? left : TM);
+          const int64_t left = n_rows - (int64_t)(t0 + t) * tile_rows;
+          const float cnt = (float)(left < tile_rows ? left : tile_rows);
           const float mt = stage[t * per_tile + c], m2t = stage[t * per_tile + h + c];
           const float delta = mt - mean, tot = n + cnt;
           mean += delta * (cnt / tot);
@@ -220,7 +234,10 @@ __device__ __forceinline__ void bn_finalize_body(const float* stats, int n_tiles
 }
 
 // ------------------------------------------------------------------------------------------------ forward unit
-__global__ void __launch_bounds__(DT) linear_fwd_kernel(const __grid_constant__ Group<cwn_linear_desc> g) {
+template <int TR>  // tile rows: 64 or 32
+__global__ void __launch_bounds__(DT, 3) linear_fwd_kernel(const __grid_constant__ Group<cwn_linear_desc> g) {
+  constexpr int TM = TR;
+  constexpr int R = TR / 16;
   extern __shared__ __align__(16) float smem[];
   const int p = find_problem(g, blockIdx.x);
   const cwn_linear_desc& d = g.d[p];
@@ -255,21 +272,21 @@ __global__ void __launch_bounds__(DT) linear_fwd_kernel(const __grid_constant__ 
     }
   }
   __syncthreads();  // vin ready
-  load_input_tile(d, vin, K, K4, row0, rows, 0, K4, As, lda, input_vec_ok(d));
+  load_input_tile(d, vin, K, K4, row0, rows, 0, K4, As, lda, input_vec_ok(d), TM);
   __syncthreads();
-  float acc[4][4] = {};
-  tile_mma(As, lda, Bs, LDT, K4, ty, tx, acc);
+  float acc[R][4] = {};
+  tile_mma<R>(As, lda, Bs, LDT, K4, ty, tx, acc);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int c = col0 + tx * 4 + j;
     const float b = (d.bias && c < d.h) ? __ldg(d.bias + c) : 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[i][j] += b;
+    for (int i = 0; i < R; ++i) acc[i][j] += b;
   }
   const bool zvec = ((reinterpret_cast<uintptr_t>(d.z) & 15u) == 0) && (d.ld_z % 4 == 0) && (col0 + tx * 4 + 3 < d.h);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = ty * 4 + i;
+  for (int i = 0; i < R; ++i) {
+    const int r = ty * R + i;
     if (r >= rows) continue;
     float* zrow = d.z + (row0 + r) * d.ld_z + col0 + tx * 4;
     if (zvec) {
@@ -290,8 +307,8 @@ __global__ void __launch_bounds__(DT) linear_fwd_kernel(const __grid_constant__ 
   float* Ys = smem;              // [TM][LDT]
   float* red = smem + TM * LDT;  // [4][TN]
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    *reinterpret_cast<float4*>(Ys + (ty * 4 + i) * LDT + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  for (int i = 0; i < R; ++i)
+    *reinterpret_cast<float4*>(Ys + (ty * R + i) * LDT + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
   __syncthreads();
   // per-column (mean, M2) of this tile: 4 row groups per column, combined in a fixed order
   const int c = tid & (TN - 1), part = tid >> 6;
@@ -318,7 +335,7 @@ __global__ void __launch_bounds__(DT) linear_fwd_kernel(const __grid_constant__ 
       const int n_tiles = (int)((d.n_rows + TM - 1) / TM);
       bn_finalize_body(d.stats, n_tiles, d.n_rows, d.h, d.bn_gamma, d.bn_eps, d.bn_momentum, 1, d.bn_running_mean,
                        d.bn_running_var, d.bn_num_batches_tracked, d.bn_mean, d.bn_scale, d.bn_rstd, smem,
-                       TM * lda + K4 * LDT);  // this problem's share of the dynamic shared memory
+                       TM * lda + K4 * LDT, TM);  // (this problem's share of the dynamic shared memory)
       if (threadIdx.x == 0) *d.counter = 0;
     }
   }
@@ -329,7 +346,8 @@ __global__ void __launch_bounds__(DT) bn_finalize_kernel(const __grid_constant__
   __shared__ float stage[kStageFloats];
   const cwn_bn_desc& d = g.d[blockIdx.x];
   bn_finalize_body(d.stats, d.n_tiles, d.n_rows, d.h, d.gamma, d.eps, d.momentum, d.training, d.running_mean,
-                   d.running_var, d.num_batches_tracked, d.mean, d.scale, d.rstd, stage);
+                   d.running_var, d.num_batches_tracked, d.mean, d.scale, d.rstd, stage, kStageFloats,
+                   d.tile_rows > 0 ? d.tile_rows : TM);
 }
 
 __global__ void __launch_bounds__(DT) bn_act_kernel(const __grid_constant__ Group<cwn_bn_act_desc> g) {
@@ -361,8 +379,8 @@ __device__ __forceinline__ void unit_gy(const cwn_unit_bwd_desc& d, int64_t row,
   }
 }
 
-__device__ __forceinline__ void unit_bwd_finalize_body(const cwn_unit_bwd_desc& d, float* stage) {
-  const int n_tiles = (int)((d.n_rows + TM - 1) / TM);
+__device__ __forceinline__ void unit_bwd_finalize_body(const cwn_unit_bwd_desc& d, float* stage, int tile_rows) {
+  const int n_tiles = (int)((d.n_rows + tile_rows - 1) / tile_rows);
   const int per_tile = 2 * d.h;
   const int chunk = kStageFloats / per_tile > 0 ? kStageFloats / per_tile : 1;
   float s1 = 0.f, s2 = 0.f;  // column threadIdx.x
@@ -386,7 +404,9 @@ __device__ __forceinline__ void unit_bwd_finalize_body(const cwn_unit_bwd_desc& 
   }
 }
 
+template <int TR>
 __global__ void __launch_bounds__(DT) unit_bwd_reduce_kernel(const __grid_constant__ Group<cwn_unit_bwd_desc> g) {
+  constexpr int TM = TR;
   __shared__ float part[2][4][TN];
   const int p = find_problem(g, blockIdx.x);
   const cwn_unit_bwd_desc& d = g.d[p];
@@ -422,7 +442,7 @@ __global__ void __launch_bounds__(DT) unit_bwd_reduce_kernel(const __grid_consta
   if (d.counter) {
     __shared__ float stage[kStageFloats];
     if (last_cta_of_problem(d.counter, g.start[p + 1] - g.start[p])) {
-      unit_bwd_finalize_body(d, stage);
+      unit_bwd_finalize_body(d, stage, TM);
       if (threadIdx.x == 0) *d.counter = 0;
     }
   }
@@ -432,21 +452,25 @@ __global__ void __launch_bounds__(DT) unit_bwd_finalize_kernel(const __grid_cons
   __shared__ float stage[kStageFloats];
   const cwn_unit_bwd_desc& d = g.d[blockIdx.x];
   if (!d.has_bn) return;
-  unit_bwd_finalize_body(d, stage);
+  unit_bwd_finalize_body(d, stage, d.tile_rows > 0 ? d.tile_rows : TM);
 }
 
 // g_z tile -> input gradient (g_z W) and per-CTA partial weight gradient (g_z^T f_in(X)); CTA j of a problem strides
 // over the row tiles j, j + n_ctas, ... and owns slab j of the partial buffers (plain read-modify-write, no atomics).
-__global__ void __launch_bounds__(DT) unit_bwd_kernel(const __grid_constant__ Group<cwn_unit_bwd_desc> g) {
+template <int TR>
+__global__ void __launch_bounds__(DT, 2) unit_bwd_kernel(const __grid_constant__ Group<cwn_unit_bwd_desc> g) {
+  constexpr int TM = TR;          // rows per tile
+  constexpr int R = TR / 16;      // rows per thread of the input-gradient tile
+  constexpr int LDR = TR + 4;     // leading dimension of g_z^T (inner dimension = rows)
   extern __shared__ __align__(16) float smem[];
   const int p = find_problem(g, blockIdx.x);
   const cwn_unit_bwd_desc& d = g.d[p];
   const int j = blockIdx.x - g.start[p];
   const int K = d.k0 + d.k1, K4 = round4(K), H4 = round4(d.h), ldg = H4 + 4;
-  const int m_tiles = (d.h + TM - 1) / TM;
+  const int m_tiles = (d.h + 63) / 64;
   float* Gz = smem;                        // [TM][ldg]            g_z[r][c]
-  float* GzT = Gz + TM * ldg;              // [m_tiles*TM][LDT]    g_z^T[c][r]
-  float* Ain = GzT + m_tiles * TM * LDT;   // [TM][LDT]            f_in(X)[r][k chunk]
+  float* GzT = Gz + TM * ldg;              // [m_tiles*64][LDR]    g_z^T[c][r]
+  float* Ain = GzT + m_tiles * 64 * LDR;   // [TM][LDT]            f_in(X)[r][k chunk]
   float* Ws = Ain + TM * LDT;              // [H4][LDT]            W[c][k chunk]
   float* vin = Ws + H4 * LDT;              // [3][K4]              input transform
   float* vout = vin + 3 * K4;              // [6][H4]              mean, scale, rstd, beta, c1, c2 of this unit
@@ -469,7 +493,7 @@ __global__ void __launch_bounds__(DT) unit_bwd_kernel(const __grid_constant__ Gr
     vout[4 * H4 + c] = live ? d.c1[c] : 0.f;
     vout[5 * H4 + c] = live ? d.c2[c] : 0.f;
   }
-  for (int i = tid; i < m_tiles * TM * LDT; i += DT) GzT[i] = 0.f;  // rows c >= h stay zero for good
+  for (int i = tid; i < m_tiles * 64 * LDR; i += DT) GzT[i] = 0.f;  // rows c >= h stay zero for good
   bool first = true;
   for (int tile = j; tile < n_tiles; tile += d.n_ctas, first = false) {
     const int64_t row0 = (int64_t)tile * TM;
@@ -517,7 +541,7 @@ __global__ void __launch_bounds__(DT) unit_bwd_kernel(const __grid_constant__ Gr
     __syncthreads();
     {  // transpose into GzT (lanes along r: conflict-free stores) and the bias-gradient partial (column sums)
       const int r = tid & (TM - 1);
-      for (int c = tid >> 6; c < d.h; c += DT / TM) GzT[c * LDT + r] = Gz[r * ldg + c];
+      for (int c = tid / TM; c < d.h; c += DT / TM) GzT[c * LDR + r] = Gz[r * ldg + c];
       for (int c = tid; c < d.h; c += DT) {
         float s_ = 0.f;
         for (int rr = 0; rr < rows; ++rr) s_ += Gz[rr * ldg + c];
@@ -538,14 +562,14 @@ __global__ void __launch_bounds__(DT) unit_bwd_kernel(const __grid_constant__ Gr
           Ws[c * LDT + k] = (c < d.h && kc + k < K) ? __ldg(d.w + (int64_t)c * d.ld_w + kc + k) : 0.f;
         }
       }
-      load_input_tile(d, vin, K, K4, row0, rows, kc, TN, Ain, LDT, in_vec);
+      load_input_tile(d, vin, K, K4, row0, rows, kc, TN, Ain, LDT, in_vec, TM);
       __syncthreads();
-      if (d.g_in0 || d.g_in1) {  // input gradient chunk: [64 rows] x [64 k] = Gz [64 x h] * Ws [h x 64]
-        float acc[4][4] = {};
-        tile_mma(Gz, ldg, Ws, LDT, H4, ty, tx, acc);
+      if (d.g_in0 || d.g_in1) {  // input gradient chunk: [TM rows] x [64 k] = Gz [TM x h] * Ws [h x 64]
+        float acc[R][4] = {};
+        tile_mma<R>(Gz, ldg, Ws, LDT, H4, ty, tx, acc);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = ty * 4 + i;
+        for (int i = 0; i < R; ++i) {
+          const int r = ty * R + i;
           if (r >= rows) continue;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -556,12 +580,12 @@ __global__ void __launch_bounds__(DT) unit_bwd_kernel(const __grid_constant__ Gr
           }
         }
       }
-      for (int mt = 0; mt < m_tiles; ++mt) {  // weight gradient chunk: [64 c] x [64 k] = GzT [64 x rows] * Ain [rows x 64]
+      for (int mt = 0; mt < m_tiles; ++mt) {  // weight gradient chunk: [64 c] x [64 k] = GzT [64 x TM] * Ain [TM x 64]
         float acc[4][4] = {};
-        tile_mma(GzT + mt * TM * LDT, LDT, Ain, LDT, TM, ty, tx, acc);
+        tile_mma<4>(GzT + mt * 64 * LDR, LDR, Ain, LDT, TM, ty, tx, acc);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int c = mt * TM + ty * 4 + i;
+          const int c = mt * 64 + ty * 4 + i;
           if (c >= d.h) continue;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -603,6 +627,16 @@ static int ensure_smem(Kernel kernel, size_t bytes, const char* what) {
   return cuda_status(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), what);
 }
 
+// tile rows of a group: every problem must agree (0 means 64)
+template <class D>
+static int group_tile_rows(const D* descs, int n, int& tr) {
+  tr = descs[0].tile_rows > 0 ? descs[0].tile_rows : 64;
+  if (tr != 64 && tr != 32) return fail(CWN_E_SHAPE, "tile_rows must be 64 or 32");
+  for (int i = 1; i < n; ++i)
+    if ((descs[i].tile_rows > 0 ? descs[i].tile_rows : 64) != tr) return fail(CWN_E_SHAPE, "tile_rows differs inside a group");
+  return CWN_OK;
+}
+
 static int check_group(const void* descs, int n, const char* what) {
   if (n < 0 || n > CWN_MAX_GROUP) return fail(CWN_E_SHAPE, what);
   if (n > 0 && !descs) return fail(CWN_E_NULL, what);
@@ -616,10 +650,12 @@ using namespace cwn;
 extern "C" int cwn_linear_fwd_grouped(const cwn_linear_desc* descs, int32_t n, cwn_stream_t stream) {
   int rc = check_group(descs, n, "cwn_linear_fwd_grouped");
   if (rc || n == 0) return rc;
+  int tr;
+  if ((rc = group_tile_rows(descs, n, tr))) return rc;
   Group<cwn_linear_desc> g;
   g.n = n;
   int total = 0;
-  size_t smem = ((size_t)TM * LDT + 4 * TN) * sizeof(float);
+  size_t smem = ((size_t)tr * LDT + 4 * TN) * sizeof(float);
   for (int i = 0; i < n; ++i) {
     const cwn_linear_desc& d = descs[i];
     if (d.n_rows < 0 || d.h <= 0 || d.k0 <= 0 || d.k1 < 0 || d.n_rows > (int64_t)INT32_MAX * TM)
@@ -627,15 +663,20 @@ extern "C" int cwn_linear_fwd_grouped(const cwn_linear_desc* descs, int32_t n, c
     if (d.n_rows > 0 && (!d.x0 || !d.w || !d.z || (d.k1 > 0 && !d.x1))) return fail(CWN_E_NULL, "cwn_linear_fwd_grouped: operand");
     g.d[i] = d;
     g.start[i] = total;
-    total += (int)((d.n_rows + TM - 1) / TM) * ((d.h + TN - 1) / TN);
+    total += (int)((d.n_rows + tr - 1) / tr) * ((d.h + TN - 1) / TN);
     const int K4 = round4(d.k0 + d.k1);
-    const size_t need = ((size_t)TM * (K4 + 4) + (size_t)K4 * LDT + 3 * (size_t)K4) * sizeof(float);
+    const size_t need = ((size_t)tr * (K4 + 4) + (size_t)K4 * LDT + 3 * (size_t)K4) * sizeof(float);
     if (need > smem) smem = need;
   }
   g.start[n] = total;
   if (total == 0) return CWN_OK;
-  if ((rc = ensure_smem(linear_fwd_kernel, smem, "cudaFuncSetAttribute(linear_fwd_kernel)"))) return rc;
-  linear_fwd_kernel<<<total, DT, smem, (cudaStream_t)stream>>>(g);
+  if (tr == 64) {
+    if ((rc = ensure_smem(linear_fwd_kernel<64>, smem, "cudaFuncSetAttribute(linear_fwd_kernel)"))) return rc;
+    linear_fwd_kernel<64><<<total, DT, smem, (cudaStream_t)stream>>>(g);
+  } else {
+    if ((rc = ensure_smem(linear_fwd_kernel<32>, smem, "cudaFuncSetAttribute(linear_fwd_kernel)"))) return rc;
+    linear_fwd_kernel<32><<<total, DT, smem, (cudaStream_t)stream>>>(g);
+  }
   return launched("linear_fwd_kernel");
 }
 
@@ -694,14 +735,17 @@ extern "C" int cwn_unit_bwd_reduce_grouped(const cwn_unit_bwd_desc* descs, int32
   Group<cwn_unit_bwd_desc> g;
   int rc = load_bwd_group(descs, n, g, "cwn_unit_bwd_reduce_grouped");
   if (rc || n == 0) return rc;
+  int tr;
+  if ((rc = group_tile_rows(descs, n, tr))) return rc;
   int total = 0;
   for (int i = 0; i < n; ++i) {
     g.start[i] = total;
-    if (g.d[i].has_bn) total += (int)((g.d[i].n_rows + TM - 1) / TM);
+    if (g.d[i].has_bn) total += (int)((g.d[i].n_rows + tr - 1) / tr);
   }
   g.start[n] = total;
   if (total == 0) return CWN_OK;
-  unit_bwd_reduce_kernel<<<total, DT, 0, (cudaStream_t)stream>>>(g);
+  if (tr == 64) unit_bwd_reduce_kernel<64><<<total, DT, 0, (cudaStream_t)stream>>>(g);
+  else unit_bwd_reduce_kernel<32><<<total, DT, 0, (cudaStream_t)stream>>>(g);
   return launched("unit_bwd_reduce_kernel");
 }
 
@@ -718,24 +762,31 @@ extern "C" int cwn_unit_bwd_grouped(const cwn_unit_bwd_desc* descs, int32_t n, c
   Group<cwn_unit_bwd_desc> g;
   int rc = load_bwd_group(descs, n, g, "cwn_unit_bwd_grouped");
   if (rc || n == 0) return rc;
+  int tr;
+  if ((rc = group_tile_rows(descs, n, tr))) return rc;
   int total = 0;
   size_t smem = 0;
   for (int i = 0; i < n; ++i) {
     const cwn_unit_bwd_desc& d = g.d[i];
-    const int n_tiles = (int)((d.n_rows + TM - 1) / TM);
+    const int n_tiles = (int)((d.n_rows + tr - 1) / tr);
     if (d.n_ctas > n_tiles || (n_tiles > 0 && d.n_ctas == 0)) return fail(CWN_E_SHAPE, "cwn_unit_bwd_grouped: n_ctas must be in [1, row tiles]");
     if (d.n_rows > 0 && (!d.w_partials || !d.b_partials)) return fail(CWN_E_NULL, "cwn_unit_bwd_grouped: partial buffers");
     g.start[i] = total;
     total += d.n_ctas;
-    const int H4 = round4(d.h), m_tiles = (d.h + TM - 1) / TM, K4 = round4(d.k0 + d.k1);
-    const size_t need = ((size_t)TM * (H4 + 4) + (size_t)m_tiles * TM * LDT + (size_t)TM * LDT + (size_t)H4 * LDT +
+    const int H4 = round4(d.h), m_tiles = (d.h + 63) / 64, K4 = round4(d.k0 + d.k1);
+    const size_t need = ((size_t)tr * (H4 + 4) + (size_t)m_tiles * 64 * (tr + 4) + (size_t)tr * LDT + (size_t)H4 * LDT +
                          3 * (size_t)K4 + 6 * (size_t)H4) * sizeof(float);
     if (need > smem) smem = need;
   }
   g.start[n] = total;
   if (total == 0) return CWN_OK;
-  if ((rc = ensure_smem(unit_bwd_kernel, smem, "cudaFuncSetAttribute(unit_bwd_kernel)"))) return rc;
-  unit_bwd_kernel<<<total, DT, smem, (cudaStream_t)stream>>>(g);
+  if (tr == 64) {
+    if ((rc = ensure_smem(unit_bwd_kernel<64>, smem, "cudaFuncSetAttribute(unit_bwd_kernel)"))) return rc;
+    unit_bwd_kernel<64><<<total, DT, smem, (cudaStream_t)stream>>>(g);
+  } else {
+    if ((rc = ensure_smem(unit_bwd_kernel<32>, smem, "cudaFuncSetAttribute(unit_bwd_kernel)"))) return rc;
+    unit_bwd_kernel<32><<<total, DT, smem, (cudaStream_t)stream>>>(g);
+  }
   return launched("unit_bwd_kernel");
 }
 

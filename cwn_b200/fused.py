@@ -24,7 +24,13 @@ from torch.nn import BatchNorm1d, Identity, Linear, Sequential
 from cwn_b200 import _lib, ops
 from cwn_b200.mp.nn import activation_name
 
-TM = 64  # row tile of csrc/dense.cu
+TM = 64  # default row tile of csrc/dense.cu
+
+
+def _tile_rows(row_counts):
+    """Rows per CTA tile for one grouped launch: 32 when 64-row tiles would leave most of the 148 SMs with at most
+    one CTA (the real-data regime: these launches are latency-bound, twice the CTAs = half the per-CTA chain)."""
+    return 32 if sum((n + 63) // 64 for n in row_counts) < 2 * 148 else 64
 
 
 class _Unit(object):
@@ -193,9 +199,10 @@ class FusedSparseCINDense(Function):
             def run_units(sts):
                 lin, alive = [], []  # `alive`: descriptors hold raw pointers only — keep the scratch tensors referenced
                 counters = _counters(dev, len(sts))
+                tr = _tile_rows([st.n for st in sts])
                 for i, st in enumerate(sts):
                     unit = st.unit
-                    n_tiles = (st.n + TM - 1) // TM
+                    n_tiles = (st.n + tr - 1) // tr
                     stats = None
                     bn_fields = (None, 0.0, 0.0, 0, None, None, None, None, None, None, None)
                     if unit.bn is not None:
@@ -214,7 +221,7 @@ class FusedSparseCINDense(Function):
                         _p(st.x0), st.x0.stride(0), st.x0.size(1), _p(st.x1), st.x1.stride(0) if st.x1 is not None else 0,
                         st.x1.size(1) if st.x1 is not None else 0, _p(i0[0]), _p(i0[1]), _p(i0[2]), _p(i1[0]), _p(i1[1]),
                         _p(i1[2]), ops.ACT_CODES[st.in_act], _p(unit.lin.weight), unit.lin.weight.stride(0),
-                        _p(unit.lin.bias), _p(st.z), st.h, _p(stats), st.n, st.h, *bn_fields))
+                        _p(unit.lin.bias), _p(st.z), st.h, _p(stats), st.n, st.h, *bn_fields, tr))
                 _launch('cwn_linear_fwd_grouped', _lib.LinearDesc, lin)
 
             l1, l2, l3 = [], [], []
@@ -267,12 +274,13 @@ class FusedSparseCINDense(Function):
             """items: list of (state, g_out, want_g_in0, want_g_in1) -> (descs, list of (g_in0, g_in1))"""
             descs, gins = [], []
             counters = _counters(dev, len(items))
+            tr = _tile_rows([it[0].n for it in items])
             for i, (st, g, want0, want1) in enumerate(items):
                 unit = st.unit
                 k0 = st.x0.size(1)
                 k1 = st.x1.size(1) if st.x1 is not None else 0
-                n_tiles = (st.n + TM - 1) // TM
-                n_ctas = min(n_tiles, 148)
+                n_tiles = (st.n + tr - 1) // tr
+                n_ctas = min(n_tiles, 2 * 148)
                 has_bn = unit.bn is not None
                 g = g.contiguous()
                 gi0 = new(st.n, k0) if want0 else None
@@ -302,7 +310,7 @@ class FusedSparseCINDense(Function):
                     _p(unit.bn.bias) if has_bn else None, _p(g), g.stride(0), _p(red), _p(c1), _p(c2), _p(gg),
                     _p(gbeta), acc_a, _p(gi0), k0, _p(gi1), k1, _p(new(max(n_ctas, 1) * st.h * (k0 + k1))),
                     _p(new(max(n_ctas, 1) * st.h)), n_ctas, _p(gw), gw.stride(0), _p(gb), acc_w, st.n, st.h,
-                    counters[i:i + 1].data_ptr() if has_bn else None))
+                    counters[i:i + 1].data_ptr() if has_bn else None, tr))
                 keep.append(g)
                 gins.append((gi0, gi1))
             return descs, gins
@@ -382,6 +390,7 @@ class GroupedLinear(Function):
         dev = xs[0].device
         ys, descs = [], []
         with torch.cuda.device(dev):
+            tr = _tile_rows([x.size(0) for x in xs])
             for x, (wi, off, bi) in zip(xs, spec):
                 w = weights[wi]
                 b = biases[bi] if bi >= 0 else None
@@ -389,7 +398,7 @@ class GroupedLinear(Function):
                 descs.append(_lib.LinearDesc(_p(x), x.stride(0), x.size(1), None, 0, 0, None, None, None, None, None,
                                              None, 0, w.data_ptr() + 4 * off, w.stride(0), _p(b), _p(y), y.size(1), None,
                                              x.size(0), w.size(0), None, 0.0, 0.0, 0, None, None, None, None, None, None,
-                                             None))
+                                             None, tr))
                 ys.append(y)
             _launch('cwn_linear_fwd_grouped', _lib.LinearDesc, descs)
         ctx.spec, ctx.n_weights, ctx.n_biases = spec, n_weights, len(biases)
@@ -424,12 +433,13 @@ class GroupedLinear(Function):
                     buf = torch.empty_like(prm)
                     gb_bufs.append(buf), gb_out.append(buf), acc_b.append(0)
             gxs, descs, keep = [], [], []
+            tr = _tile_rows([x.size(0) for x in xs])
             for i, (x, g, (wi, off, bi)) in enumerate(zip(xs, gs, spec)):
                 w = weights[wi]
                 nr, k, h = x.size(0), x.size(1), w.size(0)
                 g = (g if g is not None else torch.zeros(nr, h, device=dev)).contiguous()
-                n_tiles = (nr + TM - 1) // TM
-                n_ctas = min(n_tiles, 148)
+                n_tiles = (nr + tr - 1) // tr
+                n_ctas = min(n_tiles, 2 * 148)
                 gx = torch.empty(nr, k, dtype=torch.float32, device=dev) if ctx.needs_input_grad[2 + i] else None
                 wp = torch.empty(max(n_ctas, 1) * h * k, dtype=torch.float32, device=dev)
                 bp = torch.empty(max(n_ctas, 1) * h, dtype=torch.float32, device=dev)
@@ -444,7 +454,7 @@ class GroupedLinear(Function):
                     _p(x), x.stride(0), k, None, 0, 0, None, None, None, None, None, None, 0,
                     w.data_ptr() + 4 * off, w.stride(0), _p(g), g.stride(0), 0, 0, None, None, None, None, _p(g),
                     g.stride(0), None, None, None, None, None, 0, _p(gx), k, None, 0, _p(wp), _p(bp), n_ctas,
-                    gw_bufs[wi].data_ptr() + 4 * off, gw_bufs[wi].stride(0), _p(gb), accumulate, nr, h, None))
+                    gw_bufs[wi].data_ptr() + 4 * off, gw_bufs[wi].stride(0), _p(gb), accumulate, nr, h, None, tr))
                 gxs.append(gx)
             _launch('cwn_unit_bwd_grouped', _lib.UnitBwdDesc, descs)
             _launch('cwn_wgrad_finalize_grouped', _lib.UnitBwdDesc, descs)

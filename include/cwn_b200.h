@@ -157,6 +157,8 @@ typedef struct {
   float* bn_running_mean; float* bn_running_var; int64_t* bn_num_batches_tracked;
   float* bn_mean; float* bn_scale; float* bn_rstd;
   int32_t* counter;
+  int32_t tile_rows;   /* 64 or 32 (0 = 64): rows per CTA tile = granularity of `stats`; the same for a whole group.
+                        * 32 doubles the CTA count of small problems (latency-bound launches) */
 } cwn_linear_desc;
 int cwn_linear_fwd_grouped(const cwn_linear_desc* descs, int32_t n, cwn_stream_t stream);
 
@@ -168,6 +170,7 @@ typedef struct {
   const float* gamma; const float* beta; float eps; float momentum; int32_t training;
   float* running_mean; float* running_var; int64_t* num_batches_tracked;
   float* mean; float* scale; float* rstd;
+  int32_t tile_rows;   /* rows per tile of `stats` (0 = 64) */
 } cwn_bn_desc;
 int cwn_bn_finalize_grouped(const cwn_bn_desc* descs, int32_t n, cwn_stream_t stream);
 
@@ -208,6 +211,7 @@ typedef struct {
   float* g_w; int64_t ld_gw; float* g_b; int32_t accumulate_w;
   int64_t n_rows; int32_t h;
   int32_t* counter;      /* nullable: zero int32; if set, the last CTA of cwn_unit_bwd_reduce_grouped performs step 2 */
+  int32_t tile_rows;     /* 64 or 32 (0 = 64), same for a whole group; sizes red_partials and bounds n_ctas */
 } cwn_unit_bwd_desc;
 int cwn_unit_bwd_reduce_grouped(const cwn_unit_bwd_desc* descs, int32_t n, cwn_stream_t stream);
 int cwn_unit_bwd_finalize_grouped(const cwn_unit_bwd_desc* descs, int32_t n, cwn_stream_t stream);
