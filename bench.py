@@ -411,14 +411,16 @@ def run_cwn(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = cells * world / (float(t.item()) / args.steps / 1e3)
 
-    if rank != 0:
-        return
-    # ---- per-kernel roofline of the step (instrumented re-run of the same steps)
+    # ---- per-kernel roofline of the step (instrumented eager re-run of the same steps; every rank takes part because
+    #      the step contains the gradient all-reduce)
     with ops.KernelProfile() as prof:
         for i in range(args.steps):
             flush.zero_()
             eager_resident_step(i)
     summary = prof.summary()
+    barrier()
+    if rank != 0:
+        return
     peak, peak_src = peaks()
     dom = max((k for k in summary if k != 'csr_plan_build'), key=lambda k: summary[k]['ms'])
     rec = summary[dom]
@@ -463,6 +465,9 @@ def make_host_copy(batch):
 
 def main():
     args = parse()
+    if os.environ.get('CWN_BENCH_WATCHDOG'):  # dump every thread's stack if the run is still alive after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ['CWN_BENCH_WATCHDOG']), exit=True)
     from cwn_b200.dist import init_from_env
     if args.impl == 'reference':
         rank = int(os.environ.get('RANK', '0'))

@@ -69,12 +69,13 @@ class CapturedStep(object):
                 self._body()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        # thread_local: other threads (NCCL's watchdog under data parallelism) keep making CUDA calls during capture
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, capture_error_mode='thread_local'):
             self.loss = self._body()
         if self.optimizer is not None and not self.optimizer_in_graph:
             self.opt_graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.opt_graph):
+            with torch.cuda.graph(self.opt_graph, capture_error_mode='thread_local'):
                 self.optimizer.step()
         self.bucket.zero()  # gradients accumulated by the warm-up / capture passes must not leak into step 1
         return self
