@@ -16,6 +16,7 @@ single cell — where torch's BatchNorm raises) makes `recognise()` / `applicabl
 layer runs through its torch modules instead.
 """
 import ctypes
+import os
 
 import torch
 from torch.autograd import Function
@@ -30,7 +31,12 @@ TM = 64  # default row tile of csrc/dense.cu
 def _tile_rows(row_counts):
     """Rows per CTA tile for one grouped launch: 32 when 64-row tiles would leave most of the 148 SMs with at most
     one CTA (the real-data regime: these launches are latency-bound, twice the CTAs = half the per-CTA chain)."""
+    if _FORCED_TILE_ROWS:
+        return _FORCED_TILE_ROWS
     return 32 if sum((n + 63) // 64 for n in row_counts) < 2 * 148 else 64
+
+
+_FORCED_TILE_ROWS = int(os.environ.get('CWN_B200_TILE_ROWS', '0'))  # A/B switch for profiling (32 or 64)
 
 
 class _Unit(object):

@@ -244,12 +244,17 @@ class SparseCINCochainConv(CochainMessagePassing):
             fx = x.size(1)
             up_branch.split_linear = [(x, form[1].weight, 0, None), (up_attr.source, form[1].weight, fx, form[1].bias)]
 
+        eps_b = self._boundary_eps()
+
         def boundary_branch():  # the pass only runs when boundary features exist (reference mp/cell_mp.py:381)
             if b_attr is not None:
-                return ops.gather_scatter(as_tensor(b_attr), b_index, n, 'add', x_res=x, eps=self.eps2)
-            return (1 + self.eps2) * x
+                return ops.gather_scatter(as_tensor(b_attr), b_index, n, 'add', x_res=x, eps=eps_b)
+            return (1 + eps_b) * x
 
         return up_branch, boundary_branch
+
+    def _boundary_eps(self):
+        return self.eps2
 
     def dense_tail(self, agg_up, agg_boundaries):
         """update nets + combine on the aggregated (residual included) messages, through the torch modules."""
@@ -360,6 +365,108 @@ class SparseCINConv(_PerDimension):
                 dim, up_msg_size, down_msg_size, boundary_msg_size=boundary_msg_size, msg_up_nn=msg_up_nn,
                 msg_boundaries_nn=msg_boundaries_nn, update_up_nn=update_up_nn,
                 update_boundaries_nn=update_boundaries_nn, combine_nn=combine_nn, eps=eps, train_eps=train_eps))
+
+
+# ----------------------------------------------------------------------------------------------- CIN++
+class CINppCochainConv(SparseCINCochainConv):
+    """CIN++ cochain layer (reference `mp/layers.py:216-260`): a third update branch for lower-adjacent messages and a
+    combine over three branches. As in the reference, the layer is built with `use_down_msg=False` (it goes through
+    SparseCINCochainConv's constructor, `:223-226`, `:167-168`) and its models never request lower adjacencies
+    (`include_down_features=False`), so the "down" branch sees `(1 + eps2) * x` only — that behaviour is kept.
+    Residual epsilons: up = eps1, down = eps2, boundaries = eps3 (`:250-252`)."""
+
+    def __init__(self, dim: int, up_msg_size: int, down_msg_size: int, boundary_msg_size: int, msg_up_nn: Callable,
+                 msg_boundaries_nn: Callable, msg_down_nn: Callable, update_up_nn: Callable,
+                 update_boundaries_nn: Callable, update_down_nn: Callable, combine_nn: Callable, eps: float = 0,
+                 train_eps: bool = False):
+        super(CINppCochainConv, self).__init__(dim, up_msg_size, down_msg_size, boundary_msg_size, msg_up_nn,
+                                               msg_boundaries_nn, update_up_nn, update_boundaries_nn, combine_nn, eps,
+                                               train_eps)
+        self.msg_down_nn = msg_down_nn
+        self.update_down_nn = update_down_nn
+        if train_eps:
+            self.eps3 = torch.nn.Parameter(torch.Tensor([eps]))
+        else:
+            self.register_buffer('eps3', torch.Tensor([eps]))
+        reset(self.msg_down_nn)
+        reset(self.update_down_nn)
+        self.eps3.data.fill_(self.initial_eps)
+
+    def _boundary_eps(self):
+        return self.eps3
+
+    def message_down(self, down_x_j: Tensor, down_attr: Tensor) -> Tensor:
+        return self.msg_down_nn((down_x_j, down_attr))
+
+    def forward(self, cochain: CochainMessagePassingParams):
+        x = cochain.x
+        fused = self._fused_forward(cochain)
+        if fused is NotImplemented:
+            agg_up, agg_down, agg_b = self.propagate(cochain.up_index, cochain.down_index, cochain.boundary_index,
+                                                     x=x, up_attr=cochain.kwargs['up_attr'],
+                                                     boundary_attr=cochain.kwargs['boundary_attr'])
+            up_branch = lambda: agg_up + (1 + self.eps1) * x              # noqa: E731
+            down_branch = lambda: agg_down + (1 + self.eps2) * x          # noqa: E731
+            boundary_branch = lambda: agg_b + (1 + self.eps3) * x         # noqa: E731
+        else:
+            up_branch, boundary_branch = fused
+            if self.down_msg_size != x.size(1):  # zeros [N, down_msg_size] + (1+eps) x must broadcast as torch would
+                down_branch = lambda: torch.zeros(x.size(0), self.down_msg_size, device=x.device) + (1 + self.eps2) * x  # noqa: E731
+            else:
+                down_branch = lambda: (1 + self.eps2) * x                 # noqa: E731
+        out_up, out_down, out_boundaries = run_concurrently(
+            [lambda: self.update_up_nn(up_branch()), lambda: self.update_down_nn(down_branch()),
+             lambda: self.update_boundaries_nn(boundary_branch())], x.device)
+        return self.combine_nn(torch.cat([out_up, out_down, out_boundaries], dim=-1))
+
+
+class CINppConv(SparseCINConv):
+    """One `CINppCochainConv` per dimension (reference `mp/layers.py:344-427`). Like the reference it first runs
+    SparseCINConv's constructor (whose levels are then discarded), so a seeded construction consumes the random
+    stream identically."""
+
+    fuse_dense = False  # three update branches: the dense nets run on the torch modules
+
+    def __init__(self, up_msg_size: int, down_msg_size: int, boundary_msg_size: Optional[int],
+                 passed_msg_up_nn: Optional[Callable], passed_msg_down_nn: Optional[Callable],
+                 passed_msg_boundaries_nn: Optional[Callable], passed_update_up_nn: Optional[Callable],
+                 passed_update_down_nn: Optional[Callable], passed_update_boundaries_nn: Optional[Callable],
+                 eps: float = 0., train_eps: bool = False, max_dim: int = 2, graph_norm=BN, use_coboundaries=False,
+                 **kwargs):
+        super(CINppConv, self).__init__(up_msg_size, down_msg_size, boundary_msg_size, passed_msg_up_nn,
+                                        passed_msg_boundaries_nn, passed_update_up_nn, passed_update_boundaries_nn,
+                                        eps, train_eps, max_dim, graph_norm, use_coboundaries, **kwargs)
+        self.max_dim = max_dim
+        self.mp_levels = torch.nn.ModuleList()
+
+        def message_mlp():
+            return Sequential(Catter(), Linear(kwargs['layer_dim'] * 2, kwargs['layer_dim']), kwargs['act_module']())
+
+        def update_mlp():
+            return Sequential(Linear(kwargs['layer_dim'], kwargs['hidden']), graph_norm(kwargs['hidden']),
+                              kwargs['act_module'](),
+                              Linear(kwargs['hidden'], kwargs['hidden']), graph_norm(kwargs['hidden']),
+                              kwargs['act_module']())
+
+        for dim in range(max_dim + 1):
+            msg_up_nn = passed_msg_up_nn
+            if msg_up_nn is None:
+                msg_up_nn = message_mlp() if use_coboundaries else take_first
+            msg_down_nn = passed_msg_down_nn
+            if msg_down_nn is None:
+                msg_down_nn = message_mlp() if use_coboundaries else take_first
+            msg_boundaries_nn = identity if passed_msg_boundaries_nn is None else passed_msg_boundaries_nn
+            update_up_nn = update_mlp() if passed_update_up_nn is None else passed_update_up_nn
+            update_down_nn = update_mlp() if passed_update_down_nn is None else passed_update_down_nn
+            update_boundaries_nn = update_mlp() if passed_update_boundaries_nn is None \
+                else passed_update_boundaries_nn
+            combine_nn = Sequential(Linear(kwargs['hidden'] * 3, kwargs['hidden']), graph_norm(kwargs['hidden']),
+                                    kwargs['act_module']())
+            self.mp_levels.append(CINppCochainConv(
+                dim, up_msg_size, down_msg_size, boundary_msg_size=boundary_msg_size, msg_up_nn=msg_up_nn,
+                msg_down_nn=msg_down_nn, msg_boundaries_nn=msg_boundaries_nn, update_up_nn=update_up_nn,
+                update_down_nn=update_down_nn, update_boundaries_nn=update_boundaries_nn, combine_nn=combine_nn,
+                eps=eps, train_eps=train_eps))
 
 
 # ----------------------------------------------------------------------------------------------- initialisation

@@ -6,7 +6,8 @@ from torch.nn import Embedding, Linear
 from cwn_b200 import ops
 from cwn_b200.data.complex import ComplexBatch
 from cwn_b200.mp.encoders import AtomEncoder, BondEncoder
-from cwn_b200.mp.layers import EmbedVEWithReduce, InitReduceConv, OGBEmbedVEWithReduce, SparseCINConv
+from cwn_b200.mp.layers import (CINppConv, EmbedVEWithReduce, InitReduceConv, OGBEmbedVEWithReduce,
+                                SparseCINConv)
 from cwn_b200.mp.models import _JumpMixin, _readout_head
 from cwn_b200.mp.nn import JumpingKnowledge, get_graph_norm, get_nonlinearity, pool_complex
 
@@ -162,3 +163,50 @@ class OGBEmbedSparseCIN(_EmbedSparseCINBase):
     def forward(self, data: ComplexBatch, include_partial=False):
         return self._forward(data, include_partial, in_dropout=self.in_dropout_rate,
                              conv_dropout=self.dropout_rate)
+
+
+def _cinpp_convs(model, num_layers, hidden, embed_dim, nonlinearity, train_eps, use_coboundaries):
+    convs = torch.nn.ModuleList()
+    act_module = get_nonlinearity(nonlinearity, return_module=True)
+    if embed_dim is None:
+        embed_dim = hidden
+    for i in range(num_layers):
+        layer_dim = embed_dim if i == 0 else hidden
+        convs.append(
+            CINppConv(up_msg_size=layer_dim, down_msg_size=layer_dim, boundary_msg_size=layer_dim,
+                      passed_msg_boundaries_nn=None, passed_msg_up_nn=None, passed_msg_down_nn=None,
+                      passed_update_up_nn=None, passed_update_down_nn=None, passed_update_boundaries_nn=None,
+                      train_eps=train_eps, max_dim=model.max_dim, hidden=hidden, act_module=act_module,
+                      layer_dim=layer_dim, graph_norm=model.graph_norm, use_coboundaries=use_coboundaries))
+    return convs
+
+
+class EmbedCINpp(EmbedSparseCIN):
+    """CIN++ for ZINC-style molecules (reference `mp/molec_models.py:167-199`): EmbedSparseCIN with `CINppConv` layers."""
+
+    def __init__(self, atom_types, bond_types, out_size, num_layers, hidden, dropout_rate: float = 0.5,
+                 max_dim: int = 2, jump_mode=None, nonlinearity='relu', readout='sum', train_eps=False,
+                 final_hidden_multiplier: int = 2, readout_dims=(0, 1, 2), final_readout='sum',
+                 apply_dropout_before='lin2', init_reduce='sum', embed_edge=False, embed_dim=None,
+                 use_coboundaries=False, graph_norm='bn'):
+        super(EmbedCINpp, self).__init__(atom_types, bond_types, out_size, num_layers, hidden, dropout_rate, max_dim,
+                                         jump_mode, nonlinearity, readout, train_eps, final_hidden_multiplier,
+                                         readout_dims, final_readout, apply_dropout_before, init_reduce, embed_edge,
+                                         embed_dim, use_coboundaries, graph_norm)
+        self.convs = _cinpp_convs(self, num_layers, hidden, embed_dim, nonlinearity, train_eps, use_coboundaries)
+
+
+class OGBEmbedCINpp(OGBEmbedSparseCIN):
+    """CIN++ for ogbg-mol* (reference `mp/molec_models.py:355-385`)."""
+
+    def __init__(self, out_size, num_layers, hidden, dropout_rate: float = 0.5, indropout_rate: float = 0,
+                 max_dim: int = 2, jump_mode=None, nonlinearity='relu', readout='sum', train_eps=False,
+                 final_hidden_multiplier: int = 2, readout_dims=(0, 1, 2), final_readout='sum',
+                 apply_dropout_before='lin2', init_reduce='sum', embed_edge=False, embed_dim=None,
+                 use_coboundaries=False, graph_norm='bn', atom_feature_dims=None, bond_feature_dims=None):
+        super(OGBEmbedCINpp, self).__init__(out_size, num_layers, hidden, dropout_rate, indropout_rate, max_dim,
+                                            jump_mode, nonlinearity, readout, train_eps, final_hidden_multiplier,
+                                            readout_dims, final_readout, apply_dropout_before, init_reduce,
+                                            embed_edge, embed_dim, use_coboundaries, graph_norm, atom_feature_dims,
+                                            bond_feature_dims)
+        self.convs = _cinpp_convs(self, num_layers, hidden, embed_dim, nonlinearity, train_eps, use_coboundaries)

@@ -8,6 +8,7 @@ to it and to the CUDA implementation:
   propagate                mp/cell_mp.py:357-392 (+ __collect__/__lift__ :195-282, aggregate_* :423-479, update :511-524)
   get_cochain_params       data/complex.py:548-626
   sparse_cin_cochain_conv  mp/layers.py:184-214 with the default nets of SparseCINConv :286-325
+  cinpp_cochain_conv       mp/layers.py:243-260 (CIN++; models mp/models.py:259-283, mp/molec_models.py:167-199, :355-385)
   cin_cochain_conv         mp/layers.py:78-103 with the nets of CIN0, mp/models.py:34-50
   init_reduce / embed_ve   mp/layers.py:484-487, :516-543
   pool_complex             mp/nn.py:50-60
@@ -192,9 +193,33 @@ def sparse_cin_cochain_conv(sd, prefix, p, cfg, training, layer_dim):
     return act(_norm(sd, prefix + 'combine_nn.1.', v, cfg['graph_norm'], training))
 
 
+def cinpp_cochain_conv(sd, prefix, p, cfg, training, layer_dim):
+    """CINppCochainConv.forward (mp/layers.py:243-260). The layer is constructed with use_down_msg=False
+    (mp/layers.py:223-226 -> :167-168) and its models pass include_down_features=False, so the down branch only ever
+    sees zeros + (1+eps2) x; residual epsilons: up eps1, down eps2, boundaries eps3."""
+    act = _ACT[cfg['nonlinearity']]
+    message_up = None
+    if cfg['use_coboundaries']:
+        def message_up(x_j, attr):
+            return act(F.linear(torch.cat((x_j, attr), dim=-1), sd[prefix + 'msg_up_nn.1.weight'],
+                                sd[prefix + 'msg_up_nn.1.bias']))
+    out_up, out_down, out_b = propagate(p.x, p.up_index, p.down_index, p.boundary_index, p.up_attr, None,
+                                        p.boundary_attr, layer_dim, layer_dim, layer_dim, use_down_msg=False,
+                                        message_up=message_up)
+    out_up = out_up + (1 + sd[prefix + 'eps1']) * p.x
+    out_down = out_down + (1 + sd[prefix + 'eps2']) * p.x
+    out_b = out_b + (1 + sd[prefix + 'eps3']) * p.x
+    out_up = _update_mlp(sd, prefix + 'update_up_nn.', out_up, cfg, training)
+    out_down = _update_mlp(sd, prefix + 'update_down_nn.', out_down, cfg, training)
+    out_b = _update_mlp(sd, prefix + 'update_boundaries_nn.', out_b, cfg, training)
+    v = F.linear(torch.cat([out_up, out_down, out_b], dim=-1), sd[prefix + 'combine_nn.0.weight'],
+                 sd[prefix + 'combine_nn.0.bias'])
+    return act(_norm(sd, prefix + 'combine_nn.1.', v, cfg['graph_norm'], training))
+
+
 def sparse_cin_conv(sd, prefix, params, cfg, training, layer_dim):
-    return [sparse_cin_cochain_conv(sd, f'{prefix}mp_levels.{d}.', p, cfg, training, layer_dim)
-            for d, p in enumerate(params)]
+    level = cinpp_cochain_conv if cfg.get('cinpp') else sparse_cin_cochain_conv
+    return [level(sd, f'{prefix}mp_levels.{d}.', p, cfg, training, layer_dim) for d, p in enumerate(params)]
 
 
 def _cin_msg(sd, prefix, v, cfg, training):
@@ -349,6 +374,21 @@ def embed_sparse_cin(sd, cfg, data, training=False, include_partial=False):
 def ogb_embed_sparse_cin(sd, cfg, data, training=False, include_partial=False):
     """OGBEmbedSparseCIN.forward (mp/molec_models.py:281-350)."""
     return _sparse_family(sd, cfg, data, training, include_partial, 'ogb', cfg.get('embed_dim') or cfg['hidden'])
+
+
+def cinpp(sd, cfg, data, training=False, include_partial=False):
+    """CINpp.forward = SparseCIN.forward over CINppConv layers (mp/models.py:259-283)."""
+    return sparse_cin(sd, dict(cfg, cinpp=True), data, training, include_partial)
+
+
+def embed_cinpp(sd, cfg, data, training=False, include_partial=False):
+    """EmbedCINpp (mp/molec_models.py:167-199)."""
+    return embed_sparse_cin(sd, dict(cfg, cinpp=True), data, training, include_partial)
+
+
+def ogb_embed_cinpp(sd, cfg, data, training=False, include_partial=False):
+    """OGBEmbedCINpp (mp/molec_models.py:355-385)."""
+    return ogb_embed_sparse_cin(sd, dict(cfg, cinpp=True), data, training, include_partial)
 
 
 def cin0(sd, cfg, data, training=False):

@@ -25,8 +25,9 @@ import data.dummy_complexes as ref_fix                                    # noqa
 from data.complex import Cochain as RefCochain, Complex as RefComplex, ComplexBatch as RefBatch  # noqa: E402
 from mp.cell_mp import CochainMessagePassing as RefCMP                    # noqa: E402
 from mp.layers import DummyCellularMessagePassing as RefDummy, InitReduceConv as RefInitReduce  # noqa: E402
-from mp.models import SparseCIN as RefSparseCIN, CIN0 as RefCIN0          # noqa: E402
-from mp.molec_models import EmbedSparseCIN as RefEmbed, OGBEmbedSparseCIN as RefOGB  # noqa: E402
+from mp.models import SparseCIN as RefSparseCIN, CIN0 as RefCIN0, CINpp as RefCINpp  # noqa: E402
+from mp.molec_models import (EmbedSparseCIN as RefEmbed, OGBEmbedSparseCIN as RefOGB,  # noqa: E402
+                             EmbedCINpp as RefEmbedCINpp)
 
 from cwn_b200.data import synthetic                                        # noqa: E402
 
@@ -193,6 +194,14 @@ def main():
                jump_mode='cat')
     run_train('cin0_train', RefCIN0(**cfg), cfg,
               synthetic.float_feature_complexes(5, 4, seed=5, include_down_adj=True), l1)
+
+    # CIN++ (appended last so that the random stream of everything above is unchanged)
+    cfg = dict(num_input_features=8, num_classes=1, num_layers=2, hidden=16, dropout_rate=0.0, max_dim=2,
+               nonlinearity='relu', train_eps=True, use_coboundaries=True)
+    run_train('cinpp_train', RefCINpp(**cfg), cfg, synthetic.float_feature_complexes(5, 8, seed=6, ragged=True), l1)
+    cfg = dict(atom_types=28, bond_types=4, out_size=1, num_layers=2, hidden=16, dropout_rate=0.0, max_dim=2,
+               embed_edge=True, use_coboundaries=True, readout='mean')
+    run_train('embed_cinpp_train', RefEmbedCINpp(**cfg), cfg, synthetic.zinc_like_complexes(6, seed=7), l1)
 
     gold['models'] = models
     path = os.path.join(HERE, 'reference_golden.pt')

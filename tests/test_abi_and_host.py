@@ -10,8 +10,8 @@ import torch
 from cwn_b200 import _lib, ops
 from cwn_b200.mp.cell_mp import CochainMessagePassing
 from cwn_b200.mp.layers import CINConv, DummyCochainMessagePassing, SparseCINConv, SparseCINCochainConv
-from cwn_b200.mp.models import CIN0, SparseCIN
-from cwn_b200.mp.molec_models import EmbedSparseCIN, OGBEmbedSparseCIN
+from cwn_b200.mp.models import CIN0, CINpp, SparseCIN
+from cwn_b200.mp.molec_models import EmbedCINpp, EmbedSparseCIN, OGBEmbedSparseCIN
 from helpers import fixture, golden
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -100,7 +100,8 @@ def test_module_structure_loads_reference_state_dicts():
                         ('embed_sparse_cin_eval', EmbedSparseCIN), ('cin0_eval', CIN0),
                         ('sparse_cin_train', SparseCIN), ('embed_sparse_cin_train', EmbedSparseCIN),
                         ('embed_sparse_cin_train_nocob', EmbedSparseCIN),
-                        ('ogb_embed_sparse_cin_train', OGBEmbedSparseCIN), ('cin0_train', CIN0)]:
+                        ('ogb_embed_sparse_cin_train', OGBEmbedSparseCIN), ('cin0_train', CIN0),
+                        ('cinpp_train', CINpp), ('embed_cinpp_train', EmbedCINpp)]:
         m = golden()['models'][name]
         model = klass(**m['cfg'])
         missing, unexpected = model.load_state_dict(m['state_dict'], strict=True)

@@ -13,8 +13,8 @@ from cwn_b200.data import synthetic
 from cwn_b200.data.complex import ComplexBatch
 from cwn_b200.mp.cell_mp import CochainMessagePassing
 from cwn_b200.mp.layers import DummyCellularMessagePassing, InitReduceConv
-from cwn_b200.mp.models import CIN0, SparseCIN
-from cwn_b200.mp.molec_models import EmbedSparseCIN, OGBEmbedSparseCIN
+from cwn_b200.mp.models import CIN0, CINpp, SparseCIN
+from cwn_b200.mp.molec_models import EmbedCINpp, EmbedSparseCIN, OGBEmbedSparseCIN
 from helpers import assert_close, batch_of, fixture, golden, oracle_state, share_cin0_levels
 
 pytestmark = pytest.mark.gpu
@@ -305,13 +305,14 @@ def test_user_overridden_hooks_are_honoured():
 
 # ------------------------------------------------------------------------------------------------ models
 KLASS = {'sparse_cin': SparseCIN, 'embed_sparse_cin': EmbedSparseCIN, 'ogb_embed_sparse_cin': OGBEmbedSparseCIN,
-         'cin0': CIN0}
+         'cin0': CIN0, 'cinpp': CINpp, 'embed_cinpp': EmbedCINpp}
 ORACLE = {'sparse_cin': O.sparse_cin, 'embed_sparse_cin': O.embed_sparse_cin,
-          'ogb_embed_sparse_cin': O.ogb_embed_sparse_cin, 'cin0': O.cin0}
+          'ogb_embed_sparse_cin': O.ogb_embed_sparse_cin, 'cin0': O.cin0, 'cinpp': O.cinpp,
+          'embed_cinpp': O.embed_cinpp}
 
 
 def _family(name):
-    for k in ('ogb_embed_sparse_cin', 'embed_sparse_cin', 'sparse_cin', 'cin0'):
+    for k in ('ogb_embed_sparse_cin', 'embed_sparse_cin', 'embed_cinpp', 'cinpp', 'sparse_cin', 'cin0'):
         if name.startswith(k):
             return k
 
@@ -347,7 +348,7 @@ def _loss(name, out, y):
 
 
 @pytest.mark.parametrize('name', ['sparse_cin_train', 'embed_sparse_cin_train', 'embed_sparse_cin_train_nocob',
-                                  'ogb_embed_sparse_cin_train', 'cin0_train'])
+                                  'ogb_embed_sparse_cin_train', 'cin0_train', 'cinpp_train', 'embed_cinpp_train'])
 def test_train_step_matches_reference_and_oracle(name):
     """Forward, loss, every parameter gradient and the BatchNorm running statistics of one training step."""
     m = golden()['models'][name]
@@ -544,7 +545,7 @@ def test_fused_dense_layer_equals_torch_modules(layer_dim, hidden, act, norm, co
         else:
             scale = float(p2[k].grad.abs().max()) + 1e-6
             # d/d eps = <g, x>: a sum of ~1e5 signed terms, so its fp32 rounding is not relative to the result
-            atol = max(2e-5, 1e-4 * scale)  # (biases feeding a BatchNorm have an analytically zero gradient: pure rounding noise)
+            atol = max(5e-5, 1e-4 * scale)  # (biases feeding a BatchNorm have an analytically zero gradient: pure rounding noise)
             assert_close(p1[k].grad, p2[k].grad, rtol=1e-4, atol=atol, what=f'grad {k}')
     for k in b1:
         assert_close(b1[k].float(), b2[k].float(), rtol=1e-5, atol=1e-6, what=f'buffer {k}')
@@ -560,7 +561,7 @@ def test_fused_dense_layer_equals_torch_modules(layer_dim, hidden, act, norm, co
     for k in p1:
         if p2[k].grad is not None:
             scale = float(p2[k].grad.abs().max()) + 1e-6
-            atol = max(2e-5, 1e-4 * scale)  # (biases feeding a BatchNorm have an analytically zero gradient: pure rounding noise)
+            atol = max(5e-5, 1e-4 * scale)  # (biases feeding a BatchNorm have an analytically zero gradient: pure rounding noise)
             assert_close(p1[k].grad, p2[k].grad, rtol=1e-4, atol=atol, what=f'direct grad {k}')
     torch_conv.load_state_dict(fused_conv.state_dict())  # (the fused layer has seen one more training step)
     with torch.no_grad():
