@@ -134,7 +134,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
-                                          '-i', str(self.gpu), '-lms', '20'], stdout=subprocess.PIPE, text=True)
+                                          '-i', str(self.gpu), '-lms', os.environ.get('CWN_BENCH_SMI_MS', '20')], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None

@@ -60,6 +60,12 @@ class UnitBwdDesc(ctypes.Structure):
                 ('counter', _P), ('tile_rows', _I32)]
 
 
+class CollateJob(ctypes.Structure):
+    """cwn_collate_job"""
+    _fields_ = [('src', _P), ('dst', _P), ('src_start', _P), ('dst_start', _P), ('add', _P), ('n_segments', _I32),
+                ('kind', _I32), ('row_elems', _I32), ('n_out', _I64)]
+
+
 MAX_GROUP = 8
 
 _SIGNATURES = {
@@ -85,6 +91,7 @@ _SIGNATURES = {
     'cwn_unit_bwd_finalize_grouped': (ctypes.c_int, [ctypes.POINTER(UnitBwdDesc), _i32, _vp]),
     'cwn_unit_bwd_grouped': (ctypes.c_int, [ctypes.POINTER(UnitBwdDesc), _i32, _vp]),
     'cwn_wgrad_finalize_grouped': (ctypes.c_int, [ctypes.POINTER(UnitBwdDesc), _i32, _vp]),
+    'cwn_collate': (ctypes.c_int, [ctypes.POINTER(CollateJob), _i32, _vp]),
     'cwn_adam_step_f32': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _i32, _vp]),
     'cwn_check_index_range': (ctypes.c_int, [_c_i64p, _i64, _i64, _c_i32p, _vp]),
 }
@@ -102,7 +109,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
+    path = os.environ.get('CWN_B200_LIB', _build.LIB)
     try:
         path = _build.build_library()
     except RuntimeError:

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(CSRC, 'libcwn_b200.so')
-SOURCES = ['plan.cu', 'gsa.cu', 'dense.cu', 'optim.cu']
+SOURCES = ['plan.cu', 'gsa.cu', 'dense.cu', 'optim.cu', 'collate.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC', '-shared']
 
@@ -33,7 +33,21 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name, defines):
+    """Profiling aid: an alternative build of the library (`libcwn_b200_<name>.so`) with extra -D flags; select it
+    at run time with CWN_B200_LIB=<path>."""
+    out = os.path.join(CSRC, f'libcwn_b200_{name}.so')
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [_nvcc()] + NVCC_FLAGS + [f'-D{d}' for d in defines] + ['-o', out] + srcs
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError('cwn_b200: nvcc failed\n' + proc.stdout + proc.stderr)
+    return out
+
+
 def build_library(force=False, verbose=False):
+    if os.environ.get('CWN_B200_LIB'):
+        return os.environ['CWN_B200_LIB']
     if not force and not _stale():
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]

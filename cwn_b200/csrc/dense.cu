@@ -18,6 +18,13 @@
 // (SURVEY 7), and at the real-data shape these GEMMs are ~25 MFLOP each — launch latency, not flops, is the cost.
 #include "common.cuh"
 
+#ifndef CWN_MMA_PIPELINE
+#define CWN_MMA_PIPELINE 1  // register double-buffering of the shared-memory operands in tile_mma
+#endif
+#ifndef CWN_BWD_MIN_CTAS
+#define CWN_BWD_MIN_CTAS 2  // __launch_bounds__ occupancy target of unit_bwd_kernel (caps registers at 128)
+#endif
+
 namespace cwn {
 
 constexpr int TM = 64;    // rows per tile (large problems); small ones use 32-row tiles for twice the CTAs
@@ -77,12 +84,21 @@ __device__ __forceinline__ void tile_mma(const float* __restrict__ As, int lda, 
 #pragma unroll
   for (int q = 0; q < 4; ++q) b[q] = *reinterpret_cast<const float4*>(b0 + q * ldb);
   for (int k = 0; k < inner4; k += 4) {
+#if CWN_MMA_PIPELINE
     if (k + 4 < inner4) {
 #pragma unroll
       for (int i = 0; i < R; ++i) an[i] = *reinterpret_cast<const float4*>(a0 + i * lda + k + 4);
 #pragma unroll
       for (int q = 0; q < 4; ++q) bn[q] = *reinterpret_cast<const float4*>(b0 + (k + 4 + q) * ldb);
     }
+#else
+    if (k > 0) {
+#pragma unroll
+      for (int i = 0; i < R; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * lda + k);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) b[q] = *reinterpret_cast<const float4*>(b0 + (k + q) * ldb);
+    }
+#endif
 #pragma unroll
     for (int i = 0; i < R; ++i) {
       const float av[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
@@ -94,10 +110,12 @@ __device__ __forceinline__ void tile_mma(const float* __restrict__ As, int lda, 
         acc[i][3] = fmaf(av[q], b[q].w, acc[i][3]);
       }
     }
+#if CWN_MMA_PIPELINE
 #pragma unroll
     for (int i = 0; i < R; ++i) a[i] = an[i];
 #pragma unroll
     for (int q = 0; q < 4; ++q) b[q] = bn[q];
+#endif
   }
 }
 
@@ -458,7 +476,7 @@ __global__ void __launch_bounds__(DT) unit_bwd_finalize_kernel(const __grid_cons
 // g_z tile -> input gradient (g_z W) and per-CTA partial weight gradient (g_z^T f_in(X)); CTA j of a problem strides
 // over the row tiles j, j + n_ctas, ... and owns slab j of the partial buffers (plain read-modify-write, no atomics).
 template <int TR>
-__global__ void __launch_bounds__(DT, 2) unit_bwd_kernel(const __grid_constant__ Group<cwn_unit_bwd_desc> g) {
+__global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_kernel(const __grid_constant__ Group<cwn_unit_bwd_desc> g) {
   constexpr int TM = TR;          // rows per tile
   constexpr int R = TR / 16;      // rows per thread of the input-gradient tile
   constexpr int LDR = TR + 4;     // leading dimension of g_z^T (inner dimension = rows)

@@ -225,6 +225,23 @@ int cwn_adam_step_f32(float* param, float* grad, float* exp_avg, float* exp_avg_
                       float beta2, float eps, float weight_decay, int32_t* step, int32_t* counter, int32_t zero_grad,
                       cwn_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * GPU-side collation (replaces the CPU loops of ComplexBatch.from_complex_list / CochainBatch.from_cochain_list,
+ * data/complex.py:323-458, 690-728). Every tensor of a batch is a concatenation of per-complex segments of a
+ * device-resident dataset, each shifted by a per-segment constant (the running cell-count offsets of `__inc__`,
+ * data/complex.py:148-169). One job = one output tensor (or one row of a [2, E] index):
+ *   dst[dst_start[j] + t] = src[src_start[j] + t] (+ add[j])      for t in [0, dst_start[j+1] - dst_start[j])
+ * CWN_COLLATE_FILL writes the segment number j instead (the `batch` vector). All jobs of a batch go in ONE launch.
+ * src_start[n_segments], dst_start[n_segments + 1], add[n_segments] (nullable) are DEVICE int64 arrays. */
+enum { CWN_COLLATE_I64 = 0, CWN_COLLATE_F32_ROWS = 1, CWN_COLLATE_FILL = 2 };
+typedef struct {
+  const void* src; void* dst;
+  const int64_t* src_start; const int64_t* dst_start; const int64_t* add;
+  int32_t n_segments; int32_t kind; int32_t row_elems; /* floats per row for CWN_COLLATE_F32_ROWS */
+  int64_t n_out;                                        /* = dst_start[n_segments], known on the host */
+} cwn_collate_job;
+int cwn_collate(const cwn_collate_job* jobs, int32_t n_jobs, cwn_stream_t stream);
+
 /* Debug aid: sets bit 1 of flags[0] if any idx[e] is outside [0, n). (The reference relies on torch's device
  * assert for out-of-range indices.) */
 int cwn_check_index_range(const int64_t* idx, int64_t E, int64_t n, int32_t* flags, cwn_stream_t stream);

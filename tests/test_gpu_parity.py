@@ -658,3 +658,43 @@ def test_cob_kernels_large_row_counts(act, F):
     assert_close(Pg.grad, P.grad, rtol=1e-5, atol=5e-5, what='grad P')
     assert_close(Qg.grad, Q.grad, rtol=1e-5, atol=1e-4, what='grad Q')
     assert float(out[-50:].sub((1 + eps) * res0[-50:]).abs().max()) == 0.0  # rows without messages: residual only
+
+
+@pytest.mark.parametrize('kind', ['zinc', 'ragged', 'ragged_down', 'ogb'])
+def test_gpu_collation_equals_python_collation(kind):
+    """PackedComplexDataset.collate (one kernel, dataset resident in HBM) must reproduce
+    ComplexBatch.from_complex_list(...).pack_() bit for bit: every tensor, the packed layout, the host-side counts."""
+    from cwn_b200.data.packed import PackedComplexDataset
+    kw = dict(zinc={}, ragged=dict(ragged=True), ragged_down=dict(ragged=True, include_down_adj=True),
+              ogb=dict(ogb_features=True))[kind]
+    mk = lambda: synthetic.zinc_like_complexes(40, seed=12, **kw)  # noqa: E731
+    ds = PackedComplexDataset(mk(), max_dim=2, device=DEV)
+    comps = mk()
+    g = torch.Generator().manual_seed(0)
+    for trial in range(4):
+        ids = torch.randperm(40, generator=g)[:9 + trial].tolist()
+        ref = ComplexBatch.from_complex_list([comps[i] for i in ids], max_dim=2).pack_()
+        got = ds.collate(ids)
+        assert got.packed_signature == ref.packed_signature
+        assert got.dimension == ref.dimension and got.num_complexes == ref.num_complexes
+        assert torch.equal(got.y.cpu(), ref.y)
+        for d in range(ref.dimension + 1):
+            a, b = got.cochains[d], ref.cochains[d]
+            assert (a.num_cells, a.num_cells_up, a.num_cells_down) == (b.num_cells, b.num_cells_up, b.num_cells_down)
+            for k in ('x', 'upper_index', 'lower_index', 'boundary_index', 'shared_boundaries', 'shared_coboundaries',
+                      'batch', 'ptr'):
+                u, v = getattr(a, k), getattr(b, k)
+                assert (u is None) == (v is None), (d, k)
+                if u is not None:
+                    assert torch.equal(u.cpu(), v), (d, k)
+        for dt in ref._flat:
+            assert torch.equal(got._flat[dt].cpu(), ref._flat[dt])
+    # writing into an existing packed batch of the same layout (the static buffers of a captured graph)
+    if kind == 'zinc':
+        static = ds.collate(list(range(8)))
+        ds.collate(list(range(8, 16)), out=static)
+        ref = ComplexBatch.from_complex_list([comps[i] for i in range(8, 16)], max_dim=2).pack_()
+        for dt in ref._flat:
+            assert torch.equal(static._flat[dt].cpu(), ref._flat[dt])
+        with pytest.raises(ValueError, match='layout differs'):
+            ds.collate(list(range(9)), out=static)
