@@ -411,6 +411,38 @@ def run_cwn(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = cells * world / (float(t.item()) / args.steps / 1e3)
 
+    # ---- e2e with collation inside the timed region: the dataset lives in HBM (PackedComplexDataset), a step is
+    #      ids -> GPU collation straight into the graph's static buffers -> step -> loss.item()
+    collated = None
+    if captured is not None:
+        from cwn_b200.data import synthetic
+        from cwn_b200.data.packed import PackedComplexDataset
+        n_ds = 8 * args.batch
+        ds = PackedComplexDataset(synthetic.zinc_like_complexes(n_ds, seed=5000 + rank), max_dim=2, device=dev)
+        perm = torch.randperm(n_ds, generator=torch.Generator().manual_seed(rank)).tolist()
+        pick = lambda i: perm[(i * args.batch) % n_ds:(i * args.batch) % n_ds + args.batch]  # noqa: E731
+        for i in range(3):
+            ds.collate(pick(i), out=captured.static)
+            captured.run()
+        barrier()
+        c_ms, table_bytes = 0.0, 0
+        for i in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ds.collate(pick(i), out=captured.static)
+            captured.run()
+            float(captured.loss.item())
+            c_ms += 1e3 * (time.perf_counter() - t0)
+        t = torch.tensor([c_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        collated = {'value': cells * world / (float(t.item()) / args.steps / 1e3), 'unit': 'cells/s',
+                    'what': 'dataset resident in HBM; per step: 128 ids -> GPU collation (one kernel, written into the '
+                            'graph\'s static buffers) -> step -> loss.item(); the only host->device traffic is the '
+                            'segment table', 'h2d_bytes_per_step': int(ds._keepalive.numel() * 8),
+                    'd2h_bytes_per_step': 4}
+
     # ---- per-kernel roofline of the step (instrumented eager re-run of the same steps; every rank takes part because
     #      the step contains the gradient all-reduce)
     with ops.KernelProfile() as prof:
@@ -445,6 +477,8 @@ def run_cwn(args, rank, world, local_rank):
         'e2e': {'value': e2e_value, 'unit': 'cells/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 4},
         'roofline': roofline,
     }
+    if collated is not None:
+        line['e2e_gpu_collation'] = collated
     if not args.no_sweep:
         line['kernel_sweep'] = kernel_sweep(dev)
     if not args.no_cpu_baseline:

@@ -149,25 +149,40 @@ __device__ __forceinline__ void load_input_tile(const D& d, const float* vin, in
                                                 int kc, int width, float* dst, int ldd, bool vec, int tile_rows) {
   const int act = d.in_act;
   if (vec) {
+    // All global loads of a batch are issued before any of them is consumed (ncu showed the transform of each
+    // float4 stalling on its own load when loads and shared-memory stores were interleaved).
     const int nc4 = width / 4;  // width is a multiple of 4
-    int r = threadIdx.x / nc4, c4 = threadIdx.x % nc4;
-    const int dr = DT / nc4, dc = DT % nc4;
-#pragma unroll 4
-    while (r < tile_rows) {
-      const int k = kc + c4 * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < rows && k < K) {
-        const float* src = (k < d.k0) ? d.x0 + (row0 + r) * d.ld_x0 + k : d.x1 + (row0 + r) * d.ld_x1 + (k - d.k0);
-        v = ldg_f4(src);
-        v.x = act_apply(act, (v.x - vin[k]) * vin[K4 + k] + vin[2 * K4 + k]);
-        v.y = act_apply(act, (v.y - vin[k + 1]) * vin[K4 + k + 1] + vin[2 * K4 + k + 1]);
-        v.z = act_apply(act, (v.z - vin[k + 2]) * vin[K4 + k + 2] + vin[2 * K4 + k + 2]);
-        v.w = act_apply(act, (v.w - vin[k + 3]) * vin[K4 + k + 3] + vin[2 * K4 + k + 3]);
+    const int total = tile_rows * nc4;
+    constexpr int NB = 4;
+    for (int base = threadIdx.x; base < total; base += NB * DT) {
+      float4 v[NB];
+      int rr[NB], kk[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int i = base + j * DT;
+        rr[j] = i / nc4;
+        kk[j] = (i - rr[j] * nc4) * 4;
+        const int k = kc + kk[j];
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < total && rr[j] < rows && k < K) {
+          const float* src = (k < d.k0) ? d.x0 + (row0 + rr[j]) * d.ld_x0 + k : d.x1 + (row0 + rr[j]) * d.ld_x1 + (k - d.k0);
+          v[j] = ldg_f4(src);
+        }
       }
-      *reinterpret_cast<float4*>(dst + r * ldd + c4 * 4) = v;
-      r += dr;
-      c4 += dc;
-      if (c4 >= nc4) { c4 -= nc4; ++r; }
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int i = base + j * DT;
+        if (i >= total) continue;
+        const int k = kc + kk[j];
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rr[j] < rows && k < K) {
+          o.x = act_apply(act, (v[j].x - vin[k]) * vin[K4 + k] + vin[2 * K4 + k]);
+          o.y = act_apply(act, (v[j].y - vin[k + 1]) * vin[K4 + k + 1] + vin[2 * K4 + k + 1]);
+          o.z = act_apply(act, (v[j].z - vin[k + 2]) * vin[K4 + k + 2] + vin[2 * K4 + k + 2]);
+          o.w = act_apply(act, (v[j].w - vin[k + 3]) * vin[K4 + k + 3] + vin[2 * K4 + k + 3]);
+        }
+        *reinterpret_cast<float4*>(dst + rr[j] * ldd + kk[j]) = o;
+      }
     }
   } else {
     for (int i = threadIdx.x; i < tile_rows * width; i += DT) {
@@ -278,12 +293,23 @@ __global__ void __launch_bounds__(DT, 3) linear_fwd_kernel(const __grid_constant
     const bool live = col0 + n < d.h;
     const float* wrow = d.w + (int64_t)(col0 + n) * d.ld_w;
     if (wvec) {
-      for (int c4 = tid / TN; c4 < K4 / 4; c4 += DT / TN) {
-        const float4 w = live ? ldg_f4(wrow + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        Bs[(c4 * 4 + 0) * LDT + n] = w.x;
-        Bs[(c4 * 4 + 1) * LDT + n] = w.y;
-        Bs[(c4 * 4 + 2) * LDT + n] = w.z;
-        Bs[(c4 * 4 + 3) * LDT + n] = w.w;
+      constexpr int NB = 4;
+      for (int c0 = tid / TN; c0 < K4 / 4; c0 += NB * (DT / TN)) {
+        float4 w[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const int c4 = c0 + j * (DT / TN);
+          w[j] = (live && c4 < K4 / 4) ? ldg_f4(wrow + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const int c4 = c0 + j * (DT / TN);
+          if (c4 >= K4 / 4) continue;
+          Bs[(c4 * 4 + 0) * LDT + n] = w[j].x;
+          Bs[(c4 * 4 + 1) * LDT + n] = w[j].y;
+          Bs[(c4 * 4 + 2) * LDT + n] = w[j].z;
+          Bs[(c4 * 4 + 3) * LDT + n] = w[j].w;
+        }
       }
     } else {
       for (int k = tid / TN; k < K4; k += DT / TN) Bs[k * LDT + n] = (live && k < K) ? __ldg(wrow + k) : 0.f;
@@ -520,29 +546,41 @@ __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_kernel(const __
     // g_z = scale * (g_out act'(y) - c1 - zhat c2) of this tile (plain g_out act'(z) without BatchNorm)
     if (g_vec) {
       const int nc4 = H4 / 4;
-      int r = tid / nc4, c4 = tid % nc4;
-      const int dr = DT / nc4, dc = DT % nc4;
-#pragma unroll 4
-      while (r < TM) {
-        const int c = c4 * 4;
-        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < rows) {
-          const float4 z = ldg_f4(d.z + (row0 + r) * d.ld_z + c);
-          const float4 gv = ldg_f4(d.g_out + (row0 + r) * d.ld_g + c);
-          const float zz[4] = {z.x, z.y, z.z, z.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w};
-          float o[4];
+      const int total = TM * nc4;
+      constexpr int NB = 2;  // two operands per element: 4 loads in flight
+      for (int base = tid; base < total; base += NB * DT) {
+        float4 zv[NB], gv[NB];
+        int rr[NB], cc[NB];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float zc = zz[q] - vout[c + q];
-            const float gy = gg[q] * act_grad(d.act, zc * vout[H4 + c + q] + vout[3 * H4 + c + q]);
-            o[q] = d.has_bn ? vout[H4 + c + q] * (gy - vout[4 * H4 + c + q] - zc * vout[2 * H4 + c + q] * vout[5 * H4 + c + q]) : gy;
+        for (int jj = 0; jj < NB; ++jj) {
+          const int i = base + jj * DT;
+          rr[jj] = i / nc4;
+          cc[jj] = (i - rr[jj] * nc4) * 4;
+          zv[jj] = gv[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < total && rr[jj] < rows) {
+            zv[jj] = ldg_f4(d.z + (row0 + rr[jj]) * d.ld_z + cc[jj]);
+            gv[jj] = ldg_f4(d.g_out + (row0 + rr[jj]) * d.ld_g + cc[jj]);
           }
-          out = make_float4(o[0], o[1], o[2], o[3]);
         }
-        *reinterpret_cast<float4*>(Gz + r * ldg + c) = out;
-        r += dr;
-        c4 += dc;
-        if (c4 >= nc4) { c4 -= nc4; ++r; }
+#pragma unroll
+        for (int jj = 0; jj < NB; ++jj) {
+          const int i = base + jj * DT;
+          if (i >= total) continue;
+          const int c = cc[jj];
+          float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rr[jj] < rows) {
+            const float zz[4] = {zv[jj].x, zv[jj].y, zv[jj].z, zv[jj].w}, gg[4] = {gv[jj].x, gv[jj].y, gv[jj].z, gv[jj].w};
+            float o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float zc = zz[q] - vout[c + q];
+              const float gy = gg[q] * act_grad(d.act, zc * vout[H4 + c + q] + vout[3 * H4 + c + q]);
+              o[q] = d.has_bn ? vout[H4 + c + q] * (gy - vout[4 * H4 + c + q] - zc * vout[2 * H4 + c + q] * vout[5 * H4 + c + q]) : gy;
+            }
+            out = make_float4(o[0], o[1], o[2], o[3]);
+          }
+          *reinterpret_cast<float4*>(Gz + rr[jj] * ldg + c) = out;
+        }
       }
     } else {
       for (int i = tid; i < TM * H4; i += DT) {
@@ -569,10 +607,21 @@ __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_kernel(const __
     for (int kc = 0; kc < K; kc += TN) {
       __syncthreads();
       if (w_vec) {  // W[c][kc + k], natural layout
-        for (int i = tid; i < H4 * (TN / 4); i += DT) {
-          const int c = i / (TN / 4), k = (i % (TN / 4)) * 4;
-          const float4 w = (c < d.h && kc + k < K) ? ldg_f4(d.w + (int64_t)c * d.ld_w + kc + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4*>(Ws + c * LDT + k) = w;
+        constexpr int NB = 4;
+        for (int base = tid; base < H4 * (TN / 4); base += NB * DT) {
+          float4 w[NB];
+#pragma unroll
+          for (int jj = 0; jj < NB; ++jj) {
+            const int i = base + jj * DT;
+            const int c = i / (TN / 4), k = (i % (TN / 4)) * 4;
+            w[jj] = (i < H4 * (TN / 4) && c < d.h && kc + k < K) ? ldg_f4(d.w + (int64_t)c * d.ld_w + kc + k)
+                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int jj = 0; jj < NB; ++jj) {
+            const int i = base + jj * DT;
+            if (i < H4 * (TN / 4)) *reinterpret_cast<float4*>(Ws + (i / (TN / 4)) * LDT + (i % (TN / 4)) * 4) = w[jj];
+          }
         }
       } else {
         for (int i = tid; i < H4 * TN; i += DT) {

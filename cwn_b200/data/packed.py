@@ -131,7 +131,13 @@ class PackedComplexDataset(object):
             kind = 'rows' if y.dtype == torch.float32 else 'index1'
             slots.append((None, 'y', y.dtype, (int(lens.sum()),), (kind, y, self.ptrs['y'][ids], dst, None)))
 
-        # ---- layout: one flat buffer per dtype, 16-byte aligned sub-ranges (the rule of Complex.pack_)
+        # ---- layout: one flat buffer per dtype, 16-byte aligned sub-ranges, entries grouped by dtype in order of
+        #      first appearance (exactly the rule of Complex.pack_, so that the signatures coincide)
+        order = []
+        for slot in slots:
+            if slot[2] not in order:
+                order.append(slot[2])
+        slots = [slot for dt in order for slot in slots if slot[2] == dt]
         layout, totals = [], {}
         for d, key, dtype, shape, _ in slots:
             esz = torch.empty((), dtype=dtype).element_size()
