@@ -219,31 +219,54 @@ __device__ __forceinline__ void bn_finalize_body(const float* stats, int n_tiles
                                                  float* rstd_out, float* stage, int stage_floats = kStageFloats,
                                                  int tile_rows = TM) {
   if (training) {
-    // Chan's parallel-variance merge, tiles in order (deterministic). The partials are pulled into shared memory with
-    // coalesced loads first: the merge itself is a dependent chain per column.
+    // Exact group-combination of the per-tile (mean, M2):  mean = SUM cnt_t mean_t / N,
+    //   M2 = SUM [M2_t + cnt_t (mean_t - mean)^2]  — two passes of plain ordered sums (deterministic). A sequential
+    // Chan merge was measured first: its dependent chain of two IEEE divisions per tile, run by ONE CTA after all the
+    // others had finished, cost more than the GEMM itself. The partials are staged in shared memory with coalesced
+    // loads; a column is summed by DT/h threads over interleaved tiles and the partial sums are combined in order.
     const int per_tile = 2 * h;
     const int chunk = stage_floats / per_tile > 0 ? stage_floats / per_tile : 1;
-    float n = 0.f, m2 = 0.f, mean = 0.f;
-    for (int t0 = 0; t0 < n_tiles; t0 += chunk) {
-      const int nt = (n_tiles - t0 < chunk) ? n_tiles - t0 : chunk;
+    const int parts = (h <= DT / 4) ? 4 : (h <= DT / 2 ? 2 : 1);  // threads per column
+    const int c = threadIdx.x % h, part = threadIdx.x / h;
+    const bool live = threadIdx.x < parts * h;
+    __shared__ float comb[DT];
+    float mean = 0.f, m2 = 0.f;
+    for (int pass = 0; pass < 2; ++pass) {
+      float acc = 0.f;
+      for (int t0 = 0; t0 < n_tiles; t0 += chunk) {
+        const int nt = (n_tiles - t0 < chunk) ? n_tiles - t0 : chunk;
+        __syncthreads();
+        for (int i = threadIdx.x; i < nt * per_tile; i += DT) stage[i] = __ldcg(stats + (int64_t)t0 * per_tile + i);
+        __syncthreads();
+        if (live)
+          for (int t = part; t < nt; t += parts) {
+            const int64_t left = n_rows - (int64_t)(t0 + t) * tile_rows;
+            const float cnt = (float)(left < tile_rows ? left : tile_rows);
+            const float mt = stage[t * per_tile + c];
+            if (pass == 0) {
+              acc = fmaf(cnt, mt, acc);
+            } else {
+              const float dm = mt - mean;
+              acc += stage[t * per_tile + h + c] + cnt * dm * dm;
+            }
+          }
+      }
       __syncthreads();
-      for (int i = threadIdx.x; i < nt * per_tile; i += DT) stage[i] = __ldcg(stats + (int64_t)t0 * per_tile + i);
+      comb[threadIdx.x] = acc;
       __syncthreads();
-      if (threadIdx.x < h) {
-        const int c = threadIdx.x;
-        for (int t = 0; t < nt; ++t) {
-          const int64_t left = n_rows - (int64_t)(t0 + t) * tile_rows;
-          const float cnt = (float)(left < tile_rows ? left : tile_rows);
-          const float mt = stage[t * per_tile + c], m2t = stage[t * per_tile + h + c];
-          const float delta = mt - mean, tot = n + cnt;
-          mean += delta * (cnt / tot);
-          m2 += m2t + delta * delta * (n * cnt / tot);
-          n = tot;
-        }
+      float total = 0.f;
+      if (threadIdx.x < h)
+        for (int q = 0; q < parts; ++q) total += comb[q * h + threadIdx.x];
+      if (pass == 0) {  // every thread of a column needs the mean for the second pass
+        __syncthreads();
+        if (threadIdx.x < h) comb[threadIdx.x] = total / (float)n_rows;
+        __syncthreads();
+        mean = comb[c];
+      } else {
+        m2 = total;
       }
     }
     if (threadIdx.x < h) {
-      const int c = threadIdx.x;
       const float var = m2 / (float)n_rows;
       const float rstd = 1.f / sqrtf(var + eps);
       if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
