@@ -440,7 +440,7 @@ def run_cwn(args, rank, world, local_rank):
         collated = {'value': cells * world / (float(t.item()) / args.steps / 1e3), 'unit': 'cells/s',
                     'what': 'dataset resident in HBM; per step: 128 ids -> GPU collation (one kernel, written into the '
                             'graph\'s static buffers) -> step -> loss.item(); the only host->device traffic is the '
-                            'segment table', 'h2d_bytes_per_step': int(ds._keepalive.numel() * 8),
+                            'segment table', 'h2d_bytes_per_step': int(ds._table_bytes),
                     'd2h_bytes_per_step': 4}
 
     # ---- per-kernel roofline of the step (instrumented eager re-run of the same steps; every rank takes part because

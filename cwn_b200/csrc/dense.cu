@@ -48,7 +48,12 @@ __device__ __forceinline__ int find_problem(const Group<D>& g, int cta) {
   return p;
 }
 
-__device__ __forceinline__ float act_apply(int act, float v) {
+// Activations. The runtime-dispatched versions are deliberately NOT inlined: expm1f / tanhf / expf expand to
+// ~100 instructions each, and inlining the 5-way switch at every element of every unrolled tile loader made these
+// kernels 70-100 KB of straight-line code that each CTA executes once — ncu's top stall was `no_instruction`
+// (instruction-cache misses). The kernels are instantiated for the two common codes (identity, ReLU) at compile time
+// and fall back to the out-of-line switch for ELU / sigmoid / tanh.
+__device__ __noinline__ float act_apply_rt(int act, float v) {
   switch (act) {
     case CWN_ACT_RELU: return fmaxf(v, 0.f);
     case CWN_ACT_ELU: return v > 0.f ? v : expm1f(v);
@@ -57,7 +62,7 @@ __device__ __forceinline__ float act_apply(int act, float v) {
     default: return v;
   }
 }
-__device__ __forceinline__ float act_grad(int act, float v) {  // derivative as a function of the pre-activation
+__device__ __noinline__ float act_grad_rt(int act, float v) {  // derivative as a function of the pre-activation
   switch (act) {
     case CWN_ACT_RELU: return v > 0.f ? 1.f : 0.f;
     case CWN_ACT_ELU: return v > 0.f ? 1.f : expf(v);
@@ -65,6 +70,19 @@ __device__ __forceinline__ float act_grad(int act, float v) {  // derivative as 
     case CWN_ACT_TANH: { float t = tanhf(v); return 1.f - t * t; }
     default: return 1.f;
   }
+}
+constexpr int kActRuntime = -1;
+template <int A>
+__device__ __forceinline__ float act_apply(int act, float v) {
+  if (A == CWN_ACT_ID) return v;
+  if (A == CWN_ACT_RELU) return fmaxf(v, 0.f);
+  return act_apply_rt(act, v);
+}
+template <int A>
+__device__ __forceinline__ float act_grad(int act, float v) {
+  if (A == CWN_ACT_ID) return 1.f;
+  if (A == CWN_ACT_RELU) return v > 0.f ? 1.f : 0.f;
+  return act_grad_rt(act, v);
 }
 
 __host__ __device__ __forceinline__ int round4(int v) { return (v + 3) & ~3; }
@@ -144,7 +162,7 @@ __device__ __forceinline__ bool input_vec_ok(const D& d) {
 
 // dst[r * ldd + (k - kc)] = f_in(X)[row0 + r][k] for r < TM, k in [kc, kc + width), zero outside the matrix.
 // 128-bit loads when the layout allows; (r, column) advance incrementally so there is one division per thread.
-template <class D>
+template <int A_IN, class D>
 __device__ __forceinline__ void load_input_tile(const D& d, const float* vin, int K, int K4, int64_t row0, int rows,
                                                 int kc, int width, float* dst, int ldd, bool vec, int tile_rows) {
   const int act = d.in_act;
@@ -176,10 +194,10 @@ __device__ __forceinline__ void load_input_tile(const D& d, const float* vin, in
         const int k = kc + kk[j];
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
         if (rr[j] < rows && k < K) {
-          o.x = act_apply(act, (v[j].x - vin[k]) * vin[K4 + k] + vin[2 * K4 + k]);
-          o.y = act_apply(act, (v[j].y - vin[k + 1]) * vin[K4 + k + 1] + vin[2 * K4 + k + 1]);
-          o.z = act_apply(act, (v[j].z - vin[k + 2]) * vin[K4 + k + 2] + vin[2 * K4 + k + 2]);
-          o.w = act_apply(act, (v[j].w - vin[k + 3]) * vin[K4 + k + 3] + vin[2 * K4 + k + 3]);
+          o.x = act_apply<A_IN>(act, (v[j].x - vin[k]) * vin[K4 + k] + vin[2 * K4 + k]);
+          o.y = act_apply<A_IN>(act, (v[j].y - vin[k + 1]) * vin[K4 + k + 1] + vin[2 * K4 + k + 1]);
+          o.z = act_apply<A_IN>(act, (v[j].z - vin[k + 2]) * vin[K4 + k + 2] + vin[2 * K4 + k + 2]);
+          o.w = act_apply<A_IN>(act, (v[j].w - vin[k + 3]) * vin[K4 + k + 3] + vin[2 * K4 + k + 3]);
         }
         *reinterpret_cast<float4*>(dst + rr[j] * ldd + kk[j]) = o;
       }
@@ -190,7 +208,7 @@ __device__ __forceinline__ void load_input_tile(const D& d, const float* vin, in
       float v = 0.f;
       if (r < rows && k < K) {
         v = (k < d.k0) ? __ldg(d.x0 + (row0 + r) * d.ld_x0 + k) : __ldg(d.x1 + (row0 + r) * d.ld_x1 + (k - d.k0));
-        v = act_apply(act, (v - vin[k]) * vin[K4 + k] + vin[2 * K4 + k]);
+        v = act_apply<A_IN>(act, (v - vin[k]) * vin[K4 + k] + vin[2 * K4 + k]);
       }
       dst[r * ldd + kk] = v;
     }
@@ -290,7 +308,7 @@ __device__ __forceinline__ void bn_finalize_body(const float* stats, int n_tiles
 }
 
 // ------------------------------------------------------------------------------------------------ forward unit
-template <int TR>  // tile rows: 64 or 32
+template <int TR, int A_IN>  // tile rows: 64 or 32; input activation: compile-time code or kActRuntime
 __global__ void __launch_bounds__(DT, 3) linear_fwd_kernel(const __grid_constant__ Group<cwn_linear_desc> g) {
   constexpr int TM = TR;
   constexpr int R = TR / 16;
@@ -339,7 +357,7 @@ __global__ void __launch_bounds__(DT, 3) linear_fwd_kernel(const __grid_constant
     }
   }
   __syncthreads();  // vin ready
-  load_input_tile(d, vin, K, K4, row0, rows, 0, K4, As, lda, input_vec_ok(d), TM);
+  load_input_tile<A_IN>(d, vin, K, K4, row0, rows, 0, K4, As, lda, input_vec_ok(d), TM);
   __syncthreads();
   float acc[R][4] = {};
   tile_mma<R>(As, lda, Bs, LDT, K4, ty, tx, acc);
@@ -426,7 +444,7 @@ __global__ void __launch_bounds__(DT) bn_act_kernel(const __grid_constant__ Grou
     const int r = i / d.h, c = i % d.h;
     float v = d.z[(row0 + r) * d.ld_z + c];
     if (d.scale) v = (v - d.mean[c]) * d.scale[c] + (d.beta ? d.beta[c] : 0.f);
-    d.out[(row0 + r) * d.ld_out + c] = act_apply(d.act, v);
+    d.out[(row0 + r) * d.ld_out + c] = act_apply_rt(d.act, v);
   }
 }
 
@@ -439,10 +457,10 @@ __device__ __forceinline__ void unit_gy(const cwn_unit_bwd_desc& d, int64_t row,
     const float zc = z - __ldg(d.mean + c);
     const float y = zc * __ldg(d.scale + c) + (d.beta ? __ldg(d.beta + c) : 0.f);
     zhat = zc * __ldg(d.rstd + c);
-    gy = g * act_grad(d.act, y);
+    gy = g * act_grad_rt(d.act, y);
   } else {
     zhat = 0.f;
-    gy = g * act_grad(d.act, z);
+    gy = g * act_grad_rt(d.act, z);
   }
 }
 
@@ -471,7 +489,7 @@ __device__ __forceinline__ void unit_bwd_finalize_body(const cwn_unit_bwd_desc& 
   }
 }
 
-template <int TR>
+template <int TR, int A_OUT>
 __global__ void __launch_bounds__(DT) unit_bwd_reduce_kernel(const __grid_constant__ Group<cwn_unit_bwd_desc> g) {
   constexpr int TM = TR;
   __shared__ float part[2][4][TN];
@@ -492,7 +510,7 @@ __global__ void __launch_bounds__(DT) unit_bwd_reduce_kernel(const __grid_consta
 #pragma unroll 4
       for (int r = rg; r < rows; r += 4) {
         const float zc = __ldg(zp + r * d.ld_z) - mean;
-        const float gy = __ldg(gp + r * d.ld_g) * act_grad(d.act, zc * scale + beta);
+        const float gy = __ldg(gp + r * d.ld_g) * act_grad<A_OUT>(d.act, zc * scale + beta);
         s1 += gy;
         s2 = fmaf(gy, zc * rstd, s2);
       }
@@ -524,7 +542,7 @@ __global__ void __launch_bounds__(DT) unit_bwd_finalize_kernel(const __grid_cons
 
 // g_z tile -> input gradient (g_z W) and per-CTA partial weight gradient (g_z^T f_in(X)); CTA j of a problem strides
 // over the row tiles j, j + n_ctas, ... and owns slab j of the partial buffers (plain read-modify-write, no atomics).
-template <int TR>
+template <int TR, int A_IN, int A_OUT>
 __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_kernel(const __grid_constant__ Group<cwn_unit_bwd_desc> g) {
   constexpr int TM = TR;          // rows per tile
   constexpr int R = TR / 16;      // rows per thread of the input-gradient tile
@@ -597,7 +615,7 @@ __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_kernel(const __
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float zc = zz[q] - vout[c + q];
-              const float gy = gg[q] * act_grad(d.act, zc * vout[H4 + c + q] + vout[3 * H4 + c + q]);
+              const float gy = gg[q] * act_grad<A_OUT>(d.act, zc * vout[H4 + c + q] + vout[3 * H4 + c + q]);
               o[q] = d.has_bn ? vout[H4 + c + q] * (gy - vout[4 * H4 + c + q] - zc * vout[2 * H4 + c + q] * vout[5 * H4 + c + q]) : gy;
             }
             out = make_float4(o[0], o[1], o[2], o[3]);
@@ -611,7 +629,7 @@ __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_kernel(const __
         float gz = 0.f;
         if (r < rows && c < d.h) {
           const float zc = __ldg(d.z + (row0 + r) * d.ld_z + c) - vout[c];
-          const float gy = __ldg(d.g_out + (row0 + r) * d.ld_g + c) * act_grad(d.act, zc * vout[H4 + c] + vout[3 * H4 + c]);
+          const float gy = __ldg(d.g_out + (row0 + r) * d.ld_g + c) * act_grad<A_OUT>(d.act, zc * vout[H4 + c] + vout[3 * H4 + c]);
           gz = d.has_bn ? vout[H4 + c] * (gy - vout[4 * H4 + c] - zc * vout[2 * H4 + c] * vout[5 * H4 + c]) : gy;
         }
         Gz[r * ldg + c] = gz;
@@ -652,7 +670,7 @@ __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_kernel(const __
           Ws[c * LDT + k] = (c < d.h && kc + k < K) ? __ldg(d.w + (int64_t)c * d.ld_w + kc + k) : 0.f;
         }
       }
-      load_input_tile(d, vin, K, K4, row0, rows, kc, TN, Ain, LDT, in_vec, TM);
+      load_input_tile<A_IN>(d, vin, K, K4, row0, rows, kc, TN, Ain, LDT, in_vec, TM);
       __syncthreads();
       if (d.g_in0 || d.g_in1) {  // input gradient chunk: [TM rows] x [64 k] = Gz [TM x h] * Ws [h x 64]
         float acc[R][4] = {};
@@ -717,6 +735,16 @@ static int ensure_smem(Kernel kernel, size_t bytes, const char* what) {
   return cuda_status(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), what);
 }
 
+// common compile-time activation code of a group (identity / ReLU), else the runtime fallback
+template <class D, class Get>
+static int group_act(const D* descs, int n, Get get) {
+  const int a = get(descs[0]);
+  if (a != CWN_ACT_ID && a != CWN_ACT_RELU) return kActRuntime;
+  for (int i = 1; i < n; ++i)
+    if (get(descs[i]) != a) return kActRuntime;
+  return a;
+}
+
 // tile rows of a group: every problem must agree (0 means 64)
 template <class D>
 static int group_tile_rows(const D* descs, int n, int& tr) {
@@ -760,13 +788,19 @@ extern "C" int cwn_linear_fwd_grouped(const cwn_linear_desc* descs, int32_t n, c
   }
   g.start[n] = total;
   if (total == 0) return CWN_OK;
-  if (tr == 64) {
-    if ((rc = ensure_smem(linear_fwd_kernel<64>, smem, "cudaFuncSetAttribute(linear_fwd_kernel)"))) return rc;
-    linear_fwd_kernel<64><<<total, DT, smem, (cudaStream_t)stream>>>(g);
-  } else {
-    if ((rc = ensure_smem(linear_fwd_kernel<32>, smem, "cudaFuncSetAttribute(linear_fwd_kernel)"))) return rc;
-    linear_fwd_kernel<32><<<total, DT, smem, (cudaStream_t)stream>>>(g);
+  const int a_in = group_act(descs, n, [](const cwn_linear_desc& d) { return d.in_act; });
+#define CWN_LAUNCH_FWD(TRV, AV)                                                                             \
+  {                                                                                                         \
+    if ((rc = ensure_smem(linear_fwd_kernel<TRV, AV>, smem, "cudaFuncSetAttribute(linear_fwd_kernel)"))) return rc; \
+    linear_fwd_kernel<TRV, AV><<<total, DT, smem, (cudaStream_t)stream>>>(g);                               \
   }
+#define CWN_FWD_BY_ACT(TRV)                                    \
+  if (a_in == CWN_ACT_ID) CWN_LAUNCH_FWD(TRV, CWN_ACT_ID)      \
+  else if (a_in == CWN_ACT_RELU) CWN_LAUNCH_FWD(TRV, CWN_ACT_RELU) \
+  else CWN_LAUNCH_FWD(TRV, kActRuntime)
+  if (tr == 64) { CWN_FWD_BY_ACT(64) } else { CWN_FWD_BY_ACT(32) }
+#undef CWN_FWD_BY_ACT
+#undef CWN_LAUNCH_FWD
   return launched("linear_fwd_kernel");
 }
 
@@ -834,8 +868,13 @@ extern "C" int cwn_unit_bwd_reduce_grouped(const cwn_unit_bwd_desc* descs, int32
   }
   g.start[n] = total;
   if (total == 0) return CWN_OK;
-  if (tr == 64) unit_bwd_reduce_kernel<64><<<total, DT, 0, (cudaStream_t)stream>>>(g);
-  else unit_bwd_reduce_kernel<32><<<total, DT, 0, (cudaStream_t)stream>>>(g);
+  const int a_out = group_act(descs, n, [](const cwn_unit_bwd_desc& d) { return d.act; });
+#define CWN_RED(TRV)                                                                                          \
+  if (a_out == CWN_ACT_ID) unit_bwd_reduce_kernel<TRV, CWN_ACT_ID><<<total, DT, 0, (cudaStream_t)stream>>>(g);    \
+  else if (a_out == CWN_ACT_RELU) unit_bwd_reduce_kernel<TRV, CWN_ACT_RELU><<<total, DT, 0, (cudaStream_t)stream>>>(g); \
+  else unit_bwd_reduce_kernel<TRV, kActRuntime><<<total, DT, 0, (cudaStream_t)stream>>>(g);
+  if (tr == 64) { CWN_RED(64) } else { CWN_RED(32) }
+#undef CWN_RED
   return launched("unit_bwd_reduce_kernel");
 }
 
@@ -870,13 +909,25 @@ extern "C" int cwn_unit_bwd_grouped(const cwn_unit_bwd_desc* descs, int32_t n, c
   }
   g.start[n] = total;
   if (total == 0) return CWN_OK;
-  if (tr == 64) {
-    if ((rc = ensure_smem(unit_bwd_kernel<64>, smem, "cudaFuncSetAttribute(unit_bwd_kernel)"))) return rc;
-    unit_bwd_kernel<64><<<total, DT, smem, (cudaStream_t)stream>>>(g);
-  } else {
-    if ((rc = ensure_smem(unit_bwd_kernel<32>, smem, "cudaFuncSetAttribute(unit_bwd_kernel)"))) return rc;
-    unit_bwd_kernel<32><<<total, DT, smem, (cudaStream_t)stream>>>(g);
+  const int a_in = group_act(descs, n, [](const cwn_unit_bwd_desc& d) { return d.in_act; });
+  const int a_out = group_act(descs, n, [](const cwn_unit_bwd_desc& d) { return d.act; });
+#define CWN_LAUNCH_BWD(TRV, AI, AO)                                                                          \
+  {                                                                                                          \
+    if ((rc = ensure_smem(unit_bwd_kernel<TRV, AI, AO>, smem, "cudaFuncSetAttribute(unit_bwd_kernel)"))) return rc; \
+    unit_bwd_kernel<TRV, AI, AO><<<total, DT, smem, (cudaStream_t)stream>>>(g);                              \
   }
+#define CWN_BWD_BY_OUT(TRV, AI)                                     \
+  if (a_out == CWN_ACT_ID) CWN_LAUNCH_BWD(TRV, AI, CWN_ACT_ID)      \
+  else if (a_out == CWN_ACT_RELU) CWN_LAUNCH_BWD(TRV, AI, CWN_ACT_RELU) \
+  else CWN_LAUNCH_BWD(TRV, AI, kActRuntime)
+#define CWN_BWD_BY_IN(TRV)                                      \
+  if (a_in == CWN_ACT_ID) { CWN_BWD_BY_OUT(TRV, CWN_ACT_ID) }   \
+  else if (a_in == CWN_ACT_RELU) { CWN_BWD_BY_OUT(TRV, CWN_ACT_RELU) } \
+  else { CWN_BWD_BY_OUT(TRV, kActRuntime) }
+  if (tr == 64) { CWN_BWD_BY_IN(64) } else { CWN_BWD_BY_IN(32) }
+#undef CWN_BWD_BY_IN
+#undef CWN_BWD_BY_OUT
+#undef CWN_LAUNCH_BWD
   return launched("unit_bwd_kernel");
 }
 

@@ -190,8 +190,10 @@ class PackedComplexDataset(object):
                 ptr = spec[1]
                 pos = put(ptr)
                 jobs_spec.append(('table', view.data_ptr(), put([pos]), put([0, len(ptr)]), None, 1, 0, 1, len(ptr)))
-        host = torch.from_numpy(np.concatenate(table)).pin_memory()
-        dev_table = host.to(self.device, non_blocking=True)
+        flat_table = np.concatenate(table)
+        host, dev_table = self._staging(len(flat_table))
+        host[:len(flat_table)].copy_(torch.from_numpy(flat_table))
+        dev_table.copy_(host, non_blocking=True)
         base = dev_table.data_ptr()
         jobs = []
         for src, dst, s_off, d_off, a_off, nseg, kind, width, n_out in jobs_spec:
@@ -204,7 +206,9 @@ class PackedComplexDataset(object):
         with torch.cuda.device(self.device):
             nbytes = sum(2 * j.n_out * (8 if j.kind != 1 else 4 * j.row_elems) for j in jobs) if ops._profile else 0
             ops._call('collate', nbytes, lib.cwn_collate, arr, len(jobs), torch.cuda.current_stream().cuda_stream)
-        self._keepalive = dev_table  # until the next collate on this stream
+        self._last_slot[2].record()
+        self._keepalive = dev_table  # (ring slot: stays valid for the next 8 collations)
+        self._table_bytes = len(flat_table) * 8
         if out is not None:
             return out
 
@@ -226,5 +230,24 @@ class PackedComplexDataset(object):
             cochains.append(cb)
         batch = ComplexBatch(*cochains, y=views.get((None, 'y')), num_complexes=B, dimension=dimension)
         batch._flat, batch._layout = flat, list(layout)
-        batch._h2d_bytes = host.numel() * 8
+        batch._h2d_bytes = len(flat_table) * 8
         return batch
+
+    def _staging(self, n):
+        """A (pinned host, device) pair of int64 buffers for the segment table, from a small ring: allocating pinned
+        memory per batch would cost more than the collation. A slot is reused only after 8 later collations."""
+        ring = getattr(self, '_ring', None)
+        if ring is None:
+            ring = self._ring = {'slots': [None] * 8, 'pos': 0}
+        i = ring['pos']
+        ring['pos'] = (i + 1) % len(ring['slots'])
+        slot = ring['slots'][i]
+        if slot is None or slot[0].numel() < n:
+            cap = max(1024, 2 * n)
+            slot = (torch.empty(cap, dtype=torch.long).pin_memory(), torch.empty(cap, dtype=torch.long, device=self.device),
+                    torch.cuda.Event())
+            ring['slots'][i] = slot
+        else:
+            slot[2].synchronize()  # the copy issued from this slot 8 collations ago must have left the host buffer
+        self._last_slot = slot
+        return slot[0], slot[1]
