@@ -92,49 +92,50 @@ __host__ __device__ __forceinline__ int round4(int v) { return (v + 3) & ~3; }
 // The operands of step k+4 are fetched into a second register set before the FMAs of step k are issued: with only a
 // couple of warps per scheduler (these launches are small) the shared-memory latency would otherwise sit exposed.
 template <int R>
+__device__ __forceinline__ void mma_step(const float4 (&a)[R], const float4 (&b)[4], float (&acc)[R][4]) {
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const float av[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      acc[i][0] = fmaf(av[q], b[q].x, acc[i][0]);
+      acc[i][1] = fmaf(av[q], b[q].y, acc[i][1]);
+      acc[i][2] = fmaf(av[q], b[q].z, acc[i][2]);
+      acc[i][3] = fmaf(av[q], b[q].w, acc[i][3]);
+    }
+  }
+}
+
+template <int R>
 __device__ __forceinline__ void tile_mma(const float* __restrict__ As, int lda, const float* __restrict__ Bs, int ldb,
                                          int inner4, int ty, int tx, float (&acc)[R][4]) {
   const float* a0 = As + (ty * R) * lda;
   const float* b0 = Bs + tx * 4;
   float4 a[R], b[4], an[R], bn[4];
+  auto fetch = [&](float4 (&aa)[R], float4 (&bb)[4], int k) {
 #pragma unroll
-  for (int i = 0; i < R; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * lda);
+    for (int i = 0; i < R; ++i) aa[i] = *reinterpret_cast<const float4*>(a0 + i * lda + k);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) b[q] = *reinterpret_cast<const float4*>(b0 + q * ldb);
-  for (int k = 0; k < inner4; k += 4) {
+    for (int q = 0; q < 4; ++q) bb[q] = *reinterpret_cast<const float4*>(b0 + (k + q) * ldb);
+  };
+  fetch(a, b, 0);
 #if CWN_MMA_PIPELINE
+  // two k-steps per trip with ping-pong operand registers: the loads of the next step are in flight while the FMAs
+  // of the current one issue, and no register copies are needed
+  for (int k = 0; k < inner4; k += 8) {
+    if (k + 4 < inner4) fetch(an, bn, k + 4);
+    mma_step<R>(a, b, acc);
     if (k + 4 < inner4) {
-#pragma unroll
-      for (int i = 0; i < R; ++i) an[i] = *reinterpret_cast<const float4*>(a0 + i * lda + k + 4);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) bn[q] = *reinterpret_cast<const float4*>(b0 + (k + 4 + q) * ldb);
+      if (k + 8 < inner4) fetch(a, b, k + 8);
+      mma_step<R>(an, bn, acc);
     }
-#else
-    if (k > 0) {
-#pragma unroll
-      for (int i = 0; i < R; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * lda + k);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) b[q] = *reinterpret_cast<const float4*>(b0 + (k + q) * ldb);
-    }
-#endif
-#pragma unroll
-    for (int i = 0; i < R; ++i) {
-      const float av[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        acc[i][0] = fmaf(av[q], b[q].x, acc[i][0]);
-        acc[i][1] = fmaf(av[q], b[q].y, acc[i][1]);
-        acc[i][2] = fmaf(av[q], b[q].z, acc[i][2]);
-        acc[i][3] = fmaf(av[q], b[q].w, acc[i][3]);
-      }
-    }
-#if CWN_MMA_PIPELINE
-#pragma unroll
-    for (int i = 0; i < R; ++i) a[i] = an[i];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) b[q] = bn[q];
-#endif
   }
+#else
+  for (int k = 0; k < inner4; k += 4) {
+    if (k > 0) fetch(a, b, k);
+    mma_step<R>(a, b, acc);
+  }
+#endif
 }
 
 // f_in(X)[row][k] for the (possibly concatenated, possibly BatchNorm+activation-transformed) unit input.
@@ -213,6 +214,18 @@ __device__ __forceinline__ void load_input_tile(const D& d, const float* vin, in
       dst[r * ldd + kk] = v;
     }
   }
+}
+
+// The descriptor of this CTA's problem, copied once from the kernel-parameter (constant) space to shared memory:
+// the Group<> parameter block is 2-3 KB, each CTA needs ~300 B of it, and touching its fields one by one through
+// dynamically indexed LDC exposed one constant-cache miss after the other at the top of the kernel.
+template <class D>
+__device__ __forceinline__ const D& stage_desc(const Group<D>& g, int p, D* sd) {
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&g.d[p]);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(sd);
+  for (int i = threadIdx.x; i < (int)(sizeof(D) / 4); i += DT) dst[i] = src[i];
+  __syncthreads();
+  return *sd;
 }
 
 // "last CTA done" hand-off: every CTA of a problem publishes its partials, bumps the problem's counter, and the one
@@ -309,12 +322,13 @@ __device__ __forceinline__ void bn_finalize_body(const float* stats, int n_tiles
 
 // ------------------------------------------------------------------------------------------------ forward unit
 template <int TR, int A_IN>  // tile rows: 64 or 32; input activation: compile-time code or kActRuntime
-__global__ void __launch_bounds__(DT, 3) linear_fwd_kernel(const __grid_constant__ Group<cwn_linear_desc> g) {
+__global__ void __launch_bounds__(DT, 2) linear_fwd_kernel(const __grid_constant__ Group<cwn_linear_desc> g) {
   constexpr int TM = TR;
   constexpr int R = TR / 16;
   extern __shared__ __align__(16) float smem[];
+  __shared__ cwn_linear_desc sd;
   const int p = find_problem(g, blockIdx.x);
-  const cwn_linear_desc& d = g.d[p];
+  const cwn_linear_desc& d = stage_desc(g, p, &sd);
   const int t = blockIdx.x - g.start[p];
   const int col_tiles = (d.h + TN - 1) / TN;
   const int rt = t / col_tiles, ct = t % col_tiles;
@@ -548,8 +562,9 @@ __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_kernel(const __
   constexpr int R = TR / 16;      // rows per thread of the input-gradient tile
   constexpr int LDR = TR + 4;     // leading dimension of g_z^T (inner dimension = rows)
   extern __shared__ __align__(16) float smem[];
+  __shared__ cwn_unit_bwd_desc sd;
   const int p = find_problem(g, blockIdx.x);
-  const cwn_unit_bwd_desc& d = g.d[p];
+  const cwn_unit_bwd_desc& d = stage_desc(g, p, &sd);
   const int j = blockIdx.x - g.start[p];
   const int K = d.k0 + d.k1, K4 = round4(K), H4 = round4(d.h), ldg = H4 + 4;
   const int m_tiles = (d.h + 63) / 64;
@@ -567,6 +582,9 @@ __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_kernel(const __
   const bool w_vec = ((reinterpret_cast<uintptr_t>(d.w) & 15u) == 0) && (d.ld_w % 4 == 0) && (K % 4 == 0);
   const bool g_vec = ((reinterpret_cast<uintptr_t>(d.z) & 15u) == 0) && (d.ld_z % 4 == 0) && (d.h % 4 == 0) &&
                      ((reinterpret_cast<uintptr_t>(d.g_out) & 15u) == 0) && (d.ld_g % 4 == 0);
+  const bool gi_vec = (d.k0 % 4 == 0) && (d.k1 % 4 == 0) &&
+                      (!d.g_in0 || (((reinterpret_cast<uintptr_t>(d.g_in0) & 15u) == 0) && d.ld_gi0 % 4 == 0)) &&
+                      (!d.g_in1 || (((reinterpret_cast<uintptr_t>(d.g_in1) & 15u) == 0) && d.ld_gi1 % 4 == 0));
 
   stage_input_vectors(d, vin, K, K4);
   for (int c = tid; c < H4; c += DT) {
@@ -675,13 +693,20 @@ __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_kernel(const __
       if (d.g_in0 || d.g_in1) {  // input gradient chunk: [TM rows] x [64 k] = Gz [TM x h] * Ws [h x 64]
         float acc[R][4] = {};
         tile_mma<R>(Gz, ldg, Ws, LDT, H4, ty, tx, acc);
+        const int kq = kc + tx * 4;  // first of this thread's four columns
 #pragma unroll
         for (int i = 0; i < R; ++i) {
           const int r = ty * R + i;
           if (r >= rows) continue;
+          if (gi_vec && kq + 3 < K) {  // the four columns lie in one block (k0 % 4 == 0): one 128-bit store
+            float* base = (kq < d.k0) ? (d.g_in0 ? d.g_in0 + (row0 + r) * d.ld_gi0 + kq : nullptr)
+                                      : (d.g_in1 ? d.g_in1 + (row0 + r) * d.ld_gi1 + (kq - d.k0) : nullptr);
+            if (base) *reinterpret_cast<float4*>(base) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            continue;
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const int k = kc + tx * 4 + q;
+            const int k = kq + q;
             if (k >= K) continue;
             if (k < d.k0) { if (d.g_in0) d.g_in0[(row0 + r) * d.ld_gi0 + k] = acc[i][q]; }
             else if (d.g_in1) d.g_in1[(row0 + r) * d.ld_gi1 + (k - d.k0)] = acc[i][q];
