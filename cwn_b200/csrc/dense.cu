@@ -21,11 +21,34 @@
 #ifndef CWN_MMA_PIPELINE
 #define CWN_MMA_PIPELINE 1  // register double-buffering of the shared-memory operands in tile_mma
 #endif
+#ifndef CWN_FWD_MIN_CTAS
+#define CWN_FWD_MIN_CTAS 3  // __launch_bounds__ occupancy target of linear_fwd_kernel: the 408 CTAs of the real-data
+                            // shape fit ONE wave (2 CTAs/SM made it two: 29.6 us vs 14.7 us at 304 CTAs); 80 registers
+#endif
 #ifndef CWN_BWD_MIN_CTAS
 #define CWN_BWD_MIN_CTAS 2  // __launch_bounds__ occupancy target of unit_bwd_kernel (caps registers at 128)
 #endif
 
 namespace cwn {
+
+// Profiling aid (variant build -DCWN_PHASE_TIMING only): thread 0 of every CTA stamps clock64() at phase boundaries
+// into a caller-provided buffer [CTA][16]; slot 15 holds %globaltimer at CTA start. tools/phase_timing.py reads it.
+#ifdef CWN_PHASE_TIMING
+__device__ long long* g_phase_buf = nullptr;
+#define CWN_PHASE(i)                                                                    \
+  do {                                                                                  \
+    if (threadIdx.x == 0 && g_phase_buf) {                                              \
+      g_phase_buf[(size_t)blockIdx.x * 16 + (i)] = clock64();                           \
+      if ((i) == 0) {                                                                   \
+        unsigned long long t_;                                                          \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                          \
+        g_phase_buf[(size_t)blockIdx.x * 16 + 15] = (long long)t_;                      \
+      }                                                                                 \
+    }                                                                                   \
+  } while (0)
+#else
+#define CWN_PHASE(i)
+#endif
 
 constexpr int TM = 64;    // rows per tile (large problems); small ones use 32-row tiles for twice the CTAs
 constexpr int TN = 64;    // columns per tile
@@ -219,8 +242,10 @@ __device__ __forceinline__ void load_input_tile(const D& d, const float* vin, in
 // The descriptor of this CTA's problem, copied once from the kernel-parameter (constant) space to shared memory:
 // the Group<> parameter block is 2-3 KB, each CTA needs ~300 B of it, and touching its fields one by one through
 // dynamically indexed LDC exposed one constant-cache miss after the other at the top of the kernel.
+// The copy is then read BY VALUE into registers: a reference into shared memory made the compiler re-load fields
+// (k0, x0, ld_x0 ...) after every barrier and inside the tile loaders.
 template <class D>
-__device__ __forceinline__ const D& stage_desc(const Group<D>& g, int p, D* sd) {
+__device__ __forceinline__ D stage_desc(const Group<D>& g, int p, D* sd) {
   const uint32_t* src = reinterpret_cast<const uint32_t*>(&g.d[p]);
   uint32_t* dst = reinterpret_cast<uint32_t*>(sd);
   for (int i = threadIdx.x; i < (int)(sizeof(D) / 4); i += DT) dst[i] = src[i];
@@ -230,17 +255,133 @@ __device__ __forceinline__ const D& stage_desc(const Group<D>& g, int p, D* sd) 
 
 // "last CTA done" hand-off: every CTA of a problem publishes its partials, bumps the problem's counter, and the one
 // that observes the final count runs the (cheap, ordered => deterministic) merge. Saves a dependent launch.
+// Release/acquire through ONE thread: the CTA barrier orders every thread's partial stores before thread 0's
+// device-scope fence + counter increment (causality is cumulative, the pattern cooperative-groups grid.sync uses);
+// 256 fences per CTA were measured at ~2 000 cycles.
 __device__ __forceinline__ bool last_cta_of_problem(int32_t* counter, int total) {
   __shared__ int s_last;
-  __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1) == total - 1);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int last = (atomicAdd(counter, 1) == total - 1);
+    if (last) __threadfence();
+    s_last = last;
+  }
   __syncthreads();
-  if (s_last) __threadfence();
   return s_last != 0;
 }
 
-constexpr int kStageFloats = 8192;  // 32 KB of per-tile partials staged in shared memory at a time
+constexpr int kStageFloats = 8192;  // 32 KB of per-tile partials staged in shared memory at a time (generic path)
+
+// Ordered merge of per-tile records [n_tiles][2][h] by ONE CTA (the last one of a problem) — the serial tail of the
+// launch, so it is built to cost one batched round trip to L2: thread (q, g) owns float4 q of the record and the
+// tiles g, g + G, ... (G = DT / (h/2)); up to kMergeT tiles per thread stay in registers between the two passes of
+// the BatchNorm merge. (The first version staged the records through shared memory with scalar loads in a rolled
+// loop: ~26 dependent L2 round trips, 17 800 cycles = half of the whole forward kernel at the real-data shape.)
+constexpr int kMergeT = 16;
+
+struct MergeMap {
+  int P, G, q, g;
+  bool live;
+  __device__ __forceinline__ MergeMap(int h) {
+    P = h / 2;
+    G = DT / P;
+    q = threadIdx.x % P;
+    g = threadIdx.x / P;
+    live = g < G;
+  }
+};
+
+__device__ __forceinline__ bool merge_fast_ok(const float* partials, int h) {
+  return (h % 4 == 0) && (h / 2 <= DT) && ((reinterpret_cast<uintptr_t>(partials) & 15u) == 0);
+}
+
+__device__ __forceinline__ void merge_load(const MergeMap& m, const float* partials, int h, int n_tiles, int base,
+                                           float4 (&v)[kMergeT]) {
+#pragma unroll
+  for (int j = 0; j < kMergeT; ++j) {
+    const int t = base + m.g + j * m.G;
+    v[j] = (m.live && t < n_tiles) ? __ldcg(reinterpret_cast<const float4*>(partials + (int64_t)t * 2 * h) + m.q)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// column totals of comb[G][2h]: thread c < 2h sums its column over the G groups in order
+__device__ __forceinline__ float merge_column(const float* comb, int G, int h2, int c) {
+  float t = 0.f;
+  for (int g = 0; g < G; ++g) t += comb[g * h2 + c];
+  return t;
+}
+
+// Exact group-combination of the per-tile (mean, M2): returns (mean, M2) of column threadIdx.x (< h) over all rows.
+__device__ __forceinline__ void bn_merge_fast(const float* stats, int n_tiles, int64_t n_rows, int h, int tile_rows,
+                                              float* comb /*[4 DT]*/, float* meanv /*[DT]*/, float& mean, float& m2) {
+  const MergeMap m(h);
+  const bool is_mean = m.q < h / 4;
+  const int round = m.G * kMergeT;
+  const bool single = n_tiles <= round;
+  float4 v[kMergeT];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto count = [&](int t) {
+    const int64_t left = n_rows - (int64_t)t * tile_rows;
+    return (float)(left < tile_rows ? (left > 0 ? left : 0) : tile_rows);
+  };
+  for (int base = 0; base < n_tiles; base += round) {
+    merge_load(m, stats, h, n_tiles, base, v);
+#pragma unroll
+    for (int j = 0; j < kMergeT; ++j) {
+      const float w = is_mean ? count(base + m.g + j * m.G) : 1.f;  // sum of cnt * mean_t | sum of M2_t
+      acc.x = fmaf(w, v[j].x, acc.x); acc.y = fmaf(w, v[j].y, acc.y);
+      acc.z = fmaf(w, v[j].z, acc.z); acc.w = fmaf(w, v[j].w, acc.w);
+    }
+  }
+  if (m.live) reinterpret_cast<float4*>(comb)[m.g * m.P + m.q] = acc;
+  __syncthreads();
+  float m2a = 0.f;
+  if (threadIdx.x < h) {
+    mean = merge_column(comb, m.G, 2 * h, threadIdx.x) / (float)n_rows;
+    m2a = merge_column(comb, m.G, 2 * h, h + threadIdx.x);
+    meanv[threadIdx.x] = mean;
+  }
+  __syncthreads();
+  acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (is_mean && m.live) {
+    const float4 mu = reinterpret_cast<const float4*>(meanv)[m.q];
+    for (int base = 0; base < n_tiles; base += round) {
+      if (!single) merge_load(m, stats, h, n_tiles, base, v);
+#pragma unroll
+      for (int j = 0; j < kMergeT; ++j) {
+        const float w = count(base + m.g + j * m.G);  // 0 for tiles past the end
+        const float dx = v[j].x - mu.x, dy = v[j].y - mu.y, dz = v[j].z - mu.z, dw = v[j].w - mu.w;
+        acc.x = fmaf(w * dx, dx, acc.x); acc.y = fmaf(w * dy, dy, acc.y);
+        acc.z = fmaf(w * dz, dz, acc.z); acc.w = fmaf(w * dw, dw, acc.w);
+      }
+    }
+    reinterpret_cast<float4*>(comb)[m.g * m.P + m.q] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < h) m2 = m2a + merge_column(comb, m.G, 2 * h, threadIdx.x);
+}
+
+// Plain ordered column sums of [n_tiles][2][h] records: (s1, s2) of column threadIdx.x (< h).
+__device__ __forceinline__ void sums_merge_fast(const float* partials, int n_tiles, int h, float* comb, float& s1,
+                                                float& s2) {
+  const MergeMap m(h);
+  const int round = m.G * kMergeT;
+  float4 v[kMergeT];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int base = 0; base < n_tiles; base += round) {
+    merge_load(m, partials, h, n_tiles, base, v);
+#pragma unroll
+    for (int j = 0; j < kMergeT; ++j) acc = f4_add(acc, v[j]);
+  }
+  if (m.live) reinterpret_cast<float4*>(comb)[m.g * m.P + m.q] = acc;
+  __syncthreads();
+  if (threadIdx.x < h) {
+    s1 = merge_column(comb, m.G, 2 * h, threadIdx.x);
+    s2 = merge_column(comb, m.G, 2 * h, h + threadIdx.x);
+  }
+}
 
 // BatchNorm statistics of one problem from the per-tile (mean, M2) partials (training) or the running statistics.
 // `stage`: kStageFloats floats of shared memory. Column = threadIdx.x (h <= DT).
@@ -249,7 +390,27 @@ __device__ __forceinline__ void bn_finalize_body(const float* stats, int n_tiles
                                                  float* running_var, int64_t* nbt, float* mean_out, float* scale_out,
                                                  float* rstd_out, float* stage, int stage_floats = kStageFloats,
                                                  int tile_rows = TM) {
-  if (training) {
+  if (training && merge_fast_ok(stats, h)) {
+    __shared__ __align__(16) float comb[4 * DT];
+    __shared__ __align__(16) float meanv[DT];
+    float mean = 0.f, m2 = 0.f;
+    __syncthreads();
+    bn_merge_fast(stats, n_tiles, n_rows, h, tile_rows, comb, meanv, mean, m2);
+    if (threadIdx.x < h) {
+      const int c = threadIdx.x;
+      const float var = m2 / (float)n_rows;
+      const float rstd = 1.f / sqrtf(var + eps);
+      if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      if (running_var) {
+        const float unbiased = n_rows > 1 ? m2 / (float)(n_rows - 1) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+      }
+      mean_out[c] = mean;
+      rstd_out[c] = rstd;
+      scale_out[c] = gamma ? gamma[c] * rstd : rstd;
+    }
+    if (threadIdx.x == 0 && nbt) *nbt += 1;
+  } else if (training) {
     // Exact group-combination of the per-tile (mean, M2):  mean = SUM cnt_t mean_t / N,
     //   M2 = SUM [M2_t + cnt_t (mean_t - mean)^2]  — two passes of plain ordered sums (deterministic). A sequential
     // Chan merge was measured first: its dependent chain of two IEEE divisions per tile, run by ONE CTA after all the
@@ -322,13 +483,15 @@ __device__ __forceinline__ void bn_finalize_body(const float* stats, int n_tiles
 
 // ------------------------------------------------------------------------------------------------ forward unit
 template <int TR, int A_IN>  // tile rows: 64 or 32; input activation: compile-time code or kActRuntime
-__global__ void __launch_bounds__(DT, 2) linear_fwd_kernel(const __grid_constant__ Group<cwn_linear_desc> g) {
+__global__ void __launch_bounds__(DT, CWN_FWD_MIN_CTAS) linear_fwd_kernel(const __grid_constant__ Group<cwn_linear_desc> g) {
   constexpr int TM = TR;
   constexpr int R = TR / 16;
   extern __shared__ __align__(16) float smem[];
   __shared__ cwn_linear_desc sd;
+  CWN_PHASE(0);
   const int p = find_problem(g, blockIdx.x);
-  const cwn_linear_desc& d = stage_desc(g, p, &sd);
+  const cwn_linear_desc d = stage_desc(g, p, &sd);
+  CWN_PHASE(1);
   const int t = blockIdx.x - g.start[p];
   const int col_tiles = (d.h + TN - 1) / TN;
   const int rt = t / col_tiles, ct = t % col_tiles;
@@ -371,10 +534,13 @@ __global__ void __launch_bounds__(DT, 2) linear_fwd_kernel(const __grid_constant
     }
   }
   __syncthreads();  // vin ready
+  CWN_PHASE(2);
   load_input_tile<A_IN>(d, vin, K, K4, row0, rows, 0, K4, As, lda, input_vec_ok(d), TM);
   __syncthreads();
+  CWN_PHASE(3);
   float acc[R][4] = {};
   tile_mma<R>(As, lda, Bs, LDT, K4, ty, tx, acc);
+  CWN_PHASE(4);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int c = col0 + tx * 4 + j;
@@ -403,6 +569,7 @@ __global__ void __launch_bounds__(DT, 2) linear_fwd_kernel(const __grid_constant
     return;
   }
   __syncthreads();  // As/Bs are dead: reuse the front of shared memory for the output tile
+  CWN_PHASE(5);
   float* Ys = smem;              // [TM][LDT]
   float* red = smem + TM * LDT;  // [4][TN]
 #pragma unroll
@@ -428,37 +595,83 @@ __global__ void __launch_bounds__(DT, 2) linear_fwd_kernel(const __grid_constant
     d.stats[((int64_t)rt * 2 + 0) * d.h + col0 + c] = mean;
     d.stats[((int64_t)rt * 2 + 1) * d.h + col0 + c] = ((red[c] + red[TN + c]) + red[2 * TN + c]) + red[3 * TN + c];
   }
+  CWN_PHASE(6);
   if (d.bn_mean && d.counter) {
     const int total = g.start[p + 1] - g.start[p];
-    if (last_cta_of_problem(d.counter, total)) {
+    const bool last_ = last_cta_of_problem(d.counter, total);
+    CWN_PHASE(7);
+    if (last_) {
       const int n_tiles = (int)((d.n_rows + TM - 1) / TM);
       bn_finalize_body(d.stats, n_tiles, d.n_rows, d.h, d.bn_gamma, d.bn_eps, d.bn_momentum, 1, d.bn_running_mean,
                        d.bn_running_var, d.bn_num_batches_tracked, d.bn_mean, d.bn_scale, d.bn_rstd, smem,
                        TM * lda + K4 * LDT, TM);  // (this problem's share of the dynamic shared memory)
       if (threadIdx.x == 0) *d.counter = 0;
+      CWN_PHASE(8);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ BN statistics
 __global__ void __launch_bounds__(DT) bn_finalize_kernel(const __grid_constant__ Group<cwn_bn_desc> g) {
-  __shared__ float stage[kStageFloats];
+  __shared__ __align__(16) float stage[kStageFloats];
   const cwn_bn_desc& d = g.d[blockIdx.x];
   bn_finalize_body(d.stats, d.n_tiles, d.n_rows, d.h, d.gamma, d.eps, d.momentum, d.training, d.running_mean,
                    d.running_var, d.num_batches_tracked, d.mean, d.scale, d.rstd, stage, kStageFloats,
                    d.tile_rows > 0 ? d.tile_rows : TM);
 }
 
-__global__ void __launch_bounds__(DT) bn_act_kernel(const __grid_constant__ Group<cwn_bn_act_desc> g) {
+// out = act((z - mean) * scale + beta): the layer output the neighbours gather from. One float4 per thread per
+// step, every load of a step issued before the first use (the scalar version with an out-of-line activation call
+// serialised 16 L2 round trips per thread: 9.5 us for 1.6 MB).
+constexpr int kBnActV4 = 512;  // float4 elements per CTA on the vector path
+template <int ACT>
+__global__ void __launch_bounds__(DT) bn_act_kernel(const __grid_constant__ Group<cwn_bn_act_desc> g, int vec) {
   const int p = find_problem(g, blockIdx.x);
   const cwn_bn_act_desc& d = g.d[p];
+  if (vec) {
+    const int h4 = d.h / 4;
+    const int64_t total = d.n_rows * h4;
+    const int64_t i0 = (int64_t)(blockIdx.x - g.start[p]) * kBnActV4 + threadIdx.x;
+    constexpr int NB = kBnActV4 / DT;
+    float4 z[NB], mu[NB], sc[NB], be[NB];
+    int64_t off_out[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int64_t i = i0 + (int64_t)j * DT;
+      const int64_t r = i / h4;
+      const int c = (int)(i - r * h4) * 4;
+      off_out[j] = -1;
+      if (i < total) {
+        z[j] = __ldcg(reinterpret_cast<const float4*>(d.z + r * d.ld_z + c));
+        if (d.scale) {
+          mu[j] = __ldcg(reinterpret_cast<const float4*>(d.mean + c));
+          sc[j] = __ldcg(reinterpret_cast<const float4*>(d.scale + c));
+          be[j] = d.beta ? ldg_f4(d.beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        off_out[j] = r * d.ld_out + c;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      if (off_out[j] < 0) continue;
+      float4 v = z[j];
+      if (d.scale) {
+        v.x = (v.x - mu[j].x) * sc[j].x + be[j].x; v.y = (v.y - mu[j].y) * sc[j].y + be[j].y;
+        v.z = (v.z - mu[j].z) * sc[j].z + be[j].z; v.w = (v.w - mu[j].w) * sc[j].w + be[j].w;
+      }
+      v.x = act_apply<ACT>(d.act, v.x); v.y = act_apply<ACT>(d.act, v.y);
+      v.z = act_apply<ACT>(d.act, v.z); v.w = act_apply<ACT>(d.act, v.w);
+      *reinterpret_cast<float4*>(d.out + off_out[j]) = v;
+    }
+    return;
+  }
   const int64_t row0 = (int64_t)(blockIdx.x - g.start[p]) * TM;
   const int rows = (int)((d.n_rows - row0 < TM) ? d.n_rows - row0 : TM);
   for (int i = threadIdx.x; i < rows * d.h; i += DT) {
     const int r = i / d.h, c = i % d.h;
     float v = d.z[(row0 + r) * d.ld_z + c];
     if (d.scale) v = (v - d.mean[c]) * d.scale[c] + (d.beta ? d.beta[c] : 0.f);
-    d.out[(row0 + r) * d.ld_out + c] = act_apply_rt(d.act, v);
+    d.out[(row0 + r) * d.ld_out + c] = act_apply<ACT>(d.act, v);
   }
 }
 
@@ -483,7 +696,12 @@ __device__ __forceinline__ void unit_bwd_finalize_body(const cwn_unit_bwd_desc& 
   const int per_tile = 2 * d.h;
   const int chunk = kStageFloats / per_tile > 0 ? kStageFloats / per_tile : 1;
   float s1 = 0.f, s2 = 0.f;  // column threadIdx.x
-  for (int t0 = 0; t0 < n_tiles; t0 += chunk) {
+  const bool fast = merge_fast_ok(d.red_partials, d.h);
+  if (fast) {
+    __syncthreads();
+    sums_merge_fast(d.red_partials, n_tiles, d.h, stage, s1, s2);  // stage: >= 4 DT floats
+  }
+  for (int t0 = 0; t0 < n_tiles && !fast; t0 += chunk) {
     const int nt = (n_tiles - t0 < chunk) ? n_tiles - t0 : chunk;
     __syncthreads();
     for (int i = threadIdx.x; i < nt * per_tile; i += DT) stage[i] = __ldcg(d.red_partials + (int64_t)t0 * per_tile + i);
@@ -539,7 +757,7 @@ __global__ void __launch_bounds__(DT) unit_bwd_reduce_kernel(const __grid_consta
     __syncthreads();
   }
   if (d.counter) {
-    __shared__ float stage[kStageFloats];
+    __shared__ __align__(16) float stage[kStageFloats];
     if (last_cta_of_problem(d.counter, g.start[p + 1] - g.start[p])) {
       unit_bwd_finalize_body(d, stage, TM);
       if (threadIdx.x == 0) *d.counter = 0;
@@ -548,7 +766,7 @@ __global__ void __launch_bounds__(DT) unit_bwd_reduce_kernel(const __grid_consta
 }
 
 __global__ void __launch_bounds__(DT) unit_bwd_finalize_kernel(const __grid_constant__ Group<cwn_unit_bwd_desc> g) {
-  __shared__ float stage[kStageFloats];
+  __shared__ __align__(16) float stage[kStageFloats];
   const cwn_unit_bwd_desc& d = g.d[blockIdx.x];
   if (!d.has_bn) return;
   unit_bwd_finalize_body(d, stage, d.tile_rows > 0 ? d.tile_rows : TM);
@@ -563,8 +781,10 @@ __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_kernel(const __
   constexpr int LDR = TR + 4;     // leading dimension of g_z^T (inner dimension = rows)
   extern __shared__ __align__(16) float smem[];
   __shared__ cwn_unit_bwd_desc sd;
+  CWN_PHASE(0);
   const int p = find_problem(g, blockIdx.x);
-  const cwn_unit_bwd_desc& d = stage_desc(g, p, &sd);
+  const cwn_unit_bwd_desc d = stage_desc(g, p, &sd);
+  CWN_PHASE(1);
   const int j = blockIdx.x - g.start[p];
   const int K = d.k0 + d.k1, K4 = round4(K), H4 = round4(d.h), ldg = H4 + 4;
   const int m_tiles = (d.h + 63) / 64;
@@ -602,6 +822,7 @@ __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_kernel(const __
     const int64_t row0 = (int64_t)tile * TM;
     const int rows = (int)((d.n_rows - row0 < TM) ? d.n_rows - row0 : TM);
     __syncthreads();
+    if (first) CWN_PHASE(2);
     // g_z = scale * (g_out act'(y) - c1 - zhat c2) of this tile (plain g_out act'(z) without BatchNorm)
     if (g_vec) {
       const int nc4 = H4 / 4;
@@ -654,6 +875,7 @@ __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_kernel(const __
       }
     }
     __syncthreads();
+    if (first) CWN_PHASE(3);
     {  // transpose into GzT (lanes along r: conflict-free stores) and the bias-gradient partial (column sums)
       const int r = tid & (TM - 1);
       for (int c = tid / TM; c < d.h; c += DT / TM) GzT[c * LDR + r] = Gz[r * ldg + c];
@@ -663,6 +885,7 @@ __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_kernel(const __
         bpart[c] = first ? s_ : bpart[c] + s_;
       }
     }
+    if (first) CWN_PHASE(4);
     for (int kc = 0; kc < K; kc += TN) {
       __syncthreads();
       if (w_vec) {  // W[c][kc + k], natural layout
@@ -690,6 +913,7 @@ __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_kernel(const __
       }
       load_input_tile<A_IN>(d, vin, K, K4, row0, rows, kc, TN, Ain, LDT, in_vec, TM);
       __syncthreads();
+      if (first && kc == 0) CWN_PHASE(5);
       if (d.g_in0 || d.g_in1) {  // input gradient chunk: [TM rows] x [64 k] = Gz [TM x h] * Ws [h x 64]
         float acc[R][4] = {};
         tile_mma<R>(Gz, ldg, Ws, LDT, H4, ty, tx, acc);
@@ -713,6 +937,7 @@ __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_kernel(const __
           }
         }
       }
+      if (first && kc == 0) CWN_PHASE(6);
       for (int mt = 0; mt < m_tiles; ++mt) {  // weight gradient chunk: [64 c] x [64 k] = GzT [64 x TM] * Ain [TM x 64]
         float acc[4][4] = {};
         tile_mma<4>(GzT + mt * 64 * LDR, LDR, Ain, LDT, TM, ty, tx, acc);
@@ -729,14 +954,58 @@ __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_kernel(const __
           }
         }
       }
+      if (first && kc == 0) CWN_PHASE(7);
     }
   }
+  CWN_PHASE(8);
 }
 
-__global__ void __launch_bounds__(DT) wgrad_finalize_kernel(const __grid_constant__ Group<cwn_unit_bwd_desc> g) {
+// Ordered sum of the per-CTA partial slabs -> dW, db. Vector path: a CTA covers 64 float4 units x 4 slab groups;
+// thread (u, sg) sums slabs sg, sg + 4, ... with batched 128-bit loads, the four group sums are combined in order.
+// (One thread per element walking ~100 slabs with scalar loads was 8-9 us per launch.)
+__global__ void __launch_bounds__(DT) wgrad_finalize_kernel(const __grid_constant__ Group<cwn_unit_bwd_desc> g, int vec) {
   const int p = find_problem(g, blockIdx.x);
   const cwn_unit_bwd_desc& d = g.d[p];
   const int K = d.k0 + d.k1;
+  if (vec) {
+    __shared__ float4 comb[3][64];
+    const int u = threadIdx.x & 63, sg = threadIdx.x >> 6;
+    const int64_t w4 = (int64_t)d.h * K / 4;
+    const int b4 = d.g_b ? d.h / 4 : 0;
+    const int64_t unit = (int64_t)(blockIdx.x - g.start[p]) * 64 + u;
+    const bool is_w = unit < w4, is_b = !is_w && unit < w4 + b4;
+    const float* src = is_w ? d.w_partials + unit * 4 : d.b_partials + (unit - w4) * 4;
+    const int64_t slab = is_w ? (int64_t)d.h * K : d.h;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (is_w || is_b) {
+      constexpr int NB = 8;
+      for (int j0 = sg; j0 < d.n_ctas; j0 += 4 * NB) {
+        float4 v[NB];
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+          const int j = j0 + 4 * q;
+          v[q] = j < d.n_ctas ? __ldcg(reinterpret_cast<const float4*>(src + (int64_t)j * slab)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < NB; ++q) acc = f4_add(acc, v[q]);
+      }
+    }
+    if (sg > 0) comb[sg - 1][u] = acc;
+    __syncthreads();
+    if (sg == 0 && (is_w || is_b)) {
+      acc = f4_add(f4_add(f4_add(acc, comb[0][u]), comb[1][u]), comb[2][u]);
+      float* dst = is_w ? d.g_w + (unit * 4 / K) * d.ld_gw + (unit * 4 % K) : d.g_b + (unit - w4) * 4;
+      if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        *d4 = d.accumulate_w ? f4_add(*d4, acc) : acc;
+      } else {
+        const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dst[e] = d.accumulate_w ? dst[e] + a[e] : a[e];
+      }
+    }
+    return;
+  }
   const int64_t i = (int64_t)(blockIdx.x - g.start[p]) * DT + threadIdx.x;
   const int64_t total = (int64_t)d.h * K;
   if (i < total) {
@@ -789,6 +1058,12 @@ static int check_group(const void* descs, int n, const char* what) {
 }  // namespace cwn
 
 using namespace cwn;
+
+#ifdef CWN_PHASE_TIMING
+extern "C" int cwn_debug_set_phase_buffer(long long* buf) {
+  return cuda_status(cudaMemcpyToSymbol(g_phase_buf, &buf, sizeof(buf)), "cwn_debug_set_phase_buffer");
+}
+#endif
 
 extern "C" int cwn_linear_fwd_grouped(const cwn_linear_desc* descs, int32_t n, cwn_stream_t stream) {
   int rc = check_group(descs, n, "cwn_linear_fwd_grouped");
@@ -851,18 +1126,27 @@ extern "C" int cwn_bn_act_grouped(const cwn_bn_act_desc* descs, int32_t n, cwn_s
   if (rc || n == 0) return rc;
   Group<cwn_bn_act_desc> g;
   g.n = n;
-  int total = 0;
+  bool vec = true;
   for (int i = 0; i < n; ++i) {
     const cwn_bn_act_desc& d = descs[i];
     if (d.h <= 0 || d.n_rows < 0) return fail(CWN_E_SHAPE, "cwn_bn_act_grouped: bad shape");
     if (d.n_rows > 0 && (!d.z || !d.out)) return fail(CWN_E_NULL, "cwn_bn_act_grouped: operand");
+    vec = vec && d.h % 4 == 0 && d.ld_z % 4 == 0 && d.ld_out % 4 == 0 && aligned16(d.z) && aligned16(d.out) &&
+          (!d.scale || (aligned16(d.mean) && aligned16(d.scale) && (!d.beta || aligned16(d.beta))));
+  }
+  int total = 0;
+  for (int i = 0; i < n; ++i) {
+    const cwn_bn_act_desc& d = descs[i];
     g.d[i] = d;
     g.start[i] = total;
-    total += (int)((d.n_rows + TM - 1) / TM);
+    total += vec ? (int)((d.n_rows * (d.h / 4) + kBnActV4 - 1) / kBnActV4) : (int)((d.n_rows + TM - 1) / TM);
   }
   g.start[n] = total;
   if (total == 0) return CWN_OK;
-  bn_act_kernel<<<total, DT, 0, (cudaStream_t)stream>>>(g);
+  const int act = group_act(descs, n, [](const cwn_bn_act_desc& d) { return d.act; });
+  if (act == CWN_ACT_ID) bn_act_kernel<CWN_ACT_ID><<<total, DT, 0, (cudaStream_t)stream>>>(g, (int)vec);
+  else if (act == CWN_ACT_RELU) bn_act_kernel<CWN_ACT_RELU><<<total, DT, 0, (cudaStream_t)stream>>>(g, (int)vec);
+  else bn_act_kernel<kActRuntime><<<total, DT, 0, (cudaStream_t)stream>>>(g, (int)vec);
   return launched("bn_act_kernel");
 }
 
@@ -960,15 +1244,22 @@ extern "C" int cwn_wgrad_finalize_grouped(const cwn_unit_bwd_desc* descs, int32_
   Group<cwn_unit_bwd_desc> g;
   int rc = load_bwd_group(descs, n, g, "cwn_wgrad_finalize_grouped");
   if (rc || n == 0) return rc;
-  int total = 0;
+  bool vec = true;
   for (int i = 0; i < n; ++i) {
     const cwn_unit_bwd_desc& d = g.d[i];
     if (!d.g_w) return fail(CWN_E_NULL, "cwn_wgrad_finalize_grouped: g_w");
+    vec = vec && (d.k0 + d.k1) % 4 == 0 && d.h % 4 == 0 && aligned16(d.w_partials) && aligned16(d.b_partials);
+  }
+  int total = 0;
+  for (int i = 0; i < n; ++i) {
+    const cwn_unit_bwd_desc& d = g.d[i];
     g.start[i] = total;
-    if (d.n_ctas > 0) total += (int)(((int64_t)d.h * (d.k0 + d.k1) + d.h + DT - 1) / DT);
+    if (d.n_ctas <= 0) continue;
+    const int64_t elems = (int64_t)d.h * (d.k0 + d.k1) + d.h;
+    total += vec ? (int)((elems / 4 + 63) / 64) : (int)((elems + DT - 1) / DT);
   }
   g.start[n] = total;
   if (total == 0) return CWN_OK;
-  wgrad_finalize_kernel<<<total, DT, 0, (cudaStream_t)stream>>>(g);
+  wgrad_finalize_kernel<<<total, DT, 0, (cudaStream_t)stream>>>(g, (int)vec);
   return launched("wgrad_finalize_kernel");
 }

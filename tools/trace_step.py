@@ -44,18 +44,16 @@ def main():
         step(i)
     torch.cuda.synchronize()
     with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
-        for i in range(3):
-            step(i)
-            torch.cuda.synchronize()
-    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
-    evs.sort(key=lambda e: e.time_range.start)
-    # split into the three replays by the largest gaps
-    starts = [e.time_range.start for e in evs]
-    gaps = sorted(range(1, len(evs)), key=lambda i: starts[i] - evs[i - 1].time_range.end, reverse=True)[:2]
-    cut = sorted(gaps)
-    step = evs[cut[0]:cut[1]]  # the middle replay
+        step(0)
+        torch.cuda.synchronize()
+    step = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    step.sort(key=lambda e: e.time_range.start)
     t0, t1 = step[0].time_range.start, max(e.time_range.end for e in step)
-    print(f'one replayed step: {len(step)} device activities, span {(t1 - t0):.1f} us')
+    print(f'one eager step: {len(step)} device activities, span {(t1 - t0):.1f} us')
+    if os.environ.get('CWN_TRACE_TIMELINE'):
+        for e in step:
+            print(f'  {e.time_range.start - t0:9.1f} +{e.time_range.end - e.time_range.start:7.2f}  '
+                  + re.sub(r'<.*', '', e.name).replace('void ', '')[:60])
     tot, cnt = collections.Counter(), collections.Counter()
     for e in step:
         name = re.sub(r'<.*', '', e.name).replace('void ', '')[:70]
