@@ -72,6 +72,7 @@ _SIGNATURES = {
     'cwn_version': (ctypes.c_char_p, []),
     'cwn_last_error_string': (ctypes.c_char_p, []),
     'cwn_launch_count': (ctypes.c_ulonglong, []),
+    'cwn_debug_force_generic_dense': (ctypes.c_int, [ctypes.c_int32]),
     'cwn_csr_plan_workspace_bytes': (ctypes.c_size_t, [_i64, _i64]),
     'cwn_csr_plan_build': (ctypes.c_int, [_c_i64p, _c_i64p, _c_i64p, _i64, _i64, _c_i32p, _c_i32p, _c_i32p,
                                           _c_i32p, _c_i32p, _vp, ctypes.c_size_t, _vp]),

@@ -17,6 +17,7 @@
 // Tensor cores are deliberately not used: TF32 (10-bit mantissa) breaks the 1e-5 rtol parity gate at K = 64..128
 // (SURVEY 7), and at the real-data shape these GEMMs are ~25 MFLOP each — launch latency, not flops, is the cost.
 #include "common.cuh"
+#include <algorithm>
 
 #ifndef CWN_MMA_PIPELINE
 #define CWN_MMA_PIPELINE 1  // register double-buffering of the shared-memory operands in tile_mma
@@ -273,12 +274,15 @@ __device__ __forceinline__ bool last_cta_of_problem(int32_t* counter, int total)
 
 constexpr int kStageFloats = 8192;  // 32 KB of per-tile partials staged in shared memory at a time (generic path)
 
-// Ordered merge of per-tile records [n_tiles][2][h] by ONE CTA (the last one of a problem) — the serial tail of the
-// launch, so it is built to cost one batched round trip to L2: thread (q, g) owns float4 q of the record and the
-// tiles g, g + G, ... (G = DT / (h/2)); up to kMergeT tiles per thread stay in registers between the two passes of
-// the BatchNorm merge. (The first version staged the records through shared memory with scalar loads in a rolled
-// loop: ~26 dependent L2 round trips, 17 800 cycles = half of the whole forward kernel at the real-data shape.)
-constexpr int kMergeT = 16;
+// Ordered merge of per-tile records [n_tiles][2][h] by ONE CTA (the last one of a problem). This is the serial tail
+// of the launch and it is COLD code (executed once, by one CTA, on an SM that has never fetched it), so it is built
+// to be both short in round trips and short in instructions: thread (q, g) owns float4 q of the record and the tiles
+// g, g + G, ... (G = DT / (h/2)), eight 128-bit loads in flight per trip of a rolled loop, ONE pass.
+//   v1 staged the records through shared memory with scalar loads: ~26 dependent L2 round trips, 17 800 cycles
+//      (half of the whole forward kernel at the real-data shape);
+//   v2 kept 16 tiles per thread in registers, fully unrolled, two passes: one round trip but ~2 000 instructions of
+//      straight-line cold code: 10 400 cycles, dominated by instruction fetch.
+constexpr int kMergeBatch = 8;  // 128-bit loads in flight per thread per trip
 
 struct MergeMap {
   int P, G, q, g;
@@ -296,86 +300,82 @@ __device__ __forceinline__ bool merge_fast_ok(const float* partials, int h) {
   return (h % 4 == 0) && (h / 2 <= DT) && ((reinterpret_cast<uintptr_t>(partials) & 15u) == 0);
 }
 
-__device__ __forceinline__ void merge_load(const MergeMap& m, const float* partials, int h, int n_tiles, int base,
-                                           float4 (&v)[kMergeT]) {
-#pragma unroll
-  for (int j = 0; j < kMergeT; ++j) {
-    const int t = base + m.g + j * m.G;
-    v[j] = (m.live && t < n_tiles) ? __ldcg(reinterpret_cast<const float4*>(partials + (int64_t)t * 2 * h) + m.q)
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-}
-
-// column totals of comb[G][2h]: thread c < 2h sums its column over the G groups in order
-__device__ __forceinline__ float merge_column(const float* comb, int G, int h2, int c) {
+// column totals of comb[G][ld]: thread c sums its column over the G groups in order
+__device__ __forceinline__ float merge_column(const float* comb, int G, int ld, int c) {
   float t = 0.f;
-  for (int g = 0; g < G; ++g) t += comb[g * h2 + c];
+  for (int g = 0; g < G; ++g) t += comb[g * ld + c];
   return t;
 }
 
-// Exact group-combination of the per-tile (mean, M2): returns (mean, M2) of column threadIdx.x (< h) over all rows.
+// Exact group-combination of the per-tile (mean, M2) in one pass about a pivot p (the mean of tile 0, i.e. a value
+// within a fraction of a standard deviation of the global mean, so nothing cancels):
+//   mean = SUM cnt_t mean_t / N,   M2 = SUM M2_t + [SUM cnt_t (mean_t - p)^2 - N (mean - p)^2].
+// Returns (mean, M2) of column threadIdx.x (< h). comb: 6 DT floats of shared memory.
 __device__ __forceinline__ void bn_merge_fast(const float* stats, int n_tiles, int64_t n_rows, int h, int tile_rows,
-                                              float* comb /*[4 DT]*/, float* meanv /*[DT]*/, float& mean, float& m2) {
+                                              float* comb, float& mean, float& m2) {
   const MergeMap m(h);
   const bool is_mean = m.q < h / 4;
-  const int round = m.G * kMergeT;
-  const bool single = n_tiles <= round;
-  float4 v[kMergeT];
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto count = [&](int t) {
-    const int64_t left = n_rows - (int64_t)t * tile_rows;
-    return (float)(left < tile_rows ? (left > 0 ? left : 0) : tile_rows);
-  };
-  for (int base = 0; base < n_tiles; base += round) {
-    merge_load(m, stats, h, n_tiles, base, v);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;  // a: SUM cnt*mean_t | SUM M2_t;  b: SUM cnt*(mean_t - p)^2
+  if (m.live) {
+    const float4* rec = reinterpret_cast<const float4*>(stats) + m.q;
+    const int h2 = h / 2;  // float4 per record
+    const float4 pv = __ldcg(rec);
+    CWN_PHASE(9);
+    for (int t0 = m.g; t0 < n_tiles; t0 += kMergeBatch * m.G) {
+      float4 v[kMergeBatch];
 #pragma unroll
-    for (int j = 0; j < kMergeT; ++j) {
-      const float w = is_mean ? count(base + m.g + j * m.G) : 1.f;  // sum of cnt * mean_t | sum of M2_t
-      acc.x = fmaf(w, v[j].x, acc.x); acc.y = fmaf(w, v[j].y, acc.y);
-      acc.z = fmaf(w, v[j].z, acc.z); acc.w = fmaf(w, v[j].w, acc.w);
-    }
-  }
-  if (m.live) reinterpret_cast<float4*>(comb)[m.g * m.P + m.q] = acc;
-  __syncthreads();
-  float m2a = 0.f;
-  if (threadIdx.x < h) {
-    mean = merge_column(comb, m.G, 2 * h, threadIdx.x) / (float)n_rows;
-    m2a = merge_column(comb, m.G, 2 * h, h + threadIdx.x);
-    meanv[threadIdx.x] = mean;
-  }
-  __syncthreads();
-  acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (is_mean && m.live) {
-    const float4 mu = reinterpret_cast<const float4*>(meanv)[m.q];
-    for (int base = 0; base < n_tiles; base += round) {
-      if (!single) merge_load(m, stats, h, n_tiles, base, v);
+      for (int j = 0; j < kMergeBatch; ++j) {
+        const int t = t0 + j * m.G;
+        v[j] = t < n_tiles ? __ldcg(rec + (int64_t)t * h2) : pv;
+      }
 #pragma unroll
-      for (int j = 0; j < kMergeT; ++j) {
-        const float w = count(base + m.g + j * m.G);  // 0 for tiles past the end
-        const float dx = v[j].x - mu.x, dy = v[j].y - mu.y, dz = v[j].z - mu.z, dw = v[j].w - mu.w;
-        acc.x = fmaf(w * dx, dx, acc.x); acc.y = fmaf(w * dy, dy, acc.y);
-        acc.z = fmaf(w * dz, dz, acc.z); acc.w = fmaf(w * dw, dw, acc.w);
+      for (int j = 0; j < kMergeBatch; ++j) {
+        const int t = t0 + j * m.G;
+        const int64_t left = n_rows - (int64_t)t * tile_rows;
+        float w = t < n_tiles ? (float)(left < tile_rows ? left : tile_rows) : 0.f;
+        if (!is_mean) w = t < n_tiles ? 1.f : 0.f;
+        a.x = fmaf(w, v[j].x, a.x); a.y = fmaf(w, v[j].y, a.y); a.z = fmaf(w, v[j].z, a.z); a.w = fmaf(w, v[j].w, a.w);
+        const float dx = v[j].x - pv.x, dy = v[j].y - pv.y, dz = v[j].z - pv.z, dw = v[j].w - pv.w;
+        b.x = fmaf(w * dx, dx, b.x); b.y = fmaf(w * dy, dy, b.y); b.z = fmaf(w * dz, dz, b.z); b.w = fmaf(w * dw, dw, b.w);
       }
     }
-    reinterpret_cast<float4*>(comb)[m.g * m.P + m.q] = acc;
+    reinterpret_cast<float4*>(comb)[m.g * m.P + m.q] = a;                    // [G][2h]
+    if (is_mean) reinterpret_cast<float4*>(comb + 4 * DT)[m.g * (h / 4) + m.q] = b;  // [G][h]
+    CWN_PHASE(10);
   }
   __syncthreads();
-  if (threadIdx.x < h) m2 = m2a + merge_column(comb, m.G, 2 * h, threadIdx.x);
+  if (threadIdx.x < h) {
+    const int c = threadIdx.x;
+    const float n = (float)n_rows;
+    mean = merge_column(comb, m.G, 2 * h, c) / n;
+    const float within = merge_column(comb, m.G, 2 * h, h + c);
+    const float about_p = merge_column(comb + 4 * DT, m.G, h, c);
+    const float dm = mean - __ldcg(stats + c);
+    m2 = within + fmaxf(about_p - n * dm * dm, 0.f);
+  }
+  CWN_PHASE(11);
 }
 
-// Plain ordered column sums of [n_tiles][2][h] records: (s1, s2) of column threadIdx.x (< h).
+// Plain ordered column sums of [n_tiles][2][h] records: (s1, s2) of column threadIdx.x (< h). comb: 4 DT floats.
 __device__ __forceinline__ void sums_merge_fast(const float* partials, int n_tiles, int h, float* comb, float& s1,
                                                 float& s2) {
   const MergeMap m(h);
-  const int round = m.G * kMergeT;
-  float4 v[kMergeT];
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int base = 0; base < n_tiles; base += round) {
-    merge_load(m, partials, h, n_tiles, base, v);
+  if (m.live) {
+    const float4* rec = reinterpret_cast<const float4*>(partials) + m.q;
+    const int h2 = h / 2;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t0 = m.g; t0 < n_tiles; t0 += kMergeBatch * m.G) {
+      float4 v[kMergeBatch];
 #pragma unroll
-    for (int j = 0; j < kMergeT; ++j) acc = f4_add(acc, v[j]);
+      for (int j = 0; j < kMergeBatch; ++j) {
+        const int t = t0 + j * m.G;
+        v[j] = t < n_tiles ? __ldcg(rec + (int64_t)t * h2) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < kMergeBatch; ++j) acc = f4_add(acc, v[j]);
+    }
+    reinterpret_cast<float4*>(comb)[m.g * m.P + m.q] = acc;
   }
-  if (m.live) reinterpret_cast<float4*>(comb)[m.g * m.P + m.q] = acc;
   __syncthreads();
   if (threadIdx.x < h) {
     s1 = merge_column(comb, m.G, 2 * h, threadIdx.x);
@@ -391,23 +391,27 @@ __device__ __forceinline__ void bn_finalize_body(const float* stats, int n_tiles
                                                  float* rstd_out, float* stage, int stage_floats = kStageFloats,
                                                  int tile_rows = TM) {
   if (training && merge_fast_ok(stats, h)) {
-    __shared__ __align__(16) float comb[4 * DT];
-    __shared__ __align__(16) float meanv[DT];
+    __shared__ __align__(16) float comb[6 * DT];
     float mean = 0.f, m2 = 0.f;
+    // requested before the merge, consumed after it (one round trip less on the serial tail)
+    const bool col = threadIdx.x < h;
+    const float rm0 = (col && running_mean) ? running_mean[threadIdx.x] : 0.f;
+    const float rv0 = (col && running_var) ? running_var[threadIdx.x] : 0.f;
+    const float gm = (col && gamma) ? gamma[threadIdx.x] : 1.f;
     __syncthreads();
-    bn_merge_fast(stats, n_tiles, n_rows, h, tile_rows, comb, meanv, mean, m2);
-    if (threadIdx.x < h) {
+    bn_merge_fast(stats, n_tiles, n_rows, h, tile_rows, comb, mean, m2);
+    if (col) {
       const int c = threadIdx.x;
       const float var = m2 / (float)n_rows;
       const float rstd = 1.f / sqrtf(var + eps);
-      if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      if (running_mean) running_mean[c] = (1.f - momentum) * rm0 + momentum * mean;
       if (running_var) {
         const float unbiased = n_rows > 1 ? m2 / (float)(n_rows - 1) : var;
-        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+        running_var[c] = (1.f - momentum) * rv0 + momentum * unbiased;
       }
       mean_out[c] = mean;
       rstd_out[c] = rstd;
-      scale_out[c] = gamma ? gamma[c] * rstd : rstd;
+      scale_out[c] = gm * rstd;
     }
     if (threadIdx.x == 0 && nbt) *nbt += 1;
   } else if (training) {
@@ -611,6 +615,207 @@ __global__ void __launch_bounds__(DT, CWN_FWD_MIN_CTAS) linear_fwd_kernel(const 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ forward, fast path
+// The same unit for the layouts the models actually produce (16-byte aligned operands, k0, k1, h multiples of 4).
+// Per-phase clock64() stamps of the first version at the real-data shape (tools/phase_timing.py) showed a CTA spending
+// its life in a chain of dependent phases — descriptor 1 400 cycles, vectors + W 3 600, X tile 2 500, FMAs 7 400,
+// stores + statistics 2 100, fence 1 800 — i.e. latency, not throughput. Here every global operand of the tile (W rows,
+// X rows, the input-transform vectors) is requested up front with cp.async and awaited ONCE; W stays in its natural
+// [n][k] layout (no transposing scatter: a thread owns columns tx, tx+16, tx+32, tx+48, rows of W (K+4 floats apart)
+// fall on distinct bank groups for 128-bit reads); the input transform runs in place in shared memory; the BatchNorm
+// partials come straight from the accumulator registers (shuffle + one small shared array) instead of a staged tile.
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* src, bool valid) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int bytes = valid ? 16 : 0;  // 0 source bytes = zero-fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+template <int TR, int A_IN>
+__global__ void __launch_bounds__(DT, CWN_FWD_MIN_CTAS) linear_fwd_fast_kernel(const __grid_constant__ Group<cwn_linear_desc> g) {
+  constexpr int R = TR / 16;
+  extern __shared__ __align__(16) float smem[];
+  __shared__ cwn_linear_desc sd;
+  __shared__ float red[8][TN];
+  __shared__ float meanv[TN];
+  CWN_PHASE(0);
+  const int p = find_problem(g, blockIdx.x);
+  const cwn_linear_desc d = stage_desc(g, p, &sd);
+  CWN_PHASE(1);
+  const int t = blockIdx.x - g.start[p];
+  const int col_tiles = (d.h + TN - 1) / TN;
+  const int rt = t / col_tiles, ct = t - rt * col_tiles;
+  const int K = d.k0 + d.k1, K4 = K / 4, ld = K + 4;
+  float* Xs = smem;             // [TR][ld]   f_in(X) tile
+  float* Ws = Xs + TR * ld;     // [TN][ld]   W[col0 + n][k]
+  float* vin = Ws + TN * ld;    // [3][K]     mean | scale | beta of the input transform
+  const int64_t row0 = (int64_t)rt * TR;
+  const int rows = (int)((d.n_rows - row0 < TR) ? d.n_rows - row0 : TR);
+  const int col0 = ct * TN;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const bool transform = d.in_scale0 || d.in_scale1 || d.in_act != CWN_ACT_ID;
+
+  for (int i = tid; i < TN * K4; i += DT) {
+    const int n = i / K4, c = (i - n * K4) * 4;
+    const bool ok = col0 + n < d.h;
+    cp_async16(Ws + n * ld + c, ok ? d.w + (int64_t)(col0 + n) * d.ld_w + c : d.w, ok);
+  }
+  for (int i = tid; i < TR * K4; i += DT) {
+    const int r = i / K4, c = (i - r * K4) * 4;
+    const bool ok = r < rows;
+    const float* src = (c < d.k0) ? d.x0 + (row0 + r) * d.ld_x0 + c : d.x1 + (row0 + r) * d.ld_x1 + (c - d.k0);
+    cp_async16(Xs + r * ld + c, ok ? src : d.x0, ok);
+  }
+  if (transform)
+    for (int i = tid; i < 3 * K4; i += DT) {
+      const int which = i / K4, c = (i - which * K4) * 4;
+      const bool first = c < d.k0;
+      const float* base = which == 0 ? (first ? d.in_mean0 : d.in_mean1)
+                        : which == 1 ? (first ? d.in_scale0 : d.in_scale1) : (first ? d.in_beta0 : d.in_beta1);
+      const bool has = first ? d.in_scale0 != nullptr : d.in_scale1 != nullptr;
+      if (has && base) {
+        cp_async16(vin + which * K + c, base + (first ? c : c - d.k0), true);
+      } else {
+        const float f = which == 1 ? 1.f : 0.f;
+        *reinterpret_cast<float4*>(vin + which * K + c) = make_float4(f, f, f, f);
+      }
+    }
+  float bias[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = col0 + tx + 16 * j;
+    bias[j] = (d.bias && c < d.h) ? __ldg(d.bias + c) : 0.f;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  CWN_PHASE(2);
+  if (transform) {
+    for (int i = tid; i < rows * K4; i += DT) {
+      const int r = i / K4, c = (i - r * K4) * 4;
+      float4 v = *reinterpret_cast<const float4*>(Xs + r * ld + c);
+      const float4 mu = *reinterpret_cast<const float4*>(vin + c);
+      const float4 sc = *reinterpret_cast<const float4*>(vin + K + c);
+      const float4 be = *reinterpret_cast<const float4*>(vin + 2 * K + c);
+      v.x = act_apply<A_IN>(d.in_act, (v.x - mu.x) * sc.x + be.x);
+      v.y = act_apply<A_IN>(d.in_act, (v.y - mu.y) * sc.y + be.y);
+      v.z = act_apply<A_IN>(d.in_act, (v.z - mu.z) * sc.z + be.z);
+      v.w = act_apply<A_IN>(d.in_act, (v.w - mu.w) * sc.w + be.w);
+      *reinterpret_cast<float4*>(Xs + r * ld + c) = v;
+    }
+    __syncthreads();
+  }
+  CWN_PHASE(3);
+  float acc[R][4] = {};
+  {
+    const float* a0 = Xs + (ty * R) * ld;
+    const float* b0 = Ws + tx * ld;
+#pragma unroll 2
+    for (int k = 0; k < K; k += 4) {
+      float4 a[R], b[4];
+#pragma unroll
+      for (int i = 0; i < R; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * ld + k);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(b0 + j * 16 * ld + k);
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i].y, b[j].y, acc[i][j]);
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]);
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
+    }
+  }
+  CWN_PHASE(4);
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const int r = ty * R + i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[i][j] += bias[j];
+      const int c = col0 + tx + 16 * j;
+      if (r < rows && c < d.h) d.z[(row0 + r) * d.ld_z + c] = acc[i][j];
+    }
+  }
+  CWN_PHASE(5);
+  if (!d.stats) {
+    if (d.bn_mean && !d.bn_training && blockIdx.x == g.start[p])  // eval: statistics are the running ones
+      bn_finalize_body(nullptr, 0, d.n_rows, d.h, d.bn_gamma, d.bn_eps, d.bn_momentum, 0, d.bn_running_mean,
+                       d.bn_running_var, nullptr, d.bn_mean, d.bn_scale, d.bn_rstd, nullptr);
+    return;
+  }
+  {  // per-column (mean, M2) of this tile from the accumulators: rows of a thread, the lane 16 apart, then the warps
+    const int w = tid >> 5, lane = tid & 31;
+    float sj[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v = 0.f;
+#pragma unroll
+      for (int i = 0; i < R; ++i) v += (ty * R + i < rows) ? acc[i][j] : 0.f;
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      sj[j] = v;
+    }
+    if (lane < 16)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[w][tx + 16 * j] = sj[j];
+    __syncthreads();
+    if (tid < TN) {
+      float tot = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) tot += red[q][tid];
+      meanv[tid] = tot / (float)rows;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float mu = meanv[tx + 16 * j];
+      float v = 0.f;
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const float dv = acc[i][j] - mu;
+        v = (ty * R + i < rows) ? fmaf(dv, dv, v) : v;
+      }
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      sj[j] = v;
+    }
+    if (lane < 16)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[w][tx + 16 * j] = sj[j];
+    __syncthreads();
+    if (tid < TN && col0 + tid < d.h) {
+      float m2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) m2 += red[q][tid];
+      d.stats[((int64_t)rt * 2 + 0) * d.h + col0 + tid] = meanv[tid];
+      d.stats[((int64_t)rt * 2 + 1) * d.h + col0 + tid] = m2;
+    }
+  }
+  CWN_PHASE(6);
+  if (d.bn_mean && d.counter) {
+    const int total = g.start[p + 1] - g.start[p];
+    const bool last_ = last_cta_of_problem(d.counter, total);
+    CWN_PHASE(7);
+    if (last_) {
+      const int n_tiles = (int)((d.n_rows + TR - 1) / TR);
+      bn_finalize_body(d.stats, n_tiles, d.n_rows, d.h, d.bn_gamma, d.bn_eps, d.bn_momentum, 1, d.bn_running_mean,
+                       d.bn_running_var, d.bn_num_batches_tracked, d.bn_mean, d.bn_scale, d.bn_rstd, smem,
+                       TR * ld + TN * ld, TR);
+      if (threadIdx.x == 0) *d.counter = 0;
+      CWN_PHASE(8);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ BN statistics
 __global__ void __launch_bounds__(DT) bn_finalize_kernel(const __grid_constant__ Group<cwn_bn_desc> g) {
   __shared__ __align__(16) float stage[kStageFloats];
@@ -762,6 +967,65 @@ __global__ void __launch_bounds__(DT) unit_bwd_reduce_kernel(const __grid_consta
       unit_bwd_finalize_body(d, stage, TM);
       if (threadIdx.x == 0) *d.counter = 0;
     }
+  }
+}
+
+// BN-backward column sums, vector path (h % 4 == 0, 16-byte aligned rows): thread (q, rg) owns float4 column q and the
+// rows rg, rg + RG, ... of the tile (RG = DT / (h/4) row groups) and has its 128-bit loads of z and g_out in flight
+// together (the scalar version walked 16 rows per thread four loads at a time: 8-10 us per launch at the real-data
+// shape for 3 MB of input); the row groups are then combined in order through shared memory.
+template <int TR, int A_OUT>
+__global__ void __launch_bounds__(DT) unit_bwd_reduce_fast_kernel(const __grid_constant__ Group<cwn_unit_bwd_desc> g) {
+  __shared__ __align__(16) float part[2 * 4 * DT];   // [2][RG][h], RG * h = 4 DT
+  __shared__ __align__(16) float stage[6 * DT];      // merge scratch of the last CTA
+  const int p = find_problem(g, blockIdx.x);
+  const cwn_unit_bwd_desc& d = g.d[p];
+  const int tile = blockIdx.x - g.start[p];
+  const int h = d.h, h4 = h / 4, RG = DT / h4;
+  const int64_t row0 = (int64_t)tile * TR;
+  const int rows = (int)((d.n_rows - row0 < TR) ? d.n_rows - row0 : TR);
+  const int q = threadIdx.x % h4, rg = threadIdx.x / h4;
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  if (rg < RG) {
+    const int c = q * 4;
+    const float4 mean = ldg_f4(d.mean + c), scale = ldg_f4(d.scale + c), rstd = ldg_f4(d.rstd + c);
+    const float4 beta = d.beta ? ldg_f4(d.beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* zp = d.z + row0 * d.ld_z + c;
+    const float* gp = d.g_out + row0 * d.ld_g + c;
+    constexpr int NB = 4;
+    for (int r0 = rg; r0 < rows; r0 += NB * RG) {
+      float4 zv[NB], gv[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int r = r0 + j * RG;
+        zv[j] = gv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows) {
+          zv[j] = __ldcg(reinterpret_cast<const float4*>(zp + (int64_t)r * d.ld_z));
+          gv[j] = __ldcg(reinterpret_cast<const float4*>(gp + (int64_t)r * d.ld_g));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        if (r0 + j * RG >= rows) continue;
+        float zc, gy;
+        zc = zv[j].x - mean.x; gy = gv[j].x * act_grad<A_OUT>(d.act, zc * scale.x + beta.x); s1.x += gy; s2.x = fmaf(gy, zc * rstd.x, s2.x);
+        zc = zv[j].y - mean.y; gy = gv[j].y * act_grad<A_OUT>(d.act, zc * scale.y + beta.y); s1.y += gy; s2.y = fmaf(gy, zc * rstd.y, s2.y);
+        zc = zv[j].z - mean.z; gy = gv[j].z * act_grad<A_OUT>(d.act, zc * scale.z + beta.z); s1.z += gy; s2.z = fmaf(gy, zc * rstd.z, s2.z);
+        zc = zv[j].w - mean.w; gy = gv[j].w * act_grad<A_OUT>(d.act, zc * scale.w + beta.w); s1.w += gy; s2.w = fmaf(gy, zc * rstd.w, s2.w);
+      }
+    }
+    reinterpret_cast<float4*>(part)[rg * h4 + q] = s1;
+    reinterpret_cast<float4*>(part + 4 * DT)[rg * h4 + q] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x < h) {
+    const int c = threadIdx.x;
+    d.red_partials[((int64_t)tile * 2 + 0) * h + c] = merge_column(part, RG, h, c);
+    d.red_partials[((int64_t)tile * 2 + 1) * h + c] = merge_column(part + 4 * DT, RG, h, c);
+  }
+  if (d.counter && last_cta_of_problem(d.counter, g.start[p + 1] - g.start[p])) {
+    unit_bwd_finalize_body(d, stage, TR);
+    if (threadIdx.x == 0) *d.counter = 0;
   }
 }
 
@@ -960,6 +1224,174 @@ __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_kernel(const __
   CWN_PHASE(8);
 }
 
+// ------------------------------------------------------------------------------------------------ backward, fast path
+// unit_bwd_kernel for 16-byte aligned operands with k0, k1, h multiples of 4, restructured like linear_fwd_fast_kernel:
+// W (whole), the input-transform and BatchNorm vectors are requested once, the z / g_out / X tiles of a row tile with
+// one cp.async batch; g_z is formed in place over the g_out tile; its transpose reuses the z tile's shared memory; the
+// bias partial is read off the transposed tile; weight-gradient partials leave as 128-bit stores. Same FMA order as
+// the generic kernel, so the two agree bit for bit.
+template <int TR, int A_IN, int A_OUT>
+__global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_fast_kernel(const __grid_constant__ Group<cwn_unit_bwd_desc> g) {
+  constexpr int R = TR / 16;
+  constexpr int LDR = TR + 4;
+  extern __shared__ __align__(16) float smem[];
+  __shared__ cwn_unit_bwd_desc sd;
+  CWN_PHASE(0);
+  const int p = find_problem(g, blockIdx.x);
+  const cwn_unit_bwd_desc d = stage_desc(g, p, &sd);
+  CWN_PHASE(1);
+  const int j = blockIdx.x - g.start[p];
+  const int K = d.k0 + d.k1, K4 = K / 4, ldk = K + 4, h = d.h, h4 = h / 4, ldh = h + 4;
+  const int m_tiles = (h + 63) / 64;
+  const int zt_floats = (TR * ldh > m_tiles * 64 * LDR) ? TR * ldh : m_tiles * 64 * LDR;
+  float* Gz = smem;                 // [TR][ldh]            g_out tile, then g_z
+  float* ZT = Gz + TR * ldh;        // [TR][ldh] z tile, then [m_tiles*64][LDR] g_z^T
+  float* Xs = ZT + zt_floats;       // [TR][ldk]            f_in(X)
+  float* Ws = Xs + TR * ldk;        // [h][ldk]             W
+  float* vin = Ws + h * ldk;        // [3][K]
+  float* vout = vin + 3 * K;        // [6][h]   mean, scale, rstd, beta, c1, c2
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int n_tiles = (int)((d.n_rows + TR - 1) / TR);
+  float* wpart = d.w_partials + (int64_t)j * h * K;
+  float* bpart = d.b_partials + (int64_t)j * h;
+  const bool transform = d.in_scale0 || d.in_scale1 || d.in_act != CWN_ACT_ID;
+
+  for (int i = tid; i < h * K4; i += DT) {
+    const int c = i / K4, k = (i - c * K4) * 4;
+    cp_async16(Ws + c * ldk + k, d.w + (int64_t)c * d.ld_w + k, true);
+  }
+  if (transform)
+    for (int i = tid; i < 3 * K4; i += DT) {
+      const int which = i / K4, c = (i - which * K4) * 4;
+      const bool first = c < d.k0;
+      const float* base = which == 0 ? (first ? d.in_mean0 : d.in_mean1)
+                        : which == 1 ? (first ? d.in_scale0 : d.in_scale1) : (first ? d.in_beta0 : d.in_beta1);
+      const bool has = first ? d.in_scale0 != nullptr : d.in_scale1 != nullptr;
+      if (has && base) {
+        cp_async16(vin + which * K + c, base + (first ? c : c - d.k0), true);
+      } else {
+        const float f = which == 1 ? 1.f : 0.f;
+        *reinterpret_cast<float4*>(vin + which * K + c) = make_float4(f, f, f, f);
+      }
+    }
+  for (int c = tid; c < h; c += DT) {
+    const bool live = d.has_bn;
+    vout[c] = live ? __ldg(d.mean + c) : 0.f;
+    vout[h + c] = live ? __ldg(d.scale + c) : 1.f;
+    vout[2 * h + c] = live ? __ldg(d.rstd + c) : 0.f;
+    vout[3 * h + c] = (live && d.beta) ? __ldg(d.beta + c) : 0.f;
+    vout[4 * h + c] = live ? __ldcg(d.c1 + c) : 0.f;
+    vout[5 * h + c] = live ? __ldcg(d.c2 + c) : 0.f;
+  }
+  bool first = true;
+  for (int tile = j; tile < n_tiles; tile += d.n_ctas, first = false) {
+    const int64_t row0 = (int64_t)tile * TR;
+    const int rows = (int)((d.n_rows - row0 < TR) ? d.n_rows - row0 : TR);
+    __syncthreads();  // the previous tile's readers are done with the shared tiles
+    for (int i = tid; i < TR * h4; i += DT) {
+      const int r = i / h4, c = (i - r * h4) * 4;
+      const bool ok = r < rows;
+      cp_async16(ZT + r * ldh + c, ok ? d.z + (row0 + r) * d.ld_z + c : d.z, ok);
+      cp_async16(Gz + r * ldh + c, ok ? d.g_out + (row0 + r) * d.ld_g + c : d.g_out, ok);
+    }
+    for (int i = tid; i < TR * K4; i += DT) {
+      const int r = i / K4, c = (i - r * K4) * 4;
+      const bool ok = r < rows;
+      const float* src = (c < d.k0) ? d.x0 + (row0 + r) * d.ld_x0 + c : d.x1 + (row0 + r) * d.ld_x1 + (c - d.k0);
+      cp_async16(Xs + r * ldk + c, ok ? src : d.x0, ok);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    if (first) CWN_PHASE(2);
+    // g_z = scale * (g_out act'(y) - c1 - zhat c2), in place over the g_out tile (plain g_out act'(z) without BatchNorm)
+    for (int i = tid; i < TR * h4; i += DT) {
+      const int r = i / h4, c = (i - r * h4) * 4;
+      float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows) {
+        const float4 zv = *reinterpret_cast<const float4*>(ZT + r * ldh + c);
+        const float4 gv = *reinterpret_cast<const float4*>(Gz + r * ldh + c);
+        const float zz[4] = {zv.x, zv.y, zv.z, zv.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w};
+        float o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float zc = zz[q] - vout[c + q];
+          const float gy = gg[q] * act_grad<A_OUT>(d.act, zc * vout[h + c + q] + vout[3 * h + c + q]);
+          o[q] = d.has_bn ? vout[h + c + q] * (gy - vout[4 * h + c + q] - zc * vout[2 * h + c + q] * vout[5 * h + c + q]) : gy;
+        }
+        out = make_float4(o[0], o[1], o[2], o[3]);
+      }
+      *reinterpret_cast<float4*>(Gz + r * ldh + c) = out;
+    }
+    if (transform)
+      for (int i = tid; i < rows * K4; i += DT) {
+        const int r = i / K4, c = (i - r * K4) * 4;
+        float4 v = *reinterpret_cast<const float4*>(Xs + r * ldk + c);
+        const float4 mu = *reinterpret_cast<const float4*>(vin + c);
+        const float4 sc = *reinterpret_cast<const float4*>(vin + K + c);
+        const float4 be = *reinterpret_cast<const float4*>(vin + 2 * K + c);
+        v.x = act_apply<A_IN>(d.in_act, (v.x - mu.x) * sc.x + be.x);
+        v.y = act_apply<A_IN>(d.in_act, (v.y - mu.y) * sc.y + be.y);
+        v.z = act_apply<A_IN>(d.in_act, (v.z - mu.z) * sc.z + be.z);
+        v.w = act_apply<A_IN>(d.in_act, (v.w - mu.w) * sc.w + be.w);
+        *reinterpret_cast<float4*>(Xs + r * ldk + c) = v;
+      }
+    __syncthreads();
+    if (first) CWN_PHASE(3);
+    {  // transpose g_z into the (dead) z tile; rows c >= h of the last 64-row block are zero
+      const int r = tid & (TR - 1);
+      for (int c = tid / TR; c < m_tiles * 64; c += DT / TR) ZT[c * LDR + r] = c < h ? Gz[r * ldh + c] : 0.f;
+    }
+    __syncthreads();
+    if (first) CWN_PHASE(4);
+    if (tid < h) {  // bias-gradient partial = column sums of g_z, rows in order
+      const float4* row = reinterpret_cast<const float4*>(ZT + tid * LDR);
+      float s_ = 0.f;
+#pragma unroll 4
+      for (int q = 0; q < TR / 4; ++q) {
+        const float4 v = row[q];
+        s_ += v.x; s_ += v.y; s_ += v.z; s_ += v.w;
+      }
+      bpart[tid] = first ? s_ : bpart[tid] + s_;
+    }
+    for (int kc = 0; kc < K; kc += TN) {
+      if (d.g_in0 || d.g_in1) {  // input gradient chunk: [TR rows] x [64 k] = Gz [TR x h] * Ws [h x 64]
+        float acc[R][4] = {};
+        tile_mma<R>(Gz, ldh, Ws + kc, ldk, h, ty, tx, acc);
+        const int kq = kc + tx * 4;
+        if (kq < K) {
+          float* base = (kq < d.k0) ? (d.g_in0 ? d.g_in0 + row0 * d.ld_gi0 + kq : nullptr)
+                                    : (d.g_in1 ? d.g_in1 + row0 * d.ld_gi1 + (kq - d.k0) : nullptr);
+          const int64_t ldo = (kq < d.k0) ? d.ld_gi0 : d.ld_gi1;
+          if (base)
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+              const int r = ty * R + i;
+              if (r < rows) *reinterpret_cast<float4*>(base + r * ldo) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            }
+        }
+      }
+      if (first && kc == 0) CWN_PHASE(5);
+      for (int mt = 0; mt < m_tiles; ++mt) {  // weight gradient chunk: [64 c] x [64 k] = GzT [64 x TR] * Xs [TR x 64]
+        float acc[4][4] = {};
+        tile_mma<4>(ZT + mt * 64 * LDR, LDR, Xs + kc, ldk, TR, ty, tx, acc);
+        const int k = kc + tx * 4;
+        if (k < K)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c = mt * 64 + ty * 4 + i;
+            if (c >= h) continue;
+            float4* dst = reinterpret_cast<float4*>(wpart + (int64_t)c * K + k);
+            float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            if (!first) v = f4_add(*dst, v);
+            *dst = v;
+          }
+      }
+      if (first && kc == 0) CWN_PHASE(6);
+    }
+  }
+  CWN_PHASE(8);
+}
+
 // Ordered sum of the per-CTA partial slabs -> dW, db. Vector path: a CTA covers 64 float4 units x 4 slab groups;
 // thread (u, sg) sums slabs sg, sg + 4, ... with batched 128-bit loads, the four group sums are combined in order.
 // (One thread per element walking ~100 slabs with scalar loads was 8-9 us per launch.)
@@ -1059,6 +1491,14 @@ static int check_group(const void* descs, int n, const char* what) {
 
 using namespace cwn;
 
+// Test hook: route every grouped dense call through the generic (any shape / alignment) kernels, so the parity tests
+// can compare the two paths on the same inputs.
+static int g_force_generic_dense = 0;  // bit 0: forward entry points, bit 1: backward entry points
+extern "C" int cwn_debug_force_generic_dense(int32_t mask) {
+  g_force_generic_dense = mask;
+  return CWN_OK;
+}
+
 #ifdef CWN_PHASE_TIMING
 extern "C" int cwn_debug_set_phase_buffer(long long* buf) {
   return cuda_status(cudaMemcpyToSymbol(g_phase_buf, &buf, sizeof(buf)), "cwn_debug_set_phase_buffer");
@@ -1089,6 +1529,36 @@ extern "C" int cwn_linear_fwd_grouped(const cwn_linear_desc* descs, int32_t n, c
   g.start[n] = total;
   if (total == 0) return CWN_OK;
   const int a_in = group_act(descs, n, [](const cwn_linear_desc& d) { return d.in_act; });
+  bool fast = !(g_force_generic_dense & 1);
+  size_t smem_fast = 0;
+  for (int i = 0; i < n && fast; ++i) {
+    const cwn_linear_desc& d = descs[i];
+    if (d.n_rows == 0) continue;
+    auto vec_ok = [](const float* a, const float* b, const float* c) { return aligned16(a) && aligned16(b) && aligned16(c); };
+    fast = d.k0 % 4 == 0 && d.k1 % 4 == 0 && aligned16(d.x0) && d.ld_x0 % 4 == 0 &&
+           (d.k1 == 0 || (aligned16(d.x1) && d.ld_x1 % 4 == 0)) && aligned16(d.w) && d.ld_w % 4 == 0 &&
+           (!d.in_scale0 || vec_ok(d.in_mean0, d.in_scale0, d.in_beta0)) &&
+           (!d.in_scale1 || vec_ok(d.in_mean1, d.in_scale1, d.in_beta1)) &&
+           (!d.stats || (d.h % 4 == 0 && aligned16(d.stats)));
+    const int K = d.k0 + d.k1;
+    const size_t need = ((size_t)(tr + TN) * (K + 4) + 3 * (size_t)K) * sizeof(float);
+    if (need > smem_fast) smem_fast = need;
+  }
+  if (fast && smem_fast <= 200 * 1024) {
+#define CWN_LAUNCH_FAST(TRV, AV)                                                                                   \
+  {                                                                                                                \
+    if ((rc = ensure_smem(linear_fwd_fast_kernel<TRV, AV>, smem_fast, "cudaFuncSetAttribute(linear_fwd_fast_kernel)"))) return rc; \
+    linear_fwd_fast_kernel<TRV, AV><<<total, DT, smem_fast, (cudaStream_t)stream>>>(g);                            \
+  }
+#define CWN_FAST_BY_ACT(TRV)                                     \
+  if (a_in == CWN_ACT_ID) CWN_LAUNCH_FAST(TRV, CWN_ACT_ID)       \
+  else if (a_in == CWN_ACT_RELU) CWN_LAUNCH_FAST(TRV, CWN_ACT_RELU) \
+  else CWN_LAUNCH_FAST(TRV, kActRuntime)
+    if (tr == 64) { CWN_FAST_BY_ACT(64) } else { CWN_FAST_BY_ACT(32) }
+#undef CWN_FAST_BY_ACT
+#undef CWN_LAUNCH_FAST
+    return launched("linear_fwd_fast_kernel");
+  }
 #define CWN_LAUNCH_FWD(TRV, AV)                                                                             \
   {                                                                                                         \
     if ((rc = ensure_smem(linear_fwd_kernel<TRV, AV>, smem, "cudaFuncSetAttribute(linear_fwd_kernel)"))) return rc; \
@@ -1178,6 +1648,23 @@ extern "C" int cwn_unit_bwd_reduce_grouped(const cwn_unit_bwd_desc* descs, int32
   g.start[n] = total;
   if (total == 0) return CWN_OK;
   const int a_out = group_act(descs, n, [](const cwn_unit_bwd_desc& d) { return d.act; });
+  bool fast = !(g_force_generic_dense & 2);
+  for (int i = 0; i < n && fast; ++i) {
+    const cwn_unit_bwd_desc& d = g.d[i];
+    if (!d.has_bn || d.n_rows == 0) continue;
+    fast = d.h % 4 == 0 && aligned16(d.z) && d.ld_z % 4 == 0 && aligned16(d.g_out) && d.ld_g % 4 == 0 &&
+           aligned16(d.mean) && aligned16(d.scale) && aligned16(d.rstd) && (!d.beta || aligned16(d.beta)) &&
+           aligned16(d.red_partials);
+  }
+  if (fast) {
+#define CWN_REDF(TRV)                                                                                              \
+  if (a_out == CWN_ACT_ID) unit_bwd_reduce_fast_kernel<TRV, CWN_ACT_ID><<<total, DT, 0, (cudaStream_t)stream>>>(g);    \
+  else if (a_out == CWN_ACT_RELU) unit_bwd_reduce_fast_kernel<TRV, CWN_ACT_RELU><<<total, DT, 0, (cudaStream_t)stream>>>(g); \
+  else unit_bwd_reduce_fast_kernel<TRV, kActRuntime><<<total, DT, 0, (cudaStream_t)stream>>>(g);
+    if (tr == 64) { CWN_REDF(64) } else { CWN_REDF(32) }
+#undef CWN_REDF
+    return launched("unit_bwd_reduce_fast_kernel");
+  }
 #define CWN_RED(TRV)                                                                                          \
   if (a_out == CWN_ACT_ID) unit_bwd_reduce_kernel<TRV, CWN_ACT_ID><<<total, DT, 0, (cudaStream_t)stream>>>(g);    \
   else if (a_out == CWN_ACT_RELU) unit_bwd_reduce_kernel<TRV, CWN_ACT_RELU><<<total, DT, 0, (cudaStream_t)stream>>>(g); \
@@ -1220,6 +1707,48 @@ extern "C" int cwn_unit_bwd_grouped(const cwn_unit_bwd_desc* descs, int32_t n, c
   if (total == 0) return CWN_OK;
   const int a_in = group_act(descs, n, [](const cwn_unit_bwd_desc& d) { return d.in_act; });
   const int a_out = group_act(descs, n, [](const cwn_unit_bwd_desc& d) { return d.act; });
+  bool fast = !(g_force_generic_dense & 2);
+  size_t smem_fast = 0;
+  for (int i = 0; i < n && fast; ++i) {
+    const cwn_unit_bwd_desc& d = g.d[i];
+    if (d.n_rows == 0) continue;
+    auto vec_ok = [](const float* a, const float* b, const float* c) { return aligned16(a) && aligned16(b) && aligned16(c); };
+    const int K = d.k0 + d.k1;
+    fast = d.k0 % 4 == 0 && d.k1 % 4 == 0 && d.h % 4 == 0 && aligned16(d.x0) && d.ld_x0 % 4 == 0 &&
+           (d.k1 == 0 || (aligned16(d.x1) && d.ld_x1 % 4 == 0)) && aligned16(d.w) && d.ld_w % 4 == 0 &&
+           aligned16(d.z) && d.ld_z % 4 == 0 && aligned16(d.g_out) && d.ld_g % 4 == 0 &&
+           (!d.in_scale0 || vec_ok(d.in_mean0, d.in_scale0, d.in_beta0)) &&
+           (!d.in_scale1 || vec_ok(d.in_mean1, d.in_scale1, d.in_beta1)) &&
+           (!d.g_in0 || (aligned16(d.g_in0) && d.ld_gi0 % 4 == 0)) && (!d.g_in1 || (aligned16(d.g_in1) && d.ld_gi1 % 4 == 0)) &&
+           aligned16(d.w_partials);
+    const int m_tiles = (d.h + 63) / 64;
+    const size_t zt = std::max((size_t)tr * (d.h + 4), (size_t)m_tiles * 64 * (tr + 4));
+    // (+64: the 64-column chunks of the two products may read past column K of the last row; those lanes' results
+    // are never stored, but the reads must stay inside the allocation)
+    const size_t need = ((size_t)tr * (d.h + 4) + zt + (size_t)tr * (K + 4) + (size_t)d.h * (K + 4) + 3 * (size_t)K +
+                         6 * (size_t)d.h + 64) * sizeof(float);
+    if (need > smem_fast) smem_fast = need;
+  }
+  if (fast && smem_fast <= 210 * 1024) {
+#define CWN_LAUNCH_BWDF(TRV, AI, AO)                                                                              \
+  {                                                                                                               \
+    if ((rc = ensure_smem(unit_bwd_fast_kernel<TRV, AI, AO>, smem_fast, "cudaFuncSetAttribute(unit_bwd_fast_kernel)"))) return rc; \
+    unit_bwd_fast_kernel<TRV, AI, AO><<<total, DT, smem_fast, (cudaStream_t)stream>>>(g);                         \
+  }
+#define CWN_BWDF_BY_OUT(TRV, AI)                                     \
+  if (a_out == CWN_ACT_ID) CWN_LAUNCH_BWDF(TRV, AI, CWN_ACT_ID)      \
+  else if (a_out == CWN_ACT_RELU) CWN_LAUNCH_BWDF(TRV, AI, CWN_ACT_RELU) \
+  else CWN_LAUNCH_BWDF(TRV, AI, kActRuntime)
+#define CWN_BWDF_BY_IN(TRV)                                      \
+  if (a_in == CWN_ACT_ID) { CWN_BWDF_BY_OUT(TRV, CWN_ACT_ID) }   \
+  else if (a_in == CWN_ACT_RELU) { CWN_BWDF_BY_OUT(TRV, CWN_ACT_RELU) } \
+  else { CWN_BWDF_BY_OUT(TRV, kActRuntime) }
+    if (tr == 64) { CWN_BWDF_BY_IN(64) } else { CWN_BWDF_BY_IN(32) }
+#undef CWN_BWDF_BY_IN
+#undef CWN_BWDF_BY_OUT
+#undef CWN_LAUNCH_BWDF
+    return launched("unit_bwd_fast_kernel");
+  }
 #define CWN_LAUNCH_BWD(TRV, AI, AO)                                                                          \
   {                                                                                                          \
     if ((rc = ensure_smem(unit_bwd_kernel<TRV, AI, AO>, smem, "cudaFuncSetAttribute(unit_bwd_kernel)"))) return rc; \

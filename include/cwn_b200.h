@@ -51,6 +51,10 @@ const char* cwn_version(void);
 const char* cwn_last_error_string(void);
 /* number of kernels this library has launched in this process (for bench.py's gpu_launches) */
 unsigned long long cwn_launch_count(void);
+/* test hook: route the grouped dense entry points through their generic (any shape / alignment) kernels instead of
+ * the fast path for 16-byte aligned operands, so the two can be compared on the same inputs. Process-wide.
+ * mask bit 0: cwn_linear_fwd_grouped, bit 1: cwn_unit_bwd_grouped; 0 restores the default. */
+int cwn_debug_force_generic_dense(int32_t mask);
 
 /* ---------------------------------------------------------------------------------------------------------
  * CSR plan: group the E messages of one adjacency by one of its columns.
