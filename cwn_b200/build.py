@@ -33,16 +33,47 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _compile(srcs, out, defines=(), verbose=False, force=False):
+    """Each source to its own object (in parallel, skipped when the object is newer than the source, every header and
+    the flags), then one link step. Objects live in csrc/_obj/ (git-ignored, gpurun-ignored)."""
+    from concurrent.futures import ThreadPoolExecutor
+    tag = '_'.join(sorted(d.replace('=', '-') for d in defines)) or 'default'
+    objdir = os.path.join(CSRC, '_obj', tag)
+    os.makedirs(objdir, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))]
+    headers += [os.path.join(ROOT, 'include', 'cwn_b200.h'), os.path.abspath(__file__)]
+    newest_header = max(os.path.getmtime(h) for h in headers)
+    flags = [f for f in NVCC_FLAGS if f != '-shared'] + [f'-D{d}' for d in defines]
+
+    def one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + '.o')
+        if (not force and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(src)
+                and os.path.getmtime(obj) > newest_header):
+            return obj, ''
+        cmd = [_nvcc()] + flags + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError('cwn_b200: nvcc failed\n' + ' '.join(cmd) + '\n' + proc.stdout + proc.stderr)
+        return obj, proc.stderr
+
+    with ThreadPoolExecutor(max_workers=len(srcs)) as pool:
+        results = list(pool.map(one, srcs))
+    cmd = [_nvcc(), '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-Xcompiler', '-fPIC', '-o', out + '.tmp'] + \
+          [o for o, _ in results]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError('cwn_b200: link failed\n' + proc.stdout + proc.stderr)
+    os.replace(out + '.tmp', out)
+    if verbose:
+        print(''.join(log for _, log in results))
+    return out
+
+
 def build_variant(name, defines):
     """Profiling aid: an alternative build of the library (`libcwn_b200_<name>.so`) with extra -D flags; select it
     at run time with CWN_B200_LIB=<path>."""
     out = os.path.join(CSRC, f'libcwn_b200_{name}.so')
-    srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    cmd = [_nvcc()] + NVCC_FLAGS + [f'-D{d}' for d in defines] + ['-o', out] + srcs
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError('cwn_b200: nvcc failed\n' + proc.stdout + proc.stderr)
-    return out
+    return _compile([os.path.join(CSRC, s) for s in SOURCES], out, defines=tuple(defines))
 
 
 def build_library(force=False, verbose=False):
@@ -51,14 +82,7 @@ def build_library(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB + '.tmp'] + srcs
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError('cwn_b200: nvcc failed\n' + ' '.join(cmd) + '\n' + proc.stdout + proc.stderr)
-    os.replace(LIB + '.tmp', LIB)
-    if verbose:
-        print(proc.stderr)
-    return LIB
+    return _compile(srcs, LIB, verbose=verbose, force=force)
 
 
 if __name__ == '__main__':

@@ -22,27 +22,192 @@ template <> struct VecOps<float4> {
   static constexpr int W = 4;
   static __device__ __forceinline__ float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
   static __device__ __forceinline__ float4 load(const float* p) { return ldg_f4(p); }
+  static __device__ __forceinline__ float4 load(const char* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
   static __device__ __forceinline__ void store(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+  static __device__ __forceinline__ void store(char* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
   template <class Fn> static __device__ __forceinline__ float4 map2(float4 a, float4 b, Fn f) {
     return make_float4(f(a.x, b.x), f(a.y, b.y), f(a.z, b.z), f(a.w, b.w));
   }
   template <class Fn> static __device__ __forceinline__ float4 map3(float4 a, float4 b, float4 c, Fn f) {
     return make_float4(f(a.x, b.x, c.x), f(a.y, b.y, c.y), f(a.z, b.z, c.z), f(a.w, b.w, c.w));
   }
+  // IEEE round-to-nearest adds, two lanes per instruction (sm_100 FADD2): same bits as four __fadd_rn, half the
+  // issue slots — these kernels are issue-bound long before they are FP32-pipe bound
+  static __device__ __forceinline__ float4 add(float4 a, float4 b) {
+    const float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    const float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+  }
+  // a + s * b with the product rounded before the sum (two roundings, like the reference's separate ops). The
+  // products stay scalar __fmul_rn: ptxas contracts __fmul2_rn + __fadd2_rn into one FFMA2 (seen in the SASS), which
+  // would round once.
+  static __device__ __forceinline__ float4 add_scaled(float4 a, float s, float4 b) {
+    const float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(__fmul_rn(s, b.x), __fmul_rn(s, b.y)));
+    const float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(__fmul_rn(s, b.z), __fmul_rn(s, b.w)));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+  }
 };
 template <> struct VecOps<float> {
   static constexpr int W = 1;
   static __device__ __forceinline__ float zero() { return 0.f; }
   static __device__ __forceinline__ float load(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ float load(const char* p) { return __ldg(reinterpret_cast<const float*>(p)); }
   static __device__ __forceinline__ void store(float* p, float v) { *p = v; }
+  static __device__ __forceinline__ void store(char* p, float v) { *reinterpret_cast<float*>(p) = v; }
   template <class Fn> static __device__ __forceinline__ float map2(float a, float b, Fn f) { return f(a, b); }
   template <class Fn> static __device__ __forceinline__ float map3(float a, float b, float c, Fn f) {
     return f(a, b, c);
   }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float add_scaled(float a, float s, float b) { return __fadd_rn(a, __fmul_rn(s, b)); }
 };
 
 struct AddRn { __device__ __forceinline__ float operator()(float a, float b) const { return __fadd_rn(a, b); } };
 struct MaxOp { __device__ __forceinline__ float operator()(float a, float b) const { return fmaxf(a, b); } };
+
+// Address of row `row` seen from a lane's base pointer: ONE IMAD.WIDE.U32 (32-bit row x 32-bit pitch + 64-bit base).
+// ncu on the first version of these kernels: 60 % issue-slot utilisation at 24 % of DRAM throughput, ~95 SASS
+// instructions per two-message trip of which 24 were FP and 8 loads — the rest was 64-bit index arithmetic
+// (int64 row x int64 ld), -1 sentinels carried as 64-bit values, and per-vector column predicates. Rows and pitches
+// are validated to fit 32 bits by the entry points.
+// (lane bases are passed through `opaque()` so that the compiler keeps base + lane offset in one 64-bit register instead
+// of re-adding the kernel parameter after every multiply)
+template <class T> __device__ __forceinline__ T* opaque(T* p) {
+  asm volatile("" : "+l"(p));
+  return p;
+}
+__device__ __forceinline__ const char* row_at(const char* lane_base, uint32_t row, uint32_t pitch_bytes) {
+  uint64_t a;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(row), "r"(pitch_bytes), "l"(lane_base));
+  return reinterpret_cast<const char*>(a);
+}
+__device__ __forceinline__ char* row_at(char* lane_base, uint32_t row, uint32_t pitch_bytes) {
+  return lane_base + (uint64_t)row * pitch_bytes;
+}
+
+// ---------------------------------------------------------------------------------------------- row bodies
+// One destination row, one column block; messages [beg, end) visited in plan order, U gathers (x operands) in flight.
+// `idx_at(m)` yields the payload of message m (global plan, or its shared-memory copy in the tile-staged kernels);
+// `ld(row, k)` yields vector k of a lane's share of feature row `row` (global memory, or the feature window a
+// tile-staged kernel holds in shared memory). `live1`: the second vector of a lane (VPL == 2) is inside the row.
+
+template <typename V, int LPR>
+struct GlobalRows {  // rows of a matrix in global memory, read through the read-only path
+  const char* base;  // lane base: matrix + lane's column offset
+  uint32_t pitch;
+  __device__ __forceinline__ V operator()(uint32_t row, int k) const {
+    return VecOps<V>::load(row_at(base, row, pitch) + k * LPR * (int)sizeof(V));
+  }
+};
+
+template <typename V, int LPR>
+struct SharedRows;  // rows of a feature window staged in shared memory (128-bit path only)
+template <int LPR>
+struct SharedRows<float4, LPR> {
+  uint32_t base;  // shared-space address of the lane's share of row 0 of the MATRIX (window base - lo * rowbytes)
+  uint32_t rowbytes;
+  __device__ __forceinline__ float4 operator()(uint32_t row, int k) const {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(base + row * rowbytes + (uint32_t)(k * LPR * 16)));
+    return v;
+  }
+};
+
+template <typename V, int VPL, int REDUCE, int U, class Ld, class Idx>
+__device__ __forceinline__ void gather_row(V (&acc)[VPL], int beg, int end, Ld ld, Idx idx_at, bool live1) {
+  using O = VecOps<V>;
+  for (int i = beg; i < end; i += U) {
+    V v[U][VPL];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i + u < end) {
+        const uint32_t s_ = (uint32_t)idx_at(i + u);
+        v[u][0] = ld(s_, 0);
+        if (VPL == 2 && live1) v[u][VPL - 1] = ld(s_, 1);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i + u < end) {
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          if (REDUCE == CWN_REDUCE_MAX) acc[k] = (i + u == beg) ? v[u][k] : O::map2(acc[k], v[u][k], MaxOp());
+          else acc[k] = O::add(acc[k], v[u][k]);
+        }
+      }
+    }
+  }
+}
+
+template <typename V, int VPL, int ACT, int U, class LdP, class LdQ, class IdxS, class IdxQ>
+__device__ __forceinline__ void cob_fwd_row(V (&acc)[VPL], int beg, int end, LdP ldp, LdQ ldq, IdxS src_at,
+                                            IdxQ cob_at, bool live1) {
+  using O = VecOps<V>;
+  for (int i = beg; i < end; i += U) {
+    V vp[U][VPL], vq[U][VPL];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i + u < end) {
+        const uint32_t s_ = (uint32_t)src_at(i + u), q_ = (uint32_t)cob_at(i + u);
+        vp[u][0] = ldp(s_, 0);
+        vq[u][0] = ldq(q_, 0);
+        if (VPL == 2 && live1) {
+          vp[u][VPL - 1] = ldp(s_, 1);
+          vq[u][VPL - 1] = ldq(q_, 1);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i + u < end) {
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          V pre = O::add(vp[u][k], vq[u][k]);
+          pre = O::map2(pre, pre, [](float x, float) { return act_fwd<ACT>(x); });
+          acc[k] = O::add(acc[k], pre);
+        }
+      }
+    }
+  }
+}
+
+template <typename V, int VPL, int ACT, int U, class LdG, class LdB, class IdxT, class IdxO>
+__device__ __forceinline__ void cob_bwd_row(V (&acc)[VPL], const V (&a)[VPL], int beg, int end, LdG ldg_, LdB ldb,
+                                            IdxT dst_at, IdxO oth_at, bool live1) {
+  using O = VecOps<V>;
+  for (int i = beg; i < end; i += U) {
+    V vg[U][VPL], vb[U][VPL];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i + u < end) {
+        const uint32_t t_ = (uint32_t)dst_at(i + u), o_ = (uint32_t)oth_at(i + u);
+        vg[u][0] = ldg_(t_, 0);
+        vb[u][0] = ldb(o_, 0);
+        if (VPL == 2 && live1) {
+          vg[u][VPL - 1] = ldg_(t_, 1);
+          vb[u][VPL - 1] = ldb(o_, 1);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i + u < end) {
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          V pre = O::add(a[k], vb[u][k]);
+          if (ACT == CWN_ACT_RELU) {  // g * {0,1} as a select (what torch's threshold_backward does)
+            acc[k] = O::add(acc[k], O::map2(vg[u][k], pre, [](float g_, float z) { return z > 0.f ? g_ : 0.f; }));
+          } else {
+            V d = O::map2(pre, pre, [](float z, float) { return act_bwd<ACT>(z); });
+            acc[k] = O::add(acc[k], O::map2(vg[u][k], d, [](float g_, float d_) { return __fmul_rn(g_, d_); }));
+          }
+        }
+      }
+    }
+  }
+}
 
 // out[r] = (1+eps) * x_res[r] + REDUCE_i x_src[idx ? idx[i] : i]
 template <typename V, int LPR, int VPL, int REDUCE>
@@ -56,49 +221,34 @@ csr_gather_reduce_kernel(const float* __restrict__ x_src, int64_t ld_src, const 
   const int lane = threadIdx.x % LPR;
   const int sub = threadIdx.x / LPR;
   const float scale = x_res ? __fadd_rn(1.f, eps ? __ldg(eps) : 0.f) : 0.f;
-  for (int64_t r = (int64_t)blockIdx.x * RPB + sub; r < n_rows; r += (int64_t)gridDim.x * RPB) {
-    const int beg = __ldg(rowptr + r), end = __ldg(rowptr + r + 1);
-    for (int c0 = 0; c0 < FV; c0 += LPR * VPL) {  // one trip unless F > 4*32*VPL
+  const uint32_t pitch_s = (uint32_t)ld_src * 4u, pitch_r = (uint32_t)ld_res * 4u, pitch_o = (uint32_t)ld_out * 4u;
+  for (int c0 = 0; c0 < FV; c0 += LPR * VPL) {  // one trip unless F > 4*32*VPL
+    const int c = c0 + lane;
+    if (c >= FV) return;  // (no warp-level primitive below: idle lanes of a narrow row may leave)
+    const bool live1 = VPL == 2 && c + LPR < FV;
+    const char* xs = opaque(reinterpret_cast<const char*>(x_src) + (size_t)c * sizeof(V));
+    const char* xr = opaque(reinterpret_cast<const char*>(x_res) + (size_t)c * sizeof(V));
+    char* xo = reinterpret_cast<char*>(out) + (size_t)c * sizeof(V);
+    for (int64_t r = (int64_t)blockIdx.x * RPB + sub; r < n_rows; r += (int64_t)gridDim.x * RPB) {
+      const int beg = __ldg(rowptr + r), end = __ldg(rowptr + r + 1);
       V acc[VPL];
 #pragma unroll
       for (int k = 0; k < VPL; ++k) acc[k] = O::zero();
-      for (int i = beg; i < end; i += kUnroll) {
-        int64_t s[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) s[u] = (i + u < end) ? (idx ? (int64_t)__ldg(idx + i + u) : (int64_t)(i + u)) : -1;
-        V v[kUnroll][VPL];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-#pragma unroll
-          for (int k = 0; k < VPL; ++k) {
-            const int c = c0 + lane + k * LPR;
-            if (s[u] >= 0 && c < FV) v[u][k] = O::load(x_src + s[u] * ld_src + (int64_t)c * O::W);
-          }
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-#pragma unroll
-          for (int k = 0; k < VPL; ++k) {
-            const int c = c0 + lane + k * LPR;
-            if (s[u] >= 0 && c < FV) {
-              if (REDUCE == CWN_REDUCE_MAX) acc[k] = (i + u == beg) ? v[u][k] : O::map2(acc[k], v[u][k], MaxOp());
-              else acc[k] = O::map2(acc[k], v[u][k], AddRn());
-            }
-          }
-      }
+      const GlobalRows<V, LPR> ldx{xs, pitch_s};
+      constexpr int U = (VPL == 1) ? kUnroll : kUnroll / 2;  // same number of 128-bit gathers in flight per lane
+      if (idx) gather_row<V, VPL, REDUCE, U>(acc, beg, end, ldx, [&](int m) { return __ldg(idx + m); }, live1);
+      else gather_row<V, VPL, REDUCE, U>(acc, beg, end, ldx, [](int m) { return m; }, live1);
 #pragma unroll
       for (int k = 0; k < VPL; ++k) {
-        const int c = c0 + lane + k * LPR;
-        if (c >= FV) continue;
+        if (k == 1 && !live1) break;
         V a = acc[k];
         if (REDUCE == CWN_REDUCE_MEAN) {
           const float cnt = (float)max(end - beg, 1);
           a = O::map2(a, a, [cnt](float x, float) { return __fdiv_rn(x, cnt); });
         }
-        if (x_res) {  // GIN residual added after the aggregation, as mp/layers.py:191-192 does
-          V xr = O::load(x_res + r * ld_res + (int64_t)c * O::W);
-          a = O::map2(a, xr, [scale](float s_, float x) { return __fadd_rn(s_, __fmul_rn(scale, x)); });
-        }
-        O::store(out + r * ld_out + (int64_t)c * O::W, a);
+        // GIN residual added after the aggregation, as mp/layers.py:191-192 does
+        if (x_res) a = O::add_scaled(a, scale, O::load(row_at(xr, (uint32_t)r, pitch_r) + k * LPR * (int)sizeof(V)));
+        O::store(row_at(xo, (uint32_t)r, pitch_o) + k * LPR * (int)sizeof(V), a);
       }
     }
   }
@@ -190,56 +340,33 @@ csr_cob_fwd_kernel(const float* __restrict__ P, int64_t ld_p, const float* __res
                    int64_t ld_res, const float* __restrict__ eps, float* __restrict__ out, int64_t ld_out) {
   using O = VecOps<V>;
   constexpr int RPB = kThreads / LPR;
-  constexpr int U = 2;  // two operands per message: 2*U gathers in flight
+  constexpr int U = (VPL == 1) ? 4 : 2;  // two operands per message: 2*U*VPL gathers in flight
   const int lane = threadIdx.x % LPR;
   const int sub = threadIdx.x / LPR;
   const float scale = x_res ? __fadd_rn(1.f, eps ? __ldg(eps) : 0.f) : 0.f;
-  for (int64_t r = (int64_t)blockIdx.x * RPB + sub; r < n_rows; r += (int64_t)gridDim.x * RPB) {
-    const int beg = __ldg(rowptr + r), end = __ldg(rowptr + r + 1);
-    for (int c0 = 0; c0 < FV; c0 += LPR * VPL) {
+  const uint32_t pitch_p = (uint32_t)ld_p * 4u, pitch_q = (uint32_t)ld_q * 4u, pitch_r = (uint32_t)ld_res * 4u,
+                 pitch_o = (uint32_t)ld_out * 4u;
+  for (int c0 = 0; c0 < FV; c0 += LPR * VPL) {
+    const int c = c0 + lane;
+    if (c >= FV) return;
+    const bool live1 = VPL == 2 && c + LPR < FV;
+    const char* pl = opaque(reinterpret_cast<const char*>(P) + (size_t)c * sizeof(V));
+    const char* ql = opaque(reinterpret_cast<const char*>(Q) + (size_t)c * sizeof(V));
+    const char* xr = opaque(reinterpret_cast<const char*>(x_res) + (size_t)c * sizeof(V));
+    char* xo = reinterpret_cast<char*>(out) + (size_t)c * sizeof(V);
+    for (int64_t r = (int64_t)blockIdx.x * RPB + sub; r < n_rows; r += (int64_t)gridDim.x * RPB) {
+      const int beg = __ldg(rowptr + r), end = __ldg(rowptr + r + 1);
       V acc[VPL];
 #pragma unroll
       for (int k = 0; k < VPL; ++k) acc[k] = O::zero();
-      for (int i = beg; i < end; i += U) {
-        int64_t s[U], q[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const bool ok = i + u < end;
-          s[u] = ok ? (int64_t)__ldg(src + i + u) : -1;
-          q[u] = ok ? (int64_t)__ldg(cob + i + u) : -1;
-        }
-        V vp[U][VPL], vq[U][VPL];
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-          for (int k = 0; k < VPL; ++k) {
-            const int c = c0 + lane + k * LPR;
-            if (s[u] >= 0 && c < FV) {
-              vp[u][k] = O::load(P + s[u] * ld_p + (int64_t)c * O::W);
-              vq[u][k] = O::load(Q + q[u] * ld_q + (int64_t)c * O::W);
-            }
-          }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-          for (int k = 0; k < VPL; ++k) {
-            const int c = c0 + lane + k * LPR;
-            if (s[u] >= 0 && c < FV)
-              acc[k] = O::map3(acc[k], vp[u][k], vq[u][k], [](float a, float p, float q_) {
-                return __fadd_rn(a, act_fwd<ACT>(__fadd_rn(p, q_)));
-              });
-          }
-      }
+      cob_fwd_row<V, VPL, ACT, U>(acc, beg, end, GlobalRows<V, LPR>{pl, pitch_p}, GlobalRows<V, LPR>{ql, pitch_q},
+                                  [&](int m) { return __ldg(src + m); }, [&](int m) { return __ldg(cob + m); }, live1);
 #pragma unroll
       for (int k = 0; k < VPL; ++k) {
-        const int c = c0 + lane + k * LPR;
-        if (c >= FV) continue;
+        if (k == 1 && !live1) break;
         V a = acc[k];
-        if (x_res) {
-          V xr = O::load(x_res + r * ld_res + (int64_t)c * O::W);
-          a = O::map2(a, xr, [scale](float s_, float x) { return __fadd_rn(s_, __fmul_rn(scale, x)); });
-        }
-        O::store(out + r * ld_out + (int64_t)c * O::W, a);
+        if (x_res) a = O::add_scaled(a, scale, O::load(row_at(xr, (uint32_t)r, pitch_r) + k * LPR * (int)sizeof(V)));
+        O::store(row_at(xo, (uint32_t)r, pitch_o) + k * LPR * (int)sizeof(V), a);
       }
     }
   }
@@ -254,55 +381,34 @@ csr_cob_bwd_kernel(const float* __restrict__ G, int64_t ld_g, const float* __res
                    float* __restrict__ gA, int64_t ld_ga) {
   using O = VecOps<V>;
   constexpr int RPB = kThreads / LPR;
-  constexpr int U = 2;
+  constexpr int U = (VPL == 1) ? 4 : 2;
   const int lane = threadIdx.x % LPR;
   const int sub = threadIdx.x / LPR;
-  for (int64_t r = (int64_t)blockIdx.x * RPB + sub; r < n_rows; r += (int64_t)gridDim.x * RPB) {
-    const int beg = __ldg(rowptr + r), end = __ldg(rowptr + r + 1);
-    for (int c0 = 0; c0 < FV; c0 += LPR * VPL) {
+  const uint32_t pitch_g = (uint32_t)ld_g * 4u, pitch_a = (uint32_t)ld_a * 4u, pitch_b = (uint32_t)ld_b * 4u,
+                 pitch_o = (uint32_t)ld_ga * 4u;
+  for (int c0 = 0; c0 < FV; c0 += LPR * VPL) {
+    const int c = c0 + lane;
+    if (c >= FV) return;
+    const bool live1 = VPL == 2 && c + LPR < FV;
+    const char* gl = opaque(reinterpret_cast<const char*>(G) + (size_t)c * sizeof(V));
+    const char* al = opaque(reinterpret_cast<const char*>(A) + (size_t)c * sizeof(V));
+    const char* bl = opaque(reinterpret_cast<const char*>(B) + (size_t)c * sizeof(V));
+    char* xo = reinterpret_cast<char*>(gA) + (size_t)c * sizeof(V);
+    for (int64_t r = (int64_t)blockIdx.x * RPB + sub; r < n_rows; r += (int64_t)gridDim.x * RPB) {
+      const int beg = __ldg(rowptr + r), end = __ldg(rowptr + r + 1);
       V acc[VPL], a[VPL];
 #pragma unroll
       for (int k = 0; k < VPL; ++k) {
-        const int c = c0 + lane + k * LPR;
         acc[k] = O::zero();
-        a[k] = (c < FV && beg < end) ? O::load(A + r * ld_a + (int64_t)c * O::W) : O::zero();
+        a[k] = (beg < end && (k == 0 || live1)) ? O::load(row_at(al, (uint32_t)r, pitch_a) + k * LPR * (int)sizeof(V))
+                                                : O::zero();
       }
-      for (int i = beg; i < end; i += U) {
-        int64_t t[U], o[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const bool ok = i + u < end;
-          t[u] = ok ? (int64_t)__ldg(dst + i + u) : -1;
-          o[u] = ok ? (int64_t)__ldg(oth + i + u) : -1;
-        }
-        V vg[U][VPL], vb[U][VPL];
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-          for (int k = 0; k < VPL; ++k) {
-            const int c = c0 + lane + k * LPR;
-            if (t[u] >= 0 && c < FV) {
-              vg[u][k] = O::load(G + t[u] * ld_g + (int64_t)c * O::W);
-              vb[u][k] = O::load(B + o[u] * ld_b + (int64_t)c * O::W);
-            }
-          }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-          for (int k = 0; k < VPL; ++k) {
-            const int c = c0 + lane + k * LPR;
-            if (t[u] >= 0 && c < FV) {
-              V d = O::map2(a[k], vb[u][k], [](float x, float y) { return act_bwd<ACT>(__fadd_rn(x, y)); });
-              acc[k] = O::map3(acc[k], vg[u][k], d, [](float s_, float g, float d_) {
-                return __fadd_rn(s_, __fmul_rn(g, d_));
-              });
-            }
-          }
-      }
+      cob_bwd_row<V, VPL, ACT, U>(acc, a, beg, end, GlobalRows<V, LPR>{gl, pitch_g}, GlobalRows<V, LPR>{bl, pitch_b},
+                                  [&](int m) { return __ldg(dst + m); }, [&](int m) { return __ldg(oth + m); }, live1);
 #pragma unroll
       for (int k = 0; k < VPL; ++k) {
-        const int c = c0 + lane + k * LPR;
-        if (c < FV) O::store(gA + r * ld_ga + (int64_t)c * O::W, acc[k]);
+        if (k == 1 && !live1) break;
+        O::store(row_at(xo, (uint32_t)r, pitch_o) + k * LPR * (int)sizeof(V), acc[k]);
       }
     }
   }
@@ -326,6 +432,11 @@ gather_rows_kernel(const float* __restrict__ x, int64_t ld_x, const int64_t* __r
     }
   }
 }
+
+}  // namespace cwn
+#include "gsa_tiled.cuh"
+#include "gsa_pipelined.cuh"
+namespace cwn {
 
 __global__ void check_index_range_kernel(const int64_t* __restrict__ idx, int64_t E, int64_t n, int32_t* flags) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
@@ -395,6 +506,65 @@ static bool getenv_flag(const char* name) {  // A/B switches for profiling; read
   return v && v[0] == '1';
 }
 
+
+// Launch geometry of a tile-staged kernel: dynamic shared memory = the feature-window buffers (`n_ops` operands of
+// F floats per row); persistent grid = resident CTAs per SM x 148, capped by the number of tiles. The budget aims at
+// 3 CTAs per SM (24 warps: the gathers hit shared memory, the DRAM stream is driven by TMA), 2 when rows are wider
+// than 256 bytes. (The occupancy query is a host-side table lookup, legal during stream capture.)
+struct TiledLaunch {
+  int grid;
+  uint32_t cap;    // bytes per operand buffer
+  size_t dynamic;  // total dynamic shared memory
+};
+template <class K>
+static TiledLaunch tiled_launch(K kernel, int64_t n_rows, int lpr, int F, int n_ops) {
+  TiledLaunch t;
+  const size_t budget = (size_t)F * 4 <= 256 ? 54 * 1024 : 92 * 1024;
+  static const bool no_features = getenv_flag("CWN_B200_TILED_NO_FEATURES");  // A/B: stage the plan slices only
+  t.cap = no_features ? 0u : (uint32_t)((budget / n_ops) & ~(size_t)127);
+  t.dynamic = (size_t)t.cap * n_ops;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.dynamic);
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, t.dynamic) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int gpb = kThreads / lpr;
+  const int64_t tr = (4 * gpb < 64) ? 64 : ((4 * gpb > 128) ? 128 : 4 * gpb);  // TileRows<LPR>
+  int64_t tiles = (n_rows + tr - 1) / tr;
+  const int64_t cap = (int64_t)kNumSMs * per_sm;
+  if (tiles > cap) tiles = cap;
+  t.grid = (int)(tiles < 1 ? 1 : tiles);
+  return t;
+}
+
+// Which kernel family serves the HBM-bound regime (>= kTiledMinRows rows, vector path): 'r' plain rows / chunked,
+// 'p' software-pipelined rows, 't' tile-staged (TMA bulk copies of the plan and of the feature windows).
+// Defaults = the fastest measured at 1M rows per dimension, block-diagonal ZINC-like layout (profiles/README.md):
+//   identity pass  F <= 128: chunked 0.57-0.67 of the HBM peak | pipelined 0.53-0.60 | tile-staged 0.49-0.52
+//                  F  = 256: pipelined 1.03 (L2 reuse of shared sources) | rows 0.78 | tile-staged 0.64
+//   coboundary fwd F = 64:   rows 0.52 | pipelined (U=2) 0.50 | tile-staged 0.35-0.44
+//   coboundary bwd F = 64:   pipelined (U=2) 0.66 | rows 0.61 | tile-staged 0.35-0.38
+// A/B switches for profiling: CWN_B200_LARGE_GATHER, CWN_B200_LARGE_COB = r | p | t.
+static char large_mode(const char* env, char dflt) {
+  const char* v = getenv(env);
+  return (v && (v[0] == 't' || v[0] == 'p' || v[0] == 'r')) ? v[0] : dflt;
+}
+
+template <class Pass>
+static void launch_pipelined(const typename Pass::Params& prm, const int32_t* rowptr, int64_t n_rows, cudaStream_t st) {
+  auto kern = csr_pipelined_kernel<Pass>;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int64_t rpb = kThreads / Pass::LPR;
+  int64_t need = (n_rows + rpb - 1) / rpb;
+  const int64_t cap = (int64_t)kNumSMs * per_sm;  // persistent: every resident group walks a strided row sequence
+  if (need > cap) need = cap;
+  kern<<<(int)need, kThreads, 0, st>>>(prm, rowptr, n_rows);
+}
+
+static bool tiled_enabled() {
+  static const bool off = getenv_flag("CWN_B200_NO_TILED");
+  return !off;
+}
+constexpr int64_t kTiledMinRows = 32768;
 }  // namespace cwn
 
 using namespace cwn;
@@ -435,7 +605,48 @@ extern "C" int cwn_csr_gather_reduce_f32(const float* x_src, int64_t ld_src, con
   const int64_t chunks = (n_rows + g.lpr - 1) / g.lpr;
   const int grid_c = grid_for(chunks, g.lpr);
   const bool chunked = g.vpl == 1 && g.lpr >= 4 && n_rows >= 32768 && !getenv_flag("CWN_B200_GATHER_V1");
-  if (g.vec) {
+  const bool tiled = g.vec && g.lpr >= 4 && idx && n_rows >= kTiledMinRows && aligned16(rowptr) && aligned16(idx) &&
+                     g.fv <= g.lpr * g.vpl && tiled_enabled() && !getenv_flag("CWN_B200_NO_TILED_GATHER");
+#define LAUNCH_TILED(VPLV, RED)                                                                                   \
+  {                                                                                                               \
+    auto kern = csr_gather_reduce_tiled_kernel<float4, LPR, VPLV, RED>;                                           \
+    const TiledLaunch tl = tiled_launch(kern, n_rows, LPR, F, 1);                                                 \
+    kern<<<tl.grid, kThreads, tl.dynamic, st>>>(x_src, ld_src, rowptr, idx, n_rows, g.fv, x_res, ld_res, eps, out, \
+                                                ld_out, tl.cap);                                                  \
+  }
+#define BY_REDUCE_TILED(VPLV)                                              \
+  if (reduce == CWN_REDUCE_ADD) LAUNCH_TILED(VPLV, CWN_REDUCE_ADD)         \
+  else if (reduce == CWN_REDUCE_MEAN) LAUNCH_TILED(VPLV, CWN_REDUCE_MEAN)  \
+  else LAUNCH_TILED(VPLV, CWN_REDUCE_MAX)
+  const char mode = large_mode("CWN_B200_LARGE_GATHER", g.vpl == 2 ? 'p' : 'r');
+  const bool large_ok = g.vec && g.lpr >= 4 && idx && n_rows >= kTiledMinRows && g.fv <= g.lpr * g.vpl;
+#define LAUNCH_PIPE(VPLV, RED)                                                                                       \
+  {                                                                                                                  \
+    using Pass = GatherPass<float4, LPR, VPLV, RED>;                                                                 \
+    Pass::Params prm{x_src, idx, x_res, eps, out, (uint32_t)ld_src * 4u, (uint32_t)ld_res * 4u, (uint32_t)ld_out * 4u, g.fv}; \
+    launch_pipelined<Pass>(prm, rowptr, n_rows, st);                                                                 \
+  }
+#define BY_REDUCE_PIPE(VPLV)                                             \
+  if (reduce == CWN_REDUCE_ADD) LAUNCH_PIPE(VPLV, CWN_REDUCE_ADD)        \
+  else if (reduce == CWN_REDUCE_MEAN) LAUNCH_PIPE(VPLV, CWN_REDUCE_MEAN) \
+  else LAUNCH_PIPE(VPLV, CWN_REDUCE_MAX)
+  if (large_ok && mode == 'p') {
+    if (g.vpl == 2) { constexpr int LPR = 32; BY_REDUCE_PIPE(2) }
+    else switch (g.lpr) {
+      case 4: { constexpr int LPR = 4; BY_REDUCE_PIPE(1) } break;
+      case 8: { constexpr int LPR = 8; BY_REDUCE_PIPE(1) } break;
+      case 16: { constexpr int LPR = 16; BY_REDUCE_PIPE(1) } break;
+      default: { constexpr int LPR = 32; BY_REDUCE_PIPE(1) } break;
+    }
+  } else if (tiled && mode == 't') {
+    if (g.vpl == 2) { constexpr int LPR = 32; BY_REDUCE_TILED(2) }
+    else switch (g.lpr) {
+      case 4: { constexpr int LPR = 4; BY_REDUCE_TILED(1) } break;
+      case 8: { constexpr int LPR = 8; BY_REDUCE_TILED(1) } break;
+      case 16: { constexpr int LPR = 16; BY_REDUCE_TILED(1) } break;
+      default: { constexpr int LPR = 32; BY_REDUCE_TILED(1) } break;
+    }
+  } else if (g.vec) {
     if (chunked) {
       switch (g.lpr) {
         case 4: { constexpr int LPR = 4; BY_REDUCE_CHUNKED(float4); } break;
@@ -454,6 +665,10 @@ extern "C" int cwn_csr_gather_reduce_f32(const float* x_src, int64_t ld_src, con
       }
     } else if (g.vpl == 1) { CWN_DISPATCH_LPR(g.lpr, BY_REDUCE(float, 1)) } else { constexpr int LPR = 32; BY_REDUCE(float, 2); }
   }
+#undef BY_REDUCE_PIPE
+#undef LAUNCH_PIPE
+#undef BY_REDUCE_TILED
+#undef LAUNCH_TILED
 #undef BY_REDUCE_CHUNKED
 #undef LAUNCH_CHUNKED
 #undef BY_REDUCE
@@ -501,11 +716,47 @@ extern "C" int cwn_csr_cob_fwd_f32(const float* P, int64_t ld_p, const float* Q,
                             P, ld_p, Q, ld_q, rowptr, src, cob, n_rows, g.fv, x_res, ld_res, eps, out, ld_out))
   // (a chunked variant like csr_gather_reduce_chunked_kernel was measured SLOWER for the two-operand passes —
   //  0.38 vs 0.40 of the HBM peak forward, 0.41 vs 0.53 backward at 1M rows, 80 registers — and was removed)
-  if (g.vec) {
+  const bool tiled = g.vec && g.lpr >= 4 && n_rows >= kTiledMinRows && aligned16(rowptr) && aligned16(src) &&
+                     aligned16(cob) && g.fv <= g.lpr * g.vpl && tiled_enabled();
+#define LAUNCH_TILED(VPLV)                                                                                          \
+  CWN_DISPATCH_ACT(act, {                                                                                           \
+    auto kern = csr_cob_fwd_tiled_kernel<float4, LPR, VPLV, ACT>;                                                   \
+    const TiledLaunch tl = tiled_launch(kern, n_rows, LPR, F, 2);                                                   \
+    kern<<<tl.grid, kThreads, tl.dynamic, st>>>(P, ld_p, Q, ld_q, rowptr, src, cob, n_rows, g.fv, x_res, ld_res, eps, \
+                                                out, ld_out, tl.cap, tl.cap);                                       \
+  })
+  const char mode = large_mode("CWN_B200_LARGE_COB", 'r');
+  const bool large_ok = g.vec && g.lpr >= 4 && n_rows >= kTiledMinRows && g.fv <= g.lpr * g.vpl;
+#define LAUNCH_PIPE(VPLV)                                                                                            \
+  CWN_DISPATCH_ACT(act, {                                                                                            \
+    using Pass = CobFwdPass<float4, LPR, VPLV, ACT>;                                                                 \
+    Pass::Params prm{P, Q, src, cob, x_res, eps, out, (uint32_t)ld_p * 4u, (uint32_t)ld_q * 4u, (uint32_t)ld_res * 4u, \
+                     (uint32_t)ld_out * 4u, g.fv};                                                                   \
+    launch_pipelined<Pass>(prm, rowptr, n_rows, st);                                                                 \
+  })
+  if (large_ok && mode == 'p') {
+    if (g.vpl == 2) { constexpr int LPR = 32; LAUNCH_PIPE(2) }
+    else switch (g.lpr) {
+      case 4: { constexpr int LPR = 4; LAUNCH_PIPE(1) } break;
+      case 8: { constexpr int LPR = 8; LAUNCH_PIPE(1) } break;
+      case 16: { constexpr int LPR = 16; LAUNCH_PIPE(1) } break;
+      default: { constexpr int LPR = 32; LAUNCH_PIPE(1) } break;
+    }
+  } else if (tiled && mode == 't') {
+    if (g.vpl == 2) { constexpr int LPR = 32; LAUNCH_TILED(2) }
+    else switch (g.lpr) {
+      case 4: { constexpr int LPR = 4; LAUNCH_TILED(1) } break;
+      case 8: { constexpr int LPR = 8; LAUNCH_TILED(1) } break;
+      case 16: { constexpr int LPR = 16; LAUNCH_TILED(1) } break;
+      default: { constexpr int LPR = 32; LAUNCH_TILED(1) } break;
+    }
+  } else if (g.vec) {
     if (g.vpl == 1) { CWN_DISPATCH_LPR(g.lpr, LAUNCH(float4, 1)) } else { constexpr int LPR = 32; LAUNCH(float4, 2) }
   } else {
     if (g.vpl == 1) { CWN_DISPATCH_LPR(g.lpr, LAUNCH(float, 1)) } else { constexpr int LPR = 32; LAUNCH(float, 2) }
   }
+#undef LAUNCH_PIPE
+#undef LAUNCH_TILED
 #undef LAUNCH
   return launched("cwn_csr_cob_fwd_f32");
 }
@@ -530,11 +781,47 @@ extern "C" int cwn_csr_cob_bwd_f32(const float* G, int64_t ld_g, const float* A,
 #define LAUNCH(VT, VPLV)                                                                  \
   CWN_DISPATCH_ACT(act, csr_cob_bwd_kernel<VT, LPR, VPLV, ACT><<<grid, kThreads, 0, st>>>(  \
                             G, ld_g, A, ld_a, B, ld_b, rowptr, dst, oth, n_rows, g.fv, gA, ld_ga))
-  if (g.vec) {
+  const bool tiled = g.vec && g.lpr >= 4 && G && B && n_rows >= kTiledMinRows && aligned16(rowptr) && aligned16(dst) &&
+                     aligned16(oth) && g.fv <= g.lpr * g.vpl && tiled_enabled();
+#define LAUNCH_TILED(VPLV)                                                                                       \
+  CWN_DISPATCH_ACT(act, {                                                                                        \
+    auto kern = csr_cob_bwd_tiled_kernel<float4, LPR, VPLV, ACT>;                                                \
+    const TiledLaunch tl = tiled_launch(kern, n_rows, LPR, F, 2);                                                \
+    kern<<<tl.grid, kThreads, tl.dynamic, st>>>(G, ld_g, A, ld_a, B, ld_b, rowptr, dst, oth, n_rows, g.fv, gA,   \
+                                                ld_ga, tl.cap, tl.cap);                                          \
+  })
+  const char mode = large_mode("CWN_B200_LARGE_COB", g.vpl == 1 ? 'p' : 'r');
+  const bool large_ok = g.vec && g.lpr >= 4 && G && B && n_rows >= kTiledMinRows && g.fv <= g.lpr * g.vpl;
+#define LAUNCH_PIPE(VPLV)                                                                                          \
+  CWN_DISPATCH_ACT(act, {                                                                                          \
+    using Pass = CobBwdPass<float4, LPR, VPLV, ACT>;                                                               \
+    Pass::Params prm{G, A, B, dst, oth, gA, (uint32_t)ld_g * 4u, (uint32_t)ld_a * 4u, (uint32_t)ld_b * 4u,         \
+                     (uint32_t)ld_ga * 4u, g.fv};                                                                  \
+    launch_pipelined<Pass>(prm, rowptr, n_rows, st);                                                               \
+  })
+  if (large_ok && mode == 'p') {
+    if (g.vpl == 2) { constexpr int LPR = 32; LAUNCH_PIPE(2) }
+    else switch (g.lpr) {
+      case 4: { constexpr int LPR = 4; LAUNCH_PIPE(1) } break;
+      case 8: { constexpr int LPR = 8; LAUNCH_PIPE(1) } break;
+      case 16: { constexpr int LPR = 16; LAUNCH_PIPE(1) } break;
+      default: { constexpr int LPR = 32; LAUNCH_PIPE(1) } break;
+    }
+  } else if (tiled && mode == 't') {
+    if (g.vpl == 2) { constexpr int LPR = 32; LAUNCH_TILED(2) }
+    else switch (g.lpr) {
+      case 4: { constexpr int LPR = 4; LAUNCH_TILED(1) } break;
+      case 8: { constexpr int LPR = 8; LAUNCH_TILED(1) } break;
+      case 16: { constexpr int LPR = 16; LAUNCH_TILED(1) } break;
+      default: { constexpr int LPR = 32; LAUNCH_TILED(1) } break;
+    }
+  } else if (g.vec) {
     if (g.vpl == 1) { CWN_DISPATCH_LPR(g.lpr, LAUNCH(float4, 1)) } else { constexpr int LPR = 32; LAUNCH(float4, 2) }
   } else {
     if (g.vpl == 1) { CWN_DISPATCH_LPR(g.lpr, LAUNCH(float, 1)) } else { constexpr int LPR = 32; LAUNCH(float, 2) }
   }
+#undef LAUNCH_PIPE
+#undef LAUNCH_TILED
 #undef LAUNCH
   return launched("cwn_csr_cob_bwd_f32");
 }

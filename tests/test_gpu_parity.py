@@ -576,10 +576,11 @@ def test_fused_dense_layer_equals_torch_modules(layer_dim, hidden, act, norm, co
             assert_close(outs[0][d], outs[1][d], rtol=1e-5, atol=2e-5, what=f'eval out {d}')
 
 
-@pytest.mark.parametrize('F', [16, 20, 64, 128])
+@pytest.mark.parametrize('F', [16, 20, 64, 128, 256])
 @pytest.mark.parametrize('reduce', ['add', 'mean', 'max'])
 def test_chunked_gather_kernel_large_row_counts(F, reduce):
-    """>= 32768 destination rows select the chunked kernel (coalesced index loads + shuffles). Integer-valued
+    """>= 32768 destination rows select the tile-staged kernel (plan slices brought to shared memory by TMA bulk
+    copies; the chunked kernel — coalesced index loads + shuffles — when the plan is not 16-byte aligned). Integer-valued
     features make every summation order exact, so equality with torch's own scatter must be bit-exact; rows without
     messages (every 7th destination is skipped, plus a tail) must come out as zeros / residual only."""
     n_src, n_dst, E = 50_000, 70_001, 260_000
@@ -634,6 +635,57 @@ def test_embedding_style_gather_backward_uses_split_rows():
     out.backward(go)
     ref = torch.zeros(n, F, device=DEV).index_add_(0, idx, go)
     assert torch.equal(w.grad, ref) and float(w.grad[-1].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize('F', [16, 64, 256])
+def test_tile_staged_kernels_are_bit_exact_and_survive_heavy_rows(F):
+    """The tile-staged kernels (>= 32 768 rows) keep the sequential in-row accumulation order, so on FLOAT data:
+      * the identity pass equals an unbuffered in-order CPU scatter_add bit for bit;
+      * the coboundary passes equal the same formula evaluated message by message in order on the CPU.
+    The adjacency has rows with thousands of messages (a tile whose message range exceeds the 2048-entry staging
+    buffer falls back to reading the plan from global memory), empty rows, a ragged last tile, and message ranges that
+    start at every residue mod 4 (the bulk copies move the 16-byte aligned hull, three threads the tail)."""
+    n_src, n_dst, n_cob = 3000, 33_001, 700
+    g = torch.Generator().manual_seed(F)
+    E_light = 90_000
+    dst = torch.randint(0, n_dst - 70, (E_light,), generator=g)
+    dst = dst - (dst % 5 == 0).long()
+    dst.clamp_(min=0)
+    heavy = torch.cat([torch.full((5000,), 1234), torch.full((2049,), 20_000), torch.full((2047,), 20_100)])
+    dst = torch.cat([dst, heavy])[torch.randperm(E_light + heavy.numel(), generator=g)]
+    E = dst.numel()
+    src = torch.randint(0, n_src, (E,), generator=g)
+    cob = torch.randint(0, n_cob, (E,), generator=g)
+    x = torch.randn(n_src, F, generator=g) * 10
+    idx = torch.stack([src, dst])
+    ref = np.zeros((n_dst, F), dtype=np.float32)
+    np.add.at(ref, dst.numpy(), x.numpy()[src.numpy()])
+    out = ops.gather_scatter(x.to(DEV), idx.to(DEV), n_dst)
+    assert torch.equal(out.cpu(), torch.from_numpy(ref))
+    res = torch.randn(n_dst, F, generator=g)
+    eps = torch.tensor([0.5])
+    out = ops.gather_scatter(x.to(DEV), idx.to(DEV), n_dst, 'add', x_res=res.to(DEV), eps=eps.to(DEV))
+    assert torch.equal(out.cpu(), torch.from_numpy(ref) + (1 + eps) * res)
+    # coboundary pass, forward: relu(P[src] + Q[cob]) summed in message order
+    P, Q = torch.randn(n_src, F, generator=g), torch.randn(n_cob, F, generator=g)
+    msg = torch.relu(P[src] + Q[cob]).numpy()
+    ref = np.zeros((n_dst, F), dtype=np.float32)
+    np.add.at(ref, dst.numpy(), msg)
+    Pd, Qd = P.to(DEV).requires_grad_(True), Q.to(DEV).requires_grad_(True)
+    out = ops.cob_pass(Pd, Qd, idx.to(DEV), cob.to(DEV), n_dst, act='relu')
+    assert torch.equal(out.detach().cpu(), torch.from_numpy(ref))
+    # backward w.r.t. P on a transposed problem with >= 32 768 source rows: dP[s] = sum_e G[dst_e] * relu'(.)
+    n_big = 40_000
+    src_b = torch.randint(0, n_big, (E,), generator=g)
+    Pb = torch.randn(n_big, F, generator=g)
+    G = torch.randn(n_dst, F, generator=g)
+    Pbd = Pb.to(DEV).requires_grad_(True)
+    out = ops.cob_pass(Pbd, Qd, torch.stack([src_b, dst]).to(DEV), cob.to(DEV), n_dst, act='relu')
+    out.backward(G.to(DEV))
+    gmsg = (G[dst] * (Pb[src_b] + Q[cob] > 0).float()).numpy()
+    ref = np.zeros((n_big, F), dtype=np.float32)
+    np.add.at(ref, src_b.numpy(), gmsg)
+    assert torch.equal(Pbd.grad.cpu(), torch.from_numpy(ref))
 
 
 @pytest.mark.parametrize('act,F', [('relu', 64), ('elu', 32), ('tanh', 128)])
@@ -749,207 +801,5 @@ def test_dense_fast_path_equals_generic_path(layer_dim, hidden, n_complexes):
     for k in p1:
         scale = float(p2[k].abs().max())
         assert_close(p1[k], p2[k], rtol=1e-5, atol=1e-5 * scale + 2e-6 * G, what=f'backward fast vs generic: grad {k}')
-    for k in b1:
-        assert_close(b1[k].float(), b2[k].float(), rtol=1e-5, atol=1e-6, what=f'buffer {k}')
-    # second step on the fused layer: `.grad` now exists, so the kernels accumulate straight into it (the
-    # FlatGradBucket mode) instead of handing gradients to autograd; same inputs => same gradients
-    for prm in fused_conv.parameters():
-        if prm.grad is not None:
-            prm.grad.zero_()
-    batch = ComplexBatch.from_complex_list(synthetic.float_feature_complexes(7, layer_dim, seed=11, ragged=True)).to(DEV)
-    outs = fused_conv(*batch.get_all_cochain_params(max_dim=2, include_down_features=False))
-    g = torch.Generator(device=DEV).manual_seed(3)
-    sum((o * torch.randn(o.shape, device=DEV, generator=g)).sum() for o in outs).backward()
-    for k in p1:
-        if p2[k].grad is not None:
-            scale = float(p2[k].grad.abs().max()) + 1e-6
-            atol = max(5e-5, 1e-4 * scale)  # (biases feeding a BatchNorm have an analytically zero gradient: pure rounding noise)
-            assert_close(p1[k].grad, p2[k].grad, rtol=1e-4, atol=atol, what=f'direct grad {k}')
-    torch_conv.load_state_dict(fused_conv.state_dict())  # (the fused layer has seen one more training step)
-    with torch.no_grad():
-        for conv in (fused_conv, torch_conv):
-            conv.eval()
-        outs = []
-        for conv in (fused_conv, torch_conv):
-            batch = ComplexBatch.from_complex_list(
-                synthetic.float_feature_complexes(7, layer_dim, seed=11, ragged=True)).to(DEV)
-            outs.append(conv(*batch.get_all_cochain_params(max_dim=2, include_down_features=False)))
-        for d in range(3):
-            assert_close(outs[0][d], outs[1][d], rtol=1e-5, atol=2e-5, what=f'eval out {d}')
-
-
-@pytest.mark.parametrize('F', [16, 20, 64, 128])
-@pytest.mark.parametrize('reduce', ['add', 'mean', 'max'])
-def test_chunked_gather_kernel_large_row_counts(F, reduce):
-    """>= 32768 destination rows select the chunked kernel (coalesced index loads + shuffles). Integer-valued
-    features make every summation order exact, so equality with torch's own scatter must be bit-exact; rows without
-    messages (every 7th destination is skipped, plus a tail) must come out as zeros / residual only."""
-    n_src, n_dst, E = 50_000, 70_001, 260_000
-    g = torch.Generator().manual_seed(F)
-    dst = torch.randint(0, n_dst - 300, (E,), generator=g)
-    dst = dst - (dst % 7 == 0).long()  # leave holes
-    dst.clamp_(min=1)
-    idx = torch.stack([torch.randint(0, n_src, (E,), generator=g), dst]).to(DEV)
-    x = torch.randint(-6, 7, (n_src, F), generator=g).float().to(DEV)
-    ref = O.scatter(x.index_select(0, idx[0]), idx[1], n_dst, reduce)
-    out = ops.gather_scatter(x, idx, n_dst, reduce)
-    assert torch.equal(out, ref)
-    if reduce == 'add':
-        res = torch.randint(-3, 4, (n_dst, F), generator=g).float().to(DEV)
-        eps = torch.tensor([1.0], device=DEV)
-        assert torch.equal(ops.gather_scatter(x, idx, n_dst, 'add', x_res=res, eps=eps), ref + 2 * res)
-
-
-def test_flat_adam_matches_torch_adam():
-    from cwn_b200.dist import FlatGradBucket
-    from cwn_b200.optim import FlatAdam
-    torch.manual_seed(0)
-    mk = lambda: torch.nn.Sequential(torch.nn.Linear(7, 33), torch.nn.ReLU(), torch.nn.Linear(33, 5)).to(DEV)  # noqa: E731
-    a, b = mk(), mk()
-    b.load_state_dict(a.state_dict())
-    ref = torch.optim.Adam(b.parameters(), lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-2)
-    bucket = FlatGradBucket(a)
-    opt = FlatAdam(a, bucket, lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-2)
-    for it in range(5):
-        x = torch.randn(16, 7, device=DEV)
-        a(x).pow(2).sum().backward()
-        ref.zero_grad()
-        b(x).pow(2).sum().backward()
-        opt.step()
-        ref.step()
-        assert float(bucket.flat.abs().sum()) == 0.0  # the kernel cleared the gradients it consumed
-        for p, q in zip(a.parameters(), b.parameters()):
-            assert_close(p, q, rtol=1e-5, atol=1e-6, what=f'step {it}')
-    assert opt.num_steps == 5
-
-
-def test_embedding_style_gather_backward_uses_split_rows():
-    """Few table rows, many lookups (an embedding): the gradient is a two-level segmented sum; integer-valued
-    gradients make it exactly equal to torch's index_add_."""
-    n, E, F = 7, 5000, 64
-    g = torch.Generator().manual_seed(2)
-    idx = torch.randint(0, n - 1, (E,), generator=g).to(DEV)  # row n-1 is never looked up -> zero gradient
-    w = torch.randn(n, F, device=DEV, requires_grad=True)
-    out = ops.gather_rows(w, idx)
-    assert torch.equal(out, w.detach()[idx])
-    go = torch.randint(-3, 4, (E, F), generator=g).float().to(DEV)
-    out.backward(go)
-    ref = torch.zeros(n, F, device=DEV).index_add_(0, idx, go)
-    assert torch.equal(w.grad, ref) and float(w.grad[-1].abs().sum()) == 0.0
-
-
-@pytest.mark.parametrize('act,F', [('relu', 64), ('elu', 32), ('tanh', 128)])
-def test_cob_kernels_large_row_counts(act, F):
-    """Coboundary pass at 40k rows (forward and both gradient passes, grid-stride regime) against torch autograd on
-    the same device (fp32, rtol 1e-5)."""
-    n, n_cob, E = 40_000, 9_000, 150_000
-    g = torch.Generator().manual_seed(F)
-    idx = torch.stack([torch.randint(0, n, (E,), generator=g), torch.randint(0, n - 50, (E,), generator=g)]).to(DEV)
-    cob = torch.randint(0, n_cob - 10, (E,), generator=g).to(DEV)
-    P0, Q0 = torch.randn(n, F, generator=g).to(DEV), torch.randn(40_000, F, generator=g).to(DEV)  # Q rows >= 32768 too
-    res0, w = torch.randn(n, F, generator=g).to(DEV), torch.randn(n, F, generator=g).to(DEV)
-    eps = torch.tensor([0.25], device=DEV)
-    fn = O._ACT[act]
-    P, Q, res = (t.clone().requires_grad_(True) for t in (P0, Q0, res0))
-    ref = O.scatter(fn(P.index_select(0, idx[0]) + Q.index_select(0, cob)), idx[1], n) + (1 + eps) * res
-    (ref * w).sum().backward()
-    Pg, Qg, rg = (t.clone().requires_grad_(True) for t in (P0, Q0, res0))
-    out = ops.cob_pass(Pg, Qg, idx, cob, n, act=act, x_res=rg, eps=eps)
-    assert_close(out, ref, rtol=1e-5, atol=2e-5, what='fwd')
-    (out * w).sum().backward()
-    assert_close(Pg.grad, P.grad, rtol=1e-5, atol=5e-5, what='grad P')
-    assert_close(Qg.grad, Q.grad, rtol=1e-5, atol=1e-4, what='grad Q')
-    assert float(out[-50:].sub((1 + eps) * res0[-50:]).abs().max()) == 0.0  # rows without messages: residual only
-
-
-@pytest.mark.parametrize('kind', ['zinc', 'ragged', 'ragged_down', 'ogb'])
-def test_gpu_collation_equals_python_collation(kind):
-    """PackedComplexDataset.collate (one kernel, dataset resident in HBM) must reproduce
-    ComplexBatch.from_complex_list(...).pack_() bit for bit: every tensor, the packed layout, the host-side counts."""
-    from cwn_b200.data.packed import PackedComplexDataset
-    kw = dict(zinc={}, ragged=dict(ragged=True), ragged_down=dict(ragged=True, include_down_adj=True),
-              ogb=dict(ogb_features=True))[kind]
-    mk = lambda: synthetic.zinc_like_complexes(40, seed=12, **kw)  # noqa: E731
-    ds = PackedComplexDataset(mk(), max_dim=2, device=DEV)
-    comps = mk()
-    g = torch.Generator().manual_seed(0)
-    for trial in range(4):
-        ids = torch.randperm(40, generator=g)[:9 + trial].tolist()
-        ref = ComplexBatch.from_complex_list([comps[i] for i in ids], max_dim=2).pack_()
-        got = ds.collate(ids)
-        assert got.packed_signature == ref.packed_signature
-        assert got.dimension == ref.dimension and got.num_complexes == ref.num_complexes
-        assert torch.equal(got.y.cpu(), ref.y)
-        for d in range(ref.dimension + 1):
-            a, b = got.cochains[d], ref.cochains[d]
-            assert (a.num_cells, a.num_cells_up, a.num_cells_down) == (b.num_cells, b.num_cells_up, b.num_cells_down)
-            for k in ('x', 'upper_index', 'lower_index', 'boundary_index', 'shared_boundaries', 'shared_coboundaries',
-                      'batch', 'ptr'):
-                u, v = getattr(a, k), getattr(b, k)
-                assert (u is None) == (v is None), (d, k)
-                if u is not None:
-                    assert torch.equal(u.cpu(), v), (d, k)
-        for dt in ref._flat:
-            assert torch.equal(got._flat[dt].cpu(), ref._flat[dt])
-    # writing into an existing packed batch of the same layout (the static buffers of a captured graph)
-    if kind == 'zinc':
-        static = ds.collate(list(range(8)))
-        ds.collate(list(range(8, 16)), out=static)
-        ref = ComplexBatch.from_complex_list([comps[i] for i in range(8, 16)], max_dim=2).pack_()
-        for dt in ref._flat:
-            assert torch.equal(static._flat[dt].cpu(), ref._flat[dt])
-        with pytest.raises(ValueError, match='layout differs'):
-            ds.collate(list(range(9)), out=static)
-
-
-@pytest.mark.parametrize('layer_dim,hidden,n_complexes', [(64, 64, 128), (16, 32, 40), (32, 128, 300)])
-def test_dense_fast_path_equals_generic_path(layer_dim, hidden, n_complexes):
-    """The cp.async fast path of the grouped dense kernels (16-byte aligned operands) against the generic kernels
-    (`cwn_debug_force_generic_dense`) on the same layer and inputs.
-      forward: fast vs generic — same FMA order, so outputs agree to the rounding of the BatchNorm statistics;
-      backward: fast vs generic BEHIND THE SAME (fast) FORWARD — same saved tensors and same FMA order, so every
-      gradient agrees to ~1 ulp of its largest term. (Gradients behind two different forwards are not comparable at
-      this size: a pre-activation that moves by 1e-7 across zero flips a ReLU derivative, an O(1) change.)
-    300 complexes = several hundred row tiles per problem, so the last-CTA merges run more than one trip."""
-    from cwn_b200 import _lib
-    from cwn_b200.mp.layers import SparseCINConv
-    from cwn_b200.mp.nn import get_graph_norm, get_nonlinearity
-    torch.manual_seed(2)
-    conv = SparseCINConv(layer_dim, layer_dim, layer_dim, None, None, None, None, layer_dim=layer_dim, hidden=hidden,
-                         act_module=get_nonlinearity('relu'), graph_norm=get_graph_norm('bn'), use_coboundaries=True,
-                         train_eps=True).to(DEV).train()
-    state = {k: v.clone() for k, v in conv.state_dict().items()}
-    results = []
-    try:
-        for mask in (0, 2, 1):  # all fast | fast forward + generic backward | generic forward
-            _lib.check(_lib.load().cwn_debug_force_generic_dense(mask))
-            conv.load_state_dict(state)
-            conv.zero_grad(set_to_none=True)
-            batch = ComplexBatch.from_complex_list(
-                synthetic.float_feature_complexes(n_complexes, layer_dim, seed=5, ragged=True)).to(DEV)
-            for d in range(3):
-                batch.cochains[d]._x = batch.cochains[d].x.clone().requires_grad_(True)
-            outs = conv(*batch.get_all_cochain_params(max_dim=2, include_down_features=False))
-            g = torch.Generator(device=DEV).manual_seed(3)
-            sum((o * torch.randn(o.shape, device=DEV, generator=g)).sum() for o in outs).backward()
-            results.append(([o.detach().clone() for o in outs], [batch.cochains[d].x.grad.clone() for d in range(3)],
-                            {k: p.grad.clone() for k, p in conv.named_parameters() if p.grad is not None},
-                            {k: b.clone().float() for k, b in conv.named_buffers()}))
-    finally:
-        _lib.load().cwn_debug_force_generic_dense(0)
-    (o1, gx1, p1, b1), (o2, gx2, p2, b2), (o3, _, _, b3) = results
-    for d in range(3):
-        assert torch.equal(o1[d], o2[d])  # same forward kernels
-        assert_close(o1[d], o3[d], rtol=1e-5, atol=1e-5, what=f'forward fast vs generic: out {d}')
-        assert_close(gx1[d], gx2[d], rtol=1e-5, atol=1e-5, what=f'backward fast vs generic: grad x {d}')
-    assert p1.keys() == p2.keys()
-    # an eps gradient is ONE scalar: the dot product <g_agg, x> over ~n*F O(1) terms that cancel almost completely
-    # (|result| ~ 1e-3 of sum |terms| ~ 1e5), so its error is bounded by the perturbation of g_agg, not by its own
-    # size: |<dg, x>| <= ||dg||·||x|| with ||dg|| <= 1e-5 ||g|| (Cauchy-Schwarz; gx has the magnitude of g_agg).
-    eps_atol = 1e-5 * max(float(gx2[d].norm()) * x_norm[d] for d in range(3))
-    for k in p1:
-        scale = float(p2[k].abs().max()) + 1e-6
-        atol = eps_atol if k.split('.')[-1].startswith('eps') else 1e-5 * scale + 1e-6
-        assert_close(p1[k], p2[k], rtol=1e-5, atol=atol, what=f'backward fast vs generic: grad {k}')
     for k in b1:
         assert_close(b1[k], b3[k], rtol=1e-5, atol=1e-6, what=f'forward fast vs generic: buffer {k}')
