@@ -34,6 +34,13 @@ class LinearDesc(ctypes.Structure):
                 ('bn_mean', _P), ('bn_scale', _P), ('bn_rstd', _P), ('counter', _P), ('tile_rows', _I32)]
 
 
+class HeadDim(ctypes.Structure):
+    """cwn_head_dim"""
+    _fields_ = [('x', _P), ('ld_x', _I64), ('rowptr', _P), ('perm', _P), ('w1', _P), ('b1', _P), ('pooled', _P),
+                ('z', _P), ('g_z', _P), ('g_x', _P), ('ld_gx', _I64), ('g_w1', _P), ('g_b1', _P),
+                ('accumulate', _I32)]
+
+
 class BNDesc(ctypes.Structure):
     """cwn_bn_desc"""
     _fields_ = [('stats', _P), ('n_tiles', _I32), ('n_rows', _I64), ('h', _I32), ('gamma', _P), ('beta', _P),
@@ -73,6 +80,10 @@ _SIGNATURES = {
     'cwn_last_error_string': (ctypes.c_char_p, []),
     'cwn_launch_count': (ctypes.c_ulonglong, []),
     'cwn_debug_force_generic_dense': (ctypes.c_int, [ctypes.c_int32]),
+    'cwn_readout_head_fwd': (ctypes.c_int, [_vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp,
+                                            _vp]),
+    'cwn_readout_head_bwd': (ctypes.c_int, [_vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp,
+                                            _vp, _i32, _vp]),
     'cwn_csr_plan_workspace_bytes': (ctypes.c_size_t, [_i64, _i64]),
     'cwn_csr_plan_build': (ctypes.c_int, [_c_i64p, _c_i64p, _c_i64p, _i64, _i64, _c_i32p, _c_i32p, _c_i32p,
                                           _c_i32p, _c_i32p, _vp, ctypes.c_size_t, _vp]),

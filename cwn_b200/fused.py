@@ -485,3 +485,120 @@ def grouped_linear(problems):
             bi = len(biases) - 1
         spec.append((wi, int(off), bi))
     return list(GroupedLinear.apply(tuple(spec), len(weights), *[p[0] for p in problems], *weights, *biases))
+
+
+# ----------------------------------------------------------------------------------------------- readout head
+class _ReadoutHead(Function):
+    """pool_complex + per-dimension lin1 + act + sum/mean over dimensions + lin2 (reference mp/nn.py:50-60,
+    mp/models.py:230-254, mp/molec_models.py:137-161) as one launch forward and two backward (`csrc/head.cu`)."""
+
+    @staticmethod
+    def forward(ctx, cfg, w2, b2, *tensors):
+        n = cfg['n_dims']
+        xs = [None if x is None else (x if x.stride(1) == 1 else x.contiguous()) for x in tensors[:n]]
+        w1s = [w.contiguous() for w in tensors[n:2 * n]]
+        b1s = tensors[2 * n:3 * n]
+        B, K, H2, out_size = cfg['B'], cfg['K'], w1s[0].size(0), w2.size(0)
+        dev = w2.device
+        w2c = w2.contiguous()
+        with torch.cuda.device(dev):
+            scratch = torch.empty(n * B * (K + H2) + B * H2, dtype=torch.float32, device=dev)
+            pooled = [scratch[d * B * K:(d + 1) * B * K] for d in range(n)]
+            zs = [scratch[n * B * K + d * B * H2:n * B * K + (d + 1) * B * H2] for d in range(n)]
+            h = scratch[n * B * (K + H2):]
+            out = torch.empty(B, out_size, dtype=torch.float32, device=dev)
+            descs = (_lib.HeadDim * n)()
+            for d in range(n):
+                plan = cfg['plans'][d] if xs[d] is not None else None
+                descs[d] = _lib.HeadDim(_p(xs[d]), xs[d].stride(0) if xs[d] is not None else 0,
+                                        plan.rowptr.data_ptr() if plan is not None else None,
+                                        _p(plan.perm) if plan is not None else None, _p(w1s[d]), _p(b1s[d]),
+                                        _p(pooled[d]), _p(zs[d]), None, None, 0, None, None, 0)
+            ops._call('readout_head_fwd', 4 * (sum(x.numel() for x in xs if x is not None) + n * H2 * K + B * out_size),
+                      _lib.load().cwn_readout_head_fwd, descs, n, B, K, H2, out_size, cfg['act'], cfg['pool_mean'],
+                      cfg['final_mean'], _p(w2c), _p(b2), _p(h), _p(out), ops._stream())
+        ctx.cfg, ctx.n = cfg, n
+        ctx.shapes = [None if x is None else tuple(x.shape) for x in xs]
+        ctx.save_for_backward(scratch, w2c, *w1s)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        cfg, n = ctx.cfg, ctx.n
+        scratch, w2 = ctx.saved_tensors[:2]
+        w1s = ctx.saved_tensors[2:]
+        B, K, H2, out_size = cfg['B'], cfg['K'], w1s[0].size(0), w2.size(0)
+        dev = w2.device
+        g_out = g_out.contiguous()
+        lin1s, lin2 = cfg['lin1s'], cfg['lin2']
+        with torch.cuda.device(dev):
+            pooled = [scratch[d * B * K:(d + 1) * B * K] for d in range(n)]
+            zs = [scratch[n * B * K + d * B * H2:n * B * K + (d + 1) * B * H2] for d in range(n)]
+            h = scratch[n * B * (K + H2):]
+            g_z = torch.empty(n * B * H2, dtype=torch.float32, device=dev)
+            gxs, gw1, gb1 = [], [], []
+            descs = (_lib.HeadDim * n)()
+            for d in range(n):
+                shape = ctx.shapes[d]
+                gx = torch.empty(shape, dtype=torch.float32, device=dev) \
+                    if shape is not None and ctx.needs_input_grad[3 + d] else None
+                plan = cfg['plans'][d] if shape is not None else None
+                lin = lin1s[d]
+                dw, db = _direct_grad(lin.weight), (_direct_grad(lin.bias) if lin.bias is not None else None)
+                direct = dw is not None and (lin.bias is None or db is not None)
+                if direct:
+                    gw, gb = dw, db
+                    gw1.append(None), gb1.append(None)
+                else:
+                    gw = torch.empty_like(lin.weight, memory_format=torch.contiguous_format)
+                    gb = torch.empty_like(lin.bias) if lin.bias is not None else None
+                    gw1.append(gw), gb1.append(gb)
+                descs[d] = _lib.HeadDim(None, K, plan.rowptr.data_ptr() if plan is not None else None,
+                                        _p(plan.perm) if plan is not None else None, _p(w1s[d]), None, _p(pooled[d]),
+                                        _p(zs[d]), g_z.data_ptr() + 4 * d * B * H2, _p(gx), K, _p(gw), _p(gb),
+                                        1 if direct else 0)
+                gxs.append(gx)
+            dw2, db2 = _direct_grad(lin2.weight), (_direct_grad(lin2.bias) if lin2.bias is not None else None)
+            direct2 = dw2 is not None and (lin2.bias is None or db2 is not None)
+            if direct2:
+                gw2, gb2, gw2_out, gb2_out = dw2, db2, None, None
+            else:
+                gw2 = gw2_out = torch.empty_like(w2)
+                gb2 = gb2_out = torch.empty_like(lin2.bias) if lin2.bias is not None else None
+            ops._call('readout_head_bwd', 4 * (sum(g.numel() for g in gxs if g is not None) + 2 * n * H2 * K),
+                      _lib.load().cwn_readout_head_bwd, descs, n, B, K, H2, out_size, cfg['act'], cfg['pool_mean'],
+                      cfg['final_mean'], _p(w2), _p(h), _p(g_out), _p(gw2), _p(gb2), 1 if direct2 else 0,
+                      ops._stream())
+        return (None, gw2_out, gb2_out, *gxs, *gw1, *gb1)
+
+
+def readout_head(model, xs, data, act_name):
+    """The fused readout of a SparseCIN-family model, or NotImplemented when its configuration is outside the closed
+    form (active dropout, partial outputs requested by the caller, exotic readouts, non-CUDA tensors)."""
+    from cwn_b200.mp.nn import num_complexes_of
+    if act_name is None or model.readout not in ('sum', 'mean') or model.final_readout not in ('sum', 'mean'):
+        return NotImplemented
+    if model.training and model.dropout_rate > 0:
+        return NotImplemented
+    dims = list(model.readout_dims)
+    n = len(dims)
+    if n < 1 or n > 4 or not xs or xs[0] is None:
+        return NotImplemented
+    K = xs[0].size(-1)
+    sel = [xs[d] if d < len(xs) else None for d in dims]  # dimensions absent from the batch pool to zeros
+    for x in sel:
+        if x is not None and not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.size(1) == K):
+            return NotImplemented
+    lin1s = [model.lin1s[d] for d in dims]
+    lin2 = model.lin2
+    H2 = lin1s[0].out_features
+    if any(l.in_features != K or l.out_features != H2 for l in lin1s) or lin2.in_features != H2:
+        return NotImplemented
+    if any((l.bias is None) != (lin1s[0].bias is None) for l in lin1s) or (n * K + H2) * 4 > 160 * 1024:
+        return NotImplemented
+    B = num_complexes_of(data)
+    plans = [ops._row_plan(data.cochains[d].batch, B) if x is not None else None for d, x in zip(dims, sel)]
+    cfg = {'n_dims': n, 'B': B, 'K': K, 'plans': plans, 'act': ops.ACT_CODES[act_name],
+           'pool_mean': int(model.readout == 'mean'), 'final_mean': int(model.final_readout == 'mean'),
+           'lin1s': lin1s, 'lin2': lin2}
+    return _ReadoutHead.apply(cfg, lin2.weight, lin2.bias, *sel, *[l.weight for l in lin1s], *[l.bias for l in lin1s])

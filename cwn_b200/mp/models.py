@@ -155,6 +155,8 @@ class SparseCIN(torch.nn.Module, _JumpMixin):
         self.lin1s.reset_parameters()
         self.lin2.reset_parameters()
 
+    fuse_readout = True  # pool + lin1s + act + lin2 as one kernel (cwn_b200.fused.readout_head) when its closed form applies
+
     def pool_complex(self, xs, data):
         pooled = pool_complex(xs, data, self.max_dim, self.readout)
         return [pooled[i] for i in range(self.max_dim + 1)]
@@ -179,6 +181,11 @@ class SparseCIN(torch.nn.Module, _JumpMixin):
                     jump_xs[i] += [x]
         if self.jump_mode is not None:
             xs = self.jump_complex(jump_xs)
+        if not include_partial and self.fuse_readout:
+            from cwn_b200 import fused
+            out = fused.readout_head(self, xs, data, self.nonlinearity if self.nonlinearity in ops.ACT_CODES else None)
+            if out is not NotImplemented:
+                return out
         xs = self.pool_complex(xs, data)
         xs = [xs[i] for i in self.readout_dims]
         if include_partial:

@@ -15,6 +15,8 @@ from cwn_b200.mp.nn import JumpingKnowledge, get_graph_norm, get_nonlinearity, p
 class _EmbedSparseCINBase(torch.nn.Module, _JumpMixin):
     """Everything the two molecular models share: conv stack, jump, per-dimension readout head."""
 
+    fuse_readout = True  # pool + lin1s + act + lin2 as one kernel (cwn_b200.fused.readout_head) when its closed form applies
+
     def _build_trunk(self, out_size, num_layers, hidden, max_dim, jump_mode, nonlinearity, readout, train_eps,
                      final_hidden_multiplier, readout_dims, final_readout, apply_dropout_before, embed_dim,
                      use_coboundaries, graph_norm):
@@ -89,6 +91,11 @@ class _EmbedSparseCINBase(torch.nn.Module, _JumpMixin):
                     jump_xs[i] += [x]
         if self.jump_mode is not None:
             xs = self.jump_complex(jump_xs)
+        if not include_partial and self.fuse_readout:
+            from cwn_b200 import fused
+            out = fused.readout_head(self, xs, data, self.nonlinearity if self.nonlinearity in ops.ACT_CODES else None)
+            if out is not NotImplemented:
+                return out
         xs = pool_complex(xs, data, self.max_dim, self.readout)
         xs = [xs[i] for i in self.readout_dims]
         if include_partial:

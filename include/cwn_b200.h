@@ -250,6 +250,36 @@ int cwn_collate(const cwn_collate_job* jobs, int32_t n_jobs, cwn_stream_t stream
  * assert for out-of-range indices.) */
 int cwn_check_index_range(const int64_t* idx, int64_t E, int64_t n, int32_t* flags, cwn_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Readout head of the SparseCIN-family models (reference mp/nn.py:50-60 pool_complex; mp/models.py:230-254 and
+ * mp/molec_models.py:137-161: per-dimension lin1 + act, sum/mean over dimensions, lin2), one launch forward and
+ * two backward instead of ~45 library launches:
+ *   pooled_d[b] = SUM|MEAN_{i in complex b} x_d[i] ;  z_d[b] = pooled_d[b] W1_d^T + b1_d ;
+ *   h[b] = SUM|MEAN_d act(z_d[b]) ;  out[b] = h[b] W2^T + b2
+ * The cells of complex b in dimension d are rows perm[rowptr[b] .. rowptr[b+1]) of x_d (row plan of `batch_d`;
+ * perm NULL = identity; rowptr NULL = the dimension is absent from the batch: pooled_d = 0, as pool_complex does).
+ * Dropout must be inactive (the Python wrapper falls back to torch otherwise).
+ */
+#define CWN_MAX_HEAD_DIMS 4
+typedef struct {
+  const float* x; int64_t ld_x;              /* [n_d, K] */
+  const int32_t* rowptr; const int32_t* perm;
+  const float* w1; const float* b1;          /* [H2, K] row-major, [H2] (nullable) */
+  float* pooled;                             /* [B, K]  written by fwd, read by bwd */
+  float* z;                                  /* [B, H2] pre-activations, written by fwd, read by bwd */
+  /* backward only */
+  float* g_z;                                /* [B, H2] scratch */
+  float* g_x; int64_t ld_gx;                 /* [n_d, K], nullable */
+  float* g_w1; float* g_b1;                  /* nullable */
+  int32_t accumulate;                        /* add into g_w1 / g_b1 instead of overwriting */
+} cwn_head_dim;
+int cwn_readout_head_fwd(const cwn_head_dim* dims, int32_t n_dims, int64_t B, int32_t K, int32_t H2, int32_t out_size,
+                         int32_t act, int32_t pool_mean, int32_t final_mean, const float* w2, const float* b2,
+                         float* h /* [B, H2] */, float* out /* [B, out_size] */, cwn_stream_t stream);
+int cwn_readout_head_bwd(const cwn_head_dim* dims, int32_t n_dims, int64_t B, int32_t K, int32_t H2, int32_t out_size,
+                         int32_t act, int32_t pool_mean, int32_t final_mean, const float* w2, const float* h,
+                         const float* g_out, float* g_w2, float* g_b2, int32_t accumulate_out, cwn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -803,3 +803,52 @@ def test_dense_fast_path_equals_generic_path(layer_dim, hidden, n_complexes):
         assert_close(p1[k], p2[k], rtol=1e-5, atol=1e-5 * scale + 2e-6 * G, what=f'backward fast vs generic: grad {k}')
     for k in b1:
         assert_close(b1[k], b3[k], rtol=1e-5, atol=1e-6, what=f'forward fast vs generic: buffer {k}')
+
+
+@pytest.mark.parametrize('cfg', [
+    dict(nonlinearity='relu', readout='sum', final_readout='sum', jump_mode=None, num_classes=1),
+    dict(nonlinearity='elu', readout='mean', final_readout='mean', jump_mode=None, num_classes=3),
+    dict(nonlinearity='tanh', readout='sum', final_readout='sum', jump_mode='cat', num_classes=2),
+    dict(nonlinearity='relu', readout='sum', final_readout='sum', jump_mode=None, num_classes=1, drop_rings=True),
+])
+def test_fused_readout_head_equals_torch_head(cfg):
+    """pool_complex + lin1s + act + sum/mean + lin2 as one kernel (`csrc/head.cu`) against the same model with
+    `fuse_readout = False` (segment-pool kernel + torch Linear modules): outputs, input gradients (through the last
+    layer's parameters) and every head parameter gradient, fp32 rtol 1e-5. Covers mean pooling / mean over
+    dimensions, the bias-free `jump_mode='cat'` head, several output columns, and a batch without 2-cells (the
+    absent dimension pools to zeros and still contributes act(bias), reference mp/nn.py:50-60)."""
+    from cwn_b200.mp.models import SparseCIN
+    cfg = dict(cfg)
+    drop_rings = cfg.pop('drop_rings', False)
+    torch.manual_seed(4)
+    model = SparseCIN(num_input_features=16, num_layers=2, hidden=32, dropout_rate=0.0, max_dim=2,
+                      use_coboundaries=True, train_eps=True, **cfg).to(DEV).train()
+    comps = synthetic.float_feature_complexes(9, 16, seed=3, ragged=True)
+    if drop_rings:
+        from cwn_b200.data.complex import Complex
+        comps = [Complex(*[c.cochains[d] for d in range(2)], y=c.y) for c in comps]
+        for c in comps:
+            c.cochains[1].upper_index = None
+            c.cochains[1].shared_coboundaries = None
+    results = []
+    for fuse in (True, False):
+        model.fuse_readout = fuse
+        model.zero_grad(set_to_none=True)
+        batch = ComplexBatch.from_complex_list(comps, max_dim=2).to(DEV)
+        l0 = _launches()
+        out = model(batch)
+        g = torch.Generator(device=DEV).manual_seed(1)
+        (out * torch.randn(out.shape, device=DEV, generator=g)).sum().backward()
+        results.append((out.detach().clone(), {k: p.grad.clone() for k, p in model.named_parameters()
+                                               if p.grad is not None}, _launches() - l0))
+    (o1, g1, n1), (o2, g2, n2) = results
+    assert_close(o1, o2, rtol=1e-5, atol=1e-5, what='head output')
+    assert g1.keys() == g2.keys()
+    G = max(float(v.abs().max()) for v in g2.values())
+    for k in g1:
+        assert_close(g1[k], g2[k], rtol=1e-5, atol=1e-5 * float(g2[k].abs().max()) + 2e-6 * G, what=f'grad {k}')
+
+
+def _launches():
+    from cwn_b200 import _lib
+    return _lib.launch_count()
