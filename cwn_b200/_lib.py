@@ -64,7 +64,7 @@ class UnitBwdDesc(ctypes.Structure):
                 ('g_beta', _P), ('accumulate_affine', _I32), ('g_in0', _P), ('ld_gi0', _I64), ('g_in1', _P),
                 ('ld_gi1', _I64), ('w_partials', _P), ('b_partials', _P), ('n_ctas', _I32), ('g_w', _P),
                 ('ld_gw', _I64), ('g_b', _P), ('accumulate_w', _I32), ('n_rows', _I64), ('h', _I32),
-                ('counter', _P), ('tile_rows', _I32)]
+                ('counter', _P), ('tile_rows', _I32), ('accumulate_in', _I32)]
 
 
 class CollateJob(ctypes.Structure):
@@ -91,6 +91,8 @@ _SIGNATURES = {
     'cwn_csr_plan_build_small': (ctypes.c_int, [ctypes.POINTER(PlanDesc), _i32, _c_i32p, _vp]),
     'cwn_csr_gather_reduce_f32': (ctypes.c_int, [_c_f32p, _i64, _c_i32p, _c_i32p, _i64, _i32, _c_f32p, _i64,
                                                  _c_f32p, _c_f32p, _i64, _i32, _vp]),
+    'cwn_csr_gather_reduce2_f32': (ctypes.c_int, [_c_f32p, _i64, _c_i32p, _c_i32p, _i64, _i32, _c_f32p, _i64,
+                                                  _c_f32p, _c_f32p, _i64, _c_f32p, _c_f32p, _i64, _vp]),
     'cwn_gather_rows_f32': (ctypes.c_int, [_c_f32p, _i64, _c_i64p, _i64, _i32, _f32, _c_f32p, _i64, _vp]),
     'cwn_csr_cob_fwd_f32': (ctypes.c_int, [_c_f32p, _i64, _c_f32p, _i64, _c_i32p, _c_i32p, _c_i32p, _i64, _i32,
                                            _i32, _c_f32p, _i64, _c_f32p, _c_f32p, _i64, _vp]),

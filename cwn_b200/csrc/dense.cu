@@ -1189,15 +1189,20 @@ __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_kernel(const __
           if (gi_vec && kq + 3 < K) {  // the four columns lie in one block (k0 % 4 == 0): one 128-bit store
             float* base = (kq < d.k0) ? (d.g_in0 ? d.g_in0 + (row0 + r) * d.ld_gi0 + kq : nullptr)
                                       : (d.g_in1 ? d.g_in1 + (row0 + r) * d.ld_gi1 + (kq - d.k0) : nullptr);
-            if (base) *reinterpret_cast<float4*>(base) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            if (base) {
+              float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+              if (d.accumulate_in) v = f4_add(*reinterpret_cast<const float4*>(base), v);
+              *reinterpret_cast<float4*>(base) = v;
+            }
             continue;
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int k = kq + q;
             if (k >= K) continue;
-            if (k < d.k0) { if (d.g_in0) d.g_in0[(row0 + r) * d.ld_gi0 + k] = acc[i][q]; }
-            else if (d.g_in1) d.g_in1[(row0 + r) * d.ld_gi1 + (k - d.k0)] = acc[i][q];
+            float* dst = (k < d.k0) ? (d.g_in0 ? d.g_in0 + (row0 + r) * d.ld_gi0 + k : nullptr)
+                                    : (d.g_in1 ? d.g_in1 + (row0 + r) * d.ld_gi1 + (k - d.k0) : nullptr);
+            if (dst) *dst = d.accumulate_in ? *dst + acc[i][q] : acc[i][q];
           }
         }
       }
@@ -1366,7 +1371,11 @@ __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_fast_kernel(con
 #pragma unroll
             for (int i = 0; i < R; ++i) {
               const int r = ty * R + i;
-              if (r < rows) *reinterpret_cast<float4*>(base + r * ldo) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+              if (r < rows) {
+                float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                if (d.accumulate_in) v = f4_add(*reinterpret_cast<const float4*>(base + r * ldo), v);
+                *reinterpret_cast<float4*>(base + r * ldo) = v;
+              }
             }
         }
       }

@@ -215,22 +215,26 @@ __global__ void __launch_bounds__(kThreads)
 csr_gather_reduce_kernel(const float* __restrict__ x_src, int64_t ld_src, const int32_t* __restrict__ rowptr,
                          const int32_t* __restrict__ idx, int64_t n_rows, int FV /* F / W */,
                          const float* __restrict__ x_res, int64_t ld_res, const float* __restrict__ eps,
-                         float* __restrict__ out, int64_t ld_out) {
+                         float* __restrict__ out, int64_t ld_out, const float* __restrict__ x_res2 = nullptr,
+                         int64_t ld_res2 = 0, const float* __restrict__ eps2 = nullptr) {
   using O = VecOps<V>;
   constexpr int RPB = kThreads / LPR;
   const int lane = threadIdx.x % LPR;
   const int sub = threadIdx.x / LPR;
   const float scale = x_res ? __fadd_rn(1.f, eps ? __ldg(eps) : 0.f) : 0.f;
+  const float scale2 = x_res2 ? __fadd_rn(1.f, eps2 ? __ldg(eps2) : 0.f) : 0.f;
   const uint32_t pitch_s = (uint32_t)ld_src * 4u, pitch_r = (uint32_t)ld_res * 4u, pitch_o = (uint32_t)ld_out * 4u;
+  const uint32_t pitch_r2 = (uint32_t)ld_res2 * 4u;
   for (int c0 = 0; c0 < FV; c0 += LPR * VPL) {  // one trip unless F > 4*32*VPL
     const int c = c0 + lane;
     if (c >= FV) return;  // (no warp-level primitive below: idle lanes of a narrow row may leave)
     const bool live1 = VPL == 2 && c + LPR < FV;
     const char* xs = opaque(reinterpret_cast<const char*>(x_src) + (size_t)c * sizeof(V));
     const char* xr = opaque(reinterpret_cast<const char*>(x_res) + (size_t)c * sizeof(V));
+    const char* xr2 = opaque(reinterpret_cast<const char*>(x_res2) + (size_t)c * sizeof(V));
     char* xo = reinterpret_cast<char*>(out) + (size_t)c * sizeof(V);
     for (int64_t r = (int64_t)blockIdx.x * RPB + sub; r < n_rows; r += (int64_t)gridDim.x * RPB) {
-      const int beg = __ldg(rowptr + r), end = __ldg(rowptr + r + 1);
+      const int beg = rowptr ? __ldg(rowptr + r) : 0, end = rowptr ? __ldg(rowptr + r + 1) : 0;
       V acc[VPL];
 #pragma unroll
       for (int k = 0; k < VPL; ++k) acc[k] = O::zero();
@@ -248,6 +252,7 @@ csr_gather_reduce_kernel(const float* __restrict__ x_src, int64_t ld_src, const 
         }
         // GIN residual added after the aggregation, as mp/layers.py:191-192 does
         if (x_res) a = O::add_scaled(a, scale, O::load(row_at(xr, (uint32_t)r, pitch_r) + k * LPR * (int)sizeof(V)));
+        if (x_res2) a = O::add_scaled(a, scale2, O::load(row_at(xr2, (uint32_t)r, pitch_r2) + k * LPR * (int)sizeof(V)));
         O::store(row_at(xo, (uint32_t)r, pitch_o) + k * LPR * (int)sizeof(V), a);
       }
     }
@@ -674,6 +679,34 @@ extern "C" int cwn_csr_gather_reduce_f32(const float* x_src, int64_t ld_src, con
 #undef BY_REDUCE
 #undef LAUNCH
   return launched("cwn_csr_gather_reduce_f32");
+}
+
+extern "C" int cwn_csr_gather_reduce2_f32(const float* x_src, int64_t ld_src, const int32_t* rowptr,
+                                          const int32_t* idx, int64_t n_rows, int32_t F, const float* x_res,
+                                          int64_t ld_res, const float* eps, const float* x_res2, int64_t ld_res2,
+                                          const float* eps2, float* out, int64_t ld_out, cwn_stream_t stream) {
+  if (n_rows < 0 || F <= 0 || n_rows > INT32_MAX) return fail(CWN_E_SHAPE, "cwn_csr_gather_reduce2_f32: bad n_rows/F");
+  if (n_rows == 0) return CWN_OK;
+  int rc;
+  if ((rc = check_matrix(out, ld_out, F, "out"))) return rc;
+  if (x_src && (rc = check_matrix(x_src, ld_src, F, "x_src"))) return rc;
+  if (x_res && (rc = check_matrix(x_res, ld_res, F, "x_res"))) return rc;
+  if (x_res2 && (rc = check_matrix(x_res2, ld_res2, F, "x_res2"))) return rc;
+  if (rowptr && !x_src) rowptr = nullptr;  // no source matrix: there can be no messages
+  const Geometry g = geometry(F, vec_ok(x_src, ld_src) && vec_ok(x_res, ld_res) && vec_ok(x_res2, ld_res2) &&
+                                     vec_ok(out, ld_out));
+  const int grid = grid_for(n_rows, g.lpr);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(VT, VPLV)                                                                                               \
+  csr_gather_reduce_kernel<VT, LPR, VPLV, CWN_REDUCE_ADD><<<grid, kThreads, 0, st>>>(                                    \
+      x_src, ld_src, rowptr, idx, n_rows, g.fv, x_res, ld_res, eps, out, ld_out, x_res2, ld_res2, eps2)
+  if (g.vec) {
+    if (g.vpl == 1) { CWN_DISPATCH_LPR(g.lpr, LAUNCH(float4, 1)) } else { constexpr int LPR = 32; LAUNCH(float4, 2); }
+  } else {
+    if (g.vpl == 1) { CWN_DISPATCH_LPR(g.lpr, LAUNCH(float, 1)) } else { constexpr int LPR = 32; LAUNCH(float, 2); }
+  }
+#undef LAUNCH
+  return launched("cwn_csr_gather_reduce2_f32");
 }
 
 extern "C" int cwn_gather_rows_f32(const float* x, int64_t ld_x, const int64_t* idx, int64_t E, int32_t F,

@@ -105,6 +105,16 @@ int cwn_csr_gather_reduce_f32(const float* x_src, int64_t ld_src, const int32_t*
                               int64_t n_rows, int32_t F, const float* x_res, int64_t ld_res, const float* eps,
                               float* out, int64_t ld_out, int32_t reduce, cwn_stream_t stream);
 
+/* The pass above with a SECOND residual operand and an optional plan:
+ *   out[r,:] = (1+eps) * x_res[r,:] + (1+eps2) * x_res2[r,:] + SUM_{i in row r} x_src[idx[i],:]
+ * rowptr == NULL means "no messages" (out = the two residual terms). This is the gradient fan-in of a cochain's features
+ * inside one SparseCINConv layer: (1+eps1) gU_d + (1+eps2) gB_d + the transposed boundary pass of dimension d+1 —
+ * one launch instead of a gather, two scaled copies and two additions. x_res / x_res2 nullable. */
+int cwn_csr_gather_reduce2_f32(const float* x_src, int64_t ld_src, const int32_t* rowptr, const int32_t* idx,
+                               int64_t n_rows, int32_t F, const float* x_res, int64_t ld_res, const float* eps,
+                               const float* x_res2, int64_t ld_res2, const float* eps2, float* out, int64_t ld_out,
+                               cwn_stream_t stream);
+
 /* Row gather out[e,:] = scale * x[idx[e],:] (int64 idx straight from the API). Used for operands of user-defined
  * message hooks (reference __lift__, mp/cell_mp.py:195-198), lazily requested `up_attr`/`down_attr`
  * (data/complex.py:579-580,587-588) and the gradient of the readout. */
@@ -216,6 +226,10 @@ typedef struct {
   int64_t n_rows; int32_t h;
   int32_t* counter;      /* nullable: zero int32; if set, the last CTA of cwn_unit_bwd_reduce_grouped performs step 2 */
   int32_t tile_rows;     /* 64 or 32 (0 = 64), same for a whole group; sizes red_partials and bounds n_ctas */
+  int32_t accumulate_in; /* step 3 adds the input gradient INTO g_in0 / g_in1 instead of overwriting them (every element is
+                          * owned by one thread: deterministic). Lets a caller sum the gradient contributions of several
+                          * consumers of one tensor without extra elementwise launches; problems of ONE launch must not
+                          * share an output buffer */
 } cwn_unit_bwd_desc;
 int cwn_unit_bwd_reduce_grouped(const cwn_unit_bwd_desc* descs, int32_t n, cwn_stream_t stream);
 int cwn_unit_bwd_finalize_grouped(const cwn_unit_bwd_desc* descs, int32_t n, cwn_stream_t stream);
