@@ -602,3 +602,228 @@ def readout_head(model, xs, data, act_name):
            'pool_mean': int(model.readout == 'mean'), 'final_mean': int(model.final_readout == 'mean'),
            'lin1s': lin1s, 'lin2': lin2}
     return _ReadoutHead.apply(cfg, lin2.weight, lin2.bias, *sel, *[l.weight for l in lin1s], *[l.bias for l in lin1s])
+
+
+# ----------------------------------------------------------------------------------------------- layer aggregation
+def _scale_rows(x, eps, x2=None, eps2=None, src=None, plan=None):
+    """(1+eps) x [+ (1+eps2) x2] [+ SUM over `plan` rows of src[idx]] in one launch (cwn_csr_gather_reduce2_f32)."""
+    n, F = x.size(0), x.size(1)
+    out = torch.empty(n, F, dtype=torch.float32, device=x.device)
+    E = plan.pay0.numel() if plan is not None else 0
+    algo = 16 * E + 4 * F * (n * (2 + (x2 is not None)) + (src.size(0) if src is not None else 0))
+    ops._call('csr_gather_reduce', algo, _lib.load().cwn_csr_gather_reduce2_f32,
+              _p(src) if E else None, src.stride(0) if src is not None else F,
+              plan.rowptr.data_ptr() if E else None, _p(plan.pay0) if E else None, n, F,
+              _p(x), x.stride(0), _p(eps), _p(x2), x2.stride(0) if x2 is not None else F, _p(eps2), _p(out), F,
+              ops._stream())
+    return out
+
+
+class _LayerAggregate(Function):
+    """Every aggregation pass of one SparseCINConv layer — all cochain dimensions, upper and boundary branches, the
+    split-weight products of the coboundary message nets — as ONE autograd node.
+
+        u_d = SUM_up act(P_d[src] + Q_d[cob]) + (1+eps1_d) x_d       P_d = x_d W1_d^T,  Q_d = x_{d+1} W2_d^T + b_d
+        b_d = SUM_bnd x_{d-1}[src]            + (1+eps2_d) x_d       (reference mp/layers.py:184-199, 210-214, 290-299)
+
+    Why one node: x_d feeds five consumers (two residuals, P_d, Q_{d-1}, the boundary pass of d+1). As separate
+    autograd nodes their gradients meet in the engine as 2 scaled copies + 4 elementwise additions per dimension per
+    layer (~70 launches per step). Here the backward computes
+        gx_d  = (1+eps1_d) gU_d + (1+eps2_d) gB_d + transposed boundary pass of gB_{d+1}      (one launch per d)
+        gx_d += gP_d W1_d ;  gx_{d+1} += gQ_d W2_d                                            (accumulating GEMM epilogues)
+    so nothing is left for the engine to add."""
+
+    @staticmethod
+    def forward(ctx, cfg, *tensors):
+        from cwn_b200.streams import run_concurrently
+        n = cfg['n_dims']
+        xs = [t if t.stride(1) == 1 else t.contiguous() for t in tensors[:n]]
+        eps = list(tensors[n:3 * n])                       # eps1_0, eps2_0, eps1_1, ...
+        wb = list(tensors[3 * n:])                         # (weight, bias) per dimension with a coboundary up pass
+        dev = xs[0].device
+        ups, bnds = cfg['ups'], cfg['bnds']
+        cob_dims = [d for d in range(n) if ups[d] is not None]
+        with torch.cuda.device(dev):
+            prods = {}
+            if cob_dims:
+                problems = []
+                for i, d in enumerate(cob_dims):
+                    w, b = wb[2 * i], wb[2 * i + 1]
+                    fx = xs[d].size(1)
+                    problems += [(xs[d], w, 0, None), (xs[d + 1], w, fx, b)]
+                outs = grouped_linear(problems)            # autograd is off inside Function.forward: forward only
+                for i, d in enumerate(cob_dims):
+                    prods[d] = (outs[2 * i], outs[2 * i + 1])
+            thunks = []
+            for d in range(n):
+                x, e1, e2 = xs[d], eps[2 * d], eps[2 * d + 1]
+                if ups[d] is not None:
+                    adj, act = ups[d]
+                    thunks.append(lambda x=x, e1=e1, adj=adj, act=act, pq=prods[d]:
+                                  ops._CobPass.apply(pq[0], pq[1], x, e1, adj, act))
+                else:
+                    thunks.append(lambda x=x, e1=e1: _scale_rows(x, e1))
+                if bnds[d] is not None:
+                    thunks.append(lambda x=x, e2=e2, adj=bnds[d], src=xs[d - 1]:
+                                  ops._GatherReduce.apply(src, x, e2, adj, 'add'))
+                else:
+                    thunks.append(lambda x=x, e2=e2: _scale_rows(x, e2))
+            outs = run_concurrently(thunks, dev)
+        ctx.cfg, ctx.n, ctx.cob_dims = cfg, n, cob_dims
+        ctx.save_for_backward(*xs, *eps, *wb, *[t for d in cob_dims for t in prods[d]])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        from cwn_b200.streams import run_concurrently
+        cfg, n, cob_dims = ctx.cfg, ctx.n, ctx.cob_dims
+        sv = ctx.saved_tensors
+        xs, eps = list(sv[:n]), list(sv[n:3 * n])
+        wb = list(sv[3 * n:3 * n + 2 * len(cob_dims)])
+        pq = list(sv[3 * n + 2 * len(cob_dims):])
+        ups, bnds, lins = cfg['ups'], cfg['bnds'], cfg['lins']
+        dev = xs[0].device
+        lib = _lib.load()
+        gU = [gs[2 * d] for d in range(n)]
+        gB = [gs[2 * d + 1] for d in range(n)]
+        with torch.cuda.device(dev):
+            for d in range(n):
+                if gU[d] is None:
+                    gU[d] = torch.zeros_like(xs[d])
+                if gB[d] is None:
+                    gB[d] = torch.zeros_like(xs[d])
+                gU[d], gB[d] = gU[d].contiguous(), gB[d].contiguous()
+            need_x = [ctx.needs_input_grad[1 + d] for d in range(n)]
+            # a dimension's gradient buffer is also needed as the accumulation target of the linear backward
+            thunks, slots = [], []
+            for d in range(n):
+                if not need_x[d]:
+                    continue
+                up_adj = bnds[d + 1] if d + 1 < n else None    # boundary pass of d+1 reads x_d: transposed plan
+                thunks.append(lambda d=d, up_adj=up_adj: _scale_rows(
+                    gU[d], eps[2 * d], gB[d], eps[2 * d + 1],
+                    gB[d + 1] if up_adj is not None else None, up_adj.by_src if up_adj is not None else None))
+                slots.append(('x', d))
+            for i, d in enumerate(cob_dims):
+                adj, act = ups[d]
+                P, Q = pq[2 * i], pq[2 * i + 1]
+                F = P.size(1)
+                code = ops.ACT_CODES[act]
+
+                def cob_bwd(A, B_, plan, n_rows, g=gU[d], F=F, code=code):
+                    out = torch.empty(n_rows, F, dtype=torch.float32, device=dev)
+                    algo = 24 * plan.pay0.numel() + 4 * F * (g.size(0) + 2 * A.size(0) + B_.size(0))
+                    ops._call('csr_cob_bwd', algo, lib.cwn_csr_cob_bwd_f32, _p(g), g.stride(0), _p(A), A.stride(0),
+                              _p(B_), B_.stride(0), plan.rowptr.data_ptr(), _p(plan.pay0), _p(plan.pay1), n_rows, F,
+                              code, _p(out), F, ops._stream())
+                    return out
+                thunks.append(lambda P=P, Q=Q, adj=adj, f=cob_bwd: f(P, Q, adj.by_src, adj.n_src))
+                slots.append(('p', d))
+                thunks.append(lambda P=P, Q=Q, adj=adj, f=cob_bwd: f(Q, P, adj.by_cob, adj.n_cob))
+                slots.append(('q', d))
+            res = run_concurrently(thunks, dev)
+            gx = [None] * n
+            gP, gQ = {}, {}
+            for (kind, d), t in zip(slots, res):
+                if kind == 'x':
+                    gx[d] = t
+                elif kind == 'p':
+                    gP[d] = t
+                else:
+                    gQ[d] = t
+            # split-weight products backward: two grouped launches (the P problems, then the Q problems) so that no two
+            # problems of one launch accumulate into the same gx buffer
+            gw_out, gb_out = [], []
+            if cob_dims:
+                tr = _tile_rows([xs[d].size(0) for d in cob_dims])
+                keep, all_descs = [], []
+                bufs = []
+                for i, d in enumerate(cob_dims):
+                    lin = lins[d]
+                    dw, db = _direct_grad(lin.weight), _direct_grad(lin.bias)
+                    direct = dw is not None and db is not None
+                    if direct:
+                        bufs.append((dw, db, 1))
+                        gw_out.append(None), gb_out.append(None)
+                    else:
+                        gw, gb = torch.empty_like(wb[2 * i], memory_format=torch.contiguous_format), torch.empty_like(wb[2 * i + 1])
+                        bufs.append((gw, gb, 0))
+                        gw_out.append(gw), gb_out.append(gb)
+                for which in ('p', 'q'):
+                    descs = []
+                    for i, d in enumerate(cob_dims):
+                        w = wb[2 * i]
+                        gw, gb, acc = bufs[i]
+                        fx = xs[d].size(1)
+                        x, g, off, tgt = (xs[d], gP[d], 0, d) if which == 'p' else (xs[d + 1], gQ[d], fx, d + 1)
+                        nr, k, h = x.size(0), x.size(1), w.size(0)
+                        n_tiles = (nr + tr - 1) // tr
+                        n_ctas = min(n_tiles, 2 * 148)
+                        wp = torch.empty(max(n_ctas, 1) * h * k, dtype=torch.float32, device=dev)
+                        bp = torch.empty(max(n_ctas, 1) * h, dtype=torch.float32, device=dev)
+                        keep += [wp, bp]
+                        descs.append(_lib.UnitBwdDesc(
+                            _p(x), x.stride(0), k, None, 0, 0, None, None, None, None, None, None, 0,
+                            w.data_ptr() + 4 * off, w.stride(0), _p(g), g.stride(0), 0, 0, None, None, None, None, _p(g),
+                            g.stride(0), None, None, None, None, None, 0, _p(gx[tgt]), k, None, 0, _p(wp), _p(bp),
+                            n_ctas, gw.data_ptr() + 4 * off, gw.stride(0), _p(gb) if which == 'q' else None, acc, nr, h,
+                            None, tr, 1))
+                    _launch('cwn_unit_bwd_grouped', _lib.UnitBwdDesc, descs)
+                    all_descs += descs
+                _launch('cwn_wgrad_finalize_grouped', _lib.UnitBwdDesc, all_descs)
+            # trainable epsilons (train_eps=True): scalar reductions through torch
+            g_eps = []
+            for d in range(n):
+                for j, g in ((0, gU[d]), (1, gB[d])):
+                    e = eps[2 * d + j]
+                    g_eps.append((g * xs[d]).sum().reshape(e.shape) if ctx.needs_input_grad[1 + n + 2 * d + j] else None)
+        flat_wb = [t for pair in zip(gw_out, gb_out) for t in pair]
+        return (None, *gx, *g_eps, *flat_wb)
+
+
+def layer_aggregate(levels, cochain_params):
+    """(us, bs) of a SparseCINConv layer through `_LayerAggregate`, or NotImplemented when some level is outside its
+    closed form: upper pass = coboundary message net `act(Linear([x_j ; y_cob]))` or no upper adjacency at all,
+    boundary pass = identity messages from `x_{d-1}`, fp32 CUDA features of one width, default hooks."""
+    from cwn_b200.mp.layers import identity
+    from cwn_b200.mp.params import LazyRows
+    n = len(cochain_params)
+    xs = [p.x for p in cochain_params]
+    if not all(isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 for x in xs):
+        return NotImplemented
+    F = xs[0].size(1)
+    ups, bnds, lins, eps, wb = [], [], {}, [], []
+    for d, (level, p) in enumerate(zip(levels, cochain_params)):
+        x = xs[d]
+        if x.size(1) != F or x.size(0) < 1 or level.msg_boundaries_nn is not identity or not level._hooks_untouched():
+            return NotImplemented
+        up_index, up_attr = p.up_index, p.kwargs['up_attr']
+        if up_index is None:
+            if level.up_msg_size != F:
+                return NotImplemented
+            ups.append(None)
+        else:
+            form = level._up_message_form()
+            if form is None or form[0] != 'cob' or d + 1 >= n:
+                return NotImplemented
+            lin, act = form[1], form[2]
+            if not (isinstance(up_attr, LazyRows) and up_attr.source is xs[d + 1] and lin.in_features == 2 * F
+                    and lin.out_features == F and lin.bias is not None):
+                return NotImplemented
+            adj = ops.Adjacency.of(up_index, x.size(0), x.size(0), up_attr.index, xs[d + 1].size(0))
+            ups.append((adj, act))
+            lins[d] = lin
+            wb += [lin.weight, lin.bias]
+        b_index, b_attr = p.boundary_index, p.kwargs['boundary_attr']
+        if b_attr is None:
+            if level.boundary_msg_size != F:
+                return NotImplemented
+            bnds.append(None)
+        else:
+            if b_index is None or d == 0 or b_attr is not xs[d - 1]:
+                return NotImplemented
+            bnds.append(ops.Adjacency.of(b_index, xs[d - 1].size(0), x.size(0)))
+        eps += [level.eps1, level._boundary_eps()]
+    cfg = {'n_dims': n, 'ups': ups, 'bnds': bnds, 'lins': lins}
+    outs = _LayerAggregate.apply(cfg, *xs, *eps, *wb)
+    return list(outs[0::2]), list(outs[1::2])

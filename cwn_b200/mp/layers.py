@@ -306,6 +306,7 @@ class SparseCINConv(_PerDimension):
     (`cwn_b200.fused`); otherwise each level runs on its own (torch modules for the dense nets)."""
 
     fuse_dense = True
+    fuse_aggregation = True  # all aggregation passes of the layer as one autograd node (fused._LayerAggregate)
 
     def forward(self, *cochain_params: CochainMessagePassingParams, start_to_process=0):
         assert len(cochain_params) <= self.max_dim + 1
@@ -315,6 +316,14 @@ class SparseCINConv(_PerDimension):
             forms = getattr(self, '_dense_forms', None)
             if forms is None:
                 forms = self._dense_forms = [fused.recognise(level) for level in self.mp_levels]
+            if self.fuse_aggregation and all(f is not None for f in forms[:n]) and type(self) is SparseCINConv:
+                # every pass of the layer (+ the split-weight products) as one autograd node: see fused._LayerAggregate
+                agg = fused.layer_aggregate(self.mp_levels[:n], cochain_params)
+                if agg is not NotImplemented:
+                    us, bs = agg
+                    if fused.applicable(forms[:n], us, bs, self.mp_levels[0].training):
+                        return fused.sparse_cin_dense(forms[:n], us, bs, self.mp_levels[0].training)
+                    return [self.mp_levels[d].dense_tail(us[d], bs[d]) for d in range(n)]
             branches = [self.mp_levels[d]._fused_forward(cochain_params[d]) for d in range(n)]
             if all(f is not None for f in forms[:n]) and all(b is not NotImplemented for b in branches):
                 device = cochain_params[0].x.device

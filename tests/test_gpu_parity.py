@@ -852,3 +852,45 @@ def test_fused_readout_head_equals_torch_head(cfg):
 def _launches():
     from cwn_b200 import _lib
     return _lib.launch_count()
+
+
+@pytest.mark.parametrize('train_eps,use_cob,n_complexes', [(False, True, 128), (True, True, 9), (True, False, 9)])
+def test_layer_aggregation_node_equals_separate_passes(train_eps, use_cob, n_complexes):
+    """`fused._LayerAggregate` (all aggregation passes of a layer + the split-weight products as ONE autograd node whose
+    backward sums the five gradient contributions of every x_d inside the kernels) against the same layer with one
+    autograd node per pass (`fuse_aggregation = False`, gradients summed by the autograd engine). Forward must be
+    bit-identical (same kernels, same order); gradients agree to fp32 rounding of a different summation order.
+    With identity upper messages (`use_coboundaries=False`) the node does not apply and both runs take the old path."""
+    from cwn_b200.mp.layers import SparseCINConv
+    from cwn_b200.mp.nn import get_graph_norm, get_nonlinearity
+    torch.manual_seed(6)
+    F = 32
+    conv = SparseCINConv(F, F, F, None, None, None, None, layer_dim=F, hidden=F, act_module=get_nonlinearity('relu'),
+                         graph_norm=get_graph_norm('bn'), use_coboundaries=use_cob, train_eps=train_eps).to(DEV).train()
+    state = {k: v.clone() for k, v in conv.state_dict().items()}
+    results = []
+    for fuse in (True, False):
+        conv.fuse_aggregation = fuse
+        conv.load_state_dict(state)
+        conv.zero_grad(set_to_none=True)
+        batch = ComplexBatch.from_complex_list(
+            synthetic.float_feature_complexes(n_complexes, F, seed=8, ragged=True)).to(DEV)
+        for d in range(3):
+            batch.cochains[d]._x = batch.cochains[d].x.clone().requires_grad_(True)
+        l0 = _launches()
+        outs = conv(*batch.get_all_cochain_params(max_dim=2, include_down_features=False))
+        g = torch.Generator(device=DEV).manual_seed(3)
+        sum((o * torch.randn(o.shape, device=DEV, generator=g)).sum() for o in outs).backward()
+        results.append(([o.detach().clone() for o in outs], [batch.cochains[d].x.grad.clone() for d in range(3)],
+                        {k: p.grad.clone() for k, p in conv.named_parameters() if p.grad is not None},
+                        _launches() - l0))
+    (o1, gx1, p1, n1), (o2, gx2, p2, n2) = results
+    for d in range(3):
+        assert torch.equal(o1[d], o2[d])
+        assert_close(gx1[d], gx2[d], rtol=1e-5, atol=1e-5 * float(gx2[d].abs().max()), what=f'grad x {d}')
+    assert p1.keys() == p2.keys()
+    G = max(float(v.abs().max()) for v in p2.values())
+    for k in p1:
+        assert_close(p1[k], p2[k], rtol=1e-5, atol=1e-5 * float(p2[k].abs().max()) + 2e-6 * G, what=f'grad {k}')
+    if use_cob:
+        assert n1 != n2  # the node really ran (its launch count differs from the per-pass path)
