@@ -445,10 +445,11 @@ def run_cwn(args, rank, world, local_rank):
 
     # ---- per-kernel roofline of the step (instrumented eager re-run of the same steps; every rank takes part because
     #      the step contains the gradient all-reduce)
-    with ops.KernelProfile() as prof:
-        for i in range(args.steps):
+    with ops.KernelProfile(pad_cycles=120_000) as prof:  # ~60 us of spin before each launch: see KernelProfile
+        for i in range(min(args.steps, 5)):
             flush.zero_()
             eager_resident_step(i)
+    n_prof = min(args.steps, 5)
     summary = prof.summary()
     barrier()
     if rank != 0:
@@ -457,13 +458,21 @@ def run_cwn(args, rank, world, local_rank):
     dom = max((k for k in summary if k != 'csr_plan_build'), key=lambda k: summary[k]['ms'])
     rec = summary[dom]
     achieved = rec['bytes'] / (rec['ms'] * 1e-3) / 1e9
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), if any
+    traffic, tpath = None, os.path.join(ROOT, 'profiles', 'r1_ncu_dram_traffic.json')
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dom, {}).get('dram_bytes_per_launch')
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
-                'launches_per_step': rec['launches'] / args.steps,
+                'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                'launches_per_step': rec['launches'] / n_prof,
                 'avg_launch_us': 1e3 * rec['ms'] / rec['launches'],
                 'algorithmic_bytes_per_launch': rec['bytes'] / rec['launches'],
-                'kernel_ms_per_step': {k: v['ms'] / args.steps for k, v in summary.items()},
-                'timed_in': 'instrumented eager re-run of the same steps (CUDA events around every C-ABI launch)',
+                'kernel_ms_per_step': {k: v['ms'] / n_prof for k, v in summary.items()},
+                'timed_in': 'instrumented eager re-run of the same steps: CUDA events on the launching stream around '
+                            'every C-ABI launch, each preceded by a ~60 us spin kernel so that the event pair is queued '
+                            'before the GPU reaches it and brackets device time only (an eager step is host-bound); the median '
+                            'cost of an empty event pair is subtracted',
+                'event_pair_overhead_us': 1e3 * prof.overhead_ms,
                 'note': 'at batch 128 every adjacency pass moves ~1-2 MB (L2-resident): the step is launch/latency '
                         'bound, see kernel_sweep for the HBM-bound regime'}
     line = {

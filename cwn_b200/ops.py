@@ -53,10 +53,17 @@ def _stream():
 # --------------------------------------------------------------------------------------------- per-kernel timing
 class KernelProfile(object):
     """CUDA-event timing of every C-ABI launch made while active (bench.py's roofline leg). Events are recorded on
-    the launching stream right around the launch; `summary()` synchronises once at the end."""
+    the launching stream right around the launch; `summary()` synchronises once at the end.
 
-    def __init__(self):
+    `pad_cycles` > 0 enqueues a spin kernel of that many SM clocks on the launching stream before the start event. An
+    eager step is host-bound (a launch through ctypes takes longer than a 3-15 us kernel runs), so without it the
+    stream is idle when the start event is reached and the event pair measures the HOST gap until the kernel arrives
+    (measured: 16 us for a 3.3 us kernel). With the pad the start event, the kernel and the stop event are all queued
+    while the GPU spins, and the pair brackets device time only."""
+
+    def __init__(self, pad_cycles: int = 0):
         self.records = []  # (kernel name, algorithmic bytes, start event, stop event)
+        self.pad_cycles = int(pad_cycles)
 
     def __enter__(self):
         global _profile
@@ -67,13 +74,28 @@ class KernelProfile(object):
         global _profile
         _profile = None
 
+    def event_overhead_ms(self, n=20):
+        """Median elapsed time of an EMPTY event pair queued behind a pad (what a pair costs with nothing between)."""
+        if not self.pad_cycles:
+            return 0.0
+        pairs = []
+        for _ in range(n):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(self.pad_cycles)
+            e0.record()
+            e1.record()
+            pairs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sorted(a.elapsed_time(b) for a, b in pairs)[n // 2]
+
     def summary(self):
         torch.cuda.synchronize()
+        self.overhead_ms = self.event_overhead_ms()
         out = {}
         for name, nbytes, e0, e1 in self.records:
             rec = out.setdefault(name, {'launches': 0, 'ms': 0.0, 'bytes': 0})
             rec['launches'] += 1
-            rec['ms'] += e0.elapsed_time(e1)
+            rec['ms'] += max(e0.elapsed_time(e1) - self.overhead_ms, 0.0)
             rec['bytes'] += nbytes
         return out
 
@@ -87,6 +109,8 @@ def _call(name, algo_bytes, fn, *args):
         _lib.check(fn(*args), name)
         return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if _profile.pad_cycles:
+        torch.cuda._sleep(_profile.pad_cycles)
     e0.record()
     _lib.check(fn(*args), name)
     e1.record()
