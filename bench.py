@@ -26,6 +26,11 @@ import sys
 import threading
 import time
 
+# NCCL_DEBUG=VERSION makes NCCL print its banner on STDOUT at communicator creation; stdout of rank 0 must carry exactly
+# one JSON line (the driver parses it), so the banner level is mapped to WARN (INFO and above are left to the user)
+if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+    os.environ['NCCL_DEBUG'] = 'WARN'
+
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
