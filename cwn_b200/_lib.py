@@ -93,6 +93,10 @@ _SIGNATURES = {
                                                  _c_f32p, _c_f32p, _i64, _i32, _vp]),
     'cwn_csr_gather_reduce2_f32': (ctypes.c_int, [_c_f32p, _i64, _c_i32p, _c_i32p, _i64, _i32, _c_f32p, _i64,
                                                   _c_f32p, _c_f32p, _i64, _c_f32p, _c_f32p, _i64, _vp]),
+    'cwn_csr_gather_max_arg_f32': (ctypes.c_int, [_c_f32p, _i64, _c_i32p, _c_i32p, _c_i32p, _i64, _i32, _c_f32p, _i64,
+                                                  _c_i32p, _vp]),
+    'cwn_csr_max_bwd_f32': (ctypes.c_int, [_c_f32p, _i64, _c_i32p, _c_i32p, _c_i32p, _c_i32p, _i64, _i32, _c_f32p, _i64,
+                                           _vp]),
     'cwn_gather_rows_f32': (ctypes.c_int, [_c_f32p, _i64, _c_i64p, _i64, _i32, _f32, _c_f32p, _i64, _vp]),
     'cwn_csr_cob_fwd_f32': (ctypes.c_int, [_c_f32p, _i64, _c_f32p, _i64, _c_i32p, _c_i32p, _c_i32p, _i64, _i32,
                                            _i32, _c_f32p, _i64, _c_f32p, _c_f32p, _i64, _vp]),

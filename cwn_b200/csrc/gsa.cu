@@ -443,6 +443,52 @@ gather_rows_kernel(const float* __restrict__ x, int64_t ld_x, const int64_t* __r
 #include "gsa_pipelined.cuh"
 namespace cwn {
 
+// ---- max aggregation with argument tracking (backward support). torch_scatter's CPU scatter_max keeps the FIRST
+// maximum in message order (strict '>'), which is what a sequential walk in plan order does; the backward routes the
+// gradient of (row, feature) to that one message. One thread per (row, feature), coalesced across features.
+__global__ void csr_gather_max_arg_kernel(const float* __restrict__ x_src, int64_t ld_src,
+                                          const int32_t* __restrict__ rowptr, const int32_t* __restrict__ idx,
+                                          const int32_t* __restrict__ perm, int64_t n_rows, int F,
+                                          float* __restrict__ out, int64_t ld_out, int32_t* __restrict__ arg) {
+  const int64_t total = n_rows * F;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / F;
+    const int f = (int)(e - r * F);
+    const int beg = __ldg(rowptr + r), end = __ldg(rowptr + r + 1);
+    float best = 0.f;  // rows without messages stay zero, as torch_scatter fills them
+    int32_t who = -1;
+    for (int i = beg; i < end; ++i) {
+      const float v = __ldg(x_src + (int64_t)__ldg(idx + i) * ld_src + f);
+      if (i == beg || v > best) {
+        best = v;
+        who = perm ? __ldg(perm + i) : i;
+      }
+    }
+    out[r * ld_out + f] = best;
+    arg[e] = who;
+  }
+}
+
+// gX[s, f] = SUM_{i in row s of the by-source plan} (arg[dst[i], f] == message id of i) ? G[dst[i], f] : 0
+__global__ void csr_max_bwd_kernel(const float* __restrict__ G, int64_t ld_g, const int32_t* __restrict__ arg,
+                                   const int32_t* __restrict__ rowptr, const int32_t* __restrict__ dst,
+                                   const int32_t* __restrict__ perm, int64_t n_rows, int F, float* __restrict__ gX,
+                                   int64_t ld_gx) {
+  const int64_t total = n_rows * F;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s_ = e / F;
+    const int f = (int)(e - s_ * F);
+    const int beg = __ldg(rowptr + s_), end = __ldg(rowptr + s_ + 1);
+    float acc = 0.f;
+    for (int i = beg; i < end; ++i) {
+      const int64_t t = __ldg(dst + i);
+      const int32_t id = perm ? __ldg(perm + i) : i;
+      if (__ldg(arg + t * F + f) == id) acc = __fadd_rn(acc, __ldg(G + t * ld_g + f));
+    }
+    gX[s_ * ld_gx + f] = acc;
+  }
+}
+
 __global__ void check_index_range_kernel(const int64_t* __restrict__ idx, int64_t E, int64_t n, int32_t* flags) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t v = idx[e];
@@ -707,6 +753,37 @@ extern "C" int cwn_csr_gather_reduce2_f32(const float* x_src, int64_t ld_src, co
   }
 #undef LAUNCH
   return launched("cwn_csr_gather_reduce2_f32");
+}
+
+extern "C" int cwn_csr_gather_max_arg_f32(const float* x_src, int64_t ld_src, const int32_t* rowptr, const int32_t* idx,
+                                          const int32_t* perm, int64_t n_rows, int32_t F, float* out, int64_t ld_out,
+                                          int32_t* arg, cwn_stream_t stream) {
+  if (n_rows < 0 || F <= 0 || n_rows > INT32_MAX) return fail(CWN_E_SHAPE, "cwn_csr_gather_max_arg_f32: bad n_rows/F");
+  if (n_rows == 0) return CWN_OK;
+  if (!rowptr || !arg) return fail(CWN_E_NULL, "rowptr/arg");
+  int rc;
+  if ((rc = check_matrix(out, ld_out, F, "out"))) return rc;
+  if (x_src && (rc = check_matrix(x_src, ld_src, F, "x_src"))) return rc;
+  int64_t need = (n_rows * F + 255) / 256;
+  if (need > (int64_t)kNumSMs * 16) need = (int64_t)kNumSMs * 16;
+  csr_gather_max_arg_kernel<<<(int)need, 256, 0, (cudaStream_t)stream>>>(x_src, ld_src, rowptr, idx, perm, n_rows, F, out,
+                                                                         ld_out, arg);
+  return launched("cwn_csr_gather_max_arg_f32");
+}
+
+extern "C" int cwn_csr_max_bwd_f32(const float* G, int64_t ld_g, const int32_t* arg, const int32_t* rowptr,
+                                   const int32_t* dst, const int32_t* perm, int64_t n_rows, int32_t F, float* gX,
+                                   int64_t ld_gx, cwn_stream_t stream) {
+  if (n_rows < 0 || F <= 0 || n_rows > INT32_MAX) return fail(CWN_E_SHAPE, "cwn_csr_max_bwd_f32: bad n_rows/F");
+  if (n_rows == 0) return CWN_OK;
+  if (!rowptr) return fail(CWN_E_NULL, "rowptr");
+  int rc;
+  if ((rc = check_matrix(gX, ld_gx, F, "gX"))) return rc;
+  if (G && (rc = check_matrix(G, ld_g, F, "G"))) return rc;
+  int64_t need = (n_rows * F + 255) / 256;
+  if (need > (int64_t)kNumSMs * 16) need = (int64_t)kNumSMs * 16;
+  csr_max_bwd_kernel<<<(int)need, 256, 0, (cudaStream_t)stream>>>(G, ld_g, arg, rowptr, dst, perm, n_rows, F, gX, ld_gx);
+  return launched("cwn_csr_max_bwd_f32");
 }
 
 extern "C" int cwn_gather_rows_f32(const float* x, int64_t ld_x, const int64_t* idx, int64_t E, int32_t F,

@@ -138,6 +138,77 @@ class CINConv(_PerDimension):
         return super(CINConv, self).forward(*cochain_params)
 
 
+class EdgeCINConv(torch.nn.Module):
+    """CIN layer that passes messages only up to the edges (reference `mp/layers.py:127-151`): a vertex level with upper
+    messages and an edge level with upper and lower messages, each a `CINCochainConv` with its own nets. Vertices have
+    no lower adjacency, so their down net is the reference's `lambda *args: None`."""
+
+    def __init__(self, up_msg_size: int, down_msg_size: int, v_msg_up_nn: Callable, e_msg_down_nn: Callable,
+                 e_msg_up_nn: Callable, v_update_nn: Callable, e_update_nn: Callable, eps: float = 0.,
+                 train_eps=False):
+        super(EdgeCINConv, self).__init__()
+        self.max_dim = 1
+        self.mp_levels = torch.nn.ModuleList()
+        v_mp = CINCochainConv(up_msg_size, down_msg_size, v_msg_up_nn, lambda *args: None, v_update_nn, eps, train_eps)
+        e_mp = CINCochainConv(up_msg_size, down_msg_size, e_msg_up_nn, e_msg_down_nn, e_update_nn, eps, train_eps)
+        self.mp_levels.extend([v_mp, e_mp])
+
+    def forward(self, *cochain_params: CochainMessagePassingParams):
+        assert len(cochain_params) <= self.max_dim + 1
+        device = cochain_params[0].x.device if len(cochain_params) else None
+        # the two levels own separate nets: independent branches
+        return run_concurrently([(lambda d=d: self.mp_levels[d].forward(cochain_params[d]))
+                                 for d in range(len(cochain_params))], device)
+
+    def reset_parameters(self):
+        for level in self.mp_levels:
+            level.reset_parameters()
+
+
+class OrientedConv(CochainMessagePassing):
+    """Orientation-equivariant edge convolution (reference `mp/layers.py:430-470`): messages are the neighbour's
+    features times the relative orientation (+-1) of the two cells, carried through `up_attr` / `down_attr`;
+    out = act(update(x) + update_up(SUM_up) + update_down(SUM_down)). Takes a `Cochain` (not params), as the reference."""
+
+    def __init__(self, dim: int, up_msg_size: int, down_msg_size: int, update_up_nn: Optional[Callable],
+                 update_down_nn: Optional[Callable], update_nn: Optional[Callable], act_fn, orient=True):
+        super(OrientedConv, self).__init__(up_msg_size, down_msg_size, use_boundary_msg=False)
+        self.dim = dim
+        self.update_up_nn = update_up_nn
+        self.update_down_nn = update_down_nn
+        self.update_nn = update_nn
+        self.act_fn = act_fn
+        self.orient = orient
+
+    def forward(self, cochain):
+        assert len(cochain.upper_orient) == cochain.upper_index.size(1)
+        assert len(cochain.lower_orient) == cochain.lower_index.size(1)
+        # (the reference also asserts `index.max() < len(x)`: a device->host sync per layer; out-of-range indices are
+        #  caught by cwn_check_index_range in debug mode instead)
+        out_up, out_down, _ = self.propagate(cochain.upper_index, cochain.lower_index, None, x=cochain.x,
+                                             up_attr=cochain.upper_orient.view(-1, 1),
+                                             down_attr=cochain.lower_orient.view(-1, 1))
+        out_up = self.update_up_nn(out_up)
+        out_down = self.update_down_nn(out_down)
+        x = self.update_nn(cochain.x)
+        return self.act_fn(x + out_up + out_down)
+
+    def reset_parameters(self):
+        reset(self.update_up_nn)
+        reset(self.update_down_nn)
+        reset(self.update_nn)
+
+    def message_up(self, up_x_j: Tensor, up_attr: Tensor) -> Tensor:
+        if self.orient:
+            return up_x_j * up_attr
+        return up_x_j
+
+    def message_down(self, down_x_j: Tensor, down_attr: Tensor) -> Tensor:
+        if self.orient:
+            return down_x_j * down_attr
+        return down_x_j
+
+
 # ----------------------------------------------------------------------------------------------- sparse CIN
 class Catter(torch.nn.Module):
     def forward(self, x):

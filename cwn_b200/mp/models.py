@@ -7,7 +7,7 @@ from torch.nn import Linear, Sequential, BatchNorm1d as BN
 
 from cwn_b200 import ops
 from cwn_b200.data.complex import ComplexBatch
-from cwn_b200.mp.layers import CINConv, CINppConv, SparseCINConv
+from cwn_b200.mp.layers import CINConv, CINppConv, EdgeCINConv, OrientedConv, SparseCINConv
 from cwn_b200.mp.nn import (JumpingKnowledge, get_graph_norm, get_nonlinearity, get_pooling_fn,
                             num_complexes_of, pool_complex)
 
@@ -217,3 +217,165 @@ class CINpp(SparseCIN):
                           passed_update_up_nn=None, passed_update_down_nn=None, passed_update_boundaries_nn=None,
                           train_eps=train_eps, max_dim=self.max_dim, hidden=hidden, act_module=act_module,
                           layer_dim=layer_dim, graph_norm=self.graph_norm, use_coboundaries=use_coboundaries))
+
+
+class EdgeCIN0(torch.nn.Module, _JumpMixin):
+    """CIN0 operating up to the edges; two-cell features may feed the edges' upper messages and be refreshed by their
+    own MLP between layers (reference `mp/models.py:286-419`)."""
+
+    def __init__(self, num_input_features, num_classes, num_layers, hidden, dropout_rate: float = 0.5, jump_mode=None,
+                 nonlinearity='relu', include_top_features=True, update_top_features=True, readout='sum'):
+        super(EdgeCIN0, self).__init__()
+        self.max_dim = 1
+        self.include_top_features = include_top_features
+        self.update_top_features = include_top_features and update_top_features
+        self.dropout_rate = dropout_rate
+        self.jump_mode = jump_mode
+        self.convs = torch.nn.ModuleList()
+        self.update_top_nns = torch.nn.ModuleList()
+        self.nonlinearity = nonlinearity
+        self.readout = readout
+        self.pooling_fn = get_pooling_fn(readout)
+        act = get_nonlinearity(nonlinearity, return_module=True)
+
+        def update_mlp(layer_dim):
+            return Sequential(Linear(layer_dim, hidden), act(), Linear(hidden, hidden), act(), BN(hidden))
+
+        for i in range(num_layers):
+            layer_dim = num_input_features if i == 0 else hidden
+            v_conv_update, e_conv_update = update_mlp(layer_dim), update_mlp(layer_dim)
+            v_conv_up = Sequential(Linear(layer_dim * 2, layer_dim), act(), BN(layer_dim))
+            e_conv_down = Sequential(Linear(layer_dim * 2, layer_dim), act(), BN(layer_dim))
+            e_conv_inp_dim = layer_dim * 2 if include_top_features else layer_dim
+            e_conv_up = Sequential(Linear(e_conv_inp_dim, layer_dim), act(), BN(layer_dim))
+            self.convs.append(EdgeCINConv(layer_dim, layer_dim, v_conv_up, e_conv_down, e_conv_up, v_conv_update,
+                                          e_conv_update, train_eps=False))
+            if self.update_top_features and i < num_layers - 1:
+                self.update_top_nns.append(update_mlp(layer_dim))
+        self.jump = JumpingKnowledge(jump_mode) if jump_mode is not None else None
+        self.lin1 = Linear(num_layers * hidden if jump_mode == 'cat' else hidden, hidden)
+        self.lin2 = Linear(hidden, num_classes)
+
+    def reset_parameters(self):
+        for conv in self.convs:
+            conv.reset_parameters()
+        if self.jump_mode is not None:
+            self.jump.reset_parameters()
+        self.lin1.reset_parameters()
+        self.lin2.reset_parameters()
+        for net in self.update_top_nns:
+            for m in net:
+                if hasattr(m, 'reset_parameters'):
+                    m.reset_parameters()
+
+    def pool_complex(self, xs, data):
+        return pool_complex(xs, data, self.max_dim, self.readout)
+
+    def forward(self, data: ComplexBatch):
+        model_nonlinearity = get_nonlinearity(self.nonlinearity, return_module=False)
+        xs, jump_xs = None, None
+        for c, conv in enumerate(self.convs):
+            params = data.get_all_cochain_params(max_dim=self.max_dim, include_top_features=self.include_top_features)
+            xs = conv(*params)
+            if self.update_top_features and c < len(self.convs) - 1 and 2 in data.cochains:
+                top_x = self.update_top_nns[c](data.cochains[2].x)
+                data.set_xs(xs + [top_x])
+            else:
+                data.set_xs(xs)
+            if self.jump_mode is not None:
+                if jump_xs is None:
+                    jump_xs = [[] for _ in xs]
+                for i, x in enumerate(xs):
+                    jump_xs[i] += [x]
+        if self.jump_mode is not None:
+            xs = self.jump_complex(jump_xs)
+        pooled_xs = self.pool_complex(xs, data)
+        x = pooled_xs.sum(dim=0)
+        x = model_nonlinearity(self.lin1(x))
+        x = F.dropout(x, p=self.dropout_rate, training=self.training)
+        return self.lin2(x)
+
+    def __repr__(self):
+        return self.__class__.__name__
+
+
+class _OrientedEdgeModel(torch.nn.Module):
+    """Shared body of `EdgeOrient` / `EdgeMPNN` (reference `mp/models.py:474-608`): a stack of `OrientedConv` on ONE
+    cochain batch of edges, |.| for orientation invariance, per-complex readout, lin1 + ReLU, lin2."""
+
+    def _build(self, num_input_features, num_classes, num_layers, hidden, dropout_rate, jump_mode, nonlinearity,
+               readout, fully_invar, with_up):
+        self.max_dim = 1
+        self.fully_invar = fully_invar
+        orient = not self.fully_invar
+        self.dropout_rate = dropout_rate
+        self.jump_mode = jump_mode
+        self.convs = torch.nn.ModuleList()
+        self.nonlinearity = nonlinearity
+        self.readout = readout
+        self.pooling_fn = get_pooling_fn(readout)
+        for i in range(num_layers):
+            layer_dim = num_input_features if i == 0 else hidden
+            # biases must stay off: with them the layer is not orientation-equivariant (reference :489)
+            update_up = Linear(layer_dim, hidden, bias=False) if with_up else (lambda x: 0)
+            update_down = Linear(layer_dim, hidden, bias=False)
+            update = Linear(layer_dim, hidden, bias=False)
+            self.convs.append(OrientedConv(dim=1, up_msg_size=layer_dim, down_msg_size=layer_dim,
+                                           update_up_nn=update_up, update_down_nn=update_down, update_nn=update,
+                                           act_fn=get_nonlinearity(nonlinearity, return_module=False), orient=orient))
+        self.jump = JumpingKnowledge(jump_mode) if jump_mode is not None else None
+        self.lin1 = Linear(hidden, hidden)
+        self.lin2 = Linear(hidden, num_classes)
+
+    def reset_parameters(self):
+        for conv in self.convs:
+            conv.reset_parameters()
+        if self.jump_mode is not None:
+            self.jump.reset_parameters()
+        self.lin1.reset_parameters()
+        self.lin2.reset_parameters()
+
+    def forward(self, data, include_partial=False):
+        if self.fully_invar:
+            data.x = torch.abs(data.x)
+        x = None
+        for conv in self.convs:
+            x = conv(data)
+            data.x = x
+        cell_pred = x
+        batch_size = getattr(data, 'num_cochains', None)
+        if batch_size is None:
+            batch_size = int(data.batch.max()) + 1
+        if not self.fully_invar:
+            x = torch.abs(x)
+        x = self.pooling_fn(x, data.batch, size=batch_size)
+        # invariance holds from here on: any non-linearity will do; the reference picks ReLU
+        x = torch.relu(self.lin1(x))
+        x = F.dropout(x, p=self.dropout_rate, training=self.training)
+        x = self.lin2(x)
+        if include_partial:
+            return x, cell_pred
+        return x
+
+    def __repr__(self):
+        return self.__class__.__name__
+
+
+class EdgeOrient(_OrientedEdgeModel):
+    """Edge-signal model that takes edge orientation into account (reference `mp/models.py:474-545`)."""
+
+    def __init__(self, num_input_features, num_classes, num_layers, hidden, dropout_rate: float = 0.0, jump_mode=None,
+                 nonlinearity='id', readout='sum', fully_invar=False):
+        super(EdgeOrient, self).__init__()
+        self._build(num_input_features, num_classes, num_layers, hidden, dropout_rate, jump_mode, nonlinearity, readout,
+                    fully_invar, with_up=True)
+
+
+class EdgeMPNN(_OrientedEdgeModel):
+    """MPNN on the line graph: lower adjacencies only (reference `mp/models.py:548-608`)."""
+
+    def __init__(self, num_input_features, num_classes, num_layers, hidden, dropout_rate: float = 0.0, jump_mode=None,
+                 nonlinearity='relu', readout='sum', fully_invar=True):
+        super(EdgeMPNN, self).__init__()
+        self._build(num_input_features, num_classes, num_layers, hidden, dropout_rate, jump_mode, nonlinearity, readout,
+                    fully_invar, with_up=False)

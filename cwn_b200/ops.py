@@ -359,21 +359,37 @@ class _GatherReduce(Function):
         code = REDUCE_CODES[reduce]
         plan = adj.by_dst
         F = x_src.size(1)
-        out = _launch_gather_reduce(x_src, plan.rowptr, plan.pay0, adj.n_dst, F, x_res, eps, code)
+        arg = None
+        if reduce == 'max' and ctx.needs_input_grad[0] and adj.E > 0:
+            # the backward needs to know WHICH message won every (row, feature): a scalar kernel that tracks it
+            with torch.cuda.device(x_src.device):
+                out = torch.empty(adj.n_dst, F, dtype=torch.float32, device=x_src.device)
+                arg = torch.empty(adj.n_dst, F, dtype=torch.int32, device=x_src.device)
+                _call('csr_gather_max_arg', 16 * adj.E + 4 * F * (adj.n_src + 2 * adj.n_dst),
+                      _lib.load().cwn_csr_gather_max_arg_f32, _ptr(x_src), _ld(x_src), plan.rowptr.data_ptr(),
+                      _ptr(plan.pay0), _ptr(plan.perm), adj.n_dst, F, _ptr(out), F, _ptr(arg), _stream())
+        else:
+            out = _launch_gather_reduce(x_src, plan.rowptr, plan.pay0, adj.n_dst, F, x_res, eps, code)
         ctx.adj, ctx.reduce = adj, reduce
-        ctx.save_for_backward(x_res if (eps is not None and eps.requires_grad) else None, eps)
+        ctx.save_for_backward(x_res if (eps is not None and eps.requires_grad) else None, eps, arg)
         ctx.has_res = x_res is not None
         return out
 
     @staticmethod
     def backward(ctx, g):
         adj = ctx.adj
-        x_res, eps = ctx.saved_tensors
+        x_res, eps, arg = ctx.saved_tensors
         g = _rows(g)
         g_src = None
-        if ctx.needs_input_grad[0]:
-            if ctx.reduce == 'max':
-                raise NotImplementedError('cwn_b200: backward of max aggregation is not implemented')
+        if ctx.needs_input_grad[0] and ctx.reduce == 'max':
+            plan = adj.by_src
+            with torch.cuda.device(g.device):
+                g_src = torch.zeros(adj.n_src, g.size(1), dtype=torch.float32, device=g.device)
+                if arg is not None:
+                    _call('csr_max_bwd', 16 * adj.E + 4 * g.size(1) * (2 * adj.n_dst + adj.n_src),
+                          _lib.load().cwn_csr_max_bwd_f32, _ptr(g), _ld(g), _ptr(arg), plan.rowptr.data_ptr(),
+                          _ptr(plan.pay0), _ptr(plan.perm), adj.n_src, g.size(1), _ptr(g_src), g.size(1), _stream())
+        elif ctx.needs_input_grad[0]:
             gm = g
             if ctx.reduce == 'mean':
                 deg = (adj.by_dst.rowptr[1:] - adj.by_dst.rowptr[:-1]).clamp_(min=1).to(g.dtype)
@@ -479,14 +495,34 @@ class _ScatterRows(Function):
     def forward(ctx, msg, dst, n_dst, reduce):
         plan = _row_plan(dst, n_dst)
         ctx.dst, ctx.plan, ctx.reduce = dst, plan, reduce
+        ctx.arg = None
+        if reduce == 'max' and ctx.needs_input_grad[0] and msg.size(0) > 0:
+            F = msg.size(1)
+            with torch.cuda.device(msg.device):
+                out = torch.empty(n_dst, F, dtype=torch.float32, device=msg.device)
+                ctx.arg = torch.empty(n_dst, F, dtype=torch.int32, device=msg.device)
+                _call('csr_gather_max_arg', 16 * msg.size(0) + 4 * F * (msg.size(0) + 2 * n_dst),
+                      _lib.load().cwn_csr_gather_max_arg_f32, _ptr(msg), _ld(msg), plan.rowptr.data_ptr(),
+                      _ptr(plan.perm), _ptr(plan.perm), n_dst, F, _ptr(out), F, _ptr(ctx.arg), _stream())
+            return out
         return _launch_gather_reduce(msg, plan.rowptr, plan.perm, n_dst, msg.size(1), None, None,
                                      REDUCE_CODES[reduce])
 
     @staticmethod
     def backward(ctx, g):
-        if ctx.reduce == 'max':
-            raise NotImplementedError('cwn_b200: backward of max aggregation is not implemented')
         g = _rows(g)
+        if ctx.reduce == 'max':
+            E, F = ctx.dst.numel(), g.size(1)
+            with torch.cuda.device(g.device):
+                g_msg = torch.zeros(E, F, dtype=torch.float32, device=g.device)
+                if ctx.arg is not None:
+                    # every message is its own row: g_msg[e] = (arg[dst[e]] == e) ? g[dst[e]] : 0
+                    rowptr = torch.arange(E + 1, dtype=torch.int32, device=g.device)
+                    dst32 = ctx.dst.to(torch.int32)
+                    _call('csr_max_bwd', 8 * E + 4 * F * (2 * g.size(0) + E), _lib.load().cwn_csr_max_bwd_f32,
+                          _ptr(g), _ld(g), _ptr(ctx.arg), rowptr.data_ptr(), _ptr(dst32), None, E, F, _ptr(g_msg), F,
+                          _stream())
+            return g_msg, None, None, None
         if ctx.reduce == 'mean':
             deg = (ctx.plan.rowptr[1:] - ctx.plan.rowptr[:-1]).clamp_(min=1).to(g.dtype)
             g = g / deg.unsqueeze(-1)

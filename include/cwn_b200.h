@@ -105,6 +105,17 @@ int cwn_csr_gather_reduce_f32(const float* x_src, int64_t ld_src, const int32_t*
                               int64_t n_rows, int32_t F, const float* x_res, int64_t ld_res, const float* eps,
                               float* out, int64_t ld_out, int32_t reduce, cwn_stream_t stream);
 
+/* Max aggregation with argument tracking, for the backward pass of `aggr='max'` (reference mp/cell_mp.py:437-440 ->
+ * torch_scatter.scatter(reduce='max'), whose CPU kernel keeps the FIRST maximum in message order):
+ *   out[r,f] = max_{i in row r} x_src[idx[i], f]  (0 for rows without messages);  arg[r,f] = perm[i*] (message id) or -1
+ *   gX[s,f]  = SUM_{i in row s of the by-source plan} (arg[dst[i], f] == perm[i]) ? G[dst[i], f] : 0
+ * perm = the plan's stable permutation (original message id of every plan position); deterministic, no atomics. */
+int cwn_csr_gather_max_arg_f32(const float* x_src, int64_t ld_src, const int32_t* rowptr, const int32_t* idx,
+                               const int32_t* perm, int64_t n_rows, int32_t F, float* out, int64_t ld_out,
+                               int32_t* arg /* [n_rows, F] */, cwn_stream_t stream);
+int cwn_csr_max_bwd_f32(const float* G, int64_t ld_g, const int32_t* arg, const int32_t* rowptr, const int32_t* dst,
+                        const int32_t* perm, int64_t n_rows, int32_t F, float* gX, int64_t ld_gx, cwn_stream_t stream);
+
 /* The pass above with a SECOND residual operand and an optional plan:
  *   out[r,:] = (1+eps) * x_res[r,:] + (1+eps2) * x_res2[r,:] + SUM_{i in row r} x_src[idx[i],:]
  * rowptr == NULL means "no messages" (out = the two residual terms). This is the gradient fan-in of a cochain's features

@@ -414,3 +414,75 @@ def cin0(sd, cfg, data, training=False):
     x = pool_complex(xs, data, max_dim, cfg['readout'], getattr(data, 'num_complexes', None)).sum(dim=0)
     x = act(F.linear(x, sd['lin1.weight'], sd['lin1.bias']))
     return F.linear(x, sd['lin2.weight'], sd['lin2.bias'])
+
+
+# ------------------------------------------------------------------------------------------ edge-level models
+def edge_cin0(sd, cfg, data, training=False):
+    """EdgeCIN0.forward (mp/models.py:387-416) over EdgeCINConv (mp/layers.py:127-151): CINCochainConv levels for
+    vertices and edges with their own nets; optional refresh of the two-cell features between layers."""
+    cfg = dict(cfg)
+    cfg.setdefault('nonlinearity', 'relu')
+    cfg.setdefault('readout', 'sum')
+    cfg.setdefault('jump_mode', None)
+    cfg.setdefault('dropout_rate', 0.5)
+    include_top = cfg.get('include_top_features', True)
+    update_top = include_top and cfg.get('update_top_features', True)
+    act = _ACT[cfg['nonlinearity']]
+    assert not training or cfg['dropout_rate'] == 0, 'dropout breaks parity'
+    L = cfg['num_layers']
+    jump_xs, xs = None, None
+    for c in range(L):
+        params = get_all_cochain_params(data, 1, include_top_features=include_top)
+        layer_dim = cfg['num_input_features'] if c == 0 else cfg['hidden']
+        xs = [cin_cochain_conv(sd, f'convs.{c}.mp_levels.{d}.', p, cfg, training, layer_dim)
+              for d, p in enumerate(params)]
+        if update_top and c < L - 1 and 2 in data.cochains:
+            up = f'update_top_nns.{c}.'
+            v = data.cochains[2].x
+            v = act(F.linear(v, sd[up + '0.weight'], sd[up + '0.bias']))
+            v = act(F.linear(v, sd[up + '2.weight'], sd[up + '2.bias']))
+            _set_xs(data, xs + [_norm(sd, up + '4.', v, 'bn', training)])
+        else:
+            _set_xs(data, xs)
+        if cfg['jump_mode'] is not None:
+            if jump_xs is None:
+                jump_xs = [[] for _ in xs]
+            for i, x in enumerate(xs):
+                jump_xs[i].append(x)
+    if cfg['jump_mode'] is not None:
+        xs = [_jump(j, cfg['jump_mode']) for j in jump_xs]
+    x = pool_complex(xs, data, 1, cfg['readout'], getattr(data, 'num_complexes', None)).sum(dim=0)
+    x = act(F.linear(x, sd['lin1.weight'], sd['lin1.bias']))
+    return F.linear(x, sd['lin2.weight'], sd['lin2.bias'])
+
+
+def oriented_edge_model(sd, cfg, x, upper_index, lower_index, upper_orient, lower_orient, batch, num_cochains,
+                        with_up=True, training=False):
+    """EdgeOrient (with_up=True, mp/models.py:474-545) / EdgeMPNN (with_up=False, :548-608) over OrientedConv
+    (mp/layers.py:430-470): message = x_j * orientation (unless fully_invar), out = act(U x + U_up SUM_up + U_down
+    SUM_down) with bias-free linears; |.|, per-complex readout, lin1 + ReLU, lin2. Returns (out, cell_pred)."""
+    fully_invar = cfg.get('fully_invar', not with_up)
+    act = _ACT[cfg.get('nonlinearity', 'id' if with_up else 'relu')]
+    assert not training or cfg.get('dropout_rate', 0.0) == 0, 'dropout breaks parity'
+    orient = not fully_invar
+    if fully_invar:
+        x = torch.abs(x)
+    for c in range(cfg['num_layers']):
+        size = x.size(1)
+        msg_up = (lambda x_j, a: x_j * a) if orient else (lambda x_j, a: x_j)
+        out_up, out_down, _ = propagate(x, upper_index, lower_index, None, upper_orient.view(-1, 1),
+                                        lower_orient.view(-1, 1), None, size, size, None, use_boundary_msg=False,
+                                        message_up=msg_up, message_down=msg_up)
+        pre = f'convs.{c}.'
+        v = F.linear(x, sd[pre + 'update_nn.weight']) + F.linear(out_down, sd[pre + 'update_down_nn.weight'])
+        if with_up:
+            # reference order of the sum: x + out_up + out_down (mp/layers.py:452)
+            v = F.linear(x, sd[pre + 'update_nn.weight']) + F.linear(out_up, sd[pre + 'update_up_nn.weight']) \
+                + F.linear(out_down, sd[pre + 'update_down_nn.weight'])
+        x = act(v)
+    cell_pred = x
+    if not fully_invar:
+        x = torch.abs(x)
+    x = scatter(x, batch, num_cochains, {'sum': 'add', 'mean': 'mean'}[cfg.get('readout', 'sum')])
+    x = torch.relu(F.linear(x, sd['lin1.weight'], sd['lin1.bias']))
+    return F.linear(x, sd['lin2.weight'], sd['lin2.bias']), cell_pred

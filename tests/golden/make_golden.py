@@ -26,6 +26,8 @@ from data.complex import Cochain as RefCochain, Complex as RefComplex, ComplexBa
 from mp.cell_mp import CochainMessagePassing as RefCMP                    # noqa: E402
 from mp.layers import DummyCellularMessagePassing as RefDummy, InitReduceConv as RefInitReduce  # noqa: E402
 from mp.models import SparseCIN as RefSparseCIN, CIN0 as RefCIN0, CINpp as RefCINpp  # noqa: E402
+from mp.models import EdgeCIN0 as RefEdgeCIN0, EdgeOrient as RefEdgeOrient, EdgeMPNN as RefEdgeMPNN  # noqa: E402
+from data.complex import CochainBatch as RefCochainBatch  # noqa: E402
 from mp.molec_models import (EmbedSparseCIN as RefEmbed, OGBEmbedSparseCIN as RefOGB,  # noqa: E402
                              EmbedCINpp as RefEmbedCINpp)
 
@@ -202,6 +204,48 @@ def main():
     cfg = dict(atom_types=28, bond_types=4, out_size=1, num_layers=2, hidden=16, dropout_rate=0.0, max_dim=2,
                embed_edge=True, use_coboundaries=True, readout='mean')
     run_train('embed_cinpp_train', RefEmbedCINpp(**cfg), cfg, synthetic.zinc_like_complexes(6, seed=7), l1)
+
+    # edge-level models, appended after everything else (random stream above unchanged)
+    cfg = dict(num_input_features=4, num_classes=1, num_layers=3, hidden=8, dropout_rate=0.0, jump_mode='cat')
+    run_train('edge_cin0_train', RefEdgeCIN0(**cfg), cfg,
+              synthetic.float_feature_complexes(5, 4, seed=9, include_down_adj=True), l1)
+    cfg = dict(num_input_features=4, num_classes=1, num_layers=2, hidden=8, dropout_rate=0.0,
+               include_top_features=False)
+    run_train('edge_cin0_notop_train', RefEdgeCIN0(**cfg), cfg,
+              synthetic.float_feature_complexes(5, 4, seed=10, include_down_adj=True), l1)
+
+    def run_oriented(name, model, cfg, comps, seed):
+        """EdgeOrient / EdgeMPNN on the batched EDGE cochains of `comps`, with seeded +-1 relative orientations on
+        every upper / lower adjacency message and a signed edge signal (the flow datasets' setting)."""
+        gen = torch.Generator().manual_seed(seed)
+        cochains = []
+        for comp in comps:
+            e = to_ref(comp).cochains[1]
+            sign = lambda n: (torch.randint(0, 2, (n,), generator=gen) * 2 - 1).float()  # noqa: E731
+            up_o = sign(e.upper_index.size(1)) if e.upper_index is not None else None
+            lo_o = sign(e.lower_index.size(1))
+            cochains.append(RefCochain(dim=1, x=e.x, upper_index=e.upper_index, lower_index=e.lower_index,
+                                       shared_boundaries=e.shared_boundaries, shared_coboundaries=e.shared_coboundaries,
+                                       upper_orient=up_o, lower_orient=lo_o, y=comp.y,
+                                       num_cells_down=e.num_cells_down, num_cells_up=e.num_cells_up))
+        dumps = [{k: getattr(c, k) for k in ('x', 'upper_index', 'lower_index', 'upper_orient', 'lower_orient', 'y')}
+                 for c in cochains]
+        model.train()
+        sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+        batch = RefCochainBatch.from_cochain_list(cochains)
+        out, cell_pred = model.forward(batch, include_partial=True)
+        loss = l1(out, batch.y)
+        models[name] = {'cfg': cfg, 'state_dict': sd0, 'inputs': dumps, 'output': out.detach().clone(),
+                        'cell_pred': cell_pred.detach().clone(), 'loss': loss.detach().clone(),
+                        'grads': grads_of(model, loss)}
+
+    # every edge of these complexes lies on a ring or next to one; edges without upper adjacency keep upper_index None
+    cfg = dict(num_input_features=3, num_classes=1, num_layers=2, hidden=6, nonlinearity='tanh')
+    run_oriented('edge_orient_train', RefEdgeOrient(**cfg), cfg,
+                 synthetic.float_feature_complexes(4, 3, seed=11, include_down_adj=True), 21)
+    cfg = dict(num_input_features=3, num_classes=1, num_layers=2, hidden=6)
+    run_oriented('edge_mpnn_train', RefEdgeMPNN(**cfg), cfg,
+                 synthetic.float_feature_complexes(4, 3, seed=12, include_down_adj=True), 22)
 
     gold['models'] = models
     path = os.path.join(HERE, 'reference_golden.pt')
