@@ -13,6 +13,7 @@ from torch import Tensor
 from torch.autograd import Function
 
 from cwn_b200 import _lib
+from cwn_b200 import streams as _streams
 
 REDUCE_CODES = {'add': 0, 'sum': 0, 'mean': 1, 'max': 2}
 ACT_CODES = {'id': 0, 'relu': 1, 'elu': 2, 'sigmoid': 3, 'tanh': 4}
@@ -451,36 +452,58 @@ class _CobPass(Function):
         return gP, gQ, g_res, g_eps, None, None
 
 
+def _rows_grad_plan(idx, n):
+    """(plan, split) for the gradient of `x[idx]` w.r.t. x: rows of x grouped by `idx`. Few, very long rows (an embedding
+    table): one thread group per row would serialise, so every row is split into `split` interleaved sub-rows (a
+    deterministic two-level segmented sum). Cached on `idx`."""
+    E = idx.numel()
+    split = 1
+    if E > 32 * max(n, 1):
+        split = 2
+        while split < 256 and split * 8 * n < E:
+            split *= 2
+    if split == 1:
+        return _row_plan(idx, n), 1
+    cache = idx.__dict__.setdefault('_cwn_splitkey', {})
+    gen = (idx._version, idx.data_ptr(), split)
+    if cache.get('gen') != gen:
+        cache.clear()
+        cache['gen'] = gen
+        lanes = torch.arange(E, device=idx.device).bitwise_and_(split - 1)
+        cache['key'] = torch.add(lanes, idx, alpha=split)
+    return _row_plan(cache['key'], n * split), split
+
+
 class _GatherRows(Function):
     """out[e] = scale * x[idx[e]]"""
 
     @staticmethod
     def forward(ctx, x, idx, scale):
         ctx.idx, ctx.n, ctx.scale = idx, x.size(0), scale
+        ctx.plan_ready = None
+        if ctx.needs_input_grad[0] and idx.is_cuda and idx.numel() > 0 and _streams.ENABLED:
+            # The backward needs a CSR plan of `idx` (and, for embedding tables, of its split key): 3 tiny torch
+            # launches + a plan build that would sit at the very END of the step's critical path. Build it now on a
+            # dedicated side stream — it overlaps the forward pass — and let the backward wait on the event.
+            cur = torch.cuda.current_stream(idx.device)
+            side = _streams.aux_stream(cur)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                _rows_grad_plan(idx, ctx.n)
+                ctx.plan_ready = torch.cuda.Event()
+                ctx.plan_ready.record(side)
         return _launch_gather_rows(x, idx, scale)
 
     @staticmethod
     def backward(ctx, g):
         g = _rows(g)
-        idx, n, E = ctx.idx, ctx.n, ctx.idx.numel()
-        split = 1
-        if E > 32 * max(n, 1):  # few, very long rows (an embedding table): one thread group per row would serialise
-            split = 2
-            while split < 256 and split * 8 * n < E:
-                split *= 2
+        idx, n = ctx.idx, ctx.n
+        if ctx.plan_ready is not None:
+            torch.cuda.current_stream(g.device).wait_event(ctx.plan_ready)
+        plan, split = _rows_grad_plan(idx, n)
         if split == 1:
-            plan = _row_plan(idx, n)
             gx = _launch_gather_reduce(g, plan.rowptr, plan.perm, n, g.size(1), None, None, 0)
         else:
-            # two-level segmented sum: `split` interleaved sub-rows per row (deterministic), then their ordered sum
-            cache = idx.__dict__.setdefault('_cwn_splitkey', {})
-            gen = (idx._version, idx.data_ptr(), split)
-            if cache.get('gen') != gen:
-                cache.clear()
-                cache['gen'] = gen
-                lanes = torch.arange(E, device=idx.device).bitwise_and_(split - 1)
-                cache['key'] = torch.add(lanes, idx, alpha=split)
-            plan = _row_plan(cache['key'], n * split)
             part = _launch_gather_reduce(g, plan.rowptr, plan.perm, n * split, g.size(1), None, None, 0)
             gx = part.view(n, split, g.size(1)).sum(dim=1)
         if ctx.scale != 1.0:

@@ -45,3 +45,16 @@ def run_concurrently(thunks, device=None):
     for s in streams:
         parent.wait_stream(s)
     return outs
+
+
+_aux = {}
+
+
+def aux_stream(parent: torch.cuda.Stream) -> torch.cuda.Stream:
+    """A dedicated side stream per parent for work whose JOIN is deferred (forked in forward, awaited by an event in
+    backward): kept apart from the fork/join pool so that an unrelated join does not wait for it."""
+    key = (parent.device, parent.cuda_stream)
+    s = _aux.get(key)
+    if s is None:
+        s = _aux[key] = torch.cuda.Stream(device=parent.device)
+    return s

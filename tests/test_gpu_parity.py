@@ -959,8 +959,10 @@ def test_oriented_edge_models_train_step_matches_reference(name):
     model = (EdgeOrient if name.startswith('edge_orient') else EdgeMPNN)(**m['cfg'])
     model.load_state_dict(m['state_dict'])
     model.to(DEV).train()
+    # (the shared_* columns are not inputs of these models; the explicit cell counts stand in for what they would imply)
     cochains = [Cochain(dim=1, x=c['x'], upper_index=c['upper_index'], lower_index=c['lower_index'],
-                        upper_orient=c['upper_orient'], lower_orient=c['lower_orient'], y=c['y'])
+                        upper_orient=c['upper_orient'], lower_orient=c['lower_orient'], y=c['y'],
+                        num_cells_up=1, num_cells_down=c['x'].size(0) + 1)
                 for c in m['inputs']]
     batch = CochainBatch.from_cochain_list(cochains).to(DEV)
     out, cell_pred = model(batch, include_partial=True)
