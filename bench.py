@@ -36,6 +36,7 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+PRELOAD_STEPS = 320  # untimed extra warm-up steps (~0.3 s) during which nvidia-smi samples the clocks under load
 MODEL_CFG = dict(atom_types=28, bond_types=4, out_size=1, num_layers=4, hidden=64, dropout_rate=0.0, max_dim=2,
                  embed_edge=True, use_coboundaries=True, graph_norm='bn', readout='sum')
 WORKLOAD = 'ZINC ring-lift (max_ring=6) EmbedSparseCIN 4-layer hidden=64 batch=128 (BASELINE.json configs[1])'
@@ -129,39 +130,99 @@ def run_reference(args, rank):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler(object):
+    """SM clock and throttle reasons of one GPU while the bench runs. Two sources feed the same sample list:
+    * NVML polled in-process every ~4 ms (nvidia-ml-py) — fine enough to land samples INSIDE the ~20 ms timed region;
+    * `nvidia-smi -lms 20` as a subprocess — the recipe's own clocks line, and the fallback if NVML is unavailable.
+    Every failure of a source is swallowed: the sampler must never take the bench down."""
     QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
              'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    def __init__(self, gpu_index, nvml=None):
+        self.samples, self.proc, self.gpu = [], None, gpu_index  # samples: (row, host arrival time, source)
+        self._nvml, self._stop = nvml, False
 
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
-                                          '-i', str(self.gpu), '-lms', os.environ.get('CWN_BENCH_SMI_MS', '20')], stdout=subprocess.PIPE, text=True)
+                                          '-i', str(self.gpu), '-lms', os.environ.get('CWN_BENCH_SMI_MS', '20')],
+                                         stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
+        try:
+            if self._nvml is None:
+                import pynvml
+                self._nvml = pynvml
+            self._nvml.nvmlInit()
+            handle = self._nvml.nvmlDeviceGetHandleByIndex(int(self.gpu))
+            threading.Thread(target=self._poll_nvml, args=(handle,), daemon=True).start()
+        except Exception:  # no NVML here (or no permission): nvidia-smi alone
+            self._nvml = None
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+        try:
+            for line in self.proc.stdout:
+                self.samples.append(([c.strip() for c in line.split(',')], time.perf_counter(), 'nvidia-smi'))
+        except Exception:
+            pass
 
-    def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        self.proc.terminate()
-        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 9 and r[1].isdigit())
-        mx = [int(r[2]) for r in self.rows if len(r) >= 9 and r[2].isdigit()]
+    def _poll_nvml(self, handle):
+        n = self._nvml
+        try:
+            sm_max = n.nvmlDeviceGetMaxClockInfo(handle, n.NVML_CLOCK_SM)
+            get_reasons = getattr(n, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+                n.nvmlDeviceGetCurrentClocksThrottleReasons
+            flag = lambda mask, bit: 'Active' if (mask & bit) else 'Not Active'  # noqa: E731
+            while not self._stop:
+                sm = n.nvmlDeviceGetClockInfo(handle, n.NVML_CLOCK_SM)
+                mask = int(get_reasons(handle))
+                row = [str(self.gpu), str(int(sm)), str(int(sm_max)), '', hex(mask),
+                       flag(mask, n.nvmlClocksThrottleReasonHwSlowdown),
+                       flag(mask, n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                       flag(mask, n.nvmlClocksThrottleReasonSwThermalSlowdown),
+                       flag(mask, n.nvmlClocksThrottleReasonSwPowerCap)]
+                self.samples.append((row, time.perf_counter(), 'nvml'))
+                time.sleep(0.004)
+        except Exception:
+            pass
+
+    def wait_first(self, timeout_s=3.0):
+        """nvidia-smi needs ~0.1-0.5 s before its first line: without this a 20 ms timed region ends unsampled."""
+        t0 = time.perf_counter()
+        while (self.proc is not None or self._nvml is not None) and not self.samples \
+                and time.perf_counter() - t0 < timeout_s:
+            time.sleep(0.01)
+
+    def stop(self, t_from=None, t_to=None, t_timed=None):
+        """Statistics over the samples that arrived in [t_from, t_to] (the period the GPU was under this bench's load);
+        `t_timed` = (start, end) of the timed region, to report how many samples fell inside it."""
+        self._stop = True
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        if self.proc is None and self._nvml is None and not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi and NVML unavailable'], 'samples': 0}
+        keep = [(r, t, src) for r, t, src in list(self.samples)
+                if (t_from is None or t >= t_from) and (t_to is None or t <= t_to)]
+        in_timed = sum(1 for _, t, _ in keep if t_timed is not None and t_timed[0] <= t <= t_timed[1])
+        rows = [r for r, _, _ in keep]
+        sm = sorted(int(r[1]) for r in rows if len(r) >= 9 and r[1].isdigit())
+        mx = [int(r[2]) for r in rows if len(r) >= 9 and r[2].isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 9:
                 for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
                     if v.lower().startswith('active'):
                         reasons.add(name)
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm), 'samples_in_timed_region': in_timed,
+                'sources': sorted({src for _, _, src in keep}),
+                'window': 'NVML every ~4 ms + nvidia-smi every 20 ms, from the pre-load steps through the timed region '
+                          'to the end of the e2e loop (all of it this workload under load; the timed region itself '
+                          'lasts ~20 ms)'}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -377,23 +438,33 @@ def run_cwn(args, rank, world, local_rank):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+        clocks.wait_first()
+    t_load0 = time.perf_counter()
     for i in range(max(args.warmup, 3)):
         resident_step(i)
+    # pre-load: keep the GPU busy with the same step for ~0.3 s so that the clocks are ramped and sampled under load
+    # before the (tens of ms long) timed region starts
+    # (a FIXED number of steps: every rank must issue the same count, each step holds an all-reduce)
+    for i in range(PRELOAD_STEPS):
+        resident_step(i)
+        if i % 32 == 31:
+            torch.cuda.synchronize()
     barrier()
 
     # ---- timed region: device-resident inputs
     l0 = _lib.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    t_timed0 = time.perf_counter()
     for i in range(args.steps):
         flush.zero_()
         ev[i][0].record()
         resident_step(i)
         ev[i][1].record()
     barrier()
+    t_timed1 = time.perf_counter()
     launches = _lib.launch_count() - l0 if captured is None else launches_per_step * args.steps
     ms_total = sum(a.elapsed_time(b) for a, b in ev)
-    clock_info = clocks.stop() if rank == 0 else None
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -415,6 +486,7 @@ def run_cwn(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = cells * world / (float(t.item()) / args.steps / 1e3)
+    clock_info = clocks.stop(t_load0, time.perf_counter(), (t_timed0, t_timed1)) if rank == 0 else None
 
     # ---- e2e with collation inside the timed region: the dataset lives in HBM (PackedComplexDataset), a step is
     #      ids -> GPU collation straight into the graph's static buffers -> step -> loss.item()
@@ -485,7 +557,7 @@ def run_cwn(args, rank, world, local_rank):
         'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'cells_per_step_per_gpu': cells, 'global_batch': args.batch * world,
-                   'parallelism': f'dp{world}', 'step': 'plans+fwd+loss+bwd+allreduce+adam', 'mode': mode,
+                   'parallelism': f'dp{world}', 'step': 'plans+fwd+loss+bwd+allreduce+adam', 'mode': mode, 'clock_preload_steps': PRELOAD_STEPS,
                    'l2': 'flushed (256 MB write) between timed steps', 'last_loss': loss_value},
         'clocks': clock_info, 'gpu_launches': int(launches),
         'e2e': {'value': e2e_value, 'unit': 'cells/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 4},

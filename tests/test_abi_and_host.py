@@ -113,3 +113,41 @@ def test_module_structure_loads_reference_state_dicts():
     shared = CIN0(1, 3, 2, 5).convs[0]
     assert isinstance(shared, CINConv)
     assert shared.mp_levels[0].msg_up_nn is shared.mp_levels[2].msg_up_nn  # weights shared across dimensions
+
+
+def test_bench_clock_sampler_sources_and_windows():
+    """bench.py's clock sampler on the CPU: a fake NVML module drives the in-process poller, rows in nvidia-smi's CSV
+    format are injected by hand; `stop()` must window the samples, report the median clock, the throttle reasons and how
+    many samples fell inside the timed region — and never raise when a source is missing."""
+    import sys
+    import time
+    import types
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    fake = types.SimpleNamespace(
+        NVML_CLOCK_SM=1, nvmlClocksThrottleReasonHwSlowdown=8, nvmlClocksThrottleReasonHwThermalSlowdown=64,
+        nvmlClocksThrottleReasonSwThermalSlowdown=32, nvmlClocksThrottleReasonSwPowerCap=4,
+        nvmlInit=lambda: None, nvmlDeviceGetHandleByIndex=lambda i: ('gpu', i),
+        nvmlDeviceGetMaxClockInfo=lambda h, c: 1965, nvmlDeviceGetClockInfo=lambda h, c: 1950,
+        nvmlDeviceGetCurrentClocksEventReasons=lambda h: 4)
+    s = bench.ClockSampler(0, nvml=fake)
+    s.start()                      # nvidia-smi is absent in the build container: that source must just stay empty
+    s.wait_first(2.0)
+    t0 = time.perf_counter()
+    time.sleep(0.05)
+    t1 = time.perf_counter()
+    s.samples.append((['0', '1312', '1965', '300', 'Active', 'Not Active', 'Active', 'Not Active', 'Not Active'],
+                      time.perf_counter(), 'nvidia-smi'))
+    info = s.stop(t0 - 1.0, time.perf_counter() + 1.0, (t0, t1))
+    assert info['sm_max_mhz'] == 1965 and info['sm_mhz'] == 1950 and info['samples'] >= 10
+    assert info['samples_in_timed_region'] >= 5
+    assert set(info['reasons']) == {'sw_power_cap', 'hw_thermal_slowdown'}
+    assert 'nvml' in info['sources'] and 'nvidia-smi' in info['sources']
+    # a sampler with no source at all reports that instead of raising
+    broken = types.SimpleNamespace(nvmlInit=lambda: (_ for _ in ()).throw(RuntimeError('no NVML')))
+    s2 = bench.ClockSampler(0, nvml=broken)
+    s2.start()
+    s2.wait_first(0.05)
+    out = s2.stop()
+    assert out['sm_mhz'] is None or isinstance(out['sm_mhz'], int)
