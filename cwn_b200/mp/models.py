@@ -42,6 +42,24 @@ class _JumpMixin(object):
     def jump_complex(self, jump_xs):
         return [self.jump(jumpx) for jumpx in jump_xs]
 
+    def _remember_layer(self, history, xs):
+        """Per-dimension list of every layer's output, for JumpingKnowledge (None when the model does not jump)."""
+        if self.jump_mode is None:
+            return None
+        history = history if history is not None else [[] for _ in xs]
+        for per_dim, x in zip(history, xs):
+            per_dim.append(x)
+        return history
+
+    def _summed_head(self, xs, data, history):
+        """Readout shared by the dense models: jump, per-complex pooling, sum over dimensions, lin1 + act, dropout,
+        lin2 (reference `mp/models.py:95-106, 404-416`)."""
+        if history is not None:
+            xs = self.jump_complex(history)
+        x = self.pool_complex(xs, data).sum(dim=0)
+        x = get_nonlinearity(self.nonlinearity, return_module=False)(self.lin1(x))
+        return self.lin2(F.dropout(x, p=self.dropout_rate, training=self.training))
+
 
 class CIN0(torch.nn.Module, _JumpMixin):
     """Dense cellular GIN: upper + lower messages through shared MLPs (reference `mp/models.py:12-109`)."""
@@ -81,25 +99,12 @@ class CIN0(torch.nn.Module, _JumpMixin):
         return pool_complex(xs, data, self.max_dim, self.readout)
 
     def forward(self, data: ComplexBatch):
-        model_nonlinearity = get_nonlinearity(self.nonlinearity, return_module=False)
-        xs, jump_xs = None, None
-        for c, conv in enumerate(self.convs):
-            params = data.get_all_cochain_params(max_dim=self.max_dim)
-            xs = conv(*params)
+        xs, history = None, None
+        for conv in self.convs:
+            xs = conv(*data.get_all_cochain_params(max_dim=self.max_dim))
             data.set_xs(xs)
-            if self.jump_mode is not None:
-                if jump_xs is None:
-                    jump_xs = [[] for _ in xs]
-                for i, x in enumerate(xs):
-                    jump_xs[i] += [x]
-        if self.jump_mode is not None:
-            xs = self.jump_complex(jump_xs)
-        pooled_xs = self.pool_complex(xs, data)
-        x = pooled_xs.sum(dim=0)
-        x = model_nonlinearity(self.lin1(x))
-        x = F.dropout(x, p=self.dropout_rate, training=self.training)
-        x = self.lin2(x)
-        return x
+            history = self._remember_layer(history, xs)
+        return self._summed_head(xs, data, history)
 
     def __repr__(self):
         return self.__class__.__name__
@@ -272,28 +277,19 @@ class EdgeCIN0(torch.nn.Module, _JumpMixin):
         return pool_complex(xs, data, self.max_dim, self.readout)
 
     def forward(self, data: ComplexBatch):
-        model_nonlinearity = get_nonlinearity(self.nonlinearity, return_module=False)
-        xs, jump_xs = None, None
+        xs, history = None, None
+        last = len(self.convs) - 1
         for c, conv in enumerate(self.convs):
-            params = data.get_all_cochain_params(max_dim=self.max_dim, include_top_features=self.include_top_features)
-            xs = conv(*params)
-            if self.update_top_features and c < len(self.convs) - 1 and 2 in data.cochains:
-                top_x = self.update_top_nns[c](data.cochains[2].x)
-                data.set_xs(xs + [top_x])
-            else:
-                data.set_xs(xs)
-            if self.jump_mode is not None:
-                if jump_xs is None:
-                    jump_xs = [[] for _ in xs]
-                for i, x in enumerate(xs):
-                    jump_xs[i] += [x]
-        if self.jump_mode is not None:
-            xs = self.jump_complex(jump_xs)
-        pooled_xs = self.pool_complex(xs, data)
-        x = pooled_xs.sum(dim=0)
-        x = model_nonlinearity(self.lin1(x))
-        x = F.dropout(x, p=self.dropout_rate, training=self.training)
-        return self.lin2(x)
+            xs = conv(*data.get_all_cochain_params(max_dim=self.max_dim,
+                                                   include_top_features=self.include_top_features))
+            refreshed = list(xs)
+            # between layers the two-cell features (inputs of the edges' upper messages) go through their own MLP,
+            # provided the batch has two-cells at all
+            if self.update_top_features and c < last and 2 in data.cochains:
+                refreshed.append(self.update_top_nns[c](data.cochains[2].x))
+            data.set_xs(refreshed)
+            history = self._remember_layer(history, xs)
+        return self._summed_head(xs, data, history)
 
     def __repr__(self):
         return self.__class__.__name__
