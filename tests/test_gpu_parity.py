@@ -974,3 +974,15 @@ def test_oriented_edge_models_train_step_matches_reference(name):
     got = dict(model.named_parameters())
     for k, ref in m['grads'].items():
         assert_close(got[k].grad, ref, rtol=1e-4, atol=2e-6, what=f'{name}:grad:{k}')
+
+
+@pytest.mark.parametrize('mode', ['r', 'p', 't'])
+@pytest.mark.parametrize('F', [64, 256])
+def test_every_large_row_kernel_family_is_bit_exact(mode, F, monkeypatch):
+    """The three kernel families of the HBM-bound regime — plain / chunked rows ('r'), software-pipelined rows ('p'),
+    tile-staged with TMA bulk copies of plan slices and feature windows ('t') — forced one after the other through the
+    library's A/B switches (read at every call), each against the sequential CPU definition on float data. Whatever
+    the dispatcher's defaults are, none of the families may rot."""
+    monkeypatch.setenv('CWN_B200_LARGE_GATHER', mode)
+    monkeypatch.setenv('CWN_B200_LARGE_COB', mode)
+    test_tile_staged_kernels_are_bit_exact_and_survive_heavy_rows(F)

@@ -69,3 +69,30 @@ def test_oriented_model_host_logic_matches_reference_train_step(name, monkeypatc
     got = dict(model.named_parameters())
     for k, ref in m['grads'].items():
         assert_close(got[k].grad, ref, rtol=1e-4, atol=2e-6 + 2e-5 * float(ref.abs().max()), what=f'{name}:grad:{k}')
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The reference's own known-answer / invariance tests, run through the host layer on the CPU: the
+# bodies live in tests/test_gpu_parity.py (where they run on the CUDA kernels); here the device is switched to 'cpu'
+# and the ops entry points to their torch restatements, so the SAME assertions cover hook protocol, layers and models
+# in the GPU-less tier.
+import test_gpu_parity as G  # noqa: E402
+
+_HOST_TWINS = [
+    (G.test_reference_known_answers_on_gpu, ()),                       # mp/test_cell_mp.py:13-111, :179-270
+    (G.test_isolated_cells_and_empty_index, ()),                       # mp/test_cell_mp.py:114-176
+    (G.test_init_reduce_known_answers, ()),                            # mp/test_layers.py:135-149
+    (G.test_user_overridden_hooks_are_honoured, ()),
+    (G.test_batched_equals_unbatched, ()),                             # mp/test_models.py:139-185
+    (G.test_mean_max_aggregations_equal_reference, ('mean',)),
+    (G.test_mean_max_aggregations_equal_reference, ('max',)),
+] + [(G.test_propagate_and_dummy_layers_equal_reference_on_every_fixture, (n,)) for n in golden()['fixtures']] \
+  + [(G.test_eval_models_match_reference_outputs, (n,))
+     for n in ('sparse_cin_eval', 'sparse_cin_eval_dim1', 'embed_sparse_cin_eval', 'cin0_eval')]
+
+
+@pytest.mark.parametrize('fn,args', _HOST_TWINS, ids=[f'{f.__name__}{list(a)}' for f, a in _HOST_TWINS])
+def test_reference_test_suite_through_the_host_layer(fn, args, monkeypatch):
+    cpu_ops_shim.install(monkeypatch)
+    monkeypatch.setattr(G, 'DEV', 'cpu')
+    fn(*args)
