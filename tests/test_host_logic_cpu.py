@@ -96,3 +96,29 @@ def test_reference_test_suite_through_the_host_layer(fn, args, monkeypatch):
     cpu_ops_shim.install(monkeypatch)
     monkeypatch.setattr(G, 'DEV', 'cpu')
     fn(*args)
+
+
+@pytest.mark.parametrize('use_cob', [False, True])
+def test_baseline_config0_sparse_cin_conv_on_the_house_complex(use_cob, monkeypatch):
+    """BASELINE.json configs[0]: `SparseCINConv` forward on the house complex of data/dummy_complexes.py (5 vertices,
+    6 edges, 1 two-cell, F = 1), CPU, world size 1 — the reference's own CPU-runnable plumbing case. Host layer (ops
+    substituted) against the oracle's restatement of mp/layers.py:184-199 fed the same weights, eval-mode BatchNorm."""
+    import cwn_oracle as O
+    from cwn_b200.mp.layers import SparseCINConv
+    from cwn_b200.mp.nn import get_graph_norm, get_nonlinearity
+    from helpers import fixture
+    cpu_ops_shim.install(monkeypatch)
+    torch.manual_seed(0)
+    conv = SparseCINConv(1, 1, 1, None, None, None, None, layer_dim=1, hidden=4, act_module=get_nonlinearity('relu'),
+                         graph_norm=get_graph_norm('bn'), use_coboundaries=use_cob).eval()
+    house = fixture('house')
+    params = house.get_all_cochain_params(max_dim=2, include_down_features=False)
+    with torch.no_grad():
+        outs = conv(*params)
+    sd = {k: v.detach().clone() for k, v in conv.state_dict().items()}
+    cfg = dict(nonlinearity='relu', graph_norm='bn', use_coboundaries=use_cob)
+    snap = O.Snapshot(fixture('house'))
+    ref = O.sparse_cin_conv(sd, '', O.get_all_cochain_params(snap, 2, include_down_features=False), cfg, False, 1)
+    assert [tuple(o.shape) for o in outs] == [(5, 4), (6, 4), (1, 4)]
+    for d, (o, r) in enumerate(zip(outs, ref)):
+        assert_close(o, r, rtol=1e-6, atol=1e-6, what=f'house dim {d}')
