@@ -633,7 +633,19 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
-template <int TR, int A_IN>
+// ---- tensor-core helpers (3xTF32): value -> (hi, lo) TF32 parts; one m16n8k8 TF32 MMA with fp32 accumulation
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(v - __uint_as_float(hi)));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int TR, int A_IN, bool TC>  // TC: products on the tensor cores (3xTF32 split), opt-in (CWN_B200_DENSE_TC=1)
 __global__ void __launch_bounds__(DT, CWN_FWD_MIN_CTAS) linear_fwd_fast_kernel(const __grid_constant__ Group<cwn_linear_desc> g) {
   constexpr int R = TR / 16;
   extern __shared__ __align__(16) float smem[];
@@ -706,98 +718,202 @@ __global__ void __launch_bounds__(DT, CWN_FWD_MIN_CTAS) linear_fwd_fast_kernel(c
     }
     __syncthreads();
   }
-  CWN_PHASE(3);
-  float acc[R][4] = {};
-  {
-    const float* a0 = Xs + (ty * R) * ld;
-    const float* b0 = Ws + tx * ld;
-#pragma unroll 2
-    for (int k = 0; k < K; k += 4) {
-      float4 a[R], b[4];
-#pragma unroll
-      for (int i = 0; i < R; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * ld + k);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(b0 + j * 16 * ld + k);
-#pragma unroll
-      for (int i = 0; i < R; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
-#pragma unroll
-      for (int i = 0; i < R; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i].y, b[j].y, acc[i][j]);
-#pragma unroll
-      for (int i = 0; i < R; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]);
-#pragma unroll
-      for (int i = 0; i < R; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
-    }
-  }
-  CWN_PHASE(4);
-#pragma unroll
-  for (int i = 0; i < R; ++i) {
-    const int r = ty * R + i;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      acc[i][j] += bias[j];
-      const int c = col0 + tx + 16 * j;
-      if (r < rows && c < d.h) d.z[(row0 + r) * d.ld_z + c] = acc[i][j];
-    }
-  }
-  CWN_PHASE(5);
-  if (!d.stats) {
-    if (d.bn_mean && !d.bn_training && blockIdx.x == g.start[p])  // eval: statistics are the running ones
-      bn_finalize_body(nullptr, 0, d.n_rows, d.h, d.bn_gamma, d.bn_eps, d.bn_momentum, 0, d.bn_running_mean,
-                       d.bn_running_var, nullptr, d.bn_mean, d.bn_scale, d.bn_rstd, nullptr);
-    return;
-  }
-  {  // per-column (mean, M2) of this tile from the accumulators: rows of a thread, the lane 16 apart, then the warps
-    const int w = tid >> 5, lane = tid & 31;
-    float sj[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float v = 0.f;
-#pragma unroll
-      for (int i = 0; i < R; ++i) v += (ty * R + i < rows) ? acc[i][j] : 0.f;
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      sj[j] = v;
-    }
-    if (lane < 16)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) red[w][tx + 16 * j] = sj[j];
-    __syncthreads();
-    if (tid < TN) {
-      float tot = 0.f;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) tot += red[q][tid];
-      meanv[tid] = tot / (float)rows;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float mu = meanv[tx + 16 * j];
-      float v = 0.f;
-#pragma unroll
-      for (int i = 0; i < R; ++i) {
-        const float dv = acc[i][j] - mu;
-        v = (ty * R + i < rows) ? fmaf(dv, dv, v) : v;
+  if constexpr (TC) {
+    CWN_PHASE(3);
+    // ---- TC: the 16R x 64 x K product on the tensor cores, 3xTF32 split operands (a = a_hi + a_lo, each TF32):
+    //      a_lo*b_hi + a_hi*b_lo + a_hi*b_hi with fp32 accumulation is as accurate as an fp32 FFMA chain
+    //      (tests/analysis_tf32_error_budget.py) at a quarter of the issue slots. mma.sync.m16n8k8: lane = 4*gq + tq holds
+    //      A[gq | gq+8][tq | tq+4], B[k = tq | tq+4][n = gq], C[gq | gq+8][2tq | 2tq+1]. Warp w owns the 16-row block
+    //      w % R and the R column blocks (8 wide) starting at (w / R) * R. Xs / Ws rows are K + 4 floats apart, i.e.
+    //      4 banks per row: the 8 x 4 fragment loads of a warp hit 32 different banks.
+    const int warp_tc = tid >> 5, lane_tc = tid & 31, gq = lane_tc >> 2, tq = lane_tc & 3;
+    constexpr int NT = R;
+    const int mb = warp_tc % R, nb0 = (warp_tc / R) * NT;
+    float cfr[NT][4];
+  #pragma unroll
+    for (int j = 0; j < NT; ++j) cfr[j][0] = cfr[j][1] = cfr[j][2] = cfr[j][3] = 0.f;
+    {
+      const float* a_lo_row = Xs + (mb * 16 + gq) * ld + tq;
+      const float* a_hi_row = a_lo_row + 8 * ld;
+      const float* b_row0 = Ws + (nb0 * 8 + gq) * ld + tq;
+      for (int k = 0; k < K; k += 8) {
+        const float av[4] = {a_lo_row[k], a_hi_row[k], a_lo_row[k + 4], a_hi_row[k + 4]};
+        uint32_t ah[4], al[4];
+  #pragma unroll
+        for (int i = 0; i < 4; ++i) split_tf32(av[i], ah[i], al[i]);
+  #pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const float* br = b_row0 + j * 8 * ld + k;
+          uint32_t bh[2], bl[2];
+          split_tf32(br[0], bh[0], bl[0]);
+          split_tf32(br[4], bh[1], bl[1]);
+          mma_tf32(cfr[j], al, bh);
+          mma_tf32(cfr[j], ah, bl);
+          mma_tf32(cfr[j], ah, bh);
+        }
       }
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      sj[j] = v;
     }
-    if (lane < 16)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) red[w][tx + 16 * j] = sj[j];
-    __syncthreads();
-    if (tid < TN && col0 + tid < d.h) {
-      float m2 = 0.f;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) m2 += red[q][tid];
-      d.stats[((int64_t)rt * 2 + 0) * d.h + col0 + tid] = meanv[tid];
-      d.stats[((int64_t)rt * 2 + 1) * d.h + col0 + tid] = m2;
+    CWN_PHASE(4);
+    const int r_lo = mb * 16 + gq, r_hi = r_lo + 8;
+  #pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int cn = (nb0 + j) * 8 + 2 * tq, c = col0 + cn;  // columns c, c + 1 (h % 4 == 0: both inside or both outside)
+      const float b0 = (d.bias && c < d.h) ? __ldg(d.bias + c) : 0.f;
+      const float b1 = (d.bias && c < d.h) ? __ldg(d.bias + c + 1) : 0.f;
+      cfr[j][0] += b0; cfr[j][1] += b1; cfr[j][2] += b0; cfr[j][3] += b1;
+      if (c < d.h) {
+        if (r_lo < rows) { float* zp = d.z + (row0 + r_lo) * d.ld_z + c; zp[0] = cfr[j][0]; zp[1] = cfr[j][1]; }
+        if (r_hi < rows) { float* zp = d.z + (row0 + r_hi) * d.ld_z + c; zp[0] = cfr[j][2]; zp[1] = cfr[j][3]; }
+      }
+    }
+    CWN_PHASE(5);
+    if (!d.stats) {
+      if (d.bn_mean && !d.bn_training && blockIdx.x == g.start[p])  // eval: statistics are the running ones
+        bn_finalize_body(nullptr, 0, d.n_rows, d.h, d.bn_gamma, d.bn_eps, d.bn_momentum, 0, d.bn_running_mean,
+                         d.bn_running_var, nullptr, d.bn_mean, d.bn_scale, d.bn_rstd, nullptr);
+      return;
+    }
+    {  // per-column (mean, M2) of this tile from the fragments: the two rows of a lane, the 8 lanes sharing tq, then
+       // the R warps that share the column block
+      auto column_partials = [&](float (&sj)[NT][2], bool centred) {
+  #pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const int cn = (nb0 + j) * 8 + 2 * tq;
+  #pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const float mu = centred ? meanv[cn + q] : 0.f;
+            const float lo = cfr[j][q] - mu, hi = cfr[j][2 + q] - mu;
+            float v = 0.f;
+            if (r_lo < rows) v = centred ? lo * lo : lo;
+            if (r_hi < rows) v = centred ? fmaf(hi, hi, v) : v + hi;
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            sj[j][q] = v;
+          }
+        }
+        if (gq == 0)
+  #pragma unroll
+          for (int j = 0; j < NT; ++j) {
+            red[warp_tc][(nb0 + j) * 8 + 2 * tq] = sj[j][0];
+            red[warp_tc][(nb0 + j) * 8 + 2 * tq + 1] = sj[j][1];
+          }
+      };
+      float sj[NT][2];
+      column_partials(sj, false);
+      __syncthreads();
+      const int owner0 = ((tid >> 3) / NT) * R;  // first of the R warps that own column `tid` (tid < TN)
+      if (tid < TN) {
+        float tot = 0.f;
+  #pragma unroll
+        for (int q = 0; q < R; ++q) tot += red[owner0 + q][tid];
+        meanv[tid] = tot / (float)rows;
+      }
+      __syncthreads();
+      column_partials(sj, true);
+      __syncthreads();
+      if (tid < TN && col0 + tid < d.h) {
+        float m2 = 0.f;
+  #pragma unroll
+        for (int q = 0; q < R; ++q) m2 += red[owner0 + q][tid];
+        d.stats[((int64_t)rt * 2 + 0) * d.h + col0 + tid] = meanv[tid];
+        d.stats[((int64_t)rt * 2 + 1) * d.h + col0 + tid] = m2;
+      }
+    }
+  } else {
+    CWN_PHASE(3);
+    float acc[R][4] = {};
+    {
+      const float* a0 = Xs + (ty * R) * ld;
+      const float* b0 = Ws + tx * ld;
+  #pragma unroll 2
+      for (int k = 0; k < K; k += 4) {
+        float4 a[R], b[4];
+  #pragma unroll
+        for (int i = 0; i < R; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * ld + k);
+  #pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(b0 + j * 16 * ld + k);
+  #pragma unroll
+        for (int i = 0; i < R; ++i)
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
+  #pragma unroll
+        for (int i = 0; i < R; ++i)
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i].y, b[j].y, acc[i][j]);
+  #pragma unroll
+        for (int i = 0; i < R; ++i)
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]);
+  #pragma unroll
+        for (int i = 0; i < R; ++i)
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
+      }
+    }
+    CWN_PHASE(4);
+  #pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const int r = ty * R + i;
+  #pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[i][j] += bias[j];
+        const int c = col0 + tx + 16 * j;
+        if (r < rows && c < d.h) d.z[(row0 + r) * d.ld_z + c] = acc[i][j];
+      }
+    }
+    CWN_PHASE(5);
+    if (!d.stats) {
+      if (d.bn_mean && !d.bn_training && blockIdx.x == g.start[p])  // eval: statistics are the running ones
+        bn_finalize_body(nullptr, 0, d.n_rows, d.h, d.bn_gamma, d.bn_eps, d.bn_momentum, 0, d.bn_running_mean,
+                         d.bn_running_var, nullptr, d.bn_mean, d.bn_scale, d.bn_rstd, nullptr);
+      return;
+    }
+    {  // per-column (mean, M2) of this tile from the accumulators: rows of a thread, the lane 16 apart, then the warps
+      const int w = tid >> 5, lane = tid & 31;
+      float sj[4];
+  #pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = 0.f;
+  #pragma unroll
+        for (int i = 0; i < R; ++i) v += (ty * R + i < rows) ? acc[i][j] : 0.f;
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        sj[j] = v;
+      }
+      if (lane < 16)
+  #pragma unroll
+        for (int j = 0; j < 4; ++j) red[w][tx + 16 * j] = sj[j];
+      __syncthreads();
+      if (tid < TN) {
+        float tot = 0.f;
+  #pragma unroll
+        for (int q = 0; q < 8; ++q) tot += red[q][tid];
+        meanv[tid] = tot / (float)rows;
+      }
+      __syncthreads();
+  #pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float mu = meanv[tx + 16 * j];
+        float v = 0.f;
+  #pragma unroll
+        for (int i = 0; i < R; ++i) {
+          const float dv = acc[i][j] - mu;
+          v = (ty * R + i < rows) ? fmaf(dv, dv, v) : v;
+        }
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        sj[j] = v;
+      }
+      if (lane < 16)
+  #pragma unroll
+        for (int j = 0; j < 4; ++j) red[w][tx + 16 * j] = sj[j];
+      __syncthreads();
+      if (tid < TN && col0 + tid < d.h) {
+        float m2 = 0.f;
+  #pragma unroll
+        for (int q = 0; q < 8; ++q) m2 += red[q][tid];
+        d.stats[((int64_t)rt * 2 + 0) * d.h + col0 + tid] = meanv[tid];
+        d.stats[((int64_t)rt * 2 + 1) * d.h + col0 + tid] = m2;
+      }
     }
   }
   CWN_PHASE(6);
@@ -1553,11 +1669,20 @@ extern "C" int cwn_linear_fwd_grouped(const cwn_linear_desc* descs, int32_t n, c
     const size_t need = ((size_t)(tr + TN) * (K + 4) + 3 * (size_t)K) * sizeof(float);
     if (need > smem_fast) smem_fast = need;
   }
+  // opt-in tensor-core products (3xTF32) for the fast path: every problem's K must be a multiple of the MMA's k = 8
+  static const bool tc_env = [] { const char* v = getenv("CWN_B200_DENSE_TC"); return v && v[0] == '1'; }();
+  bool tc = tc_env;
+  for (int i = 0; i < n && tc; ++i) tc = descs[i].n_rows == 0 || (descs[i].k0 + descs[i].k1) % 8 == 0;
   if (fast && smem_fast <= 200 * 1024) {
 #define CWN_LAUNCH_FAST(TRV, AV)                                                                                   \
   {                                                                                                                \
-    if ((rc = ensure_smem(linear_fwd_fast_kernel<TRV, AV>, smem_fast, "cudaFuncSetAttribute(linear_fwd_fast_kernel)"))) return rc; \
-    linear_fwd_fast_kernel<TRV, AV><<<total, DT, smem_fast, (cudaStream_t)stream>>>(g);                            \
+    if (tc) {                                                                                                      \
+      if ((rc = ensure_smem(linear_fwd_fast_kernel<TRV, AV, true>, smem_fast, "cudaFuncSetAttribute(linear_fwd_fast_kernel)"))) return rc; \
+      linear_fwd_fast_kernel<TRV, AV, true><<<total, DT, smem_fast, (cudaStream_t)stream>>>(g);                    \
+    } else {                                                                                                       \
+      if ((rc = ensure_smem(linear_fwd_fast_kernel<TRV, AV, false>, smem_fast, "cudaFuncSetAttribute(linear_fwd_fast_kernel)"))) return rc; \
+      linear_fwd_fast_kernel<TRV, AV, false><<<total, DT, smem_fast, (cudaStream_t)stream>>>(g);                   \
+    }                                                                                                              \
   }
 #define CWN_FAST_BY_ACT(TRV)                                     \
   if (a_in == CWN_ACT_ID) CWN_LAUNCH_FAST(TRV, CWN_ACT_ID)       \
