@@ -1351,7 +1351,7 @@ __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_kernel(const __
 // one cp.async batch; g_z is formed in place over the g_out tile; its transpose reuses the z tile's shared memory; the
 // bias partial is read off the transposed tile; weight-gradient partials leave as 128-bit stores. Same FMA order as
 // the generic kernel, so the two agree bit for bit.
-template <int TR, int A_IN, int A_OUT>
+template <int TR, int A_IN, int A_OUT, bool TC>  // TC: opt-in tensor-core products, as in linear_fwd_fast_kernel
 __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_fast_kernel(const __grid_constant__ Group<cwn_unit_bwd_desc> g) {
   constexpr int R = TR / 16;
   constexpr int LDR = TR + 4;
@@ -1475,43 +1475,143 @@ __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_fast_kernel(con
       bpart[tid] = first ? s_ : bpart[tid] + s_;
     }
     for (int kc = 0; kc < K; kc += TN) {
-      if (d.g_in0 || d.g_in1) {  // input gradient chunk: [TR rows] x [64 k] = Gz [TR x h] * Ws [h x 64]
-        float acc[R][4] = {};
-        tile_mma<R>(Gz, ldh, Ws + kc, ldk, h, ty, tx, acc);
-        const int kq = kc + tx * 4;
-        if (kq < K) {
-          float* base = (kq < d.k0) ? (d.g_in0 ? d.g_in0 + row0 * d.ld_gi0 + kq : nullptr)
-                                    : (d.g_in1 ? d.g_in1 + row0 * d.ld_gi1 + (kq - d.k0) : nullptr);
-          const int64_t ldo = (kq < d.k0) ? d.ld_gi0 : d.ld_gi1;
-          if (base)
-#pragma unroll
-            for (int i = 0; i < R; ++i) {
-              const int r = ty * R + i;
-              if (r < rows) {
-                float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-                if (d.accumulate_in) v = f4_add(*reinterpret_cast<const float4*>(base + r * ldo), v);
-                *reinterpret_cast<float4*>(base + r * ldo) = v;
+      if constexpr (TC) {
+        // ---- TC: both products of the chunk on the tensor cores (3xTF32 split operands, mma.sync m16n8k8; see
+        //      linear_fwd_fast_kernel for the fragment layout). Results are stored straight from the C fragments.
+        const int warp_tc = tid >> 5, lane_tc = tid & 31, gq = lane_tc >> 2, tq = lane_tc & 3;
+        if (d.g_in0 || d.g_in1) {  // input gradient chunk: [TR rows] x [64 k] = Gz [TR x h] * Ws [h x 64]
+          constexpr int NT = R;
+          const int mb = warp_tc % R, nb0 = (warp_tc / R) * NT;
+          float cfr[NT][4];
+  #pragma unroll
+          for (int j = 0; j < NT; ++j) cfr[j][0] = cfr[j][1] = cfr[j][2] = cfr[j][3] = 0.f;
+          const float* a_lo_row = Gz + (mb * 16 + gq) * ldh + tq;
+          const float* a_hi_row = a_lo_row + 8 * ldh;
+          const float* b_col0 = Ws + tq * ldk + kc + nb0 * 8 + gq;
+          for (int c0 = 0; c0 < h; c0 += 8) {
+            const float av[4] = {a_lo_row[c0], a_hi_row[c0], a_lo_row[c0 + 4], a_hi_row[c0 + 4]};
+            uint32_t ah[4], al[4];
+  #pragma unroll
+            for (int i = 0; i < 4; ++i) split_tf32(av[i], ah[i], al[i]);
+  #pragma unroll
+            for (int j = 0; j < NT; ++j) {
+              const float* bp = b_col0 + c0 * ldk + j * 8;
+              uint32_t bh[2], bl[2];
+              split_tf32(bp[0], bh[0], bl[0]);
+              split_tf32(bp[4 * ldk], bh[1], bl[1]);
+              mma_tf32(cfr[j], al, bh);
+              mma_tf32(cfr[j], ah, bl);
+              mma_tf32(cfr[j], ah, bh);
+            }
+          }
+          const int r_lo = mb * 16 + gq, r_hi = r_lo + 8;
+  #pragma unroll
+          for (int j = 0; j < NT; ++j) {
+            const int kq = kc + (nb0 + j) * 8 + 2 * tq;  // columns kq, kq + 1: one block (k0 % 4 == 0), both < K or neither
+            if (kq >= K) continue;
+            float* base = (kq < d.k0) ? (d.g_in0 ? d.g_in0 + row0 * d.ld_gi0 + kq : nullptr)
+                                      : (d.g_in1 ? d.g_in1 + row0 * d.ld_gi1 + (kq - d.k0) : nullptr);
+            const int64_t ldo = (kq < d.k0) ? d.ld_gi0 : d.ld_gi1;
+            if (!base) continue;
+            if (r_lo < rows) {
+              float2* dst = reinterpret_cast<float2*>(base + r_lo * ldo);
+              float2 v = make_float2(cfr[j][0], cfr[j][1]);
+              if (d.accumulate_in) { const float2 o = *dst; v.x += o.x; v.y += o.y; }
+              *dst = v;
+            }
+            if (r_hi < rows) {
+              float2* dst = reinterpret_cast<float2*>(base + r_hi * ldo);
+              float2 v = make_float2(cfr[j][2], cfr[j][3]);
+              if (d.accumulate_in) { const float2 o = *dst; v.x += o.x; v.y += o.y; }
+              *dst = v;
+            }
+          }
+        }
+        if (first && kc == 0) CWN_PHASE(5);
+        for (int mt = 0; mt < m_tiles; ++mt) {  // weight gradient chunk: [64 c] x [64 k] = GzT [64 x TR] * Xs [TR x 64]
+          const int mb = warp_tc & 3, nb0 = (warp_tc >> 2) * 4;
+          float cfr[4][4];
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) cfr[j][0] = cfr[j][1] = cfr[j][2] = cfr[j][3] = 0.f;
+          const float* a_lo_row = ZT + (mt * 64 + mb * 16 + gq) * LDR + tq;
+          const float* a_hi_row = a_lo_row + 8 * LDR;
+          const float* b_col0 = Xs + tq * ldk + kc + nb0 * 8 + gq;
+  #pragma unroll 2
+          for (int r0 = 0; r0 < TR; r0 += 8) {
+            const float av[4] = {a_lo_row[r0], a_hi_row[r0], a_lo_row[r0 + 4], a_hi_row[r0 + 4]};
+            uint32_t ah[4], al[4];
+  #pragma unroll
+            for (int i = 0; i < 4; ++i) split_tf32(av[i], ah[i], al[i]);
+  #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float* bp = b_col0 + r0 * ldk + j * 8;
+              uint32_t bh[2], bl[2];
+              split_tf32(bp[0], bh[0], bl[0]);
+              split_tf32(bp[4 * ldk], bh[1], bl[1]);
+              mma_tf32(cfr[j], al, bh);
+              mma_tf32(cfr[j], ah, bl);
+              mma_tf32(cfr[j], ah, bh);
+            }
+          }
+          const int c_lo = mt * 64 + mb * 16 + gq, c_hi = c_lo + 8;
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = kc + (nb0 + j) * 8 + 2 * tq;
+            if (k >= K) continue;
+            if (c_lo < h) {
+              float2* dst = reinterpret_cast<float2*>(wpart + (int64_t)c_lo * K + k);
+              float2 v = make_float2(cfr[j][0], cfr[j][1]);
+              if (!first) { const float2 o = *dst; v.x += o.x; v.y += o.y; }
+              *dst = v;
+            }
+            if (c_hi < h) {
+              float2* dst = reinterpret_cast<float2*>(wpart + (int64_t)c_hi * K + k);
+              float2 v = make_float2(cfr[j][2], cfr[j][3]);
+              if (!first) { const float2 o = *dst; v.x += o.x; v.y += o.y; }
+              *dst = v;
+            }
+          }
+        }
+        if (first && kc == 0) CWN_PHASE(6);
+      } else {
+        if (d.g_in0 || d.g_in1) {  // input gradient chunk: [TR rows] x [64 k] = Gz [TR x h] * Ws [h x 64]
+          float acc[R][4] = {};
+          tile_mma<R>(Gz, ldh, Ws + kc, ldk, h, ty, tx, acc);
+          const int kq = kc + tx * 4;
+          if (kq < K) {
+            float* base = (kq < d.k0) ? (d.g_in0 ? d.g_in0 + row0 * d.ld_gi0 + kq : nullptr)
+                                      : (d.g_in1 ? d.g_in1 + row0 * d.ld_gi1 + (kq - d.k0) : nullptr);
+            const int64_t ldo = (kq < d.k0) ? d.ld_gi0 : d.ld_gi1;
+            if (base)
+  #pragma unroll
+              for (int i = 0; i < R; ++i) {
+                const int r = ty * R + i;
+                if (r < rows) {
+                  float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                  if (d.accumulate_in) v = f4_add(*reinterpret_cast<const float4*>(base + r * ldo), v);
+                  *reinterpret_cast<float4*>(base + r * ldo) = v;
+                }
               }
+          }
+        }
+        if (first && kc == 0) CWN_PHASE(5);
+        for (int mt = 0; mt < m_tiles; ++mt) {  // weight gradient chunk: [64 c] x [64 k] = GzT [64 x TR] * Xs [TR x 64]
+          float acc[4][4] = {};
+          tile_mma<4>(ZT + mt * 64 * LDR, LDR, Xs + kc, ldk, TR, ty, tx, acc);
+          const int k = kc + tx * 4;
+          if (k < K)
+  #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int c = mt * 64 + ty * 4 + i;
+              if (c >= h) continue;
+              float4* dst = reinterpret_cast<float4*>(wpart + (int64_t)c * K + k);
+              float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+              if (!first) v = f4_add(*dst, v);
+              *dst = v;
             }
         }
+        if (first && kc == 0) CWN_PHASE(6);
       }
-      if (first && kc == 0) CWN_PHASE(5);
-      for (int mt = 0; mt < m_tiles; ++mt) {  // weight gradient chunk: [64 c] x [64 k] = GzT [64 x TR] * Xs [TR x 64]
-        float acc[4][4] = {};
-        tile_mma<4>(ZT + mt * 64 * LDR, LDR, Xs + kc, ldk, TR, ty, tx, acc);
-        const int k = kc + tx * 4;
-        if (k < K)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int c = mt * 64 + ty * 4 + i;
-            if (c >= h) continue;
-            float4* dst = reinterpret_cast<float4*>(wpart + (int64_t)c * K + k);
-            float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-            if (!first) v = f4_add(*dst, v);
-            *dst = v;
-          }
-      }
-      if (first && kc == 0) CWN_PHASE(6);
     }
   }
   CWN_PHASE(8);
@@ -1863,11 +1963,21 @@ extern "C" int cwn_unit_bwd_grouped(const cwn_unit_bwd_desc* descs, int32_t n, c
                          6 * (size_t)d.h + 64) * sizeof(float);
     if (need > smem_fast) smem_fast = need;
   }
+  // opt-in tensor-core products (3xTF32): the inner dimension of the input-gradient product is h, a multiple of the
+  // MMA's k = 8 is required (the other product's inner dimension is the tile height, 32 or 64)
+  static const bool tc_env = [] { const char* v = getenv("CWN_B200_DENSE_TC"); return v && v[0] == '1'; }();
+  bool tc = tc_env;
+  for (int i = 0; i < n && tc; ++i) tc = g.d[i].n_rows == 0 || g.d[i].h % 8 == 0;
   if (fast && smem_fast <= 210 * 1024) {
 #define CWN_LAUNCH_BWDF(TRV, AI, AO)                                                                              \
   {                                                                                                               \
-    if ((rc = ensure_smem(unit_bwd_fast_kernel<TRV, AI, AO>, smem_fast, "cudaFuncSetAttribute(unit_bwd_fast_kernel)"))) return rc; \
-    unit_bwd_fast_kernel<TRV, AI, AO><<<total, DT, smem_fast, (cudaStream_t)stream>>>(g);                         \
+    if (tc) {                                                                                                     \
+      if ((rc = ensure_smem(unit_bwd_fast_kernel<TRV, AI, AO, true>, smem_fast, "cudaFuncSetAttribute(unit_bwd_fast_kernel)"))) return rc; \
+      unit_bwd_fast_kernel<TRV, AI, AO, true><<<total, DT, smem_fast, (cudaStream_t)stream>>>(g);                 \
+    } else {                                                                                                      \
+      if ((rc = ensure_smem(unit_bwd_fast_kernel<TRV, AI, AO, false>, smem_fast, "cudaFuncSetAttribute(unit_bwd_fast_kernel)"))) return rc; \
+      unit_bwd_fast_kernel<TRV, AI, AO, false><<<total, DT, smem_fast, (cudaStream_t)stream>>>(g);                \
+    }                                                                                                             \
   }
 #define CWN_BWDF_BY_OUT(TRV, AI)                                     \
   if (a_out == CWN_ACT_ID) CWN_LAUNCH_BWDF(TRV, AI, CWN_ACT_ID)      \
