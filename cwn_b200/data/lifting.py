@@ -15,7 +15,7 @@ Ring ids: the reference keeps rings in a Python `set` of graph-tool's isomorphis
 set's iteration order — a function of CPython's tuple hashing and graph-tool's vertex mapping, not of the graph. Here
 rings are numbered by the lexicographic order of their sorted vertex tuples, which reproduces the reference's own
 known-answer test (`data/test_utils.py:215-289`: square before triangle on the house graph). Any other numbering is a
-relabelling of the 2-cells, to which the models are invariant (`tests/test_data_api.py`).
+relabelling of the 2-cells, to which the models are invariant (`tests/test_lifting.py`).
 """
 from typing import List, Optional, Sequence, Tuple, Union
 

@@ -157,3 +157,33 @@ def test_convert_graph_dataset_with_rings():
         ds.append(g)
     complexes, dim, nf = convert_graph_dataset_with_rings(ds, max_ring_size=6, init_rings=True)
     assert len(complexes) == 4 and dim == 2 and nf == [2, 2, 2]
+
+
+def test_models_are_invariant_to_the_numbering_of_the_rings(monkeypatch):
+    """The reference numbers rings in CPython-set order; `find_rings` numbers them lexicographically. Any numbering is a
+    relabelling of the 2-cells, and the models must not care: SparseCIN (host layer on the CPU, ops substituted) gives
+    the same output for the lifted complex and for the same complex with its rings in reversed order."""
+    import cpu_ops_shim
+    from cwn_b200.mp.models import SparseCIN
+    cpu_ops_shim.install(monkeypatch)
+    torch.manual_seed(0)
+    model = SparseCIN(num_input_features=3, num_classes=2, num_layers=2, hidden=8, max_dim=2,
+                      use_coboundaries=True).eval()
+    rng = np.random.default_rng(11)
+    outs = []
+    graphs = [synthetic.molecule_graph((6, 5, 6), 4, rng) for _ in range(3)]
+    xs = [torch.randn(n, 3) for n, _, _ in graphs]
+    for flip in (False, True):
+        comps = []
+        for (n, edges, _), x in zip(graphs, xs):
+            ei = torch.tensor(edges + [(b, a) for a, b in edges], dtype=torch.long).t()
+            rings = find_rings(ei, 6)
+            rings = list(reversed(rings)) if flip else rings
+            ex = torch.stack([x[a] + x[b] for a, b in sorted({(min(a, b), max(a, b)) for a, b in edges})])
+            rx = torch.stack([x[list(r)].sum(0) for r in rings])
+            c = synthetic.make_complex(n, edges, rings, x, ex)
+            c.cochains[2].x = rx
+            comps.append(c)
+        with torch.no_grad():
+            outs.append(model(ComplexBatch.from_complex_list(comps, max_dim=2)))
+    assert torch.allclose(outs[0], outs[1], rtol=1e-5, atol=1e-5)
