@@ -1,7 +1,8 @@
 """CPU ORACLE of the cochain message-passing hot path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
-Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline / `--impl reference` legs may import this
-file; nothing under `cwn_b200/` does. It is a dependency-free (torch-only, CPU or any device) restatement of what
+Only `tests/` (including the analysis script tests/analysis_tf32_error_budget.py and the test-only ops shim
+tests/cpu_ops_shim.py), `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline / `--impl reference` legs may import
+this file; nothing under `cwn_b200/` does. It is a dependency-free (torch-only, CPU or any device) restatement of what
 the reference computes on this path, written functionally over a `state_dict` so that the same weights can be fed
 to it and to the CUDA implementation:
 
@@ -14,6 +15,8 @@ to it and to the CUDA implementation:
   pool_complex             mp/nn.py:50-60
   sparse_cin / embed_sparse_cin / ogb_embed_sparse_cin / cin0   mp/models.py:194-254, mp/molec_models.py:90-161,
                            :281-350, mp/models.py:84-106
+  edge_cin0                mp/models.py:286-419 over EdgeCINConv mp/layers.py:127-151
+  oriented_edge_model      EdgeOrient / EdgeMPNN mp/models.py:474-608 over OrientedConv mp/layers.py:430-470
 
 Third-party semantics restated (their sources are not under /root/reference): torch_scatter 2.0.5
 `scatter(reduce=add|mean|max)` = zeros(dim_size) + scatter_add_ (mean: / clamp(count,1); max: empty rows 0);
