@@ -1678,6 +1678,10 @@ __global__ void __launch_bounds__(DT) wgrad_finalize_kernel(const __grid_constan
   }
 }
 
+}  // namespace cwn
+#include "dense_tc5.cuh"
+namespace cwn {
+
 // ------------------------------------------------------------------------------------------------ host side
 template <class Kernel>
 static int ensure_smem(Kernel kernel, size_t bytes, const char* what) {
@@ -1754,6 +1758,30 @@ extern "C" int cwn_linear_fwd_grouped(const cwn_linear_desc* descs, int32_t n, c
   g.start[n] = total;
   if (total == 0) return CWN_OK;
   const int a_in = group_act(descs, n, [](const cwn_linear_desc& d) { return d.in_act; });
+  // tensor-core path (tcgen05, 3xTF32 over split accumulators): 64-row tiles, every problem of the group must qualify
+  if (tr == 64 && t5_enabled() && !(g_force_generic_dense & 1)) {
+    bool ok = true;
+    size_t smem5 = 0;
+    for (int i = 0; i < n && ok; ++i) ok = descs[i].n_rows == 0 || t5_fwd_ok(descs[i], smem5);
+    if (ok && smem5 > 0) {
+      int total5 = 0;
+      for (int i = 0; i < n; ++i) {
+        g.start[i] = total5;
+        total5 += (int)((descs[i].n_rows + T5R - 1) / T5R);
+      }
+      g.start[n] = total5;
+#define CWN_LAUNCH_T5(AV)                                                                                            \
+  {                                                                                                                  \
+    if ((rc = ensure_smem(linear_fwd_tc5_kernel<AV>, smem5, "cudaFuncSetAttribute(linear_fwd_tc5_kernel)"))) return rc; \
+    linear_fwd_tc5_kernel<AV><<<total5, T5T, smem5, (cudaStream_t)stream>>>(g);                                      \
+  }
+      if (a_in == CWN_ACT_ID) CWN_LAUNCH_T5(CWN_ACT_ID)
+      else if (a_in == CWN_ACT_RELU) CWN_LAUNCH_T5(CWN_ACT_RELU)
+      else CWN_LAUNCH_T5(kActRuntime)
+#undef CWN_LAUNCH_T5
+      return launched("linear_fwd_tc5_kernel");
+    }
+  }
   bool fast = !(g_force_generic_dense & 1);
   size_t smem_fast = 0;
   for (int i = 0; i < n && fast; ++i) {
@@ -1941,6 +1969,28 @@ extern "C" int cwn_unit_bwd_grouped(const cwn_unit_bwd_desc* descs, int32_t n, c
   if (total == 0) return CWN_OK;
   const int a_in = group_act(descs, n, [](const cwn_unit_bwd_desc& d) { return d.in_act; });
   const int a_out = group_act(descs, n, [](const cwn_unit_bwd_desc& d) { return d.act; });
+  if (tr == 64 && t5_enabled() && !(g_force_generic_dense & 2)) {  // tensor-core path (see dense_tc5.cuh)
+    bool ok = true;
+    size_t smem5 = 0;
+    for (int i = 0; i < n && ok; ++i) ok = g.d[i].n_rows == 0 || t5_bwd_ok(g.d[i], smem5);
+    if (ok && smem5 > 0) {
+#define CWN_LAUNCH_T5B(AI, AO)                                                                                            \
+  {                                                                                                                       \
+    if ((rc = ensure_smem(unit_bwd_tc5_kernel<AI, AO>, smem5, "cudaFuncSetAttribute(unit_bwd_tc5_kernel)"))) return rc;   \
+    unit_bwd_tc5_kernel<AI, AO><<<total, T5T, smem5, (cudaStream_t)stream>>>(g);                                          \
+  }
+#define CWN_T5B_BY_OUT(AI)                                        \
+  if (a_out == CWN_ACT_ID) CWN_LAUNCH_T5B(AI, CWN_ACT_ID)         \
+  else if (a_out == CWN_ACT_RELU) CWN_LAUNCH_T5B(AI, CWN_ACT_RELU) \
+  else CWN_LAUNCH_T5B(AI, kActRuntime)
+      if (a_in == CWN_ACT_ID) { CWN_T5B_BY_OUT(CWN_ACT_ID) }
+      else if (a_in == CWN_ACT_RELU) { CWN_T5B_BY_OUT(CWN_ACT_RELU) }
+      else { CWN_T5B_BY_OUT(kActRuntime) }
+#undef CWN_T5B_BY_OUT
+#undef CWN_LAUNCH_T5B
+      return launched("unit_bwd_tc5_kernel");
+    }
+  }
   bool fast = !(g_force_generic_dense & 2);
   size_t smem_fast = 0;
   for (int i = 0; i < n && fast; ++i) {

@@ -1,0 +1,583 @@
+// Dense update / combine units on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM).
+// Included by dense.cu (shares Group<>, stage_desc, the BatchNorm merges and the activation helpers).
+//
+// Reference: mp/layers.py:191-199, 303-325 (Linear -> BatchNorm -> act nets after propagate) and :290-293 (the
+// coboundary message Linear, applied here as two per-cell products).
+//
+// Precision. fp32 parity (rtol 1e-5) rules out plain TF32 (10-bit mantissa). Every operand is split in registers into
+// hi = tf32(v), lo = tf32(v - hi) and the product is formed as lo*hi + hi*lo + hi*hi (3xTF32). What limits accuracy
+// then is the tensor core's accumulator: it truncates (rounds toward zero) at every accumulation, a biased error that
+// a chain of 24 accumulations makes 3-4x larger than a sequential fp32 FMA chain (measured:
+// profiles/r2_tc5_probe_accumulation.txt; the round-1 mma.sync variant failed the training-step parity test for this
+// reason). So the accumulation is spread over several TMEM accumulators — one for all the small lo*hi / hi*lo terms,
+// `nb` for k-ranges of the hi*hi terms — which the epilogue adds in fp32 round-to-nearest. With nb >= 2 the result is
+// MORE accurate than the FMA chain (rms error 0.85x at nb = 2, 0.65x at nb = 4, K = 64); TMEM (512 columns) is what
+// pays for it.
+//
+// Tiles. A CTA owns 64 rows (instruction M = 64; D row i lives in TMEM lane 32 (i / 16) + i % 16). Operands pass
+// through registers exactly once (the previous unit's BatchNorm + activation is applied there, then the split) and are
+// written to shared memory in the two layouts of tc5.cuh with conflict-free 16-byte stores:
+//   forward   z = f(X) W^T          : A = f(X) [64 x K] K-major, B = W [h x K] K-major                       N = h
+//   backward  g_in = g_z W          : A = g_z [64 x h] K-major,  B = W [h (inner) x K] MN-major              N = K
+//             g_W  = g_z^T f(X)     : A = g_z [64 (inner) x h] MN-major, B = f(X) [64 (inner) x K] MN-major  M = h, N = K
+// One thread issues the MMAs, one tcgen05.commit arrives on an mbarrier, and the epilogue reads TMEM with
+// tcgen05.ld (32x32b), stages the tile in shared memory (the operand buffers are dead by then) and leaves with
+// coalesced 128-bit stores; BatchNorm partials are taken from the staged tile.
+#pragma once
+#include "tc5.cuh"
+
+namespace cwn {
+
+constexpr int T5R = 64;    // rows per CTA tile
+constexpr int T5T = 256;   // threads per CTA
+
+// number of k-range accumulators for the hi*hi terms, given the accumulator width N and the inner extent
+__host__ __device__ __forceinline__ int t5_big_blocks(int N, int inner, int column_budget) {
+  int nb = column_budget / N - 1;
+  if (nb > 4) nb = 4;
+  const int ksteps = inner / 8;
+  if (nb > ksteps) nb = ksteps;
+  if (nb < 1) nb = 1;
+  const int per = (ksteps + nb - 1) / nb;   // k-steps per accumulator; every accumulator must receive at least one
+  return (ksteps + per - 1) / per;
+}
+__host__ __device__ __forceinline__ uint32_t t5_pow2_cols(int cols) {
+  uint32_t c = 32;
+  while ((int)c < cols) c <<= 1;
+  return c;
+}
+
+// Issue D[M x N] = A * B over `inner` with the accumulator scheme above. ONE thread.
+// acc 0 at d_tmem: small terms; acc 1 + b at d_tmem + (1 + b) N: hi*hi of k-steps [b per, (b + 1) per).
+__device__ __forceinline__ void t5_issue(uint32_t d_tmem, int N, int nb, uint32_t a_hi, uint32_t a_lo, uint32_t a_lbo, uint32_t a_sbo,
+                                         uint32_t a_step, uint32_t a_layout, uint32_t b_hi, uint32_t b_lo, uint32_t b_lbo,
+                                         uint32_t b_sbo, uint32_t b_step, uint32_t b_layout, int inner, uint32_t idesc) {
+  // Lean by construction: the issuing thread is the serial bottleneck of a tile this small (a first version that built
+  // four descriptors and divided ks by `per` at every step spent ~120 cycles per MMA in integer arithmetic — tools/
+  // tc5_probe3.cu). Descriptors advance by adding to their start-address field (bits 0..13, units of 16 bytes).
+  const int ksteps = inner >> 3, per = (ksteps + nb - 1) / nb;
+  uint64_t dah = tc5::smem_desc(a_hi, a_lbo, a_sbo, a_layout), dal = tc5::smem_desc(a_lo, a_lbo, a_sbo, a_layout);
+  uint64_t dbh = tc5::smem_desc(b_hi, b_lbo, b_sbo, b_layout), dbl = tc5::smem_desc(b_lo, b_lbo, b_sbo, b_layout);
+  const uint64_t sa = a_step >> 4, sb = b_step >> 4;
+  uint32_t d_big = d_tmem + (uint32_t)N;
+  int ks = 0;
+  for (int blk = 0; blk < nb; ++blk, d_big += (uint32_t)N) {
+    const int end = (ks + per < ksteps) ? ks + per : ksteps;
+    for (int first = 1; ks < end; ++ks, first = 0, dah += sa, dal += sa, dbh += sb, dbl += sb) {
+      tc5::mma_tf32(d_tmem, dal, dbh, idesc, ks > 0);
+      tc5::mma_tf32(d_big, dah, dbh, idesc, first ? 0u : 1u);
+      tc5::mma_tf32(d_tmem, dah, dbl, idesc, 1u);
+    }
+  }
+}
+
+// 16 consecutive accumulator columns of this thread's TMEM lane: every accumulator's load is issued before the single
+// wait; hi*hi blocks are added in order, then the small terms (fp32 RN adds)
+__device__ __forceinline__ void t5_read16(uint32_t taddr, int N, int nb, float (&v)[16]) {
+  float small[16], b1[16], b2[16], b3[16];
+  tc5::tmem_ld16(taddr, small);
+  tc5::tmem_ld16(taddr + (uint32_t)N, v);
+  if (nb > 1) tc5::tmem_ld16(taddr + (uint32_t)(2 * N), b1);
+  if (nb > 2) tc5::tmem_ld16(taddr + (uint32_t)(3 * N), b2);
+  if (nb > 3) tc5::tmem_ld16(taddr + (uint32_t)(4 * N), b3);
+  tc5::tmem_ld_wait();
+  if (nb > 1) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] += b1[j];
+  }
+  if (nb > 2) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] += b2[j];
+  }
+  if (nb > 3) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] += b3[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] += small[j];
+}
+
+__device__ __forceinline__ float4 t5_transform(const float4 v, const float4 mu, const float4 sc, const float4 be, int act_code,
+                                               int A) {
+  float4 o;
+  if (A == CWN_ACT_ID) {
+    o.x = (v.x - mu.x) * sc.x + be.x; o.y = (v.y - mu.y) * sc.y + be.y; o.z = (v.z - mu.z) * sc.z + be.z; o.w = (v.w - mu.w) * sc.w + be.w;
+  } else if (A == CWN_ACT_RELU) {
+    o.x = fmaxf((v.x - mu.x) * sc.x + be.x, 0.f); o.y = fmaxf((v.y - mu.y) * sc.y + be.y, 0.f);
+    o.z = fmaxf((v.z - mu.z) * sc.z + be.z, 0.f); o.w = fmaxf((v.w - mu.w) * sc.w + be.w, 0.f);
+  } else {
+    o.x = act_apply_rt(act_code, (v.x - mu.x) * sc.x + be.x); o.y = act_apply_rt(act_code, (v.y - mu.y) * sc.y + be.y);
+    o.z = act_apply_rt(act_code, (v.z - mu.z) * sc.z + be.z); o.w = act_apply_rt(act_code, (v.w - mu.w) * sc.w + be.w);
+  }
+  return o;
+}
+
+// One thread's 4-column chunk of a unit's input f_in(X) (virtual concat [X0 | X1] + the previous unit's BatchNorm /
+// activation). The column is the same for every row a thread touches (256 threads, K/4 a power of two), so the block
+// selection and the transform vectors are resolved ONCE; raw loads are separated from the transform so that a whole
+// batch of 128-bit loads is in flight before the first is consumed.
+template <class D>
+struct T5InCol {
+  const float* base;
+  int64_t ld;
+  float4 mu, sc, be;
+  bool tf;
+  int act;
+  __device__ __forceinline__ T5InCol(const D& d, int c, int64_t row0, bool transform) {
+    const bool first = c < d.k0;
+    base = first ? d.x0 + row0 * d.ld_x0 + c : d.x1 + row0 * d.ld_x1 + (c - d.k0);
+    ld = first ? d.ld_x0 : d.ld_x1;
+    mu = make_float4(0.f, 0.f, 0.f, 0.f); sc = make_float4(1.f, 1.f, 1.f, 1.f); be = mu;
+    tf = transform; act = d.in_act;
+    const float* sp = first ? d.in_scale0 : d.in_scale1;
+    if (transform && sp) {
+      const int cc = first ? c : c - d.k0;
+      mu = ldg_f4((first ? d.in_mean0 : d.in_mean1) + cc);
+      sc = ldg_f4(sp + cc);
+      be = ldg_f4((first ? d.in_beta0 : d.in_beta1) + cc);
+    }
+  }
+  __device__ __forceinline__ float4 raw(int r, int rows) const {  // zero past the matrix
+    return r < rows ? ldg_f4(base + (int64_t)r * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  template <int A_IN>
+  __device__ __forceinline__ float4 apply(float4 v, int r, int rows) const {  // padding rows stay zero
+    return (tf && r < rows) ? t5_transform(v, mu, sc, be, act, A_IN) : v;
+  }
+};
+
+__device__ __forceinline__ int t5_log2(int v) { return 31 - __clz(v); }
+
+// ------------------------------------------------------------------------------------------------ forward
+struct T5FwdSmem {  // byte offsets into dynamic shared memory (host and device agree through this one function)
+  uint32_t a_hi, a_lo, b_hi, b_lo, total;
+  __host__ __device__ T5FwdSmem(int K, int h) {
+    const uint32_t a = tc5::Tiled::bytes(T5R, K), b = tc5::Tiled::bytes(h, K);
+    a_hi = 0; a_lo = a; b_hi = 2 * a; b_lo = 2 * a + b;
+    total = 2 * a + 2 * b;
+    const uint32_t stage = (uint32_t)T5R * (uint32_t)(h + 4) * 4u;  // output tile staged over the dead operand buffers
+    if (total < stage) total = stage;
+  }
+};
+
+template <int A_IN>
+__global__ void __launch_bounds__(T5T, 2) linear_fwd_tc5_kernel(const __grid_constant__ Group<cwn_linear_desc> g) {
+  extern __shared__ __align__(1024) unsigned char smem5[];
+  __shared__ cwn_linear_desc sd;
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_s;
+  __shared__ float red[T5T];
+  __shared__ float meanv[128];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  CWN_PHASE(0);
+  const int p = find_problem(g, blockIdx.x);
+  if (tid == 0) { tc5::mbar_init(&bar, 1); tc5::mbar_fence_init(); }
+  const cwn_linear_desc d = stage_desc(g, p, &sd);  // (contains the CTA barrier that publishes the mbarrier init)
+  CWN_PHASE(1);
+  const int rt = blockIdx.x - g.start[p];
+  const int K = d.k0 + d.k1, K4 = K >> 2, h = d.h;
+  const int nb = t5_big_blocks(h, K, h <= 64 ? 256 : 512);
+  const uint32_t tmem_cols = t5_pow2_cols((1 + nb) * h);
+  if (warp == 0) tc5::tmem_alloc(&tmem_s, tmem_cols);
+  const int64_t row0 = (int64_t)rt * T5R;
+  const int rows = (int)((d.n_rows - row0 < T5R) ? d.n_rows - row0 : T5R);
+  const bool transform = d.in_scale0 || d.in_scale1 || d.in_act != CWN_ACT_ID;
+  const T5FwdSmem L(K, h);
+  const tc5::Tiled ta(T5R), tb(h);
+  {  // operands: global -> registers (transform, split) -> shared memory. Thread -> column chunk c4 (fixed) and rows
+     // rb, rb + rs, ...; per trip up to 4 rows of X and 4 rows of W are requested before any is consumed.
+    const int lg = t5_log2(K4), c4 = tid & (K4 - 1), rb = tid >> lg, rs = T5T >> lg;
+    const T5InCol<cwn_linear_desc> col(d, c4 * 4, row0, transform);
+    const float* wcol = d.w + c4 * 4;
+    const int r_end = h > T5R ? h : T5R;
+    for (int r0 = rb; r0 < r_end; r0 += 4 * rs) {
+      float4 va[4], vw[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = r0 + j * rs;
+        va[j] = col.raw(r, rows);
+        vw[j] = r < h ? ldg_f4(wcol + (int64_t)r * d.ld_w) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = r0 + j * rs;
+        float4 hi, lo;
+        if (r < T5R) {
+          tc5::split_tf32x4(col.template apply<A_IN>(va[j], r, rows), hi, lo);
+          const uint32_t o = ta.off(r, c4);
+          *reinterpret_cast<float4*>(smem5 + L.a_hi + o) = hi;
+          *reinterpret_cast<float4*>(smem5 + L.a_lo + o) = lo;
+        }
+        if (r < h) {
+          tc5::split_tf32x4(vw[j], hi, lo);
+          const uint32_t o = tb.off(r, c4);
+          *reinterpret_cast<float4*>(smem5 + L.b_hi + o) = hi;
+          *reinterpret_cast<float4*>(smem5 + L.b_lo + o) = lo;
+        }
+      }
+    }
+  }
+  tc5::fence_async_smem();
+  tc5::fence_before_sync();
+  __syncthreads();
+  tc5::fence_after_sync();
+  CWN_PHASE(2);
+  const uint32_t tmem = tmem_s;
+  if (tid == 0) {
+    const uint32_t s0 = tc5::smem_u32(smem5);
+    t5_issue(tmem, h, nb, s0 + L.a_hi, s0 + L.a_lo, ta.s_c, ta.s_r, 2 * ta.s_c, 0, s0 + L.b_hi, s0 + L.b_lo, tb.s_c, tb.s_r,
+             2 * tb.s_c, 0, K, tc5::idesc_tf32(T5R, h, 0, 0));
+    tc5::mma_commit(&bar);
+  }
+  tc5::mbar_wait(&bar, 0);
+  tc5::fence_after_sync();
+  CWN_PHASE(3);
+  // epilogue: TMEM -> (+ bias) -> staged tile Ys[64][h + 4] over the operand buffers (all MMAs have completed)
+  float* Ys = reinterpret_cast<float*>(smem5);
+  const int ldy = h + 4;
+  {
+    const int q = warp & 3, half = warp >> 2;  // TMEM lane quadrant; the two warps of a quadrant split the columns
+    const int r = 16 * q + lane;                // M = 64: rows sit in lanes 0..15 of each quadrant
+    const int per_half = h >= 32 ? (h >> 1) : h;  // (h = 16: one warp per quadrant does it all)
+    const int c_lo = half * per_half, c_hi = (c_lo + per_half < h) ? c_lo + per_half : h;
+    for (int c0 = c_lo; c0 < c_hi; c0 += 16) {  // (warp-uniform trip count: tcgen05.ld is warp-collective)
+      float v[16];
+      t5_read16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, h, nb, v);
+      if (lane < 16) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float4 b4 = d.bias ? ldg_f4(d.bias + c0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(Ys + r * ldy + c0 + j) = make_float4(v[j] + b4.x, v[j + 1] + b4.y, v[j + 2] + b4.z, v[j + 3] + b4.w);
+        }
+      }
+    }
+  }
+  tc5::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc5::tmem_dealloc(tmem, tmem_cols);
+  CWN_PHASE(4);
+  {  // coalesced stores of z
+    const int h4 = h >> 2;
+    for (int i = tid; i < rows * h4; i += T5T) {
+      const int r = i / h4, c = (i - r * h4) * 4;
+      *reinterpret_cast<float4*>(d.z + (row0 + r) * d.ld_z + c) = *reinterpret_cast<const float4*>(Ys + r * ldy + c);
+    }
+  }
+  CWN_PHASE(5);
+  if (!d.stats) {
+    if (d.bn_mean && !d.bn_training && blockIdx.x == g.start[p])  // eval: statistics are the running ones
+      bn_finalize_body(nullptr, 0, d.n_rows, d.h, d.bn_gamma, d.bn_eps, d.bn_momentum, 0, d.bn_running_mean,
+                       d.bn_running_var, nullptr, d.bn_mean, d.bn_scale, d.bn_rstd, nullptr);
+    return;
+  }
+  {  // per-column (mean, M2) of this tile: 256 / h row groups per column, combined in a fixed order
+    const int parts = T5T / h, c = tid % h, part = tid / h;
+    float s = 0.f;
+    for (int r = part; r < rows; r += parts) s += Ys[r * ldy + c];
+    red[tid] = s;
+    __syncthreads();
+    if (tid < h) {
+      float tot = 0.f;
+      for (int q = 0; q < parts; ++q) tot += red[q * h + tid];
+      meanv[tid] = tot / (float)rows;
+    }
+    __syncthreads();
+    const float mu = meanv[c];
+    float m2 = 0.f;
+    for (int r = part; r < rows; r += parts) {
+      const float dv = Ys[r * ldy + c] - mu;
+      m2 = fmaf(dv, dv, m2);
+    }
+    red[tid] = m2;
+    __syncthreads();
+    if (tid < h) {
+      float tot = 0.f;
+      for (int q = 0; q < parts; ++q) tot += red[q * h + tid];
+      d.stats[((int64_t)rt * 2 + 0) * h + tid] = meanv[tid];
+      d.stats[((int64_t)rt * 2 + 1) * h + tid] = tot;
+    }
+  }
+  CWN_PHASE(6);
+  if (d.bn_mean && d.counter) {
+    const int total = g.start[p + 1] - g.start[p];
+    const bool last_ = last_cta_of_problem(d.counter, total);
+    CWN_PHASE(7);
+    if (last_) {
+      const int n_tiles = (int)((d.n_rows + T5R - 1) / T5R);
+      bn_finalize_body(d.stats, n_tiles, d.n_rows, d.h, d.bn_gamma, d.bn_eps, d.bn_momentum, 1, d.bn_running_mean,
+                       d.bn_running_var, d.bn_num_batches_tracked, d.bn_mean, d.bn_scale, d.bn_rstd,
+                       reinterpret_cast<float*>(smem5), (int)(L.total / 4), T5R);
+      if (threadIdx.x == 0) *d.counter = 0;
+      CWN_PHASE(8);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+struct T5BwdSmem {
+  uint32_t gm_hi, gm_lo, xm_hi, xm_lo, wm_hi, wm_lo, gt_hi, gt_lo, vout, bsum, total;
+  uint32_t g_lbo, x_lbo, w_lbo;  // MN-major: stride between 32-column groups (sbo = 512 everywhere)
+  __host__ __device__ T5BwdSmem(int K, int h) {
+    g_lbo = x_lbo = 512u * (T5R / 4);
+    w_lbo = 512u * (uint32_t)(h / 4);
+    const uint32_t gm = (uint32_t)(h / 32) * g_lbo, xm = (uint32_t)(K / 32) * x_lbo, wm = (uint32_t)(K / 32) * w_lbo;
+    const uint32_t gt = (tc5::Tiled::bytes(T5R, h) + 1023u) & ~1023u;
+    gm_hi = 0; gm_lo = gm; xm_hi = 2 * gm; xm_lo = 2 * gm + xm; wm_hi = 2 * gm + 2 * xm; wm_lo = wm_hi + wm;
+    gt_hi = wm_lo + wm; gt_lo = gt_hi + gt;
+    vout = gt_lo + gt;                        // [6][h] floats
+    bsum = vout + 6u * (uint32_t)h * 4u;      // [256 / (h/4)][h] floats
+    total = bsum + (uint32_t)(T5T / (h / 4)) * (uint32_t)h * 4u;
+    // M = h may read one 32-column group past g_z when h < 64 is ever allowed; staging of g_in [64][K + 4] lives over gm/xm
+  }
+};
+
+template <int A_IN, int A_OUT>
+__global__ void __launch_bounds__(T5T, 1) unit_bwd_tc5_kernel(const __grid_constant__ Group<cwn_unit_bwd_desc> g) {
+  extern __shared__ __align__(1024) unsigned char smem5[];
+  __shared__ cwn_unit_bwd_desc sd;
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  CWN_PHASE(0);
+  const int p = find_problem(g, blockIdx.x);
+  if (tid == 0) { tc5::mbar_init(&bar, 1); tc5::mbar_fence_init(); }
+  const cwn_unit_bwd_desc d = stage_desc(g, p, &sd);
+  CWN_PHASE(1);
+  const int j = blockIdx.x - g.start[p];
+  const int K = d.k0 + d.k1, K4 = K >> 2, h = d.h, h4 = h >> 2;
+  const bool want_gin = d.g_in0 || d.g_in1;
+  // TMEM: product 1 (g_in, N = K) at column 0: 1 + nb1 accumulators; product 2 (g_W, N = K) behind it: 1 + nb2
+  const int nb1 = K <= 64 ? 2 : 1, nb2 = 1;
+  const uint32_t col2 = (uint32_t)((1 + nb1) * K);
+  const uint32_t tmem_cols = t5_pow2_cols((int)col2 + (1 + nb2) * K);
+  if (warp == 0) tc5::tmem_alloc(&tmem_s, tmem_cols);
+  const T5BwdSmem L(K, h);
+  const tc5::Tiled tg(T5R);
+  const int n_tiles = (int)((d.n_rows + T5R - 1) / T5R);
+  float* wpart = d.w_partials + (int64_t)j * h * K;
+  float* bpart = d.b_partials + (int64_t)j * h;
+  const bool transform = d.in_scale0 || d.in_scale1 || d.in_act != CWN_ACT_ID;
+  float* vout = reinterpret_cast<float*>(smem5 + L.vout);
+  float* bsum = reinterpret_cast<float*>(smem5 + L.bsum);
+  for (int c = tid; c < h; c += T5T) {
+    const bool live = d.has_bn;
+    vout[c] = live ? __ldg(d.mean + c) : 0.f;
+    vout[h + c] = live ? __ldg(d.scale + c) : 1.f;
+    vout[2 * h + c] = live ? __ldg(d.rstd + c) : 0.f;
+    vout[3 * h + c] = (live && d.beta) ? __ldg(d.beta + c) : 0.f;
+    vout[4 * h + c] = live ? __ldcg(d.c1 + c) : 0.f;
+    vout[5 * h + c] = live ? __ldcg(d.c2 + c) : 0.f;
+  }
+  const int lgk = t5_log2(K4), c4x = tid & (K4 - 1), rbx = tid >> lgk, rsx = T5T >> lgk;  // this thread's chunk of X / W rows
+  {  // W [h (inner) x K] -> MN-major swizzled, once per CTA
+    const float* wcol = d.w + c4x * 4;
+    for (int r0 = rbx; r0 < h; r0 += 4 * rsx) {
+      float4 v[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int r = r0 + jj * rsx;
+        v[jj] = r < h ? ldg_f4(wcol + (int64_t)r * d.ld_w) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int r = r0 + jj * rsx;
+        if (r >= h) continue;
+        float4 hi, lo;
+        tc5::split_tf32x4(v[jj], hi, lo);
+        const uint32_t o = tc5::mn_off(r, c4x, L.w_lbo, 512u);
+        *reinterpret_cast<float4*>(smem5 + L.wm_hi + o) = hi;
+        *reinterpret_cast<float4*>(smem5 + L.wm_lo + o) = lo;
+      }
+    }
+  }
+  __syncthreads();  // vout ready
+  const uint32_t tmem_base_lane = ((uint32_t)(32 * (warp & 3)) << 16);
+  uint32_t parity = 0;
+  bool first = true;
+  for (int tile = j; tile < n_tiles; tile += d.n_ctas, first = false, parity ^= 1u) {
+    const int64_t row0 = (int64_t)tile * T5R;
+    const int rows = (int)((d.n_rows - row0 < T5R) ? d.n_rows - row0 : T5R);
+    if (first) CWN_PHASE(2);
+    {  // g_z = scale * (g_out act'(y) - c1 - zhat c2)  (plain g_out act'(z) without BatchNorm): registers -> both layouts;
+       // f_in(X) -> MN-major. Thread -> (column chunk q of z / g_out, rows rbg + j rsg) and (chunk c4x of X, rows rbx + j rsx);
+       // the loads of a trip (z, g_out and X rows) are all requested before the first is consumed.
+      const int lgh = t5_log2(h4), q = tid & (h4 - 1), c = q * 4, rbg = tid >> lgh, rsg = T5T >> lgh;
+      const float4 mu = *reinterpret_cast<const float4*>(vout + c), sc = *reinterpret_cast<const float4*>(vout + h + c);
+      const float4 rs = *reinterpret_cast<const float4*>(vout + 2 * h + c), be = *reinterpret_cast<const float4*>(vout + 3 * h + c);
+      const float4 c1 = *reinterpret_cast<const float4*>(vout + 4 * h + c), c2 = *reinterpret_cast<const float4*>(vout + 5 * h + c);
+      const T5InCol<cwn_unit_bwd_desc> col(d, c4x * 4, row0, transform);
+      const float* zcol = d.z + row0 * d.ld_z + c;
+      const float* gcol = d.g_out + row0 * d.ld_g + c;
+      float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
+      constexpr int NB = 4;
+      for (int t0 = 0; t0 * rsg + rbg < T5R || t0 * rsx + rbx < T5R; t0 += NB) {
+        float4 zv[NB], gv[NB], xv[NB];
+#pragma unroll
+        for (int jj = 0; jj < NB; ++jj) {
+          const int r = rbg + (t0 + jj) * rsg, rx = rbx + (t0 + jj) * rsx;
+          zv[jj] = gv[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < rows) {
+            zv[jj] = ldg_f4(zcol + (int64_t)r * d.ld_z);
+            gv[jj] = ldg_f4(gcol + (int64_t)r * d.ld_g);
+          }
+          xv[jj] = col.raw(rx, rows);
+        }
+#pragma unroll
+        for (int jj = 0; jj < NB; ++jj) {
+          const int r = rbg + (t0 + jj) * rsg, rx = rbx + (t0 + jj) * rsx;
+          float4 hi, lo;
+          if (r < T5R) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < rows) {
+              const float zz[4] = {zv[jj].x, zv[jj].y, zv[jj].z, zv[jj].w}, gg[4] = {gv[jj].x, gv[jj].y, gv[jj].z, gv[jj].w};
+              const float m_[4] = {mu.x, mu.y, mu.z, mu.w}, s_[4] = {sc.x, sc.y, sc.z, sc.w}, r_[4] = {rs.x, rs.y, rs.z, rs.w};
+              const float b_[4] = {be.x, be.y, be.z, be.w}, c1_[4] = {c1.x, c1.y, c1.z, c1.w}, c2_[4] = {c2.x, c2.y, c2.z, c2.w};
+              float ov[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float zc = zz[e] - m_[e];
+                const float gy = gg[e] * act_grad<A_OUT>(d.act, zc * s_[e] + b_[e]);
+                ov[e] = d.has_bn ? s_[e] * (gy - c1_[e] - zc * r_[e] * c2_[e]) : gy;
+              }
+              o = make_float4(ov[0], ov[1], ov[2], ov[3]);
+              colsum = f4_add(colsum, o);
+            }
+            tc5::split_tf32x4(o, hi, lo);
+            const uint32_t om = tc5::mn_off(r, q, L.g_lbo, 512u), ot = tg.off(r, q);
+            *reinterpret_cast<float4*>(smem5 + L.gm_hi + om) = hi;
+            *reinterpret_cast<float4*>(smem5 + L.gm_lo + om) = lo;
+            *reinterpret_cast<float4*>(smem5 + L.gt_hi + ot) = hi;
+            *reinterpret_cast<float4*>(smem5 + L.gt_lo + ot) = lo;
+          }
+          if (rx < T5R) {
+            tc5::split_tf32x4(col.template apply<A_IN>(xv[jj], rx, rows), hi, lo);
+            const uint32_t o = tc5::mn_off(rx, c4x, L.x_lbo, 512u);
+            *reinterpret_cast<float4*>(smem5 + L.xm_hi + o) = hi;
+            *reinterpret_cast<float4*>(smem5 + L.xm_lo + o) = lo;
+          }
+        }
+      }
+      *reinterpret_cast<float4*>(bsum + rbg * h + c) = colsum;
+    }
+    tc5::fence_async_smem();
+    tc5::fence_before_sync();
+    __syncthreads();
+    tc5::fence_after_sync();
+    if (first) CWN_PHASE(3);
+    const uint32_t tmem = tmem_s;
+    if (tid == 0) {
+      const uint32_t s0 = tc5::smem_u32(smem5);
+      if (want_gin)  // g_in [64 x K] = g_z [64 x h] (K-major) * W [h x K] (MN-major), inner = h
+        t5_issue(tmem, K, nb1, s0 + L.gt_hi, s0 + L.gt_lo, tg.s_c, tg.s_r, 2 * tg.s_c, 0, s0 + L.wm_hi, s0 + L.wm_lo, L.w_lbo,
+                 512u, 1024u, 1, h, tc5::idesc_tf32(T5R, K, 0, 1));
+      // g_W [h x K] = g_z^T (A MN-major, inner = rows) * f_in(X) (B MN-major)
+      t5_issue(tmem + col2, K, nb2, s0 + L.gm_hi, s0 + L.gm_lo, L.g_lbo, 512u, 1024u, 1, s0 + L.xm_hi, s0 + L.xm_lo, L.x_lbo,
+               512u, 1024u, 1, T5R, tc5::idesc_tf32(h, K, 1, 1));
+      tc5::mma_commit(&bar);
+    }
+    if (tid < h) {  // bias-gradient partial = column sums of g_z (row groups in order), while the tensor core works
+      float s_ = 0.f;
+      for (int m = 0; m < T5T / h4; ++m) s_ += bsum[m * h + tid];  // (thread group m summed rows m, m + 256 / h4, ...)
+      bpart[tid] = first ? s_ : bpart[tid] + s_;
+    }
+    tc5::mbar_wait(&bar, parity);
+    tc5::fence_after_sync();
+    if (first) CWN_PHASE(4);
+    // ---- epilogue 2 first (it only needs registers): weight-gradient partial rows straight to this CTA's slab
+    {
+      const int q = warp & 3, half = warp >> 2;
+      const bool m64 = h == 64;
+      const int c_row = m64 ? 16 * q + lane : 32 * q + lane;  // M = 64: lanes 0..15 of each quadrant; M = 128: lane == row
+      const bool live = m64 ? lane < 16 : true;
+      const int k_lo = half * (K >> 1), k_hi = k_lo + (K >> 1);
+      for (int k0 = k_lo; k0 < k_hi; k0 += 16) {
+        float v[16];
+        t5_read16(tmem + tmem_base_lane + col2 + (uint32_t)k0, K, nb2, v);
+        if (live) {
+          float4* dst = reinterpret_cast<float4*>(wpart + (int64_t)c_row * K + k0);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float4 o = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+            if (!first) o = f4_add(dst[e], o);
+            dst[e] = o;
+          }
+        }
+      }
+    }
+    // ---- epilogue 1: g_in tile staged in shared memory (over g_z / X, dead now), then coalesced (accumulating) stores
+    if (want_gin) {
+      float* Gs = reinterpret_cast<float*>(smem5);
+      const int ldgs = K + 4;
+      const int q = warp & 3, half = warp >> 2;
+      const int r = 16 * q + lane;
+      const int k_lo = half * (K >> 1), k_hi = k_lo + (K >> 1);
+      for (int k0 = k_lo; k0 < k_hi; k0 += 16) {
+        float v[16];
+        t5_read16(tmem + tmem_base_lane + (uint32_t)k0, K, nb1, v);
+        if (lane < 16) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            *reinterpret_cast<float4*>(Gs + r * ldgs + k0 + 4 * e) = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+        }
+      }
+      tc5::fence_before_sync();
+      __syncthreads();
+      for (int i = tid; i < rows * K4; i += T5T) {
+        const int rr = i / K4, kq = (i - rr * K4) * 4;
+        float* base = (kq < d.k0) ? (d.g_in0 ? d.g_in0 + (row0 + rr) * d.ld_gi0 + kq : nullptr)
+                                  : (d.g_in1 ? d.g_in1 + (row0 + rr) * d.ld_gi1 + (kq - d.k0) : nullptr);
+        if (!base) continue;
+        float4 o = *reinterpret_cast<const float4*>(Gs + rr * ldgs + kq);
+        if (d.accumulate_in) o = f4_add(*reinterpret_cast<const float4*>(base), o);
+        *reinterpret_cast<float4*>(base) = o;
+      }
+    }
+    tc5::fence_before_sync();
+    __syncthreads();  // staging and TMEM reads are done before the next tile overwrites them
+    tc5::fence_after_sync();
+    if (first) CWN_PHASE(5);
+  }
+  if (warp == 0) tc5::tmem_dealloc(tmem_s, tmem_cols);
+  CWN_PHASE(8);
+}
+
+// ------------------------------------------------------------------------------------------------ eligibility
+inline bool t5_enabled() {
+  static const bool on = [] { const char* v = getenv("CWN_B200_DENSE_TC5"); return !(v && v[0] == '0'); }();
+  return on;
+}
+
+inline bool t5_fwd_ok(const cwn_linear_desc& d, size_t& smem) {
+  const int K = d.k0 + d.k1, h = d.h;
+  const bool shape = (h == 16 || h == 32 || h == 64 || h == 128) && (K == 8 || K == 16 || K == 32 || K == 64 || K == 128) &&
+                     d.k0 % 4 == 0 && d.k1 % 4 == 0;
+  if (!shape) return false;
+  auto vec_ok = [](const float* a, const float* b, const float* c) { return aligned16(a) && aligned16(b) && aligned16(c); };
+  const bool lay = aligned16(d.x0) && d.ld_x0 % 4 == 0 && (d.k1 == 0 || (aligned16(d.x1) && d.ld_x1 % 4 == 0)) && aligned16(d.w) &&
+                   d.ld_w % 4 == 0 && aligned16(d.z) && d.ld_z % 4 == 0 && (!d.bias || aligned16(d.bias)) &&
+                   (!d.in_scale0 || vec_ok(d.in_mean0, d.in_scale0, d.in_beta0)) &&
+                   (!d.in_scale1 || vec_ok(d.in_mean1, d.in_scale1, d.in_beta1)) && (!d.stats || aligned16(d.stats));
+  if (!lay) return false;
+  const T5FwdSmem L(K, h);
+  if (L.total > smem) smem = L.total;
+  return L.total <= 200u * 1024u;
+}
+
+inline bool t5_bwd_ok(const cwn_unit_bwd_desc& d, size_t& smem) {
+  const int K = d.k0 + d.k1, h = d.h;
+  const bool shape = (h == 64 || h == 128) && (K == 32 || K == 64 || K == 128) && d.k0 % 4 == 0 && d.k1 % 4 == 0;
+  if (!shape) return false;
+  auto vec_ok = [](const float* a, const float* b, const float* c) { return aligned16(a) && aligned16(b) && aligned16(c); };
+  const bool lay = aligned16(d.x0) && d.ld_x0 % 4 == 0 && (d.k1 == 0 || (aligned16(d.x1) && d.ld_x1 % 4 == 0)) && aligned16(d.w) &&
+                   d.ld_w % 4 == 0 && aligned16(d.z) && d.ld_z % 4 == 0 && aligned16(d.g_out) && d.ld_g % 4 == 0 &&
+                   (!d.in_scale0 || vec_ok(d.in_mean0, d.in_scale0, d.in_beta0)) &&
+                   (!d.in_scale1 || vec_ok(d.in_mean1, d.in_scale1, d.in_beta1)) &&
+                   (!d.g_in0 || (aligned16(d.g_in0) && d.ld_gi0 % 4 == 0)) && (!d.g_in1 || (aligned16(d.g_in1) && d.ld_gi1 % 4 == 0)) &&
+                   aligned16(d.w_partials) && (!d.has_bn || (aligned16(d.mean) && aligned16(d.scale) && aligned16(d.rstd)));
+  if (!lay) return false;
+  const T5BwdSmem L(K, h);
+  if (L.total > smem) smem = L.total;
+  return L.total <= 220u * 1024u;
+}
+
+}  // namespace cwn

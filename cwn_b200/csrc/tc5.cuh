@@ -3,12 +3,17 @@
 // Operand layout ("core-matrix tiled", no swizzle). A row-major fp32 matrix [R][C] (R % 8 == 0, C % 4 == 0) is kept in
 // shared memory as 8-row x 16-byte core matrices:
 //     byte(r, c) = (r / 8) * S_r + (r % 8) * 16 + (c / 4) * S_c + (c % 4) * 4
-// with S_r, S_c free multiples of 16 bytes (S_r >= 128). ONE such buffer serves both operand majors of tcgen05.mma:
-//   * rows = M/N index, columns = inner index  -> "K-major"  descriptor: SBO = S_r, LBO = S_c; k-step of 8: += 2 S_c
-//   * columns = M/N index, rows = inner index  -> "MN-major" descriptor: SBO = S_c, LBO = S_r; k-step of 8: += S_r
-// so the transposed products of the backward pass (g_z^T X, g_z W) need no transposed copies. S_c = (R/8)*128 + 16
-// skews consecutive 16-byte column chunks by 4 banks: the transform-and-store loops (a lane per column chunk, i.e.
-// coalesced global reads) are shared-memory conflict-free.
+// with S_r, S_c free multiples of 16 bytes (S_r >= 128): the "K-major" operand form (rows = M/N index, columns = inner
+// index), descriptor SBO = S_r, LBO = S_c, k-step of 8: += 2 S_c. S_c = (R/8)*128 + 16 skews consecutive 16-byte column
+// chunks by 4 banks: the transform-and-store loops (a lane per column chunk, i.e. coalesced global reads) are
+// shared-memory conflict-free.
+//
+// Operands whose INNER index is the row of the row-major source (the transposed products of the backward pass,
+// g_z^T X and g_z W) are "MN-major". For 32-bit data the hardware accepts exactly one MN-major layout, the 128-byte
+// swizzle with 32-byte atoms (an un-swizzled MN-major tf32 descriptor silently yields zeros — profiles/
+// r2_tc5_probe_accumulation.txt): rows of 32 consecutive M/N elements (128 B), 4 inner rows per 512-byte atom, the
+// 32-byte chunks of a row XOR-ed with (inner row % 4); see mn_off(). Both forms are written with 16-byte stores from
+// the same registers, no transposition anywhere. Verified on hardware by tools/tc5_probe*.cu.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -54,17 +59,18 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- TMEM
-template <int COLS>
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {  // one full warp
-  static_assert(COLS >= 32 && COLS <= 512 && (COLS & (COLS - 1)) == 0, "TMEM columns: power of two in [32, 512]");
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(COLS)
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t cols) {  // one full warp; cols: power of two in [32, 512]
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(cols)
                : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
-template <int COLS>
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {  // the same warp
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(COLS) : "memory");
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {  // the same warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) { tmem_alloc(smem_result, (uint32_t)COLS); }
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) { tmem_dealloc(taddr, (uint32_t)COLS); }
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -151,6 +157,14 @@ __device__ __forceinline__ void issue_3xtf32(uint32_t d_tmem, uint32_t a_hi, uin
     mma_tf32(d_tmem, dah, dbh, idesc, 1u);
     acc = 1u;
   }
+}
+
+// MN-major swizzled buffer of a row-major [R (inner)][C (M or N)] matrix: byte offset of the 16-byte chunk (r, c = 4 q).
+// Atoms of 4 inner rows x 32 columns (512 B): sbo = stride between 4-row groups, lbo = stride between 32-column groups.
+// The buffer must be 1024-byte aligned; descriptor layout type 1; k-step of 8 inner rows: += 2 sbo.
+__host__ __device__ __forceinline__ uint32_t mn_off(int r, int q, uint32_t lbo, uint32_t sbo) {
+  return (uint32_t)(q >> 3) * lbo + (uint32_t)(r >> 2) * sbo + (uint32_t)(r & 3) * 128u +
+         ((((uint32_t)(q & 7) >> 1) ^ (uint32_t)(r & 3)) << 5) + ((uint32_t)(q & 1) << 4);
 }
 
 }  // namespace tc5

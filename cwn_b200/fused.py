@@ -35,11 +35,14 @@ def _tile_rows(row_counts):
     last CTA to merge, and the backward kernel fits one wave.)"""
     if _FORCED_TILE_ROWS:
         return _FORCED_TILE_ROWS
+    if _TC5:
+        return 64  # the tensor-core kernels (csrc/dense_tc5.cuh) own 64-row tiles; other tile heights take the FFMA path
     return 32 if sum((n + 63) // 64 for n in row_counts) < _TILE32_BELOW else 64
 
 
 _TILE32_BELOW = int(os.environ.get('CWN_B200_TILE32_BELOW', '96'))  # A/B switch for profiling
 _FORCED_TILE_ROWS = int(os.environ.get('CWN_B200_TILE_ROWS', '0'))  # A/B switch for profiling (32 or 64)
+_TC5 = os.environ.get('CWN_B200_DENSE_TC5', '1') != '0'  # tcgen05 dense kernels (default); 0 = FFMA kernels
 
 
 class _Unit(object):

@@ -399,20 +399,32 @@ def test_batched_equals_unbatched():  # mp/test_models.py:139-185, mp/test_molec
             assert_close(torch.cat(batched[k]), torch.cat(single[k]), rtol=0, atol=1e-6, what=k)
 
 
-def test_zinc_shaped_training_step_against_oracle():
-    """BASELINE config 2 shape (hidden 64, 4 layers, use_coboundaries, edge embeddings) on a reduced batch."""
+@pytest.mark.parametrize('nonlinearity,n_complexes,seed', [('relu', 16, 0), ('elu', 16, 0), ('elu', 64, 1), ('tanh', 16, 2)])
+def test_zinc_shaped_training_step_against_oracle(nonlinearity, n_complexes, seed):
+    """BASELINE config 2 shape (hidden 64, 4 layers, use_coboundaries, edge embeddings) on a reduced batch: output and
+    loss against the CPU oracle for every activation; EVERY parameter gradient for the smooth activations.
+
+    Why not the ReLU gradients: two fp32 forwards (CPU oracle, GPU) differ by ~1e-6 in every pre-activation, and a
+    pre-activation that crosses zero flips a ReLU derivative — an O(1) change of that element's whole gradient path.
+    Measured with tools/dbg_grad_err.py (profiles/r2_relu_gradient_flips.txt): at 64 complexes the FFMA kernels and the
+    tensor-core kernels each exceed rtol 1e-4 against the oracle for 2 of 4 seeds (errors up to 1e-2), with the SAME
+    kernels passing at 1e-6 for the other seeds — a property of the comparison, not of a kernel. ReLU backward is
+    pinned where no second forward is involved: the reference's golden training steps
+    (test_train_step_matches_reference_and_oracle) and fast / tensor-core vs generic kernels behind the same forward
+    (test_dense_fast_path_equals_generic_path). ELU (C1) and tanh make the gradient a Lipschitz function of the
+    forward, so there the per-parameter check is exact science."""
     cfg = dict(atom_types=28, bond_types=4, out_size=1, num_layers=4, hidden=64, dropout_rate=0.0, max_dim=2,
-               embed_edge=True, use_coboundaries=True)
-    torch.manual_seed(0)
+               embed_edge=True, use_coboundaries=True, nonlinearity=nonlinearity)
+    torch.manual_seed(seed)
     model = EmbedSparseCIN(**cfg)
     sd = oracle_state(model.state_dict(), requires_grad=True)
-    comps = synthetic.zinc_like_complexes(16, seed=0)
+    comps = synthetic.zinc_like_complexes(n_complexes, seed=seed)
     snap = O.Snapshot(ComplexBatch.from_complex_list(comps))
     ref = O.embed_sparse_cin(sd, cfg, snap, training=True)
     ref_loss = torch.nn.functional.l1_loss(ref, snap.y.view(-1, 1))
     ref_loss.backward()
     model.to(DEV).train()
-    batch = ComplexBatch.from_complex_list(synthetic.zinc_like_complexes(16, seed=0)).to(DEV)
+    batch = ComplexBatch.from_complex_list(synthetic.zinc_like_complexes(n_complexes, seed=seed)).to(DEV)
     out = model(batch)
     loss = torch.nn.functional.l1_loss(out, batch.y.view(-1, 1))
     loss.backward()
@@ -422,7 +434,8 @@ def test_zinc_shaped_training_step_against_oracle():
         if sd[k].grad is None:  # e.g. the coboundary message net of the top dimension: no upper adjacency there
             assert p.grad is None or float(p.grad.abs().sum()) == 0.0, k
             continue
-        assert_close(p.grad, sd[k].grad, rtol=1e-4, atol=1e-5, what=f'grad {k}')
+        if nonlinearity != 'relu':
+            assert_close(p.grad, sd[k].grad, rtol=1e-4, atol=1e-5, what=f'grad {k}')
 
 
 # ------------------------------------------------------------------------------------------------ full-size properties

@@ -17,12 +17,6 @@ using namespace cwn::tc5;
 
 struct Args { const float* a; const float* b; float* d; int K, N, M, a_fmt, b_fmt, gm; };
 
-// MN-major swizzled buffer of a row-major [R (inner)][C (M or N)] matrix: byte offset of the 16-byte chunk (r, c = 4 q)
-__device__ __forceinline__ uint32_t mn_off(int r, int q, uint32_t lbo, uint32_t sbo) {
-  return (uint32_t)(q >> 3) * lbo + (uint32_t)(r >> 2) * sbo + (uint32_t)(r & 3) * 128u +
-         ((((uint32_t)(q & 7) >> 1) ^ (uint32_t)(r & 3)) << 5) + ((uint32_t)(q & 1) << 4);
-}
-
 __global__ void __launch_bounds__(128) probe2_kernel(Args p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bar;
