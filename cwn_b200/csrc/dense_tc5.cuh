@@ -5,24 +5,32 @@
 // coboundary message Linear, applied here as two per-cell products).
 //
 // Precision. fp32 parity (rtol 1e-5) rules out plain TF32 (10-bit mantissa). Every operand is split in registers into
-// hi = tf32(v), lo = tf32(v - hi) and the product is formed as lo*hi + hi*lo + hi*hi (3xTF32). What limits accuracy
-// then is the tensor core's accumulator: it truncates (rounds toward zero) at every accumulation, a biased error that
-// a chain of 24 accumulations makes 3-4x larger than a sequential fp32 FMA chain (measured:
-// profiles/r2_tc5_probe_accumulation.txt; the round-1 mma.sync variant failed the training-step parity test for this
-// reason). So the accumulation is spread over several TMEM accumulators — one for all the small lo*hi / hi*lo terms,
-// `nb` for k-ranges of the hi*hi terms — which the epilogue adds in fp32 round-to-nearest. With nb >= 2 the result is
-// MORE accurate than the FMA chain (rms error 0.85x at nb = 2, 0.65x at nb = 4, K = 64); TMEM (512 columns) is what
-// pays for it.
+// hi = tf32(v), lo = tf32(v - hi) (3xTF32 and the lo*lo term on top). What limits accuracy then is the tensor core's
+// accumulator: it truncates (rounds toward zero) at every accumulation, a biased error that a chain of 24
+// accumulations makes 3-4x larger than a sequential fp32 FMA chain (measured: profiles/r2_tc5_probe_accumulation.txt;
+// the round-1 mma.sync variant failed the training-step parity test for this reason). So (a) the small cross terms
+// never share an accumulator with hi*hi, and (b) the hi*hi chain is cut into `nb` k-ranges with one accumulator each,
+// which the epilogue adds in fp32 round-to-nearest. With nb >= 2 the result is MORE accurate than the FMA chain (rms
+// error 0.85x at nb = 2, 0.65x at nb = 4, K = 64); TMEM (512 columns) is what pays for it.
 //
-// Tiles. A CTA owns 64 rows (instruction M = 64; D row i lives in TMEM lane 32 (i / 16) + i % 16). Operands pass
-// through registers exactly once (the previous unit's BatchNorm + activation is applied there, then the split) and are
-// written to shared memory in the two layouts of tc5.cuh with conflict-free 16-byte stores:
-//   forward   z = f(X) W^T          : A = f(X) [64 x K] K-major, B = W [h x K] K-major                       N = h
-//   backward  g_in = g_z W          : A = g_z [64 x h] K-major,  B = W [h (inner) x K] MN-major              N = K
-//             g_W  = g_z^T f(X)     : A = g_z [64 (inner) x h] MN-major, B = f(X) [64 (inner) x K] MN-major  M = h, N = K
+// One instruction per k-step. A tcgen05.mma costs ~80 cycles to issue whatever its shape up to 128 x 128 x 8
+// (profiles/r2_tc5_probe_issue_latency.txt), and the issuing thread is the serial bottleneck of tiles this small. So
+// the hi and lo parts are CONCATENATED along the operand's M / N extent instead of being issued as three products:
+//     [A_hi ; A_lo] (M = 128)  x  [B_hi ; B_lo] (N = 2 n)   ->   D = | hi*hi  hi*lo |   rows 0..63    (TMEM lanes 0..63)
+//                                                                   | lo*hi  lo*lo |   rows 64..127
+// all four terms, each in its own accumulator cells, from ONE instruction (K/8 instructions per product instead of
+// 3 K/8). The epilogue adds the two column halves per lane, stages the 128 rows in shared memory and adds row r + 64
+// to row r there.
+//
+// Tiles. A CTA owns 64 rows of the unit. Operands pass through registers exactly once (the previous unit's BatchNorm +
+// activation is applied there, then the split) and are written to shared memory in the two layouts of tc5.cuh with
+// conflict-free 16-byte stores:
+//   forward   z = f(X) W^T       : A = f(X) [64 x K] K-major, B = W [h x K] K-major                          N = 2 h
+//   backward  g_in = g_z W       : A = g_z [64 x h] K-major,  B = W [h (inner) x K] MN-major                 N = 2 K
+//             g_W  = g_z^T f(X)  : A = g_z [64 (inner) x h] MN-major, B = f(X) [64 (inner) x K] MN-major     M = 2 h, N = 2 K
 // One thread issues the MMAs, one tcgen05.commit arrives on an mbarrier, and the epilogue reads TMEM with
-// tcgen05.ld (32x32b), stages the tile in shared memory (the operand buffers are dead by then) and leaves with
-// coalesced 128-bit stores; BatchNorm partials are taken from the staged tile.
+// tcgen05.ld (32x32b; M = 128: D row i is TMEM lane i), stages the tile in shared memory (the operand buffers are dead
+// by then) and leaves with coalesced 128-bit stores; BatchNorm partials are taken from the staged tile.
 #pragma once
 #include "tc5.cuh"
 
@@ -31,14 +39,13 @@ namespace cwn {
 constexpr int T5R = 64;    // rows per CTA tile
 constexpr int T5T = 256;   // threads per CTA
 
-// number of k-range accumulators for the hi*hi terms, given the accumulator width N and the inner extent
-__host__ __device__ __forceinline__ int t5_big_blocks(int N, int inner, int column_budget) {
-  int nb = column_budget / N - 1;
-  if (nb > 4) nb = 4;
+// number of k-range accumulators, given how many the TMEM budget allows and the inner extent; every accumulator
+// receives at least one k-step
+__host__ __device__ __forceinline__ int t5_blocks(int want, int inner) {
   const int ksteps = inner / 8;
-  if (nb > ksteps) nb = ksteps;
+  int nb = want < ksteps ? want : ksteps;
   if (nb < 1) nb = 1;
-  const int per = (ksteps + nb - 1) / nb;   // k-steps per accumulator; every accumulator must receive at least one
+  const int per = (ksteps + nb - 1) / nb;
   return (ksteps + per - 1) / per;
 }
 __host__ __device__ __forceinline__ uint32_t t5_pow2_cols(int cols) {
@@ -47,54 +54,51 @@ __host__ __device__ __forceinline__ uint32_t t5_pow2_cols(int cols) {
   return c;
 }
 
-// Issue D[M x N] = A * B over `inner` with the accumulator scheme above. ONE thread.
-// acc 0 at d_tmem: small terms; acc 1 + b at d_tmem + (1 + b) N: hi*hi of k-steps [b per, (b + 1) per).
-__device__ __forceinline__ void t5_issue(uint32_t d_tmem, int N, int nb, uint32_t a_hi, uint32_t a_lo, uint32_t a_lbo, uint32_t a_sbo,
-                                         uint32_t a_step, uint32_t a_layout, uint32_t b_hi, uint32_t b_lo, uint32_t b_lbo,
-                                         uint32_t b_sbo, uint32_t b_step, uint32_t b_layout, int inner, uint32_t idesc) {
-  // Lean by construction: the issuing thread is the serial bottleneck of a tile this small (a first version that built
-  // four descriptors and divided ks by `per` at every step spent ~120 cycles per MMA in integer arithmetic — tools/
-  // tc5_probe3.cu). Descriptors advance by adding to their start-address field (bits 0..13, units of 16 bytes).
+// Issue D = A_cat * B_cat over `inner` (one instruction per k-step of 8), k-range block b into the accumulator at
+// d_tmem + b * N. ONE thread. Lean by construction: a first version that rebuilt four descriptors and divided at every
+// step spent ~120 cycles per MMA in integer arithmetic; descriptors now advance by adding to their start-address
+// field (bits 0..13, units of 16 bytes).
+__device__ __forceinline__ void t5_issue(uint32_t d_tmem, int N, int nb, uint32_t a, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_step,
+                                         uint32_t a_layout, uint32_t b, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_step,
+                                         uint32_t b_layout, int inner, uint32_t idesc) {
   const int ksteps = inner >> 3, per = (ksteps + nb - 1) / nb;
-  uint64_t dah = tc5::smem_desc(a_hi, a_lbo, a_sbo, a_layout), dal = tc5::smem_desc(a_lo, a_lbo, a_sbo, a_layout);
-  uint64_t dbh = tc5::smem_desc(b_hi, b_lbo, b_sbo, b_layout), dbl = tc5::smem_desc(b_lo, b_lbo, b_sbo, b_layout);
+  uint64_t da = tc5::smem_desc(a, a_lbo, a_sbo, a_layout), db = tc5::smem_desc(b, b_lbo, b_sbo, b_layout);
   const uint64_t sa = a_step >> 4, sb = b_step >> 4;
-  uint32_t d_big = d_tmem + (uint32_t)N;
   int ks = 0;
-  for (int blk = 0; blk < nb; ++blk, d_big += (uint32_t)N) {
+  for (int blk = 0; blk < nb; ++blk, d_tmem += (uint32_t)N) {
     const int end = (ks + per < ksteps) ? ks + per : ksteps;
-    for (int first = 1; ks < end; ++ks, first = 0, dah += sa, dal += sa, dbh += sb, dbl += sb) {
-      tc5::mma_tf32(d_tmem, dal, dbh, idesc, ks > 0);
-      tc5::mma_tf32(d_big, dah, dbh, idesc, first ? 0u : 1u);
-      tc5::mma_tf32(d_tmem, dah, dbl, idesc, 1u);
-    }
+    for (uint32_t acc = 0; ks < end; ++ks, acc = 1u, da += sa, db += sb) tc5::mma_tf32(d_tmem, da, db, idesc, acc);
   }
 }
 
-// 16 consecutive accumulator columns of this thread's TMEM lane: every accumulator's load is issued before the single
-// wait; hi*hi blocks are added in order, then the small terms (fp32 RN adds)
-__device__ __forceinline__ void t5_read16(uint32_t taddr, int N, int nb, float (&v)[16]) {
-  float small[16], b1[16], b2[16], b3[16];
-  tc5::tmem_ld16(taddr, small);
-  tc5::tmem_ld16(taddr + (uint32_t)N, v);
-  if (nb > 1) tc5::tmem_ld16(taddr + (uint32_t)(2 * N), b1);
-  if (nb > 2) tc5::tmem_ld16(taddr + (uint32_t)(3 * N), b2);
-  if (nb > 3) tc5::tmem_ld16(taddr + (uint32_t)(4 * N), b3);
+// v[0..16) = SUM over the nb accumulators (`stride` columns apart) of 16 consecutive columns of this thread's TMEM
+// lane: two loads in flight per wait (register budget: the forward kernel runs two CTAs per SM), blocks added in order
+__device__ __forceinline__ void t5_sum16(uint32_t taddr, int stride, int nb, float (&v)[16]) {
+  float b1[16];
+  tc5::tmem_ld16(taddr, v);
+  if (nb > 1) tc5::tmem_ld16(taddr + (uint32_t)stride, b1);
   tc5::tmem_ld_wait();
   if (nb > 1) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] += b1[j];
   }
-  if (nb > 2) {
+  for (int b = 2; b < nb; ++b) {
+    tc5::tmem_ld16(taddr + (uint32_t)(b * stride), b1);
+    tc5::tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] += b2[j];
+    for (int j = 0; j < 16; ++j) v[j] += b1[j];
   }
-  if (nb > 3) {
+}
+
+// One lane's row of a concatenated product, columns [c0, c0 + 16) of the logical result: the (x*hi) half summed over
+// its k-range blocks, then the (x*lo) half; written to the staging tile T[128][ldt] (row = TMEM lane).
+__device__ __forceinline__ void t5_stage16(uint32_t tmem_lane, int n, int nb, int c0, float* trow) {
+  float a[16], b[16];
+  t5_sum16(tmem_lane + (uint32_t)c0, 2 * n, nb, a);
+  t5_sum16(tmem_lane + (uint32_t)(n + c0), 2 * n, nb, b);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] += b3[j];
-  }
-#pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] += small[j];
+  for (int e = 0; e < 16; e += 4)
+    *reinterpret_cast<float4*>(trow + c0 + e) = make_float4(a[e] + b[e], a[e + 1] + b[e + 1], a[e + 2] + b[e + 2], a[e + 3] + b[e + 3]);
 }
 
 __device__ __forceinline__ float4 t5_transform(const float4 v, const float4 mu, const float4 sc, const float4 be, int act_code,
@@ -150,13 +154,20 @@ __device__ __forceinline__ int t5_log2(int v) { return 31 - __clz(v); }
 
 // ------------------------------------------------------------------------------------------------ forward
 struct T5FwdSmem {  // byte offsets into dynamic shared memory (host and device agree through this one function)
-  uint32_t a_hi, a_lo, b_hi, b_lo, total;
+  uint32_t a, b, total;   // A_cat = [f(X)_hi ; f(X)_lo] tiled over 128 rows, B_cat = [W_hi ; W_lo] tiled over 2 h rows
+  int nb;                 // k-range accumulators of 2 h columns each
+  uint32_t tmem_cols;
   __host__ __device__ T5FwdSmem(int K, int h) {
-    const uint32_t a = tc5::Tiled::bytes(T5R, K), b = tc5::Tiled::bytes(h, K);
-    a_hi = 0; a_lo = a; b_hi = 2 * a; b_lo = 2 * a + b;
-    total = 2 * a + 2 * b;
-    const uint32_t stage = (uint32_t)T5R * (uint32_t)(h + 4) * 4u;  // output tile staged over the dead operand buffers
+    const uint32_t ab = tc5::Tiled::bytes(2 * T5R, K), bb = tc5::Tiled::bytes(2 * h, K);
+    a = 0; b = ab;
+    total = ab + bb;
+    const uint32_t stage = 2u * T5R * (uint32_t)(h + 4) * 4u;  // 128 staged rows over the dead operand buffers
     if (total < stage) total = stage;
+    int fit = 512 / (2 * h);            // accumulators that fit TMEM
+    int want = K <= 64 ? 2 : 4;         // (K <= 64: 2 keeps h = 64 at 256 columns, i.e. two CTAs per SM)
+    if (want > fit) want = fit;
+    nb = t5_blocks(want, K);
+    tmem_cols = t5_pow2_cols(nb * 2 * h);
   }
 };
 
@@ -176,14 +187,12 @@ __global__ void __launch_bounds__(T5T, 2) linear_fwd_tc5_kernel(const __grid_con
   CWN_PHASE(1);
   const int rt = blockIdx.x - g.start[p];
   const int K = d.k0 + d.k1, K4 = K >> 2, h = d.h;
-  const int nb = t5_big_blocks(h, K, h <= 64 ? 256 : 512);
-  const uint32_t tmem_cols = t5_pow2_cols((1 + nb) * h);
-  if (warp == 0) tc5::tmem_alloc(&tmem_s, tmem_cols);
+  const T5FwdSmem L(K, h);
+  const int nb = L.nb;
   const int64_t row0 = (int64_t)rt * T5R;
   const int rows = (int)((d.n_rows - row0 < T5R) ? d.n_rows - row0 : T5R);
   const bool transform = d.in_scale0 || d.in_scale1 || d.in_act != CWN_ACT_ID;
-  const T5FwdSmem L(K, h);
-  const tc5::Tiled ta(T5R), tb(h);
+  const tc5::Tiled ta(2 * T5R), tb(2 * h);
   {  // operands: global -> registers (transform, split) -> shared memory. Thread -> column chunk c4 (fixed) and rows
      // rb, rb + rs, ...; per trip up to 4 rows of X and 4 rows of W are requested before any is consumed.
     const int lg = t5_log2(K4), c4 = tid & (K4 - 1), rb = tid >> lg, rs = T5T >> lg;
@@ -198,21 +207,20 @@ __global__ void __launch_bounds__(T5T, 2) linear_fwd_tc5_kernel(const __grid_con
         va[j] = col.raw(r, rows);
         vw[j] = r < h ? ldg_f4(wcol + (int64_t)r * d.ld_w) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      if (warp == 0 && r0 == rb) tc5::tmem_alloc(&tmem_s, L.tmem_cols);  // (~330 cycles: under the loads just requested)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int r = r0 + j * rs;
         float4 hi, lo;
         if (r < T5R) {
           tc5::split_tf32x4(col.template apply<A_IN>(va[j], r, rows), hi, lo);
-          const uint32_t o = ta.off(r, c4);
-          *reinterpret_cast<float4*>(smem5 + L.a_hi + o) = hi;
-          *reinterpret_cast<float4*>(smem5 + L.a_lo + o) = lo;
+          *reinterpret_cast<float4*>(smem5 + L.a + ta.off(r, c4)) = hi;
+          *reinterpret_cast<float4*>(smem5 + L.a + ta.off(r + T5R, c4)) = lo;
         }
         if (r < h) {
           tc5::split_tf32x4(vw[j], hi, lo);
-          const uint32_t o = tb.off(r, c4);
-          *reinterpret_cast<float4*>(smem5 + L.b_hi + o) = hi;
-          *reinterpret_cast<float4*>(smem5 + L.b_lo + o) = lo;
+          *reinterpret_cast<float4*>(smem5 + L.b + tb.off(r, c4)) = hi;
+          *reinterpret_cast<float4*>(smem5 + L.b + tb.off(r + h, c4)) = lo;
         }
       }
     }
@@ -225,42 +233,37 @@ __global__ void __launch_bounds__(T5T, 2) linear_fwd_tc5_kernel(const __grid_con
   const uint32_t tmem = tmem_s;
   if (tid == 0) {
     const uint32_t s0 = tc5::smem_u32(smem5);
-    t5_issue(tmem, h, nb, s0 + L.a_hi, s0 + L.a_lo, ta.s_c, ta.s_r, 2 * ta.s_c, 0, s0 + L.b_hi, s0 + L.b_lo, tb.s_c, tb.s_r,
-             2 * tb.s_c, 0, K, tc5::idesc_tf32(T5R, h, 0, 0));
+    t5_issue(tmem, 2 * h, nb, s0 + L.a, ta.s_c, ta.s_r, 2 * ta.s_c, 0, s0 + L.b, tb.s_c, tb.s_r, 2 * tb.s_c, 0, K,
+             tc5::idesc_tf32(2 * T5R, 2 * h, 0, 0));
     tc5::mma_commit(&bar);
   }
   tc5::mbar_wait(&bar, 0);
   tc5::fence_after_sync();
   CWN_PHASE(3);
-  // epilogue: TMEM -> (+ bias) -> staged tile Ys[64][h + 4] over the operand buffers (all MMAs have completed)
-  float* Ys = reinterpret_cast<float*>(smem5);
+  // epilogue: TMEM -> staged rows T[128][h + 4] over the operand buffers (all MMAs have completed); row r of the unit
+  // is T[r] (hi*hi + hi*lo) + T[r + 64] (lo*hi + lo*lo)
+  float* T = reinterpret_cast<float*>(smem5);
   const int ldy = h + 4;
   {
-    const int q = warp & 3, half = warp >> 2;  // TMEM lane quadrant; the two warps of a quadrant split the columns
-    const int r = 16 * q + lane;                // M = 64: rows sit in lanes 0..15 of each quadrant
+    const int q = warp & 3, half = warp >> 2;     // TMEM lane quadrant; the two warps of a quadrant split the columns
     const int per_half = h >= 32 ? (h >> 1) : h;  // (h = 16: one warp per quadrant does it all)
     const int c_lo = half * per_half, c_hi = (c_lo + per_half < h) ? c_lo + per_half : h;
-    for (int c0 = c_lo; c0 < c_hi; c0 += 16) {  // (warp-uniform trip count: tcgen05.ld is warp-collective)
-      float v[16];
-      t5_read16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, h, nb, v);
-      if (lane < 16) {
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          float4 b4 = d.bias ? ldg_f4(d.bias + c0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4*>(Ys + r * ldy + c0 + j) = make_float4(v[j] + b4.x, v[j + 1] + b4.y, v[j + 2] + b4.z, v[j + 3] + b4.w);
-        }
-      }
-    }
+    const uint32_t tl = tmem + ((uint32_t)(32 * q) << 16);
+    for (int c0 = c_lo; c0 < c_hi; c0 += 16)      // (warp-uniform trip count: tcgen05.ld is warp-collective)
+      t5_stage16(tl, h, nb, c0, T + (32 * q + lane) * ldy);
   }
   tc5::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc5::tmem_dealloc(tmem, tmem_cols);
+  if (warp == 0) tc5::tmem_dealloc(tmem, L.tmem_cols);
   CWN_PHASE(4);
-  {  // coalesced stores of z
-    const int h4 = h >> 2;
+  {  // combine the two row halves, add the bias, leave with coalesced stores; the tile stays staged for the statistics
+    const int h4 = h >> 2, lgh = t5_log2(h4);
     for (int i = tid; i < rows * h4; i += T5T) {
-      const int r = i / h4, c = (i - r * h4) * 4;
-      *reinterpret_cast<float4*>(d.z + (row0 + r) * d.ld_z + c) = *reinterpret_cast<const float4*>(Ys + r * ldy + c);
+      const int r = i >> lgh, c = (i & (h4 - 1)) * 4;
+      float4 v = f4_add(*reinterpret_cast<const float4*>(T + r * ldy + c), *reinterpret_cast<const float4*>(T + (r + T5R) * ldy + c));
+      if (d.bias) v = f4_add(v, ldg_f4(d.bias + c));
+      *reinterpret_cast<float4*>(T + r * ldy + c) = v;
+      *reinterpret_cast<float4*>(d.z + (row0 + r) * d.ld_z + c) = v;
     }
   }
   CWN_PHASE(5);
@@ -270,10 +273,11 @@ __global__ void __launch_bounds__(T5T, 2) linear_fwd_tc5_kernel(const __grid_con
                        d.bn_running_var, nullptr, d.bn_mean, d.bn_scale, d.bn_rstd, nullptr);
     return;
   }
+  __syncthreads();
   {  // per-column (mean, M2) of this tile: 256 / h row groups per column, combined in a fixed order
     const int parts = T5T / h, c = tid % h, part = tid / h;
     float s = 0.f;
-    for (int r = part; r < rows; r += parts) s += Ys[r * ldy + c];
+    for (int r = part; r < rows; r += parts) s += T[r * ldy + c];
     red[tid] = s;
     __syncthreads();
     if (tid < h) {
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(T5T, 2) linear_fwd_tc5_kernel(const __grid_con
     const float mu = meanv[c];
     float m2 = 0.f;
     for (int r = part; r < rows; r += parts) {
-      const float dv = Ys[r * ldy + c] - mu;
+      const float dv = T[r * ldy + c] - mu;
       m2 = fmaf(dv, dv, m2);
     }
     red[tid] = m2;
@@ -313,21 +317,27 @@ __global__ void __launch_bounds__(T5T, 2) linear_fwd_tc5_kernel(const __grid_con
   }
 }
 
-// ------------------------------------------------------------------------------------------------ backward
+// ------------------------------------------------------------------------------------------------ backward (h = 64)
 struct T5BwdSmem {
-  uint32_t gm_hi, gm_lo, xm_hi, xm_lo, wm_hi, wm_lo, gt_hi, gt_lo, vout, bsum, total;
+  // gm = [g_z_hi | g_z_lo] MN-major (inner = rows, M = 2 h); xm = [f(X)_hi | f(X)_lo] MN-major (inner = rows, N = 2 K);
+  // gt = [g_z_hi ; g_z_lo] K-major tiled over 128 rows; wm = [W_hi | W_lo] MN-major (inner = h, N = 2 K)
+  uint32_t gm, xm, gt, wm, vout, bsum, total;
   uint32_t g_lbo, x_lbo, w_lbo;  // MN-major: stride between 32-column groups (sbo = 512 everywhere)
+  int nb1, nb2;
+  uint32_t col2, tmem_cols;
   __host__ __device__ T5BwdSmem(int K, int h) {
     g_lbo = x_lbo = 512u * (T5R / 4);
     w_lbo = 512u * (uint32_t)(h / 4);
-    const uint32_t gm = (uint32_t)(h / 32) * g_lbo, xm = (uint32_t)(K / 32) * x_lbo, wm = (uint32_t)(K / 32) * w_lbo;
-    const uint32_t gt = (tc5::Tiled::bytes(T5R, h) + 1023u) & ~1023u;
-    gm_hi = 0; gm_lo = gm; xm_hi = 2 * gm; xm_lo = 2 * gm + xm; wm_hi = 2 * gm + 2 * xm; wm_lo = wm_hi + wm;
-    gt_hi = wm_lo + wm; gt_lo = gt_hi + gt;
-    vout = gt_lo + gt;                        // [6][h] floats
-    bsum = vout + 6u * (uint32_t)h * 4u;      // [256 / (h/4)][h] floats
+    const uint32_t gmb = 2u * (uint32_t)(h / 32) * g_lbo, xmb = 2u * (uint32_t)(K / 32) * x_lbo, wmb = 2u * (uint32_t)(K / 32) * w_lbo;
+    const uint32_t gtb = (tc5::Tiled::bytes(2 * T5R, h) + 1023u) & ~1023u;
+    gm = 0; xm = gmb; gt = gmb + xmb; wm = gt + gtb;   // (the staging tile T[128][K + 4] lives over gm + xm + gt)
+    vout = wm + wmb;                                   // [6][h] floats
+    bsum = vout + 6u * (uint32_t)h * 4u;               // [256 / (h/4)][h] floats
     total = bsum + (uint32_t)(T5T / (h / 4)) * (uint32_t)h * 4u;
-    // M = h may read one 32-column group past g_z when h < 64 is ever allowed; staging of g_in [64][K + 4] lives over gm/xm
+    nb1 = t5_blocks(K <= 64 ? 2 : 1, h);               // g_in: accumulators of 2 K columns
+    nb2 = 1;                                           // g_W (only rtol 1e-4 is asked of parameter gradients)
+    col2 = (uint32_t)(nb1 * 2 * K);
+    tmem_cols = t5_pow2_cols((int)col2 + nb2 * 2 * K);
   }
 };
 
@@ -346,13 +356,8 @@ __global__ void __launch_bounds__(T5T, 1) unit_bwd_tc5_kernel(const __grid_const
   const int j = blockIdx.x - g.start[p];
   const int K = d.k0 + d.k1, K4 = K >> 2, h = d.h, h4 = h >> 2;
   const bool want_gin = d.g_in0 || d.g_in1;
-  // TMEM: product 1 (g_in, N = K) at column 0: 1 + nb1 accumulators; product 2 (g_W, N = K) behind it: 1 + nb2
-  const int nb1 = K <= 64 ? 2 : 1, nb2 = 1;
-  const uint32_t col2 = (uint32_t)((1 + nb1) * K);
-  const uint32_t tmem_cols = t5_pow2_cols((int)col2 + (1 + nb2) * K);
-  if (warp == 0) tc5::tmem_alloc(&tmem_s, tmem_cols);
   const T5BwdSmem L(K, h);
-  const tc5::Tiled tg(T5R);
+  const tc5::Tiled tg(2 * T5R);
   const int n_tiles = (int)((d.n_rows + T5R - 1) / T5R);
   float* wpart = d.w_partials + (int64_t)j * h * K;
   float* bpart = d.b_partials + (int64_t)j * h;
@@ -369,6 +374,7 @@ __global__ void __launch_bounds__(T5T, 1) unit_bwd_tc5_kernel(const __grid_const
     vout[5 * h + c] = live ? __ldcg(d.c2 + c) : 0.f;
   }
   const int lgk = t5_log2(K4), c4x = tid & (K4 - 1), rbx = tid >> lgk, rsx = T5T >> lgk;  // this thread's chunk of X / W rows
+  const uint32_t lo_x = (uint32_t)(K / 32) * L.x_lbo, lo_w = (uint32_t)(K / 32) * L.w_lbo, lo_g = (uint32_t)(h / 32) * L.g_lbo;
   {  // W [h (inner) x K] -> MN-major swizzled, once per CTA
     const float* wcol = d.w + c4x * 4;
     for (int r0 = rbx; r0 < h; r0 += 4 * rsx) {
@@ -378,6 +384,7 @@ __global__ void __launch_bounds__(T5T, 1) unit_bwd_tc5_kernel(const __grid_const
         const int r = r0 + jj * rsx;
         v[jj] = r < h ? ldg_f4(wcol + (int64_t)r * d.ld_w) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      if (warp == 0 && r0 == rbx) tc5::tmem_alloc(&tmem_s, L.tmem_cols);  // (~330 cycles: under the loads just requested)
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         const int r = r0 + jj * rsx;
@@ -385,13 +392,16 @@ __global__ void __launch_bounds__(T5T, 1) unit_bwd_tc5_kernel(const __grid_const
         float4 hi, lo;
         tc5::split_tf32x4(v[jj], hi, lo);
         const uint32_t o = tc5::mn_off(r, c4x, L.w_lbo, 512u);
-        *reinterpret_cast<float4*>(smem5 + L.wm_hi + o) = hi;
-        *reinterpret_cast<float4*>(smem5 + L.wm_lo + o) = lo;
+        *reinterpret_cast<float4*>(smem5 + L.wm + o) = hi;
+        *reinterpret_cast<float4*>(smem5 + L.wm + lo_w + o) = lo;
       }
     }
   }
   __syncthreads();  // vout ready
-  const uint32_t tmem_base_lane = ((uint32_t)(32 * (warp & 3)) << 16);
+  const uint32_t tl = ((uint32_t)(32 * (warp & 3)) << 16);  // this warp's TMEM lane quadrant
+  const int R = 32 * (warp & 3) + lane, half = warp >> 2;   // this thread's accumulator row; the quadrant's two warps split the columns
+  float* T = reinterpret_cast<float*>(smem5);               // staging [128][K + 4] over gm / xm / gt
+  const int ldt = K + 4;
   uint32_t parity = 0;
   bool first = true;
   for (int tile = j; tile < n_tiles; tile += d.n_ctas, first = false, parity ^= 1u) {
@@ -443,17 +453,17 @@ __global__ void __launch_bounds__(T5T, 1) unit_bwd_tc5_kernel(const __grid_const
               colsum = f4_add(colsum, o);
             }
             tc5::split_tf32x4(o, hi, lo);
-            const uint32_t om = tc5::mn_off(r, q, L.g_lbo, 512u), ot = tg.off(r, q);
-            *reinterpret_cast<float4*>(smem5 + L.gm_hi + om) = hi;
-            *reinterpret_cast<float4*>(smem5 + L.gm_lo + om) = lo;
-            *reinterpret_cast<float4*>(smem5 + L.gt_hi + ot) = hi;
-            *reinterpret_cast<float4*>(smem5 + L.gt_lo + ot) = lo;
+            const uint32_t om = tc5::mn_off(r, q, L.g_lbo, 512u);
+            *reinterpret_cast<float4*>(smem5 + L.gm + om) = hi;
+            *reinterpret_cast<float4*>(smem5 + L.gm + lo_g + om) = lo;
+            *reinterpret_cast<float4*>(smem5 + L.gt + tg.off(r, q)) = hi;
+            *reinterpret_cast<float4*>(smem5 + L.gt + tg.off(r + T5R, q)) = lo;
           }
           if (rx < T5R) {
             tc5::split_tf32x4(col.template apply<A_IN>(xv[jj], rx, rows), hi, lo);
             const uint32_t o = tc5::mn_off(rx, c4x, L.x_lbo, 512u);
-            *reinterpret_cast<float4*>(smem5 + L.xm_hi + o) = hi;
-            *reinterpret_cast<float4*>(smem5 + L.xm_lo + o) = lo;
+            *reinterpret_cast<float4*>(smem5 + L.xm + o) = hi;
+            *reinterpret_cast<float4*>(smem5 + L.xm + lo_x + o) = lo;
           }
         }
       }
@@ -467,12 +477,12 @@ __global__ void __launch_bounds__(T5T, 1) unit_bwd_tc5_kernel(const __grid_const
     const uint32_t tmem = tmem_s;
     if (tid == 0) {
       const uint32_t s0 = tc5::smem_u32(smem5);
-      if (want_gin)  // g_in [64 x K] = g_z [64 x h] (K-major) * W [h x K] (MN-major), inner = h
-        t5_issue(tmem, K, nb1, s0 + L.gt_hi, s0 + L.gt_lo, tg.s_c, tg.s_r, 2 * tg.s_c, 0, s0 + L.wm_hi, s0 + L.wm_lo, L.w_lbo,
-                 512u, 1024u, 1, h, tc5::idesc_tf32(T5R, K, 0, 1));
-      // g_W [h x K] = g_z^T (A MN-major, inner = rows) * f_in(X) (B MN-major)
-      t5_issue(tmem + col2, K, nb2, s0 + L.gm_hi, s0 + L.gm_lo, L.g_lbo, 512u, 1024u, 1, s0 + L.xm_hi, s0 + L.xm_lo, L.x_lbo,
-               512u, 1024u, 1, T5R, tc5::idesc_tf32(h, K, 1, 1));
+      // g_W [2 h x 2 K] = [g_z_hi | g_z_lo]^T (A MN-major, inner = rows) * [f(X)_hi | f(X)_lo] (B MN-major)
+      t5_issue(tmem + L.col2, 2 * K, L.nb2, s0 + L.gm, L.g_lbo, 512u, 1024u, 1, s0 + L.xm, L.x_lbo, 512u, 1024u, 1, T5R,
+               tc5::idesc_tf32(2 * h, 2 * K, 1, 1));
+      if (want_gin)  // g_in [128 x 2 K] = [g_z_hi ; g_z_lo] (K-major) * [W_hi | W_lo] (MN-major), inner = h
+        t5_issue(tmem, 2 * K, L.nb1, s0 + L.gt, tg.s_c, tg.s_r, 2 * tg.s_c, 0, s0 + L.wm, L.w_lbo, 512u, 1024u, 1, h,
+                 tc5::idesc_tf32(2 * T5R, 2 * K, 0, 1));
       tc5::mma_commit(&bar);
     }
     if (tid < h) {  // bias-gradient partial = column sums of g_z (row groups in order), while the tensor core works
@@ -483,51 +493,31 @@ __global__ void __launch_bounds__(T5T, 1) unit_bwd_tc5_kernel(const __grid_const
     tc5::mbar_wait(&bar, parity);
     tc5::fence_after_sync();
     if (first) CWN_PHASE(4);
-    // ---- epilogue 2 first (it only needs registers): weight-gradient partial rows straight to this CTA's slab
-    {
-      const int q = warp & 3, half = warp >> 2;
-      const bool m64 = h == 64;
-      const int c_row = m64 ? 16 * q + lane : 32 * q + lane;  // M = 64: lanes 0..15 of each quadrant; M = 128: lane == row
-      const bool live = m64 ? lane < 16 : true;
-      const int k_lo = half * (K >> 1), k_hi = k_lo + (K >> 1);
-      for (int k0 = k_lo; k0 < k_hi; k0 += 16) {
-        float v[16];
-        t5_read16(tmem + tmem_base_lane + col2 + (uint32_t)k0, K, nb2, v);
-        if (live) {
-          float4* dst = reinterpret_cast<float4*>(wpart + (int64_t)c_row * K + k0);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float4 o = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
-            if (!first) o = f4_add(dst[e], o);
-            dst[e] = o;
-          }
-        }
-      }
+    const int k_lo = half * (K >> 1), k_hi = k_lo + (K >> 1);
+    // ---- epilogue A: weight-gradient partial. T[R] = the lane's (x*hi + x*lo); g_W[c] = T[c] + T[c + 64]
+    for (int k0 = k_lo; k0 < k_hi; k0 += 16) t5_stage16(tmem + tl + L.col2, K, L.nb2, k0, T + R * ldt);
+    tc5::fence_before_sync();
+    __syncthreads();
+    for (int i = tid; i < h * K4; i += T5T) {
+      const int c = i >> lgk, k = (i & (K4 - 1)) * 4;
+      float4 v = f4_add(*reinterpret_cast<const float4*>(T + c * ldt + k), *reinterpret_cast<const float4*>(T + (c + h) * ldt + k));
+      float4* dst = reinterpret_cast<float4*>(wpart + (int64_t)c * K + k);
+      if (!first) v = f4_add(*dst, v);
+      *dst = v;
     }
-    // ---- epilogue 1: g_in tile staged in shared memory (over g_z / X, dead now), then coalesced (accumulating) stores
+    // ---- epilogue B: input gradient, the same way; coalesced (accumulating) stores
     if (want_gin) {
-      float* Gs = reinterpret_cast<float*>(smem5);
-      const int ldgs = K + 4;
-      const int q = warp & 3, half = warp >> 2;
-      const int r = 16 * q + lane;
-      const int k_lo = half * (K >> 1), k_hi = k_lo + (K >> 1);
-      for (int k0 = k_lo; k0 < k_hi; k0 += 16) {
-        float v[16];
-        t5_read16(tmem + tmem_base_lane + (uint32_t)k0, K, nb1, v);
-        if (lane < 16) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            *reinterpret_cast<float4*>(Gs + r * ldgs + k0 + 4 * e) = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
-        }
-      }
+      __syncthreads();  // T is free again
+      tc5::fence_after_sync();
+      for (int k0 = k_lo; k0 < k_hi; k0 += 16) t5_stage16(tmem + tl, K, L.nb1, k0, T + R * ldt);
       tc5::fence_before_sync();
       __syncthreads();
       for (int i = tid; i < rows * K4; i += T5T) {
-        const int rr = i / K4, kq = (i - rr * K4) * 4;
+        const int rr = i >> lgk, kq = (i & (K4 - 1)) * 4;
         float* base = (kq < d.k0) ? (d.g_in0 ? d.g_in0 + (row0 + rr) * d.ld_gi0 + kq : nullptr)
                                   : (d.g_in1 ? d.g_in1 + (row0 + rr) * d.ld_gi1 + (kq - d.k0) : nullptr);
         if (!base) continue;
-        float4 o = *reinterpret_cast<const float4*>(Gs + rr * ldgs + kq);
+        float4 o = f4_add(*reinterpret_cast<const float4*>(T + rr * ldt + kq), *reinterpret_cast<const float4*>(T + (rr + T5R) * ldt + kq));
         if (d.accumulate_in) o = f4_add(*reinterpret_cast<const float4*>(base), o);
         *reinterpret_cast<float4*>(base) = o;
       }
@@ -537,7 +527,7 @@ __global__ void __launch_bounds__(T5T, 1) unit_bwd_tc5_kernel(const __grid_const
     tc5::fence_after_sync();
     if (first) CWN_PHASE(5);
   }
-  if (warp == 0) tc5::tmem_dealloc(tmem_s, tmem_cols);
+  if (warp == 0) tc5::tmem_dealloc(tmem_s, L.tmem_cols);
   CWN_PHASE(8);
 }
 
@@ -565,7 +555,7 @@ inline bool t5_fwd_ok(const cwn_linear_desc& d, size_t& smem) {
 
 inline bool t5_bwd_ok(const cwn_unit_bwd_desc& d, size_t& smem) {
   const int K = d.k0 + d.k1, h = d.h;
-  const bool shape = (h == 64 || h == 128) && (K == 32 || K == 64 || K == 128) && d.k0 % 4 == 0 && d.k1 % 4 == 0;
+  const bool shape = h == 64 && (K == 32 || K == 64 || K == 128) && d.k0 % 4 == 0 && d.k1 % 4 == 0;
   if (!shape) return false;
   auto vec_ok = [](const float* a, const float* b, const float* c) { return aligned16(a) && aligned16(b) && aligned16(c); };
   const bool lay = aligned16(d.x0) && d.ld_x0 % 4 == 0 && (d.k1 == 0 || (aligned16(d.x1) && d.ld_x1 % 4 == 0)) && aligned16(d.w) &&

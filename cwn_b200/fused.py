@@ -176,6 +176,16 @@ def _launch(fn_name, desc_type, descs):
         ops._call(fn_name[4:], nbytes, fn, arr, len(chunk), stream)
 
 
+def _n_ctas(tile_counts):
+    """CTAs per problem of one grouped backward launch (each CTA strides over its problem's row tiles). The
+    tensor-core kernel holds one CTA per SM (130-190 KB of shared memory), so more than 148 CTAs would mean a second
+    wave that pays the descriptor + weight staging again: the tiles are spread over at most 148 CTAs instead."""
+    total = sum(tile_counts)
+    if not _TC5 or total <= 148:
+        return [min(t, 2 * 148) for t in tile_counts]
+    return [max(1, t * 148 // total) if t else 0 for t in tile_counts]
+
+
 class _UnitState(object):
     """Everything one unit keeps between forward and backward."""
     __slots__ = ('unit', 'x0', 'x1', 'in0', 'in1', 'in_act', 'z', 'mean', 'scale', 'rstd', 'n', 'h')
@@ -287,12 +297,13 @@ class FusedSparseCINDense(Function):
             descs, gins = [], []
             counters = _counters(dev, len(items))
             tr = _tile_rows([it[0].n for it in items])
+            ctas = _n_ctas([(it[0].n + tr - 1) // tr for it in items])
             for i, (st, g, want0, want1) in enumerate(items):
                 unit = st.unit
                 k0 = st.x0.size(1)
                 k1 = st.x1.size(1) if st.x1 is not None else 0
                 n_tiles = (st.n + tr - 1) // tr
-                n_ctas = min(n_tiles, 2 * 148)
+                n_ctas = ctas[i]
                 has_bn = unit.bn is not None
                 g = g.contiguous()
                 gi0 = new(st.n, k0) if want0 else None
@@ -446,12 +457,13 @@ class GroupedLinear(Function):
                     gb_bufs.append(buf), gb_out.append(buf), acc_b.append(0)
             gxs, descs, keep = [], [], []
             tr = _tile_rows([x.size(0) for x in xs])
+            ctas = _n_ctas([(x.size(0) + tr - 1) // tr for x in xs])
             for i, (x, g, (wi, off, bi)) in enumerate(zip(xs, gs, spec)):
                 w = weights[wi]
                 nr, k, h = x.size(0), x.size(1), w.size(0)
                 g = (g if g is not None else torch.zeros(nr, h, device=dev)).contiguous()
                 n_tiles = (nr + tr - 1) // tr
-                n_ctas = min(n_tiles, 2 * 148)
+                n_ctas = ctas[i]
                 gx = torch.empty(nr, k, dtype=torch.float32, device=dev) if ctx.needs_input_grad[2 + i] else None
                 wp = torch.empty(max(n_ctas, 1) * h * k, dtype=torch.float32, device=dev)
                 bp = torch.empty(max(n_ctas, 1) * h, dtype=torch.float32, device=dev)
@@ -754,14 +766,14 @@ class _LayerAggregate(Function):
                         gw_out.append(gw), gb_out.append(gb)
                 for which in ('p', 'q'):
                     descs = []
+                    ctas = _n_ctas([((xs[d] if which == 'p' else xs[d + 1]).size(0) + tr - 1) // tr for d in cob_dims])
                     for i, d in enumerate(cob_dims):
                         w = wb[2 * i]
                         gw, gb, acc = bufs[i]
                         fx = xs[d].size(1)
                         x, g, off, tgt = (xs[d], gP[d], 0, d) if which == 'p' else (xs[d + 1], gQ[d], fx, d + 1)
                         nr, k, h = x.size(0), x.size(1), w.size(0)
-                        n_tiles = (nr + tr - 1) // tr
-                        n_ctas = min(n_tiles, 2 * 148)
+                        n_ctas = ctas[i]
                         wp = torch.empty(max(n_ctas, 1) * h * k, dtype=torch.float32, device=dev)
                         bp = torch.empty(max(n_ctas, 1) * h, dtype=torch.float32, device=dev)
                         keep += [wp, bp]
