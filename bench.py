@@ -17,6 +17,13 @@ the timed region although the metric is named fwd+bwd, so nothing is skipped.
   roofline : the dominant cwn kernel of the step, algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json
   cpu_baseline : the oracle (torch-only port of the reference path; the reference itself cannot be imported
           here: torch_scatter / torch_geometric are absent) on the host cores, bounded sample
+  ragged : the same model on RAGGED batches (every step a different set of molecules, sizes varying around the ZINC
+          means) padded to one fixed-capacity layout and replayed through one CUDA graph (cwn_b200.bucketed), next to
+          the eager path on the same batches
+
+    python bench.py --config ogb ...          # BASELINE.json configs[3]: OGBEmbedSparseCIN, molhiv-shaped, 2 layers,
+                                              # mean readout, dropout 0.5 (reference exp/scripts/cwn-molhiv.sh)
+    python bench.py --sweep-full [--gpus N]   # BASELINE.json configs[4]: per-adjacency sweep, independent shards
 """
 import argparse
 import json
@@ -40,6 +47,14 @@ PRELOAD_STEPS = 320  # untimed extra warm-up steps (~0.3 s) during which nvidia-
 MODEL_CFG = dict(atom_types=28, bond_types=4, out_size=1, num_layers=4, hidden=64, dropout_rate=0.0, max_dim=2,
                  embed_edge=True, use_coboundaries=True, graph_norm='bn', readout='sum')
 WORKLOAD = 'ZINC ring-lift (max_ring=6) EmbedSparseCIN 4-layer hidden=64 batch=128 (BASELINE.json configs[1])'
+# BASELINE.json configs[3] (reference exp/scripts/cwn-molhiv.sh:3-33, mp/molec_models.py:281-350)
+OGB_CFG = dict(out_size=1, num_layers=2, hidden=64, dropout_rate=0.5, indropout_rate=0.0, max_dim=2, jump_mode=None,
+               nonlinearity='relu', readout='mean', final_readout='sum', apply_dropout_before='lin2',
+               use_coboundaries=True, embed_edge=True, graph_norm='bn')
+OGB_WORKLOAD = 'ogbg-molhiv-shaped ring-lift (max_ring=6) OGBEmbedSparseCIN 2-layer hidden=64 batch=128 dropout 0.5 ' \
+               '(BASELINE.json configs[3])'
+# ragged batches: ring count 1..4 (sizes 5..6), 4..14 chain atoms => V ~ 23, E ~ 25 on average (the ZINC means)
+RAGGED_GEN = dict(ragged=True, ring_count_range=(1, 5), pendant_range=(4, 15))
 
 
 def parse():
@@ -55,17 +70,30 @@ def parse():
     ap.add_argument('--sweep-only', action='store_true', help='only the per-adjacency kernel sweep (for ncu)')
     ap.add_argument('--sweep-full', action='store_true', help='BASELINE config 5 grid, one JSON line per point')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-ragged', action='store_true', help='skip the ragged-batch leg (padded layout, one CUDA graph)')
+    ap.add_argument('--config', default='zinc', choices=['zinc', 'ogb'], help="'ogb' = BASELINE.json configs[3]")
     return ap.parse_args()
+
+
+def workload(args):
+    """(model class name, constructor kwargs, workload string, generator kwargs, loss) of --config."""
+    if args.config == 'ogb':
+        return 'OGBEmbedSparseCIN', OGB_CFG, OGB_WORKLOAD, dict(ogb_features=True, num_pendant=8), bce
+    return 'EmbedSparseCIN', MODEL_CFG, WORKLOAD, {}, l1
+
+
+def bce(out, y):
+    return torch.nn.functional.binary_cross_entropy_with_logits(out, (y.view(-1, 1) > 0).float())  # exp/train_utils.py:11
 
 
 def l1(out, y):
     return torch.nn.functional.l1_loss(out, y.view(-1, 1))  # reference exp/train_utils.py:25-26
 
 
-def make_batches(n_batches, batch_size, seed0):
+def make_batches(n_batches, batch_size, seed0, **gen):
     from cwn_b200.data import synthetic
     from cwn_b200.data.complex import ComplexBatch
-    return [ComplexBatch.from_complex_list(synthetic.zinc_like_complexes(batch_size, seed=seed0 + i))
+    return [ComplexBatch.from_complex_list(synthetic.zinc_like_complexes(batch_size, seed=seed0 + i, **gen))
             for i in range(n_batches)]
 
 
@@ -74,13 +102,24 @@ def cells_of(batch):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_steps(steps, warmup, batch_size, budget_s=None):
+def host_threads():
+    """Every host thread this process may use (torchrun pins OMP_NUM_THREADS=1: the CPU arm undoes that explicitly)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_steps(steps, warmup, batch_size, budget_s=None, args=None):
     """The oracle's forward + loss + backward + Adam on the host cores. Returns (cells/s, ms/step, steps done)."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import cwn_oracle as O
-    from cwn_b200.mp.molec_models import EmbedSparseCIN
+    from cwn_b200.mp import molec_models
+    name, cfg, _, gen, loss_fn = workload(args) if args is not None else ('EmbedSparseCIN', MODEL_CFG, None, {}, l1)
+    oracle_fn = O.ogb_embed_sparse_cin if name == 'OGBEmbedSparseCIN' else O.embed_sparse_cin
+    torch.set_num_threads(host_threads())
     torch.manual_seed(0)
-    sd = {k: v.detach().clone() for k, v in EmbedSparseCIN(**MODEL_CFG).state_dict().items()}
+    sd = {k: v.detach().clone() for k, v in getattr(molec_models, name)(**cfg).state_dict().items()}
     leaves = []
     for k, v in sd.items():
         if v.is_floating_point() and 'running' not in k and not k.endswith(('eps1', 'eps2')):
@@ -88,15 +127,15 @@ def cpu_steps(steps, warmup, batch_size, budget_s=None):
             leaves.append(v)
     leaves = list({id(v): v for v in leaves}.values())
     opt = torch.optim.Adam(leaves, lr=1e-3)
-    batches = make_batches(4, batch_size, seed0=1000)
+    batches = make_batches(4, batch_size, seed0=1000, **gen)
     cells = cells_of(batches[0])
     done, t_total = 0, 0.0
     for i in range(warmup + steps):
         snap = O.Snapshot(batches[i % len(batches)])
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
-        out = O.embed_sparse_cin(sd, MODEL_CFG, snap, training=True)
-        loss = l1(out, snap.y)
+        out = oracle_fn(sd, cfg, snap, training=True)
+        loss = loss_fn(out, snap.y)
         loss.backward()
         opt.step()
         dt = time.perf_counter() - t0
@@ -110,15 +149,20 @@ def cpu_steps(steps, warmup, batch_size, budget_s=None):
 
 
 def run_reference(args, rank):
+    """The reference arm: rank 0 alone, on ALL the host threads of the box (the other ranks exit without work). At
+    N > 1 its line still describes the whole host: N GPUs are compared with the box's CPUs, not with one thread
+    (torchrun's OMP_NUM_THREADS=1 is overridden in cpu_steps)."""
     if rank != 0:
         return
-    value, ms, done, cells = cpu_steps(args.steps, args.warmup, args.batch)
+    value, ms, done, cells = cpu_steps(args.steps, args.warmup, args.batch, args=args)
     cores = torch.get_num_threads()
+    wl = workload(args)[2]
     line = {
         'impl': 'reference', 'metric': 'cells/sec fwd+bwd ZINC ring-lifted CWN', 'value': value, 'unit': 'cells/s',
         'n_gpus': args.gpus, 'steps': done, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'cells_per_step': cells, 'step': 'fwd+loss+bwd+adam'},
+        'config': {'workload': wl, 'cells_per_step': cells, 'step': 'fwd+loss+bwd+adam',
+                   'host': f'rank 0 only, {cores} host threads (the whole box), whatever --gpus says'},
         'cpu_baseline': {'value': value, 'unit': 'cells/s', 'cores': cores, 'kind': 'port',
                          'sample': f'{done} full steps of the same workload (batch {args.batch}) through the '
                                    f'torch-only oracle; the reference cannot be imported (torch_scatter, '
@@ -280,7 +324,7 @@ def kernel_sweep(dev):
     return out
 
 
-def kernel_sweep_full(dev):
+def kernel_sweep_full(dev, rank=0, world=1):
     """BASELINE config 5: N in {1e4,1e5,1e6} cells/dim x F in {16,64,256} x the four adjacency types, block-diagonal
     ZINC-like layout (+ one uniform-random stress point per F); forward, transposed (backward) and coboundary passes.
     One JSON object per point on stdout."""
@@ -343,7 +387,7 @@ def kernel_sweep_full(dev):
                 rows.append(('cob_bwd (avg of dP, dQ)', t, b))
             for name, t, b in rows:
                 gbs = b / (t * 1e-3) / 1e9
-                print(json.dumps({'pass': name, 'adjacency': kind, 'layout': layout, 'cells': n_dst,
+                print(json.dumps({'rank': rank, 'n_gpus': world, 'pass': name, 'adjacency': kind, 'layout': layout, 'cells': n_dst,
                                   'messages': index.size(1), 'F': F, 'us': round(1e3 * t, 2),
                                   'algorithmic_MB': round(b / 1e6, 3), 'GBps': round(gbs, 1),
                                   'frac_of_measured_peak': round(gbs / peak, 4)}), flush=True)
@@ -355,7 +399,8 @@ def run_cwn(args, rank, world, local_rank):
     from cwn_b200 import _lib, ops
     from cwn_b200.dist import FlatGradBucket, broadcast_parameters
     from cwn_b200.optim import FlatAdam
-    from cwn_b200.mp.molec_models import EmbedSparseCIN
+    from cwn_b200.mp import molec_models
+    model_name, model_cfg, workload_name, gen, loss_fn = workload(args)
 
     if not torch.cuda.is_available():
         raise RuntimeError('bench.py: no CUDA device; the cwn_b200 path is CUDA-only (use --impl reference for the CPU arm)')
@@ -365,18 +410,18 @@ def run_cwn(args, rank, world, local_rank):
     if args.sweep_only:
         print(json.dumps({'kernel_sweep': kernel_sweep(dev)}), flush=True)
         return
-    if args.sweep_full:
-        kernel_sweep_full(dev)
+    if args.sweep_full:  # independent shards: every rank sweeps its own GPU, lines carry the rank (weak scaling)
+        kernel_sweep_full(dev, rank, world)
         return
     torch.manual_seed(0)
-    model = EmbedSparseCIN(**MODEL_CFG).to(dev).train()
+    model = getattr(molec_models, model_name)(**model_cfg).to(dev).train()
     broadcast_parameters(model)
     bucket = FlatGradBucket(model)
     opt = FlatAdam(model, bucket, lr=1e-3)  # one launch; also clears the gradient bucket for the next step
 
-    host_batches = [b.pack_(pin_memory=True) for b in make_batches(args.pool, args.batch, seed0=1000 + 100 * rank)]
+    host_batches = [b.pack_(pin_memory=True) for b in make_batches(args.pool, args.batch, seed0=1000 + 100 * rank, **gen)]
     cells = cells_of(host_batches[0])
-    dev_batches = [b.to(dev) for b in make_batches(args.pool, args.batch, seed0=1000 + 100 * rank)]
+    dev_batches = [b.to(dev) for b in make_batches(args.pool, args.batch, seed0=1000 + 100 * rank, **gen)]
     index_tensors = [[t for d in range(3) for t in (b.cochains[d].upper_index, b.cochains[d].boundary_index,
                                                     b.cochains[d].batch)] for b in dev_batches]
     inputs = [[b.cochains[d].x for d in range(3)] for b in dev_batches]
@@ -384,7 +429,7 @@ def run_cwn(args, rank, world, local_rank):
 
     def step(batch):
         out = model(batch)
-        loss = l1(out, batch.y)
+        loss = loss_fn(out, batch.y)
         loss.backward()
         bucket.all_reduce()
         opt.step()
@@ -402,8 +447,8 @@ def run_cwn(args, rank, world, local_rank):
     if args.mode in ('auto', 'graph'):
         from cwn_b200.graph import CapturedStep
         try:
-            captured = CapturedStep(model, l1, bucket, opt, optimizer_in_graph=(world == 1))
-            static = make_batches(1, args.batch, seed0=999)[0].to(dev)
+            captured = CapturedStep(model, loss_fn, bucket, opt, optimizer_in_graph=(world == 1))
+            static = make_batches(1, args.batch, seed0=999, **gen)[0].to(dev)
             captured.capture(static)
             l0 = _lib.launch_count()
             captured._body()  # one eager pass of the captured body: counts the cwn kernels one replay launches
@@ -495,7 +540,7 @@ def run_cwn(args, rank, world, local_rank):
         from cwn_b200.data import synthetic
         from cwn_b200.data.packed import PackedComplexDataset
         n_ds = 8 * args.batch
-        ds = PackedComplexDataset(synthetic.zinc_like_complexes(n_ds, seed=5000 + rank), max_dim=2, device=dev)
+        ds = PackedComplexDataset(synthetic.zinc_like_complexes(n_ds, seed=5000 + rank, **gen), max_dim=2, device=dev)
         perm = torch.randperm(n_ds, generator=torch.Generator().manual_seed(rank)).tolist()
         pick = lambda i: perm[(i * args.batch) % n_ds:(i * args.batch) % n_ds + args.batch]  # noqa: E731
         for i in range(3):
@@ -520,6 +565,11 @@ def run_cwn(args, rank, world, local_rank):
                             'segment table', 'h2d_bytes_per_step': int(ds._table_bytes),
                     'd2h_bytes_per_step': 4}
 
+    # ---- ragged batches (every step a different set of molecules): padded to ONE layout, replayed through one graph
+    ragged = None
+    if not args.no_ragged and world == 1 and args.config == 'zinc':
+        ragged = ragged_leg(args, dev, model, bucket, opt, flush)
+
     # ---- per-kernel roofline of the step (instrumented eager re-run of the same steps; every rank takes part because
     #      the step contains the gradient all-reduce)
     with ops.KernelProfile(pad_cycles=120_000) as prof:  # ~60 us of spin before each launch: see KernelProfile
@@ -541,6 +591,7 @@ def run_cwn(args, rank, world, local_rank):
         traffic = json.load(open(tpath)).get(dom, {}).get('dram_bytes_per_launch')
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                'as_contraction': tensor_roofline(dom, rec),
                 'launches_per_step': rec['launches'] / n_prof,
                 'avg_launch_us': 1e3 * rec['ms'] / rec['launches'],
                 'algorithmic_bytes_per_launch': rec['bytes'] / rec['launches'],
@@ -556,7 +607,7 @@ def run_cwn(args, rank, world, local_rank):
         'metric': 'cells/sec fwd+bwd ZINC ring-lifted CWN', 'value': value, 'unit': 'cells/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'cells_per_step_per_gpu': cells, 'global_batch': args.batch * world,
+        'config': {'workload': workload_name, 'cells_per_step_per_gpu': cells, 'global_batch': args.batch * world,
                    'parallelism': f'dp{world}', 'step': 'plans+fwd+loss+bwd+allreduce+adam', 'mode': mode, 'clock_preload_steps': PRELOAD_STEPS,
                    'l2': 'flushed (256 MB write) between timed steps', 'last_loss': loss_value},
         'clocks': clock_info, 'gpu_launches': int(launches),
@@ -565,14 +616,103 @@ def run_cwn(args, rank, world, local_rank):
     }
     if collated is not None:
         line['e2e_gpu_collation'] = collated
+    if ragged is not None:
+        line['ragged'] = ragged
     if not args.no_sweep:
         line['kernel_sweep'] = kernel_sweep(dev)
     if not args.no_cpu_baseline:
-        v, ms, done, _ = cpu_steps(10, 2, args.batch, budget_s=20.0)
+        v, ms, done, _ = cpu_steps(10, 2, args.batch, budget_s=20.0, args=args)
         line['cpu_baseline'] = {'value': v, 'unit': 'cells/s', 'cores': torch.get_num_threads(), 'kind': 'port',
                                 'ms_per_step': ms,
                                 'sample': f'{done} full steps of the same workload through the torch-only oracle'}
     print(json.dumps(line), flush=True)
+
+
+def tensor_roofline(name, rec):
+    """The dense kernels are contractions, not streams: their algorithmic flops (2 n K h per product, fp32-equivalent;
+    the 3xTF32 split issues four TF32 products for each) against the TF32 tensor peak = half the MEASURED bf16 peak."""
+    flops = rec.get('flops', 0)
+    if not flops:
+        return None
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    bf16 = json.load(open(path))['bf16_tflops'] if os.path.exists(path) else 1590.0
+    achieved = flops / (rec['ms'] * 1e-3) / 1e12
+    return {'bound': 'tensor', 'kernel': name, 'achieved': achieved, 'unit': 'TFLOP/s (fp32-equivalent)', 'peak': bf16 / 2,
+            'peak_source': 'TF32 dense = MEASURED_PEAKS.json bf16_tflops / 2', 'frac': achieved / (bf16 / 2),
+            'tf32_products_per_fp32_product': 4,
+            'note': 'latency-bound at this size: ~100-200 CTAs of 64 x 64 x 64..128 tiles, one wave'}
+
+
+def ragged_leg(args, dev, model, bucket, opt, flush):
+    """Ragged batches through cwn_b200.bucketed.BucketedStep (one graph, padded layout) and, for comparison, through the
+    eager path on their own layouts. Runs after the uniform legs on the same model (weights keep training)."""
+    from cwn_b200.bucketed import BucketedStep, Capacity, masked_l1
+    from cwn_b200.data import synthetic
+    from cwn_b200.data.complex import ComplexBatch
+    n_pool = max(args.pool, 8)
+    pool = synthetic.zinc_like_complexes(n_pool * args.batch, seed=7000, **RAGGED_GEN)
+    lists = [pool[i * args.batch:(i + 1) * args.batch] for i in range(n_pool)]
+    cap = Capacity.from_dataset(pool, args.batch)
+    step = BucketedStep(model, masked_l1, bucket, opt, capacity=cap, optimizer_in_graph=True)
+    step.capture(lists[0])
+    host = [step.pad(lst) for lst in lists]                      # padded + packed + pinned
+    resident = [step.pad(lst, pin_memory=False).to(dev) for lst in lists]
+    real_cells = [sum(int(b.cochains[d].live_rows) for d in range(3)) for b in host]
+    layouts = len({tuple(int(b.cochains[d].live_rows) for d in range(3)) for b in host})
+    for i in range(5):
+        step.run(resident[i % n_pool])
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        step.run(resident[i % n_pool])
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    cells = sum(real_cells[i % n_pool] for i in range(args.steps)) / args.steps
+    # end to end: padded pinned host batch -> static buffers -> replay -> loss.item()
+    for i in range(3):
+        step.run(host[i % n_pool])
+    torch.cuda.synchronize()
+    e2e = 0.0
+    for i in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step.run(host[i % n_pool])
+        float(step.loss.item())
+        e2e += 1e3 * (time.perf_counter() - t0)
+    e2e /= args.steps
+    # the eager path on the same (unpadded) batches: what a ragged batch cost before
+    eager_batches = [ComplexBatch.from_complex_list(lst).to(dev) for lst in lists]
+    eager_inputs = [[b.cochains[d].x for d in range(3)] for b in eager_batches]
+
+    def eager(i):
+        b = eager_batches[i % n_pool]
+        for d, x in enumerate(eager_inputs[i % n_pool]):
+            b.cochains[d]._x = x
+        loss = l1(model(b), b.y)
+        loss.backward()
+        opt.step()
+    n_eager = min(args.steps, 10)
+    for i in range(2):
+        eager(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(n_eager):
+        eager(i)
+    torch.cuda.synchronize()
+    eager_ms = 1e3 * (time.perf_counter() - t0) / n_eager
+    return {'value': cells / (ms / 1e3), 'unit': 'cells/s', 'ms_per_step': ms, 'real_cells_per_step': cells,
+            'e2e': {'value': cells / (e2e / 1e3), 'unit': 'cells/s', 'h2d_bytes_per_step': int(host[0].packed_nbytes),
+                    'd2h_bytes_per_step': 4},
+            'distinct_layouts_in_pool': layouts, 'capacity': repr(cap), 'padded_cells_per_step': sum(cap.cells),
+            'eager_ms_per_step': eager_ms, 'eager_value': cells / (eager_ms / 1e3),
+            'what': f'{n_pool} ragged batches of {args.batch} molecules (ring count 1..4, 4..14 chain atoms: ZINC-like '
+                    'means) padded to one fixed-capacity layout and replayed through ONE CUDA graph; BatchNorm and '
+                    'the loss see the real cells only (cwn_b200/bucketed.py); cells/s counts real cells; the eager '
+                    'number is the same model on the same batches without padding or graph (host wall clock)'}
 
 
 def make_host_copy(batch):

@@ -31,7 +31,8 @@ class LinearDesc(ctypes.Structure):
                 ('ld_z', _I64), ('stats', _P), ('n_rows', _I64), ('h', _I32),
                 ('bn_gamma', _P), ('bn_eps', _F), ('bn_momentum', _F), ('bn_training', _I32),
                 ('bn_running_mean', _P), ('bn_running_var', _P), ('bn_num_batches_tracked', _P),
-                ('bn_mean', _P), ('bn_scale', _P), ('bn_rstd', _P), ('counter', _P), ('tile_rows', _I32)]
+                ('bn_mean', _P), ('bn_scale', _P), ('bn_rstd', _P), ('counter', _P), ('tile_rows', _I32),
+                ('n_rows_live', _P)]
 
 
 class HeadDim(ctypes.Structure):
@@ -64,7 +65,7 @@ class UnitBwdDesc(ctypes.Structure):
                 ('g_beta', _P), ('accumulate_affine', _I32), ('g_in0', _P), ('ld_gi0', _I64), ('g_in1', _P),
                 ('ld_gi1', _I64), ('w_partials', _P), ('b_partials', _P), ('n_ctas', _I32), ('g_w', _P),
                 ('ld_gw', _I64), ('g_b', _P), ('accumulate_w', _I32), ('n_rows', _I64), ('h', _I32),
-                ('counter', _P), ('tile_rows', _I32), ('accumulate_in', _I32)]
+                ('counter', _P), ('tile_rows', _I32), ('accumulate_in', _I32), ('n_rows_live', _P)]
 
 
 class CollateJob(ctypes.Structure):

@@ -63,6 +63,15 @@ struct Group {
   int n;
 };
 
+// rows of a problem that are real (the rest pads a fixed-capacity batch, see cwn_linear_desc::n_rows_live)
+template <class D>
+__device__ __forceinline__ int64_t live_rows(const D& d) {
+  if (!d.n_rows_live) return d.n_rows;
+  int64_t n = (int64_t)__ldg(d.n_rows_live);
+  n = n < 1 ? 1 : n;
+  return n < d.n_rows ? n : d.n_rows;
+}
+
 template <class D>
 __device__ __forceinline__ int find_problem(const Group<D>& g, int cta) {
   int p = 0;
@@ -1035,8 +1044,9 @@ __device__ __forceinline__ void unit_bwd_finalize_body(const cwn_unit_bwd_desc& 
   }
   if (threadIdx.x < d.h) {
     const int c = threadIdx.x;
-    d.c1[c] = s1 / (float)d.n_rows;
-    d.c2[c] = s2 / (float)d.n_rows;
+    const float n_live = (float)live_rows(d);  // (padding rows carry zero gradients: they add nothing to s1, s2)
+    d.c1[c] = s1 / n_live;
+    d.c2[c] = s2 / n_live;
     if (d.g_gamma) d.g_gamma[c] = d.accumulate_affine ? d.g_gamma[c] + s2 : s2;
     if (d.g_beta) d.g_beta[c] = d.accumulate_affine ? d.g_beta[c] + s1 : s1;
   }
@@ -1782,6 +1792,8 @@ extern "C" int cwn_linear_fwd_grouped(const cwn_linear_desc* descs, int32_t n, c
       return launched("linear_fwd_tc5_kernel");
     }
   }
+  for (int i = 0; i < n; ++i)
+    if (descs[i].n_rows_live) return fail(CWN_E_SHAPE, "cwn_linear_fwd_grouped: n_rows_live needs the tensor-core path (h, K powers of two <= 128, tile_rows 64)");
   bool fast = !(g_force_generic_dense & 1);
   size_t smem_fast = 0;
   for (int i = 0; i < n && fast; ++i) {
@@ -1991,6 +2003,8 @@ extern "C" int cwn_unit_bwd_grouped(const cwn_unit_bwd_desc* descs, int32_t n, c
       return launched("unit_bwd_tc5_kernel");
     }
   }
+  for (int i = 0; i < n; ++i)
+    if (g.d[i].n_rows_live) return fail(CWN_E_SHAPE, "cwn_unit_bwd_grouped: n_rows_live needs the tensor-core path (h = 64, K in {32, 64, 128}, tile_rows 64)");
   bool fast = !(g_force_generic_dense & 2);
   size_t smem_fast = 0;
   for (int i = 0; i < n && fast; ++i) {

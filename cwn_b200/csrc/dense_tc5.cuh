@@ -191,6 +191,8 @@ __global__ void __launch_bounds__(T5T, 2) linear_fwd_tc5_kernel(const __grid_con
   const int nb = L.nb;
   const int64_t row0 = (int64_t)rt * T5R;
   const int rows = (int)((d.n_rows - row0 < T5R) ? d.n_rows - row0 : T5R);
+  const int64_t n_live = live_rows(d);  // rows past it pad a fixed-capacity batch: computed, but outside the statistics
+  const int rows_live = (int)((n_live - row0 < rows) ? (n_live - row0 > 0 ? n_live - row0 : 0) : rows);
   const bool transform = d.in_scale0 || d.in_scale1 || d.in_act != CWN_ACT_ID;
   const tc5::Tiled ta(2 * T5R), tb(2 * h);
   {  // operands: global -> registers (transform, split) -> shared memory. Thread -> column chunk c4 (fixed) and rows
@@ -274,21 +276,21 @@ __global__ void __launch_bounds__(T5T, 2) linear_fwd_tc5_kernel(const __grid_con
     return;
   }
   __syncthreads();
-  {  // per-column (mean, M2) of this tile: 256 / h row groups per column, combined in a fixed order
+  if (rows_live > 0) {  // per-column (mean, M2) of this tile's live rows: 256 / h row groups per column, fixed order
     const int parts = T5T / h, c = tid % h, part = tid / h;
     float s = 0.f;
-    for (int r = part; r < rows; r += parts) s += T[r * ldy + c];
+    for (int r = part; r < rows_live; r += parts) s += T[r * ldy + c];
     red[tid] = s;
     __syncthreads();
     if (tid < h) {
       float tot = 0.f;
       for (int q = 0; q < parts; ++q) tot += red[q * h + tid];
-      meanv[tid] = tot / (float)rows;
+      meanv[tid] = tot / (float)rows_live;
     }
     __syncthreads();
     const float mu = meanv[c];
     float m2 = 0.f;
-    for (int r = part; r < rows; r += parts) {
+    for (int r = part; r < rows_live; r += parts) {
       const float dv = T[r * ldy + c] - mu;
       m2 = fmaf(dv, dv, m2);
     }
@@ -307,8 +309,8 @@ __global__ void __launch_bounds__(T5T, 2) linear_fwd_tc5_kernel(const __grid_con
     const bool last_ = last_cta_of_problem(d.counter, total);
     CWN_PHASE(7);
     if (last_) {
-      const int n_tiles = (int)((d.n_rows + T5R - 1) / T5R);
-      bn_finalize_body(d.stats, n_tiles, d.n_rows, d.h, d.bn_gamma, d.bn_eps, d.bn_momentum, 1, d.bn_running_mean,
+      const int n_tiles = (int)((n_live + T5R - 1) / T5R);  // (tiles without a live row wrote no record)
+      bn_finalize_body(d.stats, n_tiles, n_live, d.h, d.bn_gamma, d.bn_eps, d.bn_momentum, 1, d.bn_running_mean,
                        d.bn_running_var, d.bn_num_batches_tracked, d.bn_mean, d.bn_scale, d.bn_rstd,
                        reinterpret_cast<float*>(smem5), (int)(L.total / 4), T5R);
       if (threadIdx.x == 0) *d.counter = 0;
@@ -359,6 +361,7 @@ __global__ void __launch_bounds__(T5T, 1) unit_bwd_tc5_kernel(const __grid_const
   const T5BwdSmem L(K, h);
   const tc5::Tiled tg(2 * T5R);
   const int n_tiles = (int)((d.n_rows + T5R - 1) / T5R);
+  const int64_t n_live = live_rows(d);  // rows past it pad a fixed-capacity batch: their g_z is zero
   float* wpart = d.w_partials + (int64_t)j * h * K;
   float* bpart = d.b_partials + (int64_t)j * h;
   const bool transform = d.in_scale0 || d.in_scale1 || d.in_act != CWN_ACT_ID;
@@ -406,7 +409,8 @@ __global__ void __launch_bounds__(T5T, 1) unit_bwd_tc5_kernel(const __grid_const
   bool first = true;
   for (int tile = j; tile < n_tiles; tile += d.n_ctas, first = false, parity ^= 1u) {
     const int64_t row0 = (int64_t)tile * T5R;
-    const int rows = (int)((d.n_rows - row0 < T5R) ? d.n_rows - row0 : T5R);
+    const int rows_cap = (int)((d.n_rows - row0 < T5R) ? d.n_rows - row0 : T5R);
+    const int rows = (int)((n_live - row0 < rows_cap) ? (n_live - row0 > 0 ? n_live - row0 : 0) : rows_cap);
     if (first) CWN_PHASE(2);
     {  // g_z = scale * (g_out act'(y) - c1 - zhat c2)  (plain g_out act'(z) without BatchNorm): registers -> both layouts;
        // f_in(X) -> MN-major. Thread -> (column chunk q of z / g_out, rows rbg + j rsg) and (chunk c4x of X, rows rbx + j rsx);
@@ -512,7 +516,7 @@ __global__ void __launch_bounds__(T5T, 1) unit_bwd_tc5_kernel(const __grid_const
       for (int k0 = k_lo; k0 < k_hi; k0 += 16) t5_stage16(tmem + tl, K, L.nb1, k0, T + R * ldt);
       tc5::fence_before_sync();
       __syncthreads();
-      for (int i = tid; i < rows * K4; i += T5T) {
+      for (int i = tid; i < rows_cap * K4; i += T5T) {  // (padding rows leave as the zeros their g_z produced)
         const int rr = i >> lgk, kq = (i & (K4 - 1)) * 4;
         float* base = (kq < d.k0) ? (d.g_in0 ? d.g_in0 + (row0 + rr) * d.ld_gi0 + kq : nullptr)
                                   : (d.g_in1 ? d.g_in1 + (row0 + rr) * d.ld_gi1 + (kq - d.k0) : nullptr);

@@ -140,10 +140,12 @@ def make_complex(num_nodes, edges, rings, atom_x: torch.Tensor, bond_x: Optional
 
 def zinc_like_complexes(num: int, seed: int = 0, ring_sizes=(6, 6, 5), num_pendant: int = 6, atom_types: int = 28,
                         bond_types: int = 4, edge_features: bool = True, ragged: bool = False,
-                        include_down_adj: bool = False, ogb_features: bool = False) -> List[Complex]:
+                        include_down_adj: bool = False, ogb_features: bool = False, ring_count_range=(0, 4),
+                        pendant_range=(2, 12)) -> List[Complex]:
     """`num` seeded synthetic molecules. `ragged=True` varies ring count/sizes and chain length per molecule
-    (ring sizes 5..6 as with max_ring=6); `ogb_features=True` emits 9 integer atom columns / 3 bond columns in
-    the ogbg-mol* vocabularies instead of the scalar ZINC types."""
+    (ring sizes 5..6 as with max_ring=6; ring count in [ring_count_range), chain atoms in [pendant_range));
+    `ogb_features=True` emits 9 integer atom columns / 3 bond columns in the ogbg-mol* vocabularies instead of the
+    scalar ZINC types."""
     from cwn_b200.mp.encoders import ATOM_FEATURE_DIMS, BOND_FEATURE_DIMS
     rng = np.random.default_rng(seed)
     gen = torch.Generator().manual_seed(seed)
@@ -151,8 +153,8 @@ def zinc_like_complexes(num: int, seed: int = 0, ring_sizes=(6, 6, 5), num_penda
     for _ in range(num):
         sizes, pend = tuple(ring_sizes), num_pendant
         if ragged:
-            sizes = tuple(int(s) for s in rng.integers(5, 7, size=int(rng.integers(0, 4))))
-            pend = int(rng.integers(2, 12))
+            sizes = tuple(int(s) for s in rng.integers(5, 7, size=int(rng.integers(*ring_count_range))))
+            pend = int(rng.integers(*pendant_range))
         n, edges, rings = molecule_graph(sizes, pend, rng)
         n_e = len({(min(a, b), max(a, b)) for a, b in edges})
         if ogb_features:

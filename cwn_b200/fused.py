@@ -45,6 +45,40 @@ _FORCED_TILE_ROWS = int(os.environ.get('CWN_B200_TILE_ROWS', '0'))  # A/B switch
 _TC5 = os.environ.get('CWN_B200_DENSE_TC5', '1') != '0'  # tcgen05 dense kernels (default); 0 = FFMA kernels
 
 
+# Live row counts of a fixed-capacity (padded) batch: one int32 DEVICE scalar per cochain dimension, or None.
+# cwn_b200.bucketed installs them around the model call (`with live_rows(...)`); the fused dense node hands them to
+# the kernels so that BatchNorm statistics and its backward see the real cells only (cwn_linear_desc::n_rows_live).
+_LIVE = None
+
+
+class live_rows(object):
+    def __init__(self, per_dimension):
+        self.per_dimension = per_dimension
+
+    def __enter__(self):
+        global _LIVE
+        self._saved, _LIVE = _LIVE, self.per_dimension
+        return self
+
+    def __exit__(self, *exc):
+        global _LIVE
+        _LIVE = self._saved
+        return False
+
+
+def padded_batch_needs_fused_path(what):
+    """Called where a layer leaves the fused dense node: with live row counts installed (a padded batch) the torch
+    modules would put the padding rows into the BatchNorm statistics, silently."""
+    if _LIVE is not None:
+        raise RuntimeError(f'cwn_b200: padded batches (cwn_b200.bucketed) need the fused dense path; {what} is outside it')
+
+
+def _live(d):
+    if _LIVE is None or d >= len(_LIVE):
+        return None
+    return _LIVE[d]
+
+
 class _Unit(object):
     """Linear (+ optional BatchNorm) (+ activation) as the kernels see it."""
     __slots__ = ('lin', 'bn', 'act')
@@ -165,6 +199,15 @@ def _algorithmic_bytes(fn_name, d):
     return 0  # the two finalize kernels move a few KB
 
 
+def _algorithmic_flops(fn_name, d):
+    """fp32-equivalent flops of the contractions of one problem (2 n K h per product)."""
+    if fn_name == 'cwn_linear_fwd_grouped':
+        return 2 * d.n_rows * (d.k0 + d.k1) * d.h
+    if fn_name == 'cwn_unit_bwd_grouped':
+        return 2 * d.n_rows * (d.k0 + d.k1) * d.h * (2 if (d.g_in0 or d.g_in1) else 1)
+    return 0
+
+
 def _launch(fn_name, desc_type, descs):
     lib = _lib.load()
     fn = getattr(lib, fn_name)
@@ -173,7 +216,8 @@ def _launch(fn_name, desc_type, descs):
         chunk = descs[i:i + _lib.MAX_GROUP]
         arr = (desc_type * len(chunk))(*chunk)
         nbytes = sum(_algorithmic_bytes(fn_name, d) for d in chunk) if ops._profile is not None else 0
-        ops._call(fn_name[4:], nbytes, fn, arr, len(chunk), stream)
+        flops = sum(_algorithmic_flops(fn_name, d) for d in chunk) if ops._profile is not None else 0
+        ops._call(fn_name[4:], nbytes, fn, arr, len(chunk), stream, flops=flops)
 
 
 def _n_ctas(tile_counts):
@@ -188,7 +232,7 @@ def _n_ctas(tile_counts):
 
 class _UnitState(object):
     """Everything one unit keeps between forward and backward."""
-    __slots__ = ('unit', 'x0', 'x1', 'in0', 'in1', 'in_act', 'z', 'mean', 'scale', 'rstd', 'n', 'h')
+    __slots__ = ('unit', 'x0', 'x1', 'in0', 'in1', 'in_act', 'z', 'mean', 'scale', 'rstd', 'n', 'h', 'live')
 
 
 def _in_vectors(prev):
@@ -208,9 +252,10 @@ class FusedSparseCINDense(Function):
         with torch.cuda.device(dev):
             states = []  # per dim: dict name -> _UnitState
 
-            def new_state(unit, x0, x1, prev0, prev1):
+            def new_state(unit, x0, x1, prev0, prev1, d):
                 st = _UnitState()
                 st.unit, st.x0, st.x1 = unit, x0, x1
+                st.live = _live(d)
                 st.in0, st.in1 = _in_vectors(prev0), _in_vectors(prev1)
                 st.in_act = prev0.unit.act if prev0 is not None else 'id'
                 st.n, st.h = x0.size(0), unit.lin.out_features
@@ -243,28 +288,28 @@ class FusedSparseCINDense(Function):
                         _p(st.x0), st.x0.stride(0), st.x0.size(1), _p(st.x1), st.x1.stride(0) if st.x1 is not None else 0,
                         st.x1.size(1) if st.x1 is not None else 0, _p(i0[0]), _p(i0[1]), _p(i0[2]), _p(i1[0]), _p(i1[1]),
                         _p(i1[2]), ops.ACT_CODES[st.in_act], _p(unit.lin.weight), unit.lin.weight.stride(0),
-                        _p(unit.lin.bias), _p(st.z), st.h, _p(stats), st.n, st.h, *bn_fields, tr))
+                        _p(unit.lin.bias), _p(st.z), st.h, _p(stats), st.n, st.h, *bn_fields, tr, _p(st.live)))
                 _launch('cwn_linear_fwd_grouped', _lib.LinearDesc, lin)
 
             l1, l2, l3 = [], [], []
             for d in range(n_dims):
                 up, bnd, comb = forms[d]
                 s = {}
-                s['u1'] = new_state(up[0], us[d].contiguous(), None, None, None)
-                s['b1'] = new_state(bnd[0], bs[d].contiguous(), None, None, None)
+                s['u1'] = new_state(up[0], us[d].contiguous(), None, None, None, d)
+                s['b1'] = new_state(bnd[0], bs[d].contiguous(), None, None, None, d)
                 states.append(s)
                 l1 += [s['u1'], s['b1']]
             run_units(l1)
             for d in range(n_dims):
                 up, bnd, comb = forms[d]
                 s = states[d]
-                s['u2'] = new_state(up[1], s['u1'].z, None, s['u1'], None)
-                s['b2'] = new_state(bnd[1], s['b1'].z, None, s['b1'], None)
+                s['u2'] = new_state(up[1], s['u1'].z, None, s['u1'], None, d)
+                s['b2'] = new_state(bnd[1], s['b1'].z, None, s['b1'], None, d)
                 l2 += [s['u2'], s['b2']]
             run_units(l2)
             for d in range(n_dims):
                 s = states[d]
-                s['c'] = new_state(forms[d][2], s['u2'].z, s['b2'].z, s['u2'], s['b2'])
+                s['c'] = new_state(forms[d][2], s['u2'].z, s['b2'].z, s['u2'], s['b2'], d)
                 l3.append(s['c'])
             run_units(l3)
             outs, descs = [], []
@@ -333,7 +378,7 @@ class FusedSparseCINDense(Function):
                     _p(unit.bn.bias) if has_bn else None, _p(g), g.stride(0), _p(red), _p(c1), _p(c2), _p(gg),
                     _p(gbeta), acc_a, _p(gi0), k0, _p(gi1), k1, _p(new(max(n_ctas, 1) * st.h * (k0 + k1))),
                     _p(new(max(n_ctas, 1) * st.h)), n_ctas, _p(gw), gw.stride(0), _p(gb), acc_w, st.n, st.h,
-                    counters[i:i + 1].data_ptr() if has_bn else None, tr))
+                    counters[i:i + 1].data_ptr() if has_bn else None, tr, 0, _p(st.live)))
                 keep.append(g)
                 gins.append((gi0, gi1))
             return descs, gins

@@ -9,9 +9,11 @@ memory or from HBM) + one graph launch.
 
 A graph is specific to a packed layout (`Complex.packed_signature`: the cell and message counts of every
 dimension). Batches of identically shaped complexes (the synthetic benchmark) share one graph; `run()` refuses a
-batch with another layout (`load_packed_` raises), in which case the caller runs the eager path or captures
-another `CapturedStep` for that layout. Padding ragged batches to a few bucketed layouts is future work.
+batch with another layout (`load_packed_` raises). Real (ragged) batches are padded to one fixed-capacity layout by
+`cwn_b200.bucketed.BucketedStep`, which replays them through a single graph as well.
 """
+import copy
+
 import torch
 
 from cwn_b200 import ops
@@ -41,19 +43,64 @@ class CapturedStep(object):
         self.warmup = warmup
         self.graph = self.opt_graph = self.static = self.loss = None
 
+    def _optimizer_clears_grads(self):
+        """True only for an in-graph `FlatAdam(zero_grad=True)`, whose kernel zeroes the gradients it consumed. Every
+        other optimizer (torch.optim.*: `zero_grad` is a bound method there, always truthy), a FlatAdam that runs in its
+        own graph after the all-reduce, or no optimizer at all leaves the flat bucket as it is — autograd ACCUMULATES
+        into the `.grad` views, so the bucket must be cleared at the top of every replayed step."""
+        from cwn_b200.optim import FlatAdam
+        return isinstance(self.optimizer, FlatAdam) and bool(self.optimizer.zero_grad)
+
+    def _forward_loss(self, b):
+        return self.loss_fn(self.model(b), b.y)
+
     def _body(self):
         b = self.static
         for d, x in enumerate(self._inputs):  # the forward overwrites cochain.x with hidden features (set_xs)
             b.cochains[d]._x = x
         ops.clear_plan_cache(*self._indices)  # plans are part of the step: every step is a new batch
-        if not getattr(self.optimizer, 'zero_grad', False):
-            self.bucket.zero()  # (FlatAdam clears the gradients it consumed itself)
-        out = self.model(b)
-        loss = self.loss_fn(out, b.y)
+        if not self._optimizer_clears_grads():
+            self.bucket.zero()
+        loss = self._forward_loss(b)
         loss.backward()
         if self.optimizer_in_graph:
             self.optimizer.step()
         return loss
+
+    # ---- the warm-up passes run REAL steps (lazy initialisations must happen before capture): everything they touch is
+    #      put back afterwards, in place (the graph has captured the addresses), so that step 1 starts from the caller's state
+    def _snapshot(self):
+        snap = {'model': {k: v.detach().clone() for k, v in self.model.state_dict().items()}} \
+            if hasattr(self.model, 'state_dict') else {'model': {}}
+        opt = self.optimizer
+        if opt is None:
+            return snap
+        from cwn_b200.optim import FlatAdam
+        if isinstance(opt, FlatAdam):
+            snap['flat'] = [t.clone() for t in (opt.flat_param, opt.exp_avg, opt.exp_avg_sq, opt._step)]
+        elif hasattr(opt, 'state_dict'):
+            snap['opt'] = copy.deepcopy(opt.state_dict()['state'])
+        return snap
+
+    def _restore(self, snap):
+        with torch.no_grad():
+            opt = self.optimizer
+            if 'flat' in snap:
+                for t, saved in zip((opt.flat_param, opt.exp_avg, opt.exp_avg_sq, opt._step), snap['flat']):
+                    t.copy_(saved)
+            elif 'opt' in snap:
+                index = {}
+                for gi, group in enumerate(opt.param_groups):
+                    for p in group['params']:
+                        index[id(p)] = len(index)
+                for p, st in opt.state.items():
+                    before = snap['opt'].get(index.get(id(p)), {})
+                    for k, v in st.items():
+                        if torch.is_tensor(v):
+                            v.copy_(before[k]) if k in before and torch.is_tensor(before[k]) else v.zero_()
+            live = self.model.state_dict() if snap['model'] else {}
+            for k, saved in snap['model'].items():
+                live[k].copy_(saved)
 
     def capture(self, example):
         """`example`: a packed batch ON THE DEVICE; it becomes the graph's static input (do not reuse it)."""
@@ -62,6 +109,7 @@ class CapturedStep(object):
         self.static = example
         self._inputs = [example.cochains[d].x for d in range(example.dimension + 1)]
         self._indices = _index_tensors(example)
+        snap = self._snapshot()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # lazy initialisations (cuBLAS workspaces, optimizer state) before capture
@@ -77,6 +125,7 @@ class CapturedStep(object):
             self.opt_graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.opt_graph, capture_error_mode='thread_local'):
                 self.optimizer.step()
+        self._restore(snap)
         self.bucket.zero()  # gradients accumulated by the warm-up / capture passes must not leak into step 1
         return self
 

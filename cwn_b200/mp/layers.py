@@ -394,6 +394,7 @@ class SparseCINConv(_PerDimension):
                     us, bs = agg
                     if fused.applicable(forms[:n], us, bs, self.mp_levels[0].training):
                         return fused.sparse_cin_dense(forms[:n], us, bs, self.mp_levels[0].training)
+                    fused.padded_batch_needs_fused_path('this SparseCINConv configuration')
                     return [self.mp_levels[d].dense_tail(us[d], bs[d]) for d in range(n)]
             branches = [self.mp_levels[d]._fused_forward(cochain_params[d]) for d in range(n)]
             if all(f is not None for f in forms[:n]) and all(b is not NotImplemented for b in branches):
@@ -409,7 +410,9 @@ class SparseCINConv(_PerDimension):
                 us, bs = aggs[0::2], aggs[1::2]
                 if fused.applicable(forms[:n], us, bs, self.mp_levels[0].training):
                     return fused.sparse_cin_dense(forms[:n], us, bs, self.mp_levels[0].training)
+                fused.padded_batch_needs_fused_path('this SparseCINConv configuration')
                 return [self.mp_levels[d].dense_tail(us[d], bs[d]) for d in range(n)]
+            fused.padded_batch_needs_fused_path('this SparseCINConv configuration')
         return super(SparseCINConv, self).forward(*cochain_params, start_to_process=start_to_process)
 
     def __init__(self, up_msg_size: int, down_msg_size: int, boundary_msg_size: Optional[int],

@@ -63,7 +63,7 @@ class KernelProfile(object):
     while the GPU spins, and the pair brackets device time only."""
 
     def __init__(self, pad_cycles: int = 0):
-        self.records = []  # (kernel name, algorithmic bytes, start event, stop event)
+        self.records = []  # (kernel name, algorithmic bytes, start event, stop event, algorithmic flops)
         self.pad_cycles = int(pad_cycles)
 
     def __enter__(self):
@@ -93,18 +93,19 @@ class KernelProfile(object):
         torch.cuda.synchronize()
         self.overhead_ms = self.event_overhead_ms()
         out = {}
-        for name, nbytes, e0, e1 in self.records:
-            rec = out.setdefault(name, {'launches': 0, 'ms': 0.0, 'bytes': 0})
+        for name, nbytes, e0, e1, flops in self.records:
+            rec = out.setdefault(name, {'launches': 0, 'ms': 0.0, 'bytes': 0, 'flops': 0})
             rec['launches'] += 1
             rec['ms'] += max(e0.elapsed_time(e1) - self.overhead_ms, 0.0)
             rec['bytes'] += nbytes
+            rec['flops'] += flops
         return out
 
 
 _profile = None
 
 
-def _call(name, algo_bytes, fn, *args):
+def _call(name, algo_bytes, fn, *args, flops=0):
     """Invoke one C-ABI entry point, timing it when a KernelProfile is active."""
     if _profile is None:
         _lib.check(fn(*args), name)
@@ -115,7 +116,7 @@ def _call(name, algo_bytes, fn, *args):
     e0.record()
     _lib.check(fn(*args), name)
     e1.record()
-    _profile.records.append((name, algo_bytes, e0, e1))
+    _profile.records.append((name, algo_bytes, e0, e1, flops))
 
 
 # --------------------------------------------------------------------------------------------- CSR plans
@@ -315,6 +316,14 @@ def _launch_gather_reduce(x_src, plan_rowptr, idx, n_rows, F, x_res, eps, reduce
     dev = plan_rowptr.device
     E = idx.numel() if idx is not None else (x_src.size(0) if x_src is not None else 0)
     n_src = x_src.size(0) if x_src is not None else 0
+    if _profile is not None and idx is not None and x_src is not None:
+        # only the source rows some message reads are compulsory traffic (a ring-boundary pass touches the 17 of 25
+        # edges that lie on a ring; charging all rows made that pass read 1.4x the HBM peak). Counted once per plan,
+        # under profiling only (it synchronises).
+        cached = idx.__dict__.get('_cwn_touched')
+        if cached is None:
+            cached = idx.__dict__['_cwn_touched'] = int(torch.unique(idx).numel())
+        n_src = min(n_src, cached)
     algo = 16 * E + 4 * F * (n_src + n_rows + (n_rows if x_res is not None else 0))
     with torch.cuda.device(dev):
         out = torch.empty(n_rows, F, dtype=torch.float32, device=dev)

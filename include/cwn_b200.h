@@ -160,7 +160,10 @@ int cwn_csr_cob_bwd_f32(const float* G, int64_t ld_g, const float* A, int64_t ld
  * applied on the fly while the tile is loaded (so normalised activations are never written to HBM), and X may be the
  * virtual concatenation [X0 | X1] (combine_nn's torch.cat). All entry points are GROUPED: `descs` is a host array of
  * up to CWN_MAX_GROUP problems (the two branches of the three cochain dimensions) served by ONE launch.
- * fp32 FFMA throughout: TF32 tensor cores cannot meet the 1e-5 rtol parity gate at K = 64..128.
+ * Products: tcgen05 tensor cores (kind::tf32 on hi/lo split operands, accumulation spread over several TMEM
+ * accumulators — as accurate as an fp32 FMA chain, see csrc/dense_tc5.cuh) when h and K are powers of two <= 128 and
+ * the operands are 16-byte aligned; fp32 FFMA kernels otherwise (plain TF32 cannot meet the 1e-5 rtol parity gate).
+ * CWN_B200_DENSE_TC5=0 forces the FFMA kernels.
  */
 #define CWN_MAX_GROUP 8
 
@@ -184,6 +187,10 @@ typedef struct {
   int32_t* counter;
   int32_t tile_rows;   /* 64 or 32 (0 = 64): rows per CTA tile = granularity of `stats`; the same for a whole group.
                         * 32 doubles the CTA count of small problems (latency-bound launches) */
+  const int32_t* n_rows_live; /* nullable DEVICE scalar: only the first *n_rows_live (<= n_rows) rows are real, the rest is
+                        * padding of a fixed-capacity batch (ragged batches replayed through one CUDA graph,
+                        * cwn_b200/bucketed.py). All n_rows rows of z are still written, but the BatchNorm statistics
+                        * (and running statistics) see the live rows only. Tensor-core path only (CWN_E_SHAPE otherwise). */
 } cwn_linear_desc;
 int cwn_linear_fwd_grouped(const cwn_linear_desc* descs, int32_t n, cwn_stream_t stream);
 
@@ -241,6 +248,10 @@ typedef struct {
                           * owned by one thread: deterministic). Lets a caller sum the gradient contributions of several
                           * consumers of one tensor without extra elementwise launches; problems of ONE launch must not
                           * share an output buffer */
+  const int32_t* n_rows_live; /* nullable DEVICE scalar, as in cwn_linear_desc: rows >= *n_rows_live are padding. Their g_z
+                          * is zero (so they add nothing to g_W / g_b and their g_in rows are written as zeros) and the
+                          * BatchNorm-backward means c1, c2 divide by the live count. cwn_unit_bwd_grouped: tensor-core
+                          * path only (CWN_E_SHAPE otherwise) */
 } cwn_unit_bwd_desc;
 int cwn_unit_bwd_reduce_grouped(const cwn_unit_bwd_desc* descs, int32_t n, cwn_stream_t stream);
 int cwn_unit_bwd_finalize_grouped(const cwn_unit_bwd_desc* descs, int32_t n, cwn_stream_t stream);

@@ -517,6 +517,169 @@ def test_captured_cuda_graph_step_equals_eager_step():
         cap.run(ComplexBatch.from_complex_list(synthetic.zinc_like_complexes(9, seed=3)).pack_())
 
 
+@pytest.mark.parametrize('nonlinearity', ['relu', 'elu'])
+def test_benchmarked_configuration_graph_replay_against_oracle(nonlinearity):
+    """The configuration bench.py times — batch 128, 4 layers, hidden 64, CUDA-graph replay, FlatGradBucket, FlatAdam —
+    against the CPU oracle on the same batches: the loss of every replayed step and (ELU: gradients are a Lipschitz
+    function of the forward there, see test_zinc_shaped_training_step_against_oracle) the flat gradient and the Adam
+    update against torch.optim.Adam on the oracle's leaves.
+
+    Adam divides by sqrt(v): where a gradient is pure rounding noise (a bias in front of BatchNorm: analytically 0) its
+    first updates are +-lr whatever the noise says, so (a) the update is compared where |g| is not noise, and (b) the
+    model is re-synchronised with the oracle's weights and moments after every step — each replayed step is checked
+    from identical state."""
+    import bench
+    from cwn_b200.dist import FlatGradBucket
+    from cwn_b200.graph import CapturedStep
+    from cwn_b200.optim import FlatAdam
+    cfg = dict(bench.MODEL_CFG, nonlinearity=nonlinearity)
+    torch.manual_seed(0)
+    model = EmbedSparseCIN(**cfg)
+    sd = oracle_state(model.state_dict(), requires_grad=True)
+    names = [k for k, _ in model.named_parameters()]
+    leaves = [sd[k] for k in names]
+    o_opt = torch.optim.Adam(leaves, lr=1e-3)
+    model.to(DEV).train()
+    bucket = FlatGradBucket(model)
+    opt = FlatAdam(model, bucket, lr=1e-3, zero_grad=False)
+    cap = CapturedStep(model, bench.l1, bucket, opt).capture(bench.make_batches(1, 128, seed0=999)[0].to(DEV))
+    flat = lambda ts: torch.cat([t.detach().reshape(-1) for t in ts])  # noqa: E731
+    for i in range(3):
+        snap = O.Snapshot(bench.make_batches(1, 128, seed0=1000 + i)[0])
+        o_opt.zero_grad(set_to_none=True)
+        ref = bench.l1(O.embed_sparse_cin(sd, cfg, snap, training=True), snap.y)
+        ref.backward()
+        loss = cap.run(bench.make_batches(1, 128, seed0=1000 + i)[0].pack_(pin_memory=True))
+        assert_close(loss, ref, rtol=1e-5, atol=1e-6, what=f'loss of replayed step {i}')
+        g_ref = flat([p.grad if p.grad is not None else torch.zeros_like(p) for p in leaves])
+        o_opt.step()
+        if nonlinearity == 'elu':
+            assert_close(bucket.flat, g_ref, rtol=1e-4, atol=1e-5, what=f'flat gradient of replayed step {i}')
+            solid = g_ref.abs() > 1e-3 * g_ref.abs().max()
+            assert int(solid.sum()) > 1000
+            assert_close(opt.flat_param.cpu()[solid], flat(leaves)[solid], rtol=1e-4, atol=5e-6, what=f'Adam update {i}')
+        with torch.no_grad():  # identical state for the next step
+            opt.flat_param.copy_(flat(leaves))
+            opt.exp_avg.copy_(flat([o_opt.state[p]['exp_avg'] if p in o_opt.state else torch.zeros_like(p) for p in leaves]))
+            opt.exp_avg_sq.copy_(flat([o_opt.state[p]['exp_avg_sq'] if p in o_opt.state else torch.zeros_like(p) for p in leaves]))
+            for k, v in model.state_dict().items():  # BatchNorm running statistics follow the oracle's as well
+                if 'running' in k or 'num_batches' in k:
+                    v.copy_(sd[k])
+
+
+def test_captured_step_with_a_torch_optimizer_clears_gradients_and_keeps_the_initial_state():
+    """CapturedStep with torch.optim.Adam(capturable=True): `zero_grad` is a bound method there (always truthy), so the
+    flat bucket must be cleared at the top of every replayed step (gradients would otherwise pile up step after step),
+    and the warm-up passes of `capture()` must leave parameters, BatchNorm buffers and optimizer state untouched.
+    Three replayed steps == three eager steps with the same optimizer."""
+    from cwn_b200.dist import FlatGradBucket
+    from cwn_b200.graph import CapturedStep
+    cfg = dict(atom_types=28, bond_types=4, out_size=1, num_layers=2, hidden=32, dropout_rate=0.0, max_dim=2,
+               embed_edge=True, use_coboundaries=True, nonlinearity='elu')
+    torch.manual_seed(0)
+    m_graph, m_eager = EmbedSparseCIN(**cfg).to(DEV).train(), EmbedSparseCIN(**cfg).to(DEV).train()
+    m_eager.load_state_dict(m_graph.state_dict())
+    loss_fn = lambda out, y: torch.nn.functional.l1_loss(out, y.view(-1, 1))  # noqa: E731
+    b_graph, b_eager = FlatGradBucket(m_graph), FlatGradBucket(m_eager)
+    o_graph = torch.optim.Adam(m_graph.parameters(), lr=1e-2, capturable=True)
+    o_eager = torch.optim.Adam(m_eager.parameters(), lr=1e-2, capturable=True)
+    mk = lambda seed: ComplexBatch.from_complex_list(synthetic.zinc_like_complexes(8, seed=seed))  # noqa: E731
+    before = {k: v.clone() for k, v in m_graph.state_dict().items()}
+    cap = CapturedStep(m_graph, loss_fn, b_graph, optimizer=o_graph).capture(mk(0).to(DEV))
+    for k, v in m_graph.state_dict().items():
+        assert torch.equal(v, before[k]), f'capture() changed {k}'
+    assert all(float(st['step']) == 0 and float(st['exp_avg'].abs().sum()) == 0 for st in o_graph.state.values())
+    for seed in (1, 2, 3):
+        loss = cap.run(mk(seed).pack_(pin_memory=True))
+        b_eager.zero()
+        eb = mk(seed).to(DEV)
+        ref = loss_fn(m_eager(eb), eb.y)
+        ref.backward()
+        o_eager.step()
+        assert_close(loss, ref, rtol=1e-5, atol=1e-6, what=f'loss of step {seed}')
+    for (k, p), q in zip(m_graph.named_parameters(), m_eager.parameters()):
+        assert_close(p, q, rtol=1e-4, atol=1e-5, what=f'{k} after three steps')
+
+
+@pytest.mark.parametrize('nonlinearity', ['relu', 'elu'])
+def test_padded_batch_equals_unpadded_batch(nonlinearity):
+    """cwn_b200.bucketed: a ragged batch completed with dummy complexes to a fixed-capacity layout gives, on the real
+    complexes, the outputs / loss / parameter gradients / BatchNorm running statistics of the unpadded batch, and the
+    CPU oracle's (which never sees padding). The comparison padded vs unpadded shares kernels and tile boundaries, so
+    ReLU is safe there; against the oracle the gradients are compared for ELU only (see the ZINC-shaped test)."""
+    from cwn_b200.bucketed import Capacity, PaddedModel, masked_l1, pad_complexes
+    cfg = dict(atom_types=28, bond_types=4, out_size=1, num_layers=3, hidden=64, dropout_rate=0.0, max_dim=2,
+               embed_edge=True, use_coboundaries=True, nonlinearity=nonlinearity)
+    pool = synthetic.zinc_like_complexes(96, seed=4, ragged=True)
+    cap = Capacity.from_dataset(pool, 24)
+    comps = pool[10:34]
+    torch.manual_seed(1)
+    m_pad, m_ref = EmbedSparseCIN(**cfg), EmbedSparseCIN(**cfg)
+    m_ref.load_state_dict(m_pad.state_dict())
+    sd = oracle_state(m_pad.state_dict(), requires_grad=True)
+    snap = O.Snapshot(ComplexBatch.from_complex_list(comps))
+    o_out = O.embed_sparse_cin(sd, cfg, snap, training=True)
+    o_loss = torch.nn.functional.l1_loss(o_out, snap.y.view(-1, 1))
+    o_loss.backward()
+    m_pad.to(DEV).train(), m_ref.to(DEV).train()
+    ub = ComplexBatch.from_complex_list(comps).to(DEV)
+    u_out = m_ref(ub)
+    u_loss = torch.nn.functional.l1_loss(u_out, ub.y.view(-1, 1))
+    u_loss.backward()
+    pb = pad_complexes(comps, cap).to(DEV)
+    assert pb.num_complexes == 25 and [pb.cochains[d].num_cells for d in range(3)] == cap.cells
+    p_out = PaddedModel(m_pad)(pb)
+    p_loss = masked_l1(p_out, pb.y, pb.cochains[0].complex_weight)
+    p_loss.backward()
+    assert_close(p_out[:24], u_out, rtol=1e-5, atol=1e-5, what='padded vs unpadded: out')
+    assert_close(p_loss, u_loss, rtol=1e-5, atol=1e-6, what='padded vs unpadded: loss')
+    assert_close(p_out[:24], o_out, rtol=1e-5, atol=1e-5, what='padded vs oracle: out')
+    assert_close(p_loss, o_loss, rtol=1e-5, atol=1e-6, what='padded vs oracle: loss')
+    G = max(float(q.grad.abs().max()) for q in m_ref.parameters() if q.grad is not None)
+    for (k, p), q in zip(m_pad.named_parameters(), m_ref.parameters()):
+        if q.grad is None:
+            assert p.grad is None or float(p.grad.abs().sum()) == 0.0, k
+            continue
+        assert_close(p.grad, q.grad, rtol=1e-4, atol=1e-5 + 2e-6 * G, what=f'padded vs unpadded: grad {k}')
+        if nonlinearity != 'relu' and sd[k].grad is not None:
+            assert_close(p.grad, sd[k].grad, rtol=1e-4, atol=1e-5, what=f'padded vs oracle: grad {k}')
+    for (k, b), c in zip(m_pad.named_buffers(), m_ref.buffers()):
+        assert_close(b.float(), c.float(), rtol=1e-5, atol=1e-6, what=f'padded vs unpadded: buffer {k}')
+
+
+def test_ragged_batches_replay_through_one_cuda_graph():
+    """cwn_b200.bucketed.BucketedStep: DIFFERENT ragged batches (different cell and message counts, a short last batch)
+    replayed through ONE captured graph give the loss and flat gradient of the eager step on the unpadded batch; a batch
+    beyond the capacities falls back to the eager path."""
+    from cwn_b200.bucketed import BucketedStep, Capacity, masked_l1
+    from cwn_b200.dist import FlatGradBucket
+    cfg = dict(atom_types=28, bond_types=4, out_size=1, num_layers=2, hidden=64, dropout_rate=0.0, max_dim=2,
+               embed_edge=True, use_coboundaries=True, nonlinearity='elu')
+    pool = synthetic.zinc_like_complexes(160, seed=7, ragged=True)
+    cap = Capacity.from_dataset(pool, 32)
+    torch.manual_seed(0)
+    m_graph, m_eager = EmbedSparseCIN(**cfg).to(DEV).train(), EmbedSparseCIN(**cfg).to(DEV).train()
+    m_eager.load_state_dict(m_graph.state_dict())
+    b_graph, b_eager = FlatGradBucket(m_graph), FlatGradBucket(m_eager)
+    step = BucketedStep(m_graph, masked_l1, b_graph, optimizer=None, capacity=cap).capture(pool[:32])
+    layouts = set()
+    for lo, hi in [(32, 64), (64, 96), (96, 128), (128, 139)]:
+        comps = pool[lo:hi]
+        eb = ComplexBatch.from_complex_list(comps)
+        layouts.add(tuple(eb.cochains[d].num_cells for d in range(3)))
+        loss = step.step(comps)
+        b_eager.zero()
+        eb = eb.to(DEV)
+        ref = torch.nn.functional.l1_loss(m_eager(eb), eb.y.view(-1, 1))
+        ref.backward()
+        assert_close(loss, ref, rtol=1e-5, atol=1e-6, what=f'loss of batch {lo}:{hi}')
+        G = float(b_eager.flat.abs().max())
+        assert_close(b_graph.flat, b_eager.flat, rtol=1e-4, atol=1e-5 + 2e-6 * G, what=f'flat gradient of batch {lo}:{hi}')
+    assert len(layouts) == 4 and step.fallbacks == 0
+    step.step(pool[:32] + pool[:8])  # 40 complexes > 32 slots
+    assert step.fallbacks == 1
+
+
 @pytest.mark.parametrize('layer_dim,hidden,act,norm,cob', [(64, 64, 'relu', 'bn', True), (8, 20, 'elu', 'bn', False),
                                                            (16, 16, 'tanh', 'id', True), (32, 128, 'relu', 'bn', True),
                                                            (5, 5, 'sigmoid', 'bn', False), (12, 70, 'id', 'bn', True)])

@@ -122,3 +122,37 @@ def test_baseline_config0_sparse_cin_conv_on_the_house_complex(use_cob, monkeypa
     assert [tuple(o.shape) for o in outs] == [(5, 4), (6, 4), (1, 4)]
     for d, (o, r) in enumerate(zip(outs, ref)):
         assert_close(o, r, rtol=1e-6, atol=1e-6, what=f'house dim {d}')
+
+
+def test_padded_batches_share_one_layout():
+    """cwn_b200.bucketed.pad_complexes: ragged batches (and a short last batch) completed with dummy complexes all have
+    ONE packed layout; the real cells keep the leading rows, the dummies are disconnected from them, and the live-row
+    scalars / complex weights describe the real part."""
+    from cwn_b200.bucketed import Capacity, Overflow, pad_complexes
+    from cwn_b200.data import synthetic
+    from cwn_b200.data.complex import ComplexBatch
+    pool = synthetic.zinc_like_complexes(300, seed=3, ragged=True)
+    cap = Capacity.from_dataset(pool, 64)
+    sigs = set()
+    for lo, hi in [(0, 64), (64, 128), (128, 192), (192, 200), (7, 8)]:
+        comps = pool[lo:hi]
+        ref = ComplexBatch.from_complex_list(comps)
+        pb = pad_complexes(comps, cap)
+        sigs.add(pb.pack_().packed_signature)
+        assert pb.num_complexes == 65 and float(pb.cochains[0].complex_weight.sum()) == len(comps)
+        for d in range(3):
+            n = ref.cochains[d].num_cells if d <= ref.dimension else 0
+            c = pb.cochains[d]
+            assert int(c.live_rows) == n and c.num_cells == cap.cells[d]
+            if n and ref.cochains[d].x is not None:
+                assert torch.equal(c.x[:n], ref.cochains[d].x)
+            assert int((c.batch[:n] >= len(comps)).sum()) == 0 and int((c.batch[n:] < len(comps)).sum()) == 0
+            for key, src_n in (('upper_index', n), ('boundary_index', ref.cochains[d - 1].num_cells if d else 0)):
+                idx = getattr(c, key)
+                if idx is None:
+                    continue
+                real_dst, real_src = idx[1] < n, idx[0] < src_n
+                assert torch.equal(real_dst, real_src), 'a message crosses between real and padding cells'
+    assert len(sigs) == 1
+    with pytest.raises(Overflow):
+        pad_complexes(pool[:65], cap)
