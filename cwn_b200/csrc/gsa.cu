@@ -594,9 +594,15 @@ static TiledLaunch tiled_launch(K kernel, int64_t n_rows, int lpr, int F, int n_
 //   coboundary fwd F = 64:   rows 0.52 | pipelined (U=2) 0.50 | tile-staged 0.35-0.44
 //   coboundary bwd F = 64:   pipelined (U=2) 0.66 | rows 0.61 | tile-staged 0.35-0.38
 // A/B switches for profiling: CWN_B200_LARGE_GATHER, CWN_B200_LARGE_COB = r | p | t.
-static char large_mode(const char* env, char dflt) {
+static char large_mode_env(const char* env) {
   const char* v = getenv(env);
-  return (v && (v[0] == 't' || v[0] == 'p' || v[0] == 'r')) ? v[0] : dflt;
+  return (v && (v[0] == 't' || v[0] == 'p' || v[0] == 'r')) ? v[0] : 0;
+}
+// (the environment is read ONCE per switch: these sit on the launch path of every adjacency pass)
+static char large_mode(const char* env, char dflt) {
+  static const char gather = large_mode_env("CWN_B200_LARGE_GATHER"), cob = large_mode_env("CWN_B200_LARGE_COB");
+  const char v = env[15] == 'G' ? gather : cob;  // "CWN_B200_LARGE_G..." / "CWN_B200_LARGE_C..."
+  return v ? v : dflt;
 }
 
 template <class Pass>
@@ -655,9 +661,10 @@ extern "C" int cwn_csr_gather_reduce_f32(const float* x_src, int64_t ld_src, con
   // with chunks (the HBM-bound regime); small batches keep one row per group for latency.
   const int64_t chunks = (n_rows + g.lpr - 1) / g.lpr;
   const int grid_c = grid_for(chunks, g.lpr);
-  const bool chunked = g.vpl == 1 && g.lpr >= 4 && n_rows >= 32768 && !getenv_flag("CWN_B200_GATHER_V1");
+  static const bool gather_v1 = getenv_flag("CWN_B200_GATHER_V1"), no_tiled_gather = getenv_flag("CWN_B200_NO_TILED_GATHER");
+  const bool chunked = g.vpl == 1 && g.lpr >= 4 && n_rows >= 32768 && !gather_v1;
   const bool tiled = g.vec && g.lpr >= 4 && idx && n_rows >= kTiledMinRows && aligned16(rowptr) && aligned16(idx) &&
-                     g.fv <= g.lpr * g.vpl && tiled_enabled() && !getenv_flag("CWN_B200_NO_TILED_GATHER");
+                     g.fv <= g.lpr * g.vpl && tiled_enabled() && !no_tiled_gather;
 #define LAUNCH_TILED(VPLV, RED)                                                                                   \
   {                                                                                                               \
     auto kern = csr_gather_reduce_tiled_kernel<float4, LPR, VPLV, RED>;                                           \

@@ -74,7 +74,14 @@ class PackedComplexDataset(object):
     # -------------------------------------------------------------------------------------------------- collate
     def collate(self, ids, out: ComplexBatch = None) -> ComplexBatch:
         """Batch of the complexes `ids` (host sequence of ints), built on the GPU. `out`: an existing packed batch of
-        the SAME layout to write into (e.g. the static batch of a captured CUDA graph) instead of allocating."""
+        the SAME layout to write into (e.g. the static batch of a captured CUDA graph) instead of allocating.
+        = `launch(prepare(ids), out)`; the two halves are separate so that a worker thread can prepare the next batch
+        (`cwn_b200.data.data_loading.prefetched`)."""
+        return self.launch(self.prepare(ids), out=out)
+
+    def prepare(self, ids):
+        """Host half of a collation: segment sizes, prefix sums, the batch layout and the segment table (numpy only, no
+        CUDA call — safe on a worker thread)."""
         ids = np.asarray(ids, dtype=np.int64)
         B = len(ids)
         dimension = int(min(self.dim_of[ids].max(), self.max_dim))
@@ -147,15 +154,7 @@ class PackedComplexDataset(object):
             layout.append((d, key, dtype, off, tuple(shape)))
             totals[dtype] = off + (numel + align - 1) // align * align
         layout = tuple(layout)
-        if out is not None:
-            if out.packed_signature != layout:
-                raise ValueError('collate(out=...): the batch layout differs from the destination (different cell / '
-                                 'message counts); collate without `out` and re-capture, or run eagerly')
-            flat = out._flat
-        else:
-            flat = {dt: torch.zeros(max(n, 1), dtype=dt, device=self.device) for dt, n in totals.items()}
-
-        # ---- one host table with every segment array, one H2D copy, one kernel
+        # ---- one host table with every segment array; destinations as (dtype, byte offset into that flat buffer)
         table, jobs_spec = [], []
 
         def put(arr):
@@ -163,43 +162,56 @@ class PackedComplexDataset(object):
             table.append(np.asarray(arr, dtype=np.int64))
             return start
 
-        views = {}
         for (d, key, dtype, off, shape), (_, _, _, _, spec) in zip(layout, slots):
-            numel = int(np.prod(shape))
-            view = flat[dtype][off:off + numel].view(shape)
-            views[(d, key)] = view
+            esz = torch.empty((), dtype=dtype).element_size()
+            dst_at = (dtype, off * esz)
             kind = spec[0]
             if kind == 'rows':
                 _, src_t, src, dst, _ = spec
                 width = src_t.size(1) if src_t.dim() == 2 else 1
-                jobs_spec.append((src_t.data_ptr(), view.data_ptr(), put(src), put(dst), None, B, 1, width, int(dst[-1])))
+                jobs_spec.append((src_t.data_ptr(), dst_at, 0, put(src), put(dst), None, B, 1, width, int(dst[-1])))
             elif kind == 'index1':  # 1-D int64 segments without offsets (integer labels)
                 _, src_t, src, dst, _ = spec
-                jobs_spec.append((src_t.data_ptr(), view.data_ptr(), put(src), put(dst), None, B, 0, 1, int(dst[-1])))
+                jobs_spec.append((src_t.data_ptr(), dst_at, 0, put(src), put(dst), None, B, 0, 1, int(dst[-1])))
             elif kind == 'index':
                 _, src_t, src, dst, adds = spec
                 s_off, d_off = put(src), put(dst)
                 total_src = src_t.size(-1)
                 for row, add in enumerate(adds):
-                    jobs_spec.append((src_t.data_ptr() + 8 * row * total_src, view.data_ptr() + 8 * row * int(dst[-1]),
+                    jobs_spec.append((src_t.data_ptr() + 8 * row * total_src, dst_at, 8 * row * int(dst[-1]),
                                       s_off, d_off, put(add), B, 0, 1, int(dst[-1])))
             elif kind == 'fill':
                 dst = spec[3]
-                jobs_spec.append((None, view.data_ptr(), None, put(dst), None, B, 2, 1, int(dst[-1])))
+                jobs_spec.append((None, dst_at, 0, None, put(dst), None, B, 2, 1, int(dst[-1])))
             else:  # 'table': host-known values (ptr) copied out of the uploaded table itself
                 ptr = spec[1]
                 pos = put(ptr)
-                jobs_spec.append(('table', view.data_ptr(), put([pos]), put([0, len(ptr)]), None, 1, 0, 1, len(ptr)))
-        flat_table = np.concatenate(table)
+                jobs_spec.append(('table', dst_at, 0, put([pos]), put([0, len(ptr)]), None, 1, 0, 1, len(ptr)))
+        return {'B': B, 'dimension': dimension, 'dims': dims, 'cell_cnt': cell_cnt, 'cell_off': cell_off,
+                'layout': layout, 'totals': totals, 'table': np.concatenate(table), 'jobs': jobs_spec}
+
+    def launch(self, prep, out: ComplexBatch = None) -> ComplexBatch:
+        """Device half: one H2D copy of the segment table + one kernel; assembles the `ComplexBatch` around the views."""
+        B, dimension, dims = prep['B'], prep['dimension'], prep['dims']
+        cell_cnt, cell_off, layout, totals = prep['cell_cnt'], prep['cell_off'], prep['layout'], prep['totals']
+        if out is not None:
+            if out.packed_signature != layout:
+                raise ValueError('collate(out=...): the batch layout differs from the destination (different cell / '
+                                 'message counts); collate without `out` and re-capture, or run eagerly')
+            flat = out._flat
+        else:
+            flat = {dt: torch.zeros(max(n, 1), dtype=dt, device=self.device) for dt, n in totals.items()}
+        flat_table = prep['table']
         host, dev_table = self._staging(len(flat_table))
         host[:len(flat_table)].copy_(torch.from_numpy(flat_table))
         dev_table.copy_(host, non_blocking=True)
         base = dev_table.data_ptr()
         jobs = []
-        for src, dst, s_off, d_off, a_off, nseg, kind, width, n_out in jobs_spec:
+        for src, (dtype, dst_bytes), extra, s_off, d_off, a_off, nseg, kind, width, n_out in prep['jobs']:
             if src == 'table':  # the source IS the table; src_start holds the position of the values inside it
                 src = base
-            jobs.append(_lib.CollateJob(src, dst, None if s_off is None else base + 8 * s_off, base + 8 * d_off,
+            jobs.append(_lib.CollateJob(src, flat[dtype].data_ptr() + dst_bytes + extra,
+                                        None if s_off is None else base + 8 * s_off, base + 8 * d_off,
                                         None if a_off is None else base + 8 * a_off, nseg, kind, width, n_out))
         lib = _lib.load()
         arr = (_lib.CollateJob * len(jobs))(*jobs)
@@ -213,6 +225,9 @@ class PackedComplexDataset(object):
             return out
 
         # ---- assemble the ComplexBatch object around the views
+        views = {}
+        for d, key, dtype, off, shape in layout:
+            views[(d, key)] = flat[dtype][off:off + int(np.prod(shape))].view(shape)
         cochains = []
         for d in dims:
             cb = CochainBatch(d)
