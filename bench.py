@@ -447,9 +447,22 @@ def run_cwn(args, rank, world, local_rank):
     if args.mode in ('auto', 'graph'):
         from cwn_b200.graph import CapturedStep
         try:
-            captured = CapturedStep(model, loss_fn, bucket, opt, optimizer_in_graph=(world == 1))
             static = make_batches(1, args.batch, seed0=999, **gen)[0].to(dev)
-            captured.capture(static)
+            dp_graph = world > 1 and os.environ.get('CWN_BENCH_DP_GRAPH', '1') != '0'
+            captured = None
+            if dp_graph:  # the all-reduce captured into the step graph (one launch per step)
+                try:
+                    captured = CapturedStep(model, loss_fn, bucket, opt, optimizer_in_graph=True, allreduce_in_graph=True)
+                    captured.capture(static)
+                except Exception as exc:  # noqa: BLE001
+                    print(f'bench.py: capturing the NCCL all-reduce failed ({type(exc).__name__}: {exc}); three-piece step',
+                          file=sys.stderr, flush=True)
+                    captured, dp_graph = None, False
+                    torch.cuda.synchronize()
+                    static = make_batches(1, args.batch, seed0=999, **gen)[0].to(dev)
+            if captured is None:
+                captured = CapturedStep(model, loss_fn, bucket, opt, optimizer_in_graph=(world == 1))
+                captured.capture(static)
             l0 = _lib.launch_count()
             captured._body()  # one eager pass of the captured body: counts the cwn kernels one replay launches
             launches_per_step = _lib.launch_count() - l0
@@ -543,28 +556,34 @@ def run_cwn(args, rank, world, local_rank):
         ds = PackedComplexDataset(synthetic.zinc_like_complexes(n_ds, seed=5000 + rank, **gen), max_dim=2, device=dev)
         perm = torch.randperm(n_ds, generator=torch.Generator().manual_seed(rank)).tolist()
         pick = lambda i: perm[(i * args.batch) % n_ds:(i * args.batch) % n_ds + args.batch]  # noqa: E731
-        from cwn_b200.data.data_loading import prefetched
         for i in range(3):
             ds.collate(pick(i), out=captured.static)
             captured.run()
         barrier()
-        # the host half of batch i + 1 (segment sizes, prefix sums, the table) is prepared on a worker thread while the
-        # GPU runs step i: the critical path per step is one small H2D copy + the collate kernel + the graph
-        c_ms, it = 0.0, prefetched(ds, [pick(i) for i in range(args.steps)], out=captured.static)
+        # Every step: table H2D + collate kernel + graph replay + that step's loss read back. The host half of the NEXT
+        # collation (numpy: segment sizes, prefix sums) runs while the GPU executes the current step — after the step
+        # has been launched, before its loss is read.
+        pinned = torch.empty(1, dtype=torch.float32).pin_memory()
+        done = torch.cuda.Event()
+        c_ms, prep = 0.0, ds.prepare(pick(0))
         for i in range(args.steps):
             flush.zero_()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            next(it)
+            ds.launch(prep, out=captured.static)
             captured.run()
-            float(captured.loss.item())
+            pinned.copy_(captured.loss.detach().reshape(1), non_blocking=True)
+            done.record()
+            prep = ds.prepare(pick(i + 1))
+            done.synchronize()
+            float(pinned[0])
             c_ms += 1e3 * (time.perf_counter() - t0)
         t = torch.tensor([c_ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         collated = {'value': cells * world / (float(t.item()) / args.steps / 1e3), 'unit': 'cells/s',
                     'what': 'dataset resident in HBM; per step: 128 ids -> GPU collation (one kernel, written into the '
-                            'graph\'s static buffers; the segment table of the NEXT batch is prepared on a worker thread) -> '
+                            'graph\'s static buffers; the segment table of the NEXT batch is prepared by the host while the GPU runs the step) -> '
                             'step -> loss.item(); the only host->device traffic is the segment table', 'h2d_bytes_per_step': int(ds._table_bytes),
                     'd2h_bytes_per_step': 4}
 
@@ -611,7 +630,9 @@ def run_cwn(args, rank, world, local_rank):
         'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': workload_name, 'cells_per_step_per_gpu': cells, 'global_batch': args.batch * world,
-                   'parallelism': f'dp{world}', 'step': 'plans+fwd+loss+bwd+allreduce+adam', 'mode': mode, 'clock_preload_steps': PRELOAD_STEPS,
+                   'parallelism': f'dp{world}', 'step': 'plans+fwd+loss+bwd+allreduce+adam', 'mode': mode,
+                   'allreduce': ('captured in the step graph' if (captured is not None and captured.allreduce_in_graph) else
+                                 'between two graphs' if world > 1 else 'none (1 GPU)'), 'clock_preload_steps': PRELOAD_STEPS,
                    'l2': 'flushed (256 MB write) between timed steps', 'last_loss': loss_value},
         'clocks': clock_info, 'gpu_launches': int(launches),
         'e2e': {'value': e2e_value, 'unit': 'cells/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 4},

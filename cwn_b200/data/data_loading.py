@@ -1,7 +1,6 @@
 """Data loading with the reference's interface (`data/data_loading.py:44-110, 113-218`): `Collater`, `DataLoader(dataset,
 batch_size, shuffle, follow_batch, max_dim)` and `load_dataset(name, ...)`, plus `DeviceDataLoader`, the GPU-side
-variant (dataset resident in HBM, batches collated by one kernel, the next batch's segment tables prepared on a worker
-thread while the current step runs).
+variant (dataset resident in HBM, batches collated by one kernel).
 
 Datasets. Download and lifting pipelines (ZINC / OGB / TU / SR files, graph-tool, gudhi) are out of scope and
 there is no network here; `load_dataset` knows
@@ -10,7 +9,6 @@ there is no network here; `load_dataset` knows
                              (`cwn_b200.data.synthetic`), ragged, split 80 / 10 / 10,
 and raises for every other name with the reason.
 """
-import threading
 from collections.abc import Mapping, Sequence
 
 import torch
@@ -63,8 +61,8 @@ class DataLoader(torch.utils.data.DataLoader):
 
 class DeviceDataLoader(object):
     """The same iteration protocol over a `PackedComplexDataset` (dataset resident in HBM): every batch is collated ON THE
-    GPU by one kernel. The host part of batch i + 1 (segment sizes, prefix sums, layout) is prepared by a worker thread
-    while the caller is busy with batch i, so the critical path per batch is one small H2D copy + one launch.
+    GPU by one kernel; per batch the host does ~0.2 ms of numpy (segment sizes, prefix sums), one small H2D copy and one
+    launch.
 
         loader = DeviceDataLoader(complex_list, batch_size=128, shuffle=True, max_dim=2, device='cuda')
         for batch in loader: ...          # device-resident, packed ComplexBatch
@@ -94,24 +92,18 @@ class DeviceDataLoader(object):
 
 
 def prefetched(packed, id_batches, out=None):
-    """Generator of collated batches; `packed.prepare(ids)` of the NEXT batch runs on a worker thread."""
+    """Generator of collated batches. The host half of batch i + 1 (`packed.prepare`: segment sizes, prefix sums, the
+    table — ~0.2 ms of numpy) is done right after the collate kernel of batch i has been QUEUED, i.e. while the GPU is
+    still copying batch i. (A worker thread was tried and measured slower: its numpy work holds the GIL in pieces and
+    delays the launching thread. To hide the host half behind the training step itself, call `prepare` for the next
+    batch between launching the step and reading its loss, as bench.py's e2e_gpu_collation loop does.)"""
     id_batches = list(id_batches)
-    if not id_batches:
-        return
-    slot = {}
-
-    def work(ids):
-        slot['prep'] = packed.prepare(ids)
-    prep = packed.prepare(id_batches[0])
+    prep = packed.prepare(id_batches[0]) if id_batches else None
     for i in range(len(id_batches)):
-        worker = None
+        batch = packed.launch(prep, out=out)
         if i + 1 < len(id_batches):
-            worker = threading.Thread(target=work, args=(id_batches[i + 1],), daemon=True)
-            worker.start()
-        yield packed.launch(prep, out=out)
-        if worker is not None:
-            worker.join()
-            prep = slot['prep']
+            prep = packed.prepare(id_batches[i + 1])
+        yield batch
 
 
 # --------------------------------------------------------------------------------------------------------- datasets

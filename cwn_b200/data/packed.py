@@ -21,6 +21,7 @@ import torch
 from cwn_b200 import _lib, ops
 from cwn_b200.data.complex import Cochain, CochainBatch, Complex, ComplexBatch
 
+_ELEMENT_SIZE = {torch.float32: 4, torch.long: 8, torch.float64: 8, torch.int32: 4}
 _INDEX_KEYS = ('upper_index', 'lower_index', 'boundary_index')
 _VECTOR_KEYS = ('shared_boundaries', 'shared_coboundaries')
 # the order in which ComplexBatch.pack_ meets the tensors of a cochain (Cochain.__init__ order, then batch / ptr)
@@ -147,24 +148,26 @@ class PackedComplexDataset(object):
         slots = [slot for dt in order for slot in slots if slot[2] == dt]
         layout, totals = [], {}
         for d, key, dtype, shape, _ in slots:
-            esz = torch.empty((), dtype=dtype).element_size()
-            align = max(1, 16 // esz)
+            align = max(1, 16 // _ELEMENT_SIZE[dtype])
             off = totals.get(dtype, 0)
-            numel = int(np.prod(shape))
+            numel = 1
+            for extent in shape:
+                numel *= int(extent)
             layout.append((d, key, dtype, off, tuple(shape)))
             totals[dtype] = off + (numel + align - 1) // align * align
         layout = tuple(layout)
         # ---- one host table with every segment array; destinations as (dtype, byte offset into that flat buffer)
-        table, jobs_spec = [], []
+        table, jobs_spec, table_len = [], [], [0]
 
         def put(arr):
-            start = sum(len(a) for a in table)
-            table.append(np.asarray(arr, dtype=np.int64))
+            start = table_len[0]
+            arr = np.asarray(arr, dtype=np.int64)
+            table.append(arr)
+            table_len[0] = start + len(arr)
             return start
 
         for (d, key, dtype, off, shape), (_, _, _, _, spec) in zip(layout, slots):
-            esz = torch.empty((), dtype=dtype).element_size()
-            dst_at = (dtype, off * esz)
+            dst_at = (dtype, off * _ELEMENT_SIZE[dtype])
             kind = spec[0]
             if kind == 'rows':
                 _, src_t, src, dst, _ = spec

@@ -34,13 +34,21 @@ class CapturedStep(object):
         model, loss_fn(out, y): the training closure pieces.
         bucket: `cwn_b200.dist.FlatGradBucket` (gradients are written into its static flat buffer).
         optimizer: captured into the graph when `optimizer_in_graph` (single GPU; needs `capturable=True`);
-            with data parallelism the all-reduce runs between the graph and a (separately captured) optimizer.
+            with data parallelism either `allreduce_in_graph=True` (the NCCL all-reduce is captured too: one graph), or
+            the all-reduce runs between the graph and a (separately captured) optimizer.
     """
 
-    def __init__(self, model, loss_fn, bucket, optimizer=None, optimizer_in_graph=True, warmup=3):
+    def __init__(self, model, loss_fn, bucket, optimizer=None, optimizer_in_graph=True, warmup=3,
+                 allreduce_in_graph=False):
         self.model, self.loss_fn, self.bucket, self.optimizer = model, loss_fn, bucket, optimizer
         self.optimizer_in_graph = optimizer_in_graph and optimizer is not None
-        self.warmup = warmup
+        # data parallel: the NCCL all-reduce of the flat bucket is captured INTO the graph, between backward and the
+        # optimizer, so a step stays one graph launch (three host-issued pieces cost +28 / +40 / +50 us per step at
+        # 2 / 4 / 8 GPUs in round 1). Needs optimizer_in_graph for the optimizer to follow it inside the graph.
+        self.allreduce_in_graph = allreduce_in_graph
+        # (Issuing it layer by layer during backward — async NCCL works from tensor hooks, captured as a parallel branch —
+        # was measured at 2 GPUs: 0.8675 vs 0.8712 ms per step, i.e. 0.4 %, and the captured async works kept
+        # destroy_process_group() from returning. Not kept: profiles/README.md, round 2.)
         self.graph = self.opt_graph = self.static = self.loss = None
 
     def _optimizer_clears_grads(self):
@@ -63,6 +71,8 @@ class CapturedStep(object):
             self.bucket.zero()
         loss = self._forward_loss(b)
         loss.backward()
+        if self.allreduce_in_graph:
+            self.bucket.all_reduce()
         if self.optimizer_in_graph:
             self.optimizer.step()
         return loss

@@ -78,3 +78,81 @@ def test_bucket_views_and_shard():
     assert all(float(p.grad.abs().sum()) == 0 for p in model.parameters())
     assert bucket.all_reduce() is None  # no process group: no-op
     assert shard(list(range(10)), 0, 4) == [0, 1, 2] and shard(list(range(10)), 3, 4) == [9]
+
+
+# ------------------------------------------------------------------------------- the real model on the data plane
+def _cwn_worker(rank, world, port, out, backend, use_cuda):
+    """Every rank: EmbedSparseCIN (graph_norm 'id': BatchNorm statistics are shard-local by design, so equality with a
+    single process on the union holds without it) on its shard of 8 molecules -> FlatGradBucket -> all-reduce."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, 'oracle'), os.path.join(root, 'tests')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    if use_cuda:
+        torch.cuda.set_device(rank)
+    dist.init_process_group(backend, rank=rank, world_size=world)
+    try:
+        from cwn_b200.data import synthetic
+        from cwn_b200.data.complex import ComplexBatch
+        from cwn_b200.mp.molec_models import EmbedSparseCIN
+        if not use_cuda:  # TEST INFRASTRUCTURE: torch restatements of the six ops entry points (the product is CUDA-only)
+            import cpu_ops_shim
+            from cwn_b200 import ops
+            for name in ('gather_scatter', 'gather_rows', 'scatter_rows', 'cob_pass', 'segment_pool', 'prepare_plans'):
+                setattr(ops, name, getattr(cpu_ops_shim, name))
+        dev = torch.device('cuda', rank) if use_cuda else torch.device('cpu')
+        torch.manual_seed(0)
+        model = EmbedSparseCIN(**_CWN_CFG).to(dev).train()
+        broadcast_parameters(model, src=0)
+        bucket = FlatGradBucket(model)
+        comps = shard(synthetic.zinc_like_complexes(8, seed=11), rank, world)
+        batch = ComplexBatch.from_complex_list(comps).to(dev)
+        loss = train_step(model, batch, lambda o, y: torch.nn.functional.l1_loss(o, y.view(-1, 1)), bucket)
+        out[rank] = (bucket.flat.cpu().clone(), float(loss))
+    finally:
+        dist.destroy_process_group()
+
+
+_CWN_CFG = dict(atom_types=28, bond_types=4, out_size=1, num_layers=2, hidden=16, dropout_rate=0.0, max_dim=2,
+                embed_edge=True, use_coboundaries=True, graph_norm='id', nonlinearity='elu')
+
+
+def _union_reference():
+    """Mean of the per-shard gradients == gradient of the mean of the shard losses (equal shard sizes), from the
+    CPU oracle-equivalent host path in ONE process."""
+    import cpu_ops_shim
+    from cwn_b200 import ops
+    from cwn_b200.data import synthetic
+    from cwn_b200.data.complex import ComplexBatch
+    from cwn_b200.mp.molec_models import EmbedSparseCIN
+    saved = {n: getattr(ops, n) for n in ('gather_scatter', 'gather_rows', 'scatter_rows', 'cob_pass', 'segment_pool', 'prepare_plans')}
+    try:
+        for n in saved:
+            setattr(ops, n, getattr(cpu_ops_shim, n))
+        torch.manual_seed(0)
+        model = EmbedSparseCIN(**_CWN_CFG).train()
+        comps = synthetic.zinc_like_complexes(8, seed=11)
+        total = 0.0
+        for r in range(2):
+            b = ComplexBatch.from_complex_list(shard(comps, r, 2))
+            total = total + torch.nn.functional.l1_loss(model(b), b.y.view(-1, 1)) / 2
+        total.backward()
+        return torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1)
+                          for p in model.parameters() if p.requires_grad])
+    finally:
+        for n, f in saved.items():
+            setattr(ops, n, f)
+
+
+def test_cwn_model_gradients_average_over_ranks_gloo():
+    """World 2 over gloo with the cochain model itself on the data plane: the all-reduced flat bucket of every rank ==
+    the mean of the per-shard gradients computed in one process."""
+    world, port = 2, _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_cwn_worker, args=(world, port, out, 'gloo', False), nprocs=world, join=True)
+    ref = _union_reference()
+    for r in range(world):
+        assert torch.allclose(out[r][0], ref, rtol=1e-5, atol=1e-6), float((out[r][0] - ref).abs().max())
+    assert torch.equal(out[0][0], out[1][0])
