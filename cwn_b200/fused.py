@@ -109,36 +109,45 @@ def _parse(seq, n_units):
 
 
 def recognise(level):
-    """(up units, boundary units, combine unit) of a SparseCINCochainConv built with the default nets, else None."""
+    """(up units, boundary units, combine unit, down units or None) of a SparseCINCochainConv / CINppCochainConv built
+    with the default nets, else None. CIN++ (reference mp/layers.py:216-260) has a third update branch, `update_down_nn`,
+    and a combine over three blocks [up | down | boundaries]."""
     up = _parse(level.update_up_nn, 2)
     bnd = _parse(level.update_boundaries_nn, 2)
     comb = _parse(level.combine_nn, 1)
-    if up is None or bnd is None or comb is None:
+    down = _parse(level.update_down_nn, 2) if hasattr(level, 'update_down_nn') else None
+    if up is None or bnd is None or comb is None or (hasattr(level, 'update_down_nn') and down is None):
         return None
-    if len({u.act for u in up + bnd}) != 1:
+    branches = [up, bnd] + ([down] if down is not None else [])
+    if len({u.act for br in branches for u in br}) != 1:
         return None
     h = up[1].lin.out_features
-    if bnd[1].lin.out_features != h or comb[0].lin.in_features != 2 * h:
+    if any(br[1].lin.out_features != h or br[0].lin.out_features != br[1].lin.in_features for br in branches):
         return None
-    if up[0].lin.out_features != up[1].lin.in_features or bnd[0].lin.out_features != bnd[1].lin.in_features:
+    if comb[0].lin.in_features != len(branches) * h:
         return None
-    if max(u.lin.out_features for u in up + bnd + comb) > 128:
+    if max(u.lin.out_features for br in branches + [comb] for u in br) > 128:
         return None  # shared-memory budget of unit_bwd_kernel
-    return up, bnd, comb[0]
+    return up, bnd, comb[0], down
 
 
-def applicable(forms, us, bs, training):
+def applicable(forms, us, bs, training, ds=None):
     if any(f is None for f in forms):
+        return False
+    if any((f[3] is not None) != (ds is not None) for f in forms):
         return False
     params = _parameters(forms)
     if len({id(p) for p in params}) != len(params):
         return False  # nets shared between dimensions (passed_update_*_nn): gradients would collide in one launch
-    for f, u, b in zip(forms, us, bs):
+    for d, (f, u, b) in enumerate(zip(forms, us, bs)):
         if not (u.is_cuda and u.dtype == torch.float32 and u.dim() == 2 and b.shape == u.shape):
             return False
         if u.size(1) != f[0][0].lin.in_features or b.size(1) != f[1][0].lin.in_features:
             return False
-        has_bn = any(unit.bn is not None for unit in f[0] + f[1] + [f[2]])
+        if ds is not None and (ds[d].shape != u.shape or ds[d].dtype != torch.float32 or not ds[d].is_cuda
+                               or ds[d].size(1) != f[3][0].lin.in_features):
+            return False
+        has_bn = any(unit.bn is not None for unit in f[0] + f[1] + [f[2]] + (f[3] or []))
         if has_bn and training and u.size(0) < 2:
             return False  # torch raises "Expected more than 1 value per channel"; keep that behaviour
         if has_bn and not training and torch.is_grad_enabled():
@@ -246,21 +255,27 @@ class FusedSparseCINDense(Function):
     """outs = f(us[0], bs[0], us[1], bs[1], ..., *parameters). `ctx_forms` carries the module structure."""
 
     @staticmethod
-    def forward(ctx, forms, training, n_dims, *tensors):
-        us, bs = list(tensors[0:2 * n_dims:2]), list(tensors[1:2 * n_dims:2])
+    def forward(ctx, forms, training, n_dims, nb, *tensors):
+        us, bs = list(tensors[0:nb * n_dims:nb]), list(tensors[1:nb * n_dims:nb])
+        ds = list(tensors[2:nb * n_dims:nb]) if nb == 3 else None
         dev = us[0].device
         with torch.cuda.device(dev):
             states = []  # per dim: dict name -> _UnitState
 
-            def new_state(unit, x0, x1, prev0, prev1, d):
+            def new_state(unit, x0, x1, prev0, prev1, d, z=None, vecs=None):
+                """`z` / `vecs`: pre-placed output matrix [n, h] (a column range of a wider matrix) and statistics
+                vectors [3, h] — how two branches of CIN++ write side by side, so that the combine unit sees them as ONE
+                input block (the kernels take two blocks; CIN++ has three)."""
                 st = _UnitState()
                 st.unit, st.x0, st.x1 = unit, x0, x1
                 st.live = _live(d)
                 st.in0, st.in1 = _in_vectors(prev0), _in_vectors(prev1)
                 st.in_act = prev0.unit.act if prev0 is not None else 'id'
                 st.n, st.h = x0.size(0), unit.lin.out_features
-                st.z = torch.empty(st.n, st.h, dtype=torch.float32, device=dev)
+                st.z = z if z is not None else torch.empty(st.n, st.h, dtype=torch.float32, device=dev)
                 st.mean = st.scale = st.rstd = None
+                if vecs is not None and unit.bn is not None:
+                    st.mean, st.scale, st.rstd = vecs[0], vecs[1], vecs[2]
                 return st
 
             def run_units(sts):
@@ -274,8 +289,9 @@ class FusedSparseCINDense(Function):
                     bn_fields = (None, 0.0, 0.0, 0, None, None, None, None, None, None, None)
                     if unit.bn is not None:
                         m = unit.bn
-                        vecs = torch.empty(3, st.h, dtype=torch.float32, device=dev)
-                        st.mean, st.scale, st.rstd = vecs[0], vecs[1], vecs[2]
+                        if st.mean is None:
+                            vecs = torch.empty(3, st.h, dtype=torch.float32, device=dev)
+                            st.mean, st.scale, st.rstd = vecs[0], vecs[1], vecs[2]
                         if training:
                             stats = torch.empty(max(n_tiles, 1) * 2 * st.h, dtype=torch.float32, device=dev)
                             alive.append(stats)
@@ -288,28 +304,48 @@ class FusedSparseCINDense(Function):
                         _p(st.x0), st.x0.stride(0), st.x0.size(1), _p(st.x1), st.x1.stride(0) if st.x1 is not None else 0,
                         st.x1.size(1) if st.x1 is not None else 0, _p(i0[0]), _p(i0[1]), _p(i0[2]), _p(i1[0]), _p(i1[1]),
                         _p(i1[2]), ops.ACT_CODES[st.in_act], _p(unit.lin.weight), unit.lin.weight.stride(0),
-                        _p(unit.lin.bias), _p(st.z), st.h, _p(stats), st.n, st.h, *bn_fields, tr, _p(st.live)))
+                        _p(unit.lin.bias), _p(st.z), st.z.stride(0), _p(stats), st.n, st.h, *bn_fields, tr, _p(st.live)))
                 _launch('cwn_linear_fwd_grouped', _lib.LinearDesc, lin)
 
             l1, l2, l3 = [], [], []
             for d in range(n_dims):
-                up, bnd, comb = forms[d]
+                up, bnd, comb, down = forms[d]
                 s = {}
                 s['u1'] = new_state(up[0], us[d].contiguous(), None, None, None, d)
                 s['b1'] = new_state(bnd[0], bs[d].contiguous(), None, None, None, d)
                 states.append(s)
                 l1 += [s['u1'], s['b1']]
+                if down is not None:
+                    s['d1'] = new_state(down[0], ds[d].contiguous(), None, None, None, d)
+                    l1.append(s['d1'])
             run_units(l1)
             for d in range(n_dims):
-                up, bnd, comb = forms[d]
+                up, bnd, comb, down = forms[d]
                 s = states[d]
-                s['u2'] = new_state(up[1], s['u1'].z, None, s['u1'], None, d)
+                if down is None:
+                    s['u2'] = new_state(up[1], s['u1'].z, None, s['u1'], None, d)
+                else:  # up and down second units write the two halves of ONE [n, 2h] matrix (and of one [3, 2h] vector block)
+                    h = up[1].lin.out_features
+                    zz = torch.empty(s['u1'].n, 2 * h, dtype=torch.float32, device=dev)
+                    vv = torch.empty(3, 2 * h, dtype=torch.float32, device=dev)
+                    s['zz'], s['vv'] = zz, vv
+                    s['u2'] = new_state(up[1], s['u1'].z, None, s['u1'], None, d, z=zz[:, :h], vecs=vv[:, :h])
+                    s['d2'] = new_state(down[1], s['d1'].z, None, s['d1'], None, d, z=zz[:, h:], vecs=vv[:, h:])
+                    l2.append(s['d2'])
                 s['b2'] = new_state(bnd[1], s['b1'].z, None, s['b1'], None, d)
                 l2 += [s['u2'], s['b2']]
             run_units(l2)
             for d in range(n_dims):
                 s = states[d]
-                s['c'] = new_state(forms[d][2], s['u2'].z, s['b2'].z, s['u2'], s['b2'], d)
+                if forms[d][3] is None:
+                    s['c'] = new_state(forms[d][2], s['u2'].z, s['b2'].z, s['u2'], s['b2'], d)
+                else:  # block 0 = [up | down] (2h columns), block 1 = boundaries
+                    st = new_state(forms[d][2], s['zz'], s['b2'].z, None, s['b2'], d)
+                    u2, d2 = s['u2'], s['d2']
+                    if u2.unit.bn is not None:
+                        st.in0 = (s['vv'][0], s['vv'][1], torch.cat([u2.unit.bn.bias.detach(), d2.unit.bn.bias.detach()]))
+                    st.in_act = u2.unit.act
+                    s['c'] = st
                 l3.append(s['c'])
             run_units(l3)
             outs, descs = [], []
@@ -321,7 +357,7 @@ class FusedSparseCINDense(Function):
                                             ops.ACT_CODES[st.unit.act], _p(out), st.h, st.n, st.h))
                 outs.append(out)
             _launch('cwn_bn_act_grouped', _lib.BNActDesc, descs)
-        ctx.states, ctx.n_dims, ctx.forms = states, n_dims, forms
+        ctx.states, ctx.n_dims, ctx.forms, ctx.nb = states, n_dims, forms, nb
         ctx.n_inputs = len(tensors)
         return tuple(outs)
 
@@ -350,7 +386,7 @@ class FusedSparseCINDense(Function):
                 n_tiles = (st.n + tr - 1) // tr
                 n_ctas = ctas[i]
                 has_bn = unit.bn is not None
-                g = g.contiguous()
+                g = g if (g.stride(1) == 1 and g.stride(0) % 4 == 0) else g.contiguous()  # (column ranges stay views)
                 gi0 = new(st.n, k0) if want0 else None
                 gi1 = new(st.n, k1) if (want1 and k1) else None
                 # parameter gradients: straight into `.grad` when it is pre-allocated (accumulate), else fresh tensors
@@ -373,7 +409,7 @@ class FusedSparseCINDense(Function):
                 descs.append(_lib.UnitBwdDesc(
                     _p(st.x0), st.x0.stride(0), k0, _p(st.x1), st.x1.stride(0) if st.x1 is not None else 0, k1,
                     _p(i0[0]), _p(i0[1]), _p(i0[2]), _p(i1[0]), _p(i1[1]), _p(i1[2]), ops.ACT_CODES[st.in_act],
-                    _p(unit.lin.weight), unit.lin.weight.stride(0), _p(st.z), st.h, int(has_bn),
+                    _p(unit.lin.weight), unit.lin.weight.stride(0), _p(st.z), st.z.stride(0), int(has_bn),
                     ops.ACT_CODES[unit.act], _p(st.mean), _p(st.scale), _p(st.rstd),
                     _p(unit.bn.bias) if has_bn else None, _p(g), g.stride(0), _p(red), _p(c1), _p(c2), _p(gg),
                     _p(gbeta), acc_a, _p(gi0), k0, _p(gi1), k1, _p(new(max(n_ctas, 1) * st.h * (k0 + k1))),
@@ -395,24 +431,35 @@ class FusedSparseCINDense(Function):
             g_outs = [g if g is not None else torch.zeros_like(states[d]['c'].z) for d, g in enumerate(g_outs)]
             descs, gins = run([(states[d]['c'], g_outs[d], True, True) for d in range(n_dims)])
             all_descs += descs
-            items = []
+            nb = ctx.nb
+            items, slot2 = [], []
             for d in range(n_dims):
-                items += [(states[d]['u2'], gins[d][0], True, False), (states[d]['b2'], gins[d][1], True, False)]
+                s = states[d]
+                if nb == 2:
+                    items += [(s['u2'], gins[d][0], True, False), (s['b2'], gins[d][1], True, False)]
+                    slot2 += [(d, 'u'), (d, 'b')]
+                else:
+                    h = s['u2'].h
+                    items += [(s['u2'], gins[d][0][:, :h], True, False), (s['d2'], gins[d][0][:, h:], True, False),
+                              (s['b2'], gins[d][1], True, False)]
+                    slot2 += [(d, 'u'), (d, 'd'), (d, 'b')]
             descs, gins2 = run(items)
             all_descs += descs
-            need_u = [ctx.needs_input_grad[3 + 2 * d] for d in range(n_dims)]
-            need_b = [ctx.needs_input_grad[4 + 2 * d] for d in range(n_dims)]
-            items = []
+            g2 = {key: gi[0] for key, gi in zip(slot2, gins2)}
+            need = {(d, 'ubd'[j]): ctx.needs_input_grad[4 + nb * d + j] for d in range(n_dims) for j in range(nb)}
+            items, slot1 = [], []
             for d in range(n_dims):
-                items += [(states[d]['u1'], gins2[2 * d][0], need_u[d], False),
-                          (states[d]['b1'], gins2[2 * d + 1][0], need_b[d], False)]
+                for key in (['u', 'b'] if nb == 2 else ['u', 'b', 'd']):
+                    items.append((states[d][key + '1'], g2[(d, key)], need[(d, key)], False))
+                    slot1.append((d, key))
             descs, gins1 = run(items)
             all_descs += descs
+            g1 = {key: gi[0] for key, gi in zip(slot1, gins1)}
             _launch('cwn_wgrad_finalize_grouped', _lib.UnitBwdDesc, all_descs)
 
-        out = [None, None, None]
+        out = [None, None, None, None]
         for d in range(n_dims):
-            out += [gins1[2 * d][0], gins1[2 * d + 1][0]]
+            out += [g1[(d, key)] for key in (['u', 'b'] if ctx.nb == 2 else ['u', 'b', 'd'])]
         out += [grads.get(id(p)) for p in _parameters(ctx.forms)]
         ctx.states = None
         return tuple(out)
@@ -420,23 +467,23 @@ class FusedSparseCINDense(Function):
 
 def _parameters(forms):
     params = []
-    for up, bnd, comb in forms:
-        for unit in up + bnd + [comb]:
+    for up, bnd, comb, down in forms:
+        for unit in up + bnd + [comb] + (down or []):
             params += [unit.lin.weight, unit.lin.bias]
             if unit.bn is not None:
                 params += [unit.bn.weight, unit.bn.bias]
     return params
 
 
-def sparse_cin_dense(forms, us, bs, training):
-    """Run the update/combine nets of every dimension of a layer. `forms[d] = recognise(level_d)`."""
+def sparse_cin_dense(forms, us, bs, training, ds=None):
+    """Run the update/combine nets of every dimension of a layer. `forms[d] = recognise(level_d)`; `ds`: the inputs of
+    the third (down) branch of CIN++."""
     n_dims = len(us)
     params = _parameters(forms)
     flat = []
-    for u, b in zip(us, bs):
-        flat += [u, b]
-
-    return list(FusedSparseCINDense.apply(forms, training, n_dims, *flat, *params))
+    for d, (u, b) in enumerate(zip(us, bs)):
+        flat += [u, b] + ([ds[d]] if ds is not None else [])
+    return list(FusedSparseCINDense.apply(forms, training, n_dims, 3 if ds is not None else 2, *flat, *params))
 
 
 # ------------------------------------------------------------------------------------------------ plain linears

@@ -42,6 +42,7 @@ class CapturedStep(object):
                  allreduce_in_graph=False):
         self.model, self.loss_fn, self.bucket, self.optimizer = model, loss_fn, bucket, optimizer
         self.optimizer_in_graph = optimizer_in_graph and optimizer is not None
+        self.warmup = warmup
         # data parallel: the NCCL all-reduce of the flat bucket is captured INTO the graph, between backward and the
         # optimizer, so a step stays one graph launch (three host-issued pieces cost +28 / +40 / +50 us per step at
         # 2 / 4 / 8 GPUs in round 1). Needs optimizer_in_graph for the optimizer to follow it inside the graph.

@@ -508,7 +508,36 @@ class CINppConv(SparseCINConv):
     SparseCINConv's constructor (whose levels are then discarded), so a seeded construction consumes the random
     stream identically."""
 
-    fuse_dense = False  # three update branches: the dense nets run on the torch modules
+    fuse_dense = True  # the three update branches + combine as one fused autograd node (cwn_b200.fused)
+
+    def forward(self, *cochain_params: CochainMessagePassingParams, start_to_process=0):
+        """All aggregation passes of the layer as one node (`fused._LayerAggregate`, boundary epsilon = eps3), the down
+        branch's input `(1 + eps2) x` (no lower messages are ever propagated: see CINppCochainConv), then the three
+        update MLPs and the 3-block combine of every dimension as ONE fused dense node; anything outside that closed
+        form runs level by level through the torch modules."""
+        n = len(cochain_params)
+        assert n <= self.max_dim + 1
+        if self.fuse_dense and self.fuse_aggregation and start_to_process == 0 and n > 0:
+            from cwn_b200 import fused
+            forms = getattr(self, '_dense_forms', None)
+            if forms is None:
+                forms = self._dense_forms = [fused.recognise(level) for level in self.mp_levels]
+            if all(f is not None and f[3] is not None for f in forms[:n]) and \
+                    all(self.mp_levels[d].down_msg_size == cochain_params[d].x.size(1) for d in range(n)
+                        if isinstance(cochain_params[d].x, Tensor) and cochain_params[d].x.dim() == 2):
+                agg = fused.layer_aggregate(self.mp_levels[:n], cochain_params)
+                if agg is not NotImplemented:
+                    us, bs = agg
+                    ds = [(1 + self.mp_levels[d].eps2) * cochain_params[d].x for d in range(n)]
+                    if fused.applicable(forms[:n], us, bs, self.mp_levels[0].training, ds):
+                        return fused.sparse_cin_dense(forms[:n], us, bs, self.mp_levels[0].training, ds)
+                    levels = self.mp_levels
+                    outs = []
+                    for d in range(n):  # aggregated already: finish through the torch modules
+                        ou, od, ob = levels[d].update_up_nn(us[d]), levels[d].update_down_nn(ds[d]), levels[d].update_boundaries_nn(bs[d])
+                        outs.append(levels[d].combine_nn(torch.cat([ou, od, ob], dim=-1)))
+                    return outs
+        return _PerDimension.forward(self, *cochain_params, start_to_process=start_to_process)
 
     def __init__(self, up_msg_size: int, down_msg_size: int, boundary_msg_size: Optional[int],
                  passed_msg_up_nn: Optional[Callable], passed_msg_down_nn: Optional[Callable],

@@ -247,6 +247,13 @@ def main():
     run_oriented('edge_mpnn_train', RefEdgeMPNN(**cfg), cfg,
                  synthetic.float_feature_complexes(4, 3, seed=12, include_down_adj=True), 22)
 
+    # OGBEmbedCINpp (mp/molec_models.py:355-385), appended after everything else (random stream above unchanged)
+    from mp.molec_models import OGBEmbedCINpp as RefOGBCINpp
+    cfg = dict(out_size=1, num_layers=2, hidden=16, dropout_rate=0.0, indropout_rate=0.0, max_dim=2,
+               embed_edge=True, use_coboundaries=True, readout='mean')
+    run_train('ogb_embed_cinpp_train', RefOGBCINpp(**cfg), cfg,
+              synthetic.zinc_like_complexes(6, seed=13, ogb_features=True), bce)
+
     gold['models'] = models
     path = os.path.join(HERE, 'reference_golden.pt')
     torch.save(gold, path)

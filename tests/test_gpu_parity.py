@@ -14,7 +14,7 @@ from cwn_b200.data.complex import ComplexBatch
 from cwn_b200.mp.cell_mp import CochainMessagePassing
 from cwn_b200.mp.layers import DummyCellularMessagePassing, InitReduceConv
 from cwn_b200.mp.models import CIN0, CINpp, SparseCIN
-from cwn_b200.mp.molec_models import EmbedCINpp, EmbedSparseCIN, OGBEmbedSparseCIN
+from cwn_b200.mp.molec_models import EmbedCINpp, EmbedSparseCIN, OGBEmbedCINpp, OGBEmbedSparseCIN
 from helpers import assert_close, batch_of, fixture, golden, oracle_state, share_cin0_levels
 
 pytestmark = pytest.mark.gpu
@@ -305,14 +305,14 @@ def test_user_overridden_hooks_are_honoured():
 
 # ------------------------------------------------------------------------------------------------ models
 KLASS = {'sparse_cin': SparseCIN, 'embed_sparse_cin': EmbedSparseCIN, 'ogb_embed_sparse_cin': OGBEmbedSparseCIN,
-         'cin0': CIN0, 'cinpp': CINpp, 'embed_cinpp': EmbedCINpp}
+         'cin0': CIN0, 'cinpp': CINpp, 'embed_cinpp': EmbedCINpp, 'ogb_embed_cinpp': OGBEmbedCINpp}
 ORACLE = {'sparse_cin': O.sparse_cin, 'embed_sparse_cin': O.embed_sparse_cin,
           'ogb_embed_sparse_cin': O.ogb_embed_sparse_cin, 'cin0': O.cin0, 'cinpp': O.cinpp,
-          'embed_cinpp': O.embed_cinpp}
+          'embed_cinpp': O.embed_cinpp, 'ogb_embed_cinpp': O.ogb_embed_cinpp}
 
 
 def _family(name):
-    for k in ('ogb_embed_sparse_cin', 'embed_sparse_cin', 'embed_cinpp', 'cinpp', 'sparse_cin', 'cin0'):
+    for k in ('ogb_embed_sparse_cin', 'ogb_embed_cinpp', 'embed_sparse_cin', 'embed_cinpp', 'cinpp', 'sparse_cin', 'cin0'):
         if name.startswith(k):
             return k
 
@@ -348,7 +348,7 @@ def _loss(name, out, y):
 
 
 @pytest.mark.parametrize('name', ['sparse_cin_train', 'embed_sparse_cin_train', 'embed_sparse_cin_train_nocob',
-                                  'ogb_embed_sparse_cin_train', 'cin0_train', 'cinpp_train', 'embed_cinpp_train'])
+                                  'ogb_embed_sparse_cin_train', 'cin0_train', 'cinpp_train', 'embed_cinpp_train', 'ogb_embed_cinpp_train'])
 def test_train_step_matches_reference_and_oracle(name):
     """Forward, loss, every parameter gradient and the BatchNorm running statistics of one training step."""
     m = golden()['models'][name]
@@ -678,6 +678,48 @@ def test_ragged_batches_replay_through_one_cuda_graph():
     assert len(layouts) == 4 and step.fallbacks == 0
     step.step(pool[:32] + pool[:8])  # 40 complexes > 32 slots
     assert step.fallbacks == 1
+
+
+@pytest.mark.parametrize('layer_dim,hidden,act,norm,cob', [(64, 64, 'elu', 'bn', True), (16, 32, 'tanh', 'bn', False),
+                                                           (8, 16, 'relu', 'id', True)])
+def test_fused_cinpp_layer_equals_torch_modules(layer_dim, hidden, act, norm, cob):
+    """CIN++ (reference mp/layers.py:216-260, 344-427) through the fused nodes — every aggregation pass of the layer as one
+    node, the THREE update MLPs + the 3-block combine as one grouped dense node (up and down branches write side by
+    side into one [n, 2h] matrix, which the combine kernel reads as its first input block) — against the same layer
+    run level by level through its torch modules: outputs, input gradients, parameter gradients, BatchNorm buffers."""
+    from cwn_b200.mp.layers import CINppConv
+    from cwn_b200.mp.nn import get_graph_norm, get_nonlinearity
+    torch.manual_seed(4)
+    mk = lambda: CINppConv(layer_dim, layer_dim, layer_dim, None, None, None, None, None, None, layer_dim=layer_dim,  # noqa: E731
+                           hidden=hidden, act_module=get_nonlinearity(act), graph_norm=get_graph_norm(norm),
+                           use_coboundaries=cob, train_eps=True).to(DEV)
+    fused_conv, torch_conv = mk(), mk()
+    torch_conv.load_state_dict(fused_conv.state_dict())
+    torch_conv.fuse_dense = False
+    results = []
+    for conv in (fused_conv, torch_conv):
+        conv.train()
+        batch = ComplexBatch.from_complex_list(
+            synthetic.float_feature_complexes(9, layer_dim, seed=12, ragged=True)).to(DEV)
+        for d in range(3):
+            batch.cochains[d]._x = batch.cochains[d].x.clone().requires_grad_(True)
+        outs = conv(*batch.get_all_cochain_params(max_dim=2, include_down_features=False))
+        g = torch.Generator(device=DEV).manual_seed(5)
+        sum((o * torch.randn(o.shape, device=DEV, generator=g)).sum() for o in outs).backward()
+        results.append((outs, [batch.cochains[d].x.grad for d in range(3)], dict(conv.named_parameters()),
+                        dict(conv.named_buffers())))
+    (o1, gx1, p1, b1), (o2, gx2, p2, b2) = results
+    for d in range(3):
+        assert_close(o1[d], o2[d], rtol=1e-5, atol=2e-5, what=f'out {d}')
+        assert_close(gx1[d], gx2[d], rtol=1e-4, atol=5e-5, what=f'grad x {d}')
+    for k in p1:
+        if p2[k].grad is None:
+            assert p1[k].grad is None or float(p1[k].grad.abs().sum()) == 0, k
+        else:
+            atol = max(5e-5, 1e-4 * (float(p2[k].grad.abs().max()) + 1e-6))
+            assert_close(p1[k].grad, p2[k].grad, rtol=1e-4, atol=atol, what=f'grad {k}')
+    for k in b1:
+        assert_close(b1[k].float(), b2[k].float(), rtol=1e-5, atol=1e-6, what=f'buffer {k}')
 
 
 @pytest.mark.parametrize('layer_dim,hidden,act,norm,cob', [(64, 64, 'relu', 'bn', True), (8, 20, 'elu', 'bn', False),

@@ -11,7 +11,8 @@ from helpers import assert_close, batch_of, golden
 
 def _klass(name):
     from cwn_b200.mp import models as M, molec_models as MM
-    table = [('ogb_embed_sparse_cin', MM.OGBEmbedSparseCIN), ('embed_sparse_cin', MM.EmbedSparseCIN),
+    table = [('ogb_embed_sparse_cin', MM.OGBEmbedSparseCIN), ('ogb_embed_cinpp', MM.OGBEmbedCINpp),
+             ('embed_sparse_cin', MM.EmbedSparseCIN),
              ('embed_cinpp', MM.EmbedCINpp), ('cinpp', M.CINpp), ('sparse_cin', M.SparseCIN), ('cin0', M.CIN0),
              ('edge_cin0', M.EdgeCIN0)]
     return next(k for prefix, k in table if name.startswith(prefix))
@@ -24,7 +25,7 @@ def _loss(name, out, y):
 
 
 @pytest.mark.parametrize('name', ['sparse_cin_train', 'embed_sparse_cin_train', 'embed_sparse_cin_train_nocob',
-                                  'ogb_embed_sparse_cin_train', 'cin0_train', 'cinpp_train', 'embed_cinpp_train',
+                                  'ogb_embed_sparse_cin_train', 'cin0_train', 'cinpp_train', 'embed_cinpp_train', 'ogb_embed_cinpp_train',
                                   'edge_cin0_train', 'edge_cin0_notop_train'])
 def test_model_host_logic_matches_reference_train_step(name, monkeypatch):
     cpu_ops_shim.install(monkeypatch)

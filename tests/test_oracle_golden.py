@@ -127,7 +127,8 @@ def test_mean_max_aggregation_matches_reference(reduce):
 
 
 FORWARDS = {'sparse_cin': O.sparse_cin, 'embed_sparse_cin': O.embed_sparse_cin,
-            'ogb_embed_sparse_cin': O.ogb_embed_sparse_cin, 'cinpp': O.cinpp, 'embed_cinpp': O.embed_cinpp}
+            'ogb_embed_sparse_cin': O.ogb_embed_sparse_cin, 'cinpp': O.cinpp, 'embed_cinpp': O.embed_cinpp,
+            'ogb_embed_cinpp': O.ogb_embed_cinpp}
 
 
 @pytest.mark.parametrize('name', ['sparse_cin_eval', 'sparse_cin_eval_dim1', 'embed_sparse_cin_eval', 'cin0_eval'])
@@ -160,7 +161,7 @@ def _loss(name, out, y):
 
 
 @pytest.mark.parametrize('name', ['sparse_cin_train', 'embed_sparse_cin_train', 'embed_sparse_cin_train_nocob',
-                                  'ogb_embed_sparse_cin_train', 'cin0_train', 'cinpp_train', 'embed_cinpp_train'])
+                                  'ogb_embed_sparse_cin_train', 'cin0_train', 'cinpp_train', 'embed_cinpp_train', 'ogb_embed_cinpp_train'])
 def test_train_models_match_reference_forward_backward(name):
     m = golden()['models'][name]
     sd = oracle_state(m['state_dict'], requires_grad=True)
@@ -171,7 +172,7 @@ def test_train_models_match_reference_forward_backward(name):
     if name.startswith('cin0'):
         out = O.cin0(sd, m['cfg'], snap, training=True)
     else:
-        key = next(k for k in ('ogb_embed_sparse_cin', 'embed_sparse_cin', 'embed_cinpp', 'cinpp', 'sparse_cin')
+        key = next(k for k in ('ogb_embed_sparse_cin', 'ogb_embed_cinpp', 'embed_sparse_cin', 'embed_cinpp', 'cinpp', 'sparse_cin')
                    if name.startswith(k))
         out = FORWARDS[key](sd, m['cfg'], snap, training=True)
     assert_close(out, m['output'], atol=1e-6, what=name)
