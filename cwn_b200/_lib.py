@@ -103,6 +103,10 @@ _SIGNATURES = {
                                            _i32, _c_f32p, _i64, _c_f32p, _c_f32p, _i64, _vp]),
     'cwn_csr_cob_bwd_f32': (ctypes.c_int, [_c_f32p, _i64, _c_f32p, _i64, _c_f32p, _i64, _c_i32p, _c_i32p,
                                            _c_i32p, _i64, _i32, _i32, _c_f32p, _i64, _vp]),
+    'cwn_cin_msg_sq_f32': (ctypes.c_int, [_c_f32p, _i64, _c_f32p, _i64, _c_i32p, _c_i32p, _c_i32p, _i64, _i32, _i32,
+                                          _c_f32p, _c_f32p, _i64, _vp]),
+    'cwn_cin_msg_bwd_f32': (ctypes.c_int, [_c_f32p, _i64, _c_f32p, _i64, _c_f32p, _i64, _c_i32p, _c_i32p, _c_i32p, _i64,
+                                           _i32, _i32, _c_f32p, _c_f32p, _c_f32p, _c_f32p, _c_f32p, _c_f32p, _i64, _vp]),
     'cwn_linear_fwd_grouped': (ctypes.c_int, [ctypes.POINTER(LinearDesc), _i32, _vp]),
     'cwn_bn_finalize_grouped': (ctypes.c_int, [ctypes.POINTER(BNDesc), _i32, _vp]),
     'cwn_bn_act_grouped': (ctypes.c_int, [ctypes.POINTER(BNActDesc), _i32, _vp]),

@@ -98,12 +98,72 @@ class CINCochainConv(CochainMessagePassing):
             self.register_buffer('eps', torch.Tensor([eps]))
         self.reset_parameters()
 
+    fuse_messages = True  # K5: message MLP + BatchNorm over the messages inside the passes (ops.cin_message_pass)
+
+    @staticmethod
+    def _message_form(nn_):
+        """(Linear, activation name, BatchNorm1d or None) of a message net `Sequential(Linear, act[, BatchNorm1d])`
+        (the nets of CIN0 / EdgeCIN0, reference mp/models.py:40-47), else None."""
+        if not isinstance(nn_, Sequential) or len(nn_) not in (2, 3) or not isinstance(nn_[0], Linear) or nn_[0].bias is None:
+            return None
+        act = activation_name(nn_[1])
+        if act is None:
+            return None
+        bn = nn_[2] if len(nn_) == 3 else None
+        if bn is not None and not (isinstance(bn, BN) and bn.affine):
+            return None
+        return nn_[0], act, bn
+
+    def _can_fuse(self, nn_, x, index, attr):
+        """Is this adjacency inside K5's closed form? (Decided for BOTH adjacencies before either runs: a half-fused
+        layer falling back to `propagate` would update shared BatchNorm buffers twice.)"""
+        form = self._message_form(nn_)
+        if form is None or not isinstance(attr, LazyRows) or not (x.is_cuda and x.dtype == torch.float32):
+            return False
+        lin, act, bn = form
+        if attr.source.dim() != 2 or x.size(1) + attr.source.size(1) != lin.in_features \
+                or attr.source.dtype != torch.float32:
+            return False
+        if bn is not None and bn.training and index.size(1) < 2:
+            return False  # torch raises "Expected more than 1 value per channel": keep that behaviour
+        return True
+
+    def _fused_pass(self, nn_, x, index, attr):
+        """One adjacency through K5 (ops.cin_message_pass); the split-weight products through the grouped linear."""
+        lin, act, bn = self._message_form(nn_)
+        fx = x.size(1)
+        from cwn_b200 import fused
+        P, Q = fused.grouped_linear([(x, lin.weight, 0, None), (attr.source, lin.weight, fx, lin.bias)])
+        return ops.cin_message_pass(P, Q, index, attr.index, x.size(0), act, bn)
+
+    def _hooks_untouched(self):
+        klass = type(self)
+        return all(getattr(klass, name) is getattr(CINCochainConv, name)
+                   for name in ('message_up', 'message_down', 'aggregate_up', 'aggregate_down', 'update', 'propagate')) \
+            and self.aggr_up == 'add' and self.aggr_down == 'add' and self.flow == 'source_to_target'
+
     def forward(self, cochain: CochainMessagePassingParams):
-        out_up, out_down, _ = self.propagate(cochain.up_index, cochain.down_index, None, x=cochain.x,
-                                             up_attr=cochain.kwargs['up_attr'],
-                                             down_attr=cochain.kwargs['down_attr'])
-        out_up = out_up + (1 + self.eps) * cochain.x
-        out_down = out_down + (1 + self.eps) * cochain.x
+        x = cochain.x
+        up_attr, down_attr = cochain.kwargs['up_attr'], cochain.kwargs['down_attr']
+        fusable = self.fuse_messages and self._hooks_untouched() and isinstance(x, Tensor) and x.dim() == 2
+        if fusable:  # absent adjacency: zeros [N, msg_size] in the reference, i.e. only the residual (widths must agree)
+            up_ok = (self.up_msg_size == x.size(1)) if cochain.up_index is None else \
+                (up_attr is not None and self._can_fuse(self.msg_up_nn, x, cochain.up_index, up_attr))
+            down_ok = (self.down_msg_size == x.size(1)) if cochain.down_index is None else \
+                self._can_fuse(self.msg_down_nn, x, cochain.down_index, down_attr)
+            fusable = up_ok and down_ok
+        if fusable:
+            # in the order of the reference: the upper net first, then the lower one (they may share BatchNorm buffers
+            # with other dimensions, whose running statistics are updated sequentially)
+            out_up = None if cochain.up_index is None else self._fused_pass(self.msg_up_nn, x, cochain.up_index, up_attr)
+            out_down = None if cochain.down_index is None else \
+                self._fused_pass(self.msg_down_nn, x, cochain.down_index, down_attr)
+        else:
+            out_up, out_down, _ = self.propagate(cochain.up_index, cochain.down_index, None, x=x, up_attr=up_attr,
+                                                 down_attr=down_attr)
+        res = (1 + self.eps) * x
+        out_up = res if out_up is None else out_up + res
+        out_down = res if out_down is None else out_down + res
         return self.update_nn(out_up + out_down)
 
     def reset_parameters(self):

@@ -461,6 +461,100 @@ class _CobPass(Function):
         return gP, gQ, g_res, g_eps, None, None
 
 
+class _CinMsgPass(Function):
+    """out[t] = SUM_{e -> t} BN(act(P[src_e] + Q[att_e])) with BatchNorm over the E messages (K5; reference
+    mp/layers.py:94-103 with the nets of mp/models.py:40-47). See csrc/cin_msg.cu for the algebra. `stats` = None for
+    batch statistics (training) or (running_mean, running_var) for eval. Returns (out, mean, var) — mean / var (detached)
+    are what the caller feeds the module's running statistics with."""
+
+    @staticmethod
+    def forward(ctx, P, Q, gamma, beta, adj: Adjacency, act: str, bn_eps: float, stats):
+        lib = _lib.load()
+        plan = adj.by_dst
+        F, E, dev = P.size(1), adj.E, P.device
+        code = ACT_CODES[act]
+        with torch.cuda.device(dev):
+            S = torch.empty(adj.n_dst, F, dtype=torch.float32, device=dev)
+            algo = 24 * E + 4 * F * (P.size(0) + Q.size(0) + adj.n_dst)
+            _call('csr_cob_fwd', algo, lib.cwn_csr_cob_fwd_f32, _ptr(P), _ld(P), _ptr(Q), _ld(Q), plan.rowptr.data_ptr(),
+                  _ptr(plan.pay0), _ptr(plan.pay1), adj.n_dst, F, code, None, F, None, _ptr(S), F, _stream())
+            deg = (plan.rowptr[1:] - plan.rowptr[:-1]).to(torch.float32).unsqueeze(1)
+            if stats is None:
+                mean = S.sum(0) / E
+                S2 = torch.empty_like(S)
+                _call('cin_msg_sq', algo, lib.cwn_cin_msg_sq_f32, _ptr(P), _ld(P), _ptr(Q), _ld(Q), plan.rowptr.data_ptr(),
+                      _ptr(plan.pay0), _ptr(plan.pay1), adj.n_dst, F, code, _ptr(mean), _ptr(S2), F, _stream())
+                var = S2.sum(0) / E
+            else:
+                mean, var = stats[0].to(torch.float32), stats[1].to(torch.float32)
+            rstd = torch.rsqrt(var + bn_eps)
+            scale = rstd * gamma if gamma is not None else rstd
+            shift = (beta if beta is not None else 0) - scale * mean
+            out = S * scale + deg * shift
+        ctx.adj, ctx.act, ctx.training, ctx.E = adj, code, stats is None, E
+        ctx.has_affine = gamma is not None
+        ctx.save_for_backward(P, Q, S, deg, mean.contiguous(), rstd.contiguous(), scale.contiguous())
+        ctx.mark_non_differentiable(mean, var)
+        return out, mean, var
+
+    @staticmethod
+    def backward(ctx, g, _gm, _gv):
+        lib = _lib.load()
+        adj, code, E = ctx.adj, ctx.act, ctx.E
+        P, Q, S, deg, mean, rstd, scale = ctx.saved_tensors
+        g = _rows(g)
+        F, dev = P.size(1), P.device
+        gP = gQ = g_gamma = g_beta = None
+        with torch.cuda.device(dev):
+            sum_g = (deg * g).sum(0)                       # SUM_e G_e
+            sum_ga = (g * (S - deg * mean)).sum(0) * rstd  # SUM_e G_e ahat_e
+            if ctx.training:
+                c1, c2 = (sum_g / E).contiguous(), (sum_ga / E).contiguous()
+            else:
+                c1 = c2 = torch.zeros(F, dtype=torch.float32, device=dev)
+            for want, plan, A, B, n_rows in ((ctx.needs_input_grad[0], adj.by_src, P, Q, adj.n_src),
+                                             (ctx.needs_input_grad[1], adj.by_cob, Q, P, adj.n_cob)):
+                if not want:
+                    continue
+                gA = torch.empty_like(A, memory_format=torch.contiguous_format)
+                algo = 24 * E + 4 * F * (g.size(0) + 2 * A.size(0) + B.size(0))
+                _call('cin_msg_bwd', algo, lib.cwn_cin_msg_bwd_f32, _ptr(g), _ld(g), _ptr(A), _ld(A), _ptr(B), _ld(B),
+                      plan.rowptr.data_ptr(), _ptr(plan.pay0), _ptr(plan.pay1), n_rows, F, code, _ptr(scale), _ptr(mean),
+                      _ptr(rstd), _ptr(c1), _ptr(c2), _ptr(gA), F, _stream())
+                if A is P:
+                    gP = gA
+                else:
+                    gQ = gA
+            if ctx.has_affine:
+                g_gamma = sum_ga if ctx.needs_input_grad[2] else None
+                g_beta = sum_g if ctx.needs_input_grad[3] else None
+        return gP, gQ, g_gamma, g_beta, None, None, None, None
+
+
+def cin_message_pass(P: Tensor, Q: Tensor, index: Tensor, att: Tensor, n_dst: int, act: str, bn=None) -> Tensor:
+    """SUM over the messages into each destination of BN(act(P[src] + Q[att])), BatchNorm over the MESSAGE population
+    (`bn`: torch BatchNorm1d or None; its running statistics are updated in training mode as torch does)."""
+    if act not in ACT_CODES:
+        raise ValueError(f'cwn_b200: unknown activation {act!r}')
+    P, Q = _rows(P), _rows(Q)
+    _require_cuda_f32(P, 'P')
+    _require_cuda_f32(Q, 'Q')
+    adj = Adjacency.of(index, P.size(0), n_dst, att, Q.size(0))
+    if bn is None:
+        return _CobPass.apply(P, Q, None, None, adj, act)
+    use_batch = bn.training or not bn.track_running_stats
+    stats = None if use_batch else (bn.running_mean, bn.running_var)
+    out, mean, var = _CinMsgPass.apply(P, Q, bn.weight, bn.bias, adj, act, float(bn.eps), stats)
+    if bn.training and bn.track_running_stats:
+        with torch.no_grad():
+            E = adj.E
+            bn.num_batches_tracked += 1
+            m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+            bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
+            bn.running_var.mul_(1 - m).add_(var * (E / max(E - 1, 1)), alpha=m)
+    return out
+
+
 def _rows_grad_plan(idx, n):
     """(plan, split) for the gradient of `x[idx]` w.r.t. x: rows of x grouped by `idx`. Few, very long rows (an embedding
     table): one thread group per row would serialise, so every row is split into `split` interleaved sub-rows (a

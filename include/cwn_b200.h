@@ -153,6 +153,25 @@ int cwn_csr_cob_bwd_f32(const float* G, int64_t ld_g, const float* A, int64_t ld
                         int32_t act, float* gA, int64_t ld_ga, cwn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * K5 — message MLP of the dense CIN layers with BatchNorm over the MESSAGE population (reference mp/layers.py:94-103,
+ * nets mp/models.py:40-47: Linear(2F -> F), act, BatchNorm1d). With the Linear in split-weight form (P, Q as in
+ * cwn_csr_cob_fwd_f32) a message is a_e = act(P[src_e] + Q[att_e]) and its BatchNorm is affine, so
+ *   out[t] = scale * S[t] + deg(t) * (beta - scale * mean),  S = cwn_csr_cob_fwd_f32 without residual,
+ * and only the statistics and the backward need message-level passes of their own:
+ *   cwn_cin_msg_sq_f32 : out[t,:] = SUM_{i in row t} (act(P[src[i]] + Q[att[i]]) - mu)^2      (var = colsum / E)
+ *   cwn_cin_msg_bwd_f32: gA[r,:]  = SUM_{i in row r} scale (G[dst[i]] - c1 - ahat_i c2) act'(A[r] + B[oth[i]]),
+ *                        ahat_i = (act(A[r] + B[oth[i]]) - mu) rstd — the BatchNorm backward over the messages folded
+ *                        into the gradient of one gathered operand (by-source plan for P, by-attribute plan for Q).
+ * mu, scale (= gamma * rstd), rstd, c1, c2: DEVICE vectors [F]. No [E, F] tensor is ever materialised. */
+int cwn_cin_msg_sq_f32(const float* P, int64_t ld_p, const float* Q, int64_t ld_q, const int32_t* rowptr,
+                       const int32_t* src, const int32_t* att, int64_t n_rows, int32_t F, int32_t act, const float* mu,
+                       float* out, int64_t ld_out, cwn_stream_t stream);
+int cwn_cin_msg_bwd_f32(const float* G, int64_t ld_g, const float* A, int64_t ld_a, const float* B, int64_t ld_b,
+                        const int32_t* rowptr, const int32_t* dst, const int32_t* oth, int64_t n_rows, int32_t F,
+                        int32_t act, const float* scale, const float* mu, const float* rstd, const float* c1,
+                        const float* c2, float* gA, int64_t ld_ga, cwn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Dense update / combine nets of SparseCINConv (reference mp/layers.py:191-199, 303-325):
  *   Linear -> BatchNorm -> act -> Linear -> BatchNorm -> act  (x2 branches),  Linear(2H->H) -> BatchNorm -> act.
  * One "unit" is  z = f_in(X) W^T + b  followed by BatchNorm statistics over the rows, where the input transform

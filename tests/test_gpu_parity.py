@@ -680,6 +680,41 @@ def test_ragged_batches_replay_through_one_cuda_graph():
     assert step.fallbacks == 1
 
 
+@pytest.mark.parametrize('F,act,training', [(64, 'relu', True), (20, 'elu', True), (3, 'tanh', True), (16, 'relu', False)])
+def test_cin_message_pass_equals_messages_through_torch(F, act, training):
+    """K5 (csrc/cin_msg.cu, ops.cin_message_pass): SUM over the messages of BN(act(P[src] + Q[att])) with BatchNorm over
+    the MESSAGE population, against the same thing through materialised [E, F] messages and torch.nn.BatchNorm1d
+    (what the reference's CINCochainConv does, mp/layers.py:94-103): output, gradients of P, Q, gamma, beta, and the
+    running statistics; training and eval mode."""
+    n_src, n_att, n_dst, E = 300, 120, 260, 1500
+    idx, att = _rand_adj(n_src, n_dst, E, 31, n_cob=n_att)
+    g = torch.Generator().manual_seed(5)
+    P0, Q0 = torch.randn(n_src, F, generator=g), torch.randn(n_att, F, generator=g)
+    G = torch.randn(n_dst, F, generator=g)
+    bn_ref, bn_gpu = torch.nn.BatchNorm1d(F), torch.nn.BatchNorm1d(F).to(DEV)
+    with torch.no_grad():
+        bn_ref.weight.uniform_(0.5, 1.5, generator=g), bn_ref.bias.normal_(generator=g)
+        bn_ref.running_mean.normal_(generator=g), bn_ref.running_var.uniform_(0.5, 2.0, generator=g)
+    bn_gpu.load_state_dict(bn_ref.state_dict())
+    bn_ref.train(training), bn_gpu.train(training)
+    P, Q = P0.clone().requires_grad_(True), Q0.clone().requires_grad_(True)
+    msg = bn_ref(O._ACT[act](P.index_select(0, idx[0]) + Q.index_select(0, att)))
+    ref = O.scatter(msg, idx[1], n_dst)
+    (ref * G).sum().backward()
+    Pg, Qg = P0.to(DEV).requires_grad_(True), Q0.to(DEV).requires_grad_(True)
+    out = ops.cin_message_pass(Pg, Qg, idx.to(DEV), att.to(DEV), n_dst, act, bn_gpu)
+    (out * G.to(DEV)).sum().backward()
+    assert_close(out, ref, rtol=1e-5, atol=2e-5, what='out')
+    assert_close(Pg.grad, P.grad, rtol=1e-4, atol=5e-5, what='grad P')
+    assert_close(Qg.grad, Q.grad, rtol=1e-4, atol=1e-4, what='grad Q')
+    scale = float(bn_ref.weight.grad.abs().max())
+    assert_close(bn_gpu.weight.grad, bn_ref.weight.grad, rtol=1e-4, atol=1e-5 * max(scale, 1.0), what='grad gamma')
+    assert_close(bn_gpu.bias.grad, bn_ref.bias.grad, rtol=1e-4, atol=1e-4, what='grad beta')
+    assert_close(bn_gpu.running_mean, bn_ref.running_mean, rtol=1e-5, atol=1e-6, what='running mean')
+    assert_close(bn_gpu.running_var, bn_ref.running_var, rtol=1e-5, atol=1e-6, what='running var')
+    assert int(bn_gpu.num_batches_tracked) == int(bn_ref.num_batches_tracked)
+
+
 @pytest.mark.parametrize('layer_dim,hidden,act,norm,cob', [(64, 64, 'elu', 'bn', True), (16, 32, 'tanh', 'bn', False),
                                                            (8, 16, 'relu', 'id', True)])
 def test_fused_cinpp_layer_equals_torch_modules(layer_dim, hidden, act, norm, cob):
