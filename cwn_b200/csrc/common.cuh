@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <atomic>
+#include <stdlib.h>
+#include <utility>
 #include "../../include/cwn_b200.h"
 
 namespace cwn {
@@ -28,6 +30,37 @@ inline int cuda_status(cudaError_t e, const char* what) {
 inline int launched(const char* what, unsigned n = 1) {
   g_launches.fetch_add(n, std::memory_order_relaxed);
   return cuda_status(cudaGetLastError(), what);
+}
+
+// ---- programmatic dependent launch (PDL). At the real-data shape the step is a chain of ~70 dependent launches of a
+// few microseconds each; between two kernel nodes of a CUDA graph the GPU idles ~1.5-2 us (launch latency + the next
+// kernel's prologue). A kernel launched with the programmatic-serialization attribute may start as soon as every CTA of
+// its stream predecessor has called pdl_trigger() (or exited): its prologue (descriptor staging, mbarrier / TMEM setup)
+// then overlaps the predecessor's tail, and pdl_wait() blocks until the predecessor grid has completed and its writes
+// are visible. Contract: a kernel launched through launch_pdl() calls pdl_wait() before its first access to global
+// memory (reads AND writes: the predecessor may still be reading what this kernel overwrites). Both calls are no-ops in
+// a kernel launched the ordinary way. CWN_B200_PDL=0 launches everything the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* v = getenv("CWN_B200_PDL"); return !(v && v[0] == '0'); }();
+  return on;
+}
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

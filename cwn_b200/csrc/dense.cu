@@ -956,6 +956,8 @@ __global__ void __launch_bounds__(DT) bn_finalize_kernel(const __grid_constant__
 constexpr int kBnActV4 = 512;  // float4 elements per CTA on the vector path
 template <int ACT>
 __global__ void __launch_bounds__(DT) bn_act_kernel(const __grid_constant__ Group<cwn_bn_act_desc> g, int vec) {
+  pdl_trigger();
+  pdl_wait();
   const int p = find_problem(g, blockIdx.x);
   const cwn_bn_act_desc& d = g.d[p];
   if (vec) {
@@ -1104,6 +1106,8 @@ template <int TR, int A_OUT>
 __global__ void __launch_bounds__(DT) unit_bwd_reduce_fast_kernel(const __grid_constant__ Group<cwn_unit_bwd_desc> g) {
   __shared__ __align__(16) float part[2 * 4 * DT];   // [2][RG][h], RG * h = 4 DT
   __shared__ __align__(16) float stage[6 * DT];      // merge scratch of the last CTA
+  pdl_trigger();
+  pdl_wait();
   const int p = find_problem(g, blockIdx.x);
   const cwn_unit_bwd_desc& d = g.d[p];
   const int tile = blockIdx.x - g.start[p];
@@ -1631,6 +1635,8 @@ __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_fast_kernel(con
 // thread (u, sg) sums slabs sg, sg + 4, ... with batched 128-bit loads, the four group sums are combined in order.
 // (One thread per element walking ~100 slabs with scalar loads was 8-9 us per launch.)
 __global__ void __launch_bounds__(DT) wgrad_finalize_kernel(const __grid_constant__ Group<cwn_unit_bwd_desc> g, int vec) {
+  pdl_trigger();
+  pdl_wait();
   const int p = find_problem(g, blockIdx.x);
   const cwn_unit_bwd_desc& d = g.d[p];
   const int K = d.k0 + d.k1;
@@ -1783,7 +1789,7 @@ extern "C" int cwn_linear_fwd_grouped(const cwn_linear_desc* descs, int32_t n, c
 #define CWN_LAUNCH_T5(AV)                                                                                            \
   {                                                                                                                  \
     if ((rc = ensure_smem(linear_fwd_tc5_kernel<AV>, smem5, "cudaFuncSetAttribute(linear_fwd_tc5_kernel)"))) return rc; \
-    linear_fwd_tc5_kernel<AV><<<total5, T5T, smem5, (cudaStream_t)stream>>>(g);                                      \
+    if ((rc = cuda_status(launch_pdl(linear_fwd_tc5_kernel<AV>, total5, T5T, smem5, (cudaStream_t)stream, g), "linear_fwd_tc5_kernel"))) return rc; \
   }
       if (a_in == CWN_ACT_ID) CWN_LAUNCH_T5(CWN_ACT_ID)
       else if (a_in == CWN_ACT_RELU) CWN_LAUNCH_T5(CWN_ACT_RELU)
@@ -1888,9 +1894,11 @@ extern "C" int cwn_bn_act_grouped(const cwn_bn_act_desc* descs, int32_t n, cwn_s
   g.start[n] = total;
   if (total == 0) return CWN_OK;
   const int act = group_act(descs, n, [](const cwn_bn_act_desc& d) { return d.act; });
-  if (act == CWN_ACT_ID) bn_act_kernel<CWN_ACT_ID><<<total, DT, 0, (cudaStream_t)stream>>>(g, (int)vec);
-  else if (act == CWN_ACT_RELU) bn_act_kernel<CWN_ACT_RELU><<<total, DT, 0, (cudaStream_t)stream>>>(g, (int)vec);
-  else bn_act_kernel<kActRuntime><<<total, DT, 0, (cudaStream_t)stream>>>(g, (int)vec);
+  cudaError_t err;
+  if (act == CWN_ACT_ID) err = launch_pdl(bn_act_kernel<CWN_ACT_ID>, total, DT, 0, (cudaStream_t)stream, g, (int)vec);
+  else if (act == CWN_ACT_RELU) err = launch_pdl(bn_act_kernel<CWN_ACT_RELU>, total, DT, 0, (cudaStream_t)stream, g, (int)vec);
+  else err = launch_pdl(bn_act_kernel<kActRuntime>, total, DT, 0, (cudaStream_t)stream, g, (int)vec);
+  if ((rc = cuda_status(err, "bn_act_kernel"))) return rc;
   return launched("bn_act_kernel");
 }
 
@@ -1932,9 +1940,13 @@ extern "C" int cwn_unit_bwd_reduce_grouped(const cwn_unit_bwd_desc* descs, int32
   }
   if (fast) {
 #define CWN_REDF(TRV)                                                                                              \
-  if (a_out == CWN_ACT_ID) unit_bwd_reduce_fast_kernel<TRV, CWN_ACT_ID><<<total, DT, 0, (cudaStream_t)stream>>>(g);    \
-  else if (a_out == CWN_ACT_RELU) unit_bwd_reduce_fast_kernel<TRV, CWN_ACT_RELU><<<total, DT, 0, (cudaStream_t)stream>>>(g); \
-  else unit_bwd_reduce_fast_kernel<TRV, kActRuntime><<<total, DT, 0, (cudaStream_t)stream>>>(g);
+  {                                                                                                                \
+    cudaError_t err;                                                                                               \
+    if (a_out == CWN_ACT_ID) err = launch_pdl(unit_bwd_reduce_fast_kernel<TRV, CWN_ACT_ID>, total, DT, 0, (cudaStream_t)stream, g); \
+    else if (a_out == CWN_ACT_RELU) err = launch_pdl(unit_bwd_reduce_fast_kernel<TRV, CWN_ACT_RELU>, total, DT, 0, (cudaStream_t)stream, g); \
+    else err = launch_pdl(unit_bwd_reduce_fast_kernel<TRV, kActRuntime>, total, DT, 0, (cudaStream_t)stream, g);   \
+    if ((rc = cuda_status(err, "unit_bwd_reduce_fast_kernel"))) return rc;                                         \
+  }
     if (tr == 64) { CWN_REDF(64) } else { CWN_REDF(32) }
 #undef CWN_REDF
     return launched("unit_bwd_reduce_fast_kernel");
@@ -1989,7 +2001,7 @@ extern "C" int cwn_unit_bwd_grouped(const cwn_unit_bwd_desc* descs, int32_t n, c
 #define CWN_LAUNCH_T5B(AI, AO)                                                                                            \
   {                                                                                                                       \
     if ((rc = ensure_smem(unit_bwd_tc5_kernel<AI, AO>, smem5, "cudaFuncSetAttribute(unit_bwd_tc5_kernel)"))) return rc;   \
-    unit_bwd_tc5_kernel<AI, AO><<<total, T5T, smem5, (cudaStream_t)stream>>>(g);                                          \
+    if ((rc = cuda_status(launch_pdl(unit_bwd_tc5_kernel<AI, AO>, total, T5T, smem5, (cudaStream_t)stream, g), "unit_bwd_tc5_kernel"))) return rc; \
   }
 #define CWN_T5B_BY_OUT(AI)                                        \
   if (a_out == CWN_ACT_ID) CWN_LAUNCH_T5B(AI, CWN_ACT_ID)         \
@@ -2097,6 +2109,6 @@ extern "C" int cwn_wgrad_finalize_grouped(const cwn_unit_bwd_desc* descs, int32_
   }
   g.start[n] = total;
   if (total == 0) return CWN_OK;
-  wgrad_finalize_kernel<<<total, DT, 0, (cudaStream_t)stream>>>(g, (int)vec);
+  if ((rc = cuda_status(launch_pdl(wgrad_finalize_kernel, total, DT, 0, (cudaStream_t)stream, g, (int)vec), "wgrad_finalize_kernel"))) return rc;
   return launched("wgrad_finalize_kernel");
 }

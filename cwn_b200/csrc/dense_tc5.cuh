@@ -184,6 +184,8 @@ __global__ void __launch_bounds__(T5T, 2) linear_fwd_tc5_kernel(const __grid_con
   const int p = find_problem(g, blockIdx.x);
   if (tid == 0) { tc5::mbar_init(&bar, 1); tc5::mbar_fence_init(); }
   const cwn_linear_desc d = stage_desc(g, p, &sd);  // (contains the CTA barrier that publishes the mbarrier init)
+  pdl_trigger();  // the next kernel of the stream may start its prologue
+  pdl_wait();     // ... and this one goes no further until its predecessor has completed (common.cuh)
   CWN_PHASE(1);
   const int rt = blockIdx.x - g.start[p];
   const int K = d.k0 + d.k1, K4 = K >> 2, h = d.h;
@@ -354,6 +356,8 @@ __global__ void __launch_bounds__(T5T, 1) unit_bwd_tc5_kernel(const __grid_const
   const int p = find_problem(g, blockIdx.x);
   if (tid == 0) { tc5::mbar_init(&bar, 1); tc5::mbar_fence_init(); }
   const cwn_unit_bwd_desc d = stage_desc(g, p, &sd);
+  pdl_trigger();
+  pdl_wait();
   CWN_PHASE(1);
   const int j = blockIdx.x - g.start[p];
   const int K = d.k0 + d.k1, K4 = K >> 2, h = d.h, h4 = h >> 2;

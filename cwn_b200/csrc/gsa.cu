@@ -217,6 +217,8 @@ csr_gather_reduce_kernel(const float* __restrict__ x_src, int64_t ld_src, const 
                          const float* __restrict__ x_res, int64_t ld_res, const float* __restrict__ eps,
                          float* __restrict__ out, int64_t ld_out, const float* __restrict__ x_res2 = nullptr,
                          int64_t ld_res2 = 0, const float* __restrict__ eps2 = nullptr) {
+  pdl_trigger();  // programmatic dependent launch: see common.cuh
+  pdl_wait();
   using O = VecOps<V>;
   constexpr int RPB = kThreads / LPR;
   const int lane = threadIdx.x % LPR;
@@ -343,6 +345,8 @@ csr_cob_fwd_kernel(const float* __restrict__ P, int64_t ld_p, const float* __res
                    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src,
                    const int32_t* __restrict__ cob, int64_t n_rows, int FV, const float* __restrict__ x_res,
                    int64_t ld_res, const float* __restrict__ eps, float* __restrict__ out, int64_t ld_out) {
+  pdl_trigger();  // programmatic dependent launch: see common.cuh
+  pdl_wait();
   using O = VecOps<V>;
   constexpr int RPB = kThreads / LPR;
   constexpr int U = (VPL == 1) ? 4 : 2;  // two operands per message: 2*U*VPL gathers in flight
@@ -384,6 +388,8 @@ csr_cob_bwd_kernel(const float* __restrict__ G, int64_t ld_g, const float* __res
                    const float* __restrict__ B, int64_t ld_b, const int32_t* __restrict__ rowptr,
                    const int32_t* __restrict__ dst, const int32_t* __restrict__ oth, int64_t n_rows, int FV,
                    float* __restrict__ gA, int64_t ld_ga) {
+  pdl_trigger();  // programmatic dependent launch: see common.cuh
+  pdl_wait();
   using O = VecOps<V>;
   constexpr int RPB = kThreads / LPR;
   constexpr int U = (VPL == 1) ? 4 : 2;
@@ -424,6 +430,8 @@ template <typename V, int LPR>
 __global__ void __launch_bounds__(kThreads)
 gather_rows_kernel(const float* __restrict__ x, int64_t ld_x, const int64_t* __restrict__ idx, int64_t E, int FV,
                    float scale, float* __restrict__ out, int64_t ld_out) {
+  pdl_trigger();  // programmatic dependent launch: see common.cuh
+  pdl_wait();
   using O = VecOps<V>;
   constexpr int RPB = kThreads / LPR;
   const int lane = threadIdx.x % LPR;
@@ -644,8 +652,8 @@ extern "C" int cwn_csr_gather_reduce_f32(const float* x_src, int64_t ld_src, con
   const int grid = grid_for(n_rows, g.lpr);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(VT, VPLV, RED)                                                                                   \
-  csr_gather_reduce_kernel<VT, LPR, VPLV, RED><<<grid, kThreads, 0, st>>>(x_src, ld_src, rowptr, idx, n_rows, g.fv, \
-                                                                           x_res, ld_res, eps, out, ld_out)
+  launch_pdl((csr_gather_reduce_kernel<VT, LPR, VPLV, RED>), grid, kThreads, 0, st, x_src, ld_src, rowptr, idx, n_rows, \
+             g.fv, x_res, ld_res, eps, out, ld_out, (const float*)nullptr, (int64_t)0, (const float*)nullptr)
 #define BY_REDUCE(VT, VPLV)                                              \
   if (reduce == CWN_REDUCE_ADD) LAUNCH(VT, VPLV, CWN_REDUCE_ADD);        \
   else if (reduce == CWN_REDUCE_MEAN) LAUNCH(VT, VPLV, CWN_REDUCE_MEAN); \
@@ -751,8 +759,8 @@ extern "C" int cwn_csr_gather_reduce2_f32(const float* x_src, int64_t ld_src, co
   const int grid = grid_for(n_rows, g.lpr);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(VT, VPLV)                                                                                               \
-  csr_gather_reduce_kernel<VT, LPR, VPLV, CWN_REDUCE_ADD><<<grid, kThreads, 0, st>>>(                                    \
-      x_src, ld_src, rowptr, idx, n_rows, g.fv, x_res, ld_res, eps, out, ld_out, x_res2, ld_res2, eps2)
+  launch_pdl((csr_gather_reduce_kernel<VT, LPR, VPLV, CWN_REDUCE_ADD>), grid, kThreads, 0, st,                          \
+             x_src, ld_src, rowptr, idx, n_rows, g.fv, x_res, ld_res, eps, out, ld_out, x_res2, ld_res2, eps2)
   if (g.vec) {
     if (g.vpl == 1) { CWN_DISPATCH_LPR(g.lpr, LAUNCH(float4, 1)) } else { constexpr int LPR = 32; LAUNCH(float4, 2); }
   } else {
@@ -805,9 +813,9 @@ extern "C" int cwn_gather_rows_f32(const float* x, int64_t ld_x, const int64_t* 
   const int grid = grid_for(E, g.lpr);
   cudaStream_t st = (cudaStream_t)stream;
   if (g.vec) {
-    CWN_DISPATCH_LPR(g.lpr, gather_rows_kernel<float4, LPR><<<grid, kThreads, 0, st>>>(x, ld_x, idx, E, g.fv, scale, out, ld_out))
+    CWN_DISPATCH_LPR(g.lpr, launch_pdl((gather_rows_kernel<float4, LPR>), grid, kThreads, 0, st, x, ld_x, idx, E, g.fv, scale, out, ld_out))
   } else {
-    CWN_DISPATCH_LPR(g.lpr, gather_rows_kernel<float, LPR><<<grid, kThreads, 0, st>>>(x, ld_x, idx, E, g.fv, scale, out, ld_out))
+    CWN_DISPATCH_LPR(g.lpr, launch_pdl((gather_rows_kernel<float, LPR>), grid, kThreads, 0, st, x, ld_x, idx, E, g.fv, scale, out, ld_out))
   }
   return launched("cwn_gather_rows_f32");
 }
@@ -829,7 +837,7 @@ extern "C" int cwn_csr_cob_fwd_f32(const float* P, int64_t ld_p, const float* Q,
   const int grid = grid_for(n_rows, g.lpr);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(VT, VPLV)                                                                                           \
-  CWN_DISPATCH_ACT(act, csr_cob_fwd_kernel<VT, LPR, VPLV, ACT><<<grid, kThreads, 0, st>>>(                           \
+  CWN_DISPATCH_ACT(act, launch_pdl((csr_cob_fwd_kernel<VT, LPR, VPLV, ACT>), grid, kThreads, 0, st,                  \
                             P, ld_p, Q, ld_q, rowptr, src, cob, n_rows, g.fv, x_res, ld_res, eps, out, ld_out))
   // (a chunked variant like csr_gather_reduce_chunked_kernel was measured SLOWER for the two-operand passes —
   //  0.38 vs 0.40 of the HBM peak forward, 0.41 vs 0.53 backward at 1M rows, 80 registers — and was removed)
@@ -896,7 +904,7 @@ extern "C" int cwn_csr_cob_bwd_f32(const float* G, int64_t ld_g, const float* A,
   const int grid = grid_for(n_rows, g.lpr);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(VT, VPLV)                                                                  \
-  CWN_DISPATCH_ACT(act, csr_cob_bwd_kernel<VT, LPR, VPLV, ACT><<<grid, kThreads, 0, st>>>(  \
+  CWN_DISPATCH_ACT(act, launch_pdl((csr_cob_bwd_kernel<VT, LPR, VPLV, ACT>), grid, kThreads, 0, st, \
                             G, ld_g, A, ld_a, B, ld_b, rowptr, dst, oth, n_rows, g.fv, gA, ld_ga))
   const bool tiled = g.vec && g.lpr >= 4 && G && B && n_rows >= kTiledMinRows && aligned16(rowptr) && aligned16(dst) &&
                      aligned16(oth) && g.fv <= g.lpr * g.vpl && tiled_enabled();

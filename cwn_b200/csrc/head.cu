@@ -25,6 +25,8 @@ __global__ void __launch_bounds__(kHeadThreads)
 head_fwd_kernel(const __grid_constant__ HeadDims dims, int n_dims, int K, int H2, int out_size, int pool_mean,
                 int final_mean, const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ h_out,
                 float* __restrict__ out) {
+  pdl_trigger();  // programmatic dependent launch: see common.cuh
+  pdl_wait();
   extern __shared__ float sm[];  // pooled[n_dims][K] | h[H2]
   float* s_pooled = sm;
   float* s_h = sm + n_dims * K;
@@ -90,6 +92,8 @@ template <int ACT>
 __global__ void __launch_bounds__(kHeadThreads)
 head_bwd_input_kernel(const __grid_constant__ HeadDims dims, int n_dims, int K, int H2, int out_size, int pool_mean,
                       int final_mean, const float* __restrict__ w2, const float* __restrict__ g_out) {
+  pdl_trigger();  // programmatic dependent launch: see common.cuh
+  pdl_wait();
   extern __shared__ float sm[];  // g_z[n_dims][H2]
   const int b = blockIdx.x;
   for (int j = threadIdx.x; j < H2; j += kHeadThreads) {
@@ -125,6 +129,8 @@ __global__ void __launch_bounds__(kHeadThreads)
 head_bwd_param_kernel(const __grid_constant__ HeadDims dims, int n_dims, int64_t B, int K, int H2, int out_size,
                       const float* __restrict__ h, const float* __restrict__ g_out, float* __restrict__ g_w2,
                       float* __restrict__ g_b2, int accumulate_out) {
+  pdl_trigger();  // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int64_t per_dim = (int64_t)H2 * K + H2;
   const int64_t total = per_dim * n_dims + (int64_t)out_size * H2 + out_size;
   for (int64_t e = (int64_t)blockIdx.x * kHeadThreads + threadIdx.x; e < total; e += (int64_t)gridDim.x * kHeadThreads) {
@@ -204,7 +210,7 @@ extern "C" int cwn_readout_head_fwd(const cwn_head_dim* dims, int32_t n_dims, in
   cudaStream_t st = (cudaStream_t)stream;
   CWN_HEAD_BY_ACT(act, {
     if (smem > 48 * 1024) cudaFuncSetAttribute(head_fwd_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    head_fwd_kernel<ACT><<<(int)B, kHeadThreads, smem, st>>>(hd, n_dims, K, H2, out_size, pool_mean, final_mean, w2, b2, h, out);
+    launch_pdl(head_fwd_kernel<ACT>, (int)B, kHeadThreads, smem, st, hd, n_dims, K, H2, out_size, pool_mean, final_mean, w2, b2, h, out);
   })
   return launched("cwn_readout_head_fwd");
 }
@@ -228,11 +234,11 @@ extern "C" int cwn_readout_head_bwd(const cwn_head_dim* dims, int32_t n_dims, in
   CWN_HEAD_BY_ACT(act, {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(head_bwd_input_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    head_bwd_input_kernel<ACT><<<(int)B, kHeadThreads, smem, st>>>(hd, n_dims, K, H2, out_size, pool_mean, final_mean, w2, g_out);
+    launch_pdl(head_bwd_input_kernel<ACT>, (int)B, kHeadThreads, smem, st, hd, n_dims, K, H2, out_size, pool_mean, final_mean, w2, g_out);
   })
   const int64_t total = ((int64_t)H2 * K + H2) * n_dims + (int64_t)out_size * H2 + out_size;
   int64_t grid = (total + kHeadThreads - 1) / kHeadThreads;
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-  head_bwd_param_kernel<<<(int)grid, kHeadThreads, 0, st>>>(hd, n_dims, B, K, H2, out_size, h, g_out, g_w2, g_b2, accumulate_out);
+  launch_pdl(head_bwd_param_kernel, (int)grid, kHeadThreads, 0, st, hd, n_dims, B, K, H2, out_size, h, g_out, g_w2, g_b2, accumulate_out);
   return launched("cwn_readout_head_bwd", 2);
 }

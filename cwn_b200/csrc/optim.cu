@@ -12,6 +12,8 @@ namespace cwn {
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
             float b1, float b2, float eps, float wd, int32_t* step, int32_t* counter, int zero_grad) {
+  pdl_trigger();  // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int t = *reinterpret_cast<volatile int32_t*>(step) + 1;
   const float bc1 = (float)(1.0 - pow((double)b1, (double)t));
   const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, (double)t));
@@ -50,7 +52,7 @@ extern "C" int cwn_adam_step_f32(float* param, float* grad, float* exp_avg, floa
   if (!param || !grad || !exp_avg || !exp_avg_sq || !step || !counter) return fail(CWN_E_NULL, "cwn_adam_step_f32");
   int64_t blocks = (n + 255) / 256;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+  launch_pdl(adam_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                              weight_decay, step, counter, zero_grad);
   return launched("adam_kernel");
 }

@@ -75,6 +75,8 @@ struct PlanBatch {
 template <int kSmallItems>
 __global__ void __launch_bounds__(kSmallThreads)
 small_plans_kernel(const __grid_constant__ PlanBatch batch, int32_t* flags) {
+  pdl_trigger();  // programmatic dependent launch: see common.cuh
+  pdl_wait();
   using Sort = cub::BlockRadixSort<int32_t, kSmallThreads, kSmallItems, int32_t>;
   extern __shared__ __align__(16) unsigned char smem[];
   typename Sort::TempStorage& temp = *reinterpret_cast<typename Sort::TempStorage*>(smem);
@@ -222,9 +224,9 @@ extern "C" int cwn_csr_plan_build_small(const cwn_plan_desc* descs, int32_t n_pl
     int64_t max_e = 0;
     for (int i = 0; i < n; ++i) max_e = batch.d[i].E > max_e ? batch.d[i].E : max_e;
     if (max_e <= kSmallThreads * kSmallItemsMin)
-      small_plans_kernel<kSmallItemsMin><<<n, kSmallThreads, smem_min, (cudaStream_t)stream>>>(batch, flags);
+      launch_pdl(small_plans_kernel<kSmallItemsMin>, n, kSmallThreads, smem_min, (cudaStream_t)stream, batch, flags);
     else
-      small_plans_kernel<kSmallItemsMax><<<n, kSmallThreads, smem_max, (cudaStream_t)stream>>>(batch, flags);
+      launch_pdl(small_plans_kernel<kSmallItemsMax>, n, kSmallThreads, smem_max, (cudaStream_t)stream, batch, flags);
     int rc = launched("small_plans_kernel");
     if (rc) return rc;
   }

@@ -15,6 +15,7 @@ contract, re-expressed without torch_sparse and designed around a device-residen
 Host-side plumbing only: nothing here launches a message-passing kernel.
 """
 import copy
+import os
 import logging
 from typing import Dict, List, Optional, Sequence
 
@@ -25,6 +26,9 @@ from cwn_b200.mp.params import CochainMessagePassingParams, LazyRows
 
 # key -> which neighbouring cell count offsets it when cochains are concatenated (reference `__inc__`, :148-169)
 _INDEX_KEYS = ('upper_index', 'lower_index', 'shared_boundaries', 'shared_coboundaries', 'boundary_index')
+
+
+_CHECK_INDICES = os.environ.get('CWN_B200_CHECK_INDICES', '1') != '0'
 
 
 class Cochain(object):
@@ -422,6 +426,8 @@ class Complex(object):
         device = torch.device(device)
         slots = self._slots()
         packable = device.type == 'cuda' and not kwargs and all(t.device.type == 'cpu' for _, _, t in slots)
+        if packable and _CHECK_INDICES:
+            self.check_indices()
         if not packable:
             for owner, key, t in slots:
                 self._rebind(owner, key, t.to(device, **kwargs))
@@ -438,6 +444,26 @@ class Complex(object):
                 n *= sdim
             self._rebind(by_key[(dim, key)], key, dev_flat[dtype][off:off + n].view(shape))
         self._flat = dev_flat
+        return self
+
+    def check_indices(self):
+        """Every index of every adjacency points at an existing cell. The kernels read `x[idx]` unchecked (the reference
+        relies on torch's device-side assert); this is the host-side equivalent, run once per batch while the tensors
+        are still on the CPU (`CWN_B200_CHECK_INDICES=0` turns it off)."""
+        for dim in range(self.dimension + 1):
+            c = self.cochains[dim]
+            n, n_up, n_down = c.num_cells or 0, c.num_cells_up or 0, c.num_cells_down or 0
+            checks = [('upper_index', c.upper_index, n), ('lower_index', c.lower_index, n),
+                      ('shared_coboundaries', c.shared_coboundaries, n_up), ('shared_boundaries', c.shared_boundaries, n_down)]
+            if c.boundary_index is not None and c.boundary_index.numel():
+                checks += [('boundary_index[0]', c.boundary_index[0], n_down), ('boundary_index[1]', c.boundary_index[1], n)]
+            for name, idx, bound in checks:
+                if idx is None or idx.numel() == 0 or idx.device.type != 'cpu':
+                    continue
+                lo, hi = int(idx.min()), int(idx.max())
+                if lo < 0 or hi >= bound:
+                    raise IndexError(f'cwn_b200: {name} of dimension {dim} has entries in [{lo}, {hi}], valid range is '
+                                     f'[0, {bound})')
         return self
 
     def get_cochain_params(self, dim: int, max_dim: int = 2, include_top_features=True,

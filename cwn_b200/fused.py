@@ -178,11 +178,13 @@ def _counters(device, n):
 def _direct_grad(p):
     """Gradient buffer to accumulate INTO (the parameter's pre-allocated `.grad`, e.g. a view of
     cwn_b200.dist.FlatGradBucket) or None. Writing there from the kernel replaces one AccumulateGrad elementwise
-    launch per parameter per step (~150 of them); autograd then receives no gradient for that input."""
+    launch per parameter per step (~150 of them); autograd then receives no gradient for that input — so
+    `torch.autograd.grad()` over such parameters returns None for them (and mutates `.grad`): set
+    `fused.DIRECT_PARAM_GRADS = False` (or keep `.grad` None) when a functional gradient is wanted."""
     g = p.grad
-    if DIRECT_PARAM_GRADS and g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.is_cuda \
-            and g.shape == p.shape:
-        return g
+    if DIRECT_PARAM_GRADS and p.requires_grad and g is not None and g.dtype == torch.float32 and g.is_contiguous() \
+            and g.is_cuda and g.shape == p.shape and not p._backward_hooks:
+        return g  # (frozen parameters and parameters with gradient hooks go through autograd as usual)
     return None
 
 

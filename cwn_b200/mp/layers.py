@@ -439,14 +439,22 @@ class SparseCINConv(_PerDimension):
     fuse_dense = True
     fuse_aggregation = True  # all aggregation passes of the layer as one autograd node (fused._LayerAggregate)
 
+    def _forms(self, fused):
+        """`fused.recognise` of every level, cached on the identity of the nets (replacing a net invalidates it)."""
+        key = tuple(id(m) for level in self.mp_levels
+                    for m in (level.update_up_nn, level.update_boundaries_nn, level.combine_nn,
+                              getattr(level, 'update_down_nn', None), level.msg_up_nn))
+        cached = getattr(self, '_dense_forms', None)
+        if cached is None or cached[0] != key:
+            cached = self._dense_forms = (key, [fused.recognise(level) for level in self.mp_levels])
+        return cached[1]
+
     def forward(self, *cochain_params: CochainMessagePassingParams, start_to_process=0):
         assert len(cochain_params) <= self.max_dim + 1
         n = len(cochain_params)
         if self.fuse_dense and start_to_process == 0 and n > 0:
             from cwn_b200 import fused
-            forms = getattr(self, '_dense_forms', None)
-            if forms is None:
-                forms = self._dense_forms = [fused.recognise(level) for level in self.mp_levels]
+            forms = self._forms(fused)
             if self.fuse_aggregation and all(f is not None for f in forms[:n]) and type(self) is SparseCINConv:
                 # every pass of the layer (+ the split-weight products) as one autograd node: see fused._LayerAggregate
                 agg = fused.layer_aggregate(self.mp_levels[:n], cochain_params)
@@ -483,6 +491,10 @@ class SparseCINConv(_PerDimension):
         super(SparseCINConv, self).__init__()
         self.max_dim = max_dim
         self.mp_levels = torch.nn.ModuleList()
+        # passed nets are the SAME objects for every dimension: their BatchNorm buffers must not be updated from
+        # concurrent streams (same rule as CINConv)
+        self.concurrent_dims = not any(net is not None for net in (passed_msg_up_nn, passed_msg_boundaries_nn,
+                                                                   passed_update_up_nn, passed_update_boundaries_nn))
 
         def update_mlp():
             return Sequential(Linear(kwargs['layer_dim'], kwargs['hidden']), graph_norm(kwargs['hidden']),
@@ -579,9 +591,7 @@ class CINppConv(SparseCINConv):
         assert n <= self.max_dim + 1
         if self.fuse_dense and self.fuse_aggregation and start_to_process == 0 and n > 0:
             from cwn_b200 import fused
-            forms = getattr(self, '_dense_forms', None)
-            if forms is None:
-                forms = self._dense_forms = [fused.recognise(level) for level in self.mp_levels]
+            forms = self._forms(fused)
             if all(f is not None and f[3] is not None for f in forms[:n]) and \
                     all(self.mp_levels[d].down_msg_size == cochain_params[d].x.size(1) for d in range(n)
                         if isinstance(cochain_params[d].x, Tensor) and cochain_params[d].x.dim() == 2):
@@ -610,6 +620,9 @@ class CINppConv(SparseCINConv):
                                         eps, train_eps, max_dim, graph_norm, use_coboundaries, **kwargs)
         self.max_dim = max_dim
         self.mp_levels = torch.nn.ModuleList()
+        self.concurrent_dims = not any(net is not None for net in (
+            passed_msg_up_nn, passed_msg_down_nn, passed_msg_boundaries_nn, passed_update_up_nn, passed_update_down_nn,
+            passed_update_boundaries_nn))
 
         def message_mlp():
             return Sequential(Catter(), Linear(kwargs['layer_dim'] * 2, kwargs['layer_dim']), kwargs['act_module']())

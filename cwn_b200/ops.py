@@ -664,6 +664,10 @@ def gather_scatter(x_src: Tensor, index: Tensor, n_dst: int, reduce: str = 'add'
     x_src = _rows(x_src)
     _require_cuda_f32(x_src, 'x_src')
     if x_res is not None:
+        if reduce not in ('add', 'sum'):
+            # (the kernel fuses the residual into an additive pass only; refusing here keeps the behaviour the same with
+            # and without autograd — the max path with gradients used to drop the residual silently)
+            raise ValueError("cwn_b200: a fused residual (x_res) requires reduce='add'")
         x_res = _rows(x_res)
         _require_cuda_f32(x_res, 'x_res')
         if x_res.size(0) != n_dst or x_res.size(1) != x_src.size(1):
