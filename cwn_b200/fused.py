@@ -219,6 +219,17 @@ def _algorithmic_flops(fn_name, d):
     return 0
 
 
+def _finalize_wgrads(descs, keep, dev):
+    """Ordered sums of the per-CTA weight-gradient partials -> dW, db. When every problem accumulates straight into a
+    pre-allocated `.grad` (the FlatGradBucket mode) nothing later in the backward pass reads the result, so the launch
+    goes to the deferred tail stream (joined when backward ends); gradients handed back to autograd stay in line."""
+    from cwn_b200.streams import run_deferred
+    if all(d.accumulate_w for d in descs):
+        run_deferred(lambda: _launch('cwn_wgrad_finalize_grouped', _lib.UnitBwdDesc, descs), (descs, list(keep)), dev)
+    else:
+        _launch('cwn_wgrad_finalize_grouped', _lib.UnitBwdDesc, descs)
+
+
 def _launch(fn_name, desc_type, descs):
     lib = _lib.load()
     fn = getattr(lib, fn_name)
@@ -457,7 +468,7 @@ class FusedSparseCINDense(Function):
             descs, gins1 = run(items)
             all_descs += descs
             g1 = {key: gi[0] for key, gi in zip(slot1, gins1)}
-            _launch('cwn_wgrad_finalize_grouped', _lib.UnitBwdDesc, all_descs)
+            _finalize_wgrads(all_descs, keep, dev)
 
         out = [None, None, None, None]
         for d in range(n_dims):
@@ -575,7 +586,7 @@ class GroupedLinear(Function):
                     gw_bufs[wi].data_ptr() + 4 * off, gw_bufs[wi].stride(0), _p(gb), accumulate, nr, h, None, tr))
                 gxs.append(gx)
             _launch('cwn_unit_bwd_grouped', _lib.UnitBwdDesc, descs)
-            _launch('cwn_wgrad_finalize_grouped', _lib.UnitBwdDesc, descs)
+            _finalize_wgrads(descs, keep + gw_bufs + gb_bufs, dev)
         return (None, None, *gxs, *gw_out, *gb_out)
 
 
@@ -879,7 +890,7 @@ class _LayerAggregate(Function):
                             None, tr, 1))
                     _launch('cwn_unit_bwd_grouped', _lib.UnitBwdDesc, descs)
                     all_descs += descs
-                _launch('cwn_wgrad_finalize_grouped', _lib.UnitBwdDesc, all_descs)
+                _finalize_wgrads(all_descs, keep + [b for pair in bufs for b in pair[:2]], dev)
             # trainable epsilons (train_eps=True): scalar reductions through torch
             g_eps = []
             for d in range(n):

@@ -58,3 +58,45 @@ def aux_stream(parent: torch.cuda.Stream) -> torch.cuda.Stream:
     if s is None:
         s = _aux[key] = torch.cuda.Stream(device=parent.device)
     return s
+
+
+# ---------------------------------------------------------------------------------------------- deferred tail work
+_tails, _pending = {}, {}
+
+
+def run_deferred(fn, keepalive, device):
+    """Run `fn()` (kernel launches) on a dedicated tail stream forked from the current one, and join it only when the
+    running BACKWARD pass ends (autograd's end-of-pass callback). For work nothing in the rest of the backward pass
+    reads — the ordered sums of the weight-gradient partials into `.grad`: issued in line they sat on the critical
+    path of every layer (two launches of 5-15 us each per layer), as a parallel branch they cost nothing.
+
+    `keepalive`: every tensor the launches touch; the references are dropped after the join, so the caching allocator
+    cannot hand their memory to a later kernel of the parent stream while the tail still reads it. Outside a backward
+    pass (or with CWN_B200_STREAMS=0) `fn` simply runs in line."""
+    if not ENABLED or torch.device(device).type != 'cuda':
+        fn()
+        return
+    engine = torch.autograd.Variable._execution_engine
+    parent = torch.cuda.current_stream(device)
+    key = (parent.device, parent.cuda_stream)
+    state = _pending.setdefault(key, {'keep': [], 'queued': False})
+    if not state['queued']:
+        def join(device=parent.device, key=key, state=state):
+            # (autograd runs end-of-pass callbacks on the stream backward() was called from, after it has been
+            # synchronised with the streams the pass used: that is the stream whoever reads `.grad` next will be on)
+            torch.cuda.current_stream(device).wait_stream(_tails[key])
+            state['keep'] = []
+            state['queued'] = False
+        try:
+            engine.queue_callback(join)
+        except RuntimeError:  # not inside a backward pass
+            fn()
+            return
+        state['queued'] = True
+    tail = _tails.get(key)
+    if tail is None:
+        tail = _tails[key] = torch.cuda.Stream(device=parent.device)
+    tail.wait_stream(parent)
+    with torch.cuda.stream(tail):
+        fn()
+    state['keep'].append(keepalive)
