@@ -277,6 +277,22 @@ def peaks():
     return 6650.0, 'fallback (B200_PROFILING.md: 6.65 TB/s)'
 
 
+class CleanL2Flush(object):
+    """Evict the previous iteration from L2 and leave the cache CLEAN: a 256 MB write (larger than the 126 MB L2) followed
+    by a 256 MB read of another buffer. After a write-only flush the L2 is full of dirty lines whose write-back (up to
+    126 MB = ~20 us of DRAM time) is charged to whatever kernel runs next — a quarter of a 100 us pass that is being
+    compared with a copy bandwidth measured over gigabytes."""
+
+    def __init__(self, dev):
+        self.w = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+        self.r = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+
+    def zero_(self):
+        self.w.zero_()
+        if not os.environ.get('CWN_BENCH_DIRTY_FLUSH'):  # A/B: what the write-only flush costs the next kernel
+            self.r.sum()
+
+
 def kernel_sweep(dev):
     """BASELINE config 5, one point: block-diagonal edge-upper adjacency at 1M edges/dim, F=64 — the regime where
     the HBM roofline is the bound. Algorithmic bytes per SURVEY 8(d)."""
@@ -284,8 +300,8 @@ def kernel_sweep(dev):
     from cwn_b200.data import synthetic
     peak, _ = peaks()
     out = []
-    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
-    for kind, F in [('edge_up', 64), ('edge_boundary', 64), ('edge_up', 256)]:
+    flush = CleanL2Flush(dev)
+    for kind, F in [('edge_up', 64), ('edge_boundary', 64), ('edge_up', 256), ('edge_up', 16)]:
         index, cob, n_src, n_dst, n_cob = synthetic.tiled_adjacency(kind, 40_000)
         index = index.to(dev)
         x = torch.randn(n_src, F, device=dev)
@@ -301,7 +317,7 @@ def kernel_sweep(dev):
         gbs = rec['bytes'] / (t * 1e-3) / 1e9
         out.append({'kernel': 'csr_gather_reduce', 'adjacency': kind, 'F': F, 'cells': n_dst, 'messages': index.size(1),
                     'ms': t, 'algorithmic_GBps': gbs, 'frac_of_peak': gbs / peak})
-        if cob is not None and F == 64:
+        if cob is not None and F in (16, 64):
             cob = cob.to(dev)
             P, Q = torch.randn(n_src, F, device=dev, requires_grad=True), torch.randn(n_cob, F, device=dev, requires_grad=True)
             o = ops.cob_pass(P, Q, index, cob, n_dst)
@@ -331,7 +347,7 @@ def kernel_sweep_full(dev, rank=0, world=1):
     from cwn_b200 import ops
     from cwn_b200.data import synthetic
     peak, _ = peaks()
-    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    flush = CleanL2Flush(dev)
 
     def timed(fn, name, reps=5):
         ms = []

@@ -8,6 +8,8 @@ Replaces in the reference: `__lift__` (mp/cell_mp.py:195-198), `aggregate_*` (mp
 `InitReduceConv` (mp/layers.py:484-487), `global_add_pool/global_mean_pool` (mp/nn.py:59), the `up_attr` gather of
 `data/complex.py:579-580`, and the autograd of all of them.
 """
+import os
+
 import torch
 from torch import Tensor
 from torch.autograd import Function
@@ -122,10 +124,63 @@ def _call(name, algo_bytes, fn, *args, flops=0):
 # --------------------------------------------------------------------------------------------- CSR plans
 class Plan(object):
     """Messages grouped (stably) by one index column: `rowptr[n_rows+1]`, `perm[E]`, up to two payload columns."""
-    __slots__ = ('rowptr', 'perm', 'pay0', 'pay1', 'n_rows', 'E')
+    __slots__ = ('rowptr', 'perm', 'pay0', 'pay1', 'n_rows', 'E', 'ws')
 
     def __init__(self, rowptr, perm, pay0, pay1, n_rows, E):
         self.rowptr, self.perm, self.pay0, self.pay1, self.n_rows, self.E = rowptr, perm, pay0, pay1, n_rows, E
+        self.ws = {}  # tile height -> (windows, cap_rows0, cap_rows1, cap_msgs): see _ws_config
+
+
+# Warp-specialised TMA kernels of the HBM-bound regime (csrc/gsa_ws.cu). CWN_B200_WS=0 keeps the register-level kernels.
+WS_MIN_ROWS = 32768
+_ws_enabled = os.environ.get('CWN_B200_WS', '1') != '0'
+_WS_MIN_STAGES = int(os.environ.get('CWN_B200_WS_MIN_STAGES', '4'))
+
+
+def _ws_ok(*mats):
+    return all(m is None or (m.data_ptr() % 16 == 0 and _ld(m) % 4 == 0) for m in mats)
+
+
+def _ws_config(plan: Plan, F: int, narr: int, rowop: bool):
+    """(windows, tile_rows, cap_rows0, cap_rows1, cap_msgs) when the plan is large enough for the warp-specialised
+    kernels and the operand windows of its tiles fit their shared-memory stages, else None. The tile windows are
+    computed once per plan and tile height (cwn_csr_tile_windows) and their maxima read back (one synchronisation
+    per plan, never during stream capture)."""
+    if (not _ws_enabled or plan.n_rows < WS_MIN_ROWS or plan.E == 0 or F % 4 or F > 128 or plan.pay0 is None
+            or (narr == 2 and plan.pay1 is None)):
+        return None
+    if plan.rowptr.data_ptr() % 16 or plan.pay0.data_ptr() % 16 or (plan.pay1 is not None and plan.pay1.data_ptr() % 16):
+        return None
+    lib = _lib.load()
+    # the tallest tile whose stage still leaves a 4-deep pipeline: taller tiles re-read less of the neighbouring
+    # tiles' windows (a window is the tile's rows plus a margin of about one complex on either side)
+    forced = int(os.environ.get('CWN_B200_WS_TILE', '0'))
+    # ... and no shorter than the number of lane groups that share its rows (a plan with few, heavy rows — the
+    # by-coboundary plan: ~26 messages per ring — would leave most consumer groups idle: it keeps the row kernels)
+    fv = F // 4
+    lpr = 4
+    while lpr < fv:
+        lpr *= 2
+    groups = lib.cwn_csr_ws_consumer_threads() // lpr
+    for tile_rows in ((forced,) if forced else (256, 128, 64, 32, 16)):
+        if tile_rows < groups and not forced:
+            break
+        entry = plan.ws.get(tile_rows)
+        if entry is None:
+            if torch.cuda.is_current_stream_capturing():
+                return None
+            n_tiles = (plan.n_rows + tile_rows - 1) // tile_rows
+            with torch.cuda.device(plan.rowptr.device):
+                windows = torch.zeros(8 * n_tiles + 4, dtype=torch.int32, device=plan.rowptr.device)
+                _call('csr_tile_windows', 4 * (plan.n_rows + 1) + 4 * plan.E * (1 + (plan.pay1 is not None)) + 32 * n_tiles,
+                      lib.cwn_csr_tile_windows, plan.rowptr.data_ptr(), _ptr(plan.pay0), _ptr(plan.pay1), plan.n_rows,
+                      tile_rows, windows.data_ptr(), _stream())
+            cap0, cap1, capm, _ = windows[-4:].tolist()
+            entry = plan.ws[tile_rows] = (windows, cap0, cap1, capm)
+        windows, cap0, cap1, capm = entry
+        if lib.cwn_csr_ws_stages(F, tile_rows, cap0, cap1 if narr == 2 else 0, capm, narr, int(rowop)) >= _WS_MIN_STAGES:
+            return windows, tile_rows, cap0, cap1, capm
+    return None
 
 
 def build_plan(key: Tensor, n_rows: int, pay0: Tensor = None, pay1: Tensor = None) -> Plan:
@@ -309,7 +364,7 @@ def clear_plan_cache(*indices):
 
 
 # --------------------------------------------------------------------------------------------- raw launches
-def _launch_gather_reduce(x_src, plan_rowptr, idx, n_rows, F, x_res, eps, reduce_code):
+def _launch_gather_reduce(x_src, plan_rowptr, idx, n_rows, F, x_res, eps, reduce_code, plan: Plan = None):
     """Algorithmic bytes: 16 B of int64 index per message + one read of every source row + one write
     of every destination row (+ one read of the residual rows when fused)."""
     lib = _lib.load()
@@ -325,8 +380,18 @@ def _launch_gather_reduce(x_src, plan_rowptr, idx, n_rows, F, x_res, eps, reduce
             cached = idx.__dict__['_cwn_touched'] = int(torch.unique(idx).numel())
         n_src = min(n_src, cached)
     algo = 16 * E + 4 * F * (n_src + n_rows + (n_rows if x_res is not None else 0))
+    ws = None
+    if plan is not None and idx is plan.pay0 and reduce_code in (0, 1) and x_src is not None and _ws_ok(x_src, x_res):
+        ws = _ws_config(plan, F, 1, x_res is not None)
     with torch.cuda.device(dev):
         out = torch.empty(n_rows, F, dtype=torch.float32, device=dev)
+        if ws is not None:
+            windows, tile_rows, cap0, _, capm = ws
+            _call('csr_gather_reduce', algo, lib.cwn_csr_gather_reduce_ws_f32,
+                  _ptr(x_src), _ld(x_src), plan_rowptr.data_ptr(), _ptr(idx), E, windows.data_ptr(), tile_rows, cap0,
+                  capm, n_rows, F, _ptr(x_res), _ld(x_res) if x_res is not None else F, _ptr(eps), _ptr(out), F,
+                  reduce_code, _stream())
+            return out
         _call('csr_gather_reduce', algo, lib.cwn_csr_gather_reduce_f32,
               _ptr(x_src), _ld(x_src) if x_src is not None else F, plan_rowptr.data_ptr(), _ptr(idx), n_rows, F,
               _ptr(x_res), _ld(x_res) if x_res is not None else F, _ptr(eps), _ptr(out), F, reduce_code, _stream())
@@ -379,7 +444,7 @@ class _GatherReduce(Function):
                       _lib.load().cwn_csr_gather_max_arg_f32, _ptr(x_src), _ld(x_src), plan.rowptr.data_ptr(),
                       _ptr(plan.pay0), _ptr(plan.perm), adj.n_dst, F, _ptr(out), F, _ptr(arg), _stream())
         else:
-            out = _launch_gather_reduce(x_src, plan.rowptr, plan.pay0, adj.n_dst, F, x_res, eps, code)
+            out = _launch_gather_reduce(x_src, plan.rowptr, plan.pay0, adj.n_dst, F, x_res, eps, code, plan=plan)
         ctx.adj, ctx.reduce = adj, reduce
         ctx.save_for_backward(x_res if (eps is not None and eps.requires_grad) else None, eps, arg)
         ctx.has_res = x_res is not None
@@ -405,11 +470,26 @@ class _GatherReduce(Function):
                 deg = (adj.by_dst.rowptr[1:] - adj.by_dst.rowptr[:-1]).clamp_(min=1).to(g.dtype)
                 gm = g / deg.unsqueeze(-1)
             plan = adj.by_src  # transposed pass: gX[s] = sum_{e: src_e = s} G[dst_e]
-            g_src = _launch_gather_reduce(gm, plan.rowptr, plan.pay0, adj.n_src, g.size(1), None, None, 0)
+            g_src = _launch_gather_reduce(gm, plan.rowptr, plan.pay0, adj.n_src, g.size(1), None, None, 0, plan=plan)
         g_res = g_eps = None
         if ctx.has_res:
             g_res, g_eps = _residual_grads(ctx.needs_input_grad[1], ctx.needs_input_grad[2], g, x_res, eps)
         return g_src, g_res, g_eps, None, None
+
+
+def _launch_cob_bwd(algo, g, A, B, plan, E, n_rows, F, act, gA):
+    lib = _lib.load()
+    ws = _ws_config(plan, F, 2, True) if _ws_ok(g, A, B) else None
+    if ws is not None:
+        windows, tile_rows, cap0, cap1, capm = ws
+        _call('csr_cob_bwd', algo, lib.cwn_csr_cob_bwd_ws_f32,
+              _ptr(g), _ld(g), _ptr(A), _ld(A), _ptr(B), _ld(B), plan.rowptr.data_ptr(), _ptr(plan.pay0),
+              _ptr(plan.pay1), E, windows.data_ptr(), tile_rows, cap0, cap1, capm, n_rows, F, act, _ptr(gA), F,
+              _stream())
+    else:
+        _call('csr_cob_bwd', algo, lib.cwn_csr_cob_bwd_f32,
+              _ptr(g), _ld(g), _ptr(A), _ld(A), _ptr(B), _ld(B), plan.rowptr.data_ptr(), _ptr(plan.pay0),
+              _ptr(plan.pay1), n_rows, F, act, _ptr(gA), F, _stream())
 
 
 class _CobPass(Function):
@@ -423,10 +503,18 @@ class _CobPass(Function):
         with torch.cuda.device(P.device):
             out = torch.empty(adj.n_dst, F, dtype=torch.float32, device=P.device)
             algo = 24 * adj.E + 4 * F * (P.size(0) + Q.size(0) + adj.n_dst * (2 if x_res is not None else 1))
-            _call('csr_cob_fwd', algo, lib.cwn_csr_cob_fwd_f32,
-                  _ptr(P), _ld(P), _ptr(Q), _ld(Q), plan.rowptr.data_ptr(), _ptr(plan.pay0), _ptr(plan.pay1),
-                  adj.n_dst, F, ACT_CODES[act], _ptr(x_res), _ld(x_res) if x_res is not None else F, _ptr(eps),
-                  _ptr(out), F, _stream())
+            ws = _ws_config(plan, F, 2, x_res is not None) if _ws_ok(P, Q, x_res) else None
+            if ws is not None:
+                windows, tile_rows, cap0, cap1, capm = ws
+                _call('csr_cob_fwd', algo, lib.cwn_csr_cob_fwd_ws_f32,
+                      _ptr(P), _ld(P), _ptr(Q), _ld(Q), plan.rowptr.data_ptr(), _ptr(plan.pay0), _ptr(plan.pay1), adj.E,
+                      windows.data_ptr(), tile_rows, cap0, cap1, capm, adj.n_dst, F, ACT_CODES[act], _ptr(x_res),
+                      _ld(x_res) if x_res is not None else F, _ptr(eps), _ptr(out), F, _stream())
+            else:
+                _call('csr_cob_fwd', algo, lib.cwn_csr_cob_fwd_f32,
+                      _ptr(P), _ld(P), _ptr(Q), _ld(Q), plan.rowptr.data_ptr(), _ptr(plan.pay0), _ptr(plan.pay1),
+                      adj.n_dst, F, ACT_CODES[act], _ptr(x_res), _ld(x_res) if x_res is not None else F, _ptr(eps),
+                      _ptr(out), F, _stream())
         ctx.adj, ctx.act = adj, act
         ctx.has_res = x_res is not None
         ctx.save_for_backward(P, Q, x_res if (eps is not None and eps.requires_grad) else None, eps)
@@ -445,16 +533,12 @@ class _CobPass(Function):
                 plan = adj.by_src
                 gP = torch.empty_like(P, memory_format=torch.contiguous_format)
                 algo = 24 * adj.E + 4 * F * (g.size(0) + 2 * P.size(0) + Q.size(0))
-                _call('csr_cob_bwd', algo, lib.cwn_csr_cob_bwd_f32,
-                      _ptr(g), _ld(g), _ptr(P), _ld(P), _ptr(Q), _ld(Q), plan.rowptr.data_ptr(), _ptr(plan.pay0),
-                      _ptr(plan.pay1), adj.n_src, F, act, _ptr(gP), F, _stream())
+                _launch_cob_bwd(algo, g, P, Q, plan, adj.E, adj.n_src, F, act, gP)
             if ctx.needs_input_grad[1]:
                 plan = adj.by_cob
                 gQ = torch.empty_like(Q, memory_format=torch.contiguous_format)
                 algo = 24 * adj.E + 4 * F * (g.size(0) + 2 * Q.size(0) + P.size(0))
-                _call('csr_cob_bwd', algo, lib.cwn_csr_cob_bwd_f32,
-                      _ptr(g), _ld(g), _ptr(Q), _ld(Q), _ptr(P), _ld(P), plan.rowptr.data_ptr(), _ptr(plan.pay0),
-                      _ptr(plan.pay1), adj.n_cob, F, act, _ptr(gQ), F, _stream())
+                _launch_cob_bwd(algo, g, Q, P, plan, adj.E, adj.n_cob, F, act, gQ)
         g_res = g_eps = None
         if ctx.has_res:
             g_res, g_eps = _residual_grads(ctx.needs_input_grad[2], ctx.needs_input_grad[3], g, x_res, eps)

@@ -153,6 +153,43 @@ int cwn_csr_cob_bwd_f32(const float* G, int64_t ld_g, const float* A, int64_t ld
                         int32_t act, float* gA, int64_t ld_ga, cwn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * The three passes above for the HBM-bound regime (tens of thousands of rows and more per launch), warp-specialised:
+ * one producer warp per persistent CTA streams, several tiles ahead, the plan slices, the operand-row WINDOWS and the
+ * tile's own residual rows into shared memory with TMA bulk copies; eight consumer warps run the rows out of shared
+ * memory (csrc/gsa_ws.cu). Same results, bit for bit, as cwn_csr_gather_reduce_f32 / cwn_csr_cob_fwd_f32 /
+ * cwn_csr_cob_bwd_f32 (same in-row order, same roundings). Requirements: F % 4 == 0, F <= 128, every matrix, rowptr,
+ * payload column and `windows` 16-byte aligned, every ld % 4 == 0.
+ *
+ * cwn_csr_tile_windows — once per plan and tile height: for tile t (rows [t*tile_rows, (t+1)*tile_rows))
+ *   windows[8t..8t+7] = { m0, m1 (message range), lo0, cnt0 (rows lo0 .. lo0+cnt0-1 of the operand behind pay0 are the
+ *   only ones its messages read), lo1, cnt1 (same for pay1; 0 if pay1 == NULL), 0, 0 }
+ * followed by 4 statistics words the CALLER ZEROES before the call: { max cnt0, max cnt1, max 4-aligned message hull, 0 }.
+ * `windows` therefore holds 8 * ceil(n_rows / tile_rows) + 4 int32. The caller sizes the kernels' buffers from the
+ * statistics (cap_rows*, cap_msgs); a tile that exceeds them is still computed correctly, from global memory.
+ * cwn_csr_ws_stages — pipeline depth the configuration gets (0 or 1: do not use these entry points for it).
+ * E = number of messages of the plan (length of the payload columns). */
+int cwn_csr_tile_windows(const int32_t* rowptr, const int32_t* pay0, const int32_t* pay1 /* nullable */, int64_t n_rows,
+                         int32_t tile_rows, int32_t* windows, cwn_stream_t stream);
+int cwn_csr_ws_consumer_threads(void); /* rows of a tile are shared by consumer_threads / lanes_per_row groups */
+int cwn_csr_ws_stages(int32_t F, int32_t tile_rows, int32_t cap_rows0, int32_t cap_rows1, int32_t cap_msgs,
+                      int32_t n_arrays, int32_t has_row_operand);
+int cwn_csr_gather_reduce_ws_f32(const float* x_src, int64_t ld_src, const int32_t* rowptr, const int32_t* idx,
+                                 int64_t E, const int32_t* windows, int32_t tile_rows, int32_t cap_rows,
+                                 int32_t cap_msgs, int64_t n_rows, int32_t F, const float* x_res, int64_t ld_res,
+                                 const float* eps, float* out, int64_t ld_out, int32_t reduce /* add | mean */,
+                                 cwn_stream_t stream);
+int cwn_csr_cob_fwd_ws_f32(const float* P, int64_t ld_p, const float* Q, int64_t ld_q, const int32_t* rowptr,
+                           const int32_t* src, const int32_t* cob, int64_t E, const int32_t* windows,
+                           int32_t tile_rows, int32_t cap_rows0, int32_t cap_rows1, int32_t cap_msgs, int64_t n_rows,
+                           int32_t F, int32_t act, const float* x_res, int64_t ld_res, const float* eps, float* out,
+                           int64_t ld_out, cwn_stream_t stream);
+int cwn_csr_cob_bwd_ws_f32(const float* G, int64_t ld_g, const float* A, int64_t ld_a, const float* B, int64_t ld_b,
+                           const int32_t* rowptr, const int32_t* dst, const int32_t* oth, int64_t E,
+                           const int32_t* windows, int32_t tile_rows, int32_t cap_rows0, int32_t cap_rows1,
+                           int32_t cap_msgs, int64_t n_rows, int32_t F, int32_t act, float* gA, int64_t ld_ga,
+                           cwn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * K5 — message MLP of the dense CIN layers with BatchNorm over the MESSAGE population (reference mp/layers.py:94-103,
  * nets mp/models.py:40-47: Linear(2F -> F), act, BatchNorm1d). With the Linear in split-weight form (P, Q as in
  * cwn_csr_cob_fwd_f32) a message is a_e = act(P[src_e] + Q[att_e]) and its BatchNorm is affine, so
