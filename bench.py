@@ -432,8 +432,19 @@ def run_cwn(args, rank, world, local_rank):
     torch.manual_seed(0)
     model = getattr(molec_models, model_name)(**model_cfg).to(dev).train()
     broadcast_parameters(model)
-    bucket = FlatGradBucket(model)
+    bucket = None
+    if world > 1 and os.environ.get('CWN_BENCH_DP_SYMM', '1') != '0':
+        # gradients in symmetric memory: the all-reduce is fused into the Adam kernel over NVLink peer memory (no NCCL call)
+        try:
+            from cwn_b200.dist import SymmetricGradBucket
+            bucket = SymmetricGradBucket(model)
+        except Exception as exc:  # noqa: BLE001 — reported, never silent: config.allreduce says which path ran
+            print(f'bench.py: symmetric memory unavailable ({type(exc).__name__}: {exc}); NCCL all-reduce',
+                  file=sys.stderr, flush=True)
+    if bucket is None:
+        bucket = FlatGradBucket(model)
     opt = FlatAdam(model, bucket, lr=1e-3)  # one launch; also clears the gradient bucket for the next step
+    fused_dp = getattr(opt, 'fuses_allreduce', False)
 
     host_batches = [b.pack_(pin_memory=True) for b in make_batches(args.pool, args.batch, seed0=1000 + 100 * rank, **gen)]
     cells = cells_of(host_batches[0])
@@ -447,7 +458,8 @@ def run_cwn(args, rank, world, local_rank):
         out = model(batch)
         loss = loss_fn(out, batch.y)
         loss.backward()
-        bucket.all_reduce()
+        if not fused_dp:
+            bucket.all_reduce()
         opt.step()
         return loss
 
@@ -647,7 +659,9 @@ def run_cwn(args, rank, world, local_rank):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': workload_name, 'cells_per_step_per_gpu': cells, 'global_batch': args.batch * world,
                    'parallelism': f'dp{world}', 'step': 'plans+fwd+loss+bwd+allreduce+adam', 'mode': mode,
-                   'allreduce': ('captured in the step graph' if (captured is not None and captured.allreduce_in_graph) else
+                   'allreduce': ('fused with Adam in one kernel over NVLink peer memory (symmetric memory, two-shot; no NCCL '
+                                 'call on the step)' if fused_dp else
+                                 'captured in the step graph' if (captured is not None and captured.allreduce_in_graph) else
                                  'between two graphs' if world > 1 else 'none (1 GPU)'), 'clock_preload_steps': PRELOAD_STEPS,
                    'l2': 'flushed (256 MB write) between timed steps', 'last_loss': loss_value},
         'clocks': clock_info, 'gpu_launches': int(launches),

@@ -127,6 +127,8 @@ _SIGNATURES = {
     'cwn_wgrad_finalize_grouped': (ctypes.c_int, [ctypes.POINTER(UnitBwdDesc), _i32, _vp]),
     'cwn_collate': (ctypes.c_int, [ctypes.POINTER(CollateJob), _i32, _vp]),
     'cwn_adam_step_f32': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _i32, _vp]),
+    'cwn_allreduce_adam_step_f32': (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i64, _f32, _f32, _f32, _f32,
+                                                   _f32, _vp, _vp, _i32, _vp, _vp]),
     'cwn_check_index_range': (ctypes.c_int, [_c_i64p, _i64, _i64, _c_i32p, _vp]),
 }
 

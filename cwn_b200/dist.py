@@ -69,6 +69,56 @@ class FlatGradBucket(object):
         return None
 
 
+class SymmetricGradBucket(FlatGradBucket):
+    """The flat gradient bucket in SYMMETRIC memory (torch.distributed._symmetric_memory): every rank of the node maps
+    every other rank's bucket, so `FlatAdam` can average the gradients and apply the update in ONE kernel over NVLink
+    peer memory (`cwn_allreduce_adam_step_f32`) — no NCCL call on the step. The buffer is padded to a multiple of four
+    floats (128-bit peer loads). `all_reduce()` remains available (NCCL on the same buffer) for callers that keep the
+    optimizer separate. Single node only; raises if symmetric memory cannot be set up (no silent fallback)."""
+
+    MAX_CTAS = 128
+
+    def __init__(self, module: torch.nn.Module, group=None):
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError('SymmetricGradBucket needs an initialised process group')
+        import torch.distributed._symmetric_memory as symm
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        if not self.params:
+            raise ValueError('module has no trainable parameters')
+        dev, dtype = self.params[0].device, self.params[0].dtype
+        if dtype != torch.float32 or dev.type != 'cuda':
+            raise ValueError('SymmetricGradBucket: CUDA float32 parameters only')
+        total = sum(p.numel() for p in self.params)
+        padded = (total + 3) // 4 * 4
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.n_ctas = self.MAX_CTAS
+        with torch.cuda.device(dev):
+            self._storage = symm.empty(padded, dtype=dtype, device=dev)
+            self._pad = symm.empty(self.n_ctas * self.world, dtype=torch.int32, device=dev)
+            self._storage.zero_()
+            self._pad.zero_()
+            self.grad_handle = symm.rendezvous(self._storage, group.group_name)
+            self.pad_handle = symm.rendezvous(self._pad, group.group_name)
+        self.flat = self._storage  # [padded]; the tail beyond `total` stays zero
+        self.numel = total
+        self.error = torch.zeros(1, dtype=torch.int32, device=dev)
+        off = 0
+        for p in self.params:
+            if p.device != dev or p.dtype != dtype:
+                raise ValueError('FlatGradBucket needs all parameters on one device with one dtype')
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)  # every rank's pad is zero before anyone signals
+
+    def check(self):
+        """Raise if a fused step ever gave up waiting for a peer (host sync: call it outside the hot loop)."""
+        code = int(self.error.item())
+        if code:
+            raise RuntimeError(f'cwn_b200: peer barrier of the fused all-reduce + Adam timed out (code {code})')
+
+
 def broadcast_parameters(module: torch.nn.Module, src: int = 0):
     """Make every rank start from rank `src`'s weights and buffers."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

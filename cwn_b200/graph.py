@@ -72,8 +72,8 @@ class CapturedStep(object):
             self.bucket.zero()
         loss = self._forward_loss(b)
         loss.backward()
-        if self.allreduce_in_graph:
-            self.bucket.all_reduce()
+        if self.allreduce_in_graph and not getattr(self.optimizer, 'fuses_allreduce', False):
+            self.bucket.all_reduce()  # (a FlatAdam over a SymmetricGradBucket averages inside its own kernel)
         if self.optimizer_in_graph:
             self.optimizer.step()
         return loss

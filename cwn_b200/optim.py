@@ -5,7 +5,7 @@ the update can be captured in a CUDA graph, and the kernel zeroes the gradients 
 import torch
 
 from cwn_b200 import _lib, ops
-from cwn_b200.dist import FlatGradBucket
+from cwn_b200.dist import FlatGradBucket, SymmetricGradBucket
 
 
 class FlatAdam(object):
@@ -28,6 +28,11 @@ class FlatAdam(object):
         self.exp_avg_sq = torch.zeros_like(self.flat_param)
         self._step = torch.zeros(1, dtype=torch.int32, device=dev)
         self._counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        # with a SymmetricGradBucket the step ALSO averages the gradients over the ranks (one kernel over NVLink peer
+        # memory): callers must not all-reduce the bucket themselves (CapturedStep checks this flag)
+        self.fuses_allreduce = isinstance(self.bucket, SymmetricGradBucket) and self.bucket.world > 1
+        if isinstance(self.bucket, SymmetricGradBucket):
+            self.flat_param[self.bucket.numel:].zero_()  # padding
 
     @property
     def num_steps(self):
@@ -36,6 +41,16 @@ class FlatAdam(object):
     def step(self):
         lib = _lib.load()
         n = self.flat_param.numel()
+        if self.fuses_allreduce:
+            b = self.bucket
+            with torch.cuda.device(self.flat_param.device):
+                ops._call('allreduce_adam_step', 4 * (7 + 2 * b.world) * n, lib.cwn_allreduce_adam_step_f32,
+                          self.flat_param.data_ptr(), b.grad_handle.buffer_ptrs_dev, b.pad_handle.buffer_ptrs_dev, b.rank,
+                          b.world, b.n_ctas, self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), n, float(self.lr),
+                          float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.weight_decay),
+                          self._step.data_ptr(), self._counter.data_ptr(), int(self.zero_grad), b.error.data_ptr(),
+                          torch.cuda.current_stream().cuda_stream)
+            return
         with torch.cuda.device(self.flat_param.device):
             ops._call('adam_step', 4 * 7 * n, lib.cwn_adam_step_f32, self.flat_param.data_ptr(),
                       self.bucket.flat.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), n,

@@ -321,6 +321,20 @@ int cwn_adam_step_f32(float* param, float* grad, float* exp_avg, float* exp_avg_
                       float beta2, float eps, float weight_decay, int32_t* step, int32_t* counter, int32_t zero_grad,
                       cwn_stream_t stream);
 
+/* Data parallel: the gradient all-reduce (average over `world` ranks of one node) fused with the Adam step above, in ONE
+ * launch over NVLink peer memory — no NCCL call on the step. `grad_ptrs` / `signal_pads` are DEVICE arrays [world] of
+ * every rank's flat gradient bucket / signal pad as mapped into THIS process (symmetric memory: cudaIpc / fabric
+ * handles; torch.distributed._symmetric_memory's buffer_ptrs_dev). Pads: n_ctas * world zero-initialised uint32 per
+ * rank, private to this entry point. n % 4 == 0, buffers 16-byte aligned, n_ctas <= 148 and identical on every rank.
+ * Two-shot: rank r averages slice r of all buckets in rank order (bit-identical results on every rank) and publishes it
+ * to every bucket; then each rank runs Adam locally. `*error` (device, zeroed by the caller) becomes non-zero if a
+ * peer did not show up within ~2 s (the kernel gives up rather than hang). Replaces: nothing in the reference (single
+ * device, exp/run_exp.py:22-23); torch DDP's NCCL all-reduce + torch.optim.Adam in a multi-GPU port of it. */
+int cwn_allreduce_adam_step_f32(float* param, float* const* grad_ptrs, uint32_t* const* signal_pads, int32_t rank,
+                                int32_t world, int32_t n_ctas, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                                float beta1, float beta2, float eps, float weight_decay, int32_t* step, int32_t* counter,
+                                int32_t zero_grad, int32_t* error, cwn_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * GPU-side collation (replaces the CPU loops of ComplexBatch.from_complex_list / CochainBatch.from_cochain_list,
  * data/complex.py:323-458, 690-728). Every tensor of a batch is a concatenation of per-complex segments of a
