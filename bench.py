@@ -438,6 +438,7 @@ def run_cwn(args, rank, world, local_rank):
         try:
             from cwn_b200.dist import SymmetricGradBucket
             bucket = SymmetricGradBucket(model)
+            bucket.self_test()  # one fused launch on known data at THIS world size, before anything depends on it
         except Exception as exc:  # noqa: BLE001 — reported, never silent: config.allreduce says which path ran
             print(f'bench.py: symmetric memory unavailable ({type(exc).__name__}: {exc}); NCCL all-reduce',
                   file=sys.stderr, flush=True)

@@ -65,7 +65,11 @@ class UnitBwdDesc(ctypes.Structure):
                 ('g_beta', _P), ('accumulate_affine', _I32), ('g_in0', _P), ('ld_gi0', _I64), ('g_in1', _P),
                 ('ld_gi1', _I64), ('w_partials', _P), ('b_partials', _P), ('n_ctas', _I32), ('g_w', _P),
                 ('ld_gw', _I64), ('g_b', _P), ('accumulate_w', _I32), ('n_rows', _I64), ('h', _I32),
-                ('counter', _P), ('tile_rows', _I32), ('accumulate_in', _I32), ('n_rows_live', _P)]
+                ('counter', _P), ('tile_rows', _I32), ('accumulate_in', _I32), ('n_rows_live', _P),
+                ('next_rstd0', _P), ('next_red0', _P), ('next_c1_0', _P), ('next_c2_0', _P), ('next_g_gamma0', _P),
+                ('next_g_beta0', _P), ('next_rstd1', _P), ('next_red1', _P), ('next_c1_1', _P), ('next_c2_1', _P),
+                ('next_g_gamma1', _P), ('next_g_beta1', _P), ('next_accumulate_affine0', _I32),
+                ('next_accumulate_affine1', _I32), ('next_counter', _P)]
 
 
 class CollateJob(ctypes.Structure):
@@ -124,6 +128,7 @@ _SIGNATURES = {
     'cwn_unit_bwd_reduce_grouped': (ctypes.c_int, [ctypes.POINTER(UnitBwdDesc), _i32, _vp]),
     'cwn_unit_bwd_finalize_grouped': (ctypes.c_int, [ctypes.POINTER(UnitBwdDesc), _i32, _vp]),
     'cwn_unit_bwd_grouped': (ctypes.c_int, [ctypes.POINTER(UnitBwdDesc), _i32, _vp]),
+    'cwn_unit_bwd_fuses_reduce': (ctypes.c_int, [ctypes.POINTER(UnitBwdDesc), _i32]),
     'cwn_wgrad_finalize_grouped': (ctypes.c_int, [ctypes.POINTER(UnitBwdDesc), _i32, _vp]),
     'cwn_collate': (ctypes.c_int, [ctypes.POINTER(CollateJob), _i32, _vp]),
     'cwn_adam_step_f32': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _i32, _vp]),

@@ -1969,6 +1969,18 @@ extern "C" int cwn_unit_bwd_finalize_grouped(const cwn_unit_bwd_desc* descs, int
   return launched("unit_bwd_finalize_kernel");
 }
 
+// 1 if cwn_unit_bwd_grouped will serve this group with the tensor-core kernel (the only one that can take the upstream
+// units' BatchNorm-backward reductions from its g_in tiles), else 0
+extern "C" int cwn_unit_bwd_fuses_reduce(const cwn_unit_bwd_desc* descs, int32_t n) {
+  if (!descs || n <= 0 || n > CWN_MAX_GROUP) return 0;
+  int tr;
+  if (group_tile_rows(descs, n, tr) || tr != 64 || !t5_enabled() || (g_force_generic_dense & 2)) return 0;
+  size_t smem5 = 0;
+  for (int i = 0; i < n; ++i)
+    if (descs[i].n_rows != 0 && !t5_bwd_ok(descs[i], smem5)) return 0;
+  return smem5 > 0 ? 1 : 0;
+}
+
 extern "C" int cwn_unit_bwd_grouped(const cwn_unit_bwd_desc* descs, int32_t n, cwn_stream_t stream) {
   Group<cwn_unit_bwd_desc> g;
   int rc = load_bwd_group(descs, n, g, "cwn_unit_bwd_grouped");
@@ -1993,6 +2005,19 @@ extern "C" int cwn_unit_bwd_grouped(const cwn_unit_bwd_desc* descs, int32_t n, c
   if (total == 0) return CWN_OK;
   const int a_in = group_act(descs, n, [](const cwn_unit_bwd_desc& d) { return d.in_act; });
   const int a_out = group_act(descs, n, [](const cwn_unit_bwd_desc& d) { return d.act; });
+  bool wants_fused_reduce = false;
+  for (int i = 0; i < n; ++i) {
+    const cwn_unit_bwd_desc& d = g.d[i];
+    for (int hf = 0; hf < 2; ++hf) {
+      if (!(hf ? d.next_red1 : d.next_red0)) continue;
+      wants_fused_reduce = true;
+      const bool ok = (hf ? d.g_in1 : d.g_in0) && !d.accumulate_in && (hf ? d.next_rstd1 : d.next_rstd0) &&
+                      (hf ? d.next_c1_1 : d.next_c1_0) && (hf ? d.next_c2_1 : d.next_c2_0) && d.next_counter &&
+                      (hf ? d.in_mean1 : d.in_mean0) && (hf ? d.in_scale1 : d.in_scale0) &&
+                      aligned16(hf ? d.next_rstd1 : d.next_rstd0) && (hf ? d.k1 : d.k0) > 0;
+      if (!ok) return fail(CWN_E_NULL, "cwn_unit_bwd_grouped: next_red needs g_in, accumulate_in == 0, next_rstd / c1 / c2 / counter and the input transform");
+    }
+  }
   if (tr == 64 && t5_enabled() && !(g_force_generic_dense & 2)) {  // tensor-core path (see dense_tc5.cuh)
     bool ok = true;
     size_t smem5 = 0;
@@ -2015,6 +2040,7 @@ extern "C" int cwn_unit_bwd_grouped(const cwn_unit_bwd_desc* descs, int32_t n, c
       return launched("unit_bwd_tc5_kernel");
     }
   }
+  if (wants_fused_reduce) return fail(CWN_E_SHAPE, "cwn_unit_bwd_grouped: next_red (fused upstream reduction) needs the tensor-core path: ask cwn_unit_bwd_fuses_reduce first");
   for (int i = 0; i < n; ++i)
     if (g.d[i].n_rows_live) return fail(CWN_E_SHAPE, "cwn_unit_bwd_grouped: n_rows_live needs the tensor-core path (h = 64, K in {32, 64, 128}, tile_rows 64)");
   bool fast = !(g_force_generic_dense & 2);

@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(T5T, 2) linear_fwd_tc5_kernel(const __grid_con
 struct T5BwdSmem {
   // gm = [g_z_hi | g_z_lo] MN-major (inner = rows, M = 2 h); xm = [f(X)_hi | f(X)_lo] MN-major (inner = rows, N = 2 K);
   // gt = [g_z_hi ; g_z_lo] K-major tiled over 128 rows; wm = [W_hi | W_lo] MN-major (inner = h, N = 2 K)
-  uint32_t gm, xm, gt, wm, vout, bsum, total;
+  uint32_t gm, xm, gt, wm, vout, bsum, npart, total;
   uint32_t g_lbo, x_lbo, w_lbo;  // MN-major: stride between 32-column groups (sbo = 512 everywhere)
   int nb1, nb2;
   uint32_t col2, tmem_cols;
@@ -337,7 +337,8 @@ struct T5BwdSmem {
     gm = 0; xm = gmb; gt = gmb + xmb; wm = gt + gtb;   // (the staging tile T[128][K + 4] lives over gm + xm + gt)
     vout = wm + wmb;                                   // [6][h] floats
     bsum = vout + 6u * (uint32_t)h * 4u;               // [256 / (h/4)][h] floats
-    total = bsum + (uint32_t)(T5T / (h / 4)) * (uint32_t)h * 4u;
+    npart = bsum + (uint32_t)(T5T / (h / 4)) * (uint32_t)h * 4u;  // [2][256 / (K/4)][K] floats: fused upstream reduction
+    total = npart + 2u * (uint32_t)T5T * 4u * 4u;
     nb1 = t5_blocks(K <= 64 ? 2 : 1, h);               // g_in: accumulators of 2 K columns
     nb2 = 1;                                           // g_W (only rtol 1e-4 is asked of parameter gradients)
     col2 = (uint32_t)(nb1 * 2 * K);
@@ -411,6 +412,25 @@ __global__ void __launch_bounds__(T5T, 1) unit_bwd_tc5_kernel(const __grid_const
   const int ldt = K + 4;
   uint32_t parity = 0;
   bool first = true;
+  // ---- fused BatchNorm-backward reduction of the upstream units (cwn_unit_bwd_desc::next_*): this thread's column chunk
+  //      c4x of the g_in tile belongs to input block nhf; the upstream unit's BatchNorm + activation are this unit's input
+  //      transform, its z is this unit's raw input
+  const bool any_next = d.next_red0 || d.next_red1;
+  const int nkq = c4x * 4, nhf = nkq < d.k0 ? 0 : 1, nkc = nhf ? nkq - d.k0 : nkq;
+  const bool do_next = nhf ? d.next_red1 != nullptr : d.next_red0 != nullptr;
+  float4 n_mean = make_float4(0.f, 0.f, 0.f, 0.f), n_scale = make_float4(1.f, 1.f, 1.f, 1.f), n_beta = n_mean, n_rstd = n_mean;
+  const float* n_x = nullptr;
+  int64_t n_ldx = 0;
+  if (do_next) {
+    n_mean = ldg_f4((nhf ? d.in_mean1 : d.in_mean0) + nkc);
+    n_scale = ldg_f4((nhf ? d.in_scale1 : d.in_scale0) + nkc);
+    const float* bp = nhf ? d.in_beta1 : d.in_beta0;
+    if (bp) n_beta = ldg_f4(bp + nkc);
+    n_rstd = ldg_f4((nhf ? d.next_rstd1 : d.next_rstd0) + nkc);
+    n_x = (nhf ? d.x1 : d.x0) + nkc;
+    n_ldx = nhf ? d.ld_x1 : d.ld_x0;
+  }
+  float* npart = reinterpret_cast<float*>(smem5 + L.npart);
   for (int tile = j; tile < n_tiles; tile += d.n_ctas, first = false, parity ^= 1u) {
     const int64_t row0 = (int64_t)tile * T5R;
     const int rows_cap = (int)((d.n_rows - row0 < T5R) ? d.n_rows - row0 : T5R);
@@ -520,14 +540,54 @@ __global__ void __launch_bounds__(T5T, 1) unit_bwd_tc5_kernel(const __grid_const
       for (int k0 = k_lo; k0 < k_hi; k0 += 16) t5_stage16(tmem + tl, K, L.nb1, k0, T + R * ldt);
       tc5::fence_before_sync();
       __syncthreads();
-      for (int i = tid; i < rows_cap * K4; i += T5T) {  // (padding rows leave as the zeros their g_z produced)
-        const int rr = i >> lgk, kq = (i & (K4 - 1)) * 4;
-        float* base = (kq < d.k0) ? (d.g_in0 ? d.g_in0 + (row0 + rr) * d.ld_gi0 + kq : nullptr)
-                                  : (d.g_in1 ? d.g_in1 + (row0 + rr) * d.ld_gi1 + (kq - d.k0) : nullptr);
-        if (!base) continue;
-        float4 o = f4_add(*reinterpret_cast<const float4*>(T + rr * ldt + kq), *reinterpret_cast<const float4*>(T + (rr + T5R) * ldt + kq));
-        if (d.accumulate_in) o = f4_add(*reinterpret_cast<const float4*>(base), o);
-        *reinterpret_cast<float4*>(base) = o;
+      float4 ns1 = make_float4(0.f, 0.f, 0.f, 0.f), ns2 = ns1;
+      constexpr int NX = 4;  // rows of a thread per trip: the upstream z values of a trip are requested together
+      for (int i0 = tid; i0 < rows_cap * K4; i0 += NX * T5T) {  // (padding rows leave as the zeros their g_z produced)
+        float4 xv[NX];
+#pragma unroll
+        for (int jj = 0; jj < NX; ++jj) {
+          const int i = i0 + jj * T5T;
+          xv[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (do_next && i < rows_cap * K4) xv[jj] = ldg_f4(n_x + (row0 + (i >> lgk)) * n_ldx);
+        }
+#pragma unroll
+        for (int jj = 0; jj < NX; ++jj) {
+          const int i = i0 + jj * T5T;
+          if (i >= rows_cap * K4) break;
+          const int rr = i >> lgk, kq = (i & (K4 - 1)) * 4;
+          float* base = (kq < d.k0) ? (d.g_in0 ? d.g_in0 + (row0 + rr) * d.ld_gi0 + kq : nullptr)
+                                    : (d.g_in1 ? d.g_in1 + (row0 + rr) * d.ld_gi1 + (kq - d.k0) : nullptr);
+          if (!base) continue;
+          float4 o = f4_add(*reinterpret_cast<const float4*>(T + rr * ldt + kq), *reinterpret_cast<const float4*>(T + (rr + T5R) * ldt + kq));
+          if (d.accumulate_in) o = f4_add(*reinterpret_cast<const float4*>(base), o);
+          *reinterpret_cast<float4*>(base) = o;
+          if (do_next) {  // the upstream unit's column sums  SUM g act'(y),  SUM g act'(y) zhat  over this thread's rows (in order)
+            const float4 x_ = xv[jj];
+            float zc, gy;
+            zc = x_.x - n_mean.x; gy = o.x * act_grad<A_IN>(d.in_act, zc * n_scale.x + n_beta.x); ns1.x += gy; ns2.x = fmaf(gy, zc * n_rstd.x, ns2.x);
+            zc = x_.y - n_mean.y; gy = o.y * act_grad<A_IN>(d.in_act, zc * n_scale.y + n_beta.y); ns1.y += gy; ns2.y = fmaf(gy, zc * n_rstd.y, ns2.y);
+            zc = x_.z - n_mean.z; gy = o.z * act_grad<A_IN>(d.in_act, zc * n_scale.z + n_beta.z); ns1.z += gy; ns2.z = fmaf(gy, zc * n_rstd.z, ns2.z);
+            zc = x_.w - n_mean.w; gy = o.w * act_grad<A_IN>(d.in_act, zc * n_scale.w + n_beta.w); ns1.w += gy; ns2.w = fmaf(gy, zc * n_rstd.w, ns2.w);
+          }
+        }
+      }
+      if (any_next) {  // row groups merged in order -> this tile's record of the upstream unit's red_partials
+        *reinterpret_cast<float4*>(npart + rbx * K + nkq) = ns1;
+        *reinterpret_cast<float4*>(npart + T5T * 4 + rbx * K + nkq) = ns2;
+        __syncthreads();
+        if (tid < K) {
+          const int hf = tid < d.k0 ? 0 : 1, kc = hf ? tid - d.k0 : tid, kh = hf ? d.k1 : d.k0;
+          float* red = hf ? d.next_red1 : d.next_red0;
+          if (red) {
+            float a = 0.f, b = 0.f;
+            for (int m = 0; m < rsx; ++m) {
+              a += npart[m * K + tid];
+              b += npart[T5T * 4 + m * K + tid];
+            }
+            red[((int64_t)tile * 2 + 0) * kh + kc] = a;
+            red[((int64_t)tile * 2 + 1) * kh + kc] = b;
+          }
+        }
       }
     }
     tc5::fence_before_sync();
@@ -536,6 +596,24 @@ __global__ void __launch_bounds__(T5T, 1) unit_bwd_tc5_kernel(const __grid_const
     if (first) CWN_PHASE(5);
   }
   if (warp == 0) tc5::tmem_dealloc(tmem_s, L.tmem_cols);
+  if (any_next && d.next_counter) {  // the last CTA of the problem finalises the upstream units (c1, c2, g_gamma, g_beta)
+    if (last_cta_of_problem(d.next_counter, g.start[p + 1] - g.start[p])) {
+      float* stage = reinterpret_cast<float*>(smem5);  // everything staged there is dead (>= 32 KB)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float* red = hf ? d.next_red1 : d.next_red0;
+        if (!red) continue;
+        cwn_unit_bwd_desc u = {};
+        u.n_rows = d.n_rows; u.n_rows_live = d.n_rows_live; u.h = hf ? d.k1 : d.k0; u.red_partials = red;
+        u.c1 = hf ? d.next_c1_1 : d.next_c1_0; u.c2 = hf ? d.next_c2_1 : d.next_c2_0;
+        u.g_gamma = hf ? d.next_g_gamma1 : d.next_g_gamma0; u.g_beta = hf ? d.next_g_beta1 : d.next_g_beta0;
+        u.accumulate_affine = hf ? d.next_accumulate_affine1 : d.next_accumulate_affine0;
+        unit_bwd_finalize_body(u, stage, T5R);
+        __syncthreads();
+      }
+      if (tid == 0) *d.next_counter = 0;
+    }
+  }
   CWN_PHASE(8);
 }
 

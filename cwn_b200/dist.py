@@ -112,6 +112,36 @@ class SymmetricGradBucket(FlatGradBucket):
         torch.cuda.synchronize(dev)
         dist.barrier(group)  # every rank's pad is zero before anyone signals
 
+    def self_test(self):
+        """One fused launch on known data (learning rate 0: parameters untouched, the bucket keeps the average) checked
+        against the closed form; raises if the peers did not meet or the average is wrong. Collective: every rank calls
+        it. Leaves the bucket zeroed. Costs one launch (or ~2 s if a peer never arrives: the kernel gives up)."""
+        from cwn_b200 import _lib
+        n = self.flat.numel()
+        dev = self.flat.device
+        with torch.cuda.device(dev):
+            base = torch.arange(n, dtype=torch.float32, device=dev).remainder_(97.0).add_(1.0)
+            self.flat.copy_(base * float(self.rank + 1))
+            scratch = torch.zeros(3, n, dtype=torch.float32, device=dev)
+            step = torch.zeros(2, dtype=torch.int32, device=dev)
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            _lib.check(_lib.load().cwn_allreduce_adam_step_f32(
+                scratch[0].data_ptr(), self.grad_handle.buffer_ptrs_dev, self.pad_handle.buffer_ptrs_dev, self.rank,
+                self.world, self.n_ctas, scratch[1].data_ptr(), scratch[2].data_ptr(), n, 0.0, 0.9, 0.999, 1e-8, 0.0,
+                step[0:1].data_ptr(), step[1:2].data_ptr(), 0, self.error.data_ptr(),
+                torch.cuda.current_stream().cuda_stream), 'cwn_allreduce_adam_step_f32 (self test)')
+            torch.cuda.synchronize(dev)
+            self.check()
+            expect = base * (sum(range(1, self.world + 1)) / self.world)
+            err = float((self.flat - expect).abs().max())
+            dist.barrier()
+            self.flat.zero_()
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+        if err > 1e-3:
+            raise RuntimeError(f'cwn_b200: fused all-reduce self test: average off by {err}')
+
     def check(self):
         """Raise if a fused step ever gave up waiting for a peer (host sync: call it outside the hot loop)."""
         code = int(self.error.item())

@@ -43,6 +43,8 @@ def _tile_rows(row_counts):
 _TILE32_BELOW = int(os.environ.get('CWN_B200_TILE32_BELOW', '96'))  # A/B switch for profiling
 _FORCED_TILE_ROWS = int(os.environ.get('CWN_B200_TILE_ROWS', '0'))  # A/B switch for profiling (32 or 64)
 _TC5 = os.environ.get('CWN_B200_DENSE_TC5', '1') != '0'  # tcgen05 dense kernels (default); 0 = FFMA kernels
+# BatchNorm-backward reductions of a unit taken from the g_in tiles of the unit downstream (no launch of their own); 0 = A/B
+_FUSE_REDUCE = os.environ.get('CWN_B200_FUSE_REDUCE', '1') != '0'
 
 
 # Live row counts of a fixed-capacity (padded) batch: one int32 DEVICE scalar per cochain dimension, or None.
@@ -386,17 +388,37 @@ class FusedSparseCINDense(Function):
             keep.append(t)
             return t
 
+        bn_bufs = {}  # id(state) -> BatchNorm-backward buffers of that unit (shared by its own descriptor and, when the
+        #               reduction is fused, by the `next_*` fields of the unit downstream)
+
+        def bn_backward_buffers(st, tr):
+            b = bn_bufs.get(id(st))
+            if b is None:
+                unit = st.unit
+                n_tiles = (st.n + tr - 1) // tr
+                red, c1, c2 = new(max(n_tiles, 1) * 2 * st.h), new(st.h), new(st.h)
+                gg, gbeta = _direct_grad(unit.bn.weight), _direct_grad(unit.bn.bias)
+                acc_a = int(gg is not None and gbeta is not None)
+                if not acc_a:
+                    gg, gbeta = new(st.h), new(st.h)
+                    grads[id(unit.bn.weight)], grads[id(unit.bn.bias)] = gg, gbeta
+                b = bn_bufs[id(st)] = dict(red=red, c1=c1, c2=c2, gg=gg, gbeta=gbeta, acc_a=acc_a, tr=tr, reduced=False)
+            return b
+
         def unit_descs(items):
-            """items: list of (state, g_out, want_g_in0, want_g_in1) -> (descs, list of (g_in0, g_in1))"""
-            descs, gins = [], []
-            counters = _counters(dev, len(items))
+            """items: list of (state, g_out, want_g_in0, want_g_in1[, upstream0, upstream1]) -> (descs, list of (g_in0,
+            g_in1)). `upstream_i`: the unit whose output is input block i (its BatchNorm-backward reduction is then
+            taken from this unit's g_in tiles, cwn_unit_bwd_desc::next_*), or None."""
+            descs, gins, ups = [], [], []
+            counters = _counters(dev, 2 * len(items))
             tr = _tile_rows([it[0].n for it in items])
             ctas = _n_ctas([(it[0].n + tr - 1) // tr for it in items])
-            for i, (st, g, want0, want1) in enumerate(items):
+            for i, it in enumerate(items):
+                st, g, want0, want1 = it[:4]
+                up0, up1 = (it[4], it[5]) if len(it) > 4 else (None, None)
                 unit = st.unit
                 k0 = st.x0.size(1)
                 k1 = st.x1.size(1) if st.x1 is not None else 0
-                n_tiles = (st.n + tr - 1) // tr
                 n_ctas = ctas[i]
                 has_bn = unit.bn is not None
                 g = g if (g.stride(1) == 1 and g.stride(0) % 4 == 0) else g.contiguous()  # (column ranges stay views)
@@ -411,12 +433,18 @@ class FusedSparseCINDense(Function):
                 red = c1 = c2 = gg = gbeta = None
                 acc_a = 0
                 if has_bn:
-                    red, c1, c2 = new(max(n_tiles, 1) * 2 * st.h), new(st.h), new(st.h)
-                    gg, gbeta = _direct_grad(unit.bn.weight), _direct_grad(unit.bn.bias)
-                    acc_a = int(gg is not None and gbeta is not None)
-                    if not acc_a:
-                        gg, gbeta = new(st.h), new(st.h)
-                        grads[id(unit.bn.weight)], grads[id(unit.bn.bias)] = gg, gbeta
+                    b = bn_backward_buffers(st, tr)
+                    red, c1, c2, gg, gbeta, acc_a = b['red'], b['c1'], b['c2'], b['gg'], b['gbeta'], b['acc_a']
+                def upstream(up, gi):
+                    """(buffers, descriptor fields) of the fused reduction of upstream unit `up` through input gradient `gi`"""
+                    if not (_FUSE_REDUCE and up is not None and up.unit.bn is not None and gi is not None and tr == 64
+                            and up.rstd is not None):
+                        return None, (None,) * 6
+                    b_ = bn_backward_buffers(up, tr)
+                    return b_, (_p(up.rstd), _p(b_['red']), _p(b_['c1']), _p(b_['c2']), _p(b_['gg']), _p(b_['gbeta']))
+                nb0, f0 = upstream(up0, gi0)
+                nb1, f1 = upstream(up1, gi1)
+                any_next = nb0 is not None or nb1 is not None
                 i0 = st.in0 or (None, None, None)
                 i1 = st.in1 or (None, None, None)
                 descs.append(_lib.UnitBwdDesc(
@@ -427,29 +455,49 @@ class FusedSparseCINDense(Function):
                     _p(unit.bn.bias) if has_bn else None, _p(g), g.stride(0), _p(red), _p(c1), _p(c2), _p(gg),
                     _p(gbeta), acc_a, _p(gi0), k0, _p(gi1), k1, _p(new(max(n_ctas, 1) * st.h * (k0 + k1))),
                     _p(new(max(n_ctas, 1) * st.h)), n_ctas, _p(gw), gw.stride(0), _p(gb), acc_w, st.n, st.h,
-                    counters[i:i + 1].data_ptr() if has_bn else None, tr, 0, _p(st.live)))
+                    counters[i:i + 1].data_ptr() if has_bn else None, tr, 0, _p(st.live),
+                    *f0, *f1, nb0['acc_a'] if nb0 else 0, nb1['acc_a'] if nb1 else 0,
+                    counters[len(items) + i:len(items) + i + 1].data_ptr() if any_next else None))
                 keep.append(g)
                 gins.append((gi0, gi1))
-            return descs, gins
+                ups.append((nb0, nb1))
+            return descs, gins, ups
+
+        _NEXT = ('next_rstd0', 'next_red0', 'next_c1_0', 'next_c2_0', 'next_g_gamma0', 'next_g_beta0', 'next_rstd1',
+                 'next_red1', 'next_c1_1', 'next_c2_1', 'next_g_gamma1', 'next_g_beta1', 'next_counter')
 
         def run(items):
-            descs, gins = unit_descs(items)
-            if any(d.has_bn for d in descs):  # column reductions; the last CTA of each problem finalises them
-                _launch('cwn_unit_bwd_reduce_grouped', _lib.UnitBwdDesc, descs)
+            descs, gins, ups = unit_descs(items)
+            if any(nb_ is not None for pair in ups for nb_ in pair):
+                arr = (_lib.UnitBwdDesc * len(descs))(*descs)
+                if len(descs) <= _lib.MAX_GROUP and _lib.load().cwn_unit_bwd_fuses_reduce(arr, len(descs)):
+                    for pair in ups:
+                        for nb_ in pair:
+                            if nb_ is not None:
+                                nb_['reduced'] = True  # this launch produces c1 / c2 / g_gamma / g_beta of the unit upstream
+                else:  # (FFMA fallback shapes, or more than one launch group: the upstream units reduce for themselves)
+                    for d_ in descs:
+                        for name in _NEXT:
+                            setattr(d_, name, None)
+            # column reductions of the units whose g_out did not come out of a fusing launch; the last CTA finalises them
+            todo = [d_ for d_, it in zip(descs, items) if d_.has_bn and not bn_bufs[id(it[0])]['reduced']]
+            if todo:
+                _launch('cwn_unit_bwd_reduce_grouped', _lib.UnitBwdDesc, todo)
             _launch('cwn_unit_bwd_grouped', _lib.UnitBwdDesc, descs)
             return descs, gins
 
         with torch.cuda.device(dev):
             all_descs = []
             g_outs = [g if g is not None else torch.zeros_like(states[d]['c'].z) for d, g in enumerate(g_outs)]
-            descs, gins = run([(states[d]['c'], g_outs[d], True, True) for d in range(n_dims)])
+            descs, gins = run([(states[d]['c'], g_outs[d], True, True) + ((states[d]['u2'], states[d]['b2']) if ctx.nb == 2 else ())
+                                for d in range(n_dims)])
             all_descs += descs
             nb = ctx.nb
             items, slot2 = [], []
             for d in range(n_dims):
                 s = states[d]
                 if nb == 2:
-                    items += [(s['u2'], gins[d][0], True, False), (s['b2'], gins[d][1], True, False)]
+                    items += [(s['u2'], gins[d][0], True, False, s['u1'], None), (s['b2'], gins[d][1], True, False, s['b1'], None)]
                     slot2 += [(d, 'u'), (d, 'b')]
                 else:
                     h = s['u2'].h

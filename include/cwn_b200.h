@@ -308,10 +308,25 @@ typedef struct {
                           * is zero (so they add nothing to g_W / g_b and their g_in rows are written as zeros) and the
                           * BatchNorm-backward means c1, c2 divide by the live count. cwn_unit_bwd_grouped: tensor-core
                           * path only (CWN_E_SHAPE otherwise) */
+  /* FUSED REDUCTION OF THE UPSTREAM UNITS (optional; tensor-core path only, CWN_E_SHAPE otherwise). Input block i of
+   * this unit is the output z of an upstream unit U_i whose BatchNorm + activation are this unit's in_mean_i / in_scale_i /
+   * in_beta_i / in_act; g_in_i is therefore U_i's g_out, and steps 1-2 of U_i (its BatchNorm-backward column sums and
+   * their finalisation) can be taken from the g_in tile while it is still in shared memory instead of by a launch of
+   * their own that re-reads g_in and z from memory. Set next_red_i to U_i's red_partials ([n_tiles, 2, k_i], tiles of 64
+   * rows) to enable it for block i; then next_rstd_i, next_c1_i, next_c2_i are required, next_g_gamma_i / next_g_beta_i /
+   * next_accumulate_affine_i have the meaning of g_gamma / g_beta / accumulate_affine of U_i, and next_counter (zero
+   * int32, reset by the kernel) elects the CTA that finalises. Requires g_in_i != NULL and accumulate_in == 0 (g_in_i must
+   * be U_i's complete output gradient). The caller then skips cwn_unit_bwd_reduce_grouped for U_i.
+   * cwn_unit_bwd_fuses_reduce(descs, n) tells whether a group will take the tensor-core path (1) or not (0). */
+  const float* next_rstd0; float* next_red0; float* next_c1_0; float* next_c2_0; float* next_g_gamma0; float* next_g_beta0;
+  const float* next_rstd1; float* next_red1; float* next_c1_1; float* next_c2_1; float* next_g_gamma1; float* next_g_beta1;
+  int32_t next_accumulate_affine0; int32_t next_accumulate_affine1;
+  int32_t* next_counter;
 } cwn_unit_bwd_desc;
 int cwn_unit_bwd_reduce_grouped(const cwn_unit_bwd_desc* descs, int32_t n, cwn_stream_t stream);
 int cwn_unit_bwd_finalize_grouped(const cwn_unit_bwd_desc* descs, int32_t n, cwn_stream_t stream);
 int cwn_unit_bwd_grouped(const cwn_unit_bwd_desc* descs, int32_t n, cwn_stream_t stream);
+int cwn_unit_bwd_fuses_reduce(const cwn_unit_bwd_desc* descs, int32_t n);
 int cwn_wgrad_finalize_grouped(const cwn_unit_bwd_desc* descs, int32_t n, cwn_stream_t stream);
 
 /* Adam (torch.optim.Adam semantics: L2 weight decay, no amsgrad; reference exp/run_exp.py:343) over flat parameter /

@@ -49,6 +49,8 @@ def _fused_worker(rank, world, port, out):
             model = EmbedSparseCIN(**_CWN_CFG).to(dev).train()
             broadcast_parameters(model, src=0)
             bucket = SymmetricGradBucket(model) if kind == 'fused' else FlatGradBucket(model)
+            if kind == 'fused':
+                bucket.self_test()
             opt = FlatAdam(model, bucket, lr=1e-2)
             assert opt.fuses_allreduce == (kind == 'fused')
             n = sum(p.numel() for p in bucket.params)
