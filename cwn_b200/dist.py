@@ -132,15 +132,19 @@ class SymmetricGradBucket(FlatGradBucket):
                 step[0:1].data_ptr(), step[1:2].data_ptr(), 0, self.error.data_ptr(),
                 torch.cuda.current_stream().cuda_stream), 'cwn_allreduce_adam_step_f32 (self test)')
             torch.cuda.synchronize(dev)
-            self.check()
+            code = int(self.error.item())
             expect = base * (sum(range(1, self.world + 1)) / self.world)
             err = float((self.flat - expect).abs().max())
-            dist.barrier()
+            # the verdict must be the same on every rank (a rank that fell back to NCCL alone would deadlock the others)
+            bad = torch.tensor([float(code != 0 or not err <= 1e-3)], device=dev)
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX)
             self.flat.zero_()
+            self.error.zero_()
             torch.cuda.synchronize(dev)
             dist.barrier()
-        if err > 1e-3:
-            raise RuntimeError(f'cwn_b200: fused all-reduce self test: average off by {err}')
+        if float(bad.item()) != 0.0:
+            raise RuntimeError(f'cwn_b200: fused all-reduce self test failed on some rank (here: barrier code {code}, '
+                               f'average off by {err})')
 
     def check(self):
         """Raise if a fused step ever gave up waiting for a peer (host sync: call it outside the hot loop)."""
