@@ -107,6 +107,12 @@ _SIGNATURES = {
                                            _i32, _c_f32p, _i64, _c_f32p, _c_f32p, _i64, _vp]),
     'cwn_csr_cob_bwd_f32': (ctypes.c_int, [_c_f32p, _i64, _c_f32p, _i64, _c_f32p, _i64, _c_i32p, _c_i32p,
                                            _c_i32p, _i64, _i32, _i32, _c_f32p, _i64, _vp]),
+    'cwn_csr_gather_reduce_f64': (ctypes.c_int, [_vp, _i64, _c_i32p, _c_i32p, _i64, _i32, _vp, _i64, _vp, _vp, _i64, _i32, _vp]),
+    'cwn_gather_rows_f64': (ctypes.c_int, [_vp, _i64, _c_i64p, _i64, _i32, ctypes.c_double, _vp, _i64, _vp]),
+    'cwn_csr_cob_fwd_f64': (ctypes.c_int, [_vp, _i64, _vp, _i64, _c_i32p, _c_i32p, _c_i32p, _i64, _i32, _i32, _vp, _i64,
+                                           _vp, _vp, _i64, _vp]),
+    'cwn_csr_cob_bwd_f64': (ctypes.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _c_i32p, _c_i32p, _c_i32p, _i64, _i32, _i32,
+                                           _vp, _i64, _vp]),
     'cwn_csr_tile_windows': (ctypes.c_int, [_c_i32p, _c_i32p, _c_i32p, _i64, _i32, _c_i32p, _vp]),
     'cwn_csr_ws_consumer_threads': (ctypes.c_int, []),
     'cwn_csr_ws_stages': (ctypes.c_int, [_i32, _i32, _i32, _i32, _i32, _i32, _i32]),

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(CSRC, 'libcwn_b200.so')
-SOURCES = ['plan.cu', 'gsa.cu', 'gsa_ws.cu', 'dense.cu', 'optim.cu', 'collate.cu', 'head.cu', 'cin_msg.cu']
+SOURCES = ['plan.cu', 'gsa.cu', 'gsa_ws.cu', 'gsa_f64.cu', 'dense.cu', 'optim.cu', 'collate.cu', 'head.cu', 'cin_msg.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC', '-shared']
 

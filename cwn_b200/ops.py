@@ -30,6 +30,22 @@ def _require_cuda_f32(t: Tensor, name: str):
         raise TypeError(f'cwn_b200: `{name}` must be float32, got {t.dtype}')
 
 
+def _require_cuda_float(t: Tensor, name: str, like: Tensor = None):
+    """float32 (the tuned kernels) or float64 (`*_f64` entry points: the reference's SR experiments run in double,
+    exp/run_exp.py:41-43); all floating operands of one call share the dtype."""
+    if not t.is_cuda:
+        raise RuntimeError(f'cwn_b200: `{name}` is on {t.device}; the message-passing path is CUDA-only '
+                           f'(sm_100a kernels, no CPU fallback)')
+    if t.dtype not in (torch.float32, torch.float64):
+        raise TypeError(f'cwn_b200: `{name}` must be float32 or float64, got {t.dtype}')
+    if like is not None and t.dtype != like.dtype:
+        raise TypeError(f'cwn_b200: `{name}` is {t.dtype} but the other operands are {like.dtype}')
+
+
+def _f64(t: Tensor) -> bool:
+    return t.dtype == torch.float64
+
+
 def _rows(t: Tensor) -> Tensor:
     """2-D view with unit inner stride (the C ABI takes an explicit leading dimension)."""
     if t.dim() == 1:
@@ -380,6 +396,14 @@ def _launch_gather_reduce(x_src, plan_rowptr, idx, n_rows, F, x_res, eps, reduce
             cached = idx.__dict__['_cwn_touched'] = int(torch.unique(idx).numel())
         n_src = min(n_src, cached)
     algo = 16 * E + 4 * F * (n_src + n_rows + (n_rows if x_res is not None else 0))
+    ref = x_src if x_src is not None else x_res
+    if ref is not None and _f64(ref):
+        with torch.cuda.device(dev):
+            out = torch.empty(n_rows, F, dtype=torch.float64, device=dev)
+            _call('csr_gather_reduce', 2 * algo - 16 * E, lib.cwn_csr_gather_reduce_f64,
+                  _ptr(x_src), _ld(x_src) if x_src is not None else F, plan_rowptr.data_ptr(), _ptr(idx), n_rows, F,
+                  _ptr(x_res), _ld(x_res) if x_res is not None else F, _ptr(eps), _ptr(out), F, reduce_code, _stream())
+        return out
     ws = None
     if plan is not None and idx is plan.pay0 and reduce_code in (0, 1) and x_src is not None and _ws_ok(x_src, x_res):
         ws = _ws_config(plan, F, 1, x_res is not None)
@@ -402,9 +426,13 @@ def _launch_gather_rows(x, idx, scale):
     lib = _lib.load()
     E, F = idx.numel(), x.size(1)
     with torch.cuda.device(x.device):
-        out = torch.empty(E, F, dtype=torch.float32, device=x.device)
-        _call('gather_rows', 8 * E + 4 * F * (x.size(0) + E), lib.cwn_gather_rows_f32,
-              _ptr(x), _ld(x), _ptr(idx), E, F, float(scale), _ptr(out), F, _stream())
+        out = torch.empty(E, F, dtype=x.dtype, device=x.device)
+        if _f64(x):
+            _call('gather_rows', 8 * E + 8 * F * (x.size(0) + E), lib.cwn_gather_rows_f64,
+                  _ptr(x), _ld(x), _ptr(idx), E, F, float(scale), _ptr(out), F, _stream())
+        else:
+            _call('gather_rows', 8 * E + 4 * F * (x.size(0) + E), lib.cwn_gather_rows_f32,
+                  _ptr(x), _ld(x), _ptr(idx), E, F, float(scale), _ptr(out), F, _stream())
     return out
 
 
@@ -418,9 +446,9 @@ def _residual_grads(needs_res, needs_eps, g, x_res_saved, eps):
     return g_res, g_eps
 
 
-def _check_eps(eps):
+def _check_eps(eps, like=None):
     if eps is not None:
-        _require_cuda_f32(eps, 'eps')
+        _require_cuda_float(eps, 'eps', like)
         if eps.numel() != 1:
             raise ValueError('cwn_b200: eps must hold a single value')
 
@@ -435,6 +463,8 @@ class _GatherReduce(Function):
         plan = adj.by_dst
         F = x_src.size(1)
         arg = None
+        if reduce == 'max' and ctx.needs_input_grad[0] and adj.E > 0 and _f64(x_src):
+            raise NotImplementedError("cwn_b200: the backward of reduce='max' is float32-only (no shipped model uses it)")
         if reduce == 'max' and ctx.needs_input_grad[0] and adj.E > 0:
             # the backward needs to know WHICH message won every (row, feature): a scalar kernel that tracks it
             with torch.cuda.device(x_src.device):
@@ -479,6 +509,12 @@ class _GatherReduce(Function):
 
 def _launch_cob_bwd(algo, g, A, B, plan, E, n_rows, F, act, gA):
     lib = _lib.load()
+    if _f64(A):
+        g = g if _f64(g) else g.double()
+        _call('csr_cob_bwd', 2 * algo - 24 * E, lib.cwn_csr_cob_bwd_f64,
+              _ptr(g), _ld(g), _ptr(A), _ld(A), _ptr(B), _ld(B), plan.rowptr.data_ptr(), _ptr(plan.pay0),
+              _ptr(plan.pay1), n_rows, F, act, _ptr(gA), F, _stream())
+        return
     ws = _ws_config(plan, F, 2, True) if _ws_ok(g, A, B) else None
     if ws is not None:
         windows, tile_rows, cap0, cap1, capm = ws
@@ -501,10 +537,15 @@ class _CobPass(Function):
         plan = adj.by_dst
         F = P.size(1)
         with torch.cuda.device(P.device):
-            out = torch.empty(adj.n_dst, F, dtype=torch.float32, device=P.device)
+            out = torch.empty(adj.n_dst, F, dtype=P.dtype, device=P.device)
             algo = 24 * adj.E + 4 * F * (P.size(0) + Q.size(0) + adj.n_dst * (2 if x_res is not None else 1))
-            ws = _ws_config(plan, F, 2, x_res is not None) if _ws_ok(P, Q, x_res) else None
-            if ws is not None:
+            ws = _ws_config(plan, F, 2, x_res is not None) if (not _f64(P) and _ws_ok(P, Q, x_res)) else None
+            if _f64(P):
+                _call('csr_cob_fwd', 2 * algo - 24 * adj.E, lib.cwn_csr_cob_fwd_f64,
+                      _ptr(P), _ld(P), _ptr(Q), _ld(Q), plan.rowptr.data_ptr(), _ptr(plan.pay0), _ptr(plan.pay1),
+                      adj.n_dst, F, ACT_CODES[act], _ptr(x_res), _ld(x_res) if x_res is not None else F, _ptr(eps),
+                      _ptr(out), F, _stream())
+            elif ws is not None:
                 windows, tile_rows, cap0, cap1, capm = ws
                 _call('csr_cob_fwd', algo, lib.cwn_csr_cob_fwd_ws_f32,
                       _ptr(P), _ld(P), _ptr(Q), _ld(Q), plan.rowptr.data_ptr(), _ptr(plan.pay0), _ptr(plan.pay1), adj.E,
@@ -621,8 +662,8 @@ def cin_message_pass(P: Tensor, Q: Tensor, index: Tensor, att: Tensor, n_dst: in
     if act not in ACT_CODES:
         raise ValueError(f'cwn_b200: unknown activation {act!r}')
     P, Q = _rows(P), _rows(Q)
-    _require_cuda_f32(P, 'P')
-    _require_cuda_f32(Q, 'Q')
+    _require_cuda_float(P, 'P')
+    _require_cuda_float(Q, 'Q', P)
     adj = Adjacency.of(index, P.size(0), n_dst, att, Q.size(0))
     if bn is None:
         return _CobPass.apply(P, Q, None, None, adj, act)
@@ -706,6 +747,8 @@ class _ScatterRows(Function):
         plan = _row_plan(dst, n_dst)
         ctx.dst, ctx.plan, ctx.reduce = dst, plan, reduce
         ctx.arg = None
+        if reduce == 'max' and ctx.needs_input_grad[0] and msg.size(0) > 0 and _f64(msg):
+            raise NotImplementedError("cwn_b200: the backward of reduce='max' is float32-only (no shipped model uses it)")
         if reduce == 'max' and ctx.needs_input_grad[0] and msg.size(0) > 0:
             F = msg.size(1)
             with torch.cuda.device(msg.device):
@@ -746,17 +789,17 @@ def gather_scatter(x_src: Tensor, index: Tensor, n_dst: int, reduce: str = 'add'
     if reduce not in REDUCE_CODES:
         raise ValueError(f'cwn_b200: unknown aggregation {reduce!r}')
     x_src = _rows(x_src)
-    _require_cuda_f32(x_src, 'x_src')
+    _require_cuda_float(x_src, 'x_src')
     if x_res is not None:
         if reduce not in ('add', 'sum'):
             # (the kernel fuses the residual into an additive pass only; refusing here keeps the behaviour the same with
             # and without autograd — the max path with gradients used to drop the residual silently)
             raise ValueError("cwn_b200: a fused residual (x_res) requires reduce='add'")
         x_res = _rows(x_res)
-        _require_cuda_f32(x_res, 'x_res')
+        _require_cuda_float(x_res, 'x_res', x_src)
         if x_res.size(0) != n_dst or x_res.size(1) != x_src.size(1):
             raise ValueError('cwn_b200: residual operand must have shape [n_dst, F]')
-    _check_eps(eps)
+    _check_eps(eps, x_src)
     adj = Adjacency.of(index, x_src.size(0), n_dst)
     return _GatherReduce.apply(x_src, x_res, eps, adj, reduce)
 
@@ -767,14 +810,14 @@ def cob_pass(P: Tensor, Q: Tensor, index: Tensor, cob: Tensor, n_dst: int, act: 
     if act not in ACT_CODES:
         raise ValueError(f'cwn_b200: unknown activation {act!r}')
     P, Q = _rows(P), _rows(Q)
-    _require_cuda_f32(P, 'P')
-    _require_cuda_f32(Q, 'Q')
+    _require_cuda_float(P, 'P')
+    _require_cuda_float(Q, 'Q', P)
     if P.size(1) != Q.size(1):
         raise ValueError('cwn_b200: P and Q must have the same width')
     if x_res is not None:
         x_res = _rows(x_res)
-        _require_cuda_f32(x_res, 'x_res')
-    _check_eps(eps)
+        _require_cuda_float(x_res, 'x_res', P)
+    _check_eps(eps, P)
     if cob.numel() != index.size(1):
         raise ValueError('cwn_b200: one coboundary id per message is required')
     adj = Adjacency.of(index, P.size(0), n_dst, cob, Q.size(0))
@@ -784,7 +827,7 @@ def cob_pass(P: Tensor, Q: Tensor, index: Tensor, cob: Tensor, n_dst: int, act: 
 def gather_rows(x: Tensor, idx: Tensor, scale: float = 1.0) -> Tensor:
     """`scale * x.index_select(0, idx)` (reference `__lift__`, mp/cell_mp.py:195-198)."""
     x = _rows(x)
-    _require_cuda_f32(x, 'x')
+    _require_cuda_float(x, 'x')
     if idx.dtype != torch.long or not idx.is_cuda:
         raise TypeError('cwn_b200: gather index must be a CUDA torch.long tensor')
     return _GatherRows.apply(x, idx.contiguous(), float(scale))
@@ -795,7 +838,7 @@ def scatter_rows(msg: Tensor, dst: Tensor, n_dst: int, reduce: str = 'add') -> T
     if reduce not in REDUCE_CODES:
         raise ValueError(f'cwn_b200: unknown aggregation {reduce!r}')
     msg = _rows(msg)
-    _require_cuda_f32(msg, 'messages')
+    _require_cuda_float(msg, 'messages')
     if dst.dtype != torch.long or not dst.is_cuda:
         raise TypeError('cwn_b200: scatter index must be a CUDA torch.long tensor')
     if dst.numel() != msg.size(0):

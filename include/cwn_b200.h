@@ -152,6 +152,23 @@ int cwn_csr_cob_bwd_f32(const float* G, int64_t ld_g, const float* A, int64_t ld
                         const int32_t* rowptr, const int32_t* dst, const int32_t* oth, int64_t n_rows, int32_t F,
                         int32_t act, float* gA, int64_t ld_ga, cwn_stream_t stream);
 
+/* fp64 instantiations of cwn_csr_gather_reduce_f32, cwn_gather_rows_f32, cwn_csr_cob_fwd_f32 and cwn_csr_cob_bwd_f32
+ * (same contracts; `eps` and `scale` are double): the reference runs its strongly-regular-graph isomorphism experiments
+ * in float64 (exp/run_exp.py:41-43). Same in-row order => bit-identical to a sequential CPU scatter_add_ in double.
+ * Plain kernels (those datasets are small); matrices need 8-byte alignment only. */
+int cwn_csr_gather_reduce_f64(const double* x_src, int64_t ld_src, const int32_t* rowptr, const int32_t* idx,
+                              int64_t n_rows, int32_t F, const double* x_res, int64_t ld_res, const double* eps,
+                              double* out, int64_t ld_out, int32_t reduce, cwn_stream_t stream);
+int cwn_gather_rows_f64(const double* x, int64_t ld_x, const int64_t* idx, int64_t E, int32_t F, double scale,
+                        double* out, int64_t ld_out, cwn_stream_t stream);
+int cwn_csr_cob_fwd_f64(const double* P, int64_t ld_p, const double* Q, int64_t ld_q, const int32_t* rowptr,
+                        const int32_t* src, const int32_t* cob, int64_t n_rows, int32_t F, int32_t act,
+                        const double* x_res, int64_t ld_res, const double* eps, double* out, int64_t ld_out,
+                        cwn_stream_t stream);
+int cwn_csr_cob_bwd_f64(const double* G, int64_t ld_g, const double* A, int64_t ld_a, const double* B, int64_t ld_b,
+                        const int32_t* rowptr, const int32_t* dst, const int32_t* oth, int64_t n_rows, int32_t F,
+                        int32_t act, double* gA, int64_t ld_ga, cwn_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * The three passes above for the HBM-bound regime (tens of thousands of rows and more per launch), warp-specialised:
  * one producer warp per persistent CTA streams, several tiles ahead, the plan slices, the operand-row WINDOWS and the
