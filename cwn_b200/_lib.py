@@ -115,6 +115,7 @@ _SIGNATURES = {
                                            _vp, _i64, _vp]),
     'cwn_csr_tile_windows': (ctypes.c_int, [_c_i32p, _c_i32p, _c_i32p, _i64, _i32, _c_i32p, _vp]),
     'cwn_csr_ws_consumer_threads': (ctypes.c_int, []),
+    'cwn_csr_ws_lanes_per_row': (ctypes.c_int, [_i32]),
     'cwn_csr_ws_stages': (ctypes.c_int, [_i32, _i32, _i32, _i32, _i32, _i32, _i32]),
     'cwn_csr_gather_reduce_ws_f32': (ctypes.c_int, [_c_f32p, _i64, _c_i32p, _c_i32p, _i64, _c_i32p, _i32, _i32, _i32,
                                                     _i64, _i32, _c_f32p, _i64, _c_f32p, _c_f32p, _i64, _i32, _vp]),

@@ -31,7 +31,11 @@ namespace cwn {
 namespace ws {
 
 #ifndef CWN_WS_CONSUMER_WARPS
-#define CWN_WS_CONSUMER_WARPS 16  // A/B switch (build_variant). Measured, edge-upper F=64 at 1M rows: 8 -> 108 us, 16 -> 91 us
+// A/B switch (build_variant). Measured, edge-upper F = 64 at 1M rows, one vector per lane: 8 consumer warps 108 us,
+// 16 -> 84 us, 20 -> 85 us, 24 -> 98 us. Registers are allocated per SM sub-partition (4 x 16 384): with the producer that
+// makes 17 warps, 5 on one sub-partition, i.e. at most 96 registers per thread (what ptxas derives from
+// __launch_bounds__(544, 1); 112 or 120 via __maxnreg__ fail to launch) — enough for one vector per lane.
+#define CWN_WS_CONSUMER_WARPS 16
 #endif
 constexpr int kConsumerWarps = CWN_WS_CONSUMER_WARPS;
 constexpr int kBlock = 32 * (kConsumerWarps + 1);
@@ -171,8 +175,10 @@ struct SmemView {
   uint32_t rowbytes;
   __device__ __forceinline__ int row_begin(int i) const { return lds32(rp + 4u * (uint32_t)i); }
   __device__ __forceinline__ int index(int a, int m) const { return lds32(ix[a] + 4u * (uint32_t)m); }
-  __device__ __forceinline__ float4 feature(int a, int row) const { return lds128(ft[a] + (uint32_t)row * rowbytes); }
-  __device__ __forceinline__ float4 rowop(int i) const { return lds128(ro + (uint32_t)i * rowbytes); }
+  __device__ __forceinline__ float4 feature(int a, int row, uint32_t koff) const {
+    return lds128(ft[a] + (uint32_t)row * rowbytes + koff);
+  }
+  __device__ __forceinline__ float4 rowop(int i, uint32_t koff) const { return lds128(ro + (uint32_t)i * rowbytes + koff); }
 };
 template <int NARR>
 struct GenericView {
@@ -184,28 +190,42 @@ struct GenericView {
   uint32_t ro_pitch;
   __device__ __forceinline__ int row_begin(int i) const { return rp[i]; }
   __device__ __forceinline__ int index(int a, int m) const { return ix[a][m]; }
-  __device__ __forceinline__ float4 feature(int a, int row) const {
-    return *reinterpret_cast<const float4*>(ft[a] + (int64_t)row * ft_pitch[a]);
+  __device__ __forceinline__ float4 feature(int a, int row, uint32_t koff) const {
+    return *reinterpret_cast<const float4*>(ft[a] + (int64_t)row * ft_pitch[a] + koff);
   }
-  __device__ __forceinline__ float4 rowop(int i) const {
-    return *reinterpret_cast<const float4*>(ro + (int64_t)i * ro_pitch);
+  __device__ __forceinline__ float4 rowop(int i, uint32_t koff) const {
+    return *reinterpret_cast<const float4*>(ro + (int64_t)i * ro_pitch + koff);
   }
 };
 
+// A lane owns kVPL vectors of a row, LPR * 16 bytes apart. Two vectors per lane (F = 64: 8 lanes per row, four rows per
+// warp instruction) share the plan reads, address arithmetic, predicates and per-row bookkeeping between twice the bytes,
+// but need 128 registers, i.e. 15 consumer warps instead of 16: measured equal (86.4 vs 85.5 us on the edge-upper pass,
+// 138 vs 141 us cob bwd, 124 vs 118 us cob fwd; profiles/README.md), so the default stays one vector per lane and 16
+// warps. `live1`: the lane's second vector is inside the row.
+#ifndef CWN_WS_VPL
+#define CWN_WS_VPL 1  // A/B switch (build_variant): vectors per lane
+#endif
+constexpr int kVPL = CWN_WS_VPL;
+
 template <class Pass, int LPR, class View>
 __device__ __forceinline__ void rows_of_tile(const View& v, int first, int rows, int m1, bool has_ro, float scale,
-                                             char* out_lane, int64_t r0, uint32_t pitch_out) {
+                                             char* out_lane, int64_t r0, uint32_t pitch_out, bool live1) {
   constexpr int G = kConsumerWarps * 32 / LPR;
   constexpr int NARR = Pass::NARR, kU = Pass::kU;
+  constexpr uint32_t kStep = LPR * 16;
   for (int i = first; i < rows; i += G) {
     const int beg = v.row_begin(i);
     const int end = (i == rows - 1) ? m1 : v.row_begin(i + 1);
-    float4 a_row = zero4();
-    if (Pass::kRowFirst) a_row = v.rowop(i);
-    float4 acc = zero4();
+    float4 a_row[kVPL], acc[kVPL];
+#pragma unroll
+    for (int k = 0; k < kVPL; ++k) {
+      acc[k] = zero4();
+      a_row[k] = (Pass::kRowFirst && (k == 0 || live1)) ? v.rowop(i, k * kStep) : zero4();
+    }
     for (int m = beg; m < end; m += kU) {
       int j0[kU], j1[kU];
-      float4 v0[kU], v1[kU];
+      float4 v0[kU][kVPL], v1[kU][kVPL];
 #pragma unroll
       for (int u = 0; u < kU; ++u)
         if (m + u < end) {
@@ -215,18 +235,30 @@ __device__ __forceinline__ void rows_of_tile(const View& v, int first, int rows,
 #pragma unroll
       for (int u = 0; u < kU; ++u)
         if (m + u < end) {
-          v0[u] = v.feature(0, j0[u]);
-          if (NARR == 2) v1[u] = v.feature(NARR - 1, j1[u]);
-          else v1[u] = zero4();
+#pragma unroll
+          for (int k = 0; k < kVPL; ++k) {
+            v0[u][k] = v1[u][k] = zero4();
+            if (k == 0 || live1) {
+              v0[u][k] = v.feature(0, j0[u], k * kStep);
+              if (NARR == 2) v1[u][k] = v.feature(NARR - 1, j1[u], k * kStep);
+            }
+          }
         }
 #pragma unroll
       for (int u = 0; u < kU; ++u)
-        if (m + u < end) acc = Pass::fold(acc, v0[u], v1[u], a_row);
+        if (m + u < end) {
+#pragma unroll
+          for (int k = 0; k < kVPL; ++k) acc[k] = Pass::fold(acc[k], v0[u][k], v1[u][k], a_row[k]);
+        }
     }
-    float4 ro = zero4();
-    if (!Pass::kRowFirst && has_ro) ro = v.rowop(i);
-    const float4 res = Pass::finish(acc, end - beg, has_ro, scale, ro);
-    *reinterpret_cast<float4*>(out_lane + (r0 + i) * (int64_t)pitch_out) = res;
+#pragma unroll
+    for (int k = 0; k < kVPL; ++k) {
+      if (k == 1 && !live1) break;
+      float4 ro = zero4();
+      if (!Pass::kRowFirst && has_ro) ro = v.rowop(i, k * kStep);
+      const float4 res = Pass::finish(acc[k], end - beg, has_ro, scale, ro);
+      *reinterpret_cast<float4*>(out_lane + (r0 + i) * (int64_t)pitch_out + k * kStep) = res;
+    }
   }
 }
 
@@ -346,6 +378,7 @@ __global__ void __launch_bounds__(kBlock, 1) csr_ws_kernel(const __grid_constant
     const int ct = (warp - 1) * 32 + lane;
     const int grp = ct / LPR, gl = ct % LPR;
     const bool live = gl < p.FV;
+    const bool live1 = gl + LPR < p.FV;
     const bool has_ro = p.rowop != nullptr;
     const float scale = (has_ro && !Pass::kRowFirst) ? __fadd_rn(1.f, p.eps ? __ldg(p.eps) : 0.f) : 0.f;
     char* out_lane = p.out + (size_t)gl * 16;
@@ -377,7 +410,7 @@ __global__ void __launch_bounds__(kBlock, 1) csr_ws_kernel(const __grid_constant
             v.ix[a] = st + p.off_ix[a] - 4u * (uint32_t)c.a0;
             v.ft[a] = st + p.off_ft[a] + (uint32_t)gl * 16u - (uint32_t)(a == 0 ? c.lo0 : c.lo1) * p.rowbytes;
           }
-          rows_of_tile<Pass, LPR>(v, first, c.rows, c.m1, has_ro, scale, out_lane, r0, p.pitch_out);
+          rows_of_tile<Pass, LPR>(v, first, c.rows, c.m1, has_ro, scale, out_lane, r0, p.pitch_out, live1);
         } else {
           GenericView<NARR> v;
           const unsigned char* st = dyn + (size_t)s * p.stage_bytes;
@@ -398,7 +431,7 @@ __global__ void __launch_bounds__(kBlock, 1) csr_ws_kernel(const __grid_constant
             v.ro = p.rowop ? p.rowop + (size_t)r0 * p.pitch_ro + (size_t)gl * 16 : nullptr;
             v.ro_pitch = p.pitch_ro;
           }
-          rows_of_tile<Pass, LPR>(v, first, c.rows, c.m1, has_ro, scale, out_lane, r0, p.pitch_out);
+          rows_of_tile<Pass, LPR>(v, first, c.rows, c.m1, has_ro, scale, out_lane, r0, p.pitch_out, live1);
         }
       }
       __syncwarp();
@@ -478,10 +511,10 @@ static int configure(Params& p, int F, int tile_rows, int cap_rows0, int cap_row
   return stages;
 }
 
-static int lanes_per_row(int FV) {
-  int lpr = 4;
-  while (lpr < FV) lpr <<= 1;
-  return lpr;
+static int lanes_per_row(int FV) {  // two vectors per lane (kVPL)
+  int lpr = 2;
+  while (lpr * kVPL < FV) lpr <<= 1;
+  return lpr;  // (FV <= 32: at most 32 with one vector per lane, 16 with two)
 }
 
 template <class Pass, int LPR>
@@ -501,6 +534,7 @@ static int launch(const Params& p, cudaStream_t st) {
 
 #define CWN_WS_BY_LPR(PASS)                                   \
   switch (lanes_per_row(p.FV)) {                              \
+    case 2: rc = launch<PASS, 2>(p, st); break;               \
     case 4: rc = launch<PASS, 4>(p, st); break;               \
     case 8: rc = launch<PASS, 8>(p, st); break;               \
     case 16: rc = launch<PASS, 16>(p, st); break;             \
@@ -552,6 +586,7 @@ extern "C" int cwn_csr_tile_windows(const int32_t* rowptr, const int32_t* pay0, 
 }
 
 extern "C" int cwn_csr_ws_consumer_threads(void) { return 32 * kConsumerWarps; }
+extern "C" int cwn_csr_ws_lanes_per_row(int32_t F) { return (F > 0 && F % 4 == 0) ? lanes_per_row(F / 4) : 0; }
 
 extern "C" int cwn_csr_ws_stages(int32_t F, int32_t tile_rows, int32_t cap_rows0, int32_t cap_rows1, int32_t cap_msgs,
                                  int32_t n_arrays, int32_t has_row_operand) {

@@ -173,11 +173,7 @@ def _ws_config(plan: Plan, F: int, narr: int, rowop: bool):
     forced = int(os.environ.get('CWN_B200_WS_TILE', '0'))
     # ... and no shorter than the number of lane groups that share its rows (a plan with few, heavy rows — the
     # by-coboundary plan: ~26 messages per ring — would leave most consumer groups idle: it keeps the row kernels)
-    fv = F // 4
-    lpr = 4
-    while lpr < fv:
-        lpr *= 2
-    groups = lib.cwn_csr_ws_consumer_threads() // lpr
+    groups = lib.cwn_csr_ws_consumer_threads() // lib.cwn_csr_ws_lanes_per_row(F)
     for tile_rows in ((forced,) if forced else (256, 128, 64, 32, 16)):
         if tile_rows < groups and not forced:
             break

@@ -187,7 +187,8 @@ int cwn_csr_cob_bwd_f64(const double* G, int64_t ld_g, const double* A, int64_t 
  * E = number of messages of the plan (length of the payload columns). */
 int cwn_csr_tile_windows(const int32_t* rowptr, const int32_t* pay0, const int32_t* pay1 /* nullable */, int64_t n_rows,
                          int32_t tile_rows, int32_t* windows, cwn_stream_t stream);
-int cwn_csr_ws_consumer_threads(void); /* rows of a tile are shared by consumer_threads / lanes_per_row groups */
+int cwn_csr_ws_consumer_threads(void); /* rows of a tile are shared by consumer_threads / lanes_per_row(F) groups */
+int cwn_csr_ws_lanes_per_row(int32_t F);
 int cwn_csr_ws_stages(int32_t F, int32_t tile_rows, int32_t cap_rows0, int32_t cap_rows1, int32_t cap_msgs,
                       int32_t n_arrays, int32_t has_row_operand);
 int cwn_csr_gather_reduce_ws_f32(const float* x_src, int64_t ld_src, const int32_t* rowptr, const int32_t* idx,
