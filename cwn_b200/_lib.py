@@ -89,6 +89,8 @@ _SIGNATURES = {
                                             _vp]),
     'cwn_readout_head_bwd': (ctypes.c_int, [_vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp,
                                             _vp, _i32, _vp]),
+    'cwn_readout_head_bwd_parts': (ctypes.c_int, [_vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp,
+                                                  _vp, _i32, _i32, _vp]),
     'cwn_csr_plan_workspace_bytes': (ctypes.c_size_t, [_i64, _i64]),
     'cwn_csr_plan_build': (ctypes.c_int, [_c_i64p, _c_i64p, _c_i64p, _i64, _i64, _c_i32p, _c_i32p, _c_i32p,
                                           _c_i32p, _c_i32p, _vp, ctypes.c_size_t, _vp]),

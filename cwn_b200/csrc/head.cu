@@ -124,47 +124,69 @@ head_bwd_input_kernel(const __grid_constant__ HeadDims dims, int n_dims, int K, 
   }
 }
 
-// parameter gradients: element e of [ g_W1_0 | g_b1_0 | g_W1_1 | ... | g_W2 | g_b2 ], an ordered sum over the complexes
+// parameter gradients: element e of [ g_W1_0 | g_b1_0 | g_W1_1 | ... | g_W2 | g_b2 ] is a sum over the B complexes.
+// A CTA owns 32 consecutive elements (lane -> element: the `pooled` / `h` reads of a warp are coalesced, the g_z / g_out
+// reads are warp broadcasts) and its kHeadThreads / 32 warps each sum one contiguous range of complexes; the ranges are
+// then added in order by warp 0 — a fixed two-level order, so the result does not depend on the launch. (One thread per
+// element walking all 128 complexes took 41 us, the longest kernel of the step.)
 __global__ void __launch_bounds__(kHeadThreads)
 head_bwd_param_kernel(const __grid_constant__ HeadDims dims, int n_dims, int64_t B, int K, int H2, int out_size,
                       const float* __restrict__ h, const float* __restrict__ g_out, float* __restrict__ g_w2,
                       float* __restrict__ g_b2, int accumulate_out) {
   pdl_trigger();  // programmatic dependent launch: see common.cuh
   pdl_wait();
+  constexpr int kWarps = kHeadThreads / 32;
+  __shared__ float part[kWarps][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t per_dim = (int64_t)H2 * K + H2;
   const int64_t total = per_dim * n_dims + (int64_t)out_size * H2 + out_size;
-  for (int64_t e = (int64_t)blockIdx.x * kHeadThreads + threadIdx.x; e < total; e += (int64_t)gridDim.x * kHeadThreads) {
+  const int64_t chunk = (B + kWarps - 1) / kWarps;
+  const int64_t b0 = warp * chunk, b1 = (b0 + chunk < B) ? b0 + chunk : B;
+  for (int64_t e0 = (int64_t)blockIdx.x * 32; e0 < total; e0 += (int64_t)gridDim.x * 32) {
+    const int64_t e = e0 + lane;
+    float acc = 0.f;
+    float* dst = nullptr;
+    bool accumulate = false;
     if (e < per_dim * n_dims) {
       const int d = (int)(e / per_dim);
       const int64_t r = e - d * per_dim;
       const cwn_head_dim& D = dims.d[d];
-      float acc = 0.f;
+      accumulate = D.accumulate != 0;
       if (r < (int64_t)H2 * K) {
-        if (!D.g_w1) continue;
         const int j = (int)(r / K), k = (int)(r - (int64_t)j * K);
-        for (int64_t b = 0; b < B; ++b) acc = fmaf(D.g_z[b * H2 + j], D.pooled[b * K + k], acc);
-        D.g_w1[r] = (D.accumulate ? D.g_w1[r] : 0.f) + acc;
+        dst = D.g_w1 ? D.g_w1 + r : nullptr;
+        if (dst)
+          for (int64_t b = b0; b < b1; ++b) acc = fmaf(D.g_z[b * H2 + j], D.pooled[b * K + k], acc);
       } else {
-        if (!D.g_b1) continue;
         const int j = (int)(r - (int64_t)H2 * K);
-        for (int64_t b = 0; b < B; ++b) acc += D.g_z[b * H2 + j];
-        D.g_b1[j] = (D.accumulate ? D.g_b1[j] : 0.f) + acc;
+        dst = D.g_b1 ? D.g_b1 + j : nullptr;
+        if (dst)
+          for (int64_t b = b0; b < b1; ++b) acc += D.g_z[b * H2 + j];
       }
-    } else {
+    } else if (e < total) {
       const int64_t r = e - per_dim * n_dims;
-      float acc = 0.f;
+      accumulate = accumulate_out != 0;
       if (r < (int64_t)out_size * H2) {
-        if (!g_w2) continue;
         const int o = (int)(r / H2), j = (int)(r - (int64_t)o * H2);
-        for (int64_t b = 0; b < B; ++b) acc = fmaf(__ldg(g_out + b * out_size + o), __ldg(h + b * H2 + j), acc);
-        g_w2[r] = (accumulate_out ? g_w2[r] : 0.f) + acc;
+        dst = g_w2 ? g_w2 + r : nullptr;
+        if (dst)
+          for (int64_t b = b0; b < b1; ++b) acc = fmaf(__ldg(g_out + b * out_size + o), __ldg(h + b * H2 + j), acc);
       } else {
-        if (!g_b2) continue;
         const int o = (int)(r - (int64_t)out_size * H2);
-        for (int64_t b = 0; b < B; ++b) acc += __ldg(g_out + b * out_size + o);
-        g_b2[o] = (accumulate_out ? g_b2[o] : 0.f) + acc;
+        dst = g_b2 ? g_b2 + o : nullptr;
+        if (dst)
+          for (int64_t b = b0; b < b1; ++b) acc += __ldg(g_out + b * out_size + o);
       }
     }
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && dst) {
+      float s = part[0][lane];
+#pragma unroll
+      for (int w = 1; w < kWarps; ++w) s += part[w][lane];
+      *dst = (accumulate ? *dst : 0.f) + s;
+    }
+    __syncthreads();
   }
 }
 
@@ -215,11 +237,28 @@ extern "C" int cwn_readout_head_fwd(const cwn_head_dim* dims, int32_t n_dims, in
   return launched("cwn_readout_head_fwd");
 }
 
+extern "C" int cwn_readout_head_bwd_parts(const cwn_head_dim* dims, int32_t n_dims, int64_t B, int32_t K, int32_t H2,
+                                          int32_t out_size, int32_t act, int32_t pool_mean, int32_t final_mean,
+                                          const float* w2, const float* h, const float* g_out, float* g_w2, float* g_b2,
+                                          int32_t accumulate_out, int32_t parts, cwn_stream_t stream);
+
 extern "C" int cwn_readout_head_bwd(const cwn_head_dim* dims, int32_t n_dims, int64_t B, int32_t K, int32_t H2,
                                     int32_t out_size, int32_t act, int32_t pool_mean, int32_t final_mean,
                                     const float* w2, const float* h, const float* g_out, float* g_w2, float* g_b2,
                                     int32_t accumulate_out, cwn_stream_t stream) {
+  return cwn_readout_head_bwd_parts(dims, n_dims, B, K, H2, out_size, act, pool_mean, final_mean, w2, h, g_out, g_w2, g_b2,
+                                    accumulate_out, 3, stream);
+}
+
+// parts: bit 0 = input gradients (g_z, g_x: what the rest of the backward pass waits for), bit 1 = parameter gradients
+// (ordered sums over the complexes, ~40 us at B = 128: nothing reads them before the optimizer, so a caller may issue
+// them on another stream once the first part has been launched)
+extern "C" int cwn_readout_head_bwd_parts(const cwn_head_dim* dims, int32_t n_dims, int64_t B, int32_t K, int32_t H2,
+                                          int32_t out_size, int32_t act, int32_t pool_mean, int32_t final_mean,
+                                          const float* w2, const float* h, const float* g_out, float* g_w2, float* g_b2,
+                                          int32_t accumulate_out, int32_t parts, cwn_stream_t stream) {
   int rc;
+  if (!(parts & 3)) return fail(CWN_E_ENUM, "cwn_readout_head_bwd_parts: parts must have bit 0 and / or bit 1 set");
   if ((rc = check_head(dims, n_dims, B, K, H2, out_size, act, false))) return rc;
   if (!w2 || !h || !g_out) return fail(CWN_E_NULL, "cwn_readout_head_bwd: w2 / h / g_out");
   for (int d = 0; d < n_dims; ++d) {
@@ -231,14 +270,18 @@ extern "C" int cwn_readout_head_bwd(const cwn_head_dim* dims, int32_t n_dims, in
   for (int d = 0; d < n_dims; ++d) hd.d[d] = dims[d];
   const size_t smem = (size_t)n_dims * H2 * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-  CWN_HEAD_BY_ACT(act, {
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(head_bwd_input_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    launch_pdl(head_bwd_input_kernel<ACT>, (int)B, kHeadThreads, smem, st, hd, n_dims, K, H2, out_size, pool_mean, final_mean, w2, g_out);
-  })
-  const int64_t total = ((int64_t)H2 * K + H2) * n_dims + (int64_t)out_size * H2 + out_size;
-  int64_t grid = (total + kHeadThreads - 1) / kHeadThreads;
-  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-  launch_pdl(head_bwd_param_kernel, (int)grid, kHeadThreads, 0, st, hd, n_dims, B, K, H2, out_size, h, g_out, g_w2, g_b2, accumulate_out);
-  return launched("cwn_readout_head_bwd", 2);
+  if (parts & 1) {
+    CWN_HEAD_BY_ACT(act, {
+      if (smem > 48 * 1024)
+        cudaFuncSetAttribute(head_bwd_input_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      launch_pdl(head_bwd_input_kernel<ACT>, (int)B, kHeadThreads, smem, st, hd, n_dims, K, H2, out_size, pool_mean, final_mean, w2, g_out);
+    })
+  }
+  if (parts & 2) {
+    const int64_t total = ((int64_t)H2 * K + H2) * n_dims + (int64_t)out_size * H2 + out_size;
+    int64_t grid = (total + 31) / 32;  // 32 elements per CTA (see head_bwd_param_kernel)
+    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+    launch_pdl(head_bwd_param_kernel, (int)grid, kHeadThreads, 0, st, hd, n_dims, B, K, H2, out_size, h, g_out, g_w2, g_b2, accumulate_out);
+  }
+  return launched("cwn_readout_head_bwd", (unsigned)((parts & 1) + ((parts >> 1) & 1)));
 }

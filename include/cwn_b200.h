@@ -418,6 +418,13 @@ int cwn_readout_head_fwd(const cwn_head_dim* dims, int32_t n_dims, int64_t B, in
 int cwn_readout_head_bwd(const cwn_head_dim* dims, int32_t n_dims, int64_t B, int32_t K, int32_t H2, int32_t out_size,
                          int32_t act, int32_t pool_mean, int32_t final_mean, const float* w2, const float* h,
                          const float* g_out, float* g_w2, float* g_b2, int32_t accumulate_out, cwn_stream_t stream);
+/* The same in two parts (`parts`: bit 0 = input gradients g_z / g_x, bit 1 = parameter gradients). Nothing in the rest
+ * of a backward pass reads the parameter gradients, so a caller can launch part 2 on another stream after part 1 and
+ * keep its ~40 us of ordered sums off the critical path. cwn_readout_head_bwd == parts 3. */
+int cwn_readout_head_bwd_parts(const cwn_head_dim* dims, int32_t n_dims, int64_t B, int32_t K, int32_t H2,
+                               int32_t out_size, int32_t act, int32_t pool_mean, int32_t final_mean, const float* w2,
+                               const float* h, const float* g_out, float* g_w2, float* g_b2, int32_t accumulate_out,
+                               int32_t parts, cwn_stream_t stream);
 
 #ifdef __cplusplus
 }
