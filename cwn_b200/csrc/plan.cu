@@ -11,6 +11,7 @@
 //   2. cub::DeviceRadixSort::SortPairs over ceil(log2(n_rows+1)) bits (LSD radix sort => stable)
 //   3. finish_plan   : rowptr[r] = lower_bound(sorted keys, r); payload columns permuted + narrowed to int32
 #include <cub/block/block_radix_sort.cuh>
+#include <cub/block/block_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include "common.cuh"
 
@@ -123,6 +124,113 @@ small_plans_kernel(const __grid_constant__ PlanBatch batch, int32_t* flags) {
   }
 }
 
+// ---- the same plans by COUNTING instead of sorting (default for the plans of a real batch). The radix kernel above moves
+// 12 288 padded (key, value) pairs through four ranking + exchange passes whatever E is: 49 us at the benchmark's batch —
+// the FIRST kernel of every step, fully on its critical path. A stable grouping needs less: histogram the keys
+// (shared-memory atomics), scan the histogram into rowptr, scatter every message id to a slot of its row in ARBITRARY
+// order (atomic cursor), then sort each row's few ids ascending — which makes the result the unique stable grouping,
+// identical to the radix sort's, however the atomics interleaved. Rows of <= kInsertMax ids are sorted by one thread
+// (insertion sort in shared memory), longer rows by a warp (rank by counting, L^2 / 32 steps per lane). Meant for short
+// rows: the host sends plans with E / n_rows > kCountMaxAvgRow, or whose tables do not fit shared memory, to the radix
+// kernel. ~8 us for the 13 plans of a 128-molecule batch.
+constexpr int kCountThreads = 1024;
+constexpr int kInsertMax = 32;
+constexpr int kCountMaxAvgRow = 64;
+constexpr size_t kCountSmemMax = 200 * 1024;
+
+static size_t count_smem_bytes(int64_t E, int64_t n_rows) { return (size_t)(2 * (n_rows + 2) + E) * sizeof(int32_t); }
+static bool count_path_ok(const cwn_plan_desc& d) {
+  return d.E > 0 && d.E <= kCountMaxAvgRow * (d.n_rows > 0 ? d.n_rows : 1) && count_smem_bytes(d.E, d.n_rows) <= kCountSmemMax;
+}
+
+__global__ void __launch_bounds__(kCountThreads)
+small_plans_count_kernel(const __grid_constant__ PlanBatch batch, int32_t* flags) {
+  pdl_trigger();  // programmatic dependent launch: see common.cuh
+  pdl_wait();
+  using Scan = cub::BlockScan<int32_t, kCountThreads>;
+  __shared__ typename Scan::TempStorage scan_temp;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const cwn_plan_desc& p = batch.d[blockIdx.x];
+  const int E = (int)p.E, n_rows = (int)p.n_rows, t = threadIdx.x;
+  const int n_keys = n_rows + 1;                      // row n_rows collects out-of-range keys (behind every real row)
+  int32_t* start = reinterpret_cast<int32_t*>(smem);  // [n_keys + 1]: counts, then their exclusive prefix (= rowptr)
+  int32_t* cur = start + (n_keys + 1);                // [n_keys]: next free slot of every row
+  int32_t* perm_s = cur + (n_keys + 1);               // [E]
+  for (int r = t; r <= n_keys; r += kCountThreads) start[r] = 0;
+  __syncthreads();
+  bool bad = false;
+  for (int e = t; e < E; e += kCountThreads) {
+    const int64_t kk = p.key[e];
+    const bool ok = kk >= 0 && kk < n_rows;
+    bad |= !ok;
+    atomicAdd(&start[ok ? (int)kk : n_rows], 1);
+  }
+  if (bad && flags) atomicOr(flags, 1);
+  __syncthreads();
+  {  // exclusive prefix of the n_keys counts; thread t owns a contiguous segment
+    const int seg = (n_keys + kCountThreads - 1) / kCountThreads;
+    const int lo = min(t * seg, n_keys), hi = min(lo + seg, n_keys);
+    int32_t sum = 0;
+    for (int i = lo; i < hi; ++i) sum += start[i];
+    int32_t base;
+    Scan(scan_temp).ExclusiveSum(sum, base);
+    for (int i = lo; i < hi; ++i) {
+      const int32_t c = start[i];
+      start[i] = base;
+      cur[i] = base;
+      base += c;
+    }
+    if (t == kCountThreads - 1) start[n_keys] = E;
+  }
+  __syncthreads();
+  for (int r = t; r <= n_rows; r += kCountThreads) p.rowptr[r] = start[r];
+  for (int e = t; e < E; e += kCountThreads) {
+    const int64_t kk = p.key[e];
+    const int k = (kk >= 0 && kk < n_rows) ? (int)kk : n_rows;
+    perm_s[atomicAdd(&cur[k], 1)] = e;
+  }
+  __syncthreads();
+  // ascending ids inside every row: short rows by one thread ...
+  for (int r = t; r < n_keys; r += kCountThreads) {
+    const int b = start[r], n = start[r + 1] - b;
+    if (n < 2 || n > kInsertMax) continue;
+    for (int i = 1; i < n; ++i) {
+      const int32_t x = perm_s[b + i];
+      int j = i - 1;
+      while (j >= 0 && perm_s[b + j] > x) {
+        perm_s[b + j + 1] = perm_s[b + j];
+        --j;
+      }
+      perm_s[b + j + 1] = x;
+    }
+  }
+  // ... long rows by a warp: the rank of an id is the number of smaller ids in its row (ids are distinct). The ranked
+  // ids pass through the output array in global memory and come back, so that the write-out below is uniform.
+  {
+    const int warp = t >> 5, lane = t & 31;
+    for (int r = warp; r < n_keys; r += kCountThreads / 32) {
+      const int b = start[r], n = start[r + 1] - b;
+      if (n <= kInsertMax) continue;
+      for (int i = lane; i < n; i += 32) {
+        const int32_t x = perm_s[b + i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += perm_s[b + j] < x;
+        p.perm[b + rank] = x;
+      }
+      __syncwarp();
+      for (int i = lane; i < n; i += 32) perm_s[b + i] = p.perm[b + i];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int pos = t; pos < E; pos += kCountThreads) {
+    const int32_t e = perm_s[pos];
+    p.perm[pos] = e;
+    if (p.pay0) p.pay0_sorted[pos] = (int32_t)p.pay0[e];
+    if (p.pay1) p.pay1_sorted[pos] = (int32_t)p.pay1[e];
+  }
+}
+
 static int key_bits(int64_t n_rows) {  // keys take values 0..n_rows (n_rows = dummy row)
   int bits = 1;
   while ((int64_t(1) << bits) <= n_rows) ++bits;
@@ -209,25 +317,55 @@ extern "C" int cwn_csr_plan_build_small(const cwn_plan_desc* descs, int32_t n_pl
     if (ce != cudaSuccess) return cuda_status(ce, "cudaFuncSetAttribute(small_plans_kernel)");
     configured.store(true, std::memory_order_release);
   }
-  for (int base = 0; base < n_plans; base += kMaxPlansPerLaunch) {
+  for (int i = 0; i < n_plans; ++i) {
+    const cwn_plan_desc& d = descs[i];
+    if (d.E < 0 || d.n_rows < 0 || d.E > kSmallCapacity || d.n_rows >= INT32_MAX)
+      return fail(CWN_E_SHAPE, "cwn_csr_plan_build_small: plan exceeds cwn_csr_plan_small_capacity()");
+    if (!d.rowptr || (d.E > 0 && (!d.key || !d.perm))) return fail(CWN_E_NULL, "plan descriptor");
+    if ((d.pay0 && !d.pay0_sorted) || (d.pay1 && !d.pay1_sorted)) return fail(CWN_E_NULL, "payload output");
+  }
+  static const bool count_enabled = [] { const char* v = getenv("CWN_B200_PLAN_COUNT"); return !(v && v[0] == '0'); }();
+  static std::atomic<bool> count_configured{false};
+  if (count_enabled && !count_configured.load(std::memory_order_acquire)) {
+    cudaError_t ce = cudaFuncSetAttribute(small_plans_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCountSmemMax);
+    if (ce != cudaSuccess) return cuda_status(ce, "cudaFuncSetAttribute(small_plans_count_kernel)");
+    count_configured.store(true, std::memory_order_release);
+  }
+  // short-row plans (what a batch of complexes produces) go to the counting kernel, the rest to the radix kernel
+  for (int pass = 0; pass < 2; ++pass) {
     PlanBatch batch;
-    const int n = (n_plans - base < kMaxPlansPerLaunch) ? n_plans - base : kMaxPlansPerLaunch;
-    for (int i = 0; i < n; ++i) {
-      const cwn_plan_desc& d = descs[base + i];
-      if (d.E < 0 || d.n_rows < 0 || d.E > kSmallCapacity || d.n_rows >= INT32_MAX)
-        return fail(CWN_E_SHAPE, "cwn_csr_plan_build_small: plan exceeds cwn_csr_plan_small_capacity()");
-      if (!d.rowptr || (d.E > 0 && (!d.key || !d.perm))) return fail(CWN_E_NULL, "plan descriptor");
-      if ((d.pay0 && !d.pay0_sorted) || (d.pay1 && !d.pay1_sorted)) return fail(CWN_E_NULL, "payload output");
-      batch.d[i] = d;
-      batch.bits[i] = key_bits(d.n_rows);
-    }
+    int n = 0;
     int64_t max_e = 0;
-    for (int i = 0; i < n; ++i) max_e = batch.d[i].E > max_e ? batch.d[i].E : max_e;
-    if (max_e <= kSmallThreads * kSmallItemsMin)
-      launch_pdl(small_plans_kernel<kSmallItemsMin>, n, kSmallThreads, smem_min, (cudaStream_t)stream, batch, flags);
-    else
-      launch_pdl(small_plans_kernel<kSmallItemsMax>, n, kSmallThreads, smem_max, (cudaStream_t)stream, batch, flags);
-    int rc = launched("small_plans_kernel");
+    size_t max_smem = 0;
+    auto flush = [&]() -> int {
+      if (n == 0) return CWN_OK;
+      if (pass == 0) {
+        launch_pdl(small_plans_count_kernel, n, kCountThreads, max_smem, (cudaStream_t)stream, batch, flags);
+      } else if (max_e <= kSmallThreads * kSmallItemsMin) {
+        launch_pdl(small_plans_kernel<kSmallItemsMin>, n, kSmallThreads, smem_min, (cudaStream_t)stream, batch, flags);
+      } else {
+        launch_pdl(small_plans_kernel<kSmallItemsMax>, n, kSmallThreads, smem_max, (cudaStream_t)stream, batch, flags);
+      }
+      n = 0;
+      max_e = 0;
+      max_smem = 0;
+      return launched("small_plans_kernel");
+    };
+    for (int i = 0; i < n_plans; ++i) {
+      const cwn_plan_desc& d = descs[i];
+      const bool by_count = count_enabled && count_path_ok(d);
+      if (by_count != (pass == 0)) continue;
+      batch.d[n] = d;
+      batch.bits[n] = key_bits(d.n_rows);
+      max_e = d.E > max_e ? d.E : max_e;
+      const size_t sm = count_smem_bytes(d.E, d.n_rows);
+      max_smem = sm > max_smem ? sm : max_smem;
+      if (++n == kMaxPlansPerLaunch) {
+        int rc = flush();
+        if (rc) return rc;
+      }
+    }
+    int rc = flush();
     if (rc) return rc;
   }
   return CWN_OK;

@@ -50,10 +50,16 @@ def test_csr_plan_is_a_stable_sort(E, n_rows):
 def test_batched_plan_build_matches_single_builds():
     """cwn_csr_plan_build_small (all plans of a batch in one launch) == the CUB path, incl. empty and oversized."""
     g = torch.Generator().manual_seed(0)
-    specs = [(0, 7), (1, 1), (999, 40), (12288, 3200), (12289, 50), (5000, 1), (40_000, 9000), (300, 100_000)] * 3
+    # (counting kernel: short rows; rows of 33+ ids -> its warp path; one heavy row among short ones; radix kernel: long
+    # average rows, tables larger than shared memory; CUB path: more messages than the small capacity)
+    specs = [(0, 7), (1, 1), (999, 40), (12288, 3200), (12289, 50), (5000, 1), (40_000, 9000), (300, 100_000),
+             (6000, 100), (10240, 3200), (4000, 500), (2944, 448), (12000, 17000)] * 3
     reqs = []
-    for E, n_rows in specs:
-        key = torch.randint(0, n_rows, (E,), generator=g).to(DEV)
+    for i, (E, n_rows) in enumerate(specs):
+        key = torch.randint(0, n_rows, (E,), generator=g)
+        if (E, n_rows) == (4000, 500):
+            key[torch.randperm(E, generator=g)[:E // 2]] = 7 + i % 3  # a 2000-id row between rows of ~4
+        key = key.to(DEV)
         pay0 = torch.randint(0, 1 << 20, (E,), generator=g).to(DEV)
         pay1 = torch.randint(0, 1 << 20, (E,), generator=g).to(DEV) if E % 2 else None
         reqs.append((key, n_rows, pay0, pay1))
