@@ -646,7 +646,9 @@ def run_cwn(args, rank, world, local_rank):
     rec = summary[dom]
     achieved = rec['bytes'] / (rec['ms'] * 1e-3) / 1e9
     # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), if any
-    traffic, tpath = None, os.path.join(ROOT, 'profiles', 'r1_ncu_dram_traffic.json')
+    traffic, tpath = None, os.path.join(ROOT, 'profiles', 'r2_ncu_dram_traffic.json')
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, 'profiles', 'r1_ncu_dram_traffic.json')
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(dom, {}).get('dram_bytes_per_launch')
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
