@@ -642,7 +642,13 @@ def run_cwn(args, rank, world, local_rank):
     if rank != 0:
         return
     peak, peak_src = peaks()
-    dom = max((k for k in summary if k != 'csr_plan_build'), key=lambda k: summary[k]['ms'])
+    # (the fused all-reduce + Adam kernel waits for its peers INSIDE the launch: in this eager, padded re-run the ranks
+    # drift apart by milliseconds, so its event time is peer wait, not kernel time — reported under a name that says so
+    # and never taken for the dominant kernel)
+    if 'allreduce_adam_step' in summary:
+        summary['allreduce_adam_step (incl. waiting for the slowest rank of the eager re-run)'] = summary.pop('allreduce_adam_step')
+    dom = max((k for k in summary if k != 'csr_plan_build' and not k.startswith('allreduce_adam_step')),
+              key=lambda k: summary[k]['ms'])
     rec = summary[dom]
     achieved = rec['bytes'] / (rec['ms'] * 1e-3) / 1e9
     # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), if any
