@@ -642,19 +642,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
-// ---- tensor-core helpers (3xTF32): value -> (hi, lo) TF32 parts; one m16n8k8 TF32 MMA with fp32 accumulation
-__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(v - __uint_as_float(hi)));
-}
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
-               "{%0, %1, %2, %3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-
-template <int TR, int A_IN, bool TC>  // TC: products on the tensor cores (3xTF32 split), opt-in (CWN_B200_DENSE_TC=1)
+template <int TR, int A_IN>
 __global__ void __launch_bounds__(DT, CWN_FWD_MIN_CTAS) linear_fwd_fast_kernel(const __grid_constant__ Group<cwn_linear_desc> g) {
   constexpr int R = TR / 16;
   extern __shared__ __align__(16) float smem[];
@@ -727,109 +715,7 @@ __global__ void __launch_bounds__(DT, CWN_FWD_MIN_CTAS) linear_fwd_fast_kernel(c
     }
     __syncthreads();
   }
-  if constexpr (TC) {
-    CWN_PHASE(3);
-    // ---- TC: the 16R x 64 x K product on the tensor cores, 3xTF32 split operands (a = a_hi + a_lo, each TF32):
-    //      a_lo*b_hi + a_hi*b_lo + a_hi*b_hi with fp32 accumulation is as accurate as an fp32 FFMA chain
-    //      (tests/analysis_tf32_error_budget.py) at a quarter of the issue slots. mma.sync.m16n8k8: lane = 4*gq + tq holds
-    //      A[gq | gq+8][tq | tq+4], B[k = tq | tq+4][n = gq], C[gq | gq+8][2tq | 2tq+1]. Warp w owns the 16-row block
-    //      w % R and the R column blocks (8 wide) starting at (w / R) * R. Xs / Ws rows are K + 4 floats apart, i.e.
-    //      4 banks per row: the 8 x 4 fragment loads of a warp hit 32 different banks.
-    const int warp_tc = tid >> 5, lane_tc = tid & 31, gq = lane_tc >> 2, tq = lane_tc & 3;
-    constexpr int NT = R;
-    const int mb = warp_tc % R, nb0 = (warp_tc / R) * NT;
-    float cfr[NT][4];
-  #pragma unroll
-    for (int j = 0; j < NT; ++j) cfr[j][0] = cfr[j][1] = cfr[j][2] = cfr[j][3] = 0.f;
-    {
-      const float* a_lo_row = Xs + (mb * 16 + gq) * ld + tq;
-      const float* a_hi_row = a_lo_row + 8 * ld;
-      const float* b_row0 = Ws + (nb0 * 8 + gq) * ld + tq;
-      for (int k = 0; k < K; k += 8) {
-        const float av[4] = {a_lo_row[k], a_hi_row[k], a_lo_row[k + 4], a_hi_row[k + 4]};
-        uint32_t ah[4], al[4];
-  #pragma unroll
-        for (int i = 0; i < 4; ++i) split_tf32(av[i], ah[i], al[i]);
-  #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-          const float* br = b_row0 + j * 8 * ld + k;
-          uint32_t bh[2], bl[2];
-          split_tf32(br[0], bh[0], bl[0]);
-          split_tf32(br[4], bh[1], bl[1]);
-          mma_tf32(cfr[j], al, bh);
-          mma_tf32(cfr[j], ah, bl);
-          mma_tf32(cfr[j], ah, bh);
-        }
-      }
-    }
-    CWN_PHASE(4);
-    const int r_lo = mb * 16 + gq, r_hi = r_lo + 8;
-  #pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      const int cn = (nb0 + j) * 8 + 2 * tq, c = col0 + cn;  // columns c, c + 1 (h % 4 == 0: both inside or both outside)
-      const float b0 = (d.bias && c < d.h) ? __ldg(d.bias + c) : 0.f;
-      const float b1 = (d.bias && c < d.h) ? __ldg(d.bias + c + 1) : 0.f;
-      cfr[j][0] += b0; cfr[j][1] += b1; cfr[j][2] += b0; cfr[j][3] += b1;
-      if (c < d.h) {
-        if (r_lo < rows) { float* zp = d.z + (row0 + r_lo) * d.ld_z + c; zp[0] = cfr[j][0]; zp[1] = cfr[j][1]; }
-        if (r_hi < rows) { float* zp = d.z + (row0 + r_hi) * d.ld_z + c; zp[0] = cfr[j][2]; zp[1] = cfr[j][3]; }
-      }
-    }
-    CWN_PHASE(5);
-    if (!d.stats) {
-      if (d.bn_mean && !d.bn_training && blockIdx.x == g.start[p])  // eval: statistics are the running ones
-        bn_finalize_body(nullptr, 0, d.n_rows, d.h, d.bn_gamma, d.bn_eps, d.bn_momentum, 0, d.bn_running_mean,
-                         d.bn_running_var, nullptr, d.bn_mean, d.bn_scale, d.bn_rstd, nullptr);
-      return;
-    }
-    {  // per-column (mean, M2) of this tile from the fragments: the two rows of a lane, the 8 lanes sharing tq, then
-       // the R warps that share the column block
-      auto column_partials = [&](float (&sj)[NT][2], bool centred) {
-  #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-          const int cn = (nb0 + j) * 8 + 2 * tq;
-  #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const float mu = centred ? meanv[cn + q] : 0.f;
-            const float lo = cfr[j][q] - mu, hi = cfr[j][2 + q] - mu;
-            float v = 0.f;
-            if (r_lo < rows) v = centred ? lo * lo : lo;
-            if (r_hi < rows) v = centred ? fmaf(hi, hi, v) : v + hi;
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            v += __shfl_xor_sync(0xffffffffu, v, 8);
-            v += __shfl_xor_sync(0xffffffffu, v, 16);
-            sj[j][q] = v;
-          }
-        }
-        if (gq == 0)
-  #pragma unroll
-          for (int j = 0; j < NT; ++j) {
-            red[warp_tc][(nb0 + j) * 8 + 2 * tq] = sj[j][0];
-            red[warp_tc][(nb0 + j) * 8 + 2 * tq + 1] = sj[j][1];
-          }
-      };
-      float sj[NT][2];
-      column_partials(sj, false);
-      __syncthreads();
-      const int owner0 = ((tid >> 3) / NT) * R;  // first of the R warps that own column `tid` (tid < TN)
-      if (tid < TN) {
-        float tot = 0.f;
-  #pragma unroll
-        for (int q = 0; q < R; ++q) tot += red[owner0 + q][tid];
-        meanv[tid] = tot / (float)rows;
-      }
-      __syncthreads();
-      column_partials(sj, true);
-      __syncthreads();
-      if (tid < TN && col0 + tid < d.h) {
-        float m2 = 0.f;
-  #pragma unroll
-        for (int q = 0; q < R; ++q) m2 += red[owner0 + q][tid];
-        d.stats[((int64_t)rt * 2 + 0) * d.h + col0 + tid] = meanv[tid];
-        d.stats[((int64_t)rt * 2 + 1) * d.h + col0 + tid] = m2;
-      }
-    }
-  } else {
+  {
     CWN_PHASE(3);
     float acc[R][4] = {};
     {
@@ -1365,7 +1251,7 @@ __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_kernel(const __
 // one cp.async batch; g_z is formed in place over the g_out tile; its transpose reuses the z tile's shared memory; the
 // bias partial is read off the transposed tile; weight-gradient partials leave as 128-bit stores. Same FMA order as
 // the generic kernel, so the two agree bit for bit.
-template <int TR, int A_IN, int A_OUT, bool TC>  // TC: opt-in tensor-core products, as in linear_fwd_fast_kernel
+template <int TR, int A_IN, int A_OUT>
 __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_fast_kernel(const __grid_constant__ Group<cwn_unit_bwd_desc> g) {
   constexpr int R = TR / 16;
   constexpr int LDR = TR + 4;
@@ -1489,105 +1375,7 @@ __global__ void __launch_bounds__(DT, CWN_BWD_MIN_CTAS) unit_bwd_fast_kernel(con
       bpart[tid] = first ? s_ : bpart[tid] + s_;
     }
     for (int kc = 0; kc < K; kc += TN) {
-      if constexpr (TC) {
-        // ---- TC: both products of the chunk on the tensor cores (3xTF32 split operands, mma.sync m16n8k8; see
-        //      linear_fwd_fast_kernel for the fragment layout). Results are stored straight from the C fragments.
-        const int warp_tc = tid >> 5, lane_tc = tid & 31, gq = lane_tc >> 2, tq = lane_tc & 3;
-        if (d.g_in0 || d.g_in1) {  // input gradient chunk: [TR rows] x [64 k] = Gz [TR x h] * Ws [h x 64]
-          constexpr int NT = R;
-          const int mb = warp_tc % R, nb0 = (warp_tc / R) * NT;
-          float cfr[NT][4];
-  #pragma unroll
-          for (int j = 0; j < NT; ++j) cfr[j][0] = cfr[j][1] = cfr[j][2] = cfr[j][3] = 0.f;
-          const float* a_lo_row = Gz + (mb * 16 + gq) * ldh + tq;
-          const float* a_hi_row = a_lo_row + 8 * ldh;
-          const float* b_col0 = Ws + tq * ldk + kc + nb0 * 8 + gq;
-          for (int c0 = 0; c0 < h; c0 += 8) {
-            const float av[4] = {a_lo_row[c0], a_hi_row[c0], a_lo_row[c0 + 4], a_hi_row[c0 + 4]};
-            uint32_t ah[4], al[4];
-  #pragma unroll
-            for (int i = 0; i < 4; ++i) split_tf32(av[i], ah[i], al[i]);
-  #pragma unroll
-            for (int j = 0; j < NT; ++j) {
-              const float* bp = b_col0 + c0 * ldk + j * 8;
-              uint32_t bh[2], bl[2];
-              split_tf32(bp[0], bh[0], bl[0]);
-              split_tf32(bp[4 * ldk], bh[1], bl[1]);
-              mma_tf32(cfr[j], al, bh);
-              mma_tf32(cfr[j], ah, bl);
-              mma_tf32(cfr[j], ah, bh);
-            }
-          }
-          const int r_lo = mb * 16 + gq, r_hi = r_lo + 8;
-  #pragma unroll
-          for (int j = 0; j < NT; ++j) {
-            const int kq = kc + (nb0 + j) * 8 + 2 * tq;  // columns kq, kq + 1: one block (k0 % 4 == 0), both < K or neither
-            if (kq >= K) continue;
-            float* base = (kq < d.k0) ? (d.g_in0 ? d.g_in0 + row0 * d.ld_gi0 + kq : nullptr)
-                                      : (d.g_in1 ? d.g_in1 + row0 * d.ld_gi1 + (kq - d.k0) : nullptr);
-            const int64_t ldo = (kq < d.k0) ? d.ld_gi0 : d.ld_gi1;
-            if (!base) continue;
-            if (r_lo < rows) {
-              float2* dst = reinterpret_cast<float2*>(base + r_lo * ldo);
-              float2 v = make_float2(cfr[j][0], cfr[j][1]);
-              if (d.accumulate_in) { const float2 o = *dst; v.x += o.x; v.y += o.y; }
-              *dst = v;
-            }
-            if (r_hi < rows) {
-              float2* dst = reinterpret_cast<float2*>(base + r_hi * ldo);
-              float2 v = make_float2(cfr[j][2], cfr[j][3]);
-              if (d.accumulate_in) { const float2 o = *dst; v.x += o.x; v.y += o.y; }
-              *dst = v;
-            }
-          }
-        }
-        if (first && kc == 0) CWN_PHASE(5);
-        for (int mt = 0; mt < m_tiles; ++mt) {  // weight gradient chunk: [64 c] x [64 k] = GzT [64 x TR] * Xs [TR x 64]
-          const int mb = warp_tc & 3, nb0 = (warp_tc >> 2) * 4;
-          float cfr[4][4];
-  #pragma unroll
-          for (int j = 0; j < 4; ++j) cfr[j][0] = cfr[j][1] = cfr[j][2] = cfr[j][3] = 0.f;
-          const float* a_lo_row = ZT + (mt * 64 + mb * 16 + gq) * LDR + tq;
-          const float* a_hi_row = a_lo_row + 8 * LDR;
-          const float* b_col0 = Xs + tq * ldk + kc + nb0 * 8 + gq;
-  #pragma unroll 2
-          for (int r0 = 0; r0 < TR; r0 += 8) {
-            const float av[4] = {a_lo_row[r0], a_hi_row[r0], a_lo_row[r0 + 4], a_hi_row[r0 + 4]};
-            uint32_t ah[4], al[4];
-  #pragma unroll
-            for (int i = 0; i < 4; ++i) split_tf32(av[i], ah[i], al[i]);
-  #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float* bp = b_col0 + r0 * ldk + j * 8;
-              uint32_t bh[2], bl[2];
-              split_tf32(bp[0], bh[0], bl[0]);
-              split_tf32(bp[4 * ldk], bh[1], bl[1]);
-              mma_tf32(cfr[j], al, bh);
-              mma_tf32(cfr[j], ah, bl);
-              mma_tf32(cfr[j], ah, bh);
-            }
-          }
-          const int c_lo = mt * 64 + mb * 16 + gq, c_hi = c_lo + 8;
-  #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int k = kc + (nb0 + j) * 8 + 2 * tq;
-            if (k >= K) continue;
-            if (c_lo < h) {
-              float2* dst = reinterpret_cast<float2*>(wpart + (int64_t)c_lo * K + k);
-              float2 v = make_float2(cfr[j][0], cfr[j][1]);
-              if (!first) { const float2 o = *dst; v.x += o.x; v.y += o.y; }
-              *dst = v;
-            }
-            if (c_hi < h) {
-              float2* dst = reinterpret_cast<float2*>(wpart + (int64_t)c_hi * K + k);
-              float2 v = make_float2(cfr[j][2], cfr[j][3]);
-              if (!first) { const float2 o = *dst; v.x += o.x; v.y += o.y; }
-              *dst = v;
-            }
-          }
-        }
-        if (first && kc == 0) CWN_PHASE(6);
-      } else {
+      {
         if (d.g_in0 || d.g_in1) {  // input gradient chunk: [TR rows] x [64 k] = Gz [TR x h] * Ws [h x 64]
           float acc[R][4] = {};
           tile_mma<R>(Gz, ldh, Ws + kc, ldk, h, ty, tx, acc);
@@ -1815,20 +1603,11 @@ extern "C" int cwn_linear_fwd_grouped(const cwn_linear_desc* descs, int32_t n, c
     const size_t need = ((size_t)(tr + TN) * (K + 4) + 3 * (size_t)K) * sizeof(float);
     if (need > smem_fast) smem_fast = need;
   }
-  // opt-in tensor-core products (3xTF32) for the fast path: every problem's K must be a multiple of the MMA's k = 8
-  static const bool tc_env = [] { const char* v = getenv("CWN_B200_DENSE_TC"); return v && v[0] == '1'; }();
-  bool tc = tc_env;
-  for (int i = 0; i < n && tc; ++i) tc = descs[i].n_rows == 0 || (descs[i].k0 + descs[i].k1) % 8 == 0;
   if (fast && smem_fast <= 200 * 1024) {
 #define CWN_LAUNCH_FAST(TRV, AV)                                                                                   \
   {                                                                                                                \
-    if (tc) {                                                                                                      \
-      if ((rc = ensure_smem(linear_fwd_fast_kernel<TRV, AV, true>, smem_fast, "cudaFuncSetAttribute(linear_fwd_fast_kernel)"))) return rc; \
-      linear_fwd_fast_kernel<TRV, AV, true><<<total, DT, smem_fast, (cudaStream_t)stream>>>(g);                    \
-    } else {                                                                                                       \
-      if ((rc = ensure_smem(linear_fwd_fast_kernel<TRV, AV, false>, smem_fast, "cudaFuncSetAttribute(linear_fwd_fast_kernel)"))) return rc; \
-      linear_fwd_fast_kernel<TRV, AV, false><<<total, DT, smem_fast, (cudaStream_t)stream>>>(g);                   \
-    }                                                                                                              \
+    if ((rc = ensure_smem(linear_fwd_fast_kernel<TRV, AV>, smem_fast, "cudaFuncSetAttribute(linear_fwd_fast_kernel)"))) return rc; \
+    linear_fwd_fast_kernel<TRV, AV><<<total, DT, smem_fast, (cudaStream_t)stream>>>(g);                            \
   }
 #define CWN_FAST_BY_ACT(TRV)                                     \
   if (a_in == CWN_ACT_ID) CWN_LAUNCH_FAST(TRV, CWN_ACT_ID)       \
@@ -2065,21 +1844,11 @@ extern "C" int cwn_unit_bwd_grouped(const cwn_unit_bwd_desc* descs, int32_t n, c
                          6 * (size_t)d.h + 64) * sizeof(float);
     if (need > smem_fast) smem_fast = need;
   }
-  // opt-in tensor-core products (3xTF32): the inner dimension of the input-gradient product is h, a multiple of the
-  // MMA's k = 8 is required (the other product's inner dimension is the tile height, 32 or 64)
-  static const bool tc_env = [] { const char* v = getenv("CWN_B200_DENSE_TC"); return v && v[0] == '1'; }();
-  bool tc = tc_env;
-  for (int i = 0; i < n && tc; ++i) tc = g.d[i].n_rows == 0 || g.d[i].h % 8 == 0;
   if (fast && smem_fast <= 210 * 1024) {
 #define CWN_LAUNCH_BWDF(TRV, AI, AO)                                                                              \
   {                                                                                                               \
-    if (tc) {                                                                                                     \
-      if ((rc = ensure_smem(unit_bwd_fast_kernel<TRV, AI, AO, true>, smem_fast, "cudaFuncSetAttribute(unit_bwd_fast_kernel)"))) return rc; \
-      unit_bwd_fast_kernel<TRV, AI, AO, true><<<total, DT, smem_fast, (cudaStream_t)stream>>>(g);                 \
-    } else {                                                                                                      \
-      if ((rc = ensure_smem(unit_bwd_fast_kernel<TRV, AI, AO, false>, smem_fast, "cudaFuncSetAttribute(unit_bwd_fast_kernel)"))) return rc; \
-      unit_bwd_fast_kernel<TRV, AI, AO, false><<<total, DT, smem_fast, (cudaStream_t)stream>>>(g);                \
-    }                                                                                                             \
+    if ((rc = ensure_smem(unit_bwd_fast_kernel<TRV, AI, AO>, smem_fast, "cudaFuncSetAttribute(unit_bwd_fast_kernel)"))) return rc; \
+    unit_bwd_fast_kernel<TRV, AI, AO><<<total, DT, smem_fast, (cudaStream_t)stream>>>(g);                         \
   }
 #define CWN_BWDF_BY_OUT(TRV, AI)                                     \
   if (a_out == CWN_ACT_ID) CWN_LAUNCH_BWDF(TRV, AI, CWN_ACT_ID)      \

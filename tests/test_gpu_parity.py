@@ -1246,20 +1246,3 @@ def test_every_large_row_kernel_family_is_bit_exact(mode, F, monkeypatch):
     monkeypatch.setenv('CWN_B200_LARGE_COB', mode)
     test_tile_staged_kernels_are_bit_exact_and_survive_heavy_rows(F)
 
-
-@pytest.mark.skipif(not __import__('os').environ.get('CWN_B200_TEST_TC'),
-                    reason='opt-in: the tensor-core (3xTF32) path of linear_fwd_fast_kernel is compiled and its fragment '
-                           'arithmetic is pinned on the CPU (tests/test_tc_fragment_mapping.py), but it has not run on '
-                           'hardware yet; set CWN_B200_TEST_TC=1 to exercise it')
-def test_dense_tensor_core_path_in_a_subprocess():
-    """`CWN_B200_DENSE_TC=1` is read once per process, so the dense-layer and training-step parity tests are re-run in
-    a child process with the switch on."""
-    import os
-    import subprocess
-    import sys
-    env = dict(os.environ, CWN_B200_DENSE_TC='1')
-    env.pop('CWN_B200_TEST_TC', None)
-    proc = subprocess.run([sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-q', '-x', '-m', 'gpu', '-k',
-                           'fused_dense_layer or dense_fast_path or train_step or zinc_shaped or captured_cuda_graph'],
-                          env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    assert proc.returncode == 0, proc.stdout[-4000:] + proc.stderr[-2000:]
