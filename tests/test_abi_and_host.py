@@ -151,3 +151,57 @@ def test_bench_clock_sampler_sources_and_windows():
     s2.wait_first(0.05)
     out = s2.stop()
     assert out['sm_mhz'] is None or isinstance(out['sm_mhz'], int)
+
+
+def test_ws_stage_geometry_queries_are_host_functions():
+    """The host-side sizing of the warp-specialised CSR kernels (what `ops._ws_config` decides with): lanes per row,
+    consumer threads and the pipeline depth a (F, tile height, window, message) configuration gets in 220 KB of shared
+    memory — pure host arithmetic, no GPU."""
+    lib = _lib.load()
+    assert lib.cwn_csr_ws_consumer_threads() % 32 == 0 and lib.cwn_csr_ws_consumer_threads() >= 256
+    for F, lpr_min in ((4, 2), (16, 2), (20, 4), (64, 8), (128, 16)):
+        lpr = lib.cwn_csr_ws_lanes_per_row(F)
+        assert lpr >= lpr_min and lpr & (lpr - 1) == 0 and lpr * 8 >= F // 4  # (one or two 128-bit vectors per lane)
+    assert lib.cwn_csr_ws_lanes_per_row(6) == 0  # F % 4 != 0: no 128-bit path
+    # edge-upper pass at F = 64: 128-row tiles, windows of ~180 rows, ~450 messages -> at least 4 stages
+    assert lib.cwn_csr_ws_stages(64, 128, 180, 0, 448, 1, 0) >= 4
+    deep = lib.cwn_csr_ws_stages(16, 256, 310, 0, 900, 1, 0)
+    assert deep >= lib.cwn_csr_ws_stages(16, 256, 310, 40, 900, 2, 1) >= 2  # a second window and the row operand cost stages
+    assert lib.cwn_csr_ws_stages(64, 128, 1_000_000, 0, 448, 1, 0) == 0     # a window that spans the matrix does not fit
+    assert lib.cwn_csr_ws_stages(256, 128, 180, 0, 448, 1, 0) == 0          # F > 128: not served
+    assert lib.cwn_csr_ws_stages(64, 130, 180, 0, 448, 1, 0) == 0           # tile height must be a multiple of 4
+    # argument errors of the launch entry points are reported without touching the device
+    assert lib.cwn_csr_gather_reduce_ws_f32(None, 64, None, None, 10, None, 128, 180, 448, 40000, 64, None, 64, None,
+                                            None, 64, 0, None) == -1
+    assert lib.cwn_csr_tile_windows(None, None, None, 40000, 128, None, None) == -1
+
+
+def test_fused_reduction_query_follows_the_tensor_core_eligibility():
+    """`cwn_unit_bwd_fuses_reduce` (host): 1 exactly when a group would run on the tcgen05 backward kernel — the only one
+    that can take the upstream units' BatchNorm-backward sums from its g_in tiles."""
+    lib = _lib.load()
+    buf = torch.zeros(64 * 256, dtype=torch.float32)  # a 16-byte aligned host address to stand in for device pointers
+    ptr = (buf.data_ptr() + 15) & ~15
+
+    def desc(h, k0, k1=0, tile_rows=64, ptr_off=0):
+        d = _lib.UnitBwdDesc()
+        d.x0, d.ld_x0, d.k0 = ptr, k0, k0
+        if k1:
+            d.x1, d.ld_x1, d.k1 = ptr, k1, k1
+        d.w, d.ld_w = ptr, k0 + k1
+        d.z, d.ld_z, d.g_out, d.ld_g = ptr, h, ptr + ptr_off, h
+        d.w_partials, d.b_partials = ptr, ptr
+        d.n_rows, d.h, d.tile_rows, d.n_ctas = 640, h, tile_rows, 10
+        return d
+
+    def ask(*ds):
+        arr = (_lib.UnitBwdDesc * len(ds))(*ds)
+        return lib.cwn_unit_bwd_fuses_reduce(arr, len(ds))
+
+    tc5 = os.environ.get('CWN_B200_DENSE_TC5', '1') != '0'
+    assert ask(desc(64, 64), desc(64, 64, 64)) == int(tc5)
+    assert ask(desc(64, 64), desc(64, 48)) == 0            # K = 48 is not a tensor-core shape: the whole group falls back
+    assert ask(desc(32, 64)) == 0                          # h = 32
+    assert ask(desc(64, 64, tile_rows=32)) == 0            # 32-row tiles
+    assert ask(desc(64, 64, ptr_off=4)) == 0               # misaligned gradient
+    assert lib.cwn_unit_bwd_fuses_reduce(None, 0) == 0
