@@ -151,6 +151,7 @@ class Plan(object):
 WS_MIN_ROWS = 32768
 _ws_enabled = os.environ.get('CWN_B200_WS', '1') != '0'
 _WS_MIN_STAGES = int(os.environ.get('CWN_B200_WS_MIN_STAGES', '4'))
+_WS_FORCED_TILE = int(os.environ.get('CWN_B200_WS_TILE', '0'))  # A/B switch: one tile height instead of the search
 
 
 def _ws_ok(*mats):
@@ -161,7 +162,7 @@ def _ws_config(plan: Plan, F: int, narr: int, rowop: bool):
     """(windows, tile_rows, cap_rows0, cap_rows1, cap_msgs) when the plan is large enough for the warp-specialised
     kernels and the operand windows of its tiles fit their shared-memory stages, else None. The tile windows are
     computed once per plan and tile height (cwn_csr_tile_windows) and their maxima read back (one synchronisation
-    per plan, never during stream capture)."""
+    per plan, never during stream capture: a plan first seen inside a capture keeps the register-level kernels)."""
     if (not _ws_enabled or plan.n_rows < WS_MIN_ROWS or plan.E == 0 or F % 4 or F > 128 or plan.pay0 is None
             or (narr == 2 and plan.pay1 is None)):
         return None
@@ -170,7 +171,7 @@ def _ws_config(plan: Plan, F: int, narr: int, rowop: bool):
     lib = _lib.load()
     # the tallest tile whose stage still leaves a 4-deep pipeline: taller tiles re-read less of the neighbouring
     # tiles' windows (a window is the tile's rows plus a margin of about one complex on either side)
-    forced = int(os.environ.get('CWN_B200_WS_TILE', '0'))
+    forced = _WS_FORCED_TILE
     # ... and no shorter than the number of lane groups that share its rows (a plan with few, heavy rows — the
     # by-coboundary plan: ~26 messages per ring — would leave most consumer groups idle: it keeps the row kernels)
     groups = lib.cwn_csr_ws_consumer_threads() // lib.cwn_csr_ws_lanes_per_row(F)
