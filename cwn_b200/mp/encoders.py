@@ -29,15 +29,18 @@ class _ColumnEmbeddingSum(torch.nn.Module):
             # ONE row gather over the concatenated tables instead of a lookup + add per feature column, and ONE
             # segmented reduction (CSR plan of the flat ids, cwn_b200.ops) instead of a sort-based embedding backward per
             # column: 9 + 3 columns were ~30 launches forward and ~100 backward per step of the ogbg-mol* models
-            from cwn_b200 import ops
-            offs = self._offsets(x.device)
-            flat = (x + offs).reshape(-1)
-            rows = ops.gather_rows(torch.cat([t.weight for t in tables]), flat)
-            return rows.view(x.size(0), len(tables), -1).sum(dim=1)
+            return self._lookup_concat(x)
         out = 0
         for i in range(x.shape[1]):
             out = out + tables[i](x[:, i])
         return out
+
+    def _lookup_concat(self, x):
+        from cwn_b200 import ops
+        tables = getattr(self, self._list_name)
+        flat = (x + self._offsets(x.device)).reshape(-1)
+        rows = ops.gather_rows(torch.cat([t.weight for t in tables]), flat)
+        return rows.view(x.size(0), len(tables), -1).sum(dim=1)
 
     fuse_lookup = os.environ.get('CWN_B200_FUSE_OGB_LOOKUP', '1') != '0'  # A/B switch
 

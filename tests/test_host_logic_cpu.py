@@ -157,3 +157,29 @@ def test_padded_batches_share_one_layout():
     assert len(sigs) == 1
     with pytest.raises(Overflow):
         pad_complexes(pool[:65], cap)
+
+
+def test_ogb_encoders_one_gather_over_the_concatenated_tables(monkeypatch):
+    """The fused form of ogb's Atom/BondEncoder (`mp/encoders.py::_lookup_concat`: one row gather over the concatenated
+    embedding tables, summed over the feature columns) equals the per-column lookups the reference performs
+    (ogb mol_encoder.py via `mp/molec_models.py:7`), values and every table's gradient; the gather goes through the
+    CPU stand-in of `ops.gather_rows` here (the CUDA guard is what `forward` checks on the GPU)."""
+    import cpu_ops_shim
+    from cwn_b200 import ops
+    from cwn_b200.mp.encoders import ATOM_FEATURE_DIMS, BOND_FEATURE_DIMS, AtomEncoder, BondEncoder
+    monkeypatch.setattr(ops, 'gather_rows', cpu_ops_shim.gather_rows)
+    g = torch.Generator().manual_seed(0)
+    for cls, dims in ((AtomEncoder, ATOM_FEATURE_DIMS), (BondEncoder, BOND_FEATURE_DIMS)):
+        torch.manual_seed(1)
+        enc = cls(12)
+        x = torch.stack([torch.randint(0, v, (70,), generator=g) for v in dims], 1)
+        w = torch.randn(70, 12, generator=g)
+        ref = enc(x)  # CPU tensors: the per-column path
+        (ref * w).sum().backward()
+        ref_grads = [t.weight.grad.clone() for t in getattr(enc, enc._list_name)]
+        enc.zero_grad()
+        out = enc._lookup_concat(x)
+        (out * w).sum().backward()
+        assert torch.allclose(out, ref, rtol=1e-6, atol=1e-6)
+        for t, rg in zip(getattr(enc, enc._list_name), ref_grads):
+            assert torch.allclose(t.weight.grad, rg, rtol=1e-6, atol=1e-6)
